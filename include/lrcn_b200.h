@@ -1,0 +1,163 @@
+/* lrcn_b200.h -- C ABI of liblrcn_b200.so: the B200-native LRCN caption-decoder hot path.
+ *
+ * Drop-in boundary for ekinakyurek/Long-Term-Recurrent-Convolutional-NN (`lrcn.jl`).  The
+ * reference has no FFI layer; its seam is a set of Julia call sites.  Each
+ * entry point below names the reference call site (file:line) it replaces.  The Julia host
+ * keeps its CLI flags, weight vector (9 column-major Float32 matrices), tokenizer and eval
+ * code and reaches this library through `ccall` (julia/lrcn_b200.jl).
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on failure; lrcn_last_error() returns a
+ *    thread-local message.  No C++ exception crosses the ABI.  There is NO CPU fallback:
+ *    without a CUDA device lrcn_create fails with LRCN_ERR_CUDA.
+ *  - Int <-> int64_t, Float32 <-> float, Float64 <-> double; matrices are raw pointers to
+ *    COLUMN-MAJOR storage exactly as Julia holds them; token / image ids are 1-based on the
+ *    wire (eos=1,bos=2,unk=3: lrcn.jl:248-255).
+ *  - the library owns all device memory, streams, CUDA graphs and NCCL communicators; the
+ *    caller owns every host buffer and may free it as soon as the call returns (all calls
+ *    are synchronous on return unless the name ends in _async).
+ *  - one host thread per handle; one handle per GPU (one process per GPU under
+ *    torch.distributed / MPI; lrcn_comm_init joins the handles into a data-parallel group).
+ */
+#ifndef LRCN_B200_H
+#define LRCN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define LRCN_API __attribute__((visibility("default")))
+#else
+#define LRCN_API
+#endif
+
+#define LRCN_ABI_VERSION 1
+#define LRCN_F_CNN 4096 /* lrcn.jl:28  const cnnout = 4096 */
+#define LRCN_NUM_PARAMS 9
+
+enum {
+  LRCN_OK = 0,
+  LRCN_ERR_ARG = 1,     /* bad argument / shape mismatch (the reference would throw) */
+  LRCN_ERR_CUDA = 2,    /* CUDA runtime/driver error, incl. "no device"; sticky on the handle */
+  LRCN_ERR_NCCL = 3,
+  LRCN_ERR_MISSING = 4, /* unknown image id: lrcn.jl:602-605 error("misssing features!!!!!!") */
+  LRCN_ERR_STATE = 5
+};
+
+enum {
+  LRCN_PREC_FP32 = 0,  /* fp32 CUDA-core GEMMs (exact-mode; bit-stable reductions) */
+  LRCN_PREC_BF16X3 = 1 /* tcgen05 tensor cores, error-compensated bf16 hi/lo split, fp32 TMEM accumulate */
+};
+
+typedef struct lrcn_handle lrcn_handle;
+
+/* Hot-path configuration.  Defaults mirror the reference: lrcn.jl:39-40 (--hidden 1000 1000,
+ * --embed 1000), lrcn.jl:402 Adam() (lr 1e-3, b1 .9, b2 .999, eps 1e-8; --lr/--gclip are ignored
+ * by the reference, lrcn.jl:330,386-393), lrcn.jl:353 (captions longer than 28 are skipped). */
+typedef struct {
+  int32_t embed;        /* E  */
+  int32_t hidden1;      /* H1 */
+  int32_t hidden2;      /* H2 (even; C = H2/2) */
+  int32_t vocab;        /* V  */
+  int32_t max_batch;    /* largest B per train/eval step on this GPU */
+  int32_t max_len;      /* largest caption length l (decoder steps T = l+1) */
+  int32_t max_gen_rows; /* largest images_in_flight * beam_width for generation */
+  int32_t device;       /* CUDA device ordinal */
+  int32_t precision;    /* LRCN_PREC_* */
+  int32_t use_graphs;   /* 1: replay each (B,l) step shape as a CUDA graph */
+  float lr, beta1, beta2, eps;
+} lrcn_config;
+
+LRCN_API int lrcn_abi_version(void);
+LRCN_API const char* lrcn_last_error(void);
+LRCN_API int lrcn_config_default(lrcn_config* cfg);
+
+/* lifecycle.  Replaces nothing in the reference (Knet allocates implicitly). */
+LRCN_API int lrcn_create(const lrcn_config* cfg, lrcn_handle** out);
+LRCN_API int lrcn_destroy(lrcn_handle* h);
+
+/* ---- weights: the frozen 9-matrix contract, idx = 1..9 in `model` order --------------------
+ * replaces initweights() hand-off lrcn.jl:87, JLD load lrcn.jl:90, save lrcn.jl:185,230.
+ *   1 W1 (E+H1)x4H1   2 b1 1x4H1   3 W2 2H2x4H2   4 b2 1x4H2   5 Wf H1xC   6 Wcnn 4096xC
+ *   7 Wemb VxE        8 Wout H2xV  9 bout 1xV            (lrcn.jl:489-510)
+ * get(set(x)) round-trips bit-exactly when no step intervened. */
+LRCN_API int lrcn_param_shape(const lrcn_handle* h, int idx, int64_t* rows, int64_t* cols);
+LRCN_API int lrcn_set_param(lrcn_handle* h, int idx, const float* colmajor, int64_t rows, int64_t cols);
+LRCN_API int lrcn_get_param(lrcn_handle* h, int idx, float* colmajor, int64_t rows, int64_t cols);
+/* gradient of the last lrcn_grad / lrcn_train_step, same shapes (what lossgradient returns, lrcn.jl:583) */
+LRCN_API int lrcn_get_grad(lrcn_handle* h, int idx, float* colmajor, int64_t rows, int64_t cols);
+/* Adam state extension (the reference never saves it): which = 0 -> m, 1 -> v */
+LRCN_API int lrcn_get_adam_state(lrcn_handle* h, int idx, int which, float* colmajor, int64_t rows, int64_t cols);
+LRCN_API int lrcn_set_adam_state(lrcn_handle* h, int idx, int which, const float* colmajor, int64_t rows, int64_t cols);
+LRCN_API int lrcn_get_adam_step(lrcn_handle* h, int64_t* t);
+LRCN_API int lrcn_set_adam_step(lrcn_handle* h, int64_t t);
+
+/* ---- features: replaces the `feats` / `featsvl` Dict{Int,Array{Float32}} globals (lrcn.jl:121-123)
+ * and the per-row staging loop lrcn.jl:369-376.  split 0 = train, 1 = val/test.  feats holds n rows
+ * of 4096 contiguous floats.  The table stays resident in HBM; ids are mapped host-side. */
+LRCN_API int lrcn_load_features(lrcn_handle* h, int split, const int64_t* ids, const float* feats, int64_t n);
+
+/* ---- training (tokens: l x B int64, time-major: tokens[t*B+i], 1-based; image_ids: B) --------
+ * lrcn_loss       = loss() forward only, lrcn.jl:553-581 / average_loss body lrcn.jl:452-474:
+ *                   returns sum of target log-probs and the token count B*(l+1).
+ * lrcn_grad       = lossgradient(...) lrcn.jl:378,583 (no update); loss_out = -total/count.
+ * lrcn_adam_update= update!(param,gloss,optim) lrcn.jl:394 on the gradients currently held.
+ * lrcn_train_step = lrcn.jl:378 + :394 fused (gradient, [allreduce], Adam).
+ * pdrop: dropout probability at the two sites lrcn.jl:542,547 (0 => identity; parity is defined
+ * at 0 since Knet's RNG is not reproducible); seed feeds the in-kernel counter RNG. */
+LRCN_API int lrcn_loss(lrcn_handle* h, int split, const int64_t* image_ids, const int64_t* tokens, int l, int B,
+              double* sum_logp_out, int64_t* count_out);
+LRCN_API int lrcn_grad(lrcn_handle* h, int split, const int64_t* image_ids, const int64_t* tokens, int l, int B,
+              float pdrop, uint64_t seed, double* loss_out);
+LRCN_API int lrcn_adam_update(lrcn_handle* h);
+LRCN_API int lrcn_train_step(lrcn_handle* h, int split, const int64_t* image_ids, const int64_t* tokens, int l, int B,
+                    float pdrop, uint64_t seed, double* loss_out);
+/* per-token target log-probs of the last lrcn_loss/lrcn_grad call, (l+1) x B time-major */
+LRCN_API int lrcn_get_token_logps(lrcn_handle* h, float* out, int64_t n);
+
+/* device-resident variant for kernel-only timing: stage a batch once (H2D), then step on it
+ * repeatedly with no host<->device traffic.  slot in [0, 64). */
+LRCN_API int lrcn_stage_batch(lrcn_handle* h, int slot, int split, const int64_t* image_ids, const int64_t* tokens,
+                     int l, int B);
+LRCN_API int lrcn_train_step_staged(lrcn_handle* h, int slot, float pdrop, uint64_t seed, double* loss_out /* may be NULL: no D2H */);
+
+/* ---- generation: generate()+beam_search() numeric part, lrcn.jl:585-632,644-678, for n images at
+ * once (the reference loops images serially, lrcn.jl:152-155).  tokens_out: n x (nword+2) int64
+ * incl. the leading bos; len_out[n] tokens used; prob_out[n] fp32 path probability of the best
+ * hypothesis; logp_out (optional, n x (nword+1)) log-prob of each generated token.  The caller
+ * prints tokens[2:] up to the first eos (lrcn.jl:633-640). */
+LRCN_API int lrcn_beam_search(lrcn_handle* h, int split, const int64_t* image_ids, int64_t n, int beam_width, int nword,
+                     int64_t* tokens_out, int32_t* len_out, float* prob_out, float* logp_out);
+
+/* ---- data-parallel group (new; the reference is single-GPU).  One handle per rank.  The id is
+ * produced on rank 0 and distributed by the host's own mechanism (torch.distributed, MPI, file). */
+#define LRCN_COMM_ID_BYTES 128
+LRCN_API int lrcn_comm_unique_id(char id[LRCN_COMM_ID_BYTES]);
+LRCN_API int lrcn_comm_init(lrcn_handle* h, const char id[LRCN_COMM_ID_BYTES], int rank, int nranks);
+
+/* ---- measurement helpers: CUDA events on the library's own compute stream */
+LRCN_API int lrcn_sync(lrcn_handle* h);
+LRCN_API int lrcn_timer_start(lrcn_handle* h);
+LRCN_API int lrcn_timer_stop(lrcn_handle* h, float* ms_out);
+LRCN_API int lrcn_kernel_launches(lrcn_handle* h, int64_t* n_out); /* kernels launched (incl. inside graph replays) */
+LRCN_API int lrcn_flush_l2(lrcn_handle* h);                        /* writes a 256 MiB scratch buffer */
+/* time `reps` launches of one named kernel family on the current buffers: "adam", "vocab_gemm", "gather" ... */
+LRCN_API int lrcn_time_kernel(lrcn_handle* h, const char* name, int reps, float* avg_ms_out, double* algo_bytes_out,
+                     double* algo_flops_out);
+
+/* ---- kernel-level test hooks (parity tests call single kernels through the ABI) ---------------
+ * C[M][N] (row-major, ldc=N) = op(A) * op(B) (+ C if beta) (+ bias[n]); a_kmajor: A is [M][K] else [K][M];
+ * b_kmajor: B is [N][K] else [K][N].  precision selects the fp32 or the tcgen05 bf16x3 kernel. */
+LRCN_API int lrcn_test_gemm(lrcn_handle* h, int precision, int a_kmajor, int b_kmajor, int M, int N, int K,
+                   const float* A, const float* B, const float* bias, int beta, float* C);
+/* beam selection on caller-supplied probabilities: probs [rows][V], parent_prob [rows]; outputs per image */
+LRCN_API int lrcn_test_beam_select(lrcn_handle* h, const float* probs, const float* parent_prob, int n_images, int K,
+                          int V, int first_step, int64_t* tok_out, int32_t* parent_out, float* score_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LRCN_B200_H */

@@ -1,0 +1,310 @@
+"""ctypes binding of liblrcn_b200.so -- the executable mirror of the Julia `ccall` shim
+(julia/lrcn_b200.jl).  Every symbol declared in include/lrcn_b200.h is bound here with the same
+argument order.  There is no fallback: if the library is missing, loading raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblrcn_b200.so")
+
+PREC_FP32, PREC_BF16X3 = 0, 1
+OK, ERR_ARG, ERR_CUDA, ERR_NCCL, ERR_MISSING, ERR_STATE = 0, 1, 2, 3, 4, 5
+COMM_ID_BYTES = 128
+
+
+class LrcnError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"liblrcn_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("embed", "hidden1", "hidden2", "vocab", "max_batch", "max_len",
+                                         "max_gen_rows", "device", "precision", "use_graphs")] + \
+               [(n, C.c_float) for n in ("lr", "beta1", "beta2", "eps")]
+
+
+_p = C.POINTER
+_f32p, _i64p, _i32p, _f64p = _p(C.c_float), _p(C.c_int64), _p(C.c_int32), _p(C.c_double)
+_H = C.c_void_p
+
+# name -> (restype, argtypes); mirrors include/lrcn_b200.h one to one
+SIGNATURES = {
+    "lrcn_abi_version": (C.c_int, []),
+    "lrcn_last_error": (C.c_char_p, []),
+    "lrcn_config_default": (C.c_int, [_p(Config)]),
+    "lrcn_create": (C.c_int, [_p(Config), _p(_H)]),
+    "lrcn_destroy": (C.c_int, [_H]),
+    "lrcn_param_shape": (C.c_int, [_H, C.c_int, _i64p, _i64p]),
+    "lrcn_set_param": (C.c_int, [_H, C.c_int, _f32p, C.c_int64, C.c_int64]),
+    "lrcn_get_param": (C.c_int, [_H, C.c_int, _f32p, C.c_int64, C.c_int64]),
+    "lrcn_get_grad": (C.c_int, [_H, C.c_int, _f32p, C.c_int64, C.c_int64]),
+    "lrcn_get_adam_state": (C.c_int, [_H, C.c_int, C.c_int, _f32p, C.c_int64, C.c_int64]),
+    "lrcn_set_adam_state": (C.c_int, [_H, C.c_int, C.c_int, _f32p, C.c_int64, C.c_int64]),
+    "lrcn_get_adam_step": (C.c_int, [_H, _i64p]),
+    "lrcn_set_adam_step": (C.c_int, [_H, C.c_int64]),
+    "lrcn_load_features": (C.c_int, [_H, C.c_int, _i64p, _f32p, C.c_int64]),
+    "lrcn_loss": (C.c_int, [_H, C.c_int, _i64p, _i64p, C.c_int, C.c_int, _f64p, _i64p]),
+    "lrcn_grad": (C.c_int, [_H, C.c_int, _i64p, _i64p, C.c_int, C.c_int, C.c_float, C.c_uint64, _f64p]),
+    "lrcn_adam_update": (C.c_int, [_H]),
+    "lrcn_train_step": (C.c_int, [_H, C.c_int, _i64p, _i64p, C.c_int, C.c_int, C.c_float, C.c_uint64, _f64p]),
+    "lrcn_get_token_logps": (C.c_int, [_H, _f32p, C.c_int64]),
+    "lrcn_stage_batch": (C.c_int, [_H, C.c_int, C.c_int, _i64p, _i64p, C.c_int, C.c_int]),
+    "lrcn_train_step_staged": (C.c_int, [_H, C.c_int, C.c_float, C.c_uint64, _f64p]),
+    "lrcn_beam_search": (C.c_int, [_H, C.c_int, _i64p, C.c_int64, C.c_int, C.c_int, _i64p, _i32p, _f32p, _f32p]),
+    "lrcn_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "lrcn_comm_init": (C.c_int, [_H, C.c_char_p, C.c_int, C.c_int]),
+    "lrcn_sync": (C.c_int, [_H]),
+    "lrcn_timer_start": (C.c_int, [_H]),
+    "lrcn_timer_stop": (C.c_int, [_H, _f32p]),
+    "lrcn_kernel_launches": (C.c_int, [_H, _i64p]),
+    "lrcn_flush_l2": (C.c_int, [_H]),
+    "lrcn_time_kernel": (C.c_int, [_H, C.c_char_p, C.c_int, _f32p, _f64p, _f64p]),
+    "lrcn_test_gemm": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, C.c_int, _f32p]),
+    "lrcn_test_beam_select": (C.c_int, [_H, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _i64p, _i32p, _f32p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load liblrcn_b200.so (built in-tree by __graft_entry__.build()).  Raises if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(f"{LIB_PATH} is not built; run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                                    "The LRCN hot path has no CPU or PyTorch fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != OK:
+        raise LrcnError(rc, load().lrcn_last_error().decode("utf-8", "replace"))
+
+
+def _f32(a):
+    return a.ctypes.data_as(_f32p)
+
+
+def _i64(a):
+    return a.ctypes.data_as(_i64p)
+
+
+def default_config(**kw) -> Config:
+    cfg = Config()
+    check(load().lrcn_config_default(C.byref(cfg)))
+    for k, v in kw.items():
+        if not hasattr(cfg, k):
+            raise AttributeError(k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+class Handle:
+    """Owns one lrcn_handle (one GPU)."""
+
+    def __init__(self, cfg: Config):
+        self.lib = load()
+        self.cfg = cfg
+        self._h = _H()
+        check(self.lib.lrcn_create(C.byref(cfg), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            self.lib.lrcn_destroy(self._h)
+            self._h = _H()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- weights
+    def param_shape(self, idx):
+        r, c = C.c_int64(), C.c_int64()
+        check(self.lib.lrcn_param_shape(self._h, idx, C.byref(r), C.byref(c)))
+        return int(r.value), int(c.value)
+
+    def set_param(self, idx, w):
+        w = np.asfortranarray(w, dtype=np.float32)
+        check(self.lib.lrcn_set_param(self._h, idx, _f32(w), w.shape[0], w.shape[1]))
+
+    def _get(self, fn, idx, *pre):
+        r, c = self.param_shape(idx)
+        out = np.empty((r, c), dtype=np.float32, order="F")
+        check(fn(self._h, idx, *pre, _f32(out), r, c))
+        return out
+
+    def get_param(self, idx):
+        return self._get(self.lib.lrcn_get_param, idx)
+
+    def get_grad(self, idx):
+        return self._get(self.lib.lrcn_get_grad, idx)
+
+    def get_adam_state(self, idx, which):
+        return self._get(self.lib.lrcn_get_adam_state, idx, which)
+
+    def set_adam_state(self, idx, which, a):
+        a = np.asfortranarray(a, dtype=np.float32)
+        check(self.lib.lrcn_set_adam_state(self._h, idx, which, _f32(a), a.shape[0], a.shape[1]))
+
+    def get_adam_step(self):
+        t = C.c_int64()
+        check(self.lib.lrcn_get_adam_step(self._h, C.byref(t)))
+        return int(t.value)
+
+    def set_adam_step(self, t):
+        check(self.lib.lrcn_set_adam_step(self._h, int(t)))
+
+    def set_model(self, model):
+        for k, w in enumerate(model):
+            self.set_param(k + 1, w)
+
+    def get_model(self):
+        return [self.get_param(k) for k in range(1, 10)]
+
+    # ---- features
+    def load_features(self, split, ids, feats):
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        feats = np.ascontiguousarray(feats, dtype=np.float32)
+        assert feats.shape == (len(ids), 4096)
+        check(self.lib.lrcn_load_features(self._h, split, _i64(ids), _f32(feats), len(ids)))
+
+    # ---- steps
+    @staticmethod
+    def _batch(image_ids, tokens):
+        image_ids = np.ascontiguousarray(image_ids, dtype=np.int64)
+        tokens = np.ascontiguousarray(tokens, dtype=np.int64)
+        if tokens.ndim == 1:
+            tokens = tokens.reshape(0, len(image_ids)) if tokens.size == 0 else tokens.reshape(-1, len(image_ids))
+        l, B = tokens.shape
+        assert B == len(image_ids)
+        return image_ids, tokens, l, B
+
+    def loss(self, split, image_ids, tokens):
+        ids, tok, l, B = self._batch(image_ids, tokens)
+        s, n = C.c_double(), C.c_int64()
+        check(self.lib.lrcn_loss(self._h, split, _i64(ids), _i64(tok), l, B, C.byref(s), C.byref(n)))
+        return float(s.value), int(n.value)
+
+    def grad(self, split, image_ids, tokens, pdrop=0.0, seed=0):
+        ids, tok, l, B = self._batch(image_ids, tokens)
+        out = C.c_double()
+        check(self.lib.lrcn_grad(self._h, split, _i64(ids), _i64(tok), l, B, pdrop, seed, C.byref(out)))
+        return float(out.value)
+
+    def train_step(self, split, image_ids, tokens, pdrop=0.0, seed=0):
+        ids, tok, l, B = self._batch(image_ids, tokens)
+        out = C.c_double()
+        check(self.lib.lrcn_train_step(self._h, split, _i64(ids), _i64(tok), l, B, pdrop, seed, C.byref(out)))
+        return float(out.value)
+
+    def adam_update(self):
+        check(self.lib.lrcn_adam_update(self._h))
+
+    def token_logps(self, l, B):
+        out = np.empty((l + 1, B), dtype=np.float32)
+        check(self.lib.lrcn_get_token_logps(self._h, _f32(out), out.size))
+        return out
+
+    def stage_batch(self, slot, split, image_ids, tokens):
+        ids, tok, l, B = self._batch(image_ids, tokens)
+        check(self.lib.lrcn_stage_batch(self._h, slot, split, _i64(ids), _i64(tok), l, B))
+
+    def train_step_staged(self, slot, pdrop=0.0, seed=0, want_loss=False):
+        if want_loss:
+            out = C.c_double()
+            check(self.lib.lrcn_train_step_staged(self._h, slot, pdrop, seed, C.byref(out)))
+            return float(out.value)
+        check(self.lib.lrcn_train_step_staged(self._h, slot, pdrop, seed, None))
+        return None
+
+    # ---- generation
+    def beam_search(self, split, image_ids, beam_width, nword, want_logps=True):
+        ids = np.ascontiguousarray(image_ids, dtype=np.int64)
+        n = len(ids)
+        toks = np.zeros((n, nword + 2), dtype=np.int64)
+        lens = np.zeros(n, dtype=np.int32)
+        prob = np.zeros(n, dtype=np.float32)
+        lps = np.zeros((n, nword + 1), dtype=np.float32) if want_logps else None
+        check(self.lib.lrcn_beam_search(self._h, split, _i64(ids), n, beam_width, nword, _i64(toks),
+                                        lens.ctypes.data_as(_i32p), _f32(prob), _f32(lps) if want_logps else None))
+        return toks, lens, prob, lps
+
+    # ---- data parallel
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        check(load().lrcn_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, uid: bytes, rank: int, nranks: int):
+        assert len(uid) == COMM_ID_BYTES
+        check(self.lib.lrcn_comm_init(self._h, uid, rank, nranks))
+
+    # ---- measurement
+    def sync(self):
+        check(self.lib.lrcn_sync(self._h))
+
+    def timer_start(self):
+        check(self.lib.lrcn_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        check(self.lib.lrcn_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def kernel_launches(self) -> int:
+        n = C.c_int64()
+        check(self.lib.lrcn_kernel_launches(self._h, C.byref(n)))
+        return int(n.value)
+
+    def flush_l2(self):
+        check(self.lib.lrcn_flush_l2(self._h))
+
+    def time_kernel(self, name: str, reps: int = 10):
+        ms, by, fl = C.c_float(), C.c_double(), C.c_double()
+        check(self.lib.lrcn_time_kernel(self._h, name.encode(), reps, C.byref(ms), C.byref(by), C.byref(fl)))
+        return float(ms.value), float(by.value), float(fl.value)
+
+    # ---- kernel-level test hooks
+    def test_gemm(self, precision, a_kmajor, b_kmajor, A, B, bias=None, C0=None):
+        A = np.ascontiguousarray(A, dtype=np.float32)
+        B = np.ascontiguousarray(B, dtype=np.float32)
+        M, K = A.shape if a_kmajor else A.shape[::-1]
+        N = B.shape[0] if b_kmajor else B.shape[1]
+        assert (B.shape[1] if b_kmajor else B.shape[0]) == K
+        out = np.zeros((M, N), dtype=np.float32) if C0 is None else np.ascontiguousarray(C0, dtype=np.float32).copy()
+        b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+        check(self.lib.lrcn_test_gemm(self._h, precision, int(a_kmajor), int(b_kmajor), M, N, K, _f32(A), _f32(B),
+                                      _f32(b) if b is not None else None, 0 if C0 is None else 1, _f32(out)))
+        return out
+
+    def test_beam_select(self, probs, parent_prob, n_images, K, first_step):
+        probs = np.ascontiguousarray(probs, dtype=np.float32)
+        parent_prob = np.ascontiguousarray(parent_prob, dtype=np.float32)
+        R, V = probs.shape
+        assert R == n_images * K
+        tok = np.zeros(R, dtype=np.int64)
+        par = np.zeros(R, dtype=np.int32)
+        sc = np.zeros(R, dtype=np.float32)
+        check(self.lib.lrcn_test_beam_select(self._h, _f32(probs), _f32(parent_prob), n_images, K, V, int(first_step),
+                                             _i64(tok), par.ctypes.data_as(_i32p), _f32(sc)))
+        return tok.reshape(n_images, K), par.reshape(n_images, K), sc.reshape(n_images, K)

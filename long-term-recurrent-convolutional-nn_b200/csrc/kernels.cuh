@@ -1,0 +1,94 @@
+// kernels.cuh -- device-kernel launchers shared by the C-ABI layer (lrcn_api.cu).
+// All matrices here are ROW-MAJOR device buffers; the reference's column-major K x N weight
+// is the same memory as a row-major [N][K] matrix, so no relayout is needed except Wemb.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace lrcn {
+
+// Scalars that change every step live in device memory so that a captured CUDA graph of the
+// step can be replayed without re-baking kernel arguments.
+struct StepScalars {
+  float inv_ntok;       // 1 / (global token count) : dA scale (lrcn.jl:580 -total/count)
+  float pdrop;          // dropout probability (lrcn.jl:542,547)
+  float keep_scale;     // 1/(1-pdrop)
+  uint32_t drop_thresh; // keep iff (hash>>8) >= drop_thresh ; drop_thresh = pdrop * 2^24
+  uint64_t seed;
+  float adam_d1;        // 1 - beta1^t
+  float adam_d2;        // 1 - beta2^t
+  float lr, beta1, beta2, eps;
+  float grad_scale;     // reserved
+};
+
+struct LaunchCounter { long long n = 0; };
+extern thread_local LaunchCounter* g_counter;  // incremented by every launcher below
+
+// ---------------------------------------------------------------- GEMM (fp32, CUDA cores)
+// C[M][N] (ldc) = sum_k Aop[m][k] * Bop[k][n]  (+ C if beta) (+ bias[n])
+//   a_kmajor: A[m*lda+k] else A[k*lda+m];  b_kmajor: B[n*ldb+k] else B[k*ldb+n]
+void sgemm(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int K, const float* A, int lda,
+           const float* B, int ldb, float* C, int ldc, bool beta, const float* bias);
+
+// ---------------------------------------------------------------- elementwise / gather kernels
+void gather_features(cudaStream_t s, const float* table, const int* rows, int B, float* X);
+// E_all[r][:] = WembT[tok[r]][:] (* dropout mask site 0);  tok 0-based
+void gather_embed(cudaStream_t s, const float* WembT, const int* tok, int R, int E, float* out,
+                  const StepScalars* sc, bool train);
+// Z[r][C+j] = v[r % B][j]; then dropout (site 1) over the whole row of 2C
+void z_finish(cudaStream_t s, float* Z, const float* v, int R, int B, int C, const StepScalars* sc, bool train);
+// LSTM cell forward for one step: gates (pre-activation, [B][4H], order f,i,o,g) are activated in place
+void lstm_cell_fwd(cudaStream_t s, float* gates, const float* c_prev, float* c_out, float* h_out, int B, int H);
+// LSTM cell backward for one step; gates buffer holds activations and receives dG in place
+void lstm_cell_bwd(cudaStream_t s, float* gates, const float* c_prev, const float* c_cur, const float* dh_in,
+                   const float* dh_rec /*nullable*/, float* dc /*in/out*/, bool first /*dc,dh_rec are zero*/,
+                   int B, int H);
+// row-wise log-softmax cross-entropy: rowlp[r] = logp(a_r)[y_r]; if train, logits <- (softmax - onehot)*inv_ntok
+void softmax_ce(cudaStream_t s, float* logits, int ld, int R, int V, const int* tgt, float* rowlp,
+                const StepScalars* sc, bool train);
+void reduce_sum_double(cudaStream_t s, const float* x, int n, double* out);
+void colsum(cudaStream_t s, const float* A, int ld, int R, int N, float* out, bool accumulate);
+// dZ *= dropout mask (site 1); dv[i][j] = sum_t dZ[(t*B+i)][C+j]
+void dz_finish(cudaStream_t s, float* dZ, float* dv, int T, int B, int C, const StepScalars* sc, bool train);
+// dWembT[tok[r]][:] += dE[r][:] (* dropout mask site 0)
+void scatter_add_embed(cudaStream_t s, float* dWembT, const int* tok, const float* dE, int R, int E,
+                       const StepScalars* sc, bool train);
+// fused dense Adam over one flat range (Knet defaults, lrcn.jl:394,402); optionally refreshes bf16 hi/lo shadows
+void adam_flat(cudaStream_t s, float* w, const float* g, float* m, float* v, size_t n, const StepScalars* sc,
+               __nv_bfloat16* w_hi, __nv_bfloat16* w_lo);
+void split_bf16(cudaStream_t s, const float* x, size_t n, __nv_bfloat16* hi, __nv_bfloat16* lo);
+void transpose2d(cudaStream_t s, const float* in, int rows, int cols, float* out);  // out[c][r] = in[r][c]
+void fill_l2_scratch(cudaStream_t s, float* buf, size_t n, float val);
+
+// ---------------------------------------------------------------- beam search
+// per row: prob = exp(logp(a)); top-K by (prob desc, index asc); cand_* are [R][K]
+void beam_row_topk(cudaStream_t s, const float* logits, int ld, int R, int V, int K, const float* parent_prob,
+                   int* cand_tok, float* cand_score, float* cand_lp);
+void beam_row_topk_probs(cudaStream_t s, const float* probs, int ld, int R, int V, int K, const float* parent_prob,
+                         int* cand_tok, float* cand_score, float* cand_lp);
+// per image: pick K of the K*K (K at the first step) candidates by (score desc, list position asc)
+void beam_select(cudaStream_t s, const int* cand_tok, const float* cand_score, const float* cand_lp, int n_img, int K,
+                 int first_step, int* sel_tok, int* sel_parent, float* sel_score, float* sel_lp);
+struct BeamAdvanceArgs {
+  int n_img, K, H1, H2, maxlen, step, nword;
+  const int* sel_tok; const int* sel_parent; const float* sel_score; const float* sel_lp;
+  const float *h1_in, *c1_in, *h2_in, *c2_in; float *h1_out, *c1_out, *h2_out, *c2_out;
+  const int* hist_in; int* hist_out; const float* lp_in; float* lp_out;
+  float* prob; int* last_tok; int* done; int* n_done;
+  long long* out_tokens; int* out_len; float* out_prob; float* out_lp;
+};
+void beam_advance(cudaStream_t s, const BeamAdvanceArgs& a);
+
+// ---------------------------------------------------------------- tcgen05 path (gemm_sm100.cu)
+// Same contract as sgemm, operands given as pre-split bf16 hi/lo pairs (ld in elements, multiple of 8).
+bool gemm_bf16x3(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int K,
+                 const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo, int lda,
+                 const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, int ldb,
+                 float* C, int ldc, bool beta, const float* bias,
+                 __nv_bfloat16* C_hi, __nv_bfloat16* C_lo /* optional split of the result, same ldc */);
+const char* gemm_bf16x3_last_error();
+bool init_gemm_sm100();   // func attributes + driver entry point; call once outside any capture
+void init_simt_kernels();
+
+}  // namespace lrcn

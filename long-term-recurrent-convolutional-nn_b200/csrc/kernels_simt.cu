@@ -1,0 +1,686 @@
+// kernels_simt.cu -- CUDA-core kernels of the LRCN decoder path for sm_100a:
+// fp32 GEMM (exact mode / odd shapes), gathers, LSTM cell fwd/bwd, softmax-CE, reductions,
+// scatter-add, fused Adam (+bf16 hi/lo shadow refresh), beam-search selection kernels.
+// Reference semantics: lrcn.jl:528-581 (lstm, lrcn, loss), :644-678 (beam_search), Knet Adam.
+#include "kernels.cuh"
+#include <math.h>
+
+namespace lrcn {
+
+thread_local LaunchCounter* g_counter = nullptr;
+static inline void count_launch() { if (g_counter) g_counter->n++; }
+
+// ------------------------------------------------------------------------------------------
+// dropout mask: counter-based hash (SplitMix64 finaliser) of (seed, site, element index)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t drop_hash24(uint64_t seed, uint32_t site, uint64_t idx) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1) + 0xD1B54A32D192ED03ull * (uint64_t)(site + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (uint32_t)(z >> 40);
+}
+__device__ __forceinline__ float drop_scale(const StepScalars* sc, uint32_t site, uint64_t idx) {
+  if (sc->drop_thresh == 0) return 1.0f;
+  return drop_hash24(sc->seed, site, idx) >= sc->drop_thresh ? sc->keep_scale : 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 GEMM, 64x64x32 tiles, 256 threads, 4x4 micro-tile, register-prefetched k-tiles, split-K
+// ------------------------------------------------------------------------------------------
+constexpr int GBM = 64, GBN = 64, GBK = 32, GPAD = 4;
+
+template <bool KMAJOR>
+__device__ __forceinline__ void load_tile_regs(const float* __restrict__ P, int ld, int mn0, int MN, int k0, int kend,
+                                               int tid, float (&r)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    int idx = tid + i * 256;
+    int mm, kk;
+    if (KMAJOR) { int kq = idx & 7; mm = (idx >> 3) & 63; kk = (idx >> 9) * 8 + kq; }
+    else        { mm = idx & 63; kk = idx >> 6; }
+    int gm = mn0 + mm, gk = k0 + kk;
+    float v = 0.f;
+    if (gm < MN && gk < kend) v = KMAJOR ? __ldg(P + (size_t)gm * ld + gk) : __ldg(P + (size_t)gk * ld + gm);
+    r[i] = v;
+  }
+}
+template <bool KMAJOR>
+__device__ __forceinline__ void store_tile_smem(float (*S)[GBM + GPAD], int tid, const float (&r)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    int idx = tid + i * 256;
+    int mm, kk;
+    if (KMAJOR) { int kq = idx & 7; mm = (idx >> 3) & 63; kk = (idx >> 9) * 8 + kq; }
+    else        { mm = idx & 63; kk = idx >> 6; }
+    S[kk][mm] = r[i];
+  }
+}
+
+template <bool AK, bool BKM>
+__global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                    const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
+                                                    int beta, const float* __restrict__ bias, int kper) {
+  __shared__ __align__(16) float As[GBK][GBM + GPAD];
+  __shared__ __align__(16) float Bs[GBK][GBN + GPAD];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+  const int kbeg = blockIdx.z * kper;
+  const int kend = min(K, kbeg + kper);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+  float ra[8], rb[8];
+  load_tile_regs<AK>(A, lda, m0, M, kbeg, kend, tid, ra);
+  load_tile_regs<BKM>(B, ldb, n0, N, kbeg, kend, tid, rb);
+  for (int k0 = kbeg; k0 < kend; k0 += GBK) {
+    store_tile_smem<AK>(As, tid, ra);
+    store_tile_smem<BKM>(Bs, tid, rb);
+    __syncthreads();
+    if (k0 + GBK < kend) {
+      load_tile_regs<AK>(A, lda, m0, M, k0 + GBK, kend, tid, ra);
+      load_tile_regs<BKM>(B, ldb, n0, N, k0 + GBK, kend, tid, rb);
+    }
+#pragma unroll
+    for (int kk = 0; kk < GBK; kk++) {
+      float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const bool split = gridDim.z > 1;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      float* c = C + (size_t)gm * ldc + gn;
+      if (split) {
+        if (blockIdx.z == 0 && bias) v += bias[gn];
+        atomicAdd(c, v);  // C was pre-zeroed by the launcher when !beta
+      } else {
+        if (bias) v += bias[gn];
+        if (beta) v += *c;
+        *c = v;
+      }
+    }
+  }
+}
+
+void sgemm(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int K, const float* A, int lda, const float* B,
+           int ldb, float* C, int ldc, bool beta, const float* bias) {
+  if (M <= 0 || N <= 0) return;
+  int tm = (M + GBM - 1) / GBM, tn = (N + GBN - 1) / GBN;
+  int tiles = tm * tn;
+  int splits = 1;
+  if (tiles < 148 && K >= 256) {
+    splits = (296 + tiles - 1) / tiles;
+    int maxs = K / 128;
+    if (splits > maxs) splits = maxs;
+    if (splits < 1) splits = 1;
+    if (splits > 32) splits = 32;
+  }
+  int kper = ((K + splits - 1) / splits + GBK - 1) / GBK * GBK;
+  if (kper <= 0) kper = GBK;
+  splits = (K + kper - 1) / kper;
+  if (splits < 1) splits = 1;
+  if (splits > 1 && !beta) {
+    if (ldc == N) cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), s);
+    else cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, s);
+  }
+  dim3 grid(tn, tm, splits);
+  int b = beta ? 1 : 0;
+  if (a_kmajor && b_kmajor) sgemm_kernel<true, true><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, b, bias, kper);
+  else if (a_kmajor && !b_kmajor) sgemm_kernel<true, false><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, b, bias, kper);
+  else if (!a_kmajor && b_kmajor) sgemm_kernel<false, true><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, b, bias, kper);
+  else sgemm_kernel<false, false><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, b, bias, kper);
+  count_launch();
+}
+
+// ------------------------------------------------------------------------------------------
+// gathers
+// ------------------------------------------------------------------------------------------
+__global__ void gather_features_kernel(const float4* __restrict__ table, const int* __restrict__ rows, float4* __restrict__ X) {
+  int i = blockIdx.x;
+  const float4* src = table + (size_t)rows[i] * 1024;
+  float4* dst = X + (size_t)i * 1024;
+  for (int j = threadIdx.x; j < 1024; j += blockDim.x) dst[j] = __ldg(src + j);
+}
+void gather_features(cudaStream_t s, const float* table, const int* rows, int B, float* X) {
+  gather_features_kernel<<<B, 256, 0, s>>>((const float4*)table, rows, (float4*)X);
+  count_launch();
+}
+
+__global__ void gather_embed_kernel(const float* __restrict__ W, const int* __restrict__ tok, int R, int E,
+                                    float* __restrict__ out, const StepScalars* __restrict__ sc, int train) {
+  int r = blockIdx.x;
+  const float* src = W + (size_t)tok[r] * E;
+  float* dst = out + (size_t)r * E;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    float v = __ldg(src + e);
+    if (train) v *= drop_scale(sc, 0, (uint64_t)r * E + e);
+    dst[e] = v;
+  }
+}
+void gather_embed(cudaStream_t s, const float* WembT, const int* tok, int R, int E, float* out, const StepScalars* sc,
+                  bool train) {
+  gather_embed_kernel<<<R, 128, 0, s>>>(WembT, tok, R, E, out, sc, train ? 1 : 0);
+  count_launch();
+}
+
+__global__ void z_finish_kernel(float* __restrict__ Z, const float* __restrict__ v, int R, int B, int C,
+                                const StepScalars* __restrict__ sc, int train) {
+  int r = blockIdx.x;
+  int i = B > 0 ? r % B : r / (-B);  // B<0: generation, image index = row / beam_width
+  float* z = Z + (size_t)r * 2 * C;
+  for (int j = threadIdx.x; j < 2 * C; j += blockDim.x) {
+    float x = (j < C) ? z[j] : v[(size_t)i * C + (j - C)];
+    if (train) x *= drop_scale(sc, 1, (uint64_t)r * 2 * C + j);
+    z[j] = x;
+  }
+}
+void z_finish(cudaStream_t s, float* Z, const float* v, int R, int B, int C, const StepScalars* sc, bool train) {
+  z_finish_kernel<<<R, 128, 0, s>>>(Z, v, R, B, C, sc, train ? 1 : 0);
+  count_launch();
+}
+
+// ------------------------------------------------------------------------------------------
+// LSTM cell (lrcn.jl:528-538): gate column order [forget | ingate | outgate | change]
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigm_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void lstm_cell_fwd_kernel(float* __restrict__ gates, const float* __restrict__ c_prev, float* __restrict__ c_out,
+                                     float* __restrict__ h_out, int B, int H) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * H) return;
+  int i = idx / H, j = idx - i * H;
+  float* g = gates + (size_t)i * 4 * H;
+  float f = sigm_f(g[j]), in = sigm_f(g[H + j]), o = sigm_f(g[2 * H + j]), ch = tanhf(g[3 * H + j]);
+  float c = c_prev[idx] * f + in * ch;
+  g[j] = f; g[H + j] = in; g[2 * H + j] = o; g[3 * H + j] = ch;
+  c_out[idx] = c;
+  h_out[idx] = o * tanhf(c);
+}
+void lstm_cell_fwd(cudaStream_t s, float* gates, const float* c_prev, float* c_out, float* h_out, int B, int H) {
+  int n = B * H;
+  lstm_cell_fwd_kernel<<<(n + 255) / 256, 256, 0, s>>>(gates, c_prev, c_out, h_out, B, H);
+  count_launch();
+}
+
+__global__ void lstm_cell_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c_cur,
+                                     const float* __restrict__ dh_in, const float* __restrict__ dh_rec, float* __restrict__ dc,
+                                     int first, int B, int H) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * H) return;
+  int i = idx / H, j = idx - i * H;
+  float* g = gates + (size_t)i * 4 * H;
+  float f = g[j], in = g[H + j], o = g[2 * H + j], ch = g[3 * H + j];
+  float dh = dh_in[idx];
+  if (!first && dh_rec) dh += dh_rec[idx];
+  float tc = tanhf(c_cur[idx]);
+  float dcv = (first ? 0.f : dc[idx]) + dh * o * (1.f - tc * tc);
+  float dO = dh * tc;
+  float dF = dcv * c_prev[idx];
+  float dI = dcv * ch;
+  float dG = dcv * in;
+  dc[idx] = dcv * f;
+  g[j] = dF * f * (1.f - f);
+  g[H + j] = dI * in * (1.f - in);
+  g[2 * H + j] = dO * o * (1.f - o);
+  g[3 * H + j] = dG * (1.f - ch * ch);
+}
+void lstm_cell_bwd(cudaStream_t s, float* gates, const float* c_prev, const float* c_cur, const float* dh_in,
+                   const float* dh_rec, float* dc, bool first, int B, int H) {
+  int n = B * H;
+  lstm_cell_bwd_kernel<<<(n + 255) / 256, 256, 0, s>>>(gates, c_prev, c_cur, dh_in, dh_rec, dc, first ? 1 : 0, B, H);
+  count_launch();
+}
+
+// ------------------------------------------------------------------------------------------
+// block reductions
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  v = (l < nw) ? red[l] : -INFINITY;
+  return warp_max(v);
+}
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  v = (l < nw) ? red[l] : 0.f;
+  return warp_sum(v);
+}
+
+// ------------------------------------------------------------------------------------------
+// softmax cross-entropy, one CTA per row (Knet logp(x,2), lrcn.jl:562-567 and its adjoint)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_ce_kernel(float* __restrict__ logits, int ld, int V, const int* __restrict__ tgt,
+                                                         float* __restrict__ rowlp, const StepScalars* __restrict__ sc, int train) {
+  extern __shared__ float row[];
+  __shared__ float red[32];
+  int r = blockIdx.x;
+  float* a = logits + (size_t)r * ld;
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < V; j += blockDim.x) { float x = a[j]; row[j] = x; mx = fmaxf(mx, x); }
+  mx = block_max(mx, red);
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < V; j += blockDim.x) sum += expf(row[j] - mx);
+  sum = block_sum(sum, red);
+  float lse = logf(sum);
+  int y = tgt[r];
+  if (threadIdx.x == 0) rowlp[r] = (row[y] - mx) - lse;
+  if (train) {
+    float inv = sc->inv_ntok;
+    for (int j = threadIdx.x; j < V; j += blockDim.x) {
+      float p = expf((row[j] - mx) - lse);
+      if (j == y) p -= 1.0f;
+      a[j] = p * inv;
+    }
+    for (int j = V + threadIdx.x; j < ld; j += blockDim.x) a[j] = 0.f;  // keep the padding columns clean
+  }
+}
+void softmax_ce(cudaStream_t s, float* logits, int ld, int R, int V, const int* tgt, float* rowlp, const StepScalars* sc,
+                bool train) {
+  size_t smem = (size_t)V * sizeof(float);
+  softmax_ce_kernel<<<R, 256, smem, s>>>(logits, ld, V, tgt, rowlp, sc, train ? 1 : 0);
+  count_launch();
+}
+
+__global__ void reduce_sum_double_kernel(const float* __restrict__ x, int n, double* __restrict__ out) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)x[i];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = red[0];
+}
+void reduce_sum_double(cudaStream_t s, const float* x, int n, double* out) {
+  reduce_sum_double_kernel<<<1, 256, 0, s>>>(x, n, out);
+  count_launch();
+}
+
+// out[n] (+)= sum_r A[r][n] ; block = 32 columns x 8 row-lanes, grid.y splits rows (atomic combine)
+__global__ void colsum_kernel(const float* __restrict__ A, int ld, int R, int N, float* __restrict__ out, int rows_per) {
+  __shared__ float red[8][33];
+  int n = blockIdx.x * 32 + threadIdx.x;
+  int r0 = blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
+  float acc = 0.f;
+  if (n < N)
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) acc += A[(size_t)r * ld + n];
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += red[k][threadIdx.x];
+    atomicAdd(out + n, s);
+  }
+}
+void colsum(cudaStream_t s, const float* A, int ld, int R, int N, float* out, bool accumulate) {
+  if (!accumulate) cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), s);
+  int gx = (N + 31) / 32;
+  int gy = 1;
+  while (gx * gy < 296 && gy * 64 < R) gy *= 2;
+  int rows_per = (R + gy - 1) / gy;
+  colsum_kernel<<<dim3(gx, gy), dim3(32, 8), 0, s>>>(A, ld, R, N, out, rows_per);
+  count_launch();
+}
+
+__global__ void dz_finish_kernel(float* __restrict__ dZ, float* __restrict__ dv, int T, int B, int C,
+                                 const StepScalars* __restrict__ sc, int train) {
+  int i = blockIdx.x;  // batch row
+  for (int j = threadIdx.x; j < 2 * C; j += blockDim.x) {
+    float acc = 0.f;
+    for (int t = 0; t < T; t++) {
+      size_t r = (size_t)t * B + i;
+      float x = dZ[r * 2 * C + j];
+      if (train) { x *= drop_scale(sc, 1, (uint64_t)r * 2 * C + j); dZ[r * 2 * C + j] = x; }
+      acc += x;
+    }
+    if (j >= C) dv[(size_t)i * C + (j - C)] = acc;
+  }
+}
+void dz_finish(cudaStream_t s, float* dZ, float* dv, int T, int B, int C, const StepScalars* sc, bool train) {
+  dz_finish_kernel<<<B, 256, 0, s>>>(dZ, dv, T, B, C, sc, train ? 1 : 0);
+  count_launch();
+}
+
+__global__ void scatter_add_embed_kernel(float* __restrict__ dW, const int* __restrict__ tok, const float* __restrict__ dE, int R,
+                                         int E, const StepScalars* __restrict__ sc, int train) {
+  int r = blockIdx.x;
+  float* dst = dW + (size_t)tok[r] * E;
+  const float* src = dE + (size_t)r * E;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    float v = src[e];
+    if (train) v *= drop_scale(sc, 0, (uint64_t)r * E + e);
+    atomicAdd(dst + e, v);
+  }
+}
+void scatter_add_embed(cudaStream_t s, float* dWembT, const int* tok, const float* dE, int R, int E, const StepScalars* sc,
+                       bool train) {
+  scatter_add_embed_kernel<<<R, 128, 0, s>>>(dWembT, tok, dE, R, E, sc, train ? 1 : 0);
+  count_launch();
+}
+
+// ------------------------------------------------------------------------------------------
+// fused Adam over the flat parameter arena (Knet Adam defaults; dense over every element)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_one(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ w, const float4* __restrict__ g, float4* __restrict__ m,
+                                                   float4* __restrict__ v, size_t n4, const StepScalars* __restrict__ sc,
+                                                   __nv_bfloat16* __restrict__ w_hi, __nv_bfloat16* __restrict__ w_lo) {
+  const float b1 = sc->beta1, b2 = sc->beta2, lr = sc->lr, eps = sc->eps, d1 = sc->adam_d1, d2 = sc->adam_d2;
+  const float ob1 = 1.0f - b1, ob2 = 1.0f - b2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 W = w[i], G = __ldg(g + i), Mv = m[i], Vv = v[i];
+    float* wp = reinterpret_cast<float*>(&W);
+    const float* gp = reinterpret_cast<const float*>(&G);
+    float* mp = reinterpret_cast<float*>(&Mv);
+    float* vp = reinterpret_cast<float*>(&Vv);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      float mm = __fadd_rn(__fmul_rn(b1, mp[k]), __fmul_rn(ob1, gp[k]));
+      float vv = __fadd_rn(__fmul_rn(b2, vp[k]), __fmul_rn(ob2, __fmul_rn(gp[k], gp[k])));
+      float mh = __fdiv_rn(mm, d1);
+      float vh = __fdiv_rn(vv, d2);
+      float upd = __fdiv_rn(mh, __fadd_rn(__fsqrt_rn(vh), eps));
+      wp[k] = __fsub_rn(wp[k], __fmul_rn(lr, upd));
+      mp[k] = mm; vp[k] = vv;
+    }
+    w[i] = W; m[i] = Mv; v[i] = Vv;
+    if (SPLIT) {
+      __nv_bfloat16 h[4], l[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) split_one(wp[k], h[k], l[k]);
+      *reinterpret_cast<uint2*>(w_hi + 4 * i) = *reinterpret_cast<uint2*>(h);
+      *reinterpret_cast<uint2*>(w_lo + 4 * i) = *reinterpret_cast<uint2*>(l);
+    }
+  }
+}
+void adam_flat(cudaStream_t s, float* w, const float* g, float* m, float* v, size_t n, const StepScalars* sc,
+               __nv_bfloat16* w_hi, __nv_bfloat16* w_lo) {
+  size_t n4 = n / 4;  // arena sizes are padded to multiples of 4
+  int grid = 148 * 8;
+  if (w_hi) adam_kernel<true><<<grid, 256, 0, s>>>((float4*)w, (const float4*)g, (float4*)m, (float4*)v, n4, sc, w_hi, w_lo);
+  else adam_kernel<false><<<grid, 256, 0, s>>>((float4*)w, (const float4*)g, (float4*)m, (float4*)v, n4, sc, nullptr, nullptr);
+  count_launch();
+}
+
+__global__ void split_bf16_kernel(const float4* __restrict__ x, size_t n4, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 X = __ldg(x + i);
+    const float* xp = reinterpret_cast<const float*>(&X);
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) split_one(xp[k], h[k], l[k]);
+    *reinterpret_cast<uint2*>(hi + 4 * i) = *reinterpret_cast<uint2*>(h);
+    *reinterpret_cast<uint2*>(lo + 4 * i) = *reinterpret_cast<uint2*>(l);
+  }
+}
+void split_bf16(cudaStream_t s, const float* x, size_t n, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  size_t n4 = (n + 3) / 4;  // buffers are padded to multiples of 64 elements
+  if (n4 == 0) return;
+  size_t want = (n4 + 255) / 256;
+  int grid = (int)(want < (size_t)148 * 8 ? want : (size_t)148 * 8);
+  split_bf16_kernel<<<grid, 256, 0, s>>>((const float4*)x, n4, hi, lo);
+  count_launch();
+}
+
+__global__ void transpose_kernel(const float* __restrict__ in, int rows, int cols, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  int c = blockIdx.x * 32 + threadIdx.x;
+  for (int k = threadIdx.y; k < 32; k += 8) {
+    int r = blockIdx.y * 32 + k;
+    if (r < rows && c < cols) tile[k][threadIdx.x] = in[(size_t)r * cols + c];
+  }
+  __syncthreads();
+  int r2 = blockIdx.y * 32 + threadIdx.x;
+  for (int k = threadIdx.y; k < 32; k += 8) {
+    int c2 = blockIdx.x * 32 + k;
+    if (r2 < rows && c2 < cols) out[(size_t)c2 * rows + r2] = tile[threadIdx.x][k];
+  }
+}
+void transpose2d(cudaStream_t s, const float* in, int rows, int cols, float* out) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+  transpose_kernel<<<grid, dim3(32, 8), 0, s>>>(in, rows, cols, out);
+  count_launch();
+}
+
+__global__ void fill_kernel(float4* buf, size_t n4, float val) {
+  float4 v = make_float4(val, val, val, val);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) buf[i] = v;
+}
+void fill_l2_scratch(cudaStream_t s, float* buf, size_t n, float val) {
+  fill_kernel<<<148 * 8, 256, 0, s>>>((float4*)buf, n / 4, val);
+}
+
+// ------------------------------------------------------------------------------------------
+// beam search (lrcn.jl:644-678): fp32 probabilities exp(logp), ties -> lower index
+// ------------------------------------------------------------------------------------------
+struct BestPair { float v; int i; };
+__device__ __forceinline__ BestPair better(BestPair a, BestPair b) {
+  return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
+}
+__device__ __forceinline__ BestPair block_argmax(BestPair p, BestPair* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    BestPair q;
+    q.v = __shfl_xor_sync(0xffffffffu, p.v, o);
+    q.i = __shfl_xor_sync(0xffffffffu, p.i, o);
+    p = better(p, q);
+  }
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) red[w] = p;
+  __syncthreads();
+  BestPair q;
+  q.v = -2.f; q.i = 0x7fffffff;
+  if (l < nw) q = red[l];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    BestPair t;
+    t.v = __shfl_xor_sync(0xffffffffu, q.v, o);
+    t.i = __shfl_xor_sync(0xffffffffu, q.i, o);
+    q = better(q, t);
+  }
+  return q;
+}
+
+template <bool FROM_LOGITS>
+__global__ void __launch_bounds__(256) beam_row_topk_kernel(const float* __restrict__ in, int ld, int V, int K,
+                                                            const float* __restrict__ parent_prob, int* __restrict__ cand_tok,
+                                                            float* __restrict__ cand_score, float* __restrict__ cand_lp) {
+  extern __shared__ float row[];  // V probabilities
+  __shared__ float red[32];
+  __shared__ BestPair bred[32];
+  int r = blockIdx.x;
+  const float* a = in + (size_t)r * ld;
+  float lse = 0.f, mx = 0.f;
+  if (FROM_LOGITS) {
+    mx = -INFINITY;
+    for (int j = threadIdx.x; j < V; j += blockDim.x) { float x = a[j]; row[j] = x; mx = fmaxf(mx, x); }
+    mx = block_max(mx, red);
+    float sum = 0.f;
+    for (int j = threadIdx.x; j < V; j += blockDim.x) sum += expf(row[j] - mx);
+    sum = block_sum(sum, red);
+    lse = logf(sum);
+    for (int j = threadIdx.x; j < V; j += blockDim.x) row[j] = expf((row[j] - mx) - lse);  // ynorm = exp(logp(ypred,2))
+  } else {
+    for (int j = threadIdx.x; j < V; j += blockDim.x) row[j] = a[j];
+  }
+  __syncthreads();
+  float pp = parent_prob[r];
+  for (int k = 0; k < K; k++) {
+    BestPair p;
+    p.v = -2.f; p.i = 0x7fffffff;
+    for (int j = threadIdx.x; j < V; j += blockDim.x) {
+      BestPair q; q.v = row[j]; q.i = j;
+      p = better(p, q);
+    }
+    p = block_argmax(p, bred);
+    if (threadIdx.x == 0) {
+      cand_tok[(size_t)r * K + k] = p.i;
+      cand_score[(size_t)r * K + k] = __fmul_rn(p.v, pp);  // pmaxes = ynorm[xmaxes]*current_probability
+      cand_lp[(size_t)r * K + k] = FROM_LOGITS ? ((a[p.i] - mx) - lse) : logf(p.v);
+      row[p.i] = -1.f;  // exclude from later rounds
+    }
+    __syncthreads();
+  }
+}
+static void beam_topk_launch(cudaStream_t s, bool from_logits, const float* in, int ld, int R, int V, int K,
+                             const float* parent_prob, int* cand_tok, float* cand_score, float* cand_lp) {
+  size_t smem = (size_t)V * sizeof(float);
+  if (from_logits) beam_row_topk_kernel<true><<<R, 256, smem, s>>>(in, ld, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+  else beam_row_topk_kernel<false><<<R, 256, smem, s>>>(in, ld, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+  count_launch();
+}
+void beam_row_topk(cudaStream_t s, const float* logits, int ld, int R, int V, int K, const float* parent_prob, int* cand_tok,
+                   float* cand_score, float* cand_lp) {
+  beam_topk_launch(s, true, logits, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+}
+void beam_row_topk_probs(cudaStream_t s, const float* probs, int ld, int R, int V, int K, const float* parent_prob,
+                         int* cand_tok, float* cand_score, float* cand_lp) {
+  beam_topk_launch(s, false, probs, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+}
+
+// one thread per image: stable descending selection over the candidate list (beam-major, rank-minor)
+__global__ void beam_select_kernel(const int* __restrict__ cand_tok, const float* __restrict__ cand_score,
+                                   const float* __restrict__ cand_lp, int n_img, int K, int first_step, int* __restrict__ sel_tok,
+                                   int* __restrict__ sel_parent, float* __restrict__ sel_score, float* __restrict__ sel_lp) {
+  int img = blockIdx.x * blockDim.x + threadIdx.x;
+  if (img >= n_img) return;
+  int ncand = first_step ? K : K * K;
+  const float* sc = cand_score + (size_t)img * K * K;
+  unsigned long long used_lo = 0, used_hi = 0;  // K*K <= 128 candidates
+  for (int k = 0; k < K; k++) {
+    int best = -1;
+    float bv = 0.f;
+    for (int c = 0; c < ncand; c++) {
+      bool used = c < 64 ? ((used_lo >> c) & 1ull) : ((used_hi >> (c - 64)) & 1ull);
+      if (used) continue;
+      float v = sc[c];
+      if (best < 0 || v > bv) { best = c; bv = v; }  // strict > keeps the earlier list position on ties
+    }
+    if (best < 64) used_lo |= 1ull << best; else used_hi |= 1ull << (best - 64);
+    size_t o = (size_t)img * K + k;
+    sel_tok[o] = cand_tok[(size_t)img * K * K + best];
+    sel_parent[o] = best / K;  // ceil((best+1)/K) - 1  (lrcn.jl:675)
+    sel_score[o] = bv;
+    sel_lp[o] = cand_lp[(size_t)img * K * K + best];
+  }
+}
+void beam_select(cudaStream_t s, const int* cand_tok, const float* cand_score, const float* cand_lp, int n_img, int K,
+                 int first_step, int* sel_tok, int* sel_parent, float* sel_score, float* sel_lp) {
+  beam_select_kernel<<<(n_img + 63) / 64, 64, 0, s>>>(cand_tok, cand_score, cand_lp, n_img, K, first_step, sel_tok, sel_parent,
+                                                      sel_score, sel_lp);
+  count_launch();
+}
+
+// one CTA per (image, beam) row: reorder/gather the advanced states of the parents, extend histories,
+// detect termination (best hypothesis ends in eos, or step > nword: lrcn.jl:670) and emit results.
+__global__ void __launch_bounds__(128) beam_advance_kernel(BeamAdvanceArgs a) {
+  int r = blockIdx.x;
+  int img = r / a.K, k = r - img * a.K;
+  if (a.done[img]) return;
+  int parent = img * a.K + a.sel_parent[r];
+  for (int j = threadIdx.x; j < a.H1; j += blockDim.x) {
+    a.h1_out[(size_t)r * a.H1 + j] = a.h1_in[(size_t)parent * a.H1 + j];
+    a.c1_out[(size_t)r * a.H1 + j] = a.c1_in[(size_t)parent * a.H1 + j];
+  }
+  for (int j = threadIdx.x; j < a.H2; j += blockDim.x) {
+    a.h2_out[(size_t)r * a.H2 + j] = a.h2_in[(size_t)parent * a.H2 + j];
+    a.c2_out[(size_t)r * a.H2 + j] = a.c2_in[(size_t)parent * a.H2 + j];
+  }
+  // history so far has a.step tokens (bos + step-1 generated); append one
+  int len = a.step;
+  for (int j = threadIdx.x; j < len; j += blockDim.x) {
+    a.hist_out[(size_t)r * a.maxlen + j] = a.hist_in[(size_t)parent * a.maxlen + j];
+    a.lp_out[(size_t)r * a.maxlen + j] = a.lp_in[(size_t)parent * a.maxlen + j];
+  }
+  int tok = a.sel_tok[r];
+  if (threadIdx.x == 0) {
+    a.hist_out[(size_t)r * a.maxlen + len] = tok;
+    a.lp_out[(size_t)r * a.maxlen + len] = a.sel_lp[r];
+    a.prob[r] = a.sel_score[r];
+    a.last_tok[r] = tok;
+  }
+  if (k == 0) {
+    bool stop = (tok == 0 /* eos, 0-based */) || (a.step > a.nword);
+    if (stop) {
+      __syncthreads();
+      int total = len + 1;
+      for (int j = threadIdx.x; j < total; j += blockDim.x) {
+        a.out_tokens[(size_t)img * a.maxlen + j] = (long long)a.hist_out[(size_t)r * a.maxlen + j] + 1;
+        if (a.out_lp && j >= 1) a.out_lp[(size_t)img * (a.maxlen - 1) + (j - 1)] = a.lp_out[(size_t)r * a.maxlen + j];
+      }
+      if (threadIdx.x == 0) {
+        a.out_len[img] = total;
+        a.out_prob[img] = a.sel_score[r];
+      }
+    }
+  }
+}
+// second tiny kernel marks images done AFTER all K rows of the step were advanced (avoids a race on done[])
+__global__ void beam_mark_done_kernel(const int* __restrict__ sel_tok, int n_img, int K, int step, int nword, int* __restrict__ done,
+                                      int* __restrict__ n_done) {
+  int img = blockIdx.x * blockDim.x + threadIdx.x;
+  if (img >= n_img || done[img]) return;
+  int tok = sel_tok[(size_t)img * K];
+  if (tok == 0 || step > nword) {
+    done[img] = 1;
+    atomicAdd(n_done, 1);
+  }
+}
+void beam_advance(cudaStream_t s, const BeamAdvanceArgs& a) {
+  beam_advance_kernel<<<a.n_img * a.K, 128, 0, s>>>(a);
+  count_launch();
+  beam_mark_done_kernel<<<(a.n_img + 127) / 128, 128, 0, s>>>(a.sel_tok, a.n_img, a.K, a.step, a.nword, a.done, a.n_done);
+  count_launch();
+}
+
+// called once per process from lrcn_create (never inside a stream capture)
+void init_simt_kernels() {
+  cudaFuncSetAttribute(softmax_ce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(beam_row_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(beam_row_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
+}  // namespace lrcn

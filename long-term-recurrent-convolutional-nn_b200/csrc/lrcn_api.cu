@@ -1,0 +1,1053 @@
+// lrcn_api.cu -- C ABI (include/lrcn_b200.h) and step orchestration of the LRCN decoder hot path.
+//
+// Data layout in HBM (row-major notation; the reference's column-major K x N matrix IS a row-major [N][K]):
+//   parameter arena  w / g / m / v : four flat fp32 arenas with identical offsets, ordered by
+//     backward readiness so each gradient bucket is one contiguous NCCL allreduce:
+//       bucket 1: Wout [V][H2], bout [V]          (ready after the vocab backward)
+//       bucket 2: W2 [4H2][2H2], b2, Wf [C][H1], Wcnn [C][4096]   (after layer-2 BPTT)
+//       bucket 3: W1 [4H1][E+H1], b1, WembT [V][E]                 (after layer-1 BPTT)
+//     Wemb is the only relayout (V x E column-major -> [V][E]) so a word vector is one coalesced row.
+//     In bf16x3 mode w has bf16 hi/lo shadow arenas at the same element offsets (refreshed by Adam).
+//   feature tables: [n][4096] fp32 resident per split + host id->row map.
+//   workspace arena: time-major activations, row r = t*B + i (see Workspace below) + bf16 shadows.
+// Reference call sites replaced: lrcn.jl:378 (lossgradient), :394 (update!), :452-474 (average_loss body),
+// :585-678 (generate/beam_search).
+#include "../../include/lrcn_b200.h"
+#include "kernels.cuh"
+
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <tuple>
+#include <unordered_map>
+#include <vector>
+
+using namespace lrcn;
+typedef __nv_bfloat16 bf16;
+
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CK(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess) return fail(LRCN_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------ NCCL via dlopen
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (api.lib) break;
+    }
+    if (api.lib) {
+      api.GetUniqueId = (int (*)(ncclUniqueId*))dlsym(api.lib, "ncclGetUniqueId");
+      api.CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(api.lib, "ncclCommInitRank");
+      api.CommDestroy = (int (*)(ncclComm_t))dlsym(api.lib, "ncclCommDestroy");
+      api.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(api.lib, "ncclAllReduce");
+      api.GroupStart = (int (*)())dlsym(api.lib, "ncclGroupStart");
+      api.GroupEnd = (int (*)())dlsym(api.lib, "ncclGroupEnd");
+      api.GetErrorString = (const char* (*)(int))dlsym(api.lib, "ncclGetErrorString");
+    }
+  }
+  return (api.lib && api.GetUniqueId && api.CommInitRank && api.AllReduce) ? &api : nullptr;
+}
+enum { NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+
+// ------------------------------------------------------------------------------------------ handle
+struct Arena {
+  float* f = nullptr; bf16* hi = nullptr; bf16* lo = nullptr;
+  size_t cap = 0, used = 0;
+  size_t take(size_t n) { size_t o = used; used += (n + 63) / 64 * 64; return o; }
+};
+struct Table {
+  float* d = nullptr; int64_t n = 0;
+  std::unordered_map<int64_t, int> map;
+};
+struct Slot { int l = 0, B = 0, split = 0; int *tok_in = nullptr, *tok_tgt = nullptr, *rows = nullptr; };
+struct Workspace {  // element offsets into the workspace arena
+  size_t X, v, dv, Eall, dE, acts1, h1, c1, Z, dZ, acts2, h2, c2, logits, rowlp, dh2, dh1, dhrec1, dc1, dhrec2, dc2;
+  // generation
+  size_t gX, gv, ge, gg1, gh1a, gc1a, gh1b, gc1b, gz, gg2, gh2a, gc2a, gh2b, gc2b, glogits, gprob, gcs, gclp, gss, gslp, glpa, glpb, goprob, golp;
+};
+struct lrcn_handle {
+  lrcn_config cfg;
+  int E, H1, H2, C, V, ldV, ldv;
+  bool bf16mode;
+  cudaStream_t stream = nullptr, comm_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_seg[3] = {nullptr, nullptr, nullptr}, ev_comm = nullptr;
+  // params
+  size_t P = 0, off[9], nel[9], bucket_off[4];
+  int64_t rows[9], cols[9];
+  float *w = nullptr, *g = nullptr, *m = nullptr, *v = nullptr;
+  bf16 *w_hi = nullptr, *w_lo = nullptr;
+  int64_t adam_t = 0;
+  Table tab[2];
+  Arena ws;
+  Workspace o;
+  int *d_tok_in = nullptr, *d_tok_tgt = nullptr, *d_rows = nullptr;
+  int* h_stage = nullptr;  // pinned: tok_in | tok_tgt | rows
+  StepScalars *d_sc = nullptr, *h_sc = nullptr;
+  double *d_loss = nullptr, *h_loss = nullptr;
+  Slot slots[64];
+  std::map<std::tuple<int, int, int, int>, cudaGraphExec_t> graphs;
+  std::map<std::tuple<int, int, int, int>, long long> graph_launches;
+  LaunchCounter counter;
+  int last_B = 0, last_l = 0;
+  // DP
+  ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
+  // generation int buffers
+  int *g_last = nullptr, *g_ctok = nullptr, *g_stok = nullptr, *g_spar = nullptr, *g_hista = nullptr, *g_histb = nullptr, *g_done = nullptr,
+      *g_ndone = nullptr, *g_olen = nullptr, *g_rows = nullptr;
+  long long* g_otok = nullptr;
+  int* h_ndone = nullptr;
+  float* l2_scratch = nullptr; size_t l2_n = 0;
+};
+
+static inline float* WS(lrcn_handle* h, size_t off) { return h->ws.f + off; }
+static inline float* Wp(lrcn_handle* h, int idx1) { return h->w + h->off[idx1 - 1]; }
+static inline float* Gp(lrcn_handle* h, int idx1) { return h->g + h->off[idx1 - 1]; }
+
+static void shadow(lrcn_handle* h, const float* p, bf16** hi, bf16** lo) {
+  if (p >= h->w && p < h->w + h->P) { *hi = h->w_hi + (p - h->w); *lo = h->w_lo + (p - h->w); return; }
+  *hi = h->ws.hi + (p - h->ws.f);
+  *lo = h->ws.lo + (p - h->ws.f);
+}
+static void split_ws(lrcn_handle* h, const float* p, size_t n) {
+  if (!h->bf16mode) return;
+  bf16 *hi, *lo;
+  shadow(h, p, &hi, &lo);
+  split_bf16(h->stream, p, n, hi, lo);
+}
+
+struct GemmFail { std::string msg; };
+// precision-dispatching GEMM on arena pointers (both are CUDA paths; no CPU fallback exists)
+static void gemm(lrcn_handle* h, bool aK, bool bK, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+                 int ldc, bool beta, const float* bias, bool split_out = false) {
+  if (!h->bf16mode) {
+    sgemm(h->stream, aK, bK, M, N, K, A, lda, B, ldb, C, ldc, beta, bias);
+    return;
+  }
+  bf16 *ah, *al, *bh, *bl, *ch = nullptr, *cl = nullptr;
+  shadow(h, A, &ah, &al);
+  shadow(h, B, &bh, &bl);
+  if (split_out) shadow(h, C, &ch, &cl);
+  if (!gemm_bf16x3(h->stream, aK, bK, M, N, K, ah, al, lda, bh, bl, ldb, C, ldc, beta, bias, ch, cl))
+    throw GemmFail{gemm_bf16x3_last_error()};
+}
+
+// ------------------------------------------------------------------------------------------ misc ABI
+extern "C" int lrcn_abi_version(void) { return LRCN_ABI_VERSION; }
+extern "C" const char* lrcn_last_error(void) { return g_err.c_str(); }
+extern "C" int lrcn_config_default(lrcn_config* c) {
+  if (!c) return fail(LRCN_ERR_ARG, "null config");
+  memset(c, 0, sizeof *c);
+  c->embed = 1000; c->hidden1 = 1000; c->hidden2 = 1000;  // lrcn.jl:39-40
+  c->vocab = 10636;
+  c->max_batch = 256; c->max_len = 28;                    // lrcn.jl:353
+  c->max_gen_rows = 1024; c->device = 0;
+  c->precision = LRCN_PREC_BF16X3; c->use_graphs = 1;
+  c->lr = 1e-3f; c->beta1 = 0.9f; c->beta2 = 0.999f; c->eps = 1e-8f;  // Knet Adam() via lrcn.jl:402
+  return LRCN_OK;
+}
+
+static void param_dims(const lrcn_handle* h, int k, int64_t* r, int64_t* c) {
+  const int E = h->E, H1 = h->H1, H2 = h->H2, C = h->C, V = h->V;
+  switch (k) {
+    case 1: *r = E + H1; *c = 4 * H1; break;
+    case 2: *r = 1; *c = 4 * H1; break;
+    case 3: *r = 2 * H2; *c = 4 * H2; break;
+    case 4: *r = 1; *c = 4 * H2; break;
+    case 5: *r = H1; *c = C; break;
+    case 6: *r = LRCN_F_CNN; *c = C; break;
+    case 7: *r = V; *c = E; break;
+    case 8: *r = H2; *c = V; break;
+    default: *r = 1; *c = V; break;
+  }
+}
+
+extern "C" int lrcn_destroy(lrcn_handle* h) {
+  if (!h) return LRCN_OK;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  if (h->comm && nccl_api()) nccl_api()->CommDestroy(h->comm);
+  void* ptrs[] = {h->w, h->g, h->m, h->v, h->w_hi, h->w_lo, h->tab[0].d, h->tab[1].d, h->ws.f, h->ws.hi, h->ws.lo, h->d_tok_in,
+                  h->d_tok_tgt, h->d_rows, h->d_sc, h->d_loss, h->g_last, h->g_ctok, h->g_stok, h->g_spar, h->g_hista, h->g_histb,
+                  h->g_done, h->g_ndone, h->g_olen, h->g_rows, h->g_otok, h->l2_scratch};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (auto& s : h->slots) { if (s.tok_in) cudaFree(s.tok_in); if (s.tok_tgt) cudaFree(s.tok_tgt); if (s.rows) cudaFree(s.rows); }
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  if (h->h_sc) cudaFreeHost(h->h_sc);
+  if (h->h_loss) cudaFreeHost(h->h_loss);
+  if (h->h_ndone) cudaFreeHost(h->h_ndone);
+  for (cudaEvent_t e : {h->ev0, h->ev1, h->ev_seg[0], h->ev_seg[1], h->ev_seg[2], h->ev_comm}) if (e) cudaEventDestroy(e);
+  if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return LRCN_OK;
+}
+
+static int create_impl(const lrcn_config* cfg, lrcn_handle* h) {
+  h->cfg = *cfg;
+  h->E = cfg->embed; h->H1 = cfg->hidden1; h->H2 = cfg->hidden2; h->V = cfg->vocab;
+  h->C = (h->H2 + 1) / 2;
+  h->ldV = (h->V + 7) / 8 * 8;
+  h->ldv = (h->C + 7) / 8 * 8;
+  h->bf16mode = cfg->precision == LRCN_PREC_BF16X3;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(LRCN_ERR_CUDA, "no CUDA device (%s); liblrcn_b200 has no CPU fallback", e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(LRCN_ERR_ARG, "device %d out of range (%d devices)", cfg->device, ndev);
+  CK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (h->bf16mode && prop.major != 10)
+    return fail(LRCN_ERR_CUDA, "precision bf16x3 needs sm_100a (tcgen05); device is sm_%d%d", prop.major, prop.minor);
+  init_simt_kernels();
+  if (h->bf16mode && !init_gemm_sm100()) return fail(LRCN_ERR_CUDA, "%s", gemm_bf16x3_last_error());
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&h->ev0));
+  CK(cudaEventCreate(&h->ev1));
+  for (int i = 0; i < 3; i++) CK(cudaEventCreateWithFlags(&h->ev_seg[i], cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
+
+  // ---- parameter arenas, bucket order (1-based model index): [8,9 | 3,4,5,6 | 1,2,7]
+  const int order[9] = {8, 9, 3, 4, 5, 6, 1, 2, 7};
+  size_t pos = 0;
+  for (int i = 0; i < 9; i++) {
+    int k = order[i];
+    if (i == 0) h->bucket_off[0] = pos;
+    if (i == 2) h->bucket_off[1] = pos;
+    if (i == 6) h->bucket_off[2] = pos;
+    param_dims(h, k, &h->rows[k - 1], &h->cols[k - 1]);
+    h->nel[k - 1] = (size_t)(h->rows[k - 1] * h->cols[k - 1]);
+    h->off[k - 1] = pos;
+    pos += (h->nel[k - 1] + 63) / 64 * 64;
+  }
+  h->bucket_off[3] = pos;
+  h->P = pos;
+  CK(cudaMalloc(&h->w, h->P * 4)); CK(cudaMalloc(&h->g, h->P * 4)); CK(cudaMalloc(&h->m, h->P * 4)); CK(cudaMalloc(&h->v, h->P * 4));
+  CK(cudaMemset(h->w, 0, h->P * 4)); CK(cudaMemset(h->g, 0, h->P * 4)); CK(cudaMemset(h->m, 0, h->P * 4)); CK(cudaMemset(h->v, 0, h->P * 4));
+  if (h->bf16mode) {
+    CK(cudaMalloc(&h->w_hi, h->P * 2)); CK(cudaMalloc(&h->w_lo, h->P * 2));
+    CK(cudaMemset(h->w_hi, 0, h->P * 2)); CK(cudaMemset(h->w_lo, 0, h->P * 2));
+  }
+
+  // ---- workspace arena
+  const size_t B = cfg->max_batch, T = cfg->max_len + 1, R = B * T, R1 = B * (T + 1);
+  const size_t E = h->E, H1 = h->H1, H2 = h->H2, C = h->C, ldV = h->ldV, ldv = h->ldv;
+  Arena& a = h->ws;
+  Workspace& o = h->o;
+  o.X = a.take(B * LRCN_F_CNN); o.v = a.take(B * ldv); o.dv = a.take(B * ldv);
+  o.Eall = a.take(R * E); o.dE = a.take(R * E);
+  o.acts1 = a.take(R * 4 * H1); o.h1 = a.take(R1 * H1); o.c1 = a.take(R1 * H1);
+  o.Z = a.take(R * 2 * C); o.dZ = a.take(R * 2 * C);
+  o.acts2 = a.take(R * 4 * H2); o.h2 = a.take(R1 * H2); o.c2 = a.take(R1 * H2);
+  o.logits = a.take(R * ldV); o.rowlp = a.take(R);
+  o.dh2 = a.take(R * H2); o.dh1 = a.take(R * H1);
+  o.dhrec1 = a.take(B * H1); o.dc1 = a.take(B * H1); o.dhrec2 = a.take(B * H2); o.dc2 = a.take(B * H2);
+  const size_t G = cfg->max_gen_rows > 0 ? cfg->max_gen_rows : 1;
+  const size_t ML = 64;  // max history length (nword+2 <= 64)
+  o.gX = a.take(G * LRCN_F_CNN); o.gv = a.take(G * ldv); o.ge = a.take(G * E); o.gg1 = a.take(G * 4 * H1);
+  o.gh1a = a.take(G * H1); o.gc1a = a.take(G * H1); o.gh1b = a.take(G * H1); o.gc1b = a.take(G * H1);
+  o.gz = a.take(G * 2 * C); o.gg2 = a.take(G * 4 * H2);
+  o.gh2a = a.take(G * H2); o.gc2a = a.take(G * H2); o.gh2b = a.take(G * H2); o.gc2b = a.take(G * H2);
+  o.glogits = a.take(G * ldV); o.gprob = a.take(G); o.gcs = a.take(G * 16); o.gclp = a.take(G * 16); o.gss = a.take(G); o.gslp = a.take(G);
+  o.glpa = a.take(G * ML); o.glpb = a.take(G * ML); o.goprob = a.take(G); o.golp = a.take(G * ML);
+  a.cap = a.used;
+  CK(cudaMalloc(&a.f, a.cap * 4));
+  CK(cudaMemset(a.f, 0, a.cap * 4));
+  if (h->bf16mode) {
+    CK(cudaMalloc(&a.hi, a.cap * 2)); CK(cudaMalloc(&a.lo, a.cap * 2));
+    CK(cudaMemset(a.hi, 0, a.cap * 2)); CK(cudaMemset(a.lo, 0, a.cap * 2));
+  }
+  CK(cudaMalloc(&h->d_tok_in, R * 4)); CK(cudaMalloc(&h->d_tok_tgt, R * 4)); CK(cudaMalloc(&h->d_rows, B * 4));
+  CK(cudaMallocHost(&h->h_stage, (2 * R + B) * 4));
+  CK(cudaMalloc(&h->d_sc, sizeof(StepScalars))); CK(cudaMallocHost(&h->h_sc, sizeof(StepScalars)));
+  memset(h->h_sc, 0, sizeof(StepScalars));
+  CK(cudaMalloc(&h->d_loss, 8)); CK(cudaMallocHost(&h->h_loss, 8));
+  CK(cudaMalloc(&h->g_last, G * 4)); CK(cudaMalloc(&h->g_ctok, G * 16 * 4)); CK(cudaMalloc(&h->g_stok, G * 4)); CK(cudaMalloc(&h->g_spar, G * 4));
+  CK(cudaMalloc(&h->g_hista, G * ML * 4)); CK(cudaMalloc(&h->g_histb, G * ML * 4)); CK(cudaMalloc(&h->g_done, G * 4));
+  CK(cudaMalloc(&h->g_ndone, 4)); CK(cudaMalloc(&h->g_olen, G * 4)); CK(cudaMalloc(&h->g_rows, G * 4)); CK(cudaMalloc(&h->g_otok, G * ML * 8));
+  CK(cudaMallocHost(&h->h_ndone, 4));
+  h->l2_n = (size_t)64 << 20;  // 256 MiB of floats > 126 MB L2
+  CK(cudaMalloc(&h->l2_scratch, h->l2_n * 4));
+  CK(cudaDeviceSynchronize());
+  return LRCN_OK;
+}
+
+extern "C" int lrcn_create(const lrcn_config* cfg, lrcn_handle** out) {
+  if (!cfg || !out) return fail(LRCN_ERR_ARG, "null argument");
+  if (cfg->embed <= 0 || cfg->hidden1 <= 0 || cfg->hidden2 <= 0 || cfg->vocab < 4 || cfg->max_batch <= 0 || cfg->max_len <= 0)
+    return fail(LRCN_ERR_ARG, "non-positive dimension in config");
+  if (cfg->hidden2 % 2) return fail(LRCN_ERR_ARG, "hidden2 must be even (lrcn.jl:496-498,545-546: [x*Wf, x_cnn] must be H2 wide)");
+  if (cfg->max_len > 60) return fail(LRCN_ERR_ARG, "max_len > 60 unsupported");
+  if (cfg->precision != LRCN_PREC_FP32 && cfg->precision != LRCN_PREC_BF16X3) return fail(LRCN_ERR_ARG, "unknown precision %d", cfg->precision);
+  if (cfg->precision == LRCN_PREC_BF16X3 && (cfg->embed % 8 || cfg->hidden1 % 8 || cfg->hidden2 % 8))
+    return fail(LRCN_ERR_ARG, "precision bf16x3 needs embed, hidden1, hidden2 to be multiples of 8 (TMA 16-byte pitch); use LRCN_PREC_FP32");
+  lrcn_handle* h = new lrcn_handle();
+  int rc = create_impl(cfg, h);
+  if (rc != LRCN_OK) { std::string keep = g_err; lrcn_destroy(h); g_err = keep; return rc; }
+  *out = h;
+  return LRCN_OK;
+}
+
+// ------------------------------------------------------------------------------------------ weights
+extern "C" int lrcn_param_shape(const lrcn_handle* h, int idx, int64_t* rows, int64_t* cols) {
+  if (!h || idx < 1 || idx > 9 || !rows || !cols) return fail(LRCN_ERR_ARG, "bad param index %d", idx);
+  *rows = h->rows[idx - 1]; *cols = h->cols[idx - 1];
+  return LRCN_OK;
+}
+static int check_shape(lrcn_handle* h, int idx, const void* p, int64_t rows, int64_t cols) {
+  if (!h || !p || idx < 1 || idx > 9) return fail(LRCN_ERR_ARG, "bad argument (idx=%d)", idx);
+  if (rows != h->rows[idx - 1] || cols != h->cols[idx - 1])
+    return fail(LRCN_ERR_ARG, "param %d shape mismatch: got %lldx%lld, expected %lldx%lld (lrcn.jl:489-510)", idx, (long long)rows,
+                (long long)cols, (long long)h->rows[idx - 1], (long long)h->cols[idx - 1]);
+  return LRCN_OK;
+}
+// host column-major <-> device arena.  Only Wemb (idx 7) is transposed.
+static int upload(lrcn_handle* h, float* arena, int idx, const float* src) {
+  CK(cudaSetDevice(h->cfg.device));
+  size_t n = h->nel[idx - 1];
+  float* dst = arena + h->off[idx - 1];
+  if (idx == 7) {
+    float* tmp = WS(h, h->o.logits);  // scratch: source memory is [E][V] row-major -> want [V][E]
+    if (n > h->ws.cap - h->o.logits) {
+      std::vector<float> t(n);
+      const int64_t V = h->V, E = h->E;
+      for (int64_t e = 0; e < E; e++) for (int64_t v = 0; v < V; v++) t[v * E + e] = src[e * V + v];
+      CK(cudaMemcpyAsync(dst, t.data(), n * 4, cudaMemcpyHostToDevice, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      return LRCN_OK;
+    }
+    CK(cudaMemcpyAsync(tmp, src, n * 4, cudaMemcpyHostToDevice, h->stream));
+    transpose2d(h->stream, tmp, h->E, h->V, dst);
+  } else {
+    CK(cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return LRCN_OK;
+}
+static int download(lrcn_handle* h, const float* arena, int idx, float* dst) {
+  CK(cudaSetDevice(h->cfg.device));
+  size_t n = h->nel[idx - 1];
+  const float* src = arena + h->off[idx - 1];
+  if (idx == 7) {
+    std::vector<float> t(n);
+    CK(cudaMemcpyAsync(t.data(), src, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const int64_t V = h->V, E = h->E;
+    for (int64_t v = 0; v < V; v++) for (int64_t e = 0; e < E; e++) dst[e * V + v] = t[v * E + e];
+    return LRCN_OK;
+  }
+  CK(cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return LRCN_OK;
+}
+extern "C" int lrcn_set_param(lrcn_handle* h, int idx, const float* p, int64_t rows, int64_t cols) {
+  int rc = check_shape(h, idx, p, rows, cols);
+  if (rc) return rc;
+  g_counter = &h->counter;
+  rc = upload(h, h->w, idx, p);
+  if (rc) return rc;
+  if (h->bf16mode) {
+    size_t o = h->off[idx - 1];
+    split_bf16(h->stream, h->w + o, h->nel[idx - 1], h->w_hi + o, h->w_lo + o);
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return LRCN_OK;
+}
+extern "C" int lrcn_get_param(lrcn_handle* h, int idx, float* p, int64_t rows, int64_t cols) {
+  int rc = check_shape(h, idx, p, rows, cols);
+  return rc ? rc : download(h, h->w, idx, p);
+}
+extern "C" int lrcn_get_grad(lrcn_handle* h, int idx, float* p, int64_t rows, int64_t cols) {
+  int rc = check_shape(h, idx, p, rows, cols);
+  return rc ? rc : download(h, h->g, idx, p);
+}
+extern "C" int lrcn_get_adam_state(lrcn_handle* h, int idx, int which, float* p, int64_t rows, int64_t cols) {
+  int rc = check_shape(h, idx, p, rows, cols);
+  if (rc) return rc;
+  if (which != 0 && which != 1) return fail(LRCN_ERR_ARG, "which must be 0 (m) or 1 (v)");
+  return download(h, which ? h->v : h->m, idx, p);
+}
+extern "C" int lrcn_set_adam_state(lrcn_handle* h, int idx, int which, const float* p, int64_t rows, int64_t cols) {
+  int rc = check_shape(h, idx, p, rows, cols);
+  if (rc) return rc;
+  if (which != 0 && which != 1) return fail(LRCN_ERR_ARG, "which must be 0 (m) or 1 (v)");
+  g_counter = &h->counter;
+  return upload(h, which ? h->v : h->m, idx, p);
+}
+extern "C" int lrcn_get_adam_step(lrcn_handle* h, int64_t* t) { if (!h || !t) return fail(LRCN_ERR_ARG, "null"); *t = h->adam_t; return LRCN_OK; }
+extern "C" int lrcn_set_adam_step(lrcn_handle* h, int64_t t) { if (!h || t < 0) return fail(LRCN_ERR_ARG, "bad step"); h->adam_t = t; return LRCN_OK; }
+
+// ------------------------------------------------------------------------------------------ features
+extern "C" int lrcn_load_features(lrcn_handle* h, int split, const int64_t* ids, const float* feats, int64_t n) {
+  if (!h || !ids || !feats || n <= 0 || split < 0 || split > 1) return fail(LRCN_ERR_ARG, "bad argument to lrcn_load_features");
+  CK(cudaSetDevice(h->cfg.device));
+  Table& t = h->tab[split];
+  if (t.d) { CK(cudaStreamSynchronize(h->stream)); cudaFree(t.d); t.d = nullptr; }
+  t.map.clear();
+  CK(cudaMalloc(&t.d, (size_t)n * LRCN_F_CNN * 4));
+  CK(cudaMemcpy(t.d, feats, (size_t)n * LRCN_F_CNN * 4, cudaMemcpyHostToDevice));
+  t.n = n;
+  t.map.reserve((size_t)n * 2);
+  for (int64_t i = 0; i < n; i++) t.map[ids[i]] = (int)i;
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);  // graphs bake the table pointer
+  h->graphs.clear();
+  return LRCN_OK;
+}
+
+// ------------------------------------------------------------------------------------------ step pieces
+static int stage_host(lrcn_handle* h, int split, const int64_t* image_ids, const int64_t* tokens, int l, int B, int* tok_in, int* tok_tgt,
+                      int* rows) {
+  if (!h || !image_ids || (!tokens && l > 0)) return fail(LRCN_ERR_ARG, "null argument");
+  if (B <= 0 || B > h->cfg.max_batch) return fail(LRCN_ERR_ARG, "B=%d outside [1,%d]", B, h->cfg.max_batch);
+  if (l < 0 || l > h->cfg.max_len) return fail(LRCN_ERR_ARG, "l=%d outside [0,%d]", l, h->cfg.max_len);
+  if (split < 0 || split > 1 || !h->tab[split].d) return fail(LRCN_ERR_STATE, "no features loaded for split %d", split);
+  const int T = l + 1;
+  for (int i = 0; i < B; i++) tok_in[i] = 1;  // bos (0-based 1)                      lrcn.jl:556
+  for (int t = 0; t < l; t++)
+    for (int i = 0; i < B; i++) {
+      int64_t tk = tokens[(size_t)t * B + i];
+      if (tk < 1 || tk > h->V) return fail(LRCN_ERR_ARG, "token %lld at (t=%d,i=%d) outside [1,%d]", (long long)tk, t, i, h->V);
+      tok_in[(size_t)(t + 1) * B + i] = (int)tk - 1;  // next input                   lrcn.jl:569
+      tok_tgt[(size_t)t * B + i] = (int)tk - 1;       // target of step t            lrcn.jl:563-566
+    }
+  for (int i = 0; i < B; i++) tok_tgt[(size_t)(T - 1) * B + i] = 0;  // eos           lrcn.jl:572-577
+  const Table& tb = h->tab[split];
+  for (int i = 0; i < B; i++) {
+    auto it = tb.map.find(image_ids[i]);
+    if (it == tb.map.end()) return fail(LRCN_ERR_MISSING, "missing features for image id %lld (lrcn.jl:602-605)", (long long)image_ids[i]);
+    rows[i] = it->second;
+  }
+  return LRCN_OK;
+}
+
+static void enqueue_forward(lrcn_handle* h, int split, int B, int l, bool train) {
+  const int T = l + 1, R = T * B, E = h->E, H1 = h->H1, H2 = h->H2, C = h->C, V = h->V, ldV = h->ldV, ldv = h->ldv;
+  const Workspace& o = h->o;
+  cudaStream_t s = h->stream;
+  float *X = WS(h, o.X), *v = WS(h, o.v), *Eall = WS(h, o.Eall), *acts1 = WS(h, o.acts1), *h1 = WS(h, o.h1), *c1 = WS(h, o.c1);
+  float *Z = WS(h, o.Z), *acts2 = WS(h, o.acts2), *h2 = WS(h, o.h2), *c2 = WS(h, o.c2), *logits = WS(h, o.logits);
+  gather_features(s, h->tab[split].d, h->d_rows, B, X);
+  split_ws(h, X, (size_t)B * LRCN_F_CNN);
+  gemm(h, true, true, B, C, LRCN_F_CNN, X, LRCN_F_CNN, Wp(h, 6), LRCN_F_CNN, v, ldv, false, nullptr);  // input*Wcnn  lrcn.jl:558
+  gather_embed(s, Wp(h, 7), h->d_tok_in, R, E, Eall, h->d_sc, train);
+  split_ws(h, Eall, (size_t)R * E);
+  gemm(h, true, true, R, 4 * H1, E, Eall, E, Wp(h, 1), E + H1, acts1, 4 * H1, false, Wp(h, 2));         // x-part of layer 1, all t
+  for (int t = 0; t < T; t++) {
+    float* g = acts1 + (size_t)t * B * 4 * H1;
+    if (t > 0) gemm(h, true, true, B, 4 * H1, H1, h1 + (size_t)t * B * H1, H1, Wp(h, 1) + E, E + H1, g, 4 * H1, true, nullptr);
+    lstm_cell_fwd(s, g, c1 + (size_t)t * B * H1, c1 + (size_t)(t + 1) * B * H1, h1 + (size_t)(t + 1) * B * H1, B, H1);
+    split_ws(h, h1 + (size_t)(t + 1) * B * H1, (size_t)B * H1);
+  }
+  gemm(h, true, true, R, C, H1, h1 + (size_t)B * H1, H1, Wp(h, 5), H1, Z, 2 * C, false, nullptr);         // x*w[end-4]  lrcn.jl:545
+  z_finish(s, Z, v, R, B, C, h->d_sc, train);  // hcat(x,x_cnn) + dropout                                    lrcn.jl:546-547
+  split_ws(h, Z, (size_t)R * 2 * C);
+  gemm(h, true, true, R, 4 * H2, 2 * C, Z, 2 * C, Wp(h, 3), 2 * H2, acts2, 4 * H2, false, Wp(h, 4));
+  for (int t = 0; t < T; t++) {
+    float* g = acts2 + (size_t)t * B * 4 * H2;
+    if (t > 0) gemm(h, true, true, B, 4 * H2, H2, h2 + (size_t)t * B * H2, H2, Wp(h, 3) + 2 * C, 2 * H2, g, 4 * H2, true, nullptr);
+    lstm_cell_fwd(s, g, c2 + (size_t)t * B * H2, c2 + (size_t)(t + 1) * B * H2, h2 + (size_t)(t + 1) * B * H2, B, H2);
+    split_ws(h, h2 + (size_t)(t + 1) * B * H2, (size_t)B * H2);
+  }
+  gemm(h, true, true, R, V, H2, h2 + (size_t)B * H2, H2, Wp(h, 8), H2, logits, ldV, false, Wp(h, 9));      // x*w[end-1] .+ w[end]  lrcn.jl:550
+  softmax_ce(s, logits, ldV, R, V, h->d_tok_tgt, WS(h, o.rowlp), h->d_sc, train);                          // logp + gather  lrcn.jl:562-567
+  reduce_sum_double(s, WS(h, o.rowlp), R, h->d_loss);
+}
+
+static void enqueue_backward_seg(lrcn_handle* h, int B, int l, bool train, int seg) {
+  const int T = l + 1, R = T * B, E = h->E, H1 = h->H1, H2 = h->H2, C = h->C, V = h->V, ldV = h->ldV, ldv = h->ldv;
+  const Workspace& o = h->o;
+  cudaStream_t s = h->stream;
+  float *X = WS(h, o.X), *Eall = WS(h, o.Eall), *acts1 = WS(h, o.acts1), *h1 = WS(h, o.h1), *c1 = WS(h, o.c1);
+  float *Z = WS(h, o.Z), *dZ = WS(h, o.dZ), *acts2 = WS(h, o.acts2), *h2 = WS(h, o.h2), *c2 = WS(h, o.c2), *dA = WS(h, o.logits);
+  float *dh2 = WS(h, o.dh2), *dh1 = WS(h, o.dh1), *dv = WS(h, o.dv), *dE = WS(h, o.dE);
+  if (seg == 1) {
+    split_ws(h, dA, (size_t)R * ldV);
+    gemm(h, false, false, V, H2, R, dA, ldV, h2 + (size_t)B * H2, H2, Gp(h, 8), H2, false, nullptr);      // dWout = h2' * dA
+    colsum(s, dA, ldV, R, V, Gp(h, 9), false);                                                              // dbout
+    gemm(h, true, false, R, H2, V, dA, ldV, Wp(h, 8), H2, dh2, H2, false, nullptr);                        // dh2 = dA * Wout'
+  } else if (seg == 2) {
+    float *dhrec = WS(h, o.dhrec2), *dc = WS(h, o.dc2);
+    for (int t = T - 1; t >= 0; t--) {
+      float* g = acts2 + (size_t)t * B * 4 * H2;
+      lstm_cell_bwd(s, g, c2 + (size_t)t * B * H2, c2 + (size_t)(t + 1) * B * H2, dh2 + (size_t)t * B * H2, dhrec, dc, t == T - 1, B, H2);
+      split_ws(h, g, (size_t)B * 4 * H2);
+      if (t > 0) gemm(h, true, false, B, H2, 4 * H2, g, 4 * H2, Wp(h, 3) + 2 * C, 2 * H2, dhrec, H2, false, nullptr);
+    }
+    gemm(h, false, false, 4 * H2, 2 * C, R, acts2, 4 * H2, Z, 2 * C, Gp(h, 3), 2 * H2, false, nullptr);          // dW2[:, x-part]
+    gemm(h, false, false, 4 * H2, H2, R, acts2, 4 * H2, h2, H2, Gp(h, 3) + 2 * C, 2 * H2, false, nullptr);       // dW2[:, h-part] (slot 0 = 0)
+    colsum(s, acts2, 4 * H2, R, 4 * H2, Gp(h, 4), false);
+    gemm(h, true, false, R, 2 * C, 4 * H2, acts2, 4 * H2, Wp(h, 3), 2 * H2, dZ, 2 * C, false, nullptr);
+    dz_finish(s, dZ, dv, T, B, C, h->d_sc, train);
+    split_ws(h, dZ, (size_t)R * 2 * C);
+    split_ws(h, dv, (size_t)B * ldv);
+    gemm(h, false, false, C, H1, R, dZ, 2 * C, h1 + (size_t)B * H1, H1, Gp(h, 5), H1, false, nullptr);            // dWf
+    gemm(h, true, false, R, H1, C, dZ, 2 * C, Wp(h, 5), H1, dh1, H1, false, nullptr);                             // dh1 = dq * Wf'
+    gemm(h, false, false, C, LRCN_F_CNN, B, dv, ldv, X, LRCN_F_CNN, Gp(h, 6), LRCN_F_CNN, false, nullptr);        // dWcnn = X' * dv
+  } else {
+    float *dhrec = WS(h, o.dhrec1), *dc = WS(h, o.dc1);
+    for (int t = T - 1; t >= 0; t--) {
+      float* g = acts1 + (size_t)t * B * 4 * H1;
+      lstm_cell_bwd(s, g, c1 + (size_t)t * B * H1, c1 + (size_t)(t + 1) * B * H1, dh1 + (size_t)t * B * H1, dhrec, dc, t == T - 1, B, H1);
+      split_ws(h, g, (size_t)B * 4 * H1);
+      if (t > 0) gemm(h, true, false, B, H1, 4 * H1, g, 4 * H1, Wp(h, 1) + E, E + H1, dhrec, H1, false, nullptr);
+    }
+    gemm(h, false, false, 4 * H1, E, R, acts1, 4 * H1, Eall, E, Gp(h, 1), E + H1, false, nullptr);
+    gemm(h, false, false, 4 * H1, H1, R, acts1, 4 * H1, h1, H1, Gp(h, 1) + E, E + H1, false, nullptr);
+    colsum(s, acts1, 4 * H1, R, 4 * H1, Gp(h, 2), false);
+    gemm(h, true, false, R, E, 4 * H1, acts1, 4 * H1, Wp(h, 1), E + H1, dE, E, false, nullptr);
+    cudaMemsetAsync(Gp(h, 7), 0, h->nel[6] * 4, s);
+    scatter_add_embed(s, Gp(h, 7), h->d_tok_in, dE, R, E, h->d_sc, train);                                         // adjoint of Wemb[idx,:]
+  }
+}
+
+static void enqueue_adam(lrcn_handle* h) {
+  adam_flat(h->stream, h->w, h->g, h->m, h->v, h->P, h->d_sc, h->w_hi, h->w_lo);
+}
+
+// run `fn` directly or as a cached CUDA graph keyed by (kind, B, l, flags)
+template <class F>
+static int run_cached(lrcn_handle* h, std::tuple<int, int, int, int> key, F fn) {
+  g_counter = &h->counter;
+  try {
+    if (!h->cfg.use_graphs) { fn(); CK(cudaPeekAtLastError()); return LRCN_OK; }
+    auto it = h->graphs.find(key);
+    if (it == h->graphs.end()) {
+      cudaGraph_t graph = nullptr;
+      long long before = h->counter.n;
+      CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      fn();
+      cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+      if (e != cudaSuccess) return fail(LRCN_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+      long long launches = h->counter.n - before;
+      h->counter.n = before;
+      cudaGraphExec_t exec = nullptr;
+      e = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) return fail(LRCN_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+      it = h->graphs.emplace(key, exec).first;
+      h->graph_launches[key] = launches;
+    }
+    CK(cudaGraphLaunch(it->second, h->stream));
+    h->counter.n += h->graph_launches[key];
+  } catch (GemmFail& f) {
+    cudaGraph_t junk = nullptr;
+    cudaStreamCaptureStatus st;
+    if (cudaStreamIsCapturing(h->stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) { cudaStreamEndCapture(h->stream, &junk); if (junk) cudaGraphDestroy(junk); }
+    return fail(LRCN_ERR_CUDA, "%s", f.msg.c_str());
+  }
+  return LRCN_OK;
+}
+
+static void fill_scalars(lrcn_handle* h, int B, int l, float pdrop, uint64_t seed, bool bump_adam) {
+  StepScalars* sc = h->h_sc;
+  const double ntok = (double)B * (l + 1) * h->nranks;
+  sc->inv_ntok = (float)(1.0 / ntok);
+  sc->pdrop = pdrop;
+  sc->keep_scale = pdrop > 0.f ? 1.0f / (1.0f - pdrop) : 1.0f;
+  sc->drop_thresh = pdrop > 0.f ? (uint32_t)((double)pdrop * 16777216.0) : 0u;
+  sc->seed = seed;
+  if (bump_adam) h->adam_t += 1;
+  const int64_t t = h->adam_t > 0 ? h->adam_t : 1;
+  sc->adam_d1 = (float)(1.0 - pow((double)h->cfg.beta1, (double)t));
+  sc->adam_d2 = (float)(1.0 - pow((double)h->cfg.beta2, (double)t));
+  sc->lr = h->cfg.lr; sc->beta1 = h->cfg.beta1; sc->beta2 = h->cfg.beta2; sc->eps = h->cfg.eps;
+  sc->grad_scale = 1.0f;
+}
+
+static int nccl_check(int r, const char* what) {
+  if (r == 0) return LRCN_OK;
+  NcclApi* n = nccl_api();
+  return fail(LRCN_ERR_NCCL, "%s failed: %s", what, n && n->GetErrorString ? n->GetErrorString(r) : "nccl error");
+}
+
+// forward (+ backward (+ adam)) on the tokens currently in d_tok_in/d_tok_tgt/d_rows
+static int run_step(lrcn_handle* h, int split, int B, int l, float pdrop, uint64_t seed, int mode /*0 loss,1 grad,2 train*/) {
+  CK(cudaSetDevice(h->cfg.device));
+  const bool train = mode >= 1;
+  const bool drop = train && pdrop > 0.f;
+  fill_scalars(h, B, l, train ? pdrop : 0.f, seed, mode == 2);
+  CK(cudaMemcpyAsync(h->d_sc, h->h_sc, sizeof(StepScalars), cudaMemcpyHostToDevice, h->stream));
+  h->last_B = B; h->last_l = l;
+  const int fl = (split << 1) | (drop ? 1 : 0);
+  int rc;
+  if (mode == 0) {
+    return run_cached(h, std::make_tuple(0, B, l, fl), [&] { enqueue_forward(h, split, B, l, false); });
+  }
+  if (h->nranks == 1) {
+    return run_cached(h, std::make_tuple(mode == 2 ? 2 : 1, B, l, fl), [&] {
+      enqueue_forward(h, split, B, l, true);
+      for (int seg = 1; seg <= 3; seg++) enqueue_backward_seg(h, B, l, true, seg);
+      if (mode == 2) enqueue_adam(h);
+    });
+  }
+  // data-parallel: bucketed allreduce on the comm stream, overlapped with the remaining backward segments
+  NcclApi* n = nccl_api();
+  rc = run_cached(h, std::make_tuple(10, B, l, fl), [&] { enqueue_forward(h, split, B, l, true); enqueue_backward_seg(h, B, l, true, 1); });
+  if (rc) return rc;
+  for (int seg = 1; seg <= 3; seg++) {
+    CK(cudaEventRecord(h->ev_seg[seg - 1], h->stream));
+    CK(cudaStreamWaitEvent(h->comm_stream, h->ev_seg[seg - 1], 0));
+    float* gb = h->g + h->bucket_off[seg - 1];
+    size_t cnt = h->bucket_off[seg] - h->bucket_off[seg - 1];
+    if (seg == 3) { rc = nccl_check(n->GroupStart(), "ncclGroupStart"); if (rc) return rc; }
+    rc = nccl_check(n->AllReduce(gb, gb, cnt, NCCL_FLOAT32, NCCL_SUM, h->comm, h->comm_stream), "ncclAllReduce(grad bucket)");
+    if (rc) return rc;
+    if (seg == 3) {
+      rc = nccl_check(n->AllReduce(h->d_loss, h->d_loss, 1, NCCL_FLOAT64, NCCL_SUM, h->comm, h->comm_stream), "ncclAllReduce(loss)");
+      if (rc) return rc;
+      rc = nccl_check(n->GroupEnd(), "ncclGroupEnd");
+      if (rc) return rc;
+    }
+    if (seg < 3) {
+      rc = run_cached(h, std::make_tuple(10 + seg, B, l, fl), [&] { enqueue_backward_seg(h, B, l, true, seg + 1); });
+      if (rc) return rc;
+    }
+  }
+  CK(cudaEventRecord(h->ev_comm, h->comm_stream));
+  CK(cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+  if (mode == 2) {
+    rc = run_cached(h, std::make_tuple(14, 0, 0, 0), [&] { enqueue_adam(h); });
+    if (rc) return rc;
+  }
+  return LRCN_OK;
+}
+
+static int finish_loss(lrcn_handle* h, int B, int l, double* total_out) {
+  CK(cudaMemcpyAsync(h->h_loss, h->d_loss, 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *total_out = *h->h_loss;
+  return LRCN_OK;
+}
+
+static int stage_current(lrcn_handle* h, int split, const int64_t* image_ids, const int64_t* tokens, int l, int B) {
+  const size_t R = (size_t)(l + 1) * B;
+  int* tin = h->h_stage;
+  int* ttg = h->h_stage + R;
+  int* rows = h->h_stage + 2 * R;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));  // pinned staging buffer is reused
+  int rc = stage_host(h, split, image_ids, tokens, l, B, tin, ttg, rows);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->d_tok_in, tin, R * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_tok_tgt, ttg, R * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_rows, rows, (size_t)B * 4, cudaMemcpyHostToDevice, h->stream));
+  return LRCN_OK;
+}
+
+extern "C" int lrcn_loss(lrcn_handle* h, int split, const int64_t* image_ids, const int64_t* tokens, int l, int B, double* sum_logp_out,
+                         int64_t* count_out) {
+  int rc = stage_current(h, split, image_ids, tokens, l, B);
+  if (rc) return rc;
+  rc = run_step(h, split, B, l, 0.f, 0, 0);
+  if (rc) return rc;
+  double total;
+  rc = finish_loss(h, B, l, &total);
+  if (rc) return rc;
+  if (sum_logp_out) *sum_logp_out = total;
+  if (count_out) *count_out = (int64_t)B * (l + 1);
+  return LRCN_OK;
+}
+extern "C" int lrcn_grad(lrcn_handle* h, int split, const int64_t* image_ids, const int64_t* tokens, int l, int B, float pdrop, uint64_t seed,
+                         double* loss_out) {
+  if (pdrop < 0.f || pdrop >= 1.f) return fail(LRCN_ERR_ARG, "pdrop must be in [0,1)");
+  int rc = stage_current(h, split, image_ids, tokens, l, B);
+  if (rc) return rc;
+  rc = run_step(h, split, B, l, pdrop, seed, 1);
+  if (rc) return rc;
+  double total;
+  rc = finish_loss(h, B, l, &total);
+  if (rc) return rc;
+  if (loss_out) *loss_out = -total / ((double)B * (l + 1) * h->nranks);
+  return LRCN_OK;
+}
+extern "C" int lrcn_train_step(lrcn_handle* h, int split, const int64_t* image_ids, const int64_t* tokens, int l, int B, float pdrop,
+                               uint64_t seed, double* loss_out) {
+  if (pdrop < 0.f || pdrop >= 1.f) return fail(LRCN_ERR_ARG, "pdrop must be in [0,1)");
+  int rc = stage_current(h, split, image_ids, tokens, l, B);
+  if (rc) return rc;
+  rc = run_step(h, split, B, l, pdrop, seed, 2);
+  if (rc) return rc;
+  double total;
+  rc = finish_loss(h, B, l, &total);
+  if (rc) return rc;
+  if (loss_out) *loss_out = -total / ((double)B * (l + 1) * h->nranks);
+  return LRCN_OK;
+}
+extern "C" int lrcn_adam_update(lrcn_handle* h) {
+  if (!h) return fail(LRCN_ERR_ARG, "null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  fill_scalars(h, 1, 0, 0.f, 0, true);
+  CK(cudaMemcpyAsync(h->d_sc, h->h_sc, sizeof(StepScalars), cudaMemcpyHostToDevice, h->stream));
+  g_counter = &h->counter;
+  enqueue_adam(h);
+  CK(cudaStreamSynchronize(h->stream));
+  return LRCN_OK;
+}
+extern "C" int lrcn_get_token_logps(lrcn_handle* h, float* out, int64_t n) {
+  if (!h || !out) return fail(LRCN_ERR_ARG, "null");
+  int64_t have = (int64_t)h->last_B * (h->last_l + 1);
+  if (n != have) return fail(LRCN_ERR_ARG, "expected %lld values", (long long)have);
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpyAsync(out, WS(h, h->o.rowlp), (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return LRCN_OK;
+}
+
+extern "C" int lrcn_stage_batch(lrcn_handle* h, int slot, int split, const int64_t* image_ids, const int64_t* tokens, int l, int B) {
+  if (!h || slot < 0 || slot >= 64) return fail(LRCN_ERR_ARG, "slot outside [0,64)");
+  const size_t R = (size_t)(l + 1) * B;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  int rc = stage_host(h, split, image_ids, tokens, l, B, h->h_stage, h->h_stage + R, h->h_stage + 2 * R);
+  if (rc) return rc;
+  Slot& s = h->slots[slot];
+  if (!s.tok_in) {
+    const size_t Rmax = (size_t)(h->cfg.max_len + 1) * h->cfg.max_batch;
+    CK(cudaMalloc(&s.tok_in, Rmax * 4)); CK(cudaMalloc(&s.tok_tgt, Rmax * 4)); CK(cudaMalloc(&s.rows, (size_t)h->cfg.max_batch * 4));
+  }
+  s.l = l; s.B = B; s.split = split;
+  CK(cudaMemcpyAsync(s.tok_in, h->h_stage, R * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(s.tok_tgt, h->h_stage + R, R * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(s.rows, h->h_stage + 2 * R, (size_t)B * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return LRCN_OK;
+}
+extern "C" int lrcn_train_step_staged(lrcn_handle* h, int slot, float pdrop, uint64_t seed, double* loss_out) {
+  if (!h || slot < 0 || slot >= 64 || !h->slots[slot].tok_in) return fail(LRCN_ERR_ARG, "slot %d not staged", slot);
+  if (pdrop < 0.f || pdrop >= 1.f) return fail(LRCN_ERR_ARG, "pdrop must be in [0,1)");
+  Slot& s = h->slots[slot];
+  const size_t R = (size_t)(s.l + 1) * s.B;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpyAsync(h->d_tok_in, s.tok_in, R * 4, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_tok_tgt, s.tok_tgt, R * 4, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_rows, s.rows, (size_t)s.B * 4, cudaMemcpyDeviceToDevice, h->stream));
+  int rc = run_step(h, s.split, s.B, s.l, pdrop, seed, 2);
+  if (rc) return rc;
+  if (loss_out) {
+    double total;
+    rc = finish_loss(h, s.B, s.l, &total);
+    if (rc) return rc;
+    *loss_out = -total / ((double)s.B * (s.l + 1) * h->nranks);
+  }
+  return LRCN_OK;
+}
+
+// ------------------------------------------------------------------------------------------ generation
+static void enqueue_beam_step(lrcn_handle* h, int n_img, int K, int step, int nword, int maxlen, bool flip, float* out_lp) {
+  const int R = n_img * K, E = h->E, H1 = h->H1, H2 = h->H2, C = h->C, V = h->V, ldV = h->ldV, ldv = h->ldv;
+  const Workspace& o = h->o;
+  cudaStream_t s = h->stream;
+  float *e = WS(h, o.ge), *g1 = WS(h, o.gg1), *z = WS(h, o.gz), *g2 = WS(h, o.gg2), *logits = WS(h, o.glogits), *v = WS(h, o.gv);
+  // state ping-pong: "a" holds the beams' current states; the cell writes advanced states into "b"; advance gathers b -> a
+  float *h1a = WS(h, o.gh1a), *c1a = WS(h, o.gc1a), *h1b = WS(h, o.gh1b), *c1b = WS(h, o.gc1b);
+  float *h2a = WS(h, o.gh2a), *c2a = WS(h, o.gc2a), *h2b = WS(h, o.gh2b), *c2b = WS(h, o.gc2b);
+  gather_embed(s, Wp(h, 7), h->g_last, R, E, e, h->d_sc, false);                                            // Wemb[tok:tok,:]  lrcn.jl:650
+  split_ws(h, e, (size_t)R * E);
+  gemm(h, true, true, R, 4 * H1, E, e, E, Wp(h, 1), E + H1, g1, 4 * H1, false, Wp(h, 2));
+  if (step > 1) gemm(h, true, true, R, 4 * H1, H1, h1a, H1, Wp(h, 1) + E, E + H1, g1, 4 * H1, true, nullptr);
+  lstm_cell_fwd(s, g1, c1a, c1b, h1b, R, H1);
+  split_ws(h, h1b, (size_t)R * H1);
+  gemm(h, true, true, R, C, H1, h1b, H1, Wp(h, 5), H1, z, 2 * C, false, nullptr);
+  z_finish(s, z, v, R, -K, C, h->d_sc, false);  // negative B => image index = row / K
+  split_ws(h, z, (size_t)R * 2 * C);
+  gemm(h, true, true, R, 4 * H2, 2 * C, z, 2 * C, Wp(h, 3), 2 * H2, g2, 4 * H2, false, Wp(h, 4));
+  if (step > 1) gemm(h, true, true, R, 4 * H2, H2, h2a, H2, Wp(h, 3) + 2 * C, 2 * H2, g2, 4 * H2, true, nullptr);
+  lstm_cell_fwd(s, g2, c2a, c2b, h2b, R, H2);
+  split_ws(h, h2b, (size_t)R * H2);
+  gemm(h, true, true, R, V, H2, h2b, H2, Wp(h, 8), H2, logits, ldV, false, Wp(h, 9));
+  beam_row_topk(s, logits, ldV, R, V, K, WS(h, o.gprob), h->g_ctok, WS(h, o.gcs), WS(h, o.gclp));             // lrcn.jl:652-661
+  beam_select(s, h->g_ctok, WS(h, o.gcs), WS(h, o.gclp), n_img, K, step == 1, h->g_stok, h->g_spar, WS(h, o.gss), WS(h, o.gslp));  // :667-668
+  BeamAdvanceArgs a;
+  a.n_img = n_img; a.K = K; a.H1 = H1; a.H2 = H2; a.maxlen = maxlen; a.step = step; a.nword = nword;
+  a.sel_tok = h->g_stok; a.sel_parent = h->g_spar; a.sel_score = WS(h, o.gss); a.sel_lp = WS(h, o.gslp);
+  a.h1_in = h1b; a.c1_in = c1b; a.h2_in = h2b; a.c2_in = c2b; a.h1_out = h1a; a.c1_out = c1a; a.h2_out = h2a; a.c2_out = c2a;
+  a.hist_in = flip ? h->g_histb : h->g_hista; a.hist_out = flip ? h->g_hista : h->g_histb;
+  a.lp_in = flip ? WS(h, o.glpb) : WS(h, o.glpa); a.lp_out = flip ? WS(h, o.glpa) : WS(h, o.glpb);
+  a.prob = WS(h, o.gprob); a.last_tok = h->g_last; a.done = h->g_done; a.n_done = h->g_ndone;
+  a.out_tokens = h->g_otok; a.out_len = h->g_olen; a.out_prob = WS(h, o.goprob); a.out_lp = out_lp;
+  beam_advance(s, a);                                                                                         // lrcn.jl:670-677
+}
+
+__global__ void beam_init_kernel(int R, int maxlen, float* prob, int* last, int* hist, float* lp, int* done, int* n_done, int n_img) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r == 0) *n_done = 0;
+  if (r < n_img) done[r] = 0;
+  if (r >= R) return;
+  prob[r] = 1.0f;  // (bos, 1.0)  lrcn.jl:627
+  last[r] = 1;     // bos, 0-based
+  hist[(size_t)r * maxlen] = 1;
+  lp[(size_t)r * maxlen] = 0.f;
+}
+
+extern "C" int lrcn_beam_search(lrcn_handle* h, int split, const int64_t* image_ids, int64_t n, int K, int nword, int64_t* tokens_out,
+                                int32_t* len_out, float* prob_out, float* logp_out) {
+  if (!h || !image_ids || !tokens_out || !len_out || !prob_out || n <= 0) return fail(LRCN_ERR_ARG, "bad argument to lrcn_beam_search");
+  if (K < 1 || K > 11) return fail(LRCN_ERR_ARG, "beam_width %d outside [1,11]", K);
+  if (nword < 1 || nword + 2 > 64) return fail(LRCN_ERR_ARG, "nword %d outside [1,62]", nword);
+  if (split < 0 || split > 1 || !h->tab[split].d) return fail(LRCN_ERR_STATE, "no features loaded for split %d", split);
+  if (K > h->cfg.max_gen_rows) return fail(LRCN_ERR_ARG, "max_gen_rows %d < beam_width", h->cfg.max_gen_rows);
+  CK(cudaSetDevice(h->cfg.device));
+  g_counter = &h->counter;
+  const int maxlen = nword + 2;
+  const int chunk = h->cfg.max_gen_rows / K;
+  const Workspace& o = h->o;
+  const Table& tb = h->tab[split];
+  std::vector<int> rows;
+  std::vector<long long> otok;
+  for (int64_t base = 0; base < n; base += chunk) {
+    const int ni = (int)((n - base) < chunk ? (n - base) : chunk);
+    const int R = ni * K;
+    rows.resize(ni);
+    for (int i = 0; i < ni; i++) {
+      auto it = tb.map.find(image_ids[base + i]);
+      if (it == tb.map.end()) return fail(LRCN_ERR_MISSING, "missing features for image id %lld (lrcn.jl:602-605)", (long long)image_ids[base + i]);
+      rows[i] = it->second;
+    }
+    fill_scalars(h, 1, 0, 0.f, 0, false);
+    CK(cudaMemcpyAsync(h->d_sc, h->h_sc, sizeof(StepScalars), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->g_rows, rows.data(), (size_t)ni * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    try {
+      gather_features(h->stream, tb.d, h->g_rows, ni, WS(h, o.gX));
+      split_ws(h, WS(h, o.gX), (size_t)ni * LRCN_F_CNN);
+      gemm(h, true, true, ni, h->C, LRCN_F_CNN, WS(h, o.gX), LRCN_F_CNN, Wp(h, 6), LRCN_F_CNN, WS(h, o.gv), h->ldv, false, nullptr);  // lrcn.jl:611
+      beam_init_kernel<<<(R + 255) / 256, 256, 0, h->stream>>>(R, maxlen, WS(h, o.gprob), h->g_last, h->g_hista, WS(h, o.glpa), h->g_done, h->g_ndone, ni);
+      h->counter.n++;
+      CK(cudaMemsetAsync(WS(h, o.gc1a), 0, (size_t)R * h->H1 * 4, h->stream));
+      CK(cudaMemsetAsync(WS(h, o.gc2a), 0, (size_t)R * h->H2 * 4, h->stream));
+      bool flip = false;
+      for (int step = 1; step <= nword + 1; step++) {
+        enqueue_beam_step(h, ni, K, step, nword, maxlen, flip, logp_out ? WS(h, o.golp) : nullptr);
+        flip = !flip;
+        CK(cudaMemcpyAsync(h->h_ndone, h->g_ndone, 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (*h->h_ndone >= ni) break;
+      }
+    } catch (GemmFail& f) {
+      return fail(LRCN_ERR_CUDA, "%s", f.msg.c_str());
+    }
+    CK(cudaPeekAtLastError());
+    otok.resize((size_t)ni * maxlen);
+    CK(cudaMemcpyAsync(otok.data(), h->g_otok, (size_t)ni * maxlen * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(len_out + base, h->g_olen, (size_t)ni * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(prob_out + base, WS(h, o.goprob), (size_t)ni * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (logp_out) CK(cudaMemcpyAsync(logp_out + base * (maxlen - 1), WS(h, o.golp), (size_t)ni * (maxlen - 1) * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < ni; i++) {
+      int len = len_out[base + i];
+      for (int j = 0; j < maxlen; j++) tokens_out[(base + i) * maxlen + j] = j < len ? (int64_t)otok[(size_t)i * maxlen + j] : 0;
+    }
+  }
+  return LRCN_OK;
+}
+
+// ------------------------------------------------------------------------------------------ data-parallel group
+extern "C" int lrcn_comm_unique_id(char id[LRCN_COMM_ID_BYTES]) {
+  NcclApi* n = nccl_api();
+  if (!n) return fail(LRCN_ERR_NCCL, "libnccl.so.2 not loadable: %s", dlerror() ? dlerror() : "?");
+  ncclUniqueId u;
+  int rc = nccl_check(n->GetUniqueId(&u), "ncclGetUniqueId");
+  if (rc) return rc;
+  memcpy(id, u.internal, LRCN_COMM_ID_BYTES);
+  return LRCN_OK;
+}
+extern "C" int lrcn_comm_init(lrcn_handle* h, const char id[LRCN_COMM_ID_BYTES], int rank, int nranks) {
+  if (!h || !id || nranks < 1 || rank < 0 || rank >= nranks) return fail(LRCN_ERR_ARG, "bad rank/nranks");
+  NcclApi* n = nccl_api();
+  if (!n) return fail(LRCN_ERR_NCCL, "libnccl.so.2 not loadable");
+  CK(cudaSetDevice(h->cfg.device));
+  ncclUniqueId u;
+  memcpy(u.internal, id, LRCN_COMM_ID_BYTES);
+  int rc = nccl_check(n->CommInitRank(&h->comm, nranks, u, rank), "ncclCommInitRank");
+  if (rc) return rc;
+  h->rank = rank; h->nranks = nranks;
+  return LRCN_OK;
+}
+
+// ------------------------------------------------------------------------------------------ measurement
+extern "C" int lrcn_sync(lrcn_handle* h) {
+  if (!h) return fail(LRCN_ERR_ARG, "null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaStreamSynchronize(h->comm_stream));
+  return LRCN_OK;
+}
+extern "C" int lrcn_timer_start(lrcn_handle* h) {
+  if (!h) return fail(LRCN_ERR_ARG, "null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaEventRecord(h->ev0, h->stream));
+  return LRCN_OK;
+}
+extern "C" int lrcn_timer_stop(lrcn_handle* h, float* ms) {
+  if (!h || !ms) return fail(LRCN_ERR_ARG, "null");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaEventSynchronize(h->ev1));
+  CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return LRCN_OK;
+}
+extern "C" int lrcn_kernel_launches(lrcn_handle* h, int64_t* n) {
+  if (!h || !n) return fail(LRCN_ERR_ARG, "null");
+  *n = h->counter.n;
+  return LRCN_OK;
+}
+extern "C" int lrcn_flush_l2(lrcn_handle* h) {
+  if (!h) return fail(LRCN_ERR_ARG, "null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  fill_l2_scratch(h->stream, h->l2_scratch, h->l2_n, 0.f);
+  return LRCN_OK;
+}
+
+extern "C" int lrcn_time_kernel(lrcn_handle* h, const char* name, int reps, float* avg_ms, double* algo_bytes, double* algo_flops) {
+  if (!h || !name || reps < 1 || !avg_ms) return fail(LRCN_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  g_counter = &h->counter;
+  const int B = h->last_B > 0 ? h->last_B : h->cfg.max_batch, l = h->last_l > 0 ? h->last_l : h->cfg.max_len;
+  const int T = l + 1, R = T * B;
+  const Workspace& o = h->o;
+  double bytes = 0, flops = 0;
+  float total = 0.f;
+  try {
+    for (int i = 0; i < reps; i++) {
+      fill_l2_scratch(h->stream, h->l2_scratch, h->l2_n, 0.f);  // evict L2 between timed launches
+      CK(cudaEventRecord(h->ev0, h->stream));
+      if (!strcmp(name, "adam")) {
+        // algorithmic traffic: read w,g,m,v + write w,m,v = 28 B/param (+4 B/param of bf16 shadows in bf16x3 mode)
+        enqueue_adam(h);
+        bytes = (double)h->P * (h->bf16mode ? 32.0 : 28.0);
+      } else if (!strcmp(name, "vocab_gemm")) {
+        gemm(h, true, true, R, h->V, h->H2, WS(h, o.h2) + (size_t)B * h->H2, h->H2, Wp(h, 8), h->H2, WS(h, o.logits), h->ldV, false, Wp(h, 9));
+        flops = 2.0 * R * h->V * h->H2;
+        bytes = 4.0 * ((double)R * h->H2 + (double)h->V * h->H2 + (double)R * h->V);
+      } else if (!strcmp(name, "gate_gemm")) {
+        gemm(h, true, true, R, 4 * h->H1, h->E, WS(h, o.Eall), h->E, Wp(h, 1), h->E + h->H1, WS(h, o.acts1), 4 * h->H1, false, Wp(h, 2));
+        flops = 2.0 * R * 4 * h->H1 * h->E;
+        bytes = 4.0 * ((double)R * h->E + 4.0 * h->H1 * h->E + (double)R * 4 * h->H1);
+      } else if (!strcmp(name, "gather")) {
+        gather_embed(h->stream, Wp(h, 7), h->d_tok_in, R, h->E, WS(h, o.Eall), h->d_sc, false);
+        bytes = 2.0 * 4.0 * R * h->E;
+      } else if (!strcmp(name, "softmax_ce")) {
+        softmax_ce(h->stream, WS(h, o.logits), h->ldV, R, h->V, h->d_tok_tgt, WS(h, o.rowlp), h->d_sc, true);
+        bytes = 2.0 * 4.0 * R * h->V;
+      } else {
+        return fail(LRCN_ERR_ARG, "unknown kernel family '%s'", name);
+      }
+      CK(cudaEventRecord(h->ev1, h->stream));
+      CK(cudaEventSynchronize(h->ev1));
+      float ms;
+      CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+      total += ms;
+    }
+  } catch (GemmFail& f) {
+    return fail(LRCN_ERR_CUDA, "%s", f.msg.c_str());
+  }
+  *avg_ms = total / reps;
+  if (algo_bytes) *algo_bytes = bytes;
+  if (algo_flops) *algo_flops = flops;
+  return LRCN_OK;
+}
+
+// ------------------------------------------------------------------------------------------ test hooks
+extern "C" int lrcn_test_gemm(lrcn_handle* h, int precision, int a_kmajor, int b_kmajor, int M, int N, int K, const float* A, const float* B,
+                              const float* bias, int beta, float* C) {
+  if (!h || !A || !B || !C || M <= 0 || N <= 0 || K <= 0) return fail(LRCN_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  g_counter = &h->counter;
+  // padded leading dimensions (multiples of 8) so the same buffers serve both kernels
+  const int lda = ((a_kmajor ? K : M) + 7) / 8 * 8, ldb = ((b_kmajor ? K : N) + 7) / 8 * 8;
+  const int ra = a_kmajor ? M : K, rb = b_kmajor ? N : K;
+  const int ca = a_kmajor ? K : M, cb = b_kmajor ? K : N;
+  float *dA = nullptr, *dB = nullptr, *dC = nullptr, *dbias = nullptr;
+  bf16 *ah = nullptr, *al = nullptr, *bh = nullptr, *bl = nullptr;
+  int rc = LRCN_OK;
+  auto cleanup = [&] { for (void* p : {(void*)dA, (void*)dB, (void*)dC, (void*)dbias, (void*)ah, (void*)al, (void*)bh, (void*)bl}) if (p) cudaFree(p); };
+#define CKT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(LRCN_ERR_CUDA, "%s -> %s", #call, cudaGetErrorString(e_)); cleanup(); return rc; } } while (0)
+  const size_t na = ((size_t)ra * lda + 63) / 64 * 64, nb = ((size_t)rb * ldb + 63) / 64 * 64;
+  CKT(cudaMalloc(&dA, na * 4)); CKT(cudaMalloc(&dB, nb * 4)); CKT(cudaMalloc(&dC, (size_t)M * N * 4));
+  CKT(cudaMemset(dA, 0, na * 4)); CKT(cudaMemset(dB, 0, nb * 4));
+  CKT(cudaMemcpy2D(dA, (size_t)lda * 4, A, (size_t)ca * 4, (size_t)ca * 4, ra, cudaMemcpyHostToDevice));
+  CKT(cudaMemcpy2D(dB, (size_t)ldb * 4, B, (size_t)cb * 4, (size_t)cb * 4, rb, cudaMemcpyHostToDevice));
+  CKT(cudaMemcpy(dC, C, (size_t)M * N * 4, cudaMemcpyHostToDevice));
+  if (bias) { CKT(cudaMalloc(&dbias, (size_t)N * 4)); CKT(cudaMemcpy(dbias, bias, (size_t)N * 4, cudaMemcpyHostToDevice)); }
+  if (precision == LRCN_PREC_FP32) {
+    sgemm(h->stream, a_kmajor, b_kmajor, M, N, K, dA, lda, dB, ldb, dC, N, beta != 0, dbias);
+  } else {
+    CKT(cudaMalloc(&ah, na * 2)); CKT(cudaMalloc(&al, na * 2)); CKT(cudaMalloc(&bh, nb * 2)); CKT(cudaMalloc(&bl, nb * 2));
+    split_bf16(h->stream, dA, na, ah, al);
+    split_bf16(h->stream, dB, nb, bh, bl);
+    if (!gemm_bf16x3(h->stream, a_kmajor, b_kmajor, M, N, K, ah, al, lda, bh, bl, ldb, dC, N, beta != 0, dbias, nullptr, nullptr)) {
+      rc = fail(LRCN_ERR_CUDA, "%s", gemm_bf16x3_last_error());
+      cudaStreamSynchronize(h->stream);
+      cleanup();
+      return rc;
+    }
+  }
+  CKT(cudaStreamSynchronize(h->stream));
+  CKT(cudaMemcpy(C, dC, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
+  cleanup();
+  return LRCN_OK;
+}
+
+extern "C" int lrcn_test_beam_select(lrcn_handle* h, const float* probs, const float* parent_prob, int n_images, int K, int V, int first_step,
+                                     int64_t* tok_out, int32_t* parent_out, float* score_out) {
+  if (!h || !probs || !parent_prob || n_images <= 0 || K < 1 || K > 11 || V < K) return fail(LRCN_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  g_counter = &h->counter;
+  const int R = n_images * K;
+  float *dp = nullptr, *dpp = nullptr, *cs = nullptr, *clp = nullptr, *ss = nullptr, *slp = nullptr;
+  int *ct = nullptr, *st = nullptr, *sp = nullptr;
+  int rc = LRCN_OK;
+  auto cleanup = [&] { for (void* p : {(void*)dp, (void*)dpp, (void*)cs, (void*)clp, (void*)ss, (void*)slp, (void*)ct, (void*)st, (void*)sp}) if (p) cudaFree(p); };
+  CKT(cudaMalloc(&dp, (size_t)R * V * 4)); CKT(cudaMalloc(&dpp, (size_t)R * 4)); CKT(cudaMalloc(&cs, (size_t)R * K * 4)); CKT(cudaMalloc(&clp, (size_t)R * K * 4));
+  CKT(cudaMalloc(&ss, (size_t)R * 4)); CKT(cudaMalloc(&slp, (size_t)R * 4)); CKT(cudaMalloc(&ct, (size_t)R * K * 4)); CKT(cudaMalloc(&st, (size_t)R * 4));
+  CKT(cudaMalloc(&sp, (size_t)R * 4));
+  CKT(cudaMemcpy(dp, probs, (size_t)R * V * 4, cudaMemcpyHostToDevice));
+  CKT(cudaMemcpy(dpp, parent_prob, (size_t)R * 4, cudaMemcpyHostToDevice));
+  beam_row_topk_probs(h->stream, dp, V, R, V, K, dpp, ct, cs, clp);
+  beam_select(h->stream, ct, cs, clp, n_images, K, first_step, st, sp, ss, slp);
+  CKT(cudaStreamSynchronize(h->stream));
+  std::vector<int> t(R), p(R);
+  CKT(cudaMemcpy(t.data(), st, (size_t)R * 4, cudaMemcpyDeviceToHost));
+  CKT(cudaMemcpy(p.data(), sp, (size_t)R * 4, cudaMemcpyDeviceToHost));
+  CKT(cudaMemcpy(score_out, ss, (size_t)R * 4, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < R; i++) { tok_out[i] = (int64_t)t[i] + 1; parent_out[i] = p[i]; }
+  cleanup();
+  return LRCN_OK;
+}

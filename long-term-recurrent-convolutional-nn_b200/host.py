@@ -1,0 +1,231 @@
+"""Host-side mirror of the reference's interface for the hot path (lrcn.jl), above the C ABI.
+
+Julia is not installed in the build image, so the host side is written in Python with the
+reference's own function names, argument meaning and error behaviour; the Julia `ccall` shim a
+maintainer would add is julia/lrcn_b200.jl.  Everything numeric happens inside
+liblrcn_b200.so -- this module only marshals the reference's data formats:
+
+  model      : list of 9 column-major Float32 matrices            (initweights, lrcn.jl:489-510)
+  seq        : (sequence, input_ids, lengths) as built by minibatch (lrcn.jl:257-297):
+               sequence[k][j] = token at global time row k, batch slot j (1-based ids),
+               input_ids[b][j] = image id of slot j in batch b, lengths[n] = caption length
+  feats      : dict image id -> 4096 Float32                        (lrcn.jl:121-123)
+"""
+from __future__ import annotations
+
+import sys
+
+import numpy as np
+
+from . import abi, synth
+
+EOS, BOS, UNK = synth.EOS, synth.BOS, synth.UNK
+
+
+class LRCN:
+    """The decoder on one B200.  Replaces the (param, optim, state) triple the reference threads
+    through train1 / average_loss / generate."""
+
+    def __init__(self, hidden, vocab_size, embed, batchsize, max_len=28, precision=abi.PREC_BF16X3, device=0,
+                 max_gen_rows=1024, use_graphs=True):
+        if len(hidden) != 2:
+            raise ValueError("lrcn() hard-wires two LSTM layers (lrcn.jl:540-551): --hidden needs exactly 2 sizes")
+        self.hidden = [int(hidden[0]), int(hidden[1])]
+        self.vocab_size, self.embed, self.batchsize = int(vocab_size), int(embed), int(batchsize)
+        cfg = abi.default_config(embed=self.embed, hidden1=self.hidden[0], hidden2=self.hidden[1], vocab=self.vocab_size,
+                                 max_batch=self.batchsize, max_len=max_len, max_gen_rows=max_gen_rows, device=device,
+                                 precision=precision, use_graphs=1 if use_graphs else 0)
+        self.h = abi.Handle(cfg)
+        self._step = 0
+
+    def close(self):
+        self.h.close()
+
+    # ---- weights (lrcn.jl:86-93, 183-186)
+    def initweights(self, seed=1):
+        """initweights(atype,hidden,vocab,embed) + upload; returns the host copy (list of 9)."""
+        model = synth.initweights(self.hidden, self.vocab_size, self.embed, seed=seed)
+        self.load_model(model)
+        return model
+
+    def load_model(self, model):
+        if len(model) != 9:
+            raise ValueError("model must hold 9 matrices (2*length(hidden)+5, lrcn.jl:492)")
+        self.h.set_model(model)
+
+    def model(self):
+        """Host copy of the 9 matrices, e.g. for save(file,"model",model,...) (lrcn.jl:185,230)."""
+        return self.h.get_model()
+
+    # ---- features (lrcn.jl:121-123)
+    def load_features(self, feats: dict, split=0):
+        ids = np.fromiter(feats.keys(), dtype=np.int64, count=len(feats))
+        mat = np.stack([np.asarray(feats[int(i)], dtype=np.float32).reshape(4096) for i in ids])
+        self.h.load_features(split, ids, mat)
+
+    def load_feature_matrix(self, ids, mat, split=0):
+        self.h.load_features(split, ids, mat)
+
+    # ---- one batch (lrcn.jl:553-583)
+    @staticmethod
+    def _tokens(sequence, rng):
+        rows = [np.asarray(sequence[t], dtype=np.int64) for t in rng]
+        return np.stack(rows) if rows else np.zeros((0, 0), dtype=np.int64)
+
+    def loss(self, input_ids, sequence, rng, split=0):
+        """loss(param,state,input,sequence,range): mean NLL over B*(l+1) tokens."""
+        tok = self._tokens(sequence, rng)
+        if tok.size == 0:
+            tok = np.zeros((0, len(input_ids)), dtype=np.int64)
+        s, n = self.h.loss(split, input_ids, tok)
+        return -s / n
+
+    def lossgradient(self, input_ids, sequence, rng, pdrop=0.0, seed=0, split=0):
+        """lossgradient(param,copy(state),input,sequence,range;pdrop) -> list of 9 gradients."""
+        tok = self._tokens(sequence, rng)
+        self.last_loss = self.h.grad(split, input_ids, tok, pdrop, seed)
+        return [self.h.get_grad(k) for k in range(1, 10)]
+
+    def update(self):
+        """update!(param,gloss,optim) on the gradients held by the library (lrcn.jl:394)."""
+        self.h.adam_update()
+
+    # ---- epoch drivers
+    @staticmethod
+    def _start_indices(lengths, batch_size):
+        starts, index = [], 0
+        for t in range(0, len(lengths), batch_size):  # lrcn.jl:336-342
+            starts.append(index)
+            index += int(lengths[t])
+        return starts
+
+    def train1(self, seq, batch_size=None, pdrop=0.0, shuffle_seed=0, split=0, progress=None):
+        """One epoch of the hot loop lrcn.jl:351-396: shuffled batch order, skip l>28,
+        gradient + Adam per batch.  `lr`/`gclip` are ignored by the reference and so not taken."""
+        sequence, input_ids, lengths = seq
+        batch_size = batch_size or self.batchsize
+        starts = self._start_indices(lengths, batch_size)
+        order = np.arange(0, len(lengths), batch_size)
+        np.random.RandomState(shuffle_seed).shuffle(order)
+        losses = []
+        for t in order:
+            l = int(lengths[t])
+            if l > 28:  # lrcn.jl:353
+                continue
+            b = t // batch_size
+            index = starts[b]
+            tok = self._tokens(sequence, range(index, index + l))
+            self._step += 1
+            losses.append(self.h.train_step(split, input_ids[b], tok, pdrop, self._step))
+            if progress:
+                progress(len(losses), losses[-1])
+        return losses
+
+    def average_loss(self, seq, split=0):
+        """average_loss(param,seq,feats): token-weighted mean NLL, pdrop=0 (lrcn.jl:407-486)."""
+        sequence, input_ids, lengths = seq
+        batch_size = len(sequence[0])
+        starts = self._start_indices(lengths, batch_size)
+        total, count = 0.0, 0
+        for b, t in enumerate(range(0, len(lengths), batch_size)):
+            l = int(lengths[t])
+            if l > 28:
+                continue
+            tok = self._tokens(sequence, range(starts[b], starts[b] + l))
+            s, n = self.h.loss(split, input_ids[b], tok)
+            total += s
+            count += n
+        return -total / count
+
+    # ---- generation (lrcn.jl:585-642)
+    def beam_search(self, image_ids, nword, beam_width, split=1):
+        """Numeric part of generate()+beam_search() for many images; returns
+        (list of token lists incl. bos, fp32 probabilities, per-token log-probs)."""
+        toks, lens, prob, lps = self.h.beam_search(split, image_ids, beam_width, nword)
+        out = [toks[i, :lens[i]].tolist() for i in range(len(lens))]
+        return out, prob, [lps[i, :lens[i] - 1] for i in range(len(lens))]
+
+    def generate(self, input, vocab, nword, beam_width, split=1, out=sys.stdout, in_out=sys.stdout):
+        """generate(param,state,input::Int,vocab,nword,beam_width,val_feats;out,in_out):
+        writes the id line and the caption line exactly like lrcn.jl:600,633-640."""
+        index_to_char = [None] * len(vocab)
+        for k, v in vocab.items():
+            index_to_char[v - 1] = k
+        print(input, file=in_out)
+        try:
+            hyps, _, _ = self.beam_search([input], nword, beam_width, split)
+        except abi.LrcnError as e:
+            if e.code == abi.ERR_MISSING:
+                raise RuntimeError("misssing features!!!!!!") from e  # lrcn.jl:603
+            raise
+        print(caption_text(hyps[0], index_to_char), file=out)
+        return hyps[0]
+
+
+def caption_text(word_indices, index_to_char):
+    """lrcn.jl:633-640: tokens[2:] up to the first eos, each followed by ' ', then '.'."""
+    parts = []
+    for tok in word_indices[1:]:
+        if tok == EOS:
+            break
+        parts.append(index_to_char[tok - 1] + " ")
+    return "".join(parts) + "."
+
+
+# ---- batching (lrcn.jl:257-327) -- integer-only host data prep -----------------
+def delete_unbatchable_captions(caption_dict, batch_size):
+    """delete_unbatchable_captions!(caption_dict,batch_size), lrcn.jl:299-327.  caption_dict is a
+    length-sorted list of ((id, words), length).  Returns the surviving list (new list)."""
+    lengths = [t[1] for t in caption_dict]
+    n = len(lengths)
+    if n == 0:
+        return []
+    limit = n - batch_size + 1
+    max_length = max(lengths)
+    current_length = lengths[0]
+    current_index = 1  # 1-based, as in the reference
+    drop = set()
+    while current_index < limit:
+        if lengths[current_index + batch_size - 2] == current_length:
+            current_index += batch_size
+        else:
+            old_index = current_index
+            current_index = 0
+            while current_index == 0:
+                current_length += 1
+                if current_length > max_length:
+                    break
+                try:
+                    current_index = lengths.index(current_length) + 1  # findfirst
+                except ValueError:
+                    current_index = 0
+            if current_index == 0:  # ran past max_length: everything from old_index on is unbatchable
+                drop.update(range(old_index, n + 1))
+                break
+            drop.update(range(old_index, current_index))
+        if current_index >= limit:
+            drop.update(range(current_index, n + 1))
+            break
+    return [caption_dict[k - 1] for k in range(1, n + 1) if k not in drop]
+
+
+def minibatch(caption_dict, word_to_index, batch_size):
+    """minibatch(caption_dict,word_to_index,batch_size), lrcn.jl:257-297 -> (sequence,input_ids,lengths).
+    Splits with <= 30000 captions are forced to batch_size 10 (lrcn.jl:260-269)."""
+    if len(caption_dict) <= 30000:
+        batch_size = 10
+    caption_dict = delete_unbatchable_captions(caption_dict, batch_size)
+    lengths = [t[1] for t in caption_dict]
+    nbatch = sum(lengths) // batch_size
+    sequence = [np.zeros(batch_size, dtype=np.int64) for _ in range(nbatch)]
+    input_ids = [np.zeros(batch_size, dtype=np.int64) for _ in range(0, len(lengths), batch_size)]
+    index = 0
+    for b, i in enumerate(range(0, len(lengths), batch_size)):
+        l = lengths[i]
+        for j in range(i, i + batch_size):
+            (img_id, words), _ = caption_dict[j]
+            input_ids[b][j - i] = img_id
+            for k in range(l):
+                sequence[index + k][j - i] = word_to_index.get(words[k], UNK)  # lrcn.jl:288
+        index += l
+    return sequence, input_ids, lengths
