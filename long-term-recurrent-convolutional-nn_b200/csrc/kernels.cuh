@@ -37,7 +37,7 @@ void gather_features(cudaStream_t s, const float* table, const int* rows, int B,
 void gather_embed(cudaStream_t s, const float* WembT, const int* tok, int R, int E, float* out,
                   const StepScalars* sc, bool train);
 // Z[r][C+j] = v[r % B][j]; then dropout (site 1) over the whole row of 2C
-void z_finish(cudaStream_t s, float* Z, const float* v, int R, int B, int C, const StepScalars* sc, bool train);
+void z_finish(cudaStream_t s, float* Z, const float* v, int ldv, int R, int B, int C, const StepScalars* sc, bool train);
 // LSTM cell forward for one step: gates (pre-activation, [B][4H], order f,i,o,g) are activated in place
 void lstm_cell_fwd(cudaStream_t s, float* gates, const float* c_prev, float* c_out, float* h_out, int B, int H);
 // LSTM cell backward for one step; gates buffer holds activations and receives dG in place
@@ -50,7 +50,7 @@ void softmax_ce(cudaStream_t s, float* logits, int ld, int R, int V, const int* 
 void reduce_sum_double(cudaStream_t s, const float* x, int n, double* out);
 void colsum(cudaStream_t s, const float* A, int ld, int R, int N, float* out, bool accumulate);
 // dZ *= dropout mask (site 1); dv[i][j] = sum_t dZ[(t*B+i)][C+j]
-void dz_finish(cudaStream_t s, float* dZ, float* dv, int T, int B, int C, const StepScalars* sc, bool train);
+void dz_finish(cudaStream_t s, float* dZ, float* dv, int ldv, int T, int B, int C, const StepScalars* sc, bool train);
 // dWembT[tok[r]][:] += dE[r][:] (* dropout mask site 0)
 void scatter_add_embed(cudaStream_t s, float* dWembT, const int* tok, const float* dE, int R, int E,
                        const StepScalars* sc, bool train);

@@ -180,19 +180,19 @@ void gather_embed(cudaStream_t s, const float* WembT, const int* tok, int R, int
   count_launch();
 }
 
-__global__ void z_finish_kernel(float* __restrict__ Z, const float* __restrict__ v, int R, int B, int C,
+__global__ void z_finish_kernel(float* __restrict__ Z, const float* __restrict__ v, int ldv, int R, int B, int C,
                                 const StepScalars* __restrict__ sc, int train) {
   int r = blockIdx.x;
   int i = B > 0 ? r % B : r / (-B);  // B<0: generation, image index = row / beam_width
   float* z = Z + (size_t)r * 2 * C;
   for (int j = threadIdx.x; j < 2 * C; j += blockDim.x) {
-    float x = (j < C) ? z[j] : v[(size_t)i * C + (j - C)];
+    float x = (j < C) ? z[j] : v[(size_t)i * ldv + (j - C)];
     if (train) x *= drop_scale(sc, 1, (uint64_t)r * 2 * C + j);
     z[j] = x;
   }
 }
-void z_finish(cudaStream_t s, float* Z, const float* v, int R, int B, int C, const StepScalars* sc, bool train) {
-  z_finish_kernel<<<R, 128, 0, s>>>(Z, v, R, B, C, sc, train ? 1 : 0);
+void z_finish(cudaStream_t s, float* Z, const float* v, int ldv, int R, int B, int C, const StepScalars* sc, bool train) {
+  z_finish_kernel<<<R, 128, 0, s>>>(Z, v, ldv, R, B, C, sc, train ? 1 : 0);
   count_launch();
 }
 
@@ -359,7 +359,7 @@ void colsum(cudaStream_t s, const float* A, int ld, int R, int N, float* out, bo
   count_launch();
 }
 
-__global__ void dz_finish_kernel(float* __restrict__ dZ, float* __restrict__ dv, int T, int B, int C,
+__global__ void dz_finish_kernel(float* __restrict__ dZ, float* __restrict__ dv, int ldv, int T, int B, int C,
                                  const StepScalars* __restrict__ sc, int train) {
   int i = blockIdx.x;  // batch row
   for (int j = threadIdx.x; j < 2 * C; j += blockDim.x) {
@@ -370,11 +370,11 @@ __global__ void dz_finish_kernel(float* __restrict__ dZ, float* __restrict__ dv,
       if (train) { x *= drop_scale(sc, 1, (uint64_t)r * 2 * C + j); dZ[r * 2 * C + j] = x; }
       acc += x;
     }
-    if (j >= C) dv[(size_t)i * C + (j - C)] = acc;
+    if (j >= C) dv[(size_t)i * ldv + (j - C)] = acc;
   }
 }
-void dz_finish(cudaStream_t s, float* dZ, float* dv, int T, int B, int C, const StepScalars* sc, bool train) {
-  dz_finish_kernel<<<B, 256, 0, s>>>(dZ, dv, T, B, C, sc, train ? 1 : 0);
+void dz_finish(cudaStream_t s, float* dZ, float* dv, int ldv, int T, int B, int C, const StepScalars* sc, bool train) {
+  dz_finish_kernel<<<B, 256, 0, s>>>(dZ, dv, ldv, T, B, C, sc, train ? 1 : 0);
   count_launch();
 }
 

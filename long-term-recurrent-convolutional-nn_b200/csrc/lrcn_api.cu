@@ -476,7 +476,7 @@ static void enqueue_forward(lrcn_handle* h, int split, int B, int l, bool train)
     split_ws(h, h1 + (size_t)(t + 1) * B * H1, (size_t)B * H1);
   }
   gemm(h, true, true, R, C, H1, h1 + (size_t)B * H1, H1, Wp(h, 5), H1, Z, 2 * C, false, nullptr);         // x*w[end-4]  lrcn.jl:545
-  z_finish(s, Z, v, R, B, C, h->d_sc, train);  // hcat(x,x_cnn) + dropout                                    lrcn.jl:546-547
+  z_finish(s, Z, v, ldv, R, B, C, h->d_sc, train);  // hcat(x,x_cnn) + dropout                                    lrcn.jl:546-547
   split_ws(h, Z, (size_t)R * 2 * C);
   gemm(h, true, true, R, 4 * H2, 2 * C, Z, 2 * C, Wp(h, 3), 2 * H2, acts2, 4 * H2, false, Wp(h, 4));
   for (int t = 0; t < T; t++) {
@@ -514,7 +514,7 @@ static void enqueue_backward_seg(lrcn_handle* h, int B, int l, bool train, int s
     gemm(h, false, false, 4 * H2, H2, R, acts2, 4 * H2, h2, H2, Gp(h, 3) + 2 * C, 2 * H2, false, nullptr);       // dW2[:, h-part] (slot 0 = 0)
     colsum(s, acts2, 4 * H2, R, 4 * H2, Gp(h, 4), false);
     gemm(h, true, false, R, 2 * C, 4 * H2, acts2, 4 * H2, Wp(h, 3), 2 * H2, dZ, 2 * C, false, nullptr);
-    dz_finish(s, dZ, dv, T, B, C, h->d_sc, train);
+    dz_finish(s, dZ, dv, ldv, T, B, C, h->d_sc, train);
     split_ws(h, dZ, (size_t)R * 2 * C);
     split_ws(h, dv, (size_t)B * ldv);
     gemm(h, false, false, C, H1, R, dZ, 2 * C, h1 + (size_t)B * H1, H1, Gp(h, 5), H1, false, nullptr);            // dWf
@@ -785,7 +785,7 @@ static void enqueue_beam_step(lrcn_handle* h, int n_img, int K, int step, int nw
   lstm_cell_fwd(s, g1, c1a, c1b, h1b, R, H1);
   split_ws(h, h1b, (size_t)R * H1);
   gemm(h, true, true, R, C, H1, h1b, H1, Wp(h, 5), H1, z, 2 * C, false, nullptr);
-  z_finish(s, z, v, R, -K, C, h->d_sc, false);  // negative B => image index = row / K
+  z_finish(s, z, v, ldv, R, -K, C, h->d_sc, false);  // negative B => image index = row / K
   split_ws(h, z, (size_t)R * 2 * C);
   gemm(h, true, true, R, 4 * H2, 2 * C, z, 2 * C, Wp(h, 3), 2 * H2, g2, 4 * H2, false, Wp(h, 4));
   if (step > 1) gemm(h, true, true, R, 4 * H2, H2, h2a, H2, Wp(h, 3) + 2 * C, 2 * H2, g2, 4 * H2, true, nullptr);
@@ -803,6 +803,8 @@ static void enqueue_beam_step(lrcn_handle* h, int n_img, int K, int step, int nw
   a.prob = WS(h, o.gprob); a.last_tok = h->g_last; a.done = h->g_done; a.n_done = h->g_ndone;
   a.out_tokens = h->g_otok; a.out_len = h->g_olen; a.out_prob = WS(h, o.goprob); a.out_lp = out_lp;
   beam_advance(s, a);                                                                                         // lrcn.jl:670-677
+  split_ws(h, h1a, (size_t)R * H1);  // the gathered parent states feed the next step's recurrent GEMMs
+  split_ws(h, h2a, (size_t)R * H2);
 }
 
 __global__ void beam_init_kernel(int R, int maxlen, float* prob, int* last, int* hist, float* lp, int* done, int* n_done, int n_img) {

@@ -101,6 +101,7 @@ CASES = [
     dict(E=8, H1=8, H2=16, V=23, B=3, l=4),        # tiny, ragged tiles everywhere
     dict(E=64, H1=64, H2=64, V=300, B=8, l=5),
     dict(E=128, H1=192, H2=128, V=1111, B=24, l=11, zipf=True),
+    dict(E=40, H1=24, H2=72, V=131, B=5, l=3),      # C = 36 is not a multiple of 8 -> padded ld of v/dv (the coco_2f C=500 case)
 ]
 
 
@@ -201,7 +202,7 @@ def test_adam_kernel_exact_on_given_gradient():
         h.adam_update()
         assert h.get_adam_step() == 7
         for k in range(1, 10):
-            np.testing.assert_allclose(h.get_param(k), ref[k - 1], rtol=2e-6, atol=1e-9)
+            np.testing.assert_allclose(h.get_param(k), ref[k - 1], rtol=2e-6, atol=2e-8)
             np.testing.assert_allclose(h.get_adam_state(k, 0), opt[k - 1].fstm, rtol=2e-6, atol=1e-12)
             np.testing.assert_allclose(h.get_adam_state(k, 1), opt[k - 1].scndm, rtol=2e-6, atol=1e-14)
 
@@ -219,8 +220,9 @@ def test_dropout_is_seeded_and_unbiased(prec):
         b = h.grad(0, img, tok, 0.4, 1)
         gb = h.get_grad(1)
         c = h.grad(0, img, tok, 0.4, 2)
-        assert a == b and np.array_equal(ga, gb)      # same seed -> same masks (forward and backward)
-        assert a != c and a != L0
+        # same seed -> same masks in forward and backward (split-K atomics only reorder fp32 sums)
+        assert abs(a - b) < 1e-6 * abs(a) and relerr(ga, gb) < 1e-5
+        assert abs(a - c) > 1e-4 * abs(a) and abs(a - L0) > 1e-4 * abs(a)
         assert np.isfinite(ga).all()
         with pytest.raises(abi.LrcnError):
             h.grad(0, img, tok, 1.0, 1)
@@ -252,7 +254,7 @@ def test_beam_search_matches_oracle(prec, K):
     E, H1, H2, V, n_img, nword = 64, 64, 64, 200, 24, 12
     model = synth.initweights([H1, H2], V, E, seed=7)
     model = [w * np.float32(6) if w.shape[0] > 1 else w for w in model]
-    model[8][0, O.EOS - 1] = 1.5  # bias eos so that decode lengths vary
+    model[8][0, O.EOS - 1] = 0.65  # bias eos so that decode lengths vary
     feats = synth.features(n_img, seed=9) * np.float32(100)
     ids = np.arange(1, n_img + 1, dtype=np.int64)
     with open_handle(E, H1, H2, V, 4, 3, prec, gen_rows=40) as h:  # 40 rows -> several chunks at K=3,5
@@ -260,6 +262,7 @@ def test_beam_search_matches_oracle(prec, K):
         h.load_features(1, ids, feats)
         toks, lens, prob, lps = h.beam_search(1, ids, K, nword)
     same = 0
+    assert lens.mean() >= 5 and lens.max() > lens.min(), "decodes too short to exercise the recurrent state"
     for i in range(n_img):
         trace = []
         ref_t, ref_p = O.generate(model, feats[i], nword, K, trace=trace)
