@@ -1,10 +1,10 @@
 #!/bin/bash
-# ncu evidence for one bench step (1 GPU only): launch list with device times, then a full capture of the top kernels.
+# ncu evidence (1 GPU only).  (1) launch list with device times of ONE full training step;
+# (2) --set full captures of the hot kernel families launched alone.
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -s ${NCU_SKIP:-900} -c ${NCU_COUNT:-260} --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:gemm_bf16x3 -s 60 -c 2 -o gpurun_out/prof_gemm -f \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_gemm.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:adam_kernel -c 1 -o gpurun_out/prof_adam -f \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_adam.log 2>&1
-ls -la gpurun_out
+PROFILE_STEP=1 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
+    python tools/prof_kernels.py none > gpurun_out/ncu_step.log 2>&1
+ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"gemm_bf16x3|adam_kernel|softmax_ce|gather_embed" \
+    -o gpurun_out/prof_kernels -f python tools/prof_kernels.py > gpurun_out/ncu_kernels.log 2>&1
+tail -8 gpurun_out/ncu_kernels.log
+ls -la gpurun_out | head -30
