@@ -68,7 +68,7 @@ typedef struct {
   int32_t device;       /* CUDA device ordinal */
   int32_t precision;    /* LRCN_PREC_* */
   int32_t use_graphs;   /* 1: replay each (B,l) step shape as a CUDA graph */
-  float lr, beta1, beta2, eps;
+  double lr, beta1, beta2, eps; /* Float64 like Knet's Adam fields: (float)(1-beta) must equal Knet's axpy! scalar */
 } lrcn_config;
 
 LRCN_API int lrcn_abi_version(void);

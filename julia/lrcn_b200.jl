@@ -19,7 +19,7 @@ type Config          # mirrors lrcn_config in include/lrcn_b200.h, field for fie
     embed::Int32; hidden1::Int32; hidden2::Int32; vocab::Int32
     max_batch::Int32; max_len::Int32; max_gen_rows::Int32; device::Int32
     precision::Int32; use_graphs::Int32
-    lr::Float32; beta1::Float32; beta2::Float32; eps::Float32
+    lr::Float64; beta1::Float64; beta2::Float64; eps::Float64
 end
 
 type Net
@@ -32,7 +32,7 @@ check(rc) = rc == 0 ? nothing : error(lasterror())     # reference convention: e
 abi_version() = ccall((:lrcn_abi_version, lib), Cint, ())
 
 function default_config()
-    c = Ref(Config(0,0,0,0,0,0,0,0,0,0,0f0,0f0,0f0,0f0))
+    c = Ref(Config(0,0,0,0,0,0,0,0,0,0,0.0,0.0,0.0,0.0))
     check(ccall((:lrcn_config_default, lib), Cint, (Ptr{Config},), c))
     return c[]
 end

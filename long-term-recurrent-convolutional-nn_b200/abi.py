@@ -25,7 +25,7 @@ class LrcnError(RuntimeError):
 class Config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("embed", "hidden1", "hidden2", "vocab", "max_batch", "max_len",
                                          "max_gen_rows", "device", "precision", "use_graphs")] + \
-               [(n, C.c_float) for n in ("lr", "beta1", "beta2", "eps")]
+               [(n, C.c_double) for n in ("lr", "beta1", "beta2", "eps")]
 
 
 _p = C.POINTER

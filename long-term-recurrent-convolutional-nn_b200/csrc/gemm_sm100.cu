@@ -1,23 +1,28 @@
-// gemm_sm100.cu -- tcgen05 / TMEM / TMA GEMM for sm_100a with error-compensated bf16 splitting.
+// gemm_sm100.cu -- persistent tcgen05 / TMEM / TMA GEMM for sm_100a with error-compensated bf16 splitting.
 //
 //   C[M][N] (fp32) = Aop * Bop,  A = A_hi + A_lo, B = B_hi + B_lo (bf16 pairs, |lo| <= 2^-9 |hi|)
-//   D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi        (3 tcgen05.mma per 16-wide k-step, fp32 TMEM accumulate)
+//   D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi        (3 tcgen05.mma per 16-wide k-step, fp32 TMEM accumulate)
 //
-// which keeps the result within ~2^-16 relative of an fp32 SGEMM: the 1e-4 parity bar of the LRCN
-// hot path (SURVEY.md §7 "hard parts" 1) cannot be met by single-pass bf16 (2.3e-3) or tf32 (2.9e-4).
+// which keeps the result within ~2^-16 relative of an fp32 SGEMM (measured 4.5e-6): the 1e-4 parity bar of the
+// LRCN hot path cannot be met by single-pass bf16 (2.3e-3) or tf32 (2.9e-4) (SURVEY.md §7 hard part 1).
 //
-// Operands are row-major 2-D bf16 tensors; each may be K-major ([MN][K], forward GEMMs, the
-// reference's column-major K x N weights) or MN-major ([K][MN], the data/weight-gradient GEMMs of BPTT),
-// selected by the UMMA instruction-descriptor major bits, so no transposed copies are ever made.
+// Operands are row-major 2-D bf16 tensors, each K-major ([MN][K]: forward GEMMs, the reference's column-major
+// K x N weights as they lie in memory) or MN-major ([K][MN]: the data-/weight-gradient GEMMs of BPTT), selected
+// by the UMMA instruction-descriptor major bits -- no transposed copies are ever made.
 //
-// CTA = 192 threads: warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer (one elected lane),
-// warps 2-5 epilogue (tcgen05.ld of the 4 TMEM lane quadrants).  3-stage smem ring
-// (A_hi,A_lo,B_hi,B_lo tiles of 128x64 bf16, SWIZZLE_128B), mbarrier full/empty pipeline,
-// tcgen05.commit releases stages and signals the epilogue.  Tile 128 x 128 x 64, optional split-K.
+// Persistent kernel, one CTA per SM, 192 threads:
+//   warp 0      TMA producer   (smem ring of {A_hi,A_lo,B_hi,B_lo} stages, SWIZZLE_128B, mbarrier expect_tx)
+//   warp 1      TMEM allocator + MMA issuer (one elected lane; tcgen05.commit frees stages / publishes accumulators)
+//   warps 2-5   epilogue: tcgen05.ld (32x32b.x32) -> per-warp smem transpose -> coalesced float4 global stores
+//               (+bias, +beta*C, optional bf16 hi/lo split of the result, or fp32 atomics under split-K)
+// Two TMEM accumulator stages, so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Tile 128 x BN x 64 with BN = 128 (3 smem stages) or 256 (2 stages).
 #include "kernels.cuh"
-#include <cuda.h>
-#include <stdio.h>
+#include "sm100_ptx.cuh"
+
+#include <stdlib.h>
 #include <string.h>
+
 #include <map>
 #include <mutex>
 #include <string>
@@ -25,272 +30,237 @@
 
 namespace lrcn {
 
+using namespace ptx;
+
 static thread_local std::string g_gemm_err;
 const char* gemm_bf16x3_last_error() { return g_gemm_err.c_str(); }
+void set_sm100_error(const char* msg) { g_gemm_err = msg; }
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
-constexpr int TILE_BYTES = BM * BK * 2;          // 16 KiB per operand tile
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int BM = 128, BK = 64;
+constexpr int A_TILE = BM * BK * 2;  // 16 KiB
 constexpr int NUM_THREADS = 192;
-constexpr uint32_t TMEM_COLS = 128;
+constexpr int EPI_LD = 36;                            // padded row (floats) of the per-warp transpose buffer
+constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;        // 18 KiB for the 4 epilogue warps
 
-// ------------------------------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(done)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return done != 0;
-}
-// bounded wait: a protocol bug must trap (launch failure) instead of hanging the GPU box
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) { printf("lrcn gemm_sm100: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x); __trap(); }
-  }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// smem matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
-// version=1 [46,48), layout_type [61,64) (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
-#define TMEM_LD_32(taddr, v)                                                                                      \
-  asm volatile(                                                                                                   \
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18," \
-      "%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                                               \
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), \
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),      \
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),     \
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                   \
-      : "r"(taddr)                                                                                                \
-      : "memory")
+template <int BN_>
+struct TileCfg {
+  static constexpr int STAGES = BN_ == 128 ? 3 : 2;
+  static constexpr int B_TILE = BN_ * BK * 2;
+  static constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t TMEM_COLS = 2 * BN_;
+};
 
 struct GemmParams {
   int M, N, K;
-  int kb_per_split;  // k-blocks (of BK) per grid.z slice
+  int tiles_m, tiles_n, splits, kb_per_split;
   float* C; int ldc;
   const float* bias;
   int beta;
   __nv_bfloat16* C_hi; __nv_bfloat16* C_lo;
-  int mn_lbo, mn_sbo;  // MN-major descriptor strides (bytes)
 };
 
-template <bool AK, bool BKM>
+template <bool AK, bool BKM, int BN_>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                    const GemmParams p) {
+  using Cfg = TileCfg<BN_>;
+  constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + STAGES * STAGE_BYTES);
-  const uint32_t full_bar0 = smem_u32(bars);                 // STAGES barriers
-  const uint32_t empty_bar0 = smem_u32(bars + STAGES);       // STAGES barriers
-  const uint32_t tmem_full_bar = smem_u32(bars + 2 * STAGES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  float* epi_buf = reinterpret_cast<float*>(smem_al + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + STAGES * Cfg::STAGE_BYTES + EPI_BYTES);
+  const uint32_t full_bar0 = smem_u32(bars);
+  const uint32_t empty_bar0 = smem_u32(bars + STAGES);
+  const uint32_t tfull_bar0 = smem_u32(bars + 2 * STAGES);      // 2 accumulator stages
+  const uint32_t tempty_bar0 = smem_u32(bars + 2 * STAGES + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
   const int num_kb_total = (p.K + BK - 1) / BK;
-  const int kb_begin = blockIdx.z * p.kb_per_split;
-  const int kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
-  const int num_kb = kb_end - kb_begin;
+  const int tiles_mn = p.tiles_m * p.tiles_n;
+  const int total_work = tiles_mn * p.splits;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(full_bar0 + 8 * s, 1); mbar_init(empty_bar0 + 8 * s, 1); }
-    mbar_init(tmem_full_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int a = 0; a < 2; a++) { mbar_init(tfull_bar0 + 8 * a, 1); mbar_init(tempty_bar0 + 8 * a, 4); }
+    mbar_init_fence();
   }
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_lo) : "memory");
+    prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmA_lo); prefetch_tensormap(&tmB_hi); prefetch_tensormap(&tmB_lo);
   }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tcgen05_fence_before();
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(smem_u32(tmem_slot));
+  tc_fence_before();
   __syncthreads();
-  tcgen05_fence_after();
+  tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int i = 0; i < num_kb; i++) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(empty_bar0 + 8 * s, ph ^ 1);
-        const uint32_t full = full_bar0 + 8 * s;
-        mbar_expect_tx(full, STAGE_BYTES);
-        const uint32_t st = smem_base + s * STAGE_BYTES;
-        const int k0 = (kb_begin + i) * BK;
-        if (AK) {  // A tile: [128 m][64 k], inner = k
-          tma_load_2d(st, &tmA_hi, full, k0, m0);
-          tma_load_2d(st + TILE_BYTES, &tmA_lo, full, k0, m0);
-        } else {   // A tile: two boxes [64 k][64 m], inner = m
-          tma_load_2d(st, &tmA_hi, full, m0, k0);
-          tma_load_2d(st + TILE_BYTES / 2, &tmA_hi, full, m0 + 64, k0);
-          tma_load_2d(st + TILE_BYTES, &tmA_lo, full, m0, k0);
-          tma_load_2d(st + TILE_BYTES + TILE_BYTES / 2, &tmA_lo, full, m0 + 64, k0);
-        }
-        if (BKM) {
-          tma_load_2d(st + 2 * TILE_BYTES, &tmB_hi, full, k0, n0);
-          tma_load_2d(st + 3 * TILE_BYTES, &tmB_lo, full, k0, n0);
-        } else {
-          tma_load_2d(st + 2 * TILE_BYTES, &tmB_hi, full, n0, k0);
-          tma_load_2d(st + 2 * TILE_BYTES + TILE_BYTES / 2, &tmB_hi, full, n0 + 64, k0);
-          tma_load_2d(st + 3 * TILE_BYTES, &tmB_lo, full, n0, k0);
-          tma_load_2d(st + 3 * TILE_BYTES + TILE_BYTES / 2, &tmB_lo, full, n0 + 64, k0);
+      int it = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int z = w / tiles_mn, rem = w - z * tiles_mn;
+        const int m0 = (rem % p.tiles_m) * BM, n0 = (rem / p.tiles_m) * BN_;
+        const int kb_begin = z * p.kb_per_split, kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; kb++, it++) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(empty_bar0 + 8 * s, ph ^ 1);
+          const uint32_t full = full_bar0 + 8 * s;
+          mbar_expect_tx(full, Cfg::STAGE_BYTES);
+          const uint32_t sA_hi = smem_base + s * Cfg::STAGE_BYTES, sA_lo = sA_hi + A_TILE;
+          const uint32_t sB_hi = sA_lo + A_TILE, sB_lo = sB_hi + Cfg::B_TILE;
+          const int k0 = kb * BK;
+          if (AK) {  // A tile [128 m][64 k], inner = k
+            tma_load_2d(sA_hi, &tmA_hi, full, k0, m0);
+            tma_load_2d(sA_lo, &tmA_lo, full, k0, m0);
+          } else {   // two boxes [64 k][64 m], inner = m
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+              tma_load_2d(sA_hi + b * 8192, &tmA_hi, full, m0 + 64 * b, k0);
+              tma_load_2d(sA_lo + b * 8192, &tmA_lo, full, m0 + 64 * b, k0);
+            }
+          }
+          if (BKM) {
+            tma_load_2d(sB_hi, &tmB_hi, full, k0, n0);
+            tma_load_2d(sB_lo, &tmB_lo, full, k0, n0);
+          } else {
+#pragma unroll
+            for (int b = 0; b < BN_ / 64; b++) {
+              tma_load_2d(sB_hi + b * 8192, &tmB_hi, full, n0 + 64 * b, k0);
+              tma_load_2d(sB_lo + b * 8192, &tmB_lo, full, n0 + 64 * b, k0);
+            }
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6)=1, a=bf16 [7,10)=1, b=bf16 [10,13)=1,
-      // a_major bit15, b_major bit16 (1 = MN-major), N>>3 [17,23), M>>4 [24,29)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((AK ? 0u : 1u) << 15) | ((BKM ? 0u : 1u) << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      for (int i = 0; i < num_kb; i++) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(full_bar0 + 8 * s, ph);
-        tcgen05_fence_after();
-        const uint32_t st = smem_base + s * STAGE_BYTES;
+      const uint32_t idesc = idesc_bf16(BM, BN_, !AK, !BKM);
+      int it = 0, local = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x, local++) {
+        const int z = w / tiles_mn;
+        const int kb_begin = z * p.kb_per_split, kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
+        const int acc = local & 1;
+        const uint32_t aph = (local >> 1) & 1;
+        mbar_wait(tempty_bar0 + 8 * acc, aph ^ 1);  // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN_);
+        for (int kb = kb_begin; kb < kb_end; kb++, it++) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(full_bar0 + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sA_hi = smem_base + s * Cfg::STAGE_BYTES, sA_lo = sA_hi + A_TILE;
+          const uint32_t sB_hi = sA_lo + A_TILE, sB_lo = sB_hi + Cfg::B_TILE;
 #pragma unroll
-        for (int k = 0; k < BK / 16; k++) {
-          // K-major: 16 k-elements = 32 B inside the 128 B swizzle row; SBO = 1024 B (8 rows x 128 B)
-          // MN-major: 16 k-rows = 2 x (8 rows x 128 B); LBO = stride between 64-wide MN chunks, SBO = 1024 B
-          const uint32_t a_off = AK ? (uint32_t)k * 32u : (uint32_t)k * 2048u;
-          const uint32_t b_off = BKM ? (uint32_t)k * 32u : (uint32_t)k * 2048u;
-          const uint32_t a_lbo = AK ? 16u : (uint32_t)p.mn_lbo, a_sbo = AK ? 1024u : (uint32_t)p.mn_sbo;
-          const uint32_t b_lbo = BKM ? 16u : (uint32_t)p.mn_lbo, b_sbo = BKM ? 1024u : (uint32_t)p.mn_sbo;
-          const uint64_t a_hi = make_smem_desc(st + a_off, a_lbo, a_sbo);
-          const uint64_t a_lo = make_smem_desc(st + TILE_BYTES + a_off, a_lbo, a_sbo);
-          const uint64_t b_hi = make_smem_desc(st + 2 * TILE_BYTES + b_off, b_lbo, b_sbo);
-          const uint64_t b_lo = make_smem_desc(st + 3 * TILE_BYTES + b_off, b_lbo, b_sbo);
-          umma_bf16(tmem_base, a_lo, b_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);  // small terms first
-          umma_bf16(tmem_base, a_hi, b_lo, idesc, 1u);
-          umma_bf16(tmem_base, a_hi, b_hi, idesc, 1u);
+          for (int k = 0; k < BK / 16; k++) {
+            const uint64_t a_hi = AK ? desc_kmajor(sA_hi, k) : desc_mnmajor(sA_hi, k);
+            const uint64_t a_lo = AK ? desc_kmajor(sA_lo, k) : desc_mnmajor(sA_lo, k);
+            const uint64_t b_hi = BKM ? desc_kmajor(sB_hi, k) : desc_mnmajor(sB_hi, k);
+            const uint64_t b_lo = BKM ? desc_kmajor(sB_lo, k) : desc_mnmajor(sB_lo, k);
+            umma_bf16(tmem_d, a_lo, b_hi, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);  // small terms first
+            umma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
+            umma_bf16(tmem_d, a_hi, b_hi, idesc, 1u);
+          }
+          umma_commit(empty_bar0 + 8 * s);  // frees the smem stage once the MMAs above retire
         }
-        umma_commit(empty_bar0 + 8 * s);  // frees the smem stage when the MMAs above retire
+        umma_commit(tfull_bar0 + 8 * acc);  // accumulator complete -> epilogue
       }
-      umma_commit(tmem_full_bar);         // accumulator complete -> epilogue
     }
   } else {
-    // ===================== epilogue: TMEM -> registers -> global =====================
+    // ===================== epilogue: TMEM -> registers -> smem transpose -> coalesced global =====================
     const int quad = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
-    const int m = m0 + quad * 32 + lane;
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
-    const bool split = gridDim.z > 1;
-    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    float* tb = epi_buf + quad * 32 * EPI_LD;
+    const bool split = p.splits > 1;
+    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                        (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+    int local = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, local++) {
+      const int z = w / tiles_mn, rem = w - z * tiles_mn;
+      const int m0 = (rem % p.tiles_m) * BM, n0 = (rem / p.tiles_m) * BN_;
+      const int acc = local & 1;
+      const uint32_t aph = (local >> 1) & 1;
+      mbar_wait(tfull_bar0 + 8 * acc, aph);
+      tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t v[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c;
-      TMEM_LD_32(taddr, v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (num_kb <= 0) {
-#pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = 0u;
-      }
-      if (m < p.M) {
+      for (int c = 0; c < BN_; c += 32) {
+        uint32_t v[32];
+        LRCN_TMEM_LD_32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN_ + c), v);
+        tmem_ld_wait();
+        if (c + 32 >= BN_) {  // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar0 + 8 * acc);
+        }
         const int nb = n0 + c;
-        float* crow = p.C + (size_t)m * p.ldc + nb;
-        if (split) {
+        if (nb >= p.N) continue;  // warp-uniform
+        // transpose through smem: lane i holds row i of the 32x32 chunk
 #pragma unroll
-          for (int j = 0; j < 32; j++) {
-            if (nb + j < p.N) {
-              float x = __uint_as_float(v[j]);
-              if (p.bias && blockIdx.z == 0) x += p.bias[nb + j];
-              atomicAdd(crow + j, x);
-            }
-          }
-        } else if (vec_ok && nb + 32 <= p.N) {
+        for (int q = 0; q < 8; q++)
+          *reinterpret_cast<float4*>(tb + lane * EPI_LD + 4 * q) =
+              make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+        __syncwarp();
+        const int mrow0 = m0 + quad * 32;
+        if (vec_ok && !split && nb + 32 <= p.N) {
+          const int cq = lane & 7, rsub = lane >> 3;  // lane -> 4 columns [4cq,4cq+4) of row (4*it + rsub)
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + nb + 4 * cq);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 x = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-            if (p.bias) { float4 b = *reinterpret_cast<const float4*>(p.bias + nb + j); x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w; }
-            if (p.beta) { float4 o = *reinterpret_cast<const float4*>(crow + j); x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w; }
-            *reinterpret_cast<float4*>(crow + j) = x;
-            if (p.C_hi) {
-              __nv_bfloat16 h[4], l[4];
-              const float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-              for (int q = 0; q < 4; q++) { h[q] = __float2bfloat16_rn(xs[q]); l[q] = __float2bfloat16_rn(xs[q] - __bfloat162float(h[q])); }
-              *reinterpret_cast<uint2*>(p.C_hi + (size_t)m * p.ldc + nb + j) = *reinterpret_cast<uint2*>(h);
-              *reinterpret_cast<uint2*>(p.C_lo + (size_t)m * p.ldc + nb + j) = *reinterpret_cast<uint2*>(l);
+          for (int itr = 0; itr < 8; itr++) {
+            const int rr = 4 * itr + rsub, m = mrow0 + rr;
+            if (m < p.M) {
+              float4 x = *reinterpret_cast<const float4*>(tb + rr * EPI_LD + 4 * cq);
+              x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
+              float* cp = p.C + (size_t)m * p.ldc + nb + 4 * cq;
+              if (p.beta) { const float4 o = *reinterpret_cast<const float4*>(cp); x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w; }
+              *reinterpret_cast<float4*>(cp) = x;
+              if (p.C_hi) {
+                __nv_bfloat16 hh[4], ll[4];
+                split_bf16(x.x, hh[0], ll[0]); split_bf16(x.y, hh[1], ll[1]); split_bf16(x.z, hh[2], ll[2]); split_bf16(x.w, hh[3], ll[3]);
+                *reinterpret_cast<uint2*>(p.C_hi + (size_t)m * p.ldc + nb + 4 * cq) = *reinterpret_cast<uint2*>(hh);
+                *reinterpret_cast<uint2*>(p.C_lo + (size_t)m * p.ldc + nb + 4 * cq) = *reinterpret_cast<uint2*>(ll);
+              }
             }
           }
         } else {
-#pragma unroll
-          for (int j = 0; j < 32; j++) {
-            if (nb + j < p.N) {
-              float x = __uint_as_float(v[j]);
-              if (p.bias) x += p.bias[nb + j];
-              if (p.beta) x += crow[j];
-              crow[j] = x;
-              if (p.C_hi) {
-                __nv_bfloat16 h = __float2bfloat16_rn(x);
-                p.C_hi[(size_t)m * p.ldc + nb + j] = h;
-                p.C_lo[(size_t)m * p.ldc + nb + j] = __float2bfloat16_rn(x - __bfloat162float(h));
+          const int n = nb + lane;  // lane -> column
+          const bool nok = n < p.N;
+          const float bv = (p.bias && nok && (!split || z == 0)) ? p.bias[n] : 0.f;
+#pragma unroll 4
+          for (int rr = 0; rr < 32; rr++) {
+            const int m = mrow0 + rr;
+            if (m < p.M && nok) {
+              float x = tb[rr * EPI_LD + lane] + bv;
+              float* cp = p.C + (size_t)m * p.ldc + n;
+              if (split) {
+                atomicAdd(cp, x);  // C pre-zeroed by the launcher when !beta
+              } else {
+                if (p.beta) x += *cp;
+                *cp = x;
+                if (p.C_hi) {
+                  __nv_bfloat16 hh, ll;
+                  split_bf16(x, hh, ll);
+                  p.C_hi[(size_t)m * p.ldc + n] = hh;
+                  p.C_lo[(size_t)m * p.ldc + n] = ll;
+                }
               }
             }
           }
         }
+        __syncwarp();
       }
     }
   }
-  tcgen05_fence_before();
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -311,7 +281,6 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-// 2-D bf16 row-major tensor [outer][inner] with pitch ld (elements); box = {64 inner, box_outer}
 static bool make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { g_gemm_err = "cuTensorMapEncodeTiled unavailable"; return false; }
@@ -323,9 +292,9 @@ static bool make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t o
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    char buf[160];
-    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu ld=%llu", (int)r, (unsigned long long)inner,
-             (unsigned long long)outer, (unsigned long long)ld);
+    char buf[200];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu ld=%llu box_outer=%u", (int)r, (unsigned long long)inner,
+             (unsigned long long)outer, (unsigned long long)ld, box_outer);
     g_gemm_err = buf;
     return false;
   }
@@ -339,7 +308,7 @@ struct MapKey {
 static std::map<MapKey, CUtensorMap>& map_cache() { static std::map<MapKey, CUtensorMap> c; return c; }
 static std::mutex g_map_mu;
 
-static bool get_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer) {
+bool get_tensor_map_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer) {
   MapKey k{ptr, inner, outer, ld, box_outer};
   std::lock_guard<std::mutex> lk(g_map_mu);
   auto& c = map_cache();
@@ -347,7 +316,7 @@ static bool get_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t 
   if (it != c.end()) { *out = it->second; return true; }
   CUtensorMap m;
   if (!make_map(&m, ptr, inner, outer, ld, box_outer)) return false;
-  if (c.size() > 4096) c.clear();
+  if (c.size() > 8192) c.clear();
   c[k] = m;
   *out = m;
   return true;
@@ -357,61 +326,87 @@ static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
 }
+static int g_num_sms = 148, g_force_bn = 0;
 
-static int g_mn_lbo = 8192, g_mn_sbo = 1024;
+template <bool AK, bool BKM, int BN_>
+static cudaError_t set_attr() {
+  return cudaFuncSetAttribute(gemm_bf16x3_kernel<AK, BKM, BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<BN_>::SMEM_BYTES);
+}
 bool init_gemm_sm100() {
-  cudaError_t e = cudaSuccess;
-  e = cudaFuncSetAttribute(gemm_bf16x3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16x3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16x3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16x3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  cudaError_t e = set_attr<true, true, 128>();
+  if (e == cudaSuccess) e = set_attr<true, false, 128>();
+  if (e == cudaSuccess) e = set_attr<false, true, 128>();
+  if (e == cudaSuccess) e = set_attr<false, false, 128>();
+  if (e == cudaSuccess) e = set_attr<true, true, 256>();
+  if (e == cudaSuccess) e = set_attr<true, false, 256>();
+  if (e == cudaSuccess) e = set_attr<false, true, 256>();
+  if (e == cudaSuccess) e = set_attr<false, false, 256>();
   if (e != cudaSuccess) { g_gemm_err = std::string("cudaFuncSetAttribute(gemm_bf16x3): ") + cudaGetErrorString(e); return false; }
   if (!get_encode()) { g_gemm_err = "cuTensorMapEncodeTiled unavailable"; return false; }
-  g_mn_lbo = env_int("LRCN_MN_LBO", 8192);  // debug knobs for the MN-major descriptor strides
-  g_mn_sbo = env_int("LRCN_MN_SBO", 1024);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  g_force_bn = env_int("LRCN_GEMM_BN", 0);
   return true;
+}
+
+template <bool AK, bool BKM, int BN_>
+static void launch(cudaStream_t s, int grid, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                   const GemmParams& p) {
+  gemm_bf16x3_kernel<AK, BKM, BN_><<<grid, NUM_THREADS, TileCfg<BN_>::SMEM_BYTES, s>>>(a_hi, a_lo, b_hi, b_lo, p);
 }
 
 bool gemm_bf16x3(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo,
                  int lda, const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, int ldb, float* C, int ldc, bool beta, const float* bias,
                  __nv_bfloat16* C_hi, __nv_bfloat16* C_lo) {
   if (M <= 0 || N <= 0 || K <= 0) return true;
-  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
-  bool ok = true;
-  if (a_kmajor) { ok = ok && get_map(&ta_hi, A_hi, K, M, lda, BM) && get_map(&ta_lo, A_lo, K, M, lda, BM); }
-  else          { ok = ok && get_map(&ta_hi, A_hi, M, K, lda, BK) && get_map(&ta_lo, A_lo, M, K, lda, BK); }
-  if (b_kmajor) { ok = ok && get_map(&tb_hi, B_hi, K, N, ldb, BN) && get_map(&tb_lo, B_lo, K, N, ldb, BN); }
-  else          { ok = ok && get_map(&tb_hi, B_hi, N, K, ldb, BK) && get_map(&tb_lo, B_lo, N, K, ldb, BK); }
-  if (!ok) return false;
-
-  const int tm = (M + BM - 1) / BM, tn = (N + BN - 1) / BN;
+  const int tm = (M + BM - 1) / BM;
+  // BN = 256 halves the smem operand traffic per MMA (128x128 SS-mode MMAs sit right at the 128 B/clk smem limit);
+  // use it when there is enough N to keep every SM busy
+  int bn = (N >= 512 && tm * ((N + 255) / 256) >= g_num_sms) ? 256 : 128;
+  if (g_force_bn == 128 || g_force_bn == 256) bn = g_force_bn;
+  const int tn = (N + bn - 1) / bn;
   const int num_kb = (K + BK - 1) / BK;
   int splits = 1;
   if (!C_hi) {
     const int tiles = tm * tn;
-    if (tiles < 96 && num_kb >= 8) {
-      splits = (148 + tiles - 1) / tiles;
+    if (tiles * 2 <= g_num_sms && num_kb >= 8) {
+      splits = g_num_sms / tiles;
       if (splits > num_kb / 4) splits = num_kb / 4;
       if (splits < 1) splits = 1;
       if (splits > 32) splits = 32;
     }
   }
-  int kb_per = (num_kb + splits - 1) / splits;
+  const int kb_per = (num_kb + splits - 1) / splits;
   splits = (num_kb + kb_per - 1) / kb_per;
+
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  bool ok = true;
+  if (a_kmajor) ok = ok && get_tensor_map_bf16(&ta_hi, A_hi, K, M, lda, BM) && get_tensor_map_bf16(&ta_lo, A_lo, K, M, lda, BM);
+  else          ok = ok && get_tensor_map_bf16(&ta_hi, A_hi, M, K, lda, BK) && get_tensor_map_bf16(&ta_lo, A_lo, M, K, lda, BK);
+  if (b_kmajor) ok = ok && get_tensor_map_bf16(&tb_hi, B_hi, K, N, ldb, bn) && get_tensor_map_bf16(&tb_lo, B_lo, K, N, ldb, bn);
+  else          ok = ok && get_tensor_map_bf16(&tb_hi, B_hi, N, K, ldb, BK) && get_tensor_map_bf16(&tb_lo, B_lo, N, K, ldb, BK);
+  if (!ok) return false;
+
   if (splits > 1 && !beta) {
     if (ldc == N) cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), s);
     else cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, s);
   }
   GemmParams p;
-  p.M = M; p.N = N; p.K = K; p.kb_per_split = kb_per; p.C = C; p.ldc = ldc; p.bias = bias; p.beta = beta ? 1 : 0;
-  p.C_hi = C_hi; p.C_lo = C_lo;
-  p.mn_lbo = g_mn_lbo;
-  p.mn_sbo = g_mn_sbo;
-  dim3 grid(tn, tm, splits);
-  if (a_kmajor && b_kmajor) gemm_bf16x3_kernel<true, true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
-  else if (a_kmajor && !b_kmajor) gemm_bf16x3_kernel<true, false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
-  else if (!a_kmajor && b_kmajor) gemm_bf16x3_kernel<false, true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
-  else gemm_bf16x3_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  p.M = M; p.N = N; p.K = K; p.tiles_m = tm; p.tiles_n = tn; p.splits = splits; p.kb_per_split = kb_per;
+  p.C = C; p.ldc = ldc; p.bias = bias; p.beta = beta ? 1 : 0; p.C_hi = C_hi; p.C_lo = C_lo;
+  const int total = tm * tn * splits;
+  const int grid = total < g_num_sms ? total : g_num_sms;
+#define LRCN_LAUNCH(AKv, BKv)                                                     \
+  do {                                                                            \
+    if (bn == 256) launch<AKv, BKv, 256>(s, grid, ta_hi, ta_lo, tb_hi, tb_lo, p); \
+    else launch<AKv, BKv, 128>(s, grid, ta_hi, ta_lo, tb_hi, tb_lo, p);           \
+  } while (0)
+  if (a_kmajor && b_kmajor) LRCN_LAUNCH(true, true);
+  else if (a_kmajor && !b_kmajor) LRCN_LAUNCH(true, false);
+  else if (!a_kmajor && b_kmajor) LRCN_LAUNCH(false, true);
+  else LRCN_LAUNCH(false, false);
+#undef LRCN_LAUNCH
   if (g_counter) g_counter->n++;
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) { g_gemm_err = std::string("gemm_bf16x3 launch: ") + cudaGetErrorString(e); return false; }

@@ -19,7 +19,8 @@ struct StepScalars {
   float adam_d1;        // 1 - beta1^t
   float adam_d2;        // 1 - beta2^t
   float lr, beta1, beta2, eps;
-  float grad_scale;     // reserved
+  float one_m_beta1;    // (float)(1 - beta1), computed in double like Knet's axpy!(1-p.beta1, ...)
+  float one_m_beta2;
 };
 
 struct LaunchCounter { long long n = 0; };
@@ -32,12 +33,14 @@ void sgemm(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int K, co
            const float* B, int ldb, float* C, int ldc, bool beta, const float* bias);
 
 // ---------------------------------------------------------------- elementwise / gather kernels
-void gather_features(cudaStream_t s, const float* table, const int* rows, int B, float* X);
+void gather_features(cudaStream_t s, const float* table, const int* rows, int B, float* X, __nv_bfloat16* hi = nullptr,
+                     __nv_bfloat16* lo = nullptr);  // hi/lo: optional bf16 split of the output, same indexing
 // E_all[r][:] = WembT[tok[r]][:] (* dropout mask site 0);  tok 0-based
 void gather_embed(cudaStream_t s, const float* WembT, const int* tok, int R, int E, float* out,
-                  const StepScalars* sc, bool train);
+                  const StepScalars* sc, bool train, __nv_bfloat16* hi = nullptr, __nv_bfloat16* lo = nullptr);
 // Z[r][C+j] = v[r % B][j]; then dropout (site 1) over the whole row of 2C
-void z_finish(cudaStream_t s, float* Z, const float* v, int ldv, int R, int B, int C, const StepScalars* sc, bool train);
+void z_finish(cudaStream_t s, float* Z, const float* v, int ldv, int R, int B, int C, const StepScalars* sc, bool train,
+              __nv_bfloat16* hi = nullptr, __nv_bfloat16* lo = nullptr);
 // LSTM cell forward for one step: gates (pre-activation, [B][4H], order f,i,o,g) are activated in place
 void lstm_cell_fwd(cudaStream_t s, float* gates, const float* c_prev, float* c_out, float* h_out, int B, int H);
 // LSTM cell backward for one step; gates buffer holds activations and receives dG in place
@@ -46,11 +49,12 @@ void lstm_cell_bwd(cudaStream_t s, float* gates, const float* c_prev, const floa
                    int B, int H);
 // row-wise log-softmax cross-entropy: rowlp[r] = logp(a_r)[y_r]; if train, logits <- (softmax - onehot)*inv_ntok
 void softmax_ce(cudaStream_t s, float* logits, int ld, int R, int V, const int* tgt, float* rowlp,
-                const StepScalars* sc, bool train);
+                const StepScalars* sc, bool train, __nv_bfloat16* hi = nullptr, __nv_bfloat16* lo = nullptr);
 void reduce_sum_double(cudaStream_t s, const float* x, int n, double* out);
 void colsum(cudaStream_t s, const float* A, int ld, int R, int N, float* out, bool accumulate);
 // dZ *= dropout mask (site 1); dv[i][j] = sum_t dZ[(t*B+i)][C+j]
-void dz_finish(cudaStream_t s, float* dZ, float* dv, int ldv, int T, int B, int C, const StepScalars* sc, bool train);
+void dz_finish(cudaStream_t s, float* dZ, float* dv, int ldv, int T, int B, int C, const StepScalars* sc, bool train,
+               __nv_bfloat16* z_hi = nullptr, __nv_bfloat16* z_lo = nullptr, __nv_bfloat16* v_hi = nullptr, __nv_bfloat16* v_lo = nullptr);
 // dWembT[tok[r]][:] += dE[r][:] (* dropout mask site 0)
 void scatter_add_embed(cudaStream_t s, float* dWembT, const int* tok, const float* dE, int R, int E,
                        const StepScalars* sc, bool train);
@@ -90,5 +94,19 @@ bool gemm_bf16x3(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int
 const char* gemm_bf16x3_last_error();
 bool init_gemm_sm100();   // func attributes + driver entry point; call once outside any capture
 void init_simt_kernels();
+
+// ---------------------------------------------------------------- fused LSTM timestep (lstm_sm100.cu)
+bool init_lstm_sm100();
+size_t lstm_permuted_elems(int H);
+// W_h = columns [x_off, x_off+H) of the layer weight W [4H][ldw] -> gate-interleaved bf16 hi/lo copy for lstm_fwd_step
+void lstm_permute_weights(cudaStream_t s, const float* W, int ldw, int x_off, int H, __nv_bfloat16* hi, __nv_bfloat16* lo);
+// gates [B][4H] holds x-part + bias on entry and the activated gates on exit; has_rec=false at t=0 (h_0 = 0)
+bool lstm_fwd_step(cudaStream_t s, int B, int H, bool has_rec, const __nv_bfloat16* hprev_hi, const __nv_bfloat16* hprev_lo,
+                   const __nv_bfloat16* wperm_hi, const __nv_bfloat16* wperm_lo, float* gates, const float* c_prev, float* c_out,
+                   float* h_out, __nv_bfloat16* h_hi, __nv_bfloat16* h_lo);
+// gates [B][4H] holds the step's activations on entry and dG on exit (fp32 + bf16 hi/lo); has_rec=false at t=T-1
+bool lstm_bwd_step(cudaStream_t s, int B, int H, bool has_rec, const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int ldw, int x_off,
+                   const __nv_bfloat16* gnext_hi, const __nv_bfloat16* gnext_lo, float* gates, __nv_bfloat16* g_hi, __nv_bfloat16* g_lo,
+                   const float* c_prev, const float* c_cur, const float* dh_in, float* dc);
 
 }  // namespace lrcn

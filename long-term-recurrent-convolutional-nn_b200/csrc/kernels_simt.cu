@@ -152,19 +152,36 @@ void sgemm(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int K, co
 // ------------------------------------------------------------------------------------------
 // gathers
 // ------------------------------------------------------------------------------------------
-__global__ void gather_features_kernel(const float4* __restrict__ table, const int* __restrict__ rows, float4* __restrict__ X) {
+__device__ __forceinline__ void split_one(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+__device__ __forceinline__ void store_split4(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t idx, float4 x) {
+  __nv_bfloat16 h[4], l[4];
+  split_one(x.x, h[0], l[0]); split_one(x.y, h[1], l[1]); split_one(x.z, h[2], l[2]); split_one(x.w, h[3], l[3]);
+  *reinterpret_cast<uint2*>(hi + idx) = *reinterpret_cast<uint2*>(h);
+  *reinterpret_cast<uint2*>(lo + idx) = *reinterpret_cast<uint2*>(l);
+}
+
+__global__ void gather_features_kernel(const float4* __restrict__ table, const int* __restrict__ rows, float4* __restrict__ X,
+                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   int i = blockIdx.x;
   const float4* src = table + (size_t)rows[i] * 1024;
   float4* dst = X + (size_t)i * 1024;
-  for (int j = threadIdx.x; j < 1024; j += blockDim.x) dst[j] = __ldg(src + j);
+  for (int j = threadIdx.x; j < 1024; j += blockDim.x) {
+    float4 x = __ldg(src + j);
+    dst[j] = x;
+    if (hi) store_split4(hi, lo, ((size_t)i * 1024 + j) * 4, x);
+  }
 }
-void gather_features(cudaStream_t s, const float* table, const int* rows, int B, float* X) {
-  gather_features_kernel<<<B, 256, 0, s>>>((const float4*)table, rows, (float4*)X);
+void gather_features(cudaStream_t s, const float* table, const int* rows, int B, float* X, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  gather_features_kernel<<<B, 256, 0, s>>>((const float4*)table, rows, (float4*)X, hi, lo);
   count_launch();
 }
 
 __global__ void gather_embed_kernel(const float* __restrict__ W, const int* __restrict__ tok, int R, int E,
-                                    float* __restrict__ out, const StepScalars* __restrict__ sc, int train) {
+                                    float* __restrict__ out, const StepScalars* __restrict__ sc, int train,
+                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   int r = blockIdx.x;
   const float* src = W + (size_t)tok[r] * E;
   float* dst = out + (size_t)r * E;
@@ -172,16 +189,17 @@ __global__ void gather_embed_kernel(const float* __restrict__ W, const int* __re
     float v = __ldg(src + e);
     if (train) v *= drop_scale(sc, 0, (uint64_t)r * E + e);
     dst[e] = v;
+    if (hi) { __nv_bfloat16 h, l; split_one(v, h, l); hi[(size_t)r * E + e] = h; lo[(size_t)r * E + e] = l; }
   }
 }
 void gather_embed(cudaStream_t s, const float* WembT, const int* tok, int R, int E, float* out, const StepScalars* sc,
-                  bool train) {
-  gather_embed_kernel<<<R, 128, 0, s>>>(WembT, tok, R, E, out, sc, train ? 1 : 0);
+                  bool train, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  gather_embed_kernel<<<R, 128, 0, s>>>(WembT, tok, R, E, out, sc, train ? 1 : 0, hi, lo);
   count_launch();
 }
 
 __global__ void z_finish_kernel(float* __restrict__ Z, const float* __restrict__ v, int ldv, int R, int B, int C,
-                                const StepScalars* __restrict__ sc, int train) {
+                                const StepScalars* __restrict__ sc, int train, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   int r = blockIdx.x;
   int i = B > 0 ? r % B : r / (-B);  // B<0: generation, image index = row / beam_width
   float* z = Z + (size_t)r * 2 * C;
@@ -189,10 +207,12 @@ __global__ void z_finish_kernel(float* __restrict__ Z, const float* __restrict__
     float x = (j < C) ? z[j] : v[(size_t)i * ldv + (j - C)];
     if (train) x *= drop_scale(sc, 1, (uint64_t)r * 2 * C + j);
     z[j] = x;
+    if (hi) { __nv_bfloat16 h, l; split_one(x, h, l); hi[(size_t)r * 2 * C + j] = h; lo[(size_t)r * 2 * C + j] = l; }
   }
 }
-void z_finish(cudaStream_t s, float* Z, const float* v, int ldv, int R, int B, int C, const StepScalars* sc, bool train) {
-  z_finish_kernel<<<R, 128, 0, s>>>(Z, v, ldv, R, B, C, sc, train ? 1 : 0);
+void z_finish(cudaStream_t s, float* Z, const float* v, int ldv, int R, int B, int C, const StepScalars* sc, bool train,
+              __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  z_finish_kernel<<<R, 128, 0, s>>>(Z, v, ldv, R, B, C, sc, train ? 1 : 0, hi, lo);
   count_launch();
 }
 
@@ -283,35 +303,50 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // ------------------------------------------------------------------------------------------
 // softmax cross-entropy, one CTA per row (Knet logp(x,2), lrcn.jl:562-567 and its adjoint)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) softmax_ce_kernel(float* __restrict__ logits, int ld, int V, const int* __restrict__ tgt,
-                                                         float* __restrict__ rowlp, const StepScalars* __restrict__ sc, int train) {
-  extern __shared__ float row[];
+__global__ void __launch_bounds__(512) softmax_ce_kernel(float* __restrict__ logits, int ld, int V, const int* __restrict__ tgt,
+                                                         float* __restrict__ rowlp, const StepScalars* __restrict__ sc, int train,
+                                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  extern __shared__ __align__(16) float row[];
   __shared__ float red[32];
-  int r = blockIdx.x;
+  const int r = blockIdx.x;
   float* a = logits + (size_t)r * ld;
+  const int V4 = V >> 2;  // ld % 8 == 0 and the arena is 256 B aligned -> rows are 16 B aligned
   float mx = -INFINITY;
-  for (int j = threadIdx.x; j < V; j += blockDim.x) { float x = a[j]; row[j] = x; mx = fmaxf(mx, x); }
+  for (int q = threadIdx.x; q < V4; q += blockDim.x) {
+    const float4 x = *reinterpret_cast<const float4*>(a + 4 * q);
+    *reinterpret_cast<float4*>(row + 4 * q) = x;
+    mx = fmaxf(fmaxf(mx, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
+  }
+  for (int j = 4 * V4 + threadIdx.x; j < V; j += blockDim.x) { const float x = a[j]; row[j] = x; mx = fmaxf(mx, x); }
   mx = block_max(mx, red);
   float sum = 0.f;
   for (int j = threadIdx.x; j < V; j += blockDim.x) sum += expf(row[j] - mx);
   sum = block_sum(sum, red);
-  float lse = logf(sum);
-  int y = tgt[r];
+  const float lse = logf(sum);
+  const int y = tgt[r];
   if (threadIdx.x == 0) rowlp[r] = (row[y] - mx) - lse;
   if (train) {
-    float inv = sc->inv_ntok;
-    for (int j = threadIdx.x; j < V; j += blockDim.x) {
-      float p = expf((row[j] - mx) - lse);
-      if (j == y) p -= 1.0f;
-      a[j] = p * inv;
+    const float inv = sc->inv_ntok;
+    const size_t base = (size_t)r * ld;
+    for (int q = threadIdx.x; q < (ld >> 2); q += blockDim.x) {
+      float p[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int j = 4 * q + e;
+        float v = 0.f;  // padding columns [V, ld) stay clean
+        if (j < V) { v = expf((row[j] - mx) - lse); if (j == y) v -= 1.0f; v *= inv; }
+        p[e] = v;
+      }
+      const float4 o = make_float4(p[0], p[1], p[2], p[3]);
+      *reinterpret_cast<float4*>(a + 4 * q) = o;
+      if (hi) store_split4(hi, lo, base + 4 * q, o);
     }
-    for (int j = V + threadIdx.x; j < ld; j += blockDim.x) a[j] = 0.f;  // keep the padding columns clean
   }
 }
 void softmax_ce(cudaStream_t s, float* logits, int ld, int R, int V, const int* tgt, float* rowlp, const StepScalars* sc,
-                bool train) {
-  size_t smem = (size_t)V * sizeof(float);
-  softmax_ce_kernel<<<R, 256, smem, s>>>(logits, ld, V, tgt, rowlp, sc, train ? 1 : 0);
+                bool train, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  size_t smem = (size_t)ld * sizeof(float);
+  softmax_ce_kernel<<<R, 512, smem, s>>>(logits, ld, V, tgt, rowlp, sc, train ? 1 : 0, hi, lo);
   count_launch();
 }
 
@@ -332,35 +367,47 @@ void reduce_sum_double(cudaStream_t s, const float* x, int n, double* out) {
   count_launch();
 }
 
-// out[n] (+)= sum_r A[r][n] ; block = 32 columns x 8 row-lanes, grid.y splits rows (atomic combine)
+// out[n] (+)= sum_r A[r][n] ; block = 32 float4-columns x 8 row-lanes, grid.y splits rows (atomic combine)
 __global__ void colsum_kernel(const float* __restrict__ A, int ld, int R, int N, float* __restrict__ out, int rows_per) {
-  __shared__ float red[8][33];
-  int n = blockIdx.x * 32 + threadIdx.x;
-  int r0 = blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
-  float acc = 0.f;
-  if (n < N)
-    for (int r = r0 + threadIdx.y; r < r1; r += 8) acc += A[(size_t)r * ld + n];
+  __shared__ float4 red[8][33];
+  const int n4 = blockIdx.x * 32 + threadIdx.x;  // float4 column
+  const int n = 4 * n4;
+  const int r0 = blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n < N) {
+    const bool full = n + 4 <= N;
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      const float* p = A + (size_t)r * ld + n;
+      if (full) { const float4 x = *reinterpret_cast<const float4*>(p); acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w; }
+      else { acc.x += p[0]; if (n + 1 < N) acc.y += p[1]; if (n + 2 < N) acc.z += p[2]; }
+    }
+  }
   red[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.y == 0 && n < N) {
-    float s = 0.f;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < 8; k++) s += red[k][threadIdx.x];
-    atomicAdd(out + n, s);
+    for (int k = 0; k < 8; k++) { const float4 x = red[k][threadIdx.x]; t.x += x.x; t.y += x.y; t.z += x.z; t.w += x.w; }
+    atomicAdd(out + n, t.x);
+    if (n + 1 < N) atomicAdd(out + n + 1, t.y);
+    if (n + 2 < N) atomicAdd(out + n + 2, t.z);
+    if (n + 3 < N) atomicAdd(out + n + 3, t.w);
   }
 }
+// requires ld % 4 == 0 and a 16-byte aligned A (all workspace matrices are)
 void colsum(cudaStream_t s, const float* A, int ld, int R, int N, float* out, bool accumulate) {
   if (!accumulate) cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), s);
-  int gx = (N + 31) / 32;
+  int gx = ((N + 3) / 4 + 31) / 32;
   int gy = 1;
-  while (gx * gy < 296 && gy * 64 < R) gy *= 2;
+  while (gx * gy < 592 && gy * 32 < R) gy *= 2;
   int rows_per = (R + gy - 1) / gy;
   colsum_kernel<<<dim3(gx, gy), dim3(32, 8), 0, s>>>(A, ld, R, N, out, rows_per);
   count_launch();
 }
 
 __global__ void dz_finish_kernel(float* __restrict__ dZ, float* __restrict__ dv, int ldv, int T, int B, int C,
-                                 const StepScalars* __restrict__ sc, int train) {
+                                 const StepScalars* __restrict__ sc, int train, __nv_bfloat16* __restrict__ z_hi,
+                                 __nv_bfloat16* __restrict__ z_lo, __nv_bfloat16* __restrict__ v_hi, __nv_bfloat16* __restrict__ v_lo) {
   int i = blockIdx.x;  // batch row
   for (int j = threadIdx.x; j < 2 * C; j += blockDim.x) {
     float acc = 0.f;
@@ -368,13 +415,18 @@ __global__ void dz_finish_kernel(float* __restrict__ dZ, float* __restrict__ dv,
       size_t r = (size_t)t * B + i;
       float x = dZ[r * 2 * C + j];
       if (train) { x *= drop_scale(sc, 1, (uint64_t)r * 2 * C + j); dZ[r * 2 * C + j] = x; }
+      if (z_hi) { __nv_bfloat16 h, l; split_one(x, h, l); z_hi[r * 2 * C + j] = h; z_lo[r * 2 * C + j] = l; }
       acc += x;
     }
-    if (j >= C) dv[(size_t)i * ldv + (j - C)] = acc;
+    if (j >= C) {
+      dv[(size_t)i * ldv + (j - C)] = acc;
+      if (v_hi) { __nv_bfloat16 h, l; split_one(acc, h, l); v_hi[(size_t)i * ldv + (j - C)] = h; v_lo[(size_t)i * ldv + (j - C)] = l; }
+    }
   }
 }
-void dz_finish(cudaStream_t s, float* dZ, float* dv, int ldv, int T, int B, int C, const StepScalars* sc, bool train) {
-  dz_finish_kernel<<<B, 256, 0, s>>>(dZ, dv, ldv, T, B, C, sc, train ? 1 : 0);
+void dz_finish(cudaStream_t s, float* dZ, float* dv, int ldv, int T, int B, int C, const StepScalars* sc, bool train,
+               __nv_bfloat16* z_hi, __nv_bfloat16* z_lo, __nv_bfloat16* v_hi, __nv_bfloat16* v_lo) {
+  dz_finish_kernel<<<B, 256, 0, s>>>(dZ, dv, ldv, T, B, C, sc, train ? 1 : 0, z_hi, z_lo, v_hi, v_lo);
   count_launch();
 }
 
@@ -398,17 +450,12 @@ void scatter_add_embed(cudaStream_t s, float* dWembT, const int* tok, const floa
 // ------------------------------------------------------------------------------------------
 // fused Adam over the flat parameter arena (Knet Adam defaults; dense over every element)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void split_one(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(x);
-  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-}
-
 template <bool SPLIT>
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ w, const float4* __restrict__ g, float4* __restrict__ m,
                                                    float4* __restrict__ v, size_t n4, const StepScalars* __restrict__ sc,
                                                    __nv_bfloat16* __restrict__ w_hi, __nv_bfloat16* __restrict__ w_lo) {
   const float b1 = sc->beta1, b2 = sc->beta2, lr = sc->lr, eps = sc->eps, d1 = sc->adam_d1, d2 = sc->adam_d2;
-  const float ob1 = 1.0f - b1, ob2 = 1.0f - b2;
+  const float ob1 = sc->one_m_beta1, ob2 = sc->one_m_beta2;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 W = w[i], G = __ldg(g + i), Mv = m[i], Vv = v[i];
     float* wp = reinterpret_cast<float*>(&W);

@@ -111,6 +111,7 @@ struct lrcn_handle {
   int64_t rows[9], cols[9];
   float *w = nullptr, *g = nullptr, *m = nullptr, *v = nullptr;
   bf16 *w_hi = nullptr, *w_lo = nullptr;
+  bf16 *wp1_hi = nullptr, *wp1_lo = nullptr, *wp2_hi = nullptr, *wp2_lo = nullptr;  // gate-interleaved recurrent weights (lstm_sm100.cu)
   int64_t adam_t = 0;
   Table tab[2];
   Arena ws;
@@ -142,6 +143,12 @@ static void shadow(lrcn_handle* h, const float* p, bf16** hi, bf16** lo) {
   if (p >= h->w && p < h->w + h->P) { *hi = h->w_hi + (p - h->w); *lo = h->w_lo + (p - h->w); return; }
   *hi = h->ws.hi + (p - h->ws.f);
   *lo = h->ws.lo + (p - h->ws.f);
+}
+struct ShadowPair { bf16* hi; bf16* lo; };
+static ShadowPair SH(lrcn_handle* h, const float* p) {  // null pair in fp32 mode: producers then skip the split
+  ShadowPair sp{nullptr, nullptr};
+  if (h->bf16mode) shadow(h, p, &sp.hi, &sp.lo);
+  return sp;
 }
 static void split_ws(lrcn_handle* h, const float* p, size_t n) {
   if (!h->bf16mode) return;
@@ -177,7 +184,7 @@ extern "C" int lrcn_config_default(lrcn_config* c) {
   c->max_batch = 256; c->max_len = 28;                    // lrcn.jl:353
   c->max_gen_rows = 1024; c->device = 0;
   c->precision = LRCN_PREC_BF16X3; c->use_graphs = 1;
-  c->lr = 1e-3f; c->beta1 = 0.9f; c->beta2 = 0.999f; c->eps = 1e-8f;  // Knet Adam() via lrcn.jl:402
+  c->lr = 1e-3; c->beta1 = 0.9; c->beta2 = 0.999; c->eps = 1e-8;  // Knet Adam() via lrcn.jl:402 (Float64 hyper-parameters)
   return LRCN_OK;
 }
 
@@ -202,7 +209,7 @@ extern "C" int lrcn_destroy(lrcn_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
   if (h->comm && nccl_api()) nccl_api()->CommDestroy(h->comm);
-  void* ptrs[] = {h->w, h->g, h->m, h->v, h->w_hi, h->w_lo, h->tab[0].d, h->tab[1].d, h->ws.f, h->ws.hi, h->ws.lo, h->d_tok_in,
+  void* ptrs[] = {h->w, h->g, h->m, h->v, h->w_hi, h->w_lo, h->wp1_hi, h->wp1_lo, h->wp2_hi, h->wp2_lo, h->tab[0].d, h->tab[1].d, h->ws.f, h->ws.hi, h->ws.lo, h->d_tok_in,
                   h->d_tok_tgt, h->d_rows, h->d_sc, h->d_loss, h->g_last, h->g_ctok, h->g_stok, h->g_spar, h->g_hista, h->g_histb,
                   h->g_done, h->g_ndone, h->g_olen, h->g_rows, h->g_otok, h->l2_scratch};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -236,7 +243,7 @@ static int create_impl(const lrcn_config* cfg, lrcn_handle* h) {
   if (h->bf16mode && prop.major != 10)
     return fail(LRCN_ERR_CUDA, "precision bf16x3 needs sm_100a (tcgen05); device is sm_%d%d", prop.major, prop.minor);
   init_simt_kernels();
-  if (h->bf16mode && !init_gemm_sm100()) return fail(LRCN_ERR_CUDA, "%s", gemm_bf16x3_last_error());
+  if (h->bf16mode && (!init_gemm_sm100() || !init_lstm_sm100())) return fail(LRCN_ERR_CUDA, "%s", gemm_bf16x3_last_error());
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&h->ev0));
@@ -264,6 +271,8 @@ static int create_impl(const lrcn_config* cfg, lrcn_handle* h) {
   if (h->bf16mode) {
     CK(cudaMalloc(&h->w_hi, h->P * 2)); CK(cudaMalloc(&h->w_lo, h->P * 2));
     CK(cudaMemset(h->w_hi, 0, h->P * 2)); CK(cudaMemset(h->w_lo, 0, h->P * 2));
+    CK(cudaMalloc(&h->wp1_hi, lstm_permuted_elems(h->H1) * 2)); CK(cudaMalloc(&h->wp1_lo, lstm_permuted_elems(h->H1) * 2));
+    CK(cudaMalloc(&h->wp2_hi, lstm_permuted_elems(h->H2) * 2)); CK(cudaMalloc(&h->wp2_lo, lstm_permuted_elems(h->H2) * 2));
   }
 
   // ---- workspace arena
@@ -457,36 +466,65 @@ static int stage_host(lrcn_handle* h, int split, const int64_t* image_ids, const
   return LRCN_OK;
 }
 
+// one LSTM timestep of layer `layer` (1|2) on time-major buffers: acts [T*B][4H] (x-part + bias in, activations out),
+// hs/cs [(T+1)*B][H] with slot 0 = zeros.  bf16x3: one fused tcgen05 kernel; fp32: SIMT GEMM + cell kernel.
+static void lstm_step_fwd(lrcn_handle* h, int layer, int t, int B, float* acts, float* hs, float* cs) {
+  const int H = layer == 1 ? h->H1 : h->H2;
+  const int ldw = layer == 1 ? h->E + h->H1 : 2 * h->H2, x_off = layer == 1 ? h->E : 2 * h->C;
+  float* g = acts + (size_t)t * B * 4 * H;
+  float *hp = hs + (size_t)t * B * H, *hn = hs + (size_t)(t + 1) * B * H, *cp = cs + (size_t)t * B * H, *cn = cs + (size_t)(t + 1) * B * H;
+  if (h->bf16mode) {
+    bf16 *hp_hi, *hp_lo, *hn_hi, *hn_lo;
+    shadow(h, hp, &hp_hi, &hp_lo);
+    shadow(h, hn, &hn_hi, &hn_lo);
+    if (!lstm_fwd_step(h->stream, B, H, t > 0, hp_hi, hp_lo, layer == 1 ? h->wp1_hi : h->wp2_hi, layer == 1 ? h->wp1_lo : h->wp2_lo, g, cp, cn,
+                       hn, hn_hi, hn_lo))
+      throw GemmFail{gemm_bf16x3_last_error()};
+    return;
+  }
+  if (t > 0) sgemm(h->stream, true, true, B, 4 * H, H, hp, H, Wp(h, layer == 1 ? 1 : 3) + x_off, ldw, g, 4 * H, true, nullptr);
+  lstm_cell_fwd(h->stream, g, cp, cn, hn, B, H);
+}
+static void lstm_step_bwd(lrcn_handle* h, int layer, int t, int T, int B, float* acts, float* cs, float* dh_all, float* dhrec, float* dc) {
+  const int H = layer == 1 ? h->H1 : h->H2;
+  const int ldw = layer == 1 ? h->E + h->H1 : 2 * h->H2, x_off = layer == 1 ? h->E : 2 * h->C;
+  const float* W = Wp(h, layer == 1 ? 1 : 3);
+  float* g = acts + (size_t)t * B * 4 * H;
+  const float *cp = cs + (size_t)t * B * H, *cc = cs + (size_t)(t + 1) * B * H, *dh_in = dh_all + (size_t)t * B * H;
+  const bool first = t == T - 1;
+  if (h->bf16mode) {
+    bf16 *w_hi, *w_lo, *g_hi, *g_lo, *gn_hi = nullptr, *gn_lo = nullptr;
+    shadow(h, W, &w_hi, &w_lo);
+    shadow(h, g, &g_hi, &g_lo);
+    if (!first) shadow(h, g + (size_t)B * 4 * H, &gn_hi, &gn_lo);
+    if (!lstm_bwd_step(h->stream, B, H, !first, w_hi, w_lo, ldw, x_off, gn_hi, gn_lo, g, g_hi, g_lo, cp, cc, dh_in, dc))
+      throw GemmFail{gemm_bf16x3_last_error()};
+    return;
+  }
+  // fp32: dh_rec (from step t+1) was produced by the GEMM issued after the previous cell kernel
+  lstm_cell_bwd(h->stream, g, cp, cc, dh_in, dhrec, dc, first, B, H);
+  if (t > 0) sgemm(h->stream, true, false, B, H, 4 * H, g, 4 * H, W + x_off, ldw, dhrec, H, false, nullptr);
+}
+
 static void enqueue_forward(lrcn_handle* h, int split, int B, int l, bool train) {
   const int T = l + 1, R = T * B, E = h->E, H1 = h->H1, H2 = h->H2, C = h->C, V = h->V, ldV = h->ldV, ldv = h->ldv;
   const Workspace& o = h->o;
   cudaStream_t s = h->stream;
   float *X = WS(h, o.X), *v = WS(h, o.v), *Eall = WS(h, o.Eall), *acts1 = WS(h, o.acts1), *h1 = WS(h, o.h1), *c1 = WS(h, o.c1);
   float *Z = WS(h, o.Z), *acts2 = WS(h, o.acts2), *h2 = WS(h, o.h2), *c2 = WS(h, o.c2), *logits = WS(h, o.logits);
-  gather_features(s, h->tab[split].d, h->d_rows, B, X);
-  split_ws(h, X, (size_t)B * LRCN_F_CNN);
+  gather_features(s, h->tab[split].d, h->d_rows, B, X, SH(h, X).hi, SH(h, X).lo);
   gemm(h, true, true, B, C, LRCN_F_CNN, X, LRCN_F_CNN, Wp(h, 6), LRCN_F_CNN, v, ldv, false, nullptr);  // input*Wcnn  lrcn.jl:558
-  gather_embed(s, Wp(h, 7), h->d_tok_in, R, E, Eall, h->d_sc, train);
-  split_ws(h, Eall, (size_t)R * E);
+  gather_embed(s, Wp(h, 7), h->d_tok_in, R, E, Eall, h->d_sc, train, SH(h, Eall).hi, SH(h, Eall).lo);
   gemm(h, true, true, R, 4 * H1, E, Eall, E, Wp(h, 1), E + H1, acts1, 4 * H1, false, Wp(h, 2));         // x-part of layer 1, all t
-  for (int t = 0; t < T; t++) {
-    float* g = acts1 + (size_t)t * B * 4 * H1;
-    if (t > 0) gemm(h, true, true, B, 4 * H1, H1, h1 + (size_t)t * B * H1, H1, Wp(h, 1) + E, E + H1, g, 4 * H1, true, nullptr);
-    lstm_cell_fwd(s, g, c1 + (size_t)t * B * H1, c1 + (size_t)(t + 1) * B * H1, h1 + (size_t)(t + 1) * B * H1, B, H1);
-    split_ws(h, h1 + (size_t)(t + 1) * B * H1, (size_t)B * H1);
-  }
+  if (h->bf16mode) lstm_permute_weights(s, Wp(h, 1), E + H1, E, H1, h->wp1_hi, h->wp1_lo);
+  for (int t = 0; t < T; t++) lstm_step_fwd(h, 1, t, B, acts1, h1, c1);
   gemm(h, true, true, R, C, H1, h1 + (size_t)B * H1, H1, Wp(h, 5), H1, Z, 2 * C, false, nullptr);         // x*w[end-4]  lrcn.jl:545
-  z_finish(s, Z, v, ldv, R, B, C, h->d_sc, train);  // hcat(x,x_cnn) + dropout                                    lrcn.jl:546-547
-  split_ws(h, Z, (size_t)R * 2 * C);
+  z_finish(s, Z, v, ldv, R, B, C, h->d_sc, train, SH(h, Z).hi, SH(h, Z).lo);  // hcat(x,x_cnn) + dropout          lrcn.jl:546-547
   gemm(h, true, true, R, 4 * H2, 2 * C, Z, 2 * C, Wp(h, 3), 2 * H2, acts2, 4 * H2, false, Wp(h, 4));
-  for (int t = 0; t < T; t++) {
-    float* g = acts2 + (size_t)t * B * 4 * H2;
-    if (t > 0) gemm(h, true, true, B, 4 * H2, H2, h2 + (size_t)t * B * H2, H2, Wp(h, 3) + 2 * C, 2 * H2, g, 4 * H2, true, nullptr);
-    lstm_cell_fwd(s, g, c2 + (size_t)t * B * H2, c2 + (size_t)(t + 1) * B * H2, h2 + (size_t)(t + 1) * B * H2, B, H2);
-    split_ws(h, h2 + (size_t)(t + 1) * B * H2, (size_t)B * H2);
-  }
+  if (h->bf16mode) lstm_permute_weights(s, Wp(h, 3), 2 * H2, 2 * C, H2, h->wp2_hi, h->wp2_lo);
+  for (int t = 0; t < T; t++) lstm_step_fwd(h, 2, t, B, acts2, h2, c2);
   gemm(h, true, true, R, V, H2, h2 + (size_t)B * H2, H2, Wp(h, 8), H2, logits, ldV, false, Wp(h, 9));      // x*w[end-1] .+ w[end]  lrcn.jl:550
-  softmax_ce(s, logits, ldV, R, V, h->d_tok_tgt, WS(h, o.rowlp), h->d_sc, train);                          // logp + gather  lrcn.jl:562-567
+  softmax_ce(s, logits, ldV, R, V, h->d_tok_tgt, WS(h, o.rowlp), h->d_sc, train, SH(h, logits).hi, SH(h, logits).lo);  // logp + gather  lrcn.jl:562-567
   reduce_sum_double(s, WS(h, o.rowlp), R, h->d_loss);
 }
 
@@ -498,36 +536,23 @@ static void enqueue_backward_seg(lrcn_handle* h, int B, int l, bool train, int s
   float *Z = WS(h, o.Z), *dZ = WS(h, o.dZ), *acts2 = WS(h, o.acts2), *h2 = WS(h, o.h2), *c2 = WS(h, o.c2), *dA = WS(h, o.logits);
   float *dh2 = WS(h, o.dh2), *dh1 = WS(h, o.dh1), *dv = WS(h, o.dv), *dE = WS(h, o.dE);
   if (seg == 1) {
-    split_ws(h, dA, (size_t)R * ldV);
     gemm(h, false, false, V, H2, R, dA, ldV, h2 + (size_t)B * H2, H2, Gp(h, 8), H2, false, nullptr);      // dWout = h2' * dA
     colsum(s, dA, ldV, R, V, Gp(h, 9), false);                                                              // dbout
     gemm(h, true, false, R, H2, V, dA, ldV, Wp(h, 8), H2, dh2, H2, false, nullptr);                        // dh2 = dA * Wout'
   } else if (seg == 2) {
     float *dhrec = WS(h, o.dhrec2), *dc = WS(h, o.dc2);
-    for (int t = T - 1; t >= 0; t--) {
-      float* g = acts2 + (size_t)t * B * 4 * H2;
-      lstm_cell_bwd(s, g, c2 + (size_t)t * B * H2, c2 + (size_t)(t + 1) * B * H2, dh2 + (size_t)t * B * H2, dhrec, dc, t == T - 1, B, H2);
-      split_ws(h, g, (size_t)B * 4 * H2);
-      if (t > 0) gemm(h, true, false, B, H2, 4 * H2, g, 4 * H2, Wp(h, 3) + 2 * C, 2 * H2, dhrec, H2, false, nullptr);
-    }
+    for (int t = T - 1; t >= 0; t--) lstm_step_bwd(h, 2, t, T, B, acts2, c2, dh2, dhrec, dc);
     gemm(h, false, false, 4 * H2, 2 * C, R, acts2, 4 * H2, Z, 2 * C, Gp(h, 3), 2 * H2, false, nullptr);          // dW2[:, x-part]
     gemm(h, false, false, 4 * H2, H2, R, acts2, 4 * H2, h2, H2, Gp(h, 3) + 2 * C, 2 * H2, false, nullptr);       // dW2[:, h-part] (slot 0 = 0)
     colsum(s, acts2, 4 * H2, R, 4 * H2, Gp(h, 4), false);
     gemm(h, true, false, R, 2 * C, 4 * H2, acts2, 4 * H2, Wp(h, 3), 2 * H2, dZ, 2 * C, false, nullptr);
-    dz_finish(s, dZ, dv, ldv, T, B, C, h->d_sc, train);
-    split_ws(h, dZ, (size_t)R * 2 * C);
-    split_ws(h, dv, (size_t)B * ldv);
+    dz_finish(s, dZ, dv, ldv, T, B, C, h->d_sc, train, SH(h, dZ).hi, SH(h, dZ).lo, SH(h, dv).hi, SH(h, dv).lo);
     gemm(h, false, false, C, H1, R, dZ, 2 * C, h1 + (size_t)B * H1, H1, Gp(h, 5), H1, false, nullptr);            // dWf
     gemm(h, true, false, R, H1, C, dZ, 2 * C, Wp(h, 5), H1, dh1, H1, false, nullptr);                             // dh1 = dq * Wf'
     gemm(h, false, false, C, LRCN_F_CNN, B, dv, ldv, X, LRCN_F_CNN, Gp(h, 6), LRCN_F_CNN, false, nullptr);        // dWcnn = X' * dv
   } else {
     float *dhrec = WS(h, o.dhrec1), *dc = WS(h, o.dc1);
-    for (int t = T - 1; t >= 0; t--) {
-      float* g = acts1 + (size_t)t * B * 4 * H1;
-      lstm_cell_bwd(s, g, c1 + (size_t)t * B * H1, c1 + (size_t)(t + 1) * B * H1, dh1 + (size_t)t * B * H1, dhrec, dc, t == T - 1, B, H1);
-      split_ws(h, g, (size_t)B * 4 * H1);
-      if (t > 0) gemm(h, true, false, B, H1, 4 * H1, g, 4 * H1, Wp(h, 1) + E, E + H1, dhrec, H1, false, nullptr);
-    }
+    for (int t = T - 1; t >= 0; t--) lstm_step_bwd(h, 1, t, T, B, acts1, c1, dh1, dhrec, dc);
     gemm(h, false, false, 4 * H1, E, R, acts1, 4 * H1, Eall, E, Gp(h, 1), E + H1, false, nullptr);
     gemm(h, false, false, 4 * H1, H1, R, acts1, 4 * H1, h1, H1, Gp(h, 1) + E, E + H1, false, nullptr);
     colsum(s, acts1, 4 * H1, R, 4 * H1, Gp(h, 2), false);
@@ -585,10 +610,11 @@ static void fill_scalars(lrcn_handle* h, int B, int l, float pdrop, uint64_t see
   sc->seed = seed;
   if (bump_adam) h->adam_t += 1;
   const int64_t t = h->adam_t > 0 ? h->adam_t : 1;
-  sc->adam_d1 = (float)(1.0 - pow((double)h->cfg.beta1, (double)t));
-  sc->adam_d2 = (float)(1.0 - pow((double)h->cfg.beta2, (double)t));
-  sc->lr = h->cfg.lr; sc->beta1 = h->cfg.beta1; sc->beta2 = h->cfg.beta2; sc->eps = h->cfg.eps;
-  sc->grad_scale = 1.0f;
+  sc->adam_d1 = (float)(1.0 - pow(h->cfg.beta1, (double)t));
+  sc->adam_d2 = (float)(1.0 - pow(h->cfg.beta2, (double)t));
+  sc->lr = (float)h->cfg.lr; sc->beta1 = (float)h->cfg.beta1; sc->beta2 = (float)h->cfg.beta2; sc->eps = (float)h->cfg.eps;
+  sc->one_m_beta1 = (float)(1.0 - h->cfg.beta1);
+  sc->one_m_beta2 = (float)(1.0 - h->cfg.beta2);
 }
 
 static int nccl_check(int r, const char* what) {
@@ -770,6 +796,21 @@ extern "C" int lrcn_train_step_staged(lrcn_handle* h, int slot, float pdrop, uin
 }
 
 // ------------------------------------------------------------------------------------------ generation
+static void beam_lstm_step(lrcn_handle* h, int layer, int step, int R, float* g, float* h_in, float* c_in, float* h_out, float* c_out) {
+  const int H = layer == 1 ? h->H1 : h->H2;
+  const int ldw = layer == 1 ? h->E + h->H1 : 2 * h->H2, x_off = layer == 1 ? h->E : 2 * h->C;
+  if (h->bf16mode) {
+    bf16 *hi_hi, *hi_lo, *ho_hi, *ho_lo;
+    shadow(h, h_in, &hi_hi, &hi_lo);
+    shadow(h, h_out, &ho_hi, &ho_lo);
+    if (!lstm_fwd_step(h->stream, R, H, step > 1, hi_hi, hi_lo, layer == 1 ? h->wp1_hi : h->wp2_hi, layer == 1 ? h->wp1_lo : h->wp2_lo, g, c_in, c_out,
+                       h_out, ho_hi, ho_lo))
+      throw GemmFail{gemm_bf16x3_last_error()};
+    return;
+  }
+  if (step > 1) sgemm(h->stream, true, true, R, 4 * H, H, h_in, H, Wp(h, layer == 1 ? 1 : 3) + x_off, ldw, g, 4 * H, true, nullptr);
+  lstm_cell_fwd(h->stream, g, c_in, c_out, h_out, R, H);
+}
 static void enqueue_beam_step(lrcn_handle* h, int n_img, int K, int step, int nword, int maxlen, bool flip, float* out_lp) {
   const int R = n_img * K, E = h->E, H1 = h->H1, H2 = h->H2, C = h->C, V = h->V, ldV = h->ldV, ldv = h->ldv;
   const Workspace& o = h->o;
@@ -778,19 +819,13 @@ static void enqueue_beam_step(lrcn_handle* h, int n_img, int K, int step, int nw
   // state ping-pong: "a" holds the beams' current states; the cell writes advanced states into "b"; advance gathers b -> a
   float *h1a = WS(h, o.gh1a), *c1a = WS(h, o.gc1a), *h1b = WS(h, o.gh1b), *c1b = WS(h, o.gc1b);
   float *h2a = WS(h, o.gh2a), *c2a = WS(h, o.gc2a), *h2b = WS(h, o.gh2b), *c2b = WS(h, o.gc2b);
-  gather_embed(s, Wp(h, 7), h->g_last, R, E, e, h->d_sc, false);                                            // Wemb[tok:tok,:]  lrcn.jl:650
-  split_ws(h, e, (size_t)R * E);
+  gather_embed(s, Wp(h, 7), h->g_last, R, E, e, h->d_sc, false, SH(h, e).hi, SH(h, e).lo);                  // Wemb[tok:tok,:]  lrcn.jl:650
   gemm(h, true, true, R, 4 * H1, E, e, E, Wp(h, 1), E + H1, g1, 4 * H1, false, Wp(h, 2));
-  if (step > 1) gemm(h, true, true, R, 4 * H1, H1, h1a, H1, Wp(h, 1) + E, E + H1, g1, 4 * H1, true, nullptr);
-  lstm_cell_fwd(s, g1, c1a, c1b, h1b, R, H1);
-  split_ws(h, h1b, (size_t)R * H1);
+  beam_lstm_step(h, 1, step, R, g1, h1a, c1a, h1b, c1b);
   gemm(h, true, true, R, C, H1, h1b, H1, Wp(h, 5), H1, z, 2 * C, false, nullptr);
-  z_finish(s, z, v, ldv, R, -K, C, h->d_sc, false);  // negative B => image index = row / K
-  split_ws(h, z, (size_t)R * 2 * C);
+  z_finish(s, z, v, ldv, R, -K, C, h->d_sc, false, SH(h, z).hi, SH(h, z).lo);  // negative B => image index = row / K
   gemm(h, true, true, R, 4 * H2, 2 * C, z, 2 * C, Wp(h, 3), 2 * H2, g2, 4 * H2, false, Wp(h, 4));
-  if (step > 1) gemm(h, true, true, R, 4 * H2, H2, h2a, H2, Wp(h, 3) + 2 * C, 2 * H2, g2, 4 * H2, true, nullptr);
-  lstm_cell_fwd(s, g2, c2a, c2b, h2b, R, H2);
-  split_ws(h, h2b, (size_t)R * H2);
+  beam_lstm_step(h, 2, step, R, g2, h2a, c2a, h2b, c2b);
   gemm(h, true, true, R, V, H2, h2b, H2, Wp(h, 8), H2, logits, ldV, false, Wp(h, 9));
   beam_row_topk(s, logits, ldV, R, V, K, WS(h, o.gprob), h->g_ctok, WS(h, o.gcs), WS(h, o.gclp));             // lrcn.jl:652-661
   beam_select(s, h->g_ctok, WS(h, o.gcs), WS(h, o.gclp), n_img, K, step == 1, h->g_stok, h->g_spar, WS(h, o.gss), WS(h, o.gslp));  // :667-668
@@ -847,8 +882,11 @@ extern "C" int lrcn_beam_search(lrcn_handle* h, int split, const int64_t* image_
     CK(cudaMemcpyAsync(h->g_rows, rows.data(), (size_t)ni * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     try {
-      gather_features(h->stream, tb.d, h->g_rows, ni, WS(h, o.gX));
-      split_ws(h, WS(h, o.gX), (size_t)ni * LRCN_F_CNN);
+      if (h->bf16mode) {
+        lstm_permute_weights(h->stream, Wp(h, 1), h->E + h->H1, h->E, h->H1, h->wp1_hi, h->wp1_lo);
+        lstm_permute_weights(h->stream, Wp(h, 3), 2 * h->H2, 2 * h->C, h->H2, h->wp2_hi, h->wp2_lo);
+      }
+      gather_features(h->stream, tb.d, h->g_rows, ni, WS(h, o.gX), SH(h, WS(h, o.gX)).hi, SH(h, WS(h, o.gX)).lo);
       gemm(h, true, true, ni, h->C, LRCN_F_CNN, WS(h, o.gX), LRCN_F_CNN, Wp(h, 6), LRCN_F_CNN, WS(h, o.gv), h->ldv, false, nullptr);  // lrcn.jl:611
       beam_init_kernel<<<(R + 255) / 256, 256, 0, h->stream>>>(R, maxlen, WS(h, o.gprob), h->g_last, h->g_hista, WS(h, o.glpa), h->g_done, h->g_ndone, ni);
       h->counter.n++;
@@ -966,8 +1004,8 @@ extern "C" int lrcn_time_kernel(lrcn_handle* h, const char* name, int reps, floa
         gather_embed(h->stream, Wp(h, 7), h->d_tok_in, R, h->E, WS(h, o.Eall), h->d_sc, false);
         bytes = 2.0 * 4.0 * R * h->E;
       } else if (!strcmp(name, "softmax_ce")) {
-        softmax_ce(h->stream, WS(h, o.logits), h->ldV, R, h->V, h->d_tok_tgt, WS(h, o.rowlp), h->d_sc, true);
-        bytes = 2.0 * 4.0 * R * h->V;
+        softmax_ce(h->stream, WS(h, o.logits), h->ldV, R, h->V, h->d_tok_tgt, WS(h, o.rowlp), h->d_sc, true, SH(h, WS(h, o.logits)).hi, SH(h, WS(h, o.logits)).lo);
+        bytes = (h->bf16mode ? 12.0 : 8.0) * R * h->V;  // read logits, write dA (+ bf16 hi/lo of dA)
       } else {
         return fail(LRCN_ERR_ARG, "unknown kernel family '%s'", name);
       }

@@ -41,7 +41,7 @@ def test_julia_shim_binds_every_symbol():
 def test_config_defaults_mirror_reference():
     cfg = abi.default_config()
     assert (cfg.embed, cfg.hidden1, cfg.hidden2) == (1000, 1000, 1000)  # lrcn.jl:39-40
-    assert abs(cfg.lr - 1e-3) < 1e-9 and abs(cfg.beta1 - 0.9) < 1e-7 and abs(cfg.beta2 - 0.999) < 1e-7  # Knet Adam()
+    assert cfg.lr == 1e-3 and cfg.beta1 == 0.9 and cfg.beta2 == 0.999 and cfg.eps == 1e-8  # Knet Adam()
     assert cfg.max_len == 28  # lrcn.jl:353
 
 

@@ -37,16 +37,16 @@ if __name__ == "__main__":
         one(*a)
         sys.exit(0)
     shapes = [(128, 128, 64), (128, 128, 256), (256, 384, 512), (200, 136, 520), (64, 2048, 512), (1344, 8000, 512), (1000, 500, 7731)]
-    envs = [{}]
-    if "--knobs" in sys.argv:
-        envs = [{}, {"LRCN_MN_LBO": "1024", "LRCN_MN_SBO": "8192"}, {"LRCN_MN_LBO": "8192", "LRCN_MN_SBO": "2048"}]
+    envs = [{"LRCN_GEMM_BN": "128"}, {"LRCN_GEMM_BN": "256"}]
+    if "--quick" in sys.argv:
+        shapes = [(200, 136, 520), (1344, 8000, 512), (1000, 500, 7731)]
     for env in envs:
         print("== env", env, flush=True)
         for prec in (0, 1):
             for (M, N, K) in shapes:
                 for aK in (1, 0):
                     for bK in (1, 0):
-                        if prec == 0 and env:
+                        if prec == 0 and env.get("LRCN_GEMM_BN") == "256":
                             continue
                         e = dict(os.environ)
                         e.update(env)
