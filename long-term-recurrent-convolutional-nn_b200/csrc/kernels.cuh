@@ -97,15 +97,17 @@ void init_simt_kernels();
 
 // ---------------------------------------------------------------- fused LSTM timestep (lstm_sm100.cu)
 bool init_lstm_sm100();
-size_t lstm_permuted_elems(int H);
-// W_h = columns [x_off, x_off+H) of the layer weight W [4H][ldw] -> gate-interleaved bf16 hi/lo copy for lstm_fwd_step
-void lstm_permute_weights(cudaStream_t s, const float* W, int ldw, int x_off, int H, __nv_bfloat16* hi, __nv_bfloat16* lo);
+size_t lstm_permuted_elems(int H);    // elements of the gate-interleaved forward operand (per hi / lo)
+size_t lstm_transposed_elems(int H);  // elements of the transposed backward operand (per hi / lo)
+// W_h = columns [x_off, x_off+H) of the layer weight W [4H][ldw] -> bf16 hi/lo step operands (tr_* may be null)
+void lstm_prepare_weights(cudaStream_t s, const float* W, int ldw, int x_off, int H, __nv_bfloat16* perm_hi, __nv_bfloat16* perm_lo,
+                          __nv_bfloat16* tr_hi, __nv_bfloat16* tr_lo);
 // gates [B][4H] holds x-part + bias on entry and the activated gates on exit; has_rec=false at t=0 (h_0 = 0)
 bool lstm_fwd_step(cudaStream_t s, int B, int H, bool has_rec, const __nv_bfloat16* hprev_hi, const __nv_bfloat16* hprev_lo,
                    const __nv_bfloat16* wperm_hi, const __nv_bfloat16* wperm_lo, float* gates, const float* c_prev, float* c_out,
                    float* h_out, __nv_bfloat16* h_hi, __nv_bfloat16* h_lo);
 // gates [B][4H] holds the step's activations on entry and dG on exit (fp32 + bf16 hi/lo); has_rec=false at t=T-1
-bool lstm_bwd_step(cudaStream_t s, int B, int H, bool has_rec, const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int ldw, int x_off,
+bool lstm_bwd_step(cudaStream_t s, int B, int H, bool has_rec, const __nv_bfloat16* wt_hi, const __nv_bfloat16* wt_lo,
                    const __nv_bfloat16* gnext_hi, const __nv_bfloat16* gnext_lo, float* gates, __nv_bfloat16* g_hi, __nv_bfloat16* g_lo,
                    const float* c_prev, const float* c_cur, const float* dh_in, float* dc);
 

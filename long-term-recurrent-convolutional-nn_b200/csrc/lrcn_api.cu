@@ -112,6 +112,7 @@ struct lrcn_handle {
   float *w = nullptr, *g = nullptr, *m = nullptr, *v = nullptr;
   bf16 *w_hi = nullptr, *w_lo = nullptr;
   bf16 *wp1_hi = nullptr, *wp1_lo = nullptr, *wp2_hi = nullptr, *wp2_lo = nullptr;  // gate-interleaved recurrent weights (lstm_sm100.cu)
+  bf16 *wt1_hi = nullptr, *wt1_lo = nullptr, *wt2_hi = nullptr, *wt2_lo = nullptr;  // transposed recurrent weights for the backward step
   int64_t adam_t = 0;
   Table tab[2];
   Arena ws;
@@ -273,6 +274,10 @@ static int create_impl(const lrcn_config* cfg, lrcn_handle* h) {
     CK(cudaMemset(h->w_hi, 0, h->P * 2)); CK(cudaMemset(h->w_lo, 0, h->P * 2));
     CK(cudaMalloc(&h->wp1_hi, lstm_permuted_elems(h->H1) * 2)); CK(cudaMalloc(&h->wp1_lo, lstm_permuted_elems(h->H1) * 2));
     CK(cudaMalloc(&h->wp2_hi, lstm_permuted_elems(h->H2) * 2)); CK(cudaMalloc(&h->wp2_lo, lstm_permuted_elems(h->H2) * 2));
+    CK(cudaMalloc(&h->wt1_hi, lstm_transposed_elems(h->H1) * 2)); CK(cudaMalloc(&h->wt1_lo, lstm_transposed_elems(h->H1) * 2));
+    CK(cudaMalloc(&h->wt2_hi, lstm_transposed_elems(h->H2) * 2)); CK(cudaMalloc(&h->wt2_lo, lstm_transposed_elems(h->H2) * 2));
+    CK(cudaMemset(h->wt1_hi, 0, lstm_transposed_elems(h->H1) * 2)); CK(cudaMemset(h->wt1_lo, 0, lstm_transposed_elems(h->H1) * 2));
+    CK(cudaMemset(h->wt2_hi, 0, lstm_transposed_elems(h->H2) * 2)); CK(cudaMemset(h->wt2_lo, 0, lstm_transposed_elems(h->H2) * 2));
   }
 
   // ---- workspace arena
@@ -493,11 +498,11 @@ static void lstm_step_bwd(lrcn_handle* h, int layer, int t, int T, int B, float*
   const float *cp = cs + (size_t)t * B * H, *cc = cs + (size_t)(t + 1) * B * H, *dh_in = dh_all + (size_t)t * B * H;
   const bool first = t == T - 1;
   if (h->bf16mode) {
-    bf16 *w_hi, *w_lo, *g_hi, *g_lo, *gn_hi = nullptr, *gn_lo = nullptr;
-    shadow(h, W, &w_hi, &w_lo);
+    bf16 *g_hi, *g_lo, *gn_hi = nullptr, *gn_lo = nullptr;
     shadow(h, g, &g_hi, &g_lo);
     if (!first) shadow(h, g + (size_t)B * 4 * H, &gn_hi, &gn_lo);
-    if (!lstm_bwd_step(h->stream, B, H, !first, w_hi, w_lo, ldw, x_off, gn_hi, gn_lo, g, g_hi, g_lo, cp, cc, dh_in, dc))
+    if (!lstm_bwd_step(h->stream, B, H, !first, layer == 1 ? h->wt1_hi : h->wt2_hi, layer == 1 ? h->wt1_lo : h->wt2_lo, gn_hi, gn_lo, g, g_hi, g_lo,
+                       cp, cc, dh_in, dc))
       throw GemmFail{gemm_bf16x3_last_error()};
     return;
   }
@@ -516,12 +521,12 @@ static void enqueue_forward(lrcn_handle* h, int split, int B, int l, bool train)
   gemm(h, true, true, B, C, LRCN_F_CNN, X, LRCN_F_CNN, Wp(h, 6), LRCN_F_CNN, v, ldv, false, nullptr);  // input*Wcnn  lrcn.jl:558
   gather_embed(s, Wp(h, 7), h->d_tok_in, R, E, Eall, h->d_sc, train, SH(h, Eall).hi, SH(h, Eall).lo);
   gemm(h, true, true, R, 4 * H1, E, Eall, E, Wp(h, 1), E + H1, acts1, 4 * H1, false, Wp(h, 2));         // x-part of layer 1, all t
-  if (h->bf16mode) lstm_permute_weights(s, Wp(h, 1), E + H1, E, H1, h->wp1_hi, h->wp1_lo);
+  if (h->bf16mode) lstm_prepare_weights(s, Wp(h, 1), E + H1, E, H1, h->wp1_hi, h->wp1_lo, train ? h->wt1_hi : nullptr, h->wt1_lo);
   for (int t = 0; t < T; t++) lstm_step_fwd(h, 1, t, B, acts1, h1, c1);
   gemm(h, true, true, R, C, H1, h1 + (size_t)B * H1, H1, Wp(h, 5), H1, Z, 2 * C, false, nullptr);         // x*w[end-4]  lrcn.jl:545
   z_finish(s, Z, v, ldv, R, B, C, h->d_sc, train, SH(h, Z).hi, SH(h, Z).lo);  // hcat(x,x_cnn) + dropout          lrcn.jl:546-547
   gemm(h, true, true, R, 4 * H2, 2 * C, Z, 2 * C, Wp(h, 3), 2 * H2, acts2, 4 * H2, false, Wp(h, 4));
-  if (h->bf16mode) lstm_permute_weights(s, Wp(h, 3), 2 * H2, 2 * C, H2, h->wp2_hi, h->wp2_lo);
+  if (h->bf16mode) lstm_prepare_weights(s, Wp(h, 3), 2 * H2, 2 * C, H2, h->wp2_hi, h->wp2_lo, train ? h->wt2_hi : nullptr, h->wt2_lo);
   for (int t = 0; t < T; t++) lstm_step_fwd(h, 2, t, B, acts2, h2, c2);
   gemm(h, true, true, R, V, H2, h2 + (size_t)B * H2, H2, Wp(h, 8), H2, logits, ldV, false, Wp(h, 9));      // x*w[end-1] .+ w[end]  lrcn.jl:550
   softmax_ce(s, logits, ldV, R, V, h->d_tok_tgt, WS(h, o.rowlp), h->d_sc, train, SH(h, logits).hi, SH(h, logits).lo);  // logp + gather  lrcn.jl:562-567
@@ -883,8 +888,8 @@ extern "C" int lrcn_beam_search(lrcn_handle* h, int split, const int64_t* image_
     CK(cudaStreamSynchronize(h->stream));
     try {
       if (h->bf16mode) {
-        lstm_permute_weights(h->stream, Wp(h, 1), h->E + h->H1, h->E, h->H1, h->wp1_hi, h->wp1_lo);
-        lstm_permute_weights(h->stream, Wp(h, 3), 2 * h->H2, 2 * h->C, h->H2, h->wp2_hi, h->wp2_lo);
+        lstm_prepare_weights(h->stream, Wp(h, 1), h->E + h->H1, h->E, h->H1, h->wp1_hi, h->wp1_lo, nullptr, nullptr);
+        lstm_prepare_weights(h->stream, Wp(h, 3), 2 * h->H2, 2 * h->C, h->H2, h->wp2_hi, h->wp2_lo, nullptr, nullptr);
       }
       gather_features(h->stream, tb.d, h->g_rows, ni, WS(h, o.gX), SH(h, WS(h, o.gX)).hi, SH(h, WS(h, o.gX)).lo);
       gemm(h, true, true, ni, h->C, LRCN_F_CNN, WS(h, o.gX), LRCN_F_CNN, Wp(h, 6), LRCN_F_CNN, WS(h, o.gv), h->ldv, false, nullptr);  // lrcn.jl:611

@@ -1,17 +1,24 @@
-// lstm_sm100.cu -- one LSTM timestep as ONE tcgen05 kernel: recurrent gate GEMM (bf16 hi/lo split, fp32 TMEM
+// lstm_sm100.cu -- one LSTM timestep as ONE tcgen05 kernel: recurrent GEMM (bf16 hi/lo split, fp32 TMEM
 // accumulate) fused with the sigmoid/tanh cell update (forward) or with the cell adjoint (backward).
 // Reference semantics: lstm() lrcn.jl:528-538 (gate order [forget|ingate|outgate|change]) and its adjoint
 // (SURVEY.md §10.2).  The x-part of the gates (input projection + bias) is precomputed for all timesteps by
-// one large GEMM (teacher forcing), so a step only has the h_{t-1} * W_h product left.
+// one large GEMM (teacher forcing), so a step only has the recurrent product left:
+//   forward : G_t[m][n]     += sum_k h_{t-1}[m][k] * W_h[k][n]          (K = H,  N = 4H)
+//   backward: dh_rec[m][j]   = sum_n dG_{t+1}[m][n] * W_h[j][n]         (K = 4H, N = H)
 //
-// forward  (per step t, layer with hidden size H, batch B):
-//   tile = 128 batch rows x (4 gates x 16 hidden units); B operand = W_h rows permuted so that a CTA's 64 columns
-//   are [f(16) i(16) o(16) g(16)] of the same 16 units -> a thread (= batch row, TMEM lane) owns all four gates
-//   of its 16 units and finishes c_t, h_t in registers.  grid = (H/16, B/128).
-// backward (per step t): dh_rec^T[j][m] = sum_n W_h[n][j] * dG_{t+1}[m][n]   ("swap-AB": M = 128 hidden units from
-//   the MN-major weight view, N = 32 batch rows), epilogue thread = hidden unit j: dh = dh_in + dh_rec, cell adjoint,
-//   writes dG_t (fp32 in place over the stored activations + bf16 hi/lo for the next step) and dc.  grid = (H/128, B/32).
-//   All epilogue global accesses are coalesced over j.
+// These products are skinny (M = batch), strictly sequential and bound by operand delivery, not by MMA rate:
+// a single SM's TMA engine sustains ~55 GB/s and its shared-memory port 128 B/clk (measured, profiles/).
+// So the step is spread over as many SMs as possible with the smallest per-CTA operand footprint:
+//   * CTA tile = 64 batch rows (UMMA M=64) x NT columns; grid = (N/NT, B/64), up to 128 CTAs;
+//   * the 8 CTAs of a thread-block cluster share the same 64 batch rows: each one TMA-loads 1/8 of the
+//     activation tile and MULTICASTS it to all 8 (cp.async.bulk.tensor ... .multicast::cluster), so the
+//     activation tile costs every SM 1/8 of its bytes; stage release is a multicast tcgen05.commit to the
+//     empty barriers of all 8 CTAs;
+//   * the weight operand is a K-major bf16 hi/lo copy laid out for the step (gate-interleaved rows for the
+//     forward step so one thread owns f,i,o,g of its 16 units; transposed for the backward step), refreshed
+//     once per training step.
+// Epilogue: thread = batch row (TMEM lane), finishes its units in registers and writes c_t/h_t (+bf16 split
+// of h_t) or dG_t (fp32 in place over the stored activations, + bf16 split) and dc.
 #include "kernels.cuh"
 #include "sm100_ptx.cuh"
 
@@ -20,142 +27,255 @@
 namespace lrcn {
 using namespace ptx;
 
-constexpr int LBK = 64;
-constexpr int L_A_TILE = 128 * LBK * 2;  // 16 KiB
-constexpr int L_THREADS = 192;
+constexpr int LBK = 64;          // k-block (bf16 elements) = one 128-byte swizzle row
+constexpr int LM = 64;           // batch rows per CTA (UMMA M)
+constexpr int CL = 8;            // cluster size: CTAs sharing one activation tile
+constexpr int L_THREADS = 192;   // warp 0 TMA, warp 1 MMA/TMEM, warps 2-5 epilogue
+constexpr int A_HALF = LM * LBK * 2;        // 8 KiB: one of {hi, lo} of the activation k-block
+constexpr int A_SLICE = (LM / CL) * LBK * 2;  // 1 KiB: the 8 rows this CTA loads and multicasts
 
-// ---------------------------------------------------------------------------------------------- forward
-constexpr int F_NH = 16, F_BN = 4 * F_NH;            // 64 gate columns per CTA
-constexpr int F_B_TILE = F_BN * LBK * 2;             // 8 KiB
-constexpr int F_STAGE = 2 * L_A_TILE + 2 * F_B_TILE; // 48 KiB
-constexpr int F_STAGES = 4;
-constexpr int F_SMEM = F_STAGES * F_STAGE + 1024 + 256;
-
-struct LstmFwdParams {
-  int B, H, num_kb, has_rec;
-  float* gates;         // [B][4H] pre-activations (x-part + bias) in, activations out
-  const float* c_prev;  // [B][H]
-  float* c_out;         // [B][H]
-  float* h_out;         // [B][H]
-  __nv_bfloat16* h_hi;  // bf16 split of h_out (A operand of the next step and of the batched GEMMs), may be null
-  __nv_bfloat16* h_lo;
+template <int NT>
+struct StepCfg {
+  static constexpr int B_HALF = NT * LBK * 2;
+  static constexpr int STAGE = 2 * A_HALF + 2 * B_HALF;
+  static constexpr int STAGES = NT >= 64 ? 6 : 8;
+  static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+  static constexpr uint32_t TMEM_COLS = NT < 32 ? 32 : NT;
 };
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+#define LRCN_TMEM_LD_16(taddr, v)                                                                                          \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"   \
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), \
+                 "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                    \
+               : "r"(taddr)                                                                                                \
+               : "memory")
 
 __device__ __forceinline__ float sigm_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-__global__ void __launch_bounds__(L_THREADS, 1)
-lstm_fwd_step_kernel(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant__ CUtensorMap tmH_lo,
-                     const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, const LstmFwdParams p) {
+struct StepParams {
+  int B, H, num_kb, has_rec;
+  // forward
+  float* gates;              // [B][4H]: fwd: x-part + bias in, activations out;  bwd: activations in, dG out
+  const float* c_prev;       // [B][H]  c_{t-1}
+  float* c_out;              // fwd: c_t
+  float* h_out;              // fwd: h_t
+  __nv_bfloat16* o_hi;       // fwd: bf16 split of h_t [B][H];  bwd: bf16 split of dG_t [B][4H]   (may be null)
+  __nv_bfloat16* o_lo;
+  // backward
+  const float* c_cur;        // c_t
+  const float* dh_in;        // dL/dh_t from the layer above
+  float* dc;                 // carry: in dL/dc_t, out dL/dc_{t-1}
+};
+
+// mainloop shared by both directions: A = activation tile [64 rows][K] (multicast), B = weight rows [NT][K]
+template <int NT, bool FWD>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(L_THREADS, 1)
+lstm_step_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const StepParams p) {
+  using Cfg = StepCfg<NT>;
+  constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // same offset in every CTA of the cluster
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + F_STAGES * F_STAGE);
-  const uint32_t full_bar0 = smem_u32(bars), empty_bar0 = smem_u32(bars + F_STAGES), tfull_bar = smem_u32(bars + 2 * F_STAGES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * F_STAGES + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + STAGES * Cfg::STAGE);
+  const uint32_t full_bar0 = smem_u32(bars), empty_bar0 = smem_u32(bars + STAGES), tfull_bar = smem_u32(bars + 2 * STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int jt = blockIdx.x, m0 = blockIdx.y * 128;
+  const uint32_t rank = cluster_ctarank();
+  const int nt = blockIdx.x, m0 = blockIdx.y * LM;
   const int num_kb = p.has_rec ? p.num_kb : 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < F_STAGES; s++) { mbar_init(full_bar0 + 8 * s, 1); mbar_init(empty_bar0 + 8 * s, 1); }
+    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar0 + 8 * s, 1); mbar_init(empty_bar0 + 8 * s, CL); }
     mbar_init(tfull_bar, 1);
     mbar_init_fence();
   }
   if (warp == 0 && lane == 0 && num_kb > 0) {
-    prefetch_tensormap(&tmH_hi); prefetch_tensormap(&tmH_lo); prefetch_tensormap(&tmW_hi); prefetch_tensormap(&tmW_lo);
+    prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmA_lo); prefetch_tensormap(&tmB_hi); prefetch_tensormap(&tmB_lo);
   }
-  if (warp == 1) tmem_alloc<F_BN>(smem_u32(tmem_slot));
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // every CTA's barriers are initialised before any peer multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
       for (int i = 0; i < num_kb; i++) {
-        const int s = i % F_STAGES;
-        mbar_wait(empty_bar0 + 8 * s, ((i / F_STAGES) & 1) ^ 1);
+        const int s = i % STAGES;
+        mbar_wait(empty_bar0 + 8 * s, ((i / STAGES) & 1) ^ 1);  // all CL CTAs have consumed this stage
         const uint32_t full = full_bar0 + 8 * s;
-        mbar_expect_tx(full, F_STAGE);
-        const uint32_t st = smem_base + s * F_STAGE;
-        tma_load_2d(st, &tmH_hi, full, i * LBK, m0);
-        tma_load_2d(st + L_A_TILE, &tmH_lo, full, i * LBK, m0);
-        tma_load_2d(st + 2 * L_A_TILE, &tmW_hi, full, i * LBK, jt * F_BN);
-        tma_load_2d(st + 2 * L_A_TILE + F_B_TILE, &tmW_lo, full, i * LBK, jt * F_BN);
+        mbar_expect_tx(full, Cfg::STAGE);  // 8 multicast slices of A (hi, lo) + own B (hi, lo)
+        const uint32_t st = smem_base + s * Cfg::STAGE;
+        const int k0 = i * LBK;
+        const int arow = m0 + (int)rank * (LM / CL);
+        tma_load_2d_mcast(st + rank * A_SLICE, &tmA_hi, full, k0, arow, (uint16_t)0xFF);
+        tma_load_2d_mcast(st + A_HALF + rank * A_SLICE, &tmA_lo, full, k0, arow, (uint16_t)0xFF);
+        tma_load_2d(st + 2 * A_HALF, &tmB_hi, full, k0, nt * NT);
+        tma_load_2d(st + 2 * A_HALF + Cfg::B_HALF, &tmB_lo, full, k0, nt * NT);
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && num_kb > 0) {
-      const uint32_t idesc = idesc_bf16(128, F_BN, false, false);
+      const uint32_t idesc = idesc_bf16(LM, NT, false, false);
       for (int i = 0; i < num_kb; i++) {
-        const int s = i % F_STAGES;
-        mbar_wait(full_bar0 + 8 * s, (i / F_STAGES) & 1);
+        const int s = i % STAGES;
+        mbar_wait(full_bar0 + 8 * s, (i / STAGES) & 1);
         tc_fence_after();
-        const uint32_t st = smem_base + s * F_STAGE;
+        const uint32_t st = smem_base + s * Cfg::STAGE;
 #pragma unroll
         for (int k = 0; k < LBK / 16; k++) {
-          const uint64_t a_hi = desc_kmajor(st, k), a_lo = desc_kmajor(st + L_A_TILE, k);
-          const uint64_t b_hi = desc_kmajor(st + 2 * L_A_TILE, k), b_lo = desc_kmajor(st + 2 * L_A_TILE + F_B_TILE, k);
+          const uint64_t a_hi = desc_kmajor(st, k), a_lo = desc_kmajor(st + A_HALF, k);
+          const uint64_t b_hi = desc_kmajor(st + 2 * A_HALF, k), b_lo = desc_kmajor(st + 2 * A_HALF + Cfg::B_HALF, k);
           umma_bf16(tmem_base, a_lo, b_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
           umma_bf16(tmem_base, a_hi, b_lo, idesc, 1u);
           umma_bf16(tmem_base, a_hi, b_hi, idesc, 1u);
         }
-        umma_commit(empty_bar0 + 8 * s);
+        umma_commit_mcast(empty_bar0 + 8 * s, (uint16_t)0xFF);  // this stage is free in MY smem: tell all CL producers
       }
       umma_commit(tfull_bar);
     }
   } else {
+    // UMMA M=64 accumulator layout: row r of the tile lives in TMEM lane (r%16) + 32*(r/16)  (cute tmem_frg, M_MMA == 64)
     const int quad = warp & 3;
-    const int m = m0 + quad * 32 + lane;
-    uint32_t v[64];
-    if (num_kb > 0) {
-      mbar_wait(tfull_bar, 0);
-      tc_fence_after();
-      LRCN_TMEM_LD_32(tmem_base + ((uint32_t)(quad * 32) << 16), v);
-      { uint32_t* v2 = v + 32; LRCN_TMEM_LD_32(tmem_base + ((uint32_t)(quad * 32) << 16) + 32u, v2); }
-      tmem_ld_wait();
-    } else {
+    const int m = m0 + quad * 16 + lane;
+    const bool active = lane < 16 && m < p.B;
+    const int H = p.H;
+    if (FWD) {
+      uint32_t v[64];
+      if (num_kb > 0) {
+        mbar_wait(tfull_bar, 0);
+        tc_fence_after();
+        LRCN_TMEM_LD_32(tmem_base + ((uint32_t)(quad * 32) << 16), v);
+        { uint32_t* v2 = v + 32; LRCN_TMEM_LD_32(tmem_base + ((uint32_t)(quad * 32) << 16) + 32u, v2); }
+        tmem_ld_wait();
+      } else {
 #pragma unroll
-      for (int j = 0; j < 64; j++) v[j] = 0u;
-    }
-    const int H = p.H, j0 = jt * F_NH;
-    if (m < p.B) {
-      float* grow = p.gates + (size_t)m * 4 * H;
-      const size_t hidx = (size_t)m * H + j0;
+        for (int j = 0; j < 64; j++) v[j] = 0u;
+      }
+      constexpr int NH = NT / 4;  // hidden units per CTA; columns are [f(NH) i(NH) o(NH) g(NH)]
+      const int j0 = nt * NH;
+      if (active) {
+        float* grow = p.gates + (size_t)m * 4 * H;
+        const size_t hidx = (size_t)m * H + j0;
 #pragma unroll
-      for (int q = 0; q < F_NH / 4; q++) {  // 4 units at a time (H % 4 == 0 -> a float4 never straddles H)
-        const int j = j0 + 4 * q;
-        if (j < H) {
-          float4 gf = *reinterpret_cast<const float4*>(grow + j);
-          float4 gi = *reinterpret_cast<const float4*>(grow + H + j);
-          float4 go = *reinterpret_cast<const float4*>(grow + 2 * H + j);
-          float4 gg = *reinterpret_cast<const float4*>(grow + 3 * H + j);
-          const float4 cp = *reinterpret_cast<const float4*>(p.c_prev + hidx + 4 * q);
-          float f[4] = {gf.x, gf.y, gf.z, gf.w}, in[4] = {gi.x, gi.y, gi.z, gi.w}, o[4] = {go.x, go.y, go.z, go.w}, ch[4] = {gg.x, gg.y, gg.z, gg.w};
-          const float cpv[4] = {cp.x, cp.y, cp.z, cp.w};
-          float cn[4], hn[4];
+        for (int q = 0; q < NH / 4; q++) {  // 4 units at a time (H % 4 == 0: a float4 never straddles H)
+          const int j = j0 + 4 * q;
+          if (j < H) {
+            const float4 gf = *reinterpret_cast<const float4*>(grow + j);
+            const float4 gi = *reinterpret_cast<const float4*>(grow + H + j);
+            const float4 go = *reinterpret_cast<const float4*>(grow + 2 * H + j);
+            const float4 gg = *reinterpret_cast<const float4*>(grow + 3 * H + j);
+            const float4 cp = *reinterpret_cast<const float4*>(p.c_prev + hidx + 4 * q);
+            float f[4] = {gf.x, gf.y, gf.z, gf.w}, in[4] = {gi.x, gi.y, gi.z, gi.w}, o[4] = {go.x, go.y, go.z, go.w}, ch[4] = {gg.x, gg.y, gg.z, gg.w};
+            const float cpv[4] = {cp.x, cp.y, cp.z, cp.w};
+            float cn[4], hn[4];
 #pragma unroll
-          for (int e = 0; e < 4; e++) {
-            const int u = 4 * q + e;
-            f[e] = sigm_f(f[e] + __uint_as_float(v[u]));
-            in[e] = sigm_f(in[e] + __uint_as_float(v[F_NH + u]));
-            o[e] = sigm_f(o[e] + __uint_as_float(v[2 * F_NH + u]));
-            ch[e] = tanhf(ch[e] + __uint_as_float(v[3 * F_NH + u]));
-            cn[e] = cpv[e] * f[e] + in[e] * ch[e];
-            hn[e] = o[e] * tanhf(cn[e]);
+            for (int e = 0; e < 4; e++) {
+              const int u = 4 * q + e;
+              f[e] = sigm_f(f[e] + __uint_as_float(v[u]));
+              in[e] = sigm_f(in[e] + __uint_as_float(v[NH + u]));
+              o[e] = sigm_f(o[e] + __uint_as_float(v[2 * NH + u]));
+              ch[e] = tanhf(ch[e] + __uint_as_float(v[3 * NH + u]));
+              cn[e] = cpv[e] * f[e] + in[e] * ch[e];
+              hn[e] = o[e] * tanhf(cn[e]);
+            }
+            *reinterpret_cast<float4*>(grow + j) = make_float4(f[0], f[1], f[2], f[3]);
+            *reinterpret_cast<float4*>(grow + H + j) = make_float4(in[0], in[1], in[2], in[3]);
+            *reinterpret_cast<float4*>(grow + 2 * H + j) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(grow + 3 * H + j) = make_float4(ch[0], ch[1], ch[2], ch[3]);
+            *reinterpret_cast<float4*>(p.c_out + hidx + 4 * q) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+            *reinterpret_cast<float4*>(p.h_out + hidx + 4 * q) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+            if (p.o_hi) {
+              __nv_bfloat16 hh[4], ll[4];
+#pragma unroll
+              for (int e = 0; e < 4; e++) split_bf16(hn[e], hh[e], ll[e]);
+              *reinterpret_cast<uint2*>(p.o_hi + hidx + 4 * q) = *reinterpret_cast<uint2*>(hh);
+              *reinterpret_cast<uint2*>(p.o_lo + hidx + 4 * q) = *reinterpret_cast<uint2*>(ll);
+            }
           }
-          *reinterpret_cast<float4*>(grow + j) = make_float4(f[0], f[1], f[2], f[3]);
-          *reinterpret_cast<float4*>(grow + H + j) = make_float4(in[0], in[1], in[2], in[3]);
-          *reinterpret_cast<float4*>(grow + 2 * H + j) = make_float4(o[0], o[1], o[2], o[3]);
-          *reinterpret_cast<float4*>(grow + 3 * H + j) = make_float4(ch[0], ch[1], ch[2], ch[3]);
-          *reinterpret_cast<float4*>(p.c_out + hidx + 4 * q) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-          *reinterpret_cast<float4*>(p.h_out + hidx + 4 * q) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-          if (p.h_hi) {
-            __nv_bfloat16 hh[4], ll[4];
+        }
+      }
+    } else {
+      uint32_t v[16];
+      if (num_kb > 0) {
+        mbar_wait(tfull_bar, 0);
+        tc_fence_after();
+        LRCN_TMEM_LD_16(tmem_base + ((uint32_t)(quad * 32) << 16), v);
+        tmem_ld_wait();
+      } else {
 #pragma unroll
-            for (int e = 0; e < 4; e++) split_bf16(hn[e], hh[e], ll[e]);
-            *reinterpret_cast<uint2*>(p.h_hi + hidx + 4 * q) = *reinterpret_cast<uint2*>(hh);
-            *reinterpret_cast<uint2*>(p.h_lo + hidx + 4 * q) = *reinterpret_cast<uint2*>(ll);
+        for (int j = 0; j < 16; j++) v[j] = 0u;
+      }
+      const int j0 = nt * NT;  // NT hidden units per CTA (16)
+      if (active) {
+        float* grow = p.gates + (size_t)m * 4 * H;
+        const size_t hidx = (size_t)m * H + j0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int j = j0 + 4 * q;
+          if (j < H) {
+            const float4 gf = *reinterpret_cast<const float4*>(grow + j);
+            const float4 gi = *reinterpret_cast<const float4*>(grow + H + j);
+            const float4 go = *reinterpret_cast<const float4*>(grow + 2 * H + j);
+            const float4 gg = *reinterpret_cast<const float4*>(grow + 3 * H + j);
+            const float4 cpv4 = *reinterpret_cast<const float4*>(p.c_prev + hidx + 4 * q);
+            const float4 ccv4 = *reinterpret_cast<const float4*>(p.c_cur + hidx + 4 * q);
+            const float4 dhv4 = *reinterpret_cast<const float4*>(p.dh_in + hidx + 4 * q);
+            float4 dcv4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.has_rec) dcv4 = *reinterpret_cast<const float4*>(p.dc + hidx + 4 * q);
+            const float f[4] = {gf.x, gf.y, gf.z, gf.w}, in[4] = {gi.x, gi.y, gi.z, gi.w}, o[4] = {go.x, go.y, go.z, go.w}, ch[4] = {gg.x, gg.y, gg.z, gg.w};
+            const float cpv[4] = {cpv4.x, cpv4.y, cpv4.z, cpv4.w}, ccv[4] = {ccv4.x, ccv4.y, ccv4.z, ccv4.w};
+            const float dhv[4] = {dhv4.x, dhv4.y, dhv4.z, dhv4.w}, dci[4] = {dcv4.x, dcv4.y, dcv4.z, dcv4.w};
+            float r0[4], r1[4], r2[4], r3[4], dco[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const float dh = dhv[e] + __uint_as_float(v[4 * q + e]);
+              const float tc = tanhf(ccv[e]);
+              const float dcv = dci[e] + dh * o[e] * (1.f - tc * tc);
+              const float dO = dh * tc, dF = dcv * cpv[e], dI = dcv * ch[e], dG = dcv * in[e];
+              dco[e] = dcv * f[e];
+              r0[e] = dF * f[e] * (1.f - f[e]);
+              r1[e] = dI * in[e] * (1.f - in[e]);
+              r2[e] = dO * o[e] * (1.f - o[e]);
+              r3[e] = dG * (1.f - ch[e] * ch[e]);
+            }
+            *reinterpret_cast<float4*>(p.dc + hidx + 4 * q) = make_float4(dco[0], dco[1], dco[2], dco[3]);
+            *reinterpret_cast<float4*>(grow + j) = make_float4(r0[0], r0[1], r0[2], r0[3]);
+            *reinterpret_cast<float4*>(grow + H + j) = make_float4(r1[0], r1[1], r1[2], r1[3]);
+            *reinterpret_cast<float4*>(grow + 2 * H + j) = make_float4(r2[0], r2[1], r2[2], r2[3]);
+            *reinterpret_cast<float4*>(grow + 3 * H + j) = make_float4(r3[0], r3[1], r3[2], r3[3]);
+            if (p.o_hi) {
+              const size_t gidx = (size_t)m * 4 * H + j;
+              const float* rr[4] = {r0, r1, r2, r3};
+#pragma unroll
+              for (int g = 0; g < 4; g++) {
+                __nv_bfloat16 hh[4], ll[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) split_bf16(rr[g][e], hh[e], ll[e]);
+                *reinterpret_cast<uint2*>(p.o_hi + gidx + (size_t)g * H) = *reinterpret_cast<uint2*>(hh);
+                *reinterpret_cast<uint2*>(p.o_lo + gidx + (size_t)g * H) = *reinterpret_cast<uint2*>(ll);
+              }
+            }
           }
         }
       }
@@ -163,18 +283,23 @@ lstm_fwd_step_kernel(const __grid_constant__ CUtensorMap tmH_hi, const __grid_co
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // no CTA leaves while a peer may still multicast into its smem or arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<F_BN>(tmem_base);
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
-// W_h (rows = gate columns n = g*H + j of the reference's (X+H) x 4H weight, K-major with pitch ldw, columns
-// [x_off, x_off+H)) -> permuted bf16 hi/lo [ceil(H/16)*64][Hp]: row (jt*4 + g)*16 + u  <-  n = g*H + jt*16 + u
+// ---------------------------------------------------------------------------------------------- weight copies
+constexpr int F_NT = 64, F_NH = 16;  // forward: 16 hidden units x 4 gates per CTA
+constexpr int R_NT = 16;             // backward: 16 hidden units per CTA
+
+// forward operand: rows = gate columns n = g*H + j of the layer weight W [4H][ldw] (columns [x_off, x_off+H) = W_h),
+// permuted so that CTA nt's 64 rows are [f i o g] x its 16 units:  row (jt*4 + g)*16 + u  <-  n = g*H + jt*16 + u
 __global__ void permute_split_kernel(const float* __restrict__ W, int ldw, int x_off, int H, int Hp, __nv_bfloat16* __restrict__ hi,
                                      __nv_bfloat16* __restrict__ lo) {
-  const int row = blockIdx.x;  // permuted row
-  const int jt = row / F_BN, r = row % F_BN, g = r / F_NH, u = r % F_NH;
+  const int row = blockIdx.x;
+  const int jt = row / F_NT, r = row % F_NT, g = r / F_NH, u = r % F_NH;
   const int j = jt * F_NH + u;
   for (int k = threadIdx.x; k < Hp; k += blockDim.x) {
     float x = 0.f;
@@ -185,195 +310,95 @@ __global__ void permute_split_kernel(const float* __restrict__ W, int ldw, int x
     lo[(size_t)row * Hp + k] = l;
   }
 }
-void lstm_permute_weights(cudaStream_t s, const float* W, int ldw, int x_off, int H, __nv_bfloat16* hi, __nv_bfloat16* lo) {
-  const int rows = (H + F_NH - 1) / F_NH * F_BN;
-  const int Hp = (H + 7) / 8 * 8;
-  permute_split_kernel<<<rows, 128, 0, s>>>(W, ldw, x_off, H, Hp, hi, lo);
-  if (g_counter) g_counter->n++;
+// backward operand: WhT[j][n] = W[n][x_off + j]  ([Hr rows][4H], K-major over the gate columns n)
+__global__ void transpose_split_kernel(const float* __restrict__ W, int ldw, int x_off, int H, __nv_bfloat16* __restrict__ hi,
+                                       __nv_bfloat16* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  const int n0 = blockIdx.x * 32, j0 = blockIdx.y * 32;  // n over 4H, j over Hr
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int n = n0 + r, j = j0 + threadIdx.x;
+    tile[r][threadIdx.x] = (n < 4 * H && j < H) ? W[(size_t)n * ldw + x_off + j] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int j = j0 + r, n = n0 + threadIdx.x;
+    if (n < 4 * H) {
+      __nv_bfloat16 h, l;
+      split_bf16(tile[threadIdx.x][r], h, l);
+      hi[(size_t)j * 4 * H + n] = h;
+      lo[(size_t)j * 4 * H + n] = l;
+    }
+  }
 }
-size_t lstm_permuted_elems(int H) { return (size_t)((H + F_NH - 1) / F_NH * F_BN) * ((H + 7) / 8 * 8); }
+static int fwd_rows(int H) { return (H + F_NH - 1) / F_NH * F_NT; }
+static int bwd_rows(int H) { return (H + 31) / 32 * 32; }
+size_t lstm_permuted_elems(int H) { return (size_t)fwd_rows(H) * ((H + 7) / 8 * 8); }
+size_t lstm_transposed_elems(int H) { return (size_t)bwd_rows(H) * 4 * H; }
+
+void lstm_prepare_weights(cudaStream_t s, const float* W, int ldw, int x_off, int H, __nv_bfloat16* perm_hi, __nv_bfloat16* perm_lo,
+                          __nv_bfloat16* tr_hi, __nv_bfloat16* tr_lo) {
+  const int Hp = (H + 7) / 8 * 8;
+  permute_split_kernel<<<fwd_rows(H), 128, 0, s>>>(W, ldw, x_off, H, Hp, perm_hi, perm_lo);
+  if (g_counter) g_counter->n++;
+  if (tr_hi) {
+    dim3 grid((4 * H + 31) / 32, bwd_rows(H) / 32);
+    transpose_split_kernel<<<grid, dim3(32, 8), 0, s>>>(W, ldw, x_off, H, tr_hi, tr_lo);
+    if (g_counter) g_counter->n++;
+  }
+}
+
+static bool check_launch(const char* what) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { set_sm100_error((std::string(what) + ": " + cudaGetErrorString(e)).c_str()); return false; }
+  return true;
+}
 
 bool lstm_fwd_step(cudaStream_t s, int B, int H, bool has_rec, const __nv_bfloat16* hprev_hi, const __nv_bfloat16* hprev_lo,
                    const __nv_bfloat16* wperm_hi, const __nv_bfloat16* wperm_lo, float* gates, const float* c_prev, float* c_out, float* h_out,
                    __nv_bfloat16* h_hi, __nv_bfloat16* h_lo) {
-  const int Hp = (H + 7) / 8 * 8;
-  const int rows = (H + F_NH - 1) / F_NH * F_BN;
-  CUtensorMap th_hi, th_lo, tw_hi, tw_lo;
+  const int Hp = (H + 7) / 8 * 8, rows = fwd_rows(H);
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  if (!get_tensor_map_bf16(&tb_hi, wperm_hi, H, rows, Hp, F_NT) || !get_tensor_map_bf16(&tb_lo, wperm_lo, H, rows, Hp, F_NT)) return false;
   if (has_rec) {
-    if (!get_tensor_map_bf16(&th_hi, hprev_hi, H, B, H, 128) || !get_tensor_map_bf16(&th_lo, hprev_lo, H, B, H, 128)) return false;
-  } else {  // never dereferenced, but the kernel parameters must be valid maps
-    if (!get_tensor_map_bf16(&th_hi, wperm_hi, H, rows, Hp, 128) || !get_tensor_map_bf16(&th_lo, wperm_lo, H, rows, Hp, 128)) return false;
+    if (!get_tensor_map_bf16(&ta_hi, hprev_hi, H, B, H, LM / CL) || !get_tensor_map_bf16(&ta_lo, hprev_lo, H, B, H, LM / CL)) return false;
+  } else {  // never dereferenced (no mainloop), but kernel parameters must be valid maps
+    ta_hi = tb_hi; ta_lo = tb_lo;
   }
-  if (!get_tensor_map_bf16(&tw_hi, wperm_hi, H, rows, Hp, F_BN) || !get_tensor_map_bf16(&tw_lo, wperm_lo, H, rows, Hp, F_BN)) return false;
-  LstmFwdParams p;
+  StepParams p{};
   p.B = B; p.H = H; p.num_kb = (H + LBK - 1) / LBK; p.has_rec = has_rec ? 1 : 0;
-  p.gates = gates; p.c_prev = c_prev; p.c_out = c_out; p.h_out = h_out; p.h_hi = h_hi; p.h_lo = h_lo;
-  dim3 grid((H + F_NH - 1) / F_NH, (B + 127) / 128);
-  lstm_fwd_step_kernel<<<grid, L_THREADS, F_SMEM, s>>>(th_hi, th_lo, tw_hi, tw_lo, p);
+  p.gates = gates; p.c_prev = c_prev; p.c_out = c_out; p.h_out = h_out; p.o_hi = h_hi; p.o_lo = h_lo;
+  const int nt = (H + F_NH - 1) / F_NH;
+  dim3 grid((nt + CL - 1) / CL * CL, (B + LM - 1) / LM);
+  lstm_step_kernel<F_NT, true><<<grid, L_THREADS, StepCfg<F_NT>::SMEM, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
   if (g_counter) g_counter->n++;
-  cudaError_t e = cudaPeekAtLastError();
-  if (e != cudaSuccess) { set_sm100_error((std::string("lstm_fwd_step launch: ") + cudaGetErrorString(e)).c_str()); return false; }
-  return true;
+  return check_launch("lstm_fwd_step launch");
 }
 
-// ---------------------------------------------------------------------------------------------- backward
-constexpr int R_BN = 32;                              // batch rows per CTA (UMMA N)
-constexpr int R_B_TILE = R_BN * LBK * 2;              // 4 KiB
-constexpr int R_STAGE = 2 * L_A_TILE + 2 * R_B_TILE;  // 40 KiB
-constexpr int R_STAGES = 5;
-constexpr int R_SMEM = R_STAGES * R_STAGE + 1024 + 256;
-
-struct LstmBwdParams {
-  int B, H, num_kb, has_rec;
-  float* gates;          // [B][4H]: activations (f,i,o,g) in, dG out
-  __nv_bfloat16* g_hi;   // bf16 split of dG (B operand of the next step, A/B operand of the batched gradient GEMMs)
-  __nv_bfloat16* g_lo;
-  const float* c_prev;   // c_{t-1}
-  const float* c_cur;    // c_t
-  const float* dh_in;    // dL/dh_t from the layer above
-  float* dc;             // carry: in dL/dc_t (from step t+1), out dL/dc_{t-1}
-};
-
-__global__ void __launch_bounds__(L_THREADS, 1)
-lstm_bwd_step_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
-                     const __grid_constant__ CUtensorMap tmG_hi, const __grid_constant__ CUtensorMap tmG_lo, const LstmBwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + R_STAGES * R_STAGE);
-  const uint32_t full_bar0 = smem_u32(bars), empty_bar0 = smem_u32(bars + R_STAGES), tfull_bar = smem_u32(bars + 2 * R_STAGES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * R_STAGES + 1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j0 = blockIdx.x * 128, m0 = blockIdx.y * R_BN;
-  const int num_kb = p.has_rec ? p.num_kb : 0;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < R_STAGES; s++) { mbar_init(full_bar0 + 8 * s, 1); mbar_init(empty_bar0 + 8 * s, 1); }
-    mbar_init(tfull_bar, 1);
-    mbar_init_fence();
-  }
-  if (warp == 0 && lane == 0 && num_kb > 0) {
-    prefetch_tensormap(&tmW_hi); prefetch_tensormap(&tmW_lo); prefetch_tensormap(&tmG_hi); prefetch_tensormap(&tmG_lo);
-  }
-  if (warp == 1) tmem_alloc<R_BN>(smem_u32(tmem_slot));
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      for (int i = 0; i < num_kb; i++) {
-        const int s = i % R_STAGES;
-        mbar_wait(empty_bar0 + 8 * s, ((i / R_STAGES) & 1) ^ 1);
-        const uint32_t full = full_bar0 + 8 * s;
-        mbar_expect_tx(full, R_STAGE);
-        const uint32_t st = smem_base + s * R_STAGE;
-        const int k0 = i * LBK;  // k runs over the 4H gate columns
-#pragma unroll
-        for (int b = 0; b < 2; b++) {  // A = W_h viewed MN-major: boxes [64 k][64 j]
-          tma_load_2d(st + b * 8192, &tmW_hi, full, j0 + 64 * b, k0);
-          tma_load_2d(st + L_A_TILE + b * 8192, &tmW_lo, full, j0 + 64 * b, k0);
-        }
-        tma_load_2d(st + 2 * L_A_TILE, &tmG_hi, full, k0, m0);  // B = dG_{t+1} [32 m][64 k]
-        tma_load_2d(st + 2 * L_A_TILE + R_B_TILE, &tmG_lo, full, k0, m0);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0 && num_kb > 0) {
-      const uint32_t idesc = idesc_bf16(128, R_BN, true, false);
-      for (int i = 0; i < num_kb; i++) {
-        const int s = i % R_STAGES;
-        mbar_wait(full_bar0 + 8 * s, (i / R_STAGES) & 1);
-        tc_fence_after();
-        const uint32_t st = smem_base + s * R_STAGE;
-#pragma unroll
-        for (int k = 0; k < LBK / 16; k++) {
-          const uint64_t a_hi = desc_mnmajor(st, k), a_lo = desc_mnmajor(st + L_A_TILE, k);
-          const uint64_t b_hi = desc_kmajor(st + 2 * L_A_TILE, k), b_lo = desc_kmajor(st + 2 * L_A_TILE + R_B_TILE, k);
-          umma_bf16(tmem_base, a_lo, b_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
-          umma_bf16(tmem_base, a_hi, b_lo, idesc, 1u);
-          umma_bf16(tmem_base, a_hi, b_hi, idesc, 1u);
-        }
-        umma_commit(empty_bar0 + 8 * s);
-      }
-      umma_commit(tfull_bar);
-    }
-  } else {
-    const int quad = warp & 3;
-    const int j = j0 + quad * 32 + lane;  // this thread's hidden unit (TMEM lane)
-    uint32_t v[32];
-    if (num_kb > 0) {
-      mbar_wait(tfull_bar, 0);
-      tc_fence_after();
-      LRCN_TMEM_LD_32(tmem_base + ((uint32_t)(quad * 32) << 16), v);
-      tmem_ld_wait();
-    } else {
-#pragma unroll
-      for (int c = 0; c < 32; c++) v[c] = 0u;
-    }
-    const int H = p.H;
-    if (j < H) {
-#pragma unroll
-      for (int c = 0; c < R_BN; c++) {
-        const int m = m0 + c;
-        if (m < p.B) {
-          const size_t idx = (size_t)m * H + j;
-          float* g = p.gates + (size_t)m * 4 * H + j;
-          const float f = g[0], in = g[H], o = g[2 * H], ch = g[3 * H];
-          const float dh = p.dh_in[idx] + __uint_as_float(v[c]);
-          const float tc = tanhf(p.c_cur[idx]);
-          const float dcv = (p.has_rec ? p.dc[idx] : 0.f) + dh * o * (1.f - tc * tc);
-          const float dO = dh * tc, dF = dcv * p.c_prev[idx], dI = dcv * ch, dG = dcv * in;
-          p.dc[idx] = dcv * f;
-          const float r0 = dF * f * (1.f - f), r1 = dI * in * (1.f - in), r2 = dO * o * (1.f - o), r3 = dG * (1.f - ch * ch);
-          g[0] = r0; g[H] = r1; g[2 * H] = r2; g[3 * H] = r3;
-          if (p.g_hi) {
-            __nv_bfloat16* gh = p.g_hi + (size_t)m * 4 * H + j;
-            __nv_bfloat16* gl = p.g_lo + (size_t)m * 4 * H + j;
-            __nv_bfloat16 hh, ll;
-            split_bf16(r0, hh, ll); gh[0] = hh; gl[0] = ll;
-            split_bf16(r1, hh, ll); gh[H] = hh; gl[H] = ll;
-            split_bf16(r2, hh, ll); gh[2 * H] = hh; gl[2 * H] = ll;
-            split_bf16(r3, hh, ll); gh[3 * H] = hh; gl[3 * H] = ll;
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc<R_BN>(tmem_base);
-  }
-}
-
-// w_hi/w_lo: bf16 shadows of the layer's full weight [4H][ldw]; the recurrent block is columns [x_off, x_off+H)
-bool lstm_bwd_step(cudaStream_t s, int B, int H, bool has_rec, const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int ldw, int x_off,
+// wt_hi/wt_lo: transposed recurrent weights from lstm_prepare_weights; gnext: bf16 split of dG_{t+1} [B][4H]
+bool lstm_bwd_step(cudaStream_t s, int B, int H, bool has_rec, const __nv_bfloat16* wt_hi, const __nv_bfloat16* wt_lo,
                    const __nv_bfloat16* gnext_hi, const __nv_bfloat16* gnext_lo, float* gates, __nv_bfloat16* g_hi, __nv_bfloat16* g_lo,
                    const float* c_prev, const float* c_cur, const float* dh_in, float* dc) {
-  CUtensorMap tw_hi, tw_lo, tg_hi, tg_lo;
-  if (!get_tensor_map_bf16(&tw_hi, w_hi + x_off, H, 4 * (uint64_t)H, ldw, 64) || !get_tensor_map_bf16(&tw_lo, w_lo + x_off, H, 4 * (uint64_t)H, ldw, 64))
-    return false;
-  const __nv_bfloat16* gh = has_rec ? gnext_hi : g_hi;  // a valid map is needed even when unused
-  const __nv_bfloat16* gl = has_rec ? gnext_lo : g_lo;
-  if (!get_tensor_map_bf16(&tg_hi, gh, 4 * (uint64_t)H, B, 4 * (uint64_t)H, R_BN) || !get_tensor_map_bf16(&tg_lo, gl, 4 * (uint64_t)H, B, 4 * (uint64_t)H, R_BN))
-    return false;
-  LstmBwdParams p;
-  p.B = B; p.H = H; p.num_kb = (4 * H + LBK - 1) / LBK; p.has_rec = has_rec ? 1 : 0;
-  p.gates = gates; p.g_hi = g_hi; p.g_lo = g_lo; p.c_prev = c_prev; p.c_cur = c_cur; p.dh_in = dh_in; p.dc = dc;
-  dim3 grid((H + 127) / 128, (B + R_BN - 1) / R_BN);
-  lstm_bwd_step_kernel<<<grid, L_THREADS, R_SMEM, s>>>(tw_hi, tw_lo, tg_hi, tg_lo, p);
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  const uint64_t K = 4 * (uint64_t)H;
+  if (!get_tensor_map_bf16(&tb_hi, wt_hi, K, bwd_rows(H), K, R_NT) || !get_tensor_map_bf16(&tb_lo, wt_lo, K, bwd_rows(H), K, R_NT)) return false;
+  if (has_rec) {
+    if (!get_tensor_map_bf16(&ta_hi, gnext_hi, K, B, K, LM / CL) || !get_tensor_map_bf16(&ta_lo, gnext_lo, K, B, K, LM / CL)) return false;
+  } else {
+    ta_hi = tb_hi; ta_lo = tb_lo;
+  }
+  StepParams p{};
+  p.B = B; p.H = H; p.num_kb = (int)((K + LBK - 1) / LBK); p.has_rec = has_rec ? 1 : 0;
+  p.gates = gates; p.o_hi = g_hi; p.o_lo = g_lo; p.c_prev = c_prev; p.c_cur = c_cur; p.dh_in = dh_in; p.dc = dc;
+  const int nt = (H + R_NT - 1) / R_NT;
+  dim3 grid((nt + CL - 1) / CL * CL, (B + LM - 1) / LM);
+  lstm_step_kernel<R_NT, false><<<grid, L_THREADS, StepCfg<R_NT>::SMEM, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
   if (g_counter) g_counter->n++;
-  cudaError_t e = cudaPeekAtLastError();
-  if (e != cudaSuccess) { set_sm100_error((std::string("lstm_bwd_step launch: ") + cudaGetErrorString(e)).c_str()); return false; }
-  return true;
+  return check_launch("lstm_bwd_step launch");
 }
 
 bool init_lstm_sm100() {
-  cudaError_t e = cudaFuncSetAttribute(lstm_fwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_bwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, R_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(lstm_step_kernel<F_NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, StepCfg<F_NT>::SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_step_kernel<R_NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, StepCfg<R_NT>::SMEM);
   if (e != cudaSuccess) { set_sm100_error((std::string("cudaFuncSetAttribute(lstm): ") + cudaGetErrorString(e)).c_str()); return false; }
   return true;
 }

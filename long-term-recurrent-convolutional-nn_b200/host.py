@@ -229,3 +229,26 @@ def minibatch(caption_dict, word_to_index, batch_size):
                 sequence[index + k][j - i] = word_to_index.get(words[k], UNK)  # lrcn.jl:288
         index += l
     return sequence, input_ids, lengths
+
+
+# ---- data-parallel sharding: a global batch of equal-length captions splits by rows -------------
+def shard_batch(image_ids, tokens, rank, world):
+    """Rows [rank*b, (rank+1)*b) of a global batch (image_ids: Bg, tokens: l x Bg, time-major).
+    Every rank keeps the same caption length l, so control flow is identical across ranks; the library
+    scales each rank's gradient by 1/(world*b*(l+1)) and the allreduce(sum) yields the global-batch gradient."""
+    image_ids = np.asarray(image_ids)
+    tokens = np.asarray(tokens)
+    bg = len(image_ids)
+    if bg % world:
+        raise ValueError(f"global batch {bg} not divisible by {world} ranks")
+    b = bg // world
+    sl = slice(rank * b, (rank + 1) * b)
+    return np.ascontiguousarray(image_ids[sl]), np.ascontiguousarray(tokens[:, sl])
+
+
+def shard_images(image_ids, rank, world):
+    """Generation shards images across ranks with no collective: contiguous, near-equal slices in input order."""
+    n = len(image_ids)
+    lo = (n * rank) // world
+    hi = (n * (rank + 1)) // world
+    return image_ids[lo:hi], (lo, hi)
