@@ -155,6 +155,48 @@ def cpu_baseline_leg(w):
             "sample": f"{n} oracle train steps (numpy/OpenBLAS fp32) on {rows}-row slices of the workload's batches"}
 
 
+def beam_leg(local_rank, rank, world, prec, max_over_ranks, barrier, n_img=1024, K=3, nword=30):
+    """BASELINE.json configs[2]: COCO-shaped beam-search generation (E=H=512, V=10000, beam 3, nword 30), images sharded
+    across ranks with no collective.  eos is biased so decode lengths are COCO-like (~10 steps) instead of the 31 steps an
+    untrained model takes; reported as captions/s over fully decoded images, host buffers in and out (e2e by construction)."""
+    from lrcn_b200 import abi, synth
+    E = H = 512
+    V = 10000
+    cfg = abi.default_config(embed=E, hidden1=H, hidden2=H, vocab=V, max_batch=8, max_len=2, max_gen_rows=n_img * K, device=local_rank,
+                             precision=prec, use_graphs=0)
+    model = synth.initweights([H, H], V, E, seed=1)
+    with abi.Handle(cfg) as g:
+        g.set_model(model)
+        ids = np.arange(1, n_img + 1, dtype=np.int64) + 100000 * rank
+        g.load_features(1, ids, synth.features(n_img, seed=6 + rank))
+        # untrained weights never emit eos (31-step decodes); bisect an eos bias so that the mean decode length is COCO-like
+        # (10.4 steps, SURVEY §8d).  Deterministic: same seeds -> same bias on every rank.
+        lo_b, hi_b = 0.0, 2.0
+        for _ in range(12):
+            mid = 0.5 * (lo_b + hi_b)
+            bout = model[8].copy()
+            bout[0, 0] = mid
+            g.set_param(9, bout)
+            _, lens, _, _ = g.beam_search(1, ids[:128], K, nword, want_logps=False)
+            if lens.mean() - 1 > 10.4:
+                lo_b = mid
+            else:
+                hi_b = mid
+        g.beam_search(1, ids, K, nword, want_logps=False)  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        reps = 3
+        steps = 0
+        for _ in range(reps):
+            toks, lens, prob, _ = g.beam_search(1, ids, K, nword, want_logps=False)
+            steps += int(lens.max()) - 1
+        g.sync()
+        dt = max_over_ranks(time.perf_counter() - t0)
+    return {"metric": "beam-3 captions/s", "value": reps * n_img * world / dt, "unit": "captions/s", "images_per_gpu": n_img, "beam_width": K,
+            "nword": nword, "vocab": V, "mean_len": float(lens.mean() - 1), "max_steps": steps / reps, "ms_per_batch": 1e3 * dt / reps,
+            "timing": "wall clock around lrcn_beam_search (host ids in, host tokens out), max over ranks"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -164,6 +206,7 @@ def main():
     ap.add_argument("--workload", default="flickr30k_train_b256", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-beam", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     w = WORKLOADS[args.workload]
@@ -255,6 +298,11 @@ def main():
     barrier()
     e2e_val = ntok_e * world / (ms_e * 1e-3)
 
+    # ---- secondary metric of BASELINE.json: beam-3 captions/s (COCO-shaped generation, images sharded by rank, no collective)
+    beam = None
+    if not args.no_beam:
+        beam = beam_leg(local_rank, rank, world, prec, max_over_ranks, barrier)
+
     line = None
     if rank == 0:
         peaks = {}
@@ -288,6 +336,8 @@ def main():
                 "gpu_launches": launches, "clocks": clocks,
                 "step_tflops_algorithmic": step_flops / (ms / args.steps * 1e-3) / 1e12,
                 "roofline": roof, "roofline_adam": roof_adam}
+        if beam is not None:
+            line["beam"] = beam
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg(w)
     h.close()

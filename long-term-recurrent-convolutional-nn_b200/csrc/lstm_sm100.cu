@@ -29,19 +29,17 @@ using namespace ptx;
 
 constexpr int LBK = 64;          // k-block (bf16 elements) = one 128-byte swizzle row
 constexpr int LM = 64;           // batch rows per CTA (UMMA M)
-constexpr int CL = 8;            // cluster size: CTAs sharing one activation tile
-constexpr int L_THREADS = 192;   // warp 0 TMA, warp 1 MMA/TMEM, warps 2-5 epilogue
-constexpr int A_HALF = LM * LBK * 2;        // 8 KiB: one of {hi, lo} of the activation k-block
-constexpr int A_SLICE = (LM / CL) * LBK * 2;  // 1 KiB: the 8 rows this CTA loads and multicasts
-
-template <int NT>
-struct StepCfg {
-  static constexpr int B_HALF = NT * LBK * 2;
-  static constexpr int STAGE = 2 * A_HALF + 2 * B_HALF;
-  static constexpr int STAGES = NT >= 64 ? 6 : 8;
-  static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
-  static constexpr uint32_t TMEM_COLS = NT < 32 ? 32 : NT;
-};
+constexpr int CL = 4;            // cluster size (4 packs 32 clusters = 128 CTAs onto the 148 SMs in ONE wave; 8 does not)
+constexpr int L_THREADS = 320;   // warp 0 TMA, warp 1 MMA/TMEM, warps 2-9 epilogue (two warps per TMEM lane quadrant)
+constexpr int A_HALF = LM * LBK * 2;          // 8 KiB: one of {hi, lo} of the activation k-block
+constexpr int A_SLICE = (LM / CL) * LBK * 2;  // 2 KiB: the 16 rows this CTA loads and multicasts (forward)
+constexpr int NT = 64;                        // accumulator columns per CTA (fwd: 16 units x 4 gates; bwd: 64 units)
+constexpr int B_HALF = NT * LBK * 2;          // 8 KiB
+constexpr int STAGE = 2 * A_HALF + 2 * B_HALF;  // 32 KiB
+constexpr int STAGES = 6;
+constexpr int RED_BYTES = CL * LM * (NT / CL) * 4;  // 16 KiB: split-K partials received from the cluster (backward)
+constexpr int L_SMEM = STAGES * STAGE + RED_BYTES + 1024 + 256;
+constexpr uint32_t L_TMEM_COLS = 64;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -61,238 +59,357 @@ __device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMa
 __device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
 }
-#define LRCN_TMEM_LD_16(taddr, v)                                                                                          \
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"   \
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), \
-                 "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                    \
-               : "r"(taddr)                                                                                                \
+__device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_smem_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void dsmem_st_f4(uint32_t addr, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+#define LRCN_TMEM_LD_8(taddr, v)                                                                         \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                  \
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) \
+               : "r"(taddr)                                                                              \
                : "memory")
 
-__device__ __forceinline__ float sigm_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+// bf16x3 mode only (the fp32 mode keeps expf/tanhf in kernels_simt.cu): ~1e-7 absolute error, far inside the 1e-4 budget
+__device__ __forceinline__ float sigm_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float ax = fabsf(x);
+  const float e = __expf(-2.0f * ax);                 // in (0,1]: no overflow, no cancellation blow-up
+  const float t = __fdividef(1.0f - e, 1.0f + e);
+  return copysignf(t, x);
+}
 
 struct StepParams {
   int B, H, num_kb, has_rec;
-  // forward
   float* gates;              // [B][4H]: fwd: x-part + bias in, activations out;  bwd: activations in, dG out
   const float* c_prev;       // [B][H]  c_{t-1}
   float* c_out;              // fwd: c_t
   float* h_out;              // fwd: h_t
   __nv_bfloat16* o_hi;       // fwd: bf16 split of h_t [B][H];  bwd: bf16 split of dG_t [B][4H]   (may be null)
   __nv_bfloat16* o_lo;
-  // backward
-  const float* c_cur;        // c_t
-  const float* dh_in;        // dL/dh_t from the layer above
-  float* dc;                 // carry: in dL/dc_t, out dL/dc_{t-1}
+  const float* c_cur;        // bwd: c_t
+  const float* dh_in;        // bwd: dL/dh_t from the layer above
+  float* dc;                 // bwd carry: in dL/dc_t, out dL/dc_{t-1}
 };
 
-// mainloop shared by both directions: A = activation tile [64 rows][K] (multicast), B = weight rows [NT][K]
-template <int NT, bool FWD>
+struct StepSmem {
+  uint32_t base, full_bar0, empty_bar0, tfull_bar;
+  uint32_t* tmem_slot;
+  float* red;
+};
+__device__ __forceinline__ StepSmem step_smem(uint8_t* smem_raw) {
+  StepSmem s;
+  s.base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // same offset in every CTA of the cluster
+  uint8_t* al = smem_raw + (s.base - smem_u32(smem_raw));
+  s.red = reinterpret_cast<float*>(al + STAGES * STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(al + STAGES * STAGE + RED_BYTES);
+  s.full_bar0 = smem_u32(bars);
+  s.empty_bar0 = smem_u32(bars + STAGES);
+  s.tfull_bar = smem_u32(bars + 2 * STAGES);
+  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  return s;
+}
+// MMA issue loop shared by both directions (one elected lane)
+__device__ __forceinline__ void step_mma_loop(const StepSmem& sm, uint32_t tmem_base, int num_kb, bool mcast_release) {
+  const uint32_t idesc = idesc_bf16(LM, NT, false, false);
+  for (int i = 0; i < num_kb; i++) {
+    const int s = i % STAGES;
+    mbar_wait(sm.full_bar0 + 8 * s, (i / STAGES) & 1);
+    tc_fence_after();
+    const uint32_t st = sm.base + s * STAGE;
+#pragma unroll
+    for (int k = 0; k < LBK / 16; k++) {
+      const uint64_t a_hi = desc_kmajor(st, k), a_lo = desc_kmajor(st + A_HALF, k);
+      const uint64_t b_hi = desc_kmajor(st + 2 * A_HALF, k), b_lo = desc_kmajor(st + 2 * A_HALF + B_HALF, k);
+      umma_bf16(tmem_base, a_lo, b_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
+      umma_bf16(tmem_base, a_hi, b_lo, idesc, 1u);
+      umma_bf16(tmem_base, a_hi, b_hi, idesc, 1u);
+    }
+    if (mcast_release) umma_commit_mcast(sm.empty_bar0 + 8 * s, (uint16_t)((1u << CL) - 1));  // free in MY smem: tell all CL producers
+    else umma_commit(sm.empty_bar0 + 8 * s);
+  }
+  umma_commit(sm.tfull_bar);
+}
+
+// ---------------------------------------------------------------------------------------------- forward step
+// A = h_{t-1} tile [64 rows][K=H] (each CTA loads 16 rows and multicasts them to the 4 CTAs of its cluster),
+// B = gate-interleaved W_h rows [64][K].  UMMA M=64 accumulator: tile row r lives in TMEM lane (r%16) + 32*(r/16).
+// Epilogue: 8 warps; warp (quad, half) reads units [8*half, +8) of its 16 rows, lanes 16-31 take units 4-7 by shuffle,
+// so all 256 threads finish 4 units each.
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(L_THREADS, 1)
-lstm_step_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const StepParams p) {
-  using Cfg = StepCfg<NT>;
-  constexpr int STAGES = Cfg::STAGES;
+lstm_fwd_step_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const StepParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // same offset in every CTA of the cluster
-  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + STAGES * Cfg::STAGE);
-  const uint32_t full_bar0 = smem_u32(bars), empty_bar0 = smem_u32(bars + STAGES), tfull_bar = smem_u32(bars + 2 * STAGES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  const StepSmem sm = step_smem(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int nt = blockIdx.x, m0 = blockIdx.y * LM;
   const int num_kb = p.has_rec ? p.num_kb : 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar0 + 8 * s, 1); mbar_init(empty_bar0 + 8 * s, CL); }
-    mbar_init(tfull_bar, 1);
+    for (int s = 0; s < STAGES; s++) { mbar_init(sm.full_bar0 + 8 * s, 1); mbar_init(sm.empty_bar0 + 8 * s, CL); }
+    mbar_init(sm.tfull_bar, 1);
     mbar_init_fence();
   }
   if (warp == 0 && lane == 0 && num_kb > 0) {
     prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmA_lo); prefetch_tensormap(&tmB_hi); prefetch_tensormap(&tmB_lo);
   }
-  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(smem_u32(tmem_slot));
+  if (warp == 1) tmem_alloc<L_TMEM_COLS>(smem_u32(sm.tmem_slot));
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();  // every CTA's barriers are initialised before any peer multicasts into them
+  if (num_kb > 0) cluster_sync_all();  // every CTA's barriers are initialised before any peer multicasts into them
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = *sm.tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
       for (int i = 0; i < num_kb; i++) {
         const int s = i % STAGES;
-        mbar_wait(empty_bar0 + 8 * s, ((i / STAGES) & 1) ^ 1);  // all CL CTAs have consumed this stage
-        const uint32_t full = full_bar0 + 8 * s;
-        mbar_expect_tx(full, Cfg::STAGE);  // 8 multicast slices of A (hi, lo) + own B (hi, lo)
-        const uint32_t st = smem_base + s * Cfg::STAGE;
+        mbar_wait(sm.empty_bar0 + 8 * s, ((i / STAGES) & 1) ^ 1);  // all CL CTAs have consumed this stage
+        const uint32_t full = sm.full_bar0 + 8 * s;
+        mbar_expect_tx(full, STAGE);  // CL multicast slices of A (hi, lo) + own B (hi, lo)
+        const uint32_t st = sm.base + s * STAGE;
         const int k0 = i * LBK;
         const int arow = m0 + (int)rank * (LM / CL);
-        tma_load_2d_mcast(st + rank * A_SLICE, &tmA_hi, full, k0, arow, (uint16_t)0xFF);
-        tma_load_2d_mcast(st + A_HALF + rank * A_SLICE, &tmA_lo, full, k0, arow, (uint16_t)0xFF);
+        tma_load_2d_mcast(st + rank * A_SLICE, &tmA_hi, full, k0, arow, (uint16_t)((1u << CL) - 1));
+        tma_load_2d_mcast(st + A_HALF + rank * A_SLICE, &tmA_lo, full, k0, arow, (uint16_t)((1u << CL) - 1));
         tma_load_2d(st + 2 * A_HALF, &tmB_hi, full, k0, nt * NT);
-        tma_load_2d(st + 2 * A_HALF + Cfg::B_HALF, &tmB_lo, full, k0, nt * NT);
+        tma_load_2d(st + 2 * A_HALF + B_HALF, &tmB_lo, full, k0, nt * NT);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && num_kb > 0) {
-      const uint32_t idesc = idesc_bf16(LM, NT, false, false);
+    if (lane == 0 && num_kb > 0) step_mma_loop(sm, tmem_base, num_kb, true);
+  } else {
+    const int ew = warp - 2, quad = warp & 3, half = ew >> 2;  // warp%4 fixes the TMEM lane quadrant
+    constexpr int NH = NT / 4;                                 // 16 units per CTA; columns [f(16) i(16) o(16) g(16)]
+    uint32_t v[4][8];
+    if (num_kb > 0) {
+      mbar_wait(sm.tfull_bar, 0);
+      tc_fence_after();
+      const uint32_t tl = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(8 * half);
+      LRCN_TMEM_LD_8(tl, v[0]);
+      LRCN_TMEM_LD_8(tl + NH, v[1]);
+      LRCN_TMEM_LD_8(tl + 2 * NH, v[2]);
+      LRCN_TMEM_LD_8(tl + 3 * NH, v[3]);
+      tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int g = 0; g < 4; g++)
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[g][e] = 0u;
+    }
+    // lanes 0-15 own a row; lanes 16-31 take over units 4..7 of the row owned by lane-16
+    float acc[4][4];
+    const int upper = lane >> 4;
+#pragma unroll
+    for (int g = 0; g < 4; g++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const uint32_t hi4 = __shfl_sync(0xffffffffu, v[g][4 + e], lane & 15);
+        acc[g][e] = __uint_as_float(upper ? hi4 : v[g][e]);
+      }
+    const int H = p.H;
+    const int m = m0 + quad * 16 + (lane & 15);
+    const int j = nt * NH + 8 * half + 4 * upper;  // first of this thread's 4 units (H % 4 == 0: a float4 never straddles H)
+    if (m < p.B && j < H) {
+      float* grow = p.gates + (size_t)m * 4 * H + j;
+      const size_t hidx = (size_t)m * H + j;
+      const float4 gf = *reinterpret_cast<const float4*>(grow);
+      const float4 gi = *reinterpret_cast<const float4*>(grow + H);
+      const float4 go = *reinterpret_cast<const float4*>(grow + 2 * H);
+      const float4 gg = *reinterpret_cast<const float4*>(grow + 3 * H);
+      const float4 cp = *reinterpret_cast<const float4*>(p.c_prev + hidx);
+      float f[4] = {gf.x, gf.y, gf.z, gf.w}, in[4] = {gi.x, gi.y, gi.z, gi.w}, o[4] = {go.x, go.y, go.z, go.w}, ch[4] = {gg.x, gg.y, gg.z, gg.w};
+      const float cpv[4] = {cp.x, cp.y, cp.z, cp.w};
+      float cn[4], hn[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        f[e] = sigm_fast(f[e] + acc[0][e]);
+        in[e] = sigm_fast(in[e] + acc[1][e]);
+        o[e] = sigm_fast(o[e] + acc[2][e]);
+        ch[e] = tanh_fast(ch[e] + acc[3][e]);
+        cn[e] = cpv[e] * f[e] + in[e] * ch[e];
+        hn[e] = o[e] * tanh_fast(cn[e]);
+      }
+      *reinterpret_cast<float4*>(grow) = make_float4(f[0], f[1], f[2], f[3]);
+      *reinterpret_cast<float4*>(grow + H) = make_float4(in[0], in[1], in[2], in[3]);
+      *reinterpret_cast<float4*>(grow + 2 * H) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(grow + 3 * H) = make_float4(ch[0], ch[1], ch[2], ch[3]);
+      *reinterpret_cast<float4*>(p.c_out + hidx) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+      *reinterpret_cast<float4*>(p.h_out + hidx) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+      if (p.o_hi) {
+        __nv_bfloat16 hh[4], ll[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) split_bf16(hn[e], hh[e], ll[e]);
+        *reinterpret_cast<uint2*>(p.o_hi + hidx) = *reinterpret_cast<uint2*>(hh);
+        *reinterpret_cast<uint2*>(p.o_lo + hidx) = *reinterpret_cast<uint2*>(ll);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (num_kb > 0) cluster_sync_all();  // no CTA leaves while a peer may still multicast into its smem / arrive on its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<L_TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- backward step
+// dh_rec[m][j] = sum_n dG_{t+1}[m][n] * W_h[j][n], K = 4H.  Tile = 64 rows x 64 units; the 4 CTAs of a cluster split K
+// (each streams a quarter of dG_{t+1} and of the transposed weights: 4x fewer bytes per SM than sharing the tile), then
+// exchange their fp32 partials through distributed shared memory: CTA r receives columns [16r,16r+16) from all four,
+// sums them and runs the cell adjoint for those 16 units.
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(L_THREADS, 1)
+lstm_bwd_step_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const StepParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const StepSmem sm = step_smem(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int nt = blockIdx.x / CL, m0 = blockIdx.y * LM;
+  const int kb_per = (p.num_kb + CL - 1) / CL;
+  const int kb_begin = (int)rank * kb_per;
+  const int num_kb = p.has_rec ? max(0, min(p.num_kb, kb_begin + kb_per) - kb_begin) : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(sm.full_bar0 + 8 * s, 1); mbar_init(sm.empty_bar0 + 8 * s, 1); }
+    mbar_init(sm.tfull_bar, 1);
+    mbar_init_fence();
+  }
+  if (warp == 0 && lane == 0 && num_kb > 0) {
+    prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmA_lo); prefetch_tensormap(&tmB_hi); prefetch_tensormap(&tmB_lo);
+  }
+  if (warp == 1) tmem_alloc<L_TMEM_COLS>(smem_u32(sm.tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *sm.tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
       for (int i = 0; i < num_kb; i++) {
         const int s = i % STAGES;
-        mbar_wait(full_bar0 + 8 * s, (i / STAGES) & 1);
-        tc_fence_after();
-        const uint32_t st = smem_base + s * Cfg::STAGE;
-#pragma unroll
-        for (int k = 0; k < LBK / 16; k++) {
-          const uint64_t a_hi = desc_kmajor(st, k), a_lo = desc_kmajor(st + A_HALF, k);
-          const uint64_t b_hi = desc_kmajor(st + 2 * A_HALF, k), b_lo = desc_kmajor(st + 2 * A_HALF + Cfg::B_HALF, k);
-          umma_bf16(tmem_base, a_lo, b_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
-          umma_bf16(tmem_base, a_hi, b_lo, idesc, 1u);
-          umma_bf16(tmem_base, a_hi, b_hi, idesc, 1u);
-        }
-        umma_commit_mcast(empty_bar0 + 8 * s, (uint16_t)0xFF);  // this stage is free in MY smem: tell all CL producers
+        mbar_wait(sm.empty_bar0 + 8 * s, ((i / STAGES) & 1) ^ 1);
+        const uint32_t full = sm.full_bar0 + 8 * s;
+        mbar_expect_tx(full, STAGE);
+        const uint32_t st = sm.base + s * STAGE;
+        const int k0 = (kb_begin + i) * LBK;
+        tma_load_2d(st, &tmA_hi, full, k0, m0);
+        tma_load_2d(st + A_HALF, &tmA_lo, full, k0, m0);
+        tma_load_2d(st + 2 * A_HALF, &tmB_hi, full, k0, nt * NT);
+        tma_load_2d(st + 2 * A_HALF + B_HALF, &tmB_lo, full, k0, nt * NT);
       }
-      umma_commit(tfull_bar);
     }
-  } else {
-    // UMMA M=64 accumulator layout: row r of the tile lives in TMEM lane (r%16) + 32*(r/16)  (cute tmem_frg, M_MMA == 64)
-    const int quad = warp & 3;
-    const int m = m0 + quad * 16 + lane;
-    const bool active = lane < 16 && m < p.B;
-    const int H = p.H;
-    if (FWD) {
-      uint32_t v[64];
-      if (num_kb > 0) {
-        mbar_wait(tfull_bar, 0);
-        tc_fence_after();
-        LRCN_TMEM_LD_32(tmem_base + ((uint32_t)(quad * 32) << 16), v);
-        { uint32_t* v2 = v + 32; LRCN_TMEM_LD_32(tmem_base + ((uint32_t)(quad * 32) << 16) + 32u, v2); }
-        tmem_ld_wait();
-      } else {
+  } else if (warp == 1) {
+    if (lane == 0 && num_kb > 0) step_mma_loop(sm, tmem_base, num_kb, false);
+  } else if (p.has_rec) {
+    // phase 1: scatter this CTA's partial (64 rows x 64 units) to the four owners through DSMEM.
+    // receive buffer layout in every CTA: red[src][row][16] fp32
+    const int ew = warp - 2, quad = warp & 3, half = ew >> 2;
+    uint32_t v[32];
+    if (num_kb > 0) {
+      mbar_wait(sm.tfull_bar, 0);
+      tc_fence_after();
+      LRCN_TMEM_LD_32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(32 * half), v);
+      tmem_ld_wait();
+    } else {
 #pragma unroll
-        for (int j = 0; j < 64; j++) v[j] = 0u;
+      for (int c = 0; c < 32; c++) v[c] = 0u;
+    }
+    if (lane < 16) {
+      const int row = quad * 16 + lane;
+      const uint32_t local = smem_u32(sm.red) + (uint32_t)(((int)rank * LM + row) * (NT / CL)) * 4u;
+#pragma unroll
+      for (int d2 = 0; d2 < 2; d2++) {  // columns [32*half + 16*d2, +16) belong to CTA dst
+        const uint32_t dst = (uint32_t)(2 * half + d2);
+        const uint32_t ra = dsmem_addr(local, dst);
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          dsmem_st_f4(ra + 16u * q, make_float4(__uint_as_float(v[16 * d2 + 4 * q]), __uint_as_float(v[16 * d2 + 4 * q + 1]),
+                                                 __uint_as_float(v[16 * d2 + 4 * q + 2]), __uint_as_float(v[16 * d2 + 4 * q + 3])));
       }
-      constexpr int NH = NT / 4;  // hidden units per CTA; columns are [f(NH) i(NH) o(NH) g(NH)]
-      const int j0 = nt * NH;
-      if (active) {
-        float* grow = p.gates + (size_t)m * 4 * H;
-        const size_t hidx = (size_t)m * H + j0;
+    }
+  }
+  if (p.has_rec) cluster_sync_all();  // release/acquire: all partials have landed (also orders the DSMEM stores before exit)
+
+  if (warp >= 2) {
+    // phase 2: this CTA owns units [nt*64 + 16*rank, +16) of its 64 rows; 256 threads x 4 units
+    const int ew = warp - 2, quad = warp & 3, half = ew >> 2, upper = lane >> 4;
+    const int row = quad * 16 + (lane & 15);
+    const int ug = 2 * half + upper;  // group of 4 units within the 16
+    const int H = p.H;
+    const int m = m0 + row;
+    const int j = nt * NT + 16 * (int)rank + 4 * ug;
+    if (m < p.B && j < H) {
+      float rec[4] = {0.f, 0.f, 0.f, 0.f};
+      if (p.has_rec) {
 #pragma unroll
-        for (int q = 0; q < NH / 4; q++) {  // 4 units at a time (H % 4 == 0: a float4 never straddles H)
-          const int j = j0 + 4 * q;
-          if (j < H) {
-            const float4 gf = *reinterpret_cast<const float4*>(grow + j);
-            const float4 gi = *reinterpret_cast<const float4*>(grow + H + j);
-            const float4 go = *reinterpret_cast<const float4*>(grow + 2 * H + j);
-            const float4 gg = *reinterpret_cast<const float4*>(grow + 3 * H + j);
-            const float4 cp = *reinterpret_cast<const float4*>(p.c_prev + hidx + 4 * q);
-            float f[4] = {gf.x, gf.y, gf.z, gf.w}, in[4] = {gi.x, gi.y, gi.z, gi.w}, o[4] = {go.x, go.y, go.z, go.w}, ch[4] = {gg.x, gg.y, gg.z, gg.w};
-            const float cpv[4] = {cp.x, cp.y, cp.z, cp.w};
-            float cn[4], hn[4];
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-              const int u = 4 * q + e;
-              f[e] = sigm_f(f[e] + __uint_as_float(v[u]));
-              in[e] = sigm_f(in[e] + __uint_as_float(v[NH + u]));
-              o[e] = sigm_f(o[e] + __uint_as_float(v[2 * NH + u]));
-              ch[e] = tanhf(ch[e] + __uint_as_float(v[3 * NH + u]));
-              cn[e] = cpv[e] * f[e] + in[e] * ch[e];
-              hn[e] = o[e] * tanhf(cn[e]);
-            }
-            *reinterpret_cast<float4*>(grow + j) = make_float4(f[0], f[1], f[2], f[3]);
-            *reinterpret_cast<float4*>(grow + H + j) = make_float4(in[0], in[1], in[2], in[3]);
-            *reinterpret_cast<float4*>(grow + 2 * H + j) = make_float4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<float4*>(grow + 3 * H + j) = make_float4(ch[0], ch[1], ch[2], ch[3]);
-            *reinterpret_cast<float4*>(p.c_out + hidx + 4 * q) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-            *reinterpret_cast<float4*>(p.h_out + hidx + 4 * q) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-            if (p.o_hi) {
-              __nv_bfloat16 hh[4], ll[4];
-#pragma unroll
-              for (int e = 0; e < 4; e++) split_bf16(hn[e], hh[e], ll[e]);
-              *reinterpret_cast<uint2*>(p.o_hi + hidx + 4 * q) = *reinterpret_cast<uint2*>(hh);
-              *reinterpret_cast<uint2*>(p.o_lo + hidx + 4 * q) = *reinterpret_cast<uint2*>(ll);
-            }
-          }
+        for (int src = 0; src < CL; src++) {
+          const float4 x = *reinterpret_cast<const float4*>(sm.red + (size_t)(src * LM + row) * (NT / CL) + 4 * ug);
+          rec[0] += x.x; rec[1] += x.y; rec[2] += x.z; rec[3] += x.w;
         }
       }
-    } else {
-      uint32_t v[16];
-      if (num_kb > 0) {
-        mbar_wait(tfull_bar, 0);
-        tc_fence_after();
-        LRCN_TMEM_LD_16(tmem_base + ((uint32_t)(quad * 32) << 16), v);
-        tmem_ld_wait();
-      } else {
+      float* grow = p.gates + (size_t)m * 4 * H + j;
+      const size_t hidx = (size_t)m * H + j;
+      const float4 gf = *reinterpret_cast<const float4*>(grow);
+      const float4 gi = *reinterpret_cast<const float4*>(grow + H);
+      const float4 go = *reinterpret_cast<const float4*>(grow + 2 * H);
+      const float4 gg = *reinterpret_cast<const float4*>(grow + 3 * H);
+      const float4 cpv4 = *reinterpret_cast<const float4*>(p.c_prev + hidx);
+      const float4 ccv4 = *reinterpret_cast<const float4*>(p.c_cur + hidx);
+      const float4 dhv4 = *reinterpret_cast<const float4*>(p.dh_in + hidx);
+      float4 dcv4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.has_rec) dcv4 = *reinterpret_cast<const float4*>(p.dc + hidx);
+      const float f[4] = {gf.x, gf.y, gf.z, gf.w}, in[4] = {gi.x, gi.y, gi.z, gi.w}, o[4] = {go.x, go.y, go.z, go.w}, ch[4] = {gg.x, gg.y, gg.z, gg.w};
+      const float cpv[4] = {cpv4.x, cpv4.y, cpv4.z, cpv4.w}, ccv[4] = {ccv4.x, ccv4.y, ccv4.z, ccv4.w};
+      const float dhv[4] = {dhv4.x, dhv4.y, dhv4.z, dhv4.w}, dci[4] = {dcv4.x, dcv4.y, dcv4.z, dcv4.w};
+      float r0[4], r1[4], r2[4], r3[4], dco[4];
 #pragma unroll
-        for (int j = 0; j < 16; j++) v[j] = 0u;
+      for (int e = 0; e < 4; e++) {
+        const float dh = dhv[e] + rec[e];
+        const float tc = tanh_fast(ccv[e]);
+        const float dcv = dci[e] + dh * o[e] * (1.f - tc * tc);
+        const float dO = dh * tc, dF = dcv * cpv[e], dI = dcv * ch[e], dG = dcv * in[e];
+        dco[e] = dcv * f[e];
+        r0[e] = dF * f[e] * (1.f - f[e]);
+        r1[e] = dI * in[e] * (1.f - in[e]);
+        r2[e] = dO * o[e] * (1.f - o[e]);
+        r3[e] = dG * (1.f - ch[e] * ch[e]);
       }
-      const int j0 = nt * NT;  // NT hidden units per CTA (16)
-      if (active) {
-        float* grow = p.gates + (size_t)m * 4 * H;
-        const size_t hidx = (size_t)m * H + j0;
+      *reinterpret_cast<float4*>(p.dc + hidx) = make_float4(dco[0], dco[1], dco[2], dco[3]);
+      *reinterpret_cast<float4*>(grow) = make_float4(r0[0], r0[1], r0[2], r0[3]);
+      *reinterpret_cast<float4*>(grow + H) = make_float4(r1[0], r1[1], r1[2], r1[3]);
+      *reinterpret_cast<float4*>(grow + 2 * H) = make_float4(r2[0], r2[1], r2[2], r2[3]);
+      *reinterpret_cast<float4*>(grow + 3 * H) = make_float4(r3[0], r3[1], r3[2], r3[3]);
+      if (p.o_hi) {
+        const size_t gidx = (size_t)m * 4 * H + j;
+        const float* rr[4] = {r0, r1, r2, r3};
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int j = j0 + 4 * q;
-          if (j < H) {
-            const float4 gf = *reinterpret_cast<const float4*>(grow + j);
-            const float4 gi = *reinterpret_cast<const float4*>(grow + H + j);
-            const float4 go = *reinterpret_cast<const float4*>(grow + 2 * H + j);
-            const float4 gg = *reinterpret_cast<const float4*>(grow + 3 * H + j);
-            const float4 cpv4 = *reinterpret_cast<const float4*>(p.c_prev + hidx + 4 * q);
-            const float4 ccv4 = *reinterpret_cast<const float4*>(p.c_cur + hidx + 4 * q);
-            const float4 dhv4 = *reinterpret_cast<const float4*>(p.dh_in + hidx + 4 * q);
-            float4 dcv4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.has_rec) dcv4 = *reinterpret_cast<const float4*>(p.dc + hidx + 4 * q);
-            const float f[4] = {gf.x, gf.y, gf.z, gf.w}, in[4] = {gi.x, gi.y, gi.z, gi.w}, o[4] = {go.x, go.y, go.z, go.w}, ch[4] = {gg.x, gg.y, gg.z, gg.w};
-            const float cpv[4] = {cpv4.x, cpv4.y, cpv4.z, cpv4.w}, ccv[4] = {ccv4.x, ccv4.y, ccv4.z, ccv4.w};
-            const float dhv[4] = {dhv4.x, dhv4.y, dhv4.z, dhv4.w}, dci[4] = {dcv4.x, dcv4.y, dcv4.z, dcv4.w};
-            float r0[4], r1[4], r2[4], r3[4], dco[4];
+        for (int g = 0; g < 4; g++) {
+          __nv_bfloat16 hh[4], ll[4];
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-              const float dh = dhv[e] + __uint_as_float(v[4 * q + e]);
-              const float tc = tanhf(ccv[e]);
-              const float dcv = dci[e] + dh * o[e] * (1.f - tc * tc);
-              const float dO = dh * tc, dF = dcv * cpv[e], dI = dcv * ch[e], dG = dcv * in[e];
-              dco[e] = dcv * f[e];
-              r0[e] = dF * f[e] * (1.f - f[e]);
-              r1[e] = dI * in[e] * (1.f - in[e]);
-              r2[e] = dO * o[e] * (1.f - o[e]);
-              r3[e] = dG * (1.f - ch[e] * ch[e]);
-            }
-            *reinterpret_cast<float4*>(p.dc + hidx + 4 * q) = make_float4(dco[0], dco[1], dco[2], dco[3]);
-            *reinterpret_cast<float4*>(grow + j) = make_float4(r0[0], r0[1], r0[2], r0[3]);
-            *reinterpret_cast<float4*>(grow + H + j) = make_float4(r1[0], r1[1], r1[2], r1[3]);
-            *reinterpret_cast<float4*>(grow + 2 * H + j) = make_float4(r2[0], r2[1], r2[2], r2[3]);
-            *reinterpret_cast<float4*>(grow + 3 * H + j) = make_float4(r3[0], r3[1], r3[2], r3[3]);
-            if (p.o_hi) {
-              const size_t gidx = (size_t)m * 4 * H + j;
-              const float* rr[4] = {r0, r1, r2, r3};
-#pragma unroll
-              for (int g = 0; g < 4; g++) {
-                __nv_bfloat16 hh[4], ll[4];
-#pragma unroll
-                for (int e = 0; e < 4; e++) split_bf16(rr[g][e], hh[e], ll[e]);
-                *reinterpret_cast<uint2*>(p.o_hi + gidx + (size_t)g * H) = *reinterpret_cast<uint2*>(hh);
-                *reinterpret_cast<uint2*>(p.o_lo + gidx + (size_t)g * H) = *reinterpret_cast<uint2*>(ll);
-              }
-            }
-          }
+          for (int e = 0; e < 4; e++) split_bf16(rr[g][e], hh[e], ll[e]);
+          *reinterpret_cast<uint2*>(p.o_hi + gidx + (size_t)g * H) = *reinterpret_cast<uint2*>(hh);
+          *reinterpret_cast<uint2*>(p.o_lo + gidx + (size_t)g * H) = *reinterpret_cast<uint2*>(ll);
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();  // no CTA leaves while a peer may still multicast into its smem or arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    tmem_dealloc<L_TMEM_COLS>(tmem_base);
   }
 }
 
 // ---------------------------------------------------------------------------------------------- weight copies
-constexpr int F_NT = 64, F_NH = 16;  // forward: 16 hidden units x 4 gates per CTA
-constexpr int R_NT = 16;             // backward: 16 hidden units per CTA
+constexpr int F_NT = NT, F_NH = NT / 4;  // forward: 16 hidden units x 4 gates per CTA
+constexpr int R_NT = NT;                // backward: 64 hidden units per cluster, 16 finished by each CTA
 
 // forward operand: rows = gate columns n = g*H + j of the layer weight W [4H][ldw] (columns [x_off, x_off+H) = W_h),
 // permuted so that CTA nt's 64 rows are [f i o g] x its 16 units:  row (jt*4 + g)*16 + u  <-  n = g*H + jt*16 + u
@@ -331,7 +448,7 @@ __global__ void transpose_split_kernel(const float* __restrict__ W, int ldw, int
   }
 }
 static int fwd_rows(int H) { return (H + F_NH - 1) / F_NH * F_NT; }
-static int bwd_rows(int H) { return (H + 31) / 32 * 32; }
+static int bwd_rows(int H) { return (H + 63) / 64 * 64; }
 size_t lstm_permuted_elems(int H) { return (size_t)fwd_rows(H) * ((H + 7) / 8 * 8); }
 size_t lstm_transposed_elems(int H) { return (size_t)bwd_rows(H) * 4 * H; }
 
@@ -369,7 +486,7 @@ bool lstm_fwd_step(cudaStream_t s, int B, int H, bool has_rec, const __nv_bfloat
   p.gates = gates; p.c_prev = c_prev; p.c_out = c_out; p.h_out = h_out; p.o_hi = h_hi; p.o_lo = h_lo;
   const int nt = (H + F_NH - 1) / F_NH;
   dim3 grid((nt + CL - 1) / CL * CL, (B + LM - 1) / LM);
-  lstm_step_kernel<F_NT, true><<<grid, L_THREADS, StepCfg<F_NT>::SMEM, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  lstm_fwd_step_kernel<<<grid, L_THREADS, L_SMEM, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
   if (g_counter) g_counter->n++;
   return check_launch("lstm_fwd_step launch");
 }
@@ -382,7 +499,7 @@ bool lstm_bwd_step(cudaStream_t s, int B, int H, bool has_rec, const __nv_bfloat
   const uint64_t K = 4 * (uint64_t)H;
   if (!get_tensor_map_bf16(&tb_hi, wt_hi, K, bwd_rows(H), K, R_NT) || !get_tensor_map_bf16(&tb_lo, wt_lo, K, bwd_rows(H), K, R_NT)) return false;
   if (has_rec) {
-    if (!get_tensor_map_bf16(&ta_hi, gnext_hi, K, B, K, LM / CL) || !get_tensor_map_bf16(&ta_lo, gnext_lo, K, B, K, LM / CL)) return false;
+    if (!get_tensor_map_bf16(&ta_hi, gnext_hi, K, B, K, LM) || !get_tensor_map_bf16(&ta_lo, gnext_lo, K, B, K, LM)) return false;
   } else {
     ta_hi = tb_hi; ta_lo = tb_lo;
   }
@@ -390,15 +507,15 @@ bool lstm_bwd_step(cudaStream_t s, int B, int H, bool has_rec, const __nv_bfloat
   p.B = B; p.H = H; p.num_kb = (int)((K + LBK - 1) / LBK); p.has_rec = has_rec ? 1 : 0;
   p.gates = gates; p.o_hi = g_hi; p.o_lo = g_lo; p.c_prev = c_prev; p.c_cur = c_cur; p.dh_in = dh_in; p.dc = dc;
   const int nt = (H + R_NT - 1) / R_NT;
-  dim3 grid((nt + CL - 1) / CL * CL, (B + LM - 1) / LM);
-  lstm_step_kernel<R_NT, false><<<grid, L_THREADS, StepCfg<R_NT>::SMEM, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  dim3 grid(nt * CL, (B + LM - 1) / LM);  // CL k-slices per 64x64 output tile
+  lstm_bwd_step_kernel<<<grid, L_THREADS, L_SMEM, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
   if (g_counter) g_counter->n++;
   return check_launch("lstm_bwd_step launch");
 }
 
 bool init_lstm_sm100() {
-  cudaError_t e = cudaFuncSetAttribute(lstm_step_kernel<F_NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, StepCfg<F_NT>::SMEM);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_step_kernel<R_NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, StepCfg<R_NT>::SMEM);
+  cudaError_t e = cudaFuncSetAttribute(lstm_fwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_bwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM);
   if (e != cudaSuccess) { set_sm100_error((std::string("cudaFuncSetAttribute(lstm): ") + cudaGetErrorString(e)).c_str()); return false; }
   return true;
 }
