@@ -171,8 +171,8 @@ def beam_leg(local_rank, rank, world, prec, max_over_ranks, barrier, n_img=1024,
         g.load_features(1, ids, synth.features(n_img, seed=6 + rank))
         # untrained weights never emit eos (31-step decodes); bisect an eos bias so that the mean decode length is COCO-like
         # (10.4 steps).  Deterministic: same seeds -> same bias on every rank.
-        lo_b, hi_b = 0.0, 2.0
-        for _ in range(12):
+        lo_b, hi_b = -1.0, 1.0
+        for _ in range(14):
             mid = 0.5 * (lo_b + hi_b)
             bout = model[8].copy()
             bout[0, 0] = mid
@@ -182,6 +182,9 @@ def beam_leg(local_rank, rank, world, prec, max_over_ranks, barrier, n_img=1024,
                 lo_b = mid
             else:
                 hi_b = mid
+        bout = model[8].copy()
+        bout[0, 0] = lo_b  # the side whose mean decode length is >= 10.4 steps
+        g.set_param(9, bout)
         g.beam_search(1, ids, K, nword, want_logps=False)  # warm-up
         barrier()
         t0 = time.perf_counter()
