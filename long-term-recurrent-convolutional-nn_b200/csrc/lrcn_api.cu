@@ -121,6 +121,7 @@ struct lrcn_handle {
   int* h_stage = nullptr;  // pinned: tok_in | tok_tgt | rows
   StepScalars *d_sc = nullptr, *h_sc = nullptr;
   double *d_loss = nullptr, *h_loss = nullptr;
+  unsigned int* d_counters = nullptr;  // per-m-tile grid-barrier counters of the persistent LSTM kernels
   Slot slots[64];
   std::map<std::tuple<int, int, int, int>, cudaGraphExec_t> graphs;
   std::map<std::tuple<int, int, int, int>, long long> graph_launches;
@@ -211,7 +212,7 @@ extern "C" int lrcn_destroy(lrcn_handle* h) {
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
   if (h->comm && nccl_api()) nccl_api()->CommDestroy(h->comm);
   void* ptrs[] = {h->w, h->g, h->m, h->v, h->w_hi, h->w_lo, h->wp1_hi, h->wp1_lo, h->wp2_hi, h->wp2_lo, h->tab[0].d, h->tab[1].d, h->ws.f, h->ws.hi, h->ws.lo, h->d_tok_in,
-                  h->d_tok_tgt, h->d_rows, h->d_sc, h->d_loss, h->g_last, h->g_ctok, h->g_stok, h->g_spar, h->g_hista, h->g_histb,
+                  h->d_tok_tgt, h->d_rows, h->d_sc, h->d_loss, h->d_counters, h->g_last, h->g_ctok, h->g_stok, h->g_spar, h->g_hista, h->g_histb,
                   h->g_done, h->g_ndone, h->g_olen, h->g_rows, h->g_otok, h->l2_scratch};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& s : h->slots) { if (s.tok_in) cudaFree(s.tok_in); if (s.tok_tgt) cudaFree(s.tok_tgt); if (s.rows) cudaFree(s.rows); }
@@ -313,6 +314,7 @@ static int create_impl(const lrcn_config* cfg, lrcn_handle* h) {
   CK(cudaMalloc(&h->d_sc, sizeof(StepScalars))); CK(cudaMallocHost(&h->h_sc, sizeof(StepScalars)));
   memset(h->h_sc, 0, sizeof(StepScalars));
   CK(cudaMalloc(&h->d_loss, 8)); CK(cudaMallocHost(&h->h_loss, 8));
+  CK(cudaMalloc(&h->d_counters, 64 * sizeof(unsigned int)));
   CK(cudaMalloc(&h->g_last, G * 4)); CK(cudaMalloc(&h->g_ctok, G * 16 * 4)); CK(cudaMalloc(&h->g_stok, G * 4)); CK(cudaMalloc(&h->g_spar, G * 4));
   CK(cudaMalloc(&h->g_hista, G * ML * 4)); CK(cudaMalloc(&h->g_histb, G * ML * 4)); CK(cudaMalloc(&h->g_done, G * 4));
   CK(cudaMalloc(&h->g_ndone, 4)); CK(cudaMalloc(&h->g_olen, G * 4)); CK(cudaMalloc(&h->g_rows, G * 4)); CK(cudaMalloc(&h->g_otok, G * ML * 8));
@@ -511,6 +513,34 @@ static void lstm_step_bwd(lrcn_handle* h, int layer, int t, int T, int B, float*
   if (t > 0) sgemm(h->stream, true, false, B, H, 4 * H, g, 4 * H, W + x_off, ldw, dhrec, H, false, nullptr);
 }
 
+// all T steps of a layer: one persistent kernel when it applies (bf16x3, weights fit in smem, grid co-resident), else per step
+static void lstm_layer_fwd(lrcn_handle* h, int layer, int T, int B, float* acts, float* hs, float* cs) {
+  if (h->bf16mode && !getenv("LRCN_NO_PERSISTENT")) {
+    const int H = layer == 1 ? h->H1 : h->H2;
+    bf16 *hs_hi, *hs_lo;
+    shadow(h, hs, &hs_hi, &hs_lo);
+    bool launched = false;
+    if (!lstm_fwd_seq(h->stream, B, H, T, layer == 1 ? h->wp1_hi : h->wp2_hi, layer == 1 ? h->wp1_lo : h->wp2_lo, acts, hs, cs, hs_hi, hs_lo,
+                      h->d_counters, &launched))
+      throw GemmFail{gemm_bf16x3_last_error()};
+    if (launched) return;
+  }
+  for (int t = 0; t < T; t++) lstm_step_fwd(h, layer, t, B, acts, hs, cs);
+}
+static void lstm_layer_bwd(lrcn_handle* h, int layer, int T, int B, float* acts, float* cs, float* dh_all, float* dhrec, float* dc) {
+  if (h->bf16mode && !getenv("LRCN_NO_PERSISTENT")) {
+    const int H = layer == 1 ? h->H1 : h->H2;
+    bf16 *a_hi, *a_lo;
+    shadow(h, acts, &a_hi, &a_lo);
+    bool launched = false;
+    if (!lstm_bwd_seq(h->stream, B, H, T, layer == 1 ? h->wt1_hi : h->wt2_hi, layer == 1 ? h->wt1_lo : h->wt2_lo, acts, a_hi, a_lo, cs, dh_all, dc,
+                      h->d_counters, &launched))
+      throw GemmFail{gemm_bf16x3_last_error()};
+    if (launched) return;
+  }
+  for (int t = T - 1; t >= 0; t--) lstm_step_bwd(h, layer, t, T, B, acts, cs, dh_all, dhrec, dc);
+}
+
 static void enqueue_forward(lrcn_handle* h, int split, int B, int l, bool train) {
   const int T = l + 1, R = T * B, E = h->E, H1 = h->H1, H2 = h->H2, C = h->C, V = h->V, ldV = h->ldV, ldv = h->ldv;
   const Workspace& o = h->o;
@@ -522,12 +552,12 @@ static void enqueue_forward(lrcn_handle* h, int split, int B, int l, bool train)
   gather_embed(s, Wp(h, 7), h->d_tok_in, R, E, Eall, h->d_sc, train, SH(h, Eall).hi, SH(h, Eall).lo);
   gemm(h, true, true, R, 4 * H1, E, Eall, E, Wp(h, 1), E + H1, acts1, 4 * H1, false, Wp(h, 2));         // x-part of layer 1, all t
   if (h->bf16mode) lstm_prepare_weights(s, Wp(h, 1), E + H1, E, H1, h->wp1_hi, h->wp1_lo, train ? h->wt1_hi : nullptr, h->wt1_lo);
-  for (int t = 0; t < T; t++) lstm_step_fwd(h, 1, t, B, acts1, h1, c1);
+  lstm_layer_fwd(h, 1, T, B, acts1, h1, c1);
   gemm(h, true, true, R, C, H1, h1 + (size_t)B * H1, H1, Wp(h, 5), H1, Z, 2 * C, false, nullptr);         // x*w[end-4]  lrcn.jl:545
   z_finish(s, Z, v, ldv, R, B, C, h->d_sc, train, SH(h, Z).hi, SH(h, Z).lo);  // hcat(x,x_cnn) + dropout          lrcn.jl:546-547
   gemm(h, true, true, R, 4 * H2, 2 * C, Z, 2 * C, Wp(h, 3), 2 * H2, acts2, 4 * H2, false, Wp(h, 4));
   if (h->bf16mode) lstm_prepare_weights(s, Wp(h, 3), 2 * H2, 2 * C, H2, h->wp2_hi, h->wp2_lo, train ? h->wt2_hi : nullptr, h->wt2_lo);
-  for (int t = 0; t < T; t++) lstm_step_fwd(h, 2, t, B, acts2, h2, c2);
+  lstm_layer_fwd(h, 2, T, B, acts2, h2, c2);
   gemm(h, true, true, R, V, H2, h2 + (size_t)B * H2, H2, Wp(h, 8), H2, logits, ldV, false, Wp(h, 9));      // x*w[end-1] .+ w[end]  lrcn.jl:550
   softmax_ce(s, logits, ldV, R, V, h->d_tok_tgt, WS(h, o.rowlp), h->d_sc, train, SH(h, logits).hi, SH(h, logits).lo);  // logp + gather  lrcn.jl:562-567
   reduce_sum_double(s, WS(h, o.rowlp), R, h->d_loss);
@@ -546,7 +576,7 @@ static void enqueue_backward_seg(lrcn_handle* h, int B, int l, bool train, int s
     gemm(h, true, false, R, H2, V, dA, ldV, Wp(h, 8), H2, dh2, H2, false, nullptr);                        // dh2 = dA * Wout'
   } else if (seg == 2) {
     float *dhrec = WS(h, o.dhrec2), *dc = WS(h, o.dc2);
-    for (int t = T - 1; t >= 0; t--) lstm_step_bwd(h, 2, t, T, B, acts2, c2, dh2, dhrec, dc);
+    lstm_layer_bwd(h, 2, T, B, acts2, c2, dh2, dhrec, dc);
     gemm(h, false, false, 4 * H2, 2 * C, R, acts2, 4 * H2, Z, 2 * C, Gp(h, 3), 2 * H2, false, nullptr);          // dW2[:, x-part]
     gemm(h, false, false, 4 * H2, H2, R, acts2, 4 * H2, h2, H2, Gp(h, 3) + 2 * C, 2 * H2, false, nullptr);       // dW2[:, h-part] (slot 0 = 0)
     colsum(s, acts2, 4 * H2, R, 4 * H2, Gp(h, 4), false);
@@ -557,7 +587,7 @@ static void enqueue_backward_seg(lrcn_handle* h, int B, int l, bool train, int s
     gemm(h, false, false, C, LRCN_F_CNN, B, dv, ldv, X, LRCN_F_CNN, Gp(h, 6), LRCN_F_CNN, false, nullptr);        // dWcnn = X' * dv
   } else {
     float *dhrec = WS(h, o.dhrec1), *dc = WS(h, o.dc1);
-    for (int t = T - 1; t >= 0; t--) lstm_step_bwd(h, 1, t, T, B, acts1, c1, dh1, dhrec, dc);
+    lstm_layer_bwd(h, 1, T, B, acts1, c1, dh1, dhrec, dc);
     gemm(h, false, false, 4 * H1, E, R, acts1, 4 * H1, Eall, E, Gp(h, 1), E + H1, false, nullptr);
     gemm(h, false, false, 4 * H1, H1, R, acts1, 4 * H1, h1, H1, Gp(h, 1) + E, E + H1, false, nullptr);
     colsum(s, acts1, 4 * H1, R, 4 * H1, Gp(h, 2), false);

@@ -407,6 +407,441 @@ lstm_bwd_step_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   }
 }
 
+// ============================================================================================================
+// Persistent sequence kernels: ONE launch runs all T timesteps of a layer.  The CTA's slice of the recurrent weights
+// (bf16 hi/lo) is loaded once and stays resident in shared memory; per step only the activation tile streams through a
+// small TMA ring.  Steps are separated by a per-m-tile grid barrier (release/acquire counter in global memory): the
+// h_t (or dG_t) rows a step produces are read by the TMA engines of the other CTAs in the next step, so the writers
+// fence generic->async proxy before the release and the reading producer fences after the acquire.
+// All waits are clock-bounded and trap instead of hanging.
+// ============================================================================================================
+constexpr int RSTAGES = 4;                     // activation ring stages (16 KiB each: A_hi + A_lo of one k-block)
+constexpr int RSTAGE = 2 * A_HALF;
+constexpr int MAX_RES_KB = 9;                  // resident weight k-blocks that fit beside the ring (16 KiB each)
+constexpr int SEQ_EPI_THREADS = 256;
+
+struct SeqParams {
+  int B, H, T, num_kb;          // num_kb: k-blocks of the full K (fwd: H/64, bwd: 4H/64)
+  float* acts;                  // [T*B][4H]
+  float* hs;                    // fwd: [(T+1)*B][H] h slots (slot 0 = zeros)
+  float* cs;                    // [(T+1)*B][H] c slots
+  __nv_bfloat16* o_hi;          // fwd: shadows of hs;  bwd: shadows of acts
+  __nv_bfloat16* o_lo;
+  const float* dh_all;          // bwd: [T*B][H]
+  float* dc;                    // bwd: [B][H] carry
+  unsigned int* counters;       // one per m-tile, zeroed before launch
+};
+
+__device__ __forceinline__ void grid_arrive(unsigned int* ctr) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+}
+__device__ __forceinline__ void grid_wait(const unsigned int* ctr, unsigned int target) {
+  const long long t0 = clock64();
+  while (true) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    if (v >= target) break;
+    if (clock64() - t0 > 4000000000ll) { printf("lrcn lstm_seq: grid barrier timeout (block %d,%d have %u want %u)\n", blockIdx.x, blockIdx.y, v, target); __trap(); }
+  }
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(SEQ_EPI_THREADS) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (true) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000ll) { printf("lrcn lstm_seq: cluster mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
+  }
+}
+
+struct SeqSmem {
+  uint32_t res, ring, full0, empty0, wbar, tfull, tempty, redfull, redempty;
+  uint32_t* tmem_slot;
+  float* red;
+};
+__device__ __forceinline__ SeqSmem seq_smem(uint8_t* smem_raw, int res_kb) {
+  SeqSmem s;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* al = smem_raw + (base - smem_u32(smem_raw));
+  s.res = base;                                   // res_kb x {B_hi 8 KiB, B_lo 8 KiB}
+  s.ring = base + (uint32_t)res_kb * 2 * B_HALF;  // RSTAGES x {A_hi, A_lo}
+  uint8_t* after = al + (size_t)res_kb * 2 * B_HALF + RSTAGES * RSTAGE;
+  s.red = reinterpret_cast<float*>(after);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(after + RED_BYTES);
+  s.full0 = smem_u32(bars);
+  s.empty0 = smem_u32(bars + RSTAGES);
+  s.wbar = smem_u32(bars + 2 * RSTAGES);
+  s.tfull = smem_u32(bars + 2 * RSTAGES + 1);
+  s.tempty = smem_u32(bars + 2 * RSTAGES + 2);
+  s.redfull = smem_u32(bars + 2 * RSTAGES + 3);
+  s.redempty = smem_u32(bars + 2 * RSTAGES + 4);
+  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * RSTAGES + 5);
+  return s;
+}
+static int seq_smem_bytes(int res_kb) { return res_kb * 2 * B_HALF + RSTAGES * RSTAGE + RED_BYTES + 1024 + 256; }
+
+// ---- forward: all T steps of one layer.  grid = (n-tiles padded to CL, m-tiles), cluster = CL along n (multicast of h)
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(L_THREADS, 1)
+lstm_fwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const SeqParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const SeqSmem sm = seq_smem(smem_raw, p.num_kb);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int nt = blockIdx.x, mt = blockIdx.y, m0 = mt * LM;
+  const int num_kb = p.num_kb, T = p.T, B = p.B, H = p.H;
+  const unsigned int ctas_per_mtile = gridDim.x;
+  unsigned int* ctr = p.counters + mt;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < RSTAGES; s++) { mbar_init(sm.full0 + 8 * s, 1); mbar_init(sm.empty0 + 8 * s, CL); }
+    mbar_init(sm.wbar, 1); mbar_init(sm.tfull, 1); mbar_init(sm.tempty, 8);
+    mbar_init_fence();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmA_lo); prefetch_tensormap(&tmB_hi); prefetch_tensormap(&tmB_lo);
+  }
+  if (warp == 1) tmem_alloc<L_TMEM_COLS>(smem_u32(sm.tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *sm.tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(sm.wbar, (uint32_t)num_kb * 2 * B_HALF);  // resident weights: loaded once
+      for (int kb = 0; kb < num_kb; kb++) {
+        tma_load_2d(sm.res + kb * 2 * B_HALF, &tmB_hi, sm.wbar, kb * LBK, nt * NT);
+        tma_load_2d(sm.res + kb * 2 * B_HALF + B_HALF, &tmB_lo, sm.wbar, kb * LBK, nt * NT);
+      }
+      int it = 0;
+      for (int t = 1; t < T; t++) {
+        grid_wait(ctr, (unsigned int)t * ctas_per_mtile);  // h_{t-1} rows of this m-tile are complete in global memory
+        fence_proxy_async_global();
+        const int arow = t * B + m0 + (int)rank * (LM / CL);  // slot t of hs = h_{t-1}
+        for (int kb = 0; kb < num_kb; kb++, it++) {
+          const int s = it % RSTAGES;
+          mbar_wait(sm.empty0 + 8 * s, ((it / RSTAGES) & 1) ^ 1);
+          const uint32_t full = sm.full0 + 8 * s;
+          mbar_expect_tx(full, RSTAGE);
+          const uint32_t st = sm.ring + s * RSTAGE;
+          tma_load_2d_mcast(st + rank * A_SLICE, &tmA_hi, full, kb * LBK, arow, (uint16_t)((1u << CL) - 1));
+          tma_load_2d_mcast(st + A_HALF + rank * A_SLICE, &tmA_lo, full, kb * LBK, arow, (uint16_t)((1u << CL) - 1));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(LM, NT, false, false);
+      mbar_wait(sm.wbar, 0);
+      int it = 0;
+      for (int t = 1; t < T; t++) {
+        if (t >= 2) { mbar_wait(sm.tempty, (t - 2) & 1); tc_fence_after(); }  // epilogue of step t-1 has drained the accumulator
+        for (int kb = 0; kb < num_kb; kb++, it++) {
+          const int s = it % RSTAGES;
+          mbar_wait(sm.full0 + 8 * s, (it / RSTAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = sm.ring + s * RSTAGE, sb = sm.res + kb * 2 * B_HALF;
+#pragma unroll
+          for (int k = 0; k < LBK / 16; k++) {
+            const uint64_t a_hi = desc_kmajor(sa, k), a_lo = desc_kmajor(sa + A_HALF, k);
+            const uint64_t b_hi = desc_kmajor(sb, k), b_lo = desc_kmajor(sb + B_HALF, k);
+            umma_bf16(tmem_base, a_lo, b_hi, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(tmem_base, a_hi, b_lo, idesc, 1u);
+            umma_bf16(tmem_base, a_hi, b_hi, idesc, 1u);
+          }
+          umma_commit_mcast(sm.empty0 + 8 * s, (uint16_t)((1u << CL) - 1));
+        }
+        umma_commit(sm.tfull);
+      }
+    }
+  } else {
+    const int ew = warp - 2, quad = warp & 3, half = ew >> 2, upper = lane >> 4;
+    constexpr int NH = NT / 4;
+    const int m = m0 + quad * 16 + (lane & 15);
+    const int j = nt * NH + 8 * half + 4 * upper;
+    const bool active = m < B && j < H;
+    for (int t = 0; t < T; t++) {
+      float acc[4][4];
+      if (t > 0) {
+        uint32_t v[4][8];
+        mbar_wait(sm.tfull, (t - 1) & 1);
+        tc_fence_after();
+        const uint32_t tl = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(8 * half);
+        LRCN_TMEM_LD_8(tl, v[0]);
+        LRCN_TMEM_LD_8(tl + NH, v[1]);
+        LRCN_TMEM_LD_8(tl + 2 * NH, v[2]);
+        LRCN_TMEM_LD_8(tl + 3 * NH, v[3]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sm.tempty);
+#pragma unroll
+        for (int g = 0; g < 4; g++)
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const uint32_t hi4 = __shfl_sync(0xffffffffu, v[g][4 + e], lane & 15);
+            acc[g][e] = __uint_as_float(upper ? hi4 : v[g][e]);
+          }
+      } else {
+#pragma unroll
+        for (int g = 0; g < 4; g++)
+#pragma unroll
+          for (int e = 0; e < 4; e++) acc[g][e] = 0.f;
+      }
+      if (active) {
+        float* grow = p.acts + ((size_t)t * B + m) * 4 * H + j;
+        const size_t hprev = ((size_t)t * B + m) * H + j, hnext = ((size_t)(t + 1) * B + m) * H + j;
+        const float4 gf = *reinterpret_cast<const float4*>(grow);
+        const float4 gi = *reinterpret_cast<const float4*>(grow + H);
+        const float4 go = *reinterpret_cast<const float4*>(grow + 2 * H);
+        const float4 gg = *reinterpret_cast<const float4*>(grow + 3 * H);
+        const float4 cp = *reinterpret_cast<const float4*>(p.cs + hprev);
+        float f[4] = {gf.x, gf.y, gf.z, gf.w}, in[4] = {gi.x, gi.y, gi.z, gi.w}, o[4] = {go.x, go.y, go.z, go.w}, ch[4] = {gg.x, gg.y, gg.z, gg.w};
+        const float cpv[4] = {cp.x, cp.y, cp.z, cp.w};
+        float cn[4], hn[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          f[e] = sigm_fast(f[e] + acc[0][e]);
+          in[e] = sigm_fast(in[e] + acc[1][e]);
+          o[e] = sigm_fast(o[e] + acc[2][e]);
+          ch[e] = tanh_fast(ch[e] + acc[3][e]);
+          cn[e] = cpv[e] * f[e] + in[e] * ch[e];
+          hn[e] = o[e] * tanh_fast(cn[e]);
+        }
+        *reinterpret_cast<float4*>(grow) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4*>(grow + H) = make_float4(in[0], in[1], in[2], in[3]);
+        *reinterpret_cast<float4*>(grow + 2 * H) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(grow + 3 * H) = make_float4(ch[0], ch[1], ch[2], ch[3]);
+        *reinterpret_cast<float4*>(p.cs + hnext) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+        *reinterpret_cast<float4*>(p.hs + hnext) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+        __nv_bfloat16 hh[4], ll[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) split_bf16(hn[e], hh[e], ll[e]);
+        *reinterpret_cast<uint2*>(p.o_hi + hnext) = *reinterpret_cast<uint2*>(hh);
+        *reinterpret_cast<uint2*>(p.o_lo + hnext) = *reinterpret_cast<uint2*>(ll);
+      }
+      if (t + 1 < T) {  // publish h_t: generic-proxy stores -> visible to the other CTAs' TMA (async proxy) reads
+        fence_proxy_async_global();
+        __threadfence();
+        epi_bar_sync();
+        if (threadIdx.x == 64) grid_arrive(ctr);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<L_TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---- backward: all T steps of one layer, t = T-1 .. 0.  grid = (n-tiles*CL, m-tiles); the CL CTAs of a cluster are the
+// K-slices of one 64x64 output tile; partials are exchanged through DSMEM with remote mbarrier arrives.
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(L_THREADS, 1)
+lstm_bwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const SeqParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int kb_per = (p.num_kb + CL - 1) / CL;
+  const SeqSmem sm = seq_smem(smem_raw, kb_per);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int nt = blockIdx.x / CL, mt = blockIdx.y, m0 = mt * LM;
+  const int T = p.T, B = p.B, H = p.H;
+  const int kb_begin = (int)rank * kb_per;
+  const int nkb = max(0, min(p.num_kb, kb_begin + kb_per) - kb_begin);
+  const unsigned int ctas_per_mtile = gridDim.x;
+  unsigned int* ctr = p.counters + mt;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < RSTAGES; s++) { mbar_init(sm.full0 + 8 * s, 1); mbar_init(sm.empty0 + 8 * s, 1); }
+    mbar_init(sm.wbar, 1); mbar_init(sm.tfull, 1); mbar_init(sm.tempty, 8);
+    mbar_init(sm.redfull, CL * 64); mbar_init(sm.redempty, CL);
+    mbar_init_fence();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmA_lo); prefetch_tensormap(&tmB_hi); prefetch_tensormap(&tmB_lo);
+  }
+  if (warp == 1) tmem_alloc<L_TMEM_COLS>(smem_u32(sm.tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *sm.tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && nkb > 0) {
+      mbar_expect_tx(sm.wbar, (uint32_t)nkb * 2 * B_HALF);
+      for (int i = 0; i < nkb; i++) {
+        tma_load_2d(sm.res + i * 2 * B_HALF, &tmB_hi, sm.wbar, (kb_begin + i) * LBK, nt * NT);
+        tma_load_2d(sm.res + i * 2 * B_HALF + B_HALF, &tmB_lo, sm.wbar, (kb_begin + i) * LBK, nt * NT);
+      }
+      int it = 0;
+      for (int t = T - 2; t >= 0; t--) {
+        grid_wait(ctr, (unsigned int)(T - 1 - t) * ctas_per_mtile);  // dG_{t+1} rows of this m-tile are complete
+        fence_proxy_async_global();
+        const int arow = (t + 1) * B + m0;
+        for (int i = 0; i < nkb; i++, it++) {
+          const int s = it % RSTAGES;
+          mbar_wait(sm.empty0 + 8 * s, ((it / RSTAGES) & 1) ^ 1);
+          const uint32_t full = sm.full0 + 8 * s;
+          mbar_expect_tx(full, RSTAGE);
+          const uint32_t st = sm.ring + s * RSTAGE;
+          tma_load_2d(st, &tmA_hi, full, (kb_begin + i) * LBK, arow);
+          tma_load_2d(st + A_HALF, &tmA_lo, full, (kb_begin + i) * LBK, arow);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && nkb > 0) {
+      const uint32_t idesc = idesc_bf16(LM, NT, false, false);
+      mbar_wait(sm.wbar, 0);
+      int it = 0, n = 0;
+      for (int t = T - 2; t >= 0; t--, n++) {
+        if (n >= 1) { mbar_wait(sm.tempty, (n - 1) & 1); tc_fence_after(); }
+        for (int i = 0; i < nkb; i++, it++) {
+          const int s = it % RSTAGES;
+          mbar_wait(sm.full0 + 8 * s, (it / RSTAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = sm.ring + s * RSTAGE, sb = sm.res + i * 2 * B_HALF;
+#pragma unroll
+          for (int k = 0; k < LBK / 16; k++) {
+            const uint64_t a_hi = desc_kmajor(sa, k), a_lo = desc_kmajor(sa + A_HALF, k);
+            const uint64_t b_hi = desc_kmajor(sb, k), b_lo = desc_kmajor(sb + B_HALF, k);
+            umma_bf16(tmem_base, a_lo, b_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(tmem_base, a_hi, b_lo, idesc, 1u);
+            umma_bf16(tmem_base, a_hi, b_hi, idesc, 1u);
+          }
+          umma_commit(sm.empty0 + 8 * s);
+        }
+        umma_commit(sm.tfull);
+      }
+    }
+  } else {
+    const int ew = warp - 2, quad = warp & 3, half = ew >> 2, upper = lane >> 4;
+    const int row = quad * 16 + (lane & 15);
+    const int ug = 2 * half + upper;
+    const int m = m0 + row;
+    const int j = nt * NT + 16 * (int)rank + 4 * ug;
+    const bool active = m < B && j < H;
+    int n = 0;  // index of the recurrent step (steps with a partial product)
+    for (int t = T - 1; t >= 0; t--) {
+      const bool has_rec = t < T - 1;
+      float rec[4] = {0.f, 0.f, 0.f, 0.f};
+      if (has_rec) {
+        // phase 1: scatter my partial to the owners (lanes 0-15 hold the rows of this TMEM quadrant)
+        uint32_t v[32];
+        if (nkb > 0) {
+          mbar_wait(sm.tfull, n & 1);
+          tc_fence_after();
+          LRCN_TMEM_LD_32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(32 * half), v);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sm.tempty);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; c++) v[c] = 0u;
+        }
+        if (n >= 1) mbar_wait_cluster(sm.redempty, (n - 1) & 1);  // every owner has consumed my previous partial
+        if (lane < 16) {
+          const uint32_t local = smem_u32(sm.red) + (uint32_t)(((int)rank * LM + row) * (NT / CL)) * 4u;
+#pragma unroll
+          for (int d2 = 0; d2 < 2; d2++) {
+            const uint32_t dst = (uint32_t)(2 * half + d2);
+            const uint32_t ra = dsmem_addr(local, dst);
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+              dsmem_st_f4(ra + 16u * q, make_float4(__uint_as_float(v[16 * d2 + 4 * q]), __uint_as_float(v[16 * d2 + 4 * q + 1]),
+                                                     __uint_as_float(v[16 * d2 + 4 * q + 2]), __uint_as_float(v[16 * d2 + 4 * q + 3])));
+            mbar_arrive_remote(dsmem_addr(sm.redfull, dst));  // release.cluster: orders my stores before the owner's acquire
+          }
+        }
+        // phase 2: sum the CL partials of my 16 units
+        mbar_wait_cluster(sm.redfull, n & 1);
+#pragma unroll
+        for (int src = 0; src < CL; src++) {
+          const float4 x = *reinterpret_cast<const float4*>(sm.red + (size_t)(src * LM + row) * (NT / CL) + 4 * ug);
+          rec[0] += x.x; rec[1] += x.y; rec[2] += x.z; rec[3] += x.w;
+        }
+        epi_bar_sync();  // all 256 readers are done with red
+        if (threadIdx.x == 64) {
+#pragma unroll
+          for (int d = 0; d < CL; d++) mbar_arrive_remote(dsmem_addr(sm.redempty, (uint32_t)d));
+        }
+        n++;
+      }
+      if (active) {
+        float* grow = p.acts + ((size_t)t * B + m) * 4 * H + j;
+        const size_t hidx = (size_t)m * H + j;
+        const size_t cprev = ((size_t)t * B + m) * H + j, ccur = ((size_t)(t + 1) * B + m) * H + j;
+        const float4 gf = *reinterpret_cast<const float4*>(grow);
+        const float4 gi = *reinterpret_cast<const float4*>(grow + H);
+        const float4 go = *reinterpret_cast<const float4*>(grow + 2 * H);
+        const float4 gg = *reinterpret_cast<const float4*>(grow + 3 * H);
+        const float4 cpv4 = *reinterpret_cast<const float4*>(p.cs + cprev);
+        const float4 ccv4 = *reinterpret_cast<const float4*>(p.cs + ccur);
+        const float4 dhv4 = *reinterpret_cast<const float4*>(p.dh_all + ((size_t)t * B + m) * H + j);
+        float4 dcv4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_rec) dcv4 = *reinterpret_cast<const float4*>(p.dc + hidx);
+        const float f[4] = {gf.x, gf.y, gf.z, gf.w}, in[4] = {gi.x, gi.y, gi.z, gi.w}, o[4] = {go.x, go.y, go.z, go.w}, ch[4] = {gg.x, gg.y, gg.z, gg.w};
+        const float cpv[4] = {cpv4.x, cpv4.y, cpv4.z, cpv4.w}, ccv[4] = {ccv4.x, ccv4.y, ccv4.z, ccv4.w};
+        const float dhv[4] = {dhv4.x, dhv4.y, dhv4.z, dhv4.w}, dci[4] = {dcv4.x, dcv4.y, dcv4.z, dcv4.w};
+        float r0[4], r1[4], r2[4], r3[4], dco[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const float dh = dhv[e] + rec[e];
+          const float tc = tanh_fast(ccv[e]);
+          const float dcv = dci[e] + dh * o[e] * (1.f - tc * tc);
+          const float dO = dh * tc, dF = dcv * cpv[e], dI = dcv * ch[e], dG = dcv * in[e];
+          dco[e] = dcv * f[e];
+          r0[e] = dF * f[e] * (1.f - f[e]);
+          r1[e] = dI * in[e] * (1.f - in[e]);
+          r2[e] = dO * o[e] * (1.f - o[e]);
+          r3[e] = dG * (1.f - ch[e] * ch[e]);
+        }
+        *reinterpret_cast<float4*>(p.dc + hidx) = make_float4(dco[0], dco[1], dco[2], dco[3]);
+        *reinterpret_cast<float4*>(grow) = make_float4(r0[0], r0[1], r0[2], r0[3]);
+        *reinterpret_cast<float4*>(grow + H) = make_float4(r1[0], r1[1], r1[2], r1[3]);
+        *reinterpret_cast<float4*>(grow + 2 * H) = make_float4(r2[0], r2[1], r2[2], r2[3]);
+        *reinterpret_cast<float4*>(grow + 3 * H) = make_float4(r3[0], r3[1], r3[2], r3[3]);
+        const size_t gidx = ((size_t)t * B + m) * 4 * H + j;
+        const float* rr[4] = {r0, r1, r2, r3};
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+          __nv_bfloat16 hh[4], ll[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++) split_bf16(rr[g][e], hh[e], ll[e]);
+          *reinterpret_cast<uint2*>(p.o_hi + gidx + (size_t)g * H) = *reinterpret_cast<uint2*>(hh);
+          *reinterpret_cast<uint2*>(p.o_lo + gidx + (size_t)g * H) = *reinterpret_cast<uint2*>(ll);
+        }
+      }
+      if (t > 0) {  // publish dG_t
+        fence_proxy_async_global();
+        __threadfence();
+        epi_bar_sync();
+        if (threadIdx.x == 64) grid_arrive(ctr);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<L_TMEM_COLS>(tmem_base);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- weight copies
 constexpr int F_NT = NT, F_NH = NT / 4;  // forward: 16 hidden units x 4 gates per CTA
 constexpr int R_NT = NT;                // backward: 64 hidden units per cluster, 16 finished by each CTA
@@ -513,9 +948,71 @@ bool lstm_bwd_step(cudaStream_t s, int B, int H, bool has_rec, const __nv_bfloat
   return check_launch("lstm_bwd_step launch");
 }
 
+static int g_lstm_sms = 0;
+// Can the persistent kernels be used?  (weights must fit beside the ring; the whole grid must be co-resident)
+static bool seq_fits(const void* kernel, int res_kb, dim3 grid) {
+  if (res_kb > MAX_RES_KB) return false;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = dim3(L_THREADS); cfg.dynamicSmemBytes = seq_smem_bytes(res_kb);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int nclusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&nclusters, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return false; }
+  return (long long)nclusters * CL >= (long long)grid.x * grid.y;
+}
+
+// whole-sequence forward of one layer; returns false (nothing launched) when the persistent kernel does not apply
+bool lstm_fwd_seq(cudaStream_t s, int B, int H, int T, const __nv_bfloat16* wperm_hi, const __nv_bfloat16* wperm_lo, float* acts, float* hs,
+                  float* cs, __nv_bfloat16* hs_hi, __nv_bfloat16* hs_lo, unsigned int* counters, bool* launched) {
+  *launched = false;
+  const int num_kb = (H + LBK - 1) / LBK;
+  const int nt = (H + F_NH - 1) / F_NH;
+  dim3 grid((nt + CL - 1) / CL * CL, (B + LM - 1) / LM);
+  if (T < 2 || !seq_fits((const void*)lstm_fwd_seq_kernel, num_kb, grid)) return true;
+  const int Hp = (H + 7) / 8 * 8, rows = fwd_rows(H);
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  if (!get_tensor_map_bf16(&tb_hi, wperm_hi, H, rows, Hp, F_NT) || !get_tensor_map_bf16(&tb_lo, wperm_lo, H, rows, Hp, F_NT)) return false;
+  const uint64_t R = (uint64_t)(T + 1) * B;
+  if (!get_tensor_map_bf16(&ta_hi, hs_hi, H, R, H, LM / CL) || !get_tensor_map_bf16(&ta_lo, hs_lo, H, R, H, LM / CL)) return false;
+  SeqParams p{};
+  p.B = B; p.H = H; p.T = T; p.num_kb = num_kb; p.acts = acts; p.hs = hs; p.cs = cs; p.o_hi = hs_hi; p.o_lo = hs_lo; p.counters = counters;
+  cudaMemsetAsync(counters, 0, 64 * sizeof(unsigned int), s);
+  lstm_fwd_seq_kernel<<<grid, L_THREADS, seq_smem_bytes(num_kb), s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  if (g_counter) g_counter->n++;
+  *launched = true;
+  return check_launch("lstm_fwd_seq launch");
+}
+
+bool lstm_bwd_seq(cudaStream_t s, int B, int H, int T, const __nv_bfloat16* wt_hi, const __nv_bfloat16* wt_lo, float* acts,
+                  __nv_bfloat16* acts_hi, __nv_bfloat16* acts_lo, float* cs, const float* dh_all, float* dc, unsigned int* counters,
+                  bool* launched) {
+  *launched = false;
+  const uint64_t K = 4 * (uint64_t)H;
+  const int num_kb = (int)((K + LBK - 1) / LBK);
+  const int kb_per = (num_kb + CL - 1) / CL;
+  const int nt = (H + R_NT - 1) / R_NT;
+  dim3 grid(nt * CL, (B + LM - 1) / LM);
+  if (T < 2 || !seq_fits((const void*)lstm_bwd_seq_kernel, kb_per, grid)) return true;
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  if (!get_tensor_map_bf16(&tb_hi, wt_hi, K, bwd_rows(H), K, R_NT) || !get_tensor_map_bf16(&tb_lo, wt_lo, K, bwd_rows(H), K, R_NT)) return false;
+  const uint64_t R = (uint64_t)T * B;
+  if (!get_tensor_map_bf16(&ta_hi, acts_hi, K, R, K, LM) || !get_tensor_map_bf16(&ta_lo, acts_lo, K, R, K, LM)) return false;
+  SeqParams p{};
+  p.B = B; p.H = H; p.T = T; p.num_kb = num_kb; p.acts = acts; p.cs = cs; p.o_hi = acts_hi; p.o_lo = acts_lo; p.dh_all = dh_all; p.dc = dc;
+  p.counters = counters;
+  cudaMemsetAsync(counters, 0, 64 * sizeof(unsigned int), s);
+  lstm_bwd_seq_kernel<<<grid, L_THREADS, seq_smem_bytes(kb_per), s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  if (g_counter) g_counter->n++;
+  *launched = true;
+  return check_launch("lstm_bwd_seq launch");
+}
+
 bool init_lstm_sm100() {
   cudaError_t e = cudaFuncSetAttribute(lstm_fwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_bwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_fwd_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seq_smem_bytes(MAX_RES_KB));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_bwd_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seq_smem_bytes(MAX_RES_KB));
   if (e != cudaSuccess) { set_sm100_error((std::string("cudaFuncSetAttribute(lstm): ") + cudaGetErrorString(e)).c_str()); return false; }
   return true;
 }

@@ -102,13 +102,17 @@ CASES = [
     dict(E=64, H1=64, H2=64, V=300, B=8, l=5),
     dict(E=128, H1=192, H2=128, V=1111, B=24, l=11, zipf=True),
     dict(E=40, H1=24, H2=72, V=131, B=5, l=3),      # C = 36 is not a multiple of 8 -> padded ld of v/dv (the coco_2f C=500 case)
+    dict(E=64, H1=512, H2=512, V=300, B=80, l=7, scale=1.5),   # bench-sized hidden state: 8 k-blocks, 2 m-tiles (second one ragged)
+    dict(E=64, H1=640, H2=320, V=200, B=70, l=4, scale=1.5),   # H1 too large for weight residency -> per-step kernels for layer 1
 ]
 
 
 @pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("case", CASES)
 @pytest.mark.parametrize("graphs", [0, 1])
-def test_loss_and_gradients_match_oracle(prec, case, graphs):
+def test_loss_and_gradients_match_oracle(prec, case, graphs, monkeypatch):
+    if graphs == 0 and prec == abi.PREC_BF16X3:
+        monkeypatch.setenv("LRCN_NO_PERSISTENT", "1")  # graphs=0 runs double as the per-step LSTM kernel coverage
     c = dict(case)
     zipf = c.pop("zipf", False)
     model, feats, ids, img, tok, X = make_case(**c, zipf=zipf)
