@@ -568,6 +568,17 @@ lstm_fwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     const int m = m0 + quad * 16 + (lane & 15);
     const int j = nt * NH + 8 * half + 4 * upper;
     const bool active = m < B && j < H;
+    // The step-to-step critical path is: publish h_t -> grid barrier -> TMA -> MMA -> this epilogue.  Everything that does
+    // not depend on the MMA is taken off it: the x-part of the gates is prefetched one step ahead, c stays in registers,
+    // and only the bf16 split of h_t (what the other CTAs' TMA reads) is stored before the barrier arrive.
+    float creg[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 gf, gi, go, gg;
+    gf = gi = go = gg = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) {
+      const float* g0 = p.acts + (size_t)m * 4 * H + j;
+      gf = *reinterpret_cast<const float4*>(g0); gi = *reinterpret_cast<const float4*>(g0 + H);
+      go = *reinterpret_cast<const float4*>(g0 + 2 * H); gg = *reinterpret_cast<const float4*>(g0 + 3 * H);
+    }
     for (int t = 0; t < T; t++) {
       float acc[4][4];
       if (t > 0) {
@@ -596,32 +607,19 @@ lstm_fwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 #pragma unroll
           for (int e = 0; e < 4; e++) acc[g][e] = 0.f;
       }
+      float f[4] = {gf.x, gf.y, gf.z, gf.w}, in[4] = {gi.x, gi.y, gi.z, gi.w}, o[4] = {go.x, go.y, go.z, go.w}, ch[4] = {gg.x, gg.y, gg.z, gg.w};
+      float hn[4];
+      const size_t hnext = ((size_t)(t + 1) * B + m) * H + j;
       if (active) {
-        float* grow = p.acts + ((size_t)t * B + m) * 4 * H + j;
-        const size_t hprev = ((size_t)t * B + m) * H + j, hnext = ((size_t)(t + 1) * B + m) * H + j;
-        const float4 gf = *reinterpret_cast<const float4*>(grow);
-        const float4 gi = *reinterpret_cast<const float4*>(grow + H);
-        const float4 go = *reinterpret_cast<const float4*>(grow + 2 * H);
-        const float4 gg = *reinterpret_cast<const float4*>(grow + 3 * H);
-        const float4 cp = *reinterpret_cast<const float4*>(p.cs + hprev);
-        float f[4] = {gf.x, gf.y, gf.z, gf.w}, in[4] = {gi.x, gi.y, gi.z, gi.w}, o[4] = {go.x, go.y, go.z, go.w}, ch[4] = {gg.x, gg.y, gg.z, gg.w};
-        const float cpv[4] = {cp.x, cp.y, cp.z, cp.w};
-        float cn[4], hn[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           f[e] = sigm_fast(f[e] + acc[0][e]);
           in[e] = sigm_fast(in[e] + acc[1][e]);
           o[e] = sigm_fast(o[e] + acc[2][e]);
           ch[e] = tanh_fast(ch[e] + acc[3][e]);
-          cn[e] = cpv[e] * f[e] + in[e] * ch[e];
-          hn[e] = o[e] * tanh_fast(cn[e]);
+          creg[e] = creg[e] * f[e] + in[e] * ch[e];
+          hn[e] = o[e] * tanh_fast(creg[e]);
         }
-        *reinterpret_cast<float4*>(grow) = make_float4(f[0], f[1], f[2], f[3]);
-        *reinterpret_cast<float4*>(grow + H) = make_float4(in[0], in[1], in[2], in[3]);
-        *reinterpret_cast<float4*>(grow + 2 * H) = make_float4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<float4*>(grow + 3 * H) = make_float4(ch[0], ch[1], ch[2], ch[3]);
-        *reinterpret_cast<float4*>(p.cs + hnext) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-        *reinterpret_cast<float4*>(p.hs + hnext) = make_float4(hn[0], hn[1], hn[2], hn[3]);
         __nv_bfloat16 hh[4], ll[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) split_bf16(hn[e], hh[e], ll[e]);
@@ -633,6 +631,20 @@ lstm_fwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         __threadfence();
         epi_bar_sync();
         if (threadIdx.x == 64) grid_arrive(ctr);
+      }
+      if (active) {  // off the critical path: what only later kernels read
+        float* grow = p.acts + ((size_t)t * B + m) * 4 * H + j;
+        *reinterpret_cast<float4*>(grow) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4*>(grow + H) = make_float4(in[0], in[1], in[2], in[3]);
+        *reinterpret_cast<float4*>(grow + 2 * H) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(grow + 3 * H) = make_float4(ch[0], ch[1], ch[2], ch[3]);
+        *reinterpret_cast<float4*>(p.cs + hnext) = make_float4(creg[0], creg[1], creg[2], creg[3]);
+        *reinterpret_cast<float4*>(p.hs + hnext) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+        if (t + 1 < T) {  // prefetch the next step's x-part
+          const float* gn = p.acts + ((size_t)(t + 1) * B + m) * 4 * H + j;
+          gf = *reinterpret_cast<const float4*>(gn); gi = *reinterpret_cast<const float4*>(gn + H);
+          go = *reinterpret_cast<const float4*>(gn + 2 * H); gg = *reinterpret_cast<const float4*>(gn + 3 * H);
+        }
       }
     }
   }
@@ -733,6 +745,20 @@ lstm_bwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     const int m = m0 + row;
     const int j = nt * NT + 16 * (int)rank + 4 * ug;
     const bool active = m < B && j < H;
+    // Off the step-to-step critical path: the stored activations / cell states / dh of step t are prefetched while step
+    // t+1 is still in flight, dc stays in registers, and only the bf16 split of dG_t is stored before the barrier arrive.
+    float dcreg[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 pf, pi, po, pg, pcp, pcc, pdh;
+    pf = pi = po = pg = pcp = pcc = pdh = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto prefetch = [&](int tt) {
+      const float* g0 = p.acts + ((size_t)tt * B + m) * 4 * H + j;
+      pf = *reinterpret_cast<const float4*>(g0); pi = *reinterpret_cast<const float4*>(g0 + H);
+      po = *reinterpret_cast<const float4*>(g0 + 2 * H); pg = *reinterpret_cast<const float4*>(g0 + 3 * H);
+      pcp = *reinterpret_cast<const float4*>(p.cs + ((size_t)tt * B + m) * H + j);
+      pcc = *reinterpret_cast<const float4*>(p.cs + ((size_t)(tt + 1) * B + m) * H + j);
+      pdh = *reinterpret_cast<const float4*>(p.dh_all + ((size_t)tt * B + m) * H + j);
+    };
+    if (active) prefetch(T - 1);
     int n = 0;  // index of the recurrent step (steps with a partial product)
     for (int t = T - 1; t >= 0; t--) {
       const bool has_rec = t < T - 1;
@@ -773,51 +799,28 @@ lstm_bwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           const float4 x = *reinterpret_cast<const float4*>(sm.red + (size_t)(src * LM + row) * (NT / CL) + 4 * ug);
           rec[0] += x.x; rec[1] += x.y; rec[2] += x.z; rec[3] += x.w;
         }
-        epi_bar_sync();  // all 256 readers are done with red
-        if (threadIdx.x == 64) {
-#pragma unroll
-          for (int d = 0; d < CL; d++) mbar_arrive_remote(dsmem_addr(sm.redempty, (uint32_t)d));
-        }
         n++;
       }
+      float r0[4], r1[4], r2[4], r3[4];
+      const size_t gidx = ((size_t)t * B + m) * 4 * H + j;
       if (active) {
-        float* grow = p.acts + ((size_t)t * B + m) * 4 * H + j;
-        const size_t hidx = (size_t)m * H + j;
-        const size_t cprev = ((size_t)t * B + m) * H + j, ccur = ((size_t)(t + 1) * B + m) * H + j;
-        const float4 gf = *reinterpret_cast<const float4*>(grow);
-        const float4 gi = *reinterpret_cast<const float4*>(grow + H);
-        const float4 go = *reinterpret_cast<const float4*>(grow + 2 * H);
-        const float4 gg = *reinterpret_cast<const float4*>(grow + 3 * H);
-        const float4 cpv4 = *reinterpret_cast<const float4*>(p.cs + cprev);
-        const float4 ccv4 = *reinterpret_cast<const float4*>(p.cs + ccur);
-        const float4 dhv4 = *reinterpret_cast<const float4*>(p.dh_all + ((size_t)t * B + m) * H + j);
-        float4 dcv4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has_rec) dcv4 = *reinterpret_cast<const float4*>(p.dc + hidx);
-        const float f[4] = {gf.x, gf.y, gf.z, gf.w}, in[4] = {gi.x, gi.y, gi.z, gi.w}, o[4] = {go.x, go.y, go.z, go.w}, ch[4] = {gg.x, gg.y, gg.z, gg.w};
-        const float cpv[4] = {cpv4.x, cpv4.y, cpv4.z, cpv4.w}, ccv[4] = {ccv4.x, ccv4.y, ccv4.z, ccv4.w};
-        const float dhv[4] = {dhv4.x, dhv4.y, dhv4.z, dhv4.w}, dci[4] = {dcv4.x, dcv4.y, dcv4.z, dcv4.w};
-        float r0[4], r1[4], r2[4], r3[4], dco[4];
+        const float f[4] = {pf.x, pf.y, pf.z, pf.w}, in[4] = {pi.x, pi.y, pi.z, pi.w}, o[4] = {po.x, po.y, po.z, po.w}, ch[4] = {pg.x, pg.y, pg.z, pg.w};
+        const float cpv[4] = {pcp.x, pcp.y, pcp.z, pcp.w}, ccv[4] = {pcc.x, pcc.y, pcc.z, pcc.w}, dhv[4] = {pdh.x, pdh.y, pdh.z, pdh.w};
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           const float dh = dhv[e] + rec[e];
           const float tc = tanh_fast(ccv[e]);
-          const float dcv = dci[e] + dh * o[e] * (1.f - tc * tc);
+          const float dcv = dcreg[e] + dh * o[e] * (1.f - tc * tc);
           const float dO = dh * tc, dF = dcv * cpv[e], dI = dcv * ch[e], dG = dcv * in[e];
-          dco[e] = dcv * f[e];
+          dcreg[e] = dcv * f[e];
           r0[e] = dF * f[e] * (1.f - f[e]);
           r1[e] = dI * in[e] * (1.f - in[e]);
           r2[e] = dO * o[e] * (1.f - o[e]);
           r3[e] = dG * (1.f - ch[e] * ch[e]);
         }
-        *reinterpret_cast<float4*>(p.dc + hidx) = make_float4(dco[0], dco[1], dco[2], dco[3]);
-        *reinterpret_cast<float4*>(grow) = make_float4(r0[0], r0[1], r0[2], r0[3]);
-        *reinterpret_cast<float4*>(grow + H) = make_float4(r1[0], r1[1], r1[2], r1[3]);
-        *reinterpret_cast<float4*>(grow + 2 * H) = make_float4(r2[0], r2[1], r2[2], r2[3]);
-        *reinterpret_cast<float4*>(grow + 3 * H) = make_float4(r3[0], r3[1], r3[2], r3[3]);
-        const size_t gidx = ((size_t)t * B + m) * 4 * H + j;
         const float* rr[4] = {r0, r1, r2, r3};
 #pragma unroll
-        for (int g = 0; g < 4; g++) {
+        for (int g = 0; g < 4; g++) {  // the bf16 split of dG_t is what the next step's TMA reads: store it first
           __nv_bfloat16 hh[4], ll[4];
 #pragma unroll
           for (int e = 0; e < 4; e++) split_bf16(rr[g][e], hh[e], ll[e]);
@@ -828,8 +831,22 @@ lstm_bwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       if (t > 0) {  // publish dG_t
         fence_proxy_async_global();
         __threadfence();
-        epi_bar_sync();
-        if (threadIdx.x == 64) grid_arrive(ctr);
+        epi_bar_sync();  // also: all 256 readers of this step are done with the red buffer
+        if (threadIdx.x == 64) {
+          grid_arrive(ctr);
+          if (has_rec) {
+#pragma unroll
+            for (int d = 0; d < CL; d++) mbar_arrive_remote(dsmem_addr(sm.redempty, (uint32_t)d));  // my red slots are free again
+          }
+        }
+      }
+      if (active) {  // off the critical path
+        float* grow = p.acts + gidx;
+        *reinterpret_cast<float4*>(grow) = make_float4(r0[0], r0[1], r0[2], r0[3]);
+        *reinterpret_cast<float4*>(grow + H) = make_float4(r1[0], r1[1], r1[2], r1[3]);
+        *reinterpret_cast<float4*>(grow + 2 * H) = make_float4(r2[0], r2[1], r2[2], r2[3]);
+        *reinterpret_cast<float4*>(grow + 3 * H) = make_float4(r3[0], r3[1], r3[2], r3[3]);
+        if (t > 0) prefetch(t - 1);
       }
     }
   }
