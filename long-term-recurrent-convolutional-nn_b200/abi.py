@@ -63,6 +63,7 @@ SIGNATURES = {
     "lrcn_timer_stop": (C.c_int, [_H, _f32p]),
     "lrcn_kernel_launches": (C.c_int, [_H, _i64p]),
     "lrcn_flush_l2": (C.c_int, [_H]),
+    "lrcn_get_trace": (C.c_int, [_H, _p(C.c_uint64), C.c_int64]),
     "lrcn_time_kernel": (C.c_int, [_H, C.c_char_p, C.c_int, _f32p, _f64p, _f64p]),
     "lrcn_test_gemm": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, C.c_int, _f32p]),
     "lrcn_test_beam_select": (C.c_int, [_H, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _i64p, _i32p, _f32p]),
@@ -275,6 +276,11 @@ class Handle:
         n = C.c_int64()
         check(self.lib.lrcn_kernel_launches(self._h, C.byref(n)))
         return int(n.value)
+
+    def get_trace(self, steps):
+        out = np.zeros((steps, 8), dtype=np.uint64)
+        check(self.lib.lrcn_get_trace(self._h, out.ctypes.data_as(_p(C.c_uint64)), out.size))
+        return out
 
     def flush_l2(self):
         check(self.lib.lrcn_flush_l2(self._h))

@@ -115,7 +115,8 @@ bool lstm_bwd_step(cudaStream_t s, int B, int H, bool has_rec, const __nv_bfloat
 // enqueued) when they do not apply (H too large for residency, T < 2, grid not co-resident): use the per-step kernels then.
 // counters: >= 64 zero-able uint32 in device memory.  hs/cs: [(T+1)*B][H] slot buffers; acts: [T*B][4H].
 bool lstm_fwd_seq(cudaStream_t s, int B, int H, int T, const __nv_bfloat16* wperm_hi, const __nv_bfloat16* wperm_lo, float* acts, float* hs,
-                  float* cs, __nv_bfloat16* hs_hi, __nv_bfloat16* hs_lo, unsigned int* counters, bool* launched);
+                  float* cs, __nv_bfloat16* hs_hi, __nv_bfloat16* hs_lo, unsigned int* counters, bool* launched,
+                  unsigned long long* trace = nullptr /* optional [T][8] globaltimer stamps of CTA (0,0) */);
 bool lstm_bwd_seq(cudaStream_t s, int B, int H, int T, const __nv_bfloat16* wt_hi, const __nv_bfloat16* wt_lo, float* acts,
                   __nv_bfloat16* acts_hi, __nv_bfloat16* acts_lo, float* cs, const float* dh_all, float* dc, unsigned int* counters,
                   bool* launched);

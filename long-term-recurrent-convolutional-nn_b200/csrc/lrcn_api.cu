@@ -122,6 +122,7 @@ struct lrcn_handle {
   StepScalars *d_sc = nullptr, *h_sc = nullptr;
   double *d_loss = nullptr, *h_loss = nullptr;
   unsigned int* d_counters = nullptr;  // per-m-tile grid-barrier counters of the persistent LSTM kernels
+  unsigned long long* d_trace = nullptr;  // LRCN_SEQ_TRACE=1: per-step timeline of the layer-2 forward sequence kernel
   Slot slots[64];
   std::map<std::tuple<int, int, int, int>, cudaGraphExec_t> graphs;
   std::map<std::tuple<int, int, int, int>, long long> graph_launches;
@@ -212,7 +213,7 @@ extern "C" int lrcn_destroy(lrcn_handle* h) {
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
   if (h->comm && nccl_api()) nccl_api()->CommDestroy(h->comm);
   void* ptrs[] = {h->w, h->g, h->m, h->v, h->w_hi, h->w_lo, h->wp1_hi, h->wp1_lo, h->wp2_hi, h->wp2_lo, h->tab[0].d, h->tab[1].d, h->ws.f, h->ws.hi, h->ws.lo, h->d_tok_in,
-                  h->d_tok_tgt, h->d_rows, h->d_sc, h->d_loss, h->d_counters, h->g_last, h->g_ctok, h->g_stok, h->g_spar, h->g_hista, h->g_histb,
+                  h->d_tok_tgt, h->d_rows, h->d_sc, h->d_loss, h->d_counters, h->d_trace, h->g_last, h->g_ctok, h->g_stok, h->g_spar, h->g_hista, h->g_histb,
                   h->g_done, h->g_ndone, h->g_olen, h->g_rows, h->g_otok, h->l2_scratch};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& s : h->slots) { if (s.tok_in) cudaFree(s.tok_in); if (s.tok_tgt) cudaFree(s.tok_tgt); if (s.rows) cudaFree(s.rows); }
@@ -315,6 +316,7 @@ static int create_impl(const lrcn_config* cfg, lrcn_handle* h) {
   memset(h->h_sc, 0, sizeof(StepScalars));
   CK(cudaMalloc(&h->d_loss, 8)); CK(cudaMallocHost(&h->h_loss, 8));
   CK(cudaMalloc(&h->d_counters, 64 * sizeof(unsigned int)));
+  if (getenv("LRCN_SEQ_TRACE")) { CK(cudaMalloc(&h->d_trace, 64 * 8 * 8)); CK(cudaMemset(h->d_trace, 0, 64 * 8 * 8)); }
   CK(cudaMalloc(&h->g_last, G * 4)); CK(cudaMalloc(&h->g_ctok, G * 16 * 4)); CK(cudaMalloc(&h->g_stok, G * 4)); CK(cudaMalloc(&h->g_spar, G * 4));
   CK(cudaMalloc(&h->g_hista, G * ML * 4)); CK(cudaMalloc(&h->g_histb, G * ML * 4)); CK(cudaMalloc(&h->g_done, G * 4));
   CK(cudaMalloc(&h->g_ndone, 4)); CK(cudaMalloc(&h->g_olen, G * 4)); CK(cudaMalloc(&h->g_rows, G * 4)); CK(cudaMalloc(&h->g_otok, G * ML * 8));
@@ -521,7 +523,7 @@ static void lstm_layer_fwd(lrcn_handle* h, int layer, int T, int B, float* acts,
     shadow(h, hs, &hs_hi, &hs_lo);
     bool launched = false;
     if (!lstm_fwd_seq(h->stream, B, H, T, layer == 1 ? h->wp1_hi : h->wp2_hi, layer == 1 ? h->wp1_lo : h->wp2_lo, acts, hs, cs, hs_hi, hs_lo,
-                      h->d_counters, &launched))
+                      h->d_counters, &launched, layer == 2 ? h->d_trace : nullptr))
       throw GemmFail{gemm_bf16x3_last_error()};
     if (launched) return;
   }
@@ -1001,6 +1003,14 @@ extern "C" int lrcn_timer_stop(lrcn_handle* h, float* ms) {
 extern "C" int lrcn_kernel_launches(lrcn_handle* h, int64_t* n) {
   if (!h || !n) return fail(LRCN_ERR_ARG, "null");
   *n = h->counter.n;
+  return LRCN_OK;
+}
+extern "C" int lrcn_get_trace(lrcn_handle* h, uint64_t* out, int64_t n) {
+  if (!h || !out || n <= 0 || n > 512) return fail(LRCN_ERR_ARG, "bad argument");
+  if (!h->d_trace) return fail(LRCN_ERR_STATE, "create the handle with LRCN_SEQ_TRACE=1 in the environment");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(out, h->d_trace, (size_t)n * 8, cudaMemcpyDeviceToHost));
   return LRCN_OK;
 }
 extern "C" int lrcn_flush_l2(lrcn_handle* h) {

@@ -415,9 +415,9 @@ lstm_bwd_step_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
 // fence generic->async proxy before the release and the reading producer fences after the acquire.
 // All waits are clock-bounded and trap instead of hanging.
 // ============================================================================================================
-constexpr int RSTAGES = 4;                     // activation ring stages (16 KiB each: A_hi + A_lo of one k-block)
+constexpr int RSTAGES = 6;                     // activation ring stages (16 KiB each: A_hi + A_lo of one k-block): forward 6, backward 5
 constexpr int RSTAGE = 2 * A_HALF;
-constexpr int MAX_RES_KB = 9;                  // resident weight k-blocks that fit beside the ring (16 KiB each)
+constexpr int MAX_RES_KB = 8;                  // resident weight k-blocks that fit beside the ring (16 KiB each)
 constexpr int SEQ_EPI_THREADS = 256;
 
 struct SeqParams {
@@ -430,6 +430,7 @@ struct SeqParams {
   const float* dh_all;          // bwd: [T*B][H]
   float* dc;                    // bwd: [B][H] carry
   unsigned int* counters;       // one per m-tile, zeroed before launch
+  unsigned long long* trace;    // optional [T][8] globaltimer stamps of CTA (0,0) (LRCN_SEQ_TRACE=1), else null
 };
 
 __device__ __forceinline__ void grid_arrive(unsigned int* ctr) {
@@ -444,6 +445,12 @@ __device__ __forceinline__ void grid_wait(const unsigned int* ctr, unsigned int 
     if (clock64() - t0 > 4000000000ll) { printf("lrcn lstm_seq: grid barrier timeout (block %d,%d have %u want %u)\n", blockIdx.x, blockIdx.y, v, target); __trap(); }
   }
 }
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define LRCN_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[(size_t)t * 8 + (slot)] = gtime(); } while (0)
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(SEQ_EPI_THREADS) : "memory"); }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
@@ -465,33 +472,37 @@ struct SeqSmem {
   uint32_t* tmem_slot;
   float* red;
 };
+template <int NSTAGES, bool WITH_RED>
 __device__ __forceinline__ SeqSmem seq_smem(uint8_t* smem_raw, int res_kb) {
   SeqSmem s;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* al = smem_raw + (base - smem_u32(smem_raw));
   s.res = base;                                   // res_kb x {B_hi 8 KiB, B_lo 8 KiB}
-  s.ring = base + (uint32_t)res_kb * 2 * B_HALF;  // RSTAGES x {A_hi, A_lo}
-  uint8_t* after = al + (size_t)res_kb * 2 * B_HALF + RSTAGES * RSTAGE;
+  s.ring = base + (uint32_t)res_kb * 2 * B_HALF;  // NSTAGES x {A_hi, A_lo}
+  uint8_t* after = al + (size_t)res_kb * 2 * B_HALF + NSTAGES * RSTAGE;
   s.red = reinterpret_cast<float*>(after);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(after + RED_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(after + (WITH_RED ? RED_BYTES : 0));
   s.full0 = smem_u32(bars);
-  s.empty0 = smem_u32(bars + RSTAGES);
-  s.wbar = smem_u32(bars + 2 * RSTAGES);
-  s.tfull = smem_u32(bars + 2 * RSTAGES + 1);
-  s.tempty = smem_u32(bars + 2 * RSTAGES + 2);
-  s.redfull = smem_u32(bars + 2 * RSTAGES + 3);
-  s.redempty = smem_u32(bars + 2 * RSTAGES + 4);
-  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * RSTAGES + 5);
+  s.empty0 = smem_u32(bars + NSTAGES);
+  s.wbar = smem_u32(bars + 2 * NSTAGES);
+  s.tfull = smem_u32(bars + 2 * NSTAGES + 1);
+  s.tempty = smem_u32(bars + 2 * NSTAGES + 2);
+  s.redfull = smem_u32(bars + 2 * NSTAGES + 3);
+  s.redempty = smem_u32(bars + 2 * NSTAGES + 4);
+  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGES + 5);
   return s;
 }
-static int seq_smem_bytes(int res_kb) { return res_kb * 2 * B_HALF + RSTAGES * RSTAGE + RED_BYTES + 1024 + 256; }
+constexpr int FSTAGES = 6, BSTAGES = 5;
+static int seq_smem_bytes(int res_kb, bool bwd) {
+  return res_kb * 2 * B_HALF + (bwd ? BSTAGES : FSTAGES) * RSTAGE + (bwd ? RED_BYTES : 0) + 1024 + 256;
+}
 
 // ---- forward: all T steps of one layer.  grid = (n-tiles padded to CL, m-tiles), cluster = CL along n (multicast of h)
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(L_THREADS, 1)
 lstm_fwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const SeqParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const SeqSmem sm = seq_smem(smem_raw, p.num_kb);
+  const SeqSmem sm = seq_smem<FSTAGES, false>(smem_raw, p.num_kb);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int nt = blockIdx.x, mt = blockIdx.y, m0 = mt * LM;
@@ -500,7 +511,7 @@ lstm_fwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   unsigned int* ctr = p.counters + mt;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < RSTAGES; s++) { mbar_init(sm.full0 + 8 * s, 1); mbar_init(sm.empty0 + 8 * s, CL); }
+    for (int s = 0; s < FSTAGES; s++) { mbar_init(sm.full0 + 8 * s, 1); mbar_init(sm.empty0 + 8 * s, CL); }
     mbar_init(sm.wbar, 1); mbar_init(sm.tfull, 1); mbar_init(sm.tempty, 8);
     mbar_init_fence();
   }
@@ -524,11 +535,12 @@ lstm_fwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       int it = 0;
       for (int t = 1; t < T; t++) {
         grid_wait(ctr, (unsigned int)t * ctas_per_mtile);  // h_{t-1} rows of this m-tile are complete in global memory
+        LRCN_TRACE(0);
         fence_proxy_async_global();
         const int arow = t * B + m0 + (int)rank * (LM / CL);  // slot t of hs = h_{t-1}
         for (int kb = 0; kb < num_kb; kb++, it++) {
-          const int s = it % RSTAGES;
-          mbar_wait(sm.empty0 + 8 * s, ((it / RSTAGES) & 1) ^ 1);
+          const int s = it % FSTAGES;
+          mbar_wait(sm.empty0 + 8 * s, ((it / FSTAGES) & 1) ^ 1);
           const uint32_t full = sm.full0 + 8 * s;
           mbar_expect_tx(full, RSTAGE);
           const uint32_t st = sm.ring + s * RSTAGE;
@@ -545,8 +557,9 @@ lstm_fwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       for (int t = 1; t < T; t++) {
         if (t >= 2) { mbar_wait(sm.tempty, (t - 2) & 1); tc_fence_after(); }  // epilogue of step t-1 has drained the accumulator
         for (int kb = 0; kb < num_kb; kb++, it++) {
-          const int s = it % RSTAGES;
-          mbar_wait(sm.full0 + 8 * s, (it / RSTAGES) & 1);
+          const int s = it % FSTAGES;
+          mbar_wait(sm.full0 + 8 * s, (it / FSTAGES) & 1);
+          if (kb == 0) LRCN_TRACE(1);
           tc_fence_after();
           const uint32_t sa = sm.ring + s * RSTAGE, sb = sm.res + kb * 2 * B_HALF;
 #pragma unroll
@@ -560,6 +573,7 @@ lstm_fwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           umma_commit_mcast(sm.empty0 + 8 * s, (uint16_t)((1u << CL) - 1));
         }
         umma_commit(sm.tfull);
+        LRCN_TRACE(2);
       }
     }
   } else {
@@ -584,6 +598,7 @@ lstm_fwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       if (t > 0) {
         uint32_t v[4][8];
         mbar_wait(sm.tfull, (t - 1) & 1);
+        if (threadIdx.x == 64) LRCN_TRACE(3);
         tc_fence_after();
         const uint32_t tl = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(8 * half);
         LRCN_TMEM_LD_8(tl, v[0]);
@@ -627,10 +642,11 @@ lstm_fwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         *reinterpret_cast<uint2*>(p.o_lo + hnext) = *reinterpret_cast<uint2*>(ll);
       }
       if (t + 1 < T) {  // publish h_t: generic-proxy stores -> visible to the other CTAs' TMA (async proxy) reads
-        fence_proxy_async_global();
-        __threadfence();
+        // bar.sync orders every epilogue thread's stores before thread 64's gpu-scope release (cumulativity); the reading
+        // producers fence generic->async proxy after their acquire
+        if (threadIdx.x == 64) LRCN_TRACE(4);
         epi_bar_sync();
-        if (threadIdx.x == 64) grid_arrive(ctr);
+        if (threadIdx.x == 64) { LRCN_TRACE(5); fence_proxy_async_global(); grid_arrive(ctr); LRCN_TRACE(6); }
       }
       if (active) {  // off the critical path: what only later kernels read
         float* grow = p.acts + ((size_t)t * B + m) * 4 * H + j;
@@ -664,7 +680,7 @@ lstm_bwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const SeqParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int kb_per = (p.num_kb + CL - 1) / CL;
-  const SeqSmem sm = seq_smem(smem_raw, kb_per);
+  const SeqSmem sm = seq_smem<BSTAGES, true>(smem_raw, kb_per);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int nt = blockIdx.x / CL, mt = blockIdx.y, m0 = mt * LM;
@@ -675,7 +691,7 @@ lstm_bwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   unsigned int* ctr = p.counters + mt;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < RSTAGES; s++) { mbar_init(sm.full0 + 8 * s, 1); mbar_init(sm.empty0 + 8 * s, 1); }
+    for (int s = 0; s < BSTAGES; s++) { mbar_init(sm.full0 + 8 * s, 1); mbar_init(sm.empty0 + 8 * s, 1); }
     mbar_init(sm.wbar, 1); mbar_init(sm.tfull, 1); mbar_init(sm.tempty, 8);
     mbar_init(sm.redfull, CL * 64); mbar_init(sm.redempty, CL);
     mbar_init_fence();
@@ -703,8 +719,8 @@ lstm_bwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         fence_proxy_async_global();
         const int arow = (t + 1) * B + m0;
         for (int i = 0; i < nkb; i++, it++) {
-          const int s = it % RSTAGES;
-          mbar_wait(sm.empty0 + 8 * s, ((it / RSTAGES) & 1) ^ 1);
+          const int s = it % BSTAGES;
+          mbar_wait(sm.empty0 + 8 * s, ((it / BSTAGES) & 1) ^ 1);
           const uint32_t full = sm.full0 + 8 * s;
           mbar_expect_tx(full, RSTAGE);
           const uint32_t st = sm.ring + s * RSTAGE;
@@ -721,8 +737,8 @@ lstm_bwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       for (int t = T - 2; t >= 0; t--, n++) {
         if (n >= 1) { mbar_wait(sm.tempty, (n - 1) & 1); tc_fence_after(); }
         for (int i = 0; i < nkb; i++, it++) {
-          const int s = it % RSTAGES;
-          mbar_wait(sm.full0 + 8 * s, (it / RSTAGES) & 1);
+          const int s = it % BSTAGES;
+          mbar_wait(sm.full0 + 8 * s, (it / BSTAGES) & 1);
           tc_fence_after();
           const uint32_t sa = sm.ring + s * RSTAGE, sb = sm.res + i * 2 * B_HALF;
 #pragma unroll
@@ -829,10 +845,9 @@ lstm_bwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         }
       }
       if (t > 0) {  // publish dG_t
-        fence_proxy_async_global();
-        __threadfence();
-        epi_bar_sync();  // also: all 256 readers of this step are done with the red buffer
+        epi_bar_sync();  // orders all epilogue stores before the release below; also: all 256 readers are done with red
         if (threadIdx.x == 64) {
+          fence_proxy_async_global();
           grid_arrive(ctr);
           if (has_rec) {
 #pragma unroll
@@ -967,10 +982,10 @@ bool lstm_bwd_step(cudaStream_t s, int B, int H, bool has_rec, const __nv_bfloat
 
 static int g_lstm_sms = 0;
 // Can the persistent kernels be used?  (weights must fit beside the ring; the whole grid must be co-resident)
-static bool seq_fits(const void* kernel, int res_kb, dim3 grid) {
+static bool seq_fits(const void* kernel, int res_kb, dim3 grid, bool bwd) {
   if (res_kb > MAX_RES_KB) return false;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid; cfg.blockDim = dim3(L_THREADS); cfg.dynamicSmemBytes = seq_smem_bytes(res_kb);
+  cfg.gridDim = grid; cfg.blockDim = dim3(L_THREADS); cfg.dynamicSmemBytes = seq_smem_bytes(res_kb, bwd);
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
@@ -981,21 +996,21 @@ static bool seq_fits(const void* kernel, int res_kb, dim3 grid) {
 
 // whole-sequence forward of one layer; returns false (nothing launched) when the persistent kernel does not apply
 bool lstm_fwd_seq(cudaStream_t s, int B, int H, int T, const __nv_bfloat16* wperm_hi, const __nv_bfloat16* wperm_lo, float* acts, float* hs,
-                  float* cs, __nv_bfloat16* hs_hi, __nv_bfloat16* hs_lo, unsigned int* counters, bool* launched) {
+                  float* cs, __nv_bfloat16* hs_hi, __nv_bfloat16* hs_lo, unsigned int* counters, bool* launched, unsigned long long* trace) {
   *launched = false;
   const int num_kb = (H + LBK - 1) / LBK;
   const int nt = (H + F_NH - 1) / F_NH;
   dim3 grid((nt + CL - 1) / CL * CL, (B + LM - 1) / LM);
-  if (T < 2 || !seq_fits((const void*)lstm_fwd_seq_kernel, num_kb, grid)) return true;
+  if (T < 2 || !seq_fits((const void*)lstm_fwd_seq_kernel, num_kb, grid, false)) return true;
   const int Hp = (H + 7) / 8 * 8, rows = fwd_rows(H);
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   if (!get_tensor_map_bf16(&tb_hi, wperm_hi, H, rows, Hp, F_NT) || !get_tensor_map_bf16(&tb_lo, wperm_lo, H, rows, Hp, F_NT)) return false;
   const uint64_t R = (uint64_t)(T + 1) * B;
   if (!get_tensor_map_bf16(&ta_hi, hs_hi, H, R, H, LM / CL) || !get_tensor_map_bf16(&ta_lo, hs_lo, H, R, H, LM / CL)) return false;
   SeqParams p{};
-  p.B = B; p.H = H; p.T = T; p.num_kb = num_kb; p.acts = acts; p.hs = hs; p.cs = cs; p.o_hi = hs_hi; p.o_lo = hs_lo; p.counters = counters;
+  p.B = B; p.H = H; p.T = T; p.num_kb = num_kb; p.acts = acts; p.hs = hs; p.cs = cs; p.o_hi = hs_hi; p.o_lo = hs_lo; p.counters = counters; p.trace = trace;
   cudaMemsetAsync(counters, 0, 64 * sizeof(unsigned int), s);
-  lstm_fwd_seq_kernel<<<grid, L_THREADS, seq_smem_bytes(num_kb), s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  lstm_fwd_seq_kernel<<<grid, L_THREADS, seq_smem_bytes(num_kb, false), s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
   if (g_counter) g_counter->n++;
   *launched = true;
   return check_launch("lstm_fwd_seq launch");
@@ -1010,7 +1025,7 @@ bool lstm_bwd_seq(cudaStream_t s, int B, int H, int T, const __nv_bfloat16* wt_h
   const int kb_per = (num_kb + CL - 1) / CL;
   const int nt = (H + R_NT - 1) / R_NT;
   dim3 grid(nt * CL, (B + LM - 1) / LM);
-  if (T < 2 || !seq_fits((const void*)lstm_bwd_seq_kernel, kb_per, grid)) return true;
+  if (T < 2 || !seq_fits((const void*)lstm_bwd_seq_kernel, kb_per, grid, true)) return true;
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   if (!get_tensor_map_bf16(&tb_hi, wt_hi, K, bwd_rows(H), K, R_NT) || !get_tensor_map_bf16(&tb_lo, wt_lo, K, bwd_rows(H), K, R_NT)) return false;
   const uint64_t R = (uint64_t)T * B;
@@ -1019,7 +1034,7 @@ bool lstm_bwd_seq(cudaStream_t s, int B, int H, int T, const __nv_bfloat16* wt_h
   p.B = B; p.H = H; p.T = T; p.num_kb = num_kb; p.acts = acts; p.cs = cs; p.o_hi = acts_hi; p.o_lo = acts_lo; p.dh_all = dh_all; p.dc = dc;
   p.counters = counters;
   cudaMemsetAsync(counters, 0, 64 * sizeof(unsigned int), s);
-  lstm_bwd_seq_kernel<<<grid, L_THREADS, seq_smem_bytes(kb_per), s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  lstm_bwd_seq_kernel<<<grid, L_THREADS, seq_smem_bytes(kb_per, true), s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
   if (g_counter) g_counter->n++;
   *launched = true;
   return check_launch("lstm_bwd_seq launch");
@@ -1028,8 +1043,8 @@ bool lstm_bwd_seq(cudaStream_t s, int B, int H, int T, const __nv_bfloat16* wt_h
 bool init_lstm_sm100() {
   cudaError_t e = cudaFuncSetAttribute(lstm_fwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_bwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_fwd_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seq_smem_bytes(MAX_RES_KB));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_bwd_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seq_smem_bytes(MAX_RES_KB));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_fwd_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seq_smem_bytes(MAX_RES_KB, false));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_bwd_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seq_smem_bytes(MAX_RES_KB, true));
   if (e != cudaSuccess) { set_sm100_error((std::string("cudaFuncSetAttribute(lstm): ") + cudaGetErrorString(e)).c_str()); return false; }
   return true;
 }

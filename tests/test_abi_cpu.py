@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 def test_julia_shim_binds_every_symbol():
     jl = open(os.path.join(ROOT, "julia", "lrcn_b200.jl")).read()
     for s in header_symbols():
-        if s.startswith("lrcn_test_") or s in ("lrcn_time_kernel", "lrcn_flush_l2", "lrcn_kernel_launches"):
+        if s.startswith("lrcn_test_") or s in ("lrcn_time_kernel", "lrcn_flush_l2", "lrcn_kernel_launches", "lrcn_get_trace"):
             continue  # measurement / test hooks are not part of the reference-facing surface
         assert f":{s}" in jl, f"julia/lrcn_b200.jl has no ccall for {s}"
 
