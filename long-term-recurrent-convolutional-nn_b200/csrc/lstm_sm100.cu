@@ -184,32 +184,26 @@ lstm_fwd_step_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
     if (lane == 0 && num_kb > 0) step_mma_loop(sm, tmem_base, num_kb, true);
   } else {
     const int ew = warp - 2, quad = warp & 3, half = ew >> 2;  // warp%4 fixes the TMEM lane quadrant
-    constexpr int NH = NT / 4;                                 // 16 units per CTA; columns [f(16) i(16) o(16) g(16)]
-    uint32_t v[4][8];
+    constexpr int NH = NT / 4;                                 // 16 units per CTA; columns are unit-major: col = u*4 + gate
+    uint32_t v[32];
     if (num_kb > 0) {
       mbar_wait(sm.tfull_bar, 0);
       tc_fence_after();
-      const uint32_t tl = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(8 * half);
-      LRCN_TMEM_LD_8(tl, v[0]);
-      LRCN_TMEM_LD_8(tl + NH, v[1]);
-      LRCN_TMEM_LD_8(tl + 2 * NH, v[2]);
-      LRCN_TMEM_LD_8(tl + 3 * NH, v[3]);
+      LRCN_TMEM_LD_32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(32 * half), v);  // units [8*half, +8) x 4 gates
       tmem_ld_wait();
     } else {
 #pragma unroll
-      for (int g = 0; g < 4; g++)
-#pragma unroll
-        for (int e = 0; e < 8; e++) v[g][e] = 0u;
+      for (int c = 0; c < 32; c++) v[c] = 0u;
     }
     // lanes 0-15 own a row; lanes 16-31 take over units 4..7 of the row owned by lane-16
-    float acc[4][4];
+    float acc[4][4];  // [gate][unit]
     const int upper = lane >> 4;
 #pragma unroll
-    for (int g = 0; g < 4; g++)
+    for (int e = 0; e < 4; e++)
 #pragma unroll
-      for (int e = 0; e < 4; e++) {
-        const uint32_t hi4 = __shfl_sync(0xffffffffu, v[g][4 + e], lane & 15);
-        acc[g][e] = __uint_as_float(upper ? hi4 : v[g][e]);
+      for (int g = 0; g < 4; g++) {
+        const uint32_t hi4 = __shfl_sync(0xffffffffu, v[16 + 4 * e + g], lane & 15);
+        acc[g][e] = __uint_as_float(upper ? hi4 : v[4 * e + g]);
       }
     const int H = p.H;
     const int m = m0 + quad * 16 + (lane & 15);
@@ -411,14 +405,26 @@ lstm_bwd_step_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
 // Persistent sequence kernels: ONE launch runs all T timesteps of a layer.  The CTA's slice of the recurrent weights
 // (bf16 hi/lo) is loaded once and stays resident in shared memory; per step only the activation tile streams through a
 // small TMA ring.  Steps are separated by a per-m-tile grid barrier (release/acquire counter in global memory): the
-// h_t (or dG_t) rows a step produces are read by the TMA engines of the other CTAs in the next step, so the writers
-// fence generic->async proxy before the release and the reading producer fences after the acquire.
+// h_t (or dG_t) rows a step produces are read by the TMA engines of the other CTAs in the next step, so the releasing
+// thread fences generic->async proxy before the release and the reading producer fences after the acquire.
+//
+// STACKED SPLIT MMA.  The ring stage holds {A_hi (64 rows), A_lo (64 rows)} back to back and the resident block holds
+// {B_hi (64 rows), B_lo (64 rows)} back to back; both are therefore valid 128-row K-major SWIZZLE_128B tiles, and ONE
+// full-rate 128x128x16 tcgen05.mma per k-step produces all split products at once:
+//     lanes 0-63   x cols 0-63  : A_hi*B_hi      lanes 0-63   x cols 64-127 : A_hi*B_lo
+//     lanes 64-127 x cols 0-63  : A_lo*B_hi      lanes 64-127 x cols 64-127 : A_lo*B_lo (ignored)
+// instead of three half-rate M=64 MMAs (measured: the M=64 SS-mode chain of 96 MMAs took 4.1 us of an 8 us step).
+// The epilogue adds the three pieces: the warps of TMEM lane quadrants 2,3 pass the A_lo*B_hi rows through a small
+// smem buffer to the warps of quadrants 0,1, which own the 64 batch rows.
 // All waits are clock-bounded and trap instead of hanging.
 // ============================================================================================================
-constexpr int RSTAGES = 6;                     // activation ring stages (16 KiB each: A_hi + A_lo of one k-block): forward 6, backward 5
-constexpr int RSTAGE = 2 * A_HALF;
-constexpr int MAX_RES_KB = 8;                  // resident weight k-blocks that fit beside the ring (16 KiB each)
+constexpr int RSTAGE = 2 * A_HALF;             // 16 KiB: A_hi + A_lo of one k-block = one 128-row tile
+constexpr int MAX_RES_KB = 8;                  // resident weight k-blocks (16 KiB each)
+constexpr int FSTAGES = 5, BSTAGES = 4;        // activation ring depth: forward / backward (which also needs the red buffer)
 constexpr int SEQ_EPI_THREADS = 256;
+constexpr int SLO_LD = 68;                     // padded row (floats) of the A_lo*B_hi hand-over buffer
+constexpr int SLO_BYTES = LM * SLO_LD * 4;     // 17 KiB
+constexpr uint32_t SEQ_TMEM_COLS = 128;
 
 struct SeqParams {
   int B, H, T, num_kb;          // num_kb: k-blocks of the full K (fwd: H/64, bwd: 4H/64)
@@ -428,7 +434,7 @@ struct SeqParams {
   __nv_bfloat16* o_hi;          // fwd: shadows of hs;  bwd: shadows of acts
   __nv_bfloat16* o_lo;
   const float* dh_all;          // bwd: [T*B][H]
-  float* dc;                    // bwd: [B][H] carry
+  float* dc;                    // unused by the sequence kernels (dc is carried in registers)
   unsigned int* counters;       // one per m-tile, zeroed before launch
   unsigned long long* trace;    // optional [T][8] globaltimer stamps of CTA (0,0) (LRCN_SEQ_TRACE=1), else null
 };
@@ -453,6 +459,8 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define LRCN_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[(size_t)t * 8 + (slot)] = gtime(); } while (0)
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(SEQ_EPI_THREADS) : "memory"); }
+__device__ __forceinline__ void slo_bar_sync() { asm volatile("bar.sync 2, %0;" ::"n"(SEQ_EPI_THREADS) : "memory"); }
+__device__ __forceinline__ void slo_bar_arrive() { asm volatile("bar.arrive 2, %0;" ::"n"(SEQ_EPI_THREADS) : "memory"); }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
@@ -470,6 +478,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
 struct SeqSmem {
   uint32_t res, ring, full0, empty0, wbar, tfull, tempty, redfull, redempty;
   uint32_t* tmem_slot;
+  float* slo;
   float* red;
 };
 template <int NSTAGES, bool WITH_RED>
@@ -480,8 +489,9 @@ __device__ __forceinline__ SeqSmem seq_smem(uint8_t* smem_raw, int res_kb) {
   s.res = base;                                   // res_kb x {B_hi 8 KiB, B_lo 8 KiB}
   s.ring = base + (uint32_t)res_kb * 2 * B_HALF;  // NSTAGES x {A_hi, A_lo}
   uint8_t* after = al + (size_t)res_kb * 2 * B_HALF + NSTAGES * RSTAGE;
-  s.red = reinterpret_cast<float*>(after);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(after + (WITH_RED ? RED_BYTES : 0));
+  s.slo = reinterpret_cast<float*>(after);
+  s.red = reinterpret_cast<float*>(after + SLO_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(after + SLO_BYTES + (WITH_RED ? RED_BYTES : 0));
   s.full0 = smem_u32(bars);
   s.empty0 = smem_u32(bars + NSTAGES);
   s.wbar = smem_u32(bars + 2 * NSTAGES);
@@ -492,12 +502,52 @@ __device__ __forceinline__ SeqSmem seq_smem(uint8_t* smem_raw, int res_kb) {
   s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGES + 5);
   return s;
 }
-constexpr int FSTAGES = 6, BSTAGES = 5;
 static int seq_smem_bytes(int res_kb, bool bwd) {
-  return res_kb * 2 * B_HALF + (bwd ? BSTAGES : FSTAGES) * RSTAGE + (bwd ? RED_BYTES : 0) + 1024 + 256;
+  return res_kb * 2 * B_HALF + (bwd ? BSTAGES : FSTAGES) * RSTAGE + SLO_BYTES + (bwd ? RED_BYTES : 0) + 1024 + 256;
 }
 
-// ---- forward: all T steps of one layer.  grid = (n-tiles padded to CL, m-tiles), cluster = CL along n (multicast of h)
+// one stacked MMA per 16-wide k-step: A tile = 128 rows {hi;lo} at `sa`, B tile = 128 rows {hi;lo} at `sb`
+__device__ __forceinline__ void stacked_mma_kblock(uint32_t tmem_base, uint32_t sa, uint32_t sb, uint32_t idesc, bool first_kb) {
+#pragma unroll
+  for (int k = 0; k < LBK / 16; k++)
+    umma_bf16(tmem_base, desc_kmajor(sa, k), desc_kmajor(sb, k), idesc, (!first_kb || k > 0) ? 1u : 0u);
+}
+
+// Epilogue helper: returns in out[32] the finished accumulator row r (= 32*quad + lane, quad in {0,1}) for columns
+// [32*half, +32) as hi*hi + hi*lo + lo*hi.  Warps of quadrants 2,3 only feed the hand-over buffer and get nothing back.
+__device__ __forceinline__ void stacked_collect(const SeqSmem& sm, uint32_t tmem_base, int quad, int half, int lane, float (&out)[32]) {
+  const uint32_t tl = tmem_base + ((uint32_t)(quad * 32) << 16);
+  if (quad >= 2) {
+    uint32_t v[32];
+    LRCN_TMEM_LD_32(tl + (uint32_t)(32 * half), v);  // A_lo*B_hi, rows r = 32*(quad-2)+lane
+    tmem_ld_wait();
+    float* dst = sm.slo + (size_t)(32 * (quad - 2) + lane) * SLO_LD + 32 * half;
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+      *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                                             __uint_as_float(v[4 * q + 3]));
+    slo_bar_arrive();
+  } else {
+    uint32_t v[32], w[32];
+    LRCN_TMEM_LD_32(tl + (uint32_t)(32 * half), v);        // A_hi*B_hi
+    LRCN_TMEM_LD_32(tl + (uint32_t)(64 + 32 * half), w);   // A_hi*B_lo
+    tmem_ld_wait();
+    slo_bar_sync();
+    const float* src = sm.slo + (size_t)(32 * quad + lane) * SLO_LD + 32 * half;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const float4 x = *reinterpret_cast<const float4*>(src + 4 * q);
+      out[4 * q] = __uint_as_float(v[4 * q]) + __uint_as_float(w[4 * q]) + x.x;
+      out[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + __uint_as_float(w[4 * q + 1]) + x.y;
+      out[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + __uint_as_float(w[4 * q + 2]) + x.z;
+      out[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + __uint_as_float(w[4 * q + 3]) + x.w;
+    }
+  }
+}
+
+// ---- forward: all T steps of one layer.  grid = (n-tiles padded to CL, m-tiles), cluster = CL along n (multicast of h).
+// Weight rows are UNIT-major: row u*4+g of the CTA's block = gate g of its unit u, so the 32 columns a thread finishes are
+// the f,i,o,g of 8 consecutive hidden units.
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(L_THREADS, 1)
 lstm_fwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const SeqParams p) {
@@ -518,7 +568,7 @@ lstm_fwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmA_lo); prefetch_tensormap(&tmB_hi); prefetch_tensormap(&tmB_lo);
   }
-  if (warp == 1) tmem_alloc<L_TMEM_COLS>(smem_u32(sm.tmem_slot));
+  if (warp == 1) tmem_alloc<SEQ_TMEM_COLS>(smem_u32(sm.tmem_slot));
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -551,7 +601,7 @@ lstm_fwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = idesc_bf16(LM, NT, false, false);
+      const uint32_t idesc = idesc_bf16(128, 128, false, false);
       mbar_wait(sm.wbar, 0);
       int it = 0;
       for (int t = 1; t < T; t++) {
@@ -561,15 +611,7 @@ lstm_fwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           mbar_wait(sm.full0 + 8 * s, (it / FSTAGES) & 1);
           if (kb == 0) LRCN_TRACE(1);
           tc_fence_after();
-          const uint32_t sa = sm.ring + s * RSTAGE, sb = sm.res + kb * 2 * B_HALF;
-#pragma unroll
-          for (int k = 0; k < LBK / 16; k++) {
-            const uint64_t a_hi = desc_kmajor(sa, k), a_lo = desc_kmajor(sa + A_HALF, k);
-            const uint64_t b_hi = desc_kmajor(sb, k), b_lo = desc_kmajor(sb + B_HALF, k);
-            umma_bf16(tmem_base, a_lo, b_hi, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            umma_bf16(tmem_base, a_hi, b_lo, idesc, 1u);
-            umma_bf16(tmem_base, a_hi, b_hi, idesc, 1u);
-          }
+          stacked_mma_kblock(tmem_base, sm.ring + s * RSTAGE, sm.res + kb * 2 * B_HALF, idesc, kb == 0);
           umma_commit_mcast(sm.empty0 + 8 * s, (uint16_t)((1u << CL) - 1));
         }
         umma_commit(sm.tfull);
@@ -577,73 +619,63 @@ lstm_fwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       }
     }
   } else {
-    const int ew = warp - 2, quad = warp & 3, half = ew >> 2, upper = lane >> 4;
-    constexpr int NH = NT / 4;
-    const int m = m0 + quad * 16 + (lane & 15);
-    const int j = nt * NH + 8 * half + 4 * upper;
-    const bool active = m < B && j < H;
-    // The step-to-step critical path is: publish h_t -> grid barrier -> TMA -> MMA -> this epilogue.  Everything that does
-    // not depend on the MMA is taken off it: the x-part of the gates is prefetched one step ahead, c stays in registers,
-    // and only the bf16 split of h_t (what the other CTAs' TMA reads) is stored before the barrier arrive.
-    float creg[4] = {0.f, 0.f, 0.f, 0.f};
-    float4 gf, gi, go, gg;
-    gf = gi = go = gg = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int ew = warp - 2, quad = warp & 3, half = ew >> 2;
+    constexpr int NH = NT / 4;                       // 16 units per CTA
+    const bool owner = quad < 2;                     // warps of lane quadrants 0,1 own the 64 batch rows
+    const int m = m0 + 32 * quad + lane;             // (owner only)
+    const int j = nt * NH + 8 * half;                // first of this thread's 8 units (H % 8 == 0)
+    const bool active = owner && m < B && j < H;
+    // Off the step-to-step critical path: the x-part of the gates is prefetched one step ahead, c stays in registers, and
+    // only the bf16 split of h_t (what the other CTAs' TMA reads) is stored before the barrier arrive.
+    float creg[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) creg[e] = 0.f;
+    float4 xg[4][2];
+#pragma unroll
+    for (int g = 0; g < 4; g++) xg[g][0] = xg[g][1] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (active) {
       const float* g0 = p.acts + (size_t)m * 4 * H + j;
-      gf = *reinterpret_cast<const float4*>(g0); gi = *reinterpret_cast<const float4*>(g0 + H);
-      go = *reinterpret_cast<const float4*>(g0 + 2 * H); gg = *reinterpret_cast<const float4*>(g0 + 3 * H);
+#pragma unroll
+      for (int g = 0; g < 4; g++) { xg[g][0] = *reinterpret_cast<const float4*>(g0 + g * H); xg[g][1] = *reinterpret_cast<const float4*>(g0 + g * H + 4); }
     }
     for (int t = 0; t < T; t++) {
-      float acc[4][4];
+      float acc[32];  // unit-major: acc[u*4 + g]
       if (t > 0) {
-        uint32_t v[4][8];
         mbar_wait(sm.tfull, (t - 1) & 1);
         if (threadIdx.x == 64) LRCN_TRACE(3);
         tc_fence_after();
-        const uint32_t tl = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(8 * half);
-        LRCN_TMEM_LD_8(tl, v[0]);
-        LRCN_TMEM_LD_8(tl + NH, v[1]);
-        LRCN_TMEM_LD_8(tl + 2 * NH, v[2]);
-        LRCN_TMEM_LD_8(tl + 3 * NH, v[3]);
-        tmem_ld_wait();
+        stacked_collect(sm, tmem_base, quad, half, lane, acc);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(sm.tempty);
-#pragma unroll
-        for (int g = 0; g < 4; g++)
-#pragma unroll
-          for (int e = 0; e < 4; e++) {
-            const uint32_t hi4 = __shfl_sync(0xffffffffu, v[g][4 + e], lane & 15);
-            acc[g][e] = __uint_as_float(upper ? hi4 : v[g][e]);
-          }
       } else {
 #pragma unroll
-        for (int g = 0; g < 4; g++)
-#pragma unroll
-          for (int e = 0; e < 4; e++) acc[g][e] = 0.f;
+        for (int c = 0; c < 32; c++) acc[c] = 0.f;
       }
-      float f[4] = {gf.x, gf.y, gf.z, gf.w}, in[4] = {gi.x, gi.y, gi.z, gi.w}, o[4] = {go.x, go.y, go.z, go.w}, ch[4] = {gg.x, gg.y, gg.z, gg.w};
-      float hn[4];
+      float f[8], in[8], o[8], ch[8], hn[8];
       const size_t hnext = ((size_t)(t + 1) * B + m) * H + j;
       if (active) {
+        const float xf[8] = {xg[0][0].x, xg[0][0].y, xg[0][0].z, xg[0][0].w, xg[0][1].x, xg[0][1].y, xg[0][1].z, xg[0][1].w};
+        const float xi[8] = {xg[1][0].x, xg[1][0].y, xg[1][0].z, xg[1][0].w, xg[1][1].x, xg[1][1].y, xg[1][1].z, xg[1][1].w};
+        const float xo[8] = {xg[2][0].x, xg[2][0].y, xg[2][0].z, xg[2][0].w, xg[2][1].x, xg[2][1].y, xg[2][1].z, xg[2][1].w};
+        const float xc[8] = {xg[3][0].x, xg[3][0].y, xg[3][0].z, xg[3][0].w, xg[3][1].x, xg[3][1].y, xg[3][1].z, xg[3][1].w};
+        __nv_bfloat16 hh[8], ll[8];
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-          f[e] = sigm_fast(f[e] + acc[0][e]);
-          in[e] = sigm_fast(in[e] + acc[1][e]);
-          o[e] = sigm_fast(o[e] + acc[2][e]);
-          ch[e] = tanh_fast(ch[e] + acc[3][e]);
+        for (int e = 0; e < 8; e++) {
+          f[e] = sigm_fast(xf[e] + acc[4 * e]);
+          in[e] = sigm_fast(xi[e] + acc[4 * e + 1]);
+          o[e] = sigm_fast(xo[e] + acc[4 * e + 2]);
+          ch[e] = tanh_fast(xc[e] + acc[4 * e + 3]);
           creg[e] = creg[e] * f[e] + in[e] * ch[e];
           hn[e] = o[e] * tanh_fast(creg[e]);
+          split_bf16(hn[e], hh[e], ll[e]);
         }
-        __nv_bfloat16 hh[4], ll[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) split_bf16(hn[e], hh[e], ll[e]);
-        *reinterpret_cast<uint2*>(p.o_hi + hnext) = *reinterpret_cast<uint2*>(hh);
-        *reinterpret_cast<uint2*>(p.o_lo + hnext) = *reinterpret_cast<uint2*>(ll);
+        *reinterpret_cast<uint4*>(p.o_hi + hnext) = *reinterpret_cast<uint4*>(hh);
+        *reinterpret_cast<uint4*>(p.o_lo + hnext) = *reinterpret_cast<uint4*>(ll);
       }
-      if (t + 1 < T) {  // publish h_t: generic-proxy stores -> visible to the other CTAs' TMA (async proxy) reads
-        // bar.sync orders every epilogue thread's stores before thread 64's gpu-scope release (cumulativity); the reading
-        // producers fence generic->async proxy after their acquire
+      if (t + 1 < T) {
+        // publish h_t: bar.sync orders every epilogue thread's stores before thread 64's gpu-scope release (cumulativity);
+        // the reading producers fence generic->async proxy after their acquire
         if (threadIdx.x == 64) LRCN_TRACE(4);
         epi_bar_sync();
         if (threadIdx.x == 64) { LRCN_TRACE(5); fence_proxy_async_global(); grid_arrive(ctr); LRCN_TRACE(6); }
@@ -651,15 +683,21 @@ lstm_fwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       if (active) {  // off the critical path: what only later kernels read
         float* grow = p.acts + ((size_t)t * B + m) * 4 * H + j;
         *reinterpret_cast<float4*>(grow) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4*>(grow + 4) = make_float4(f[4], f[5], f[6], f[7]);
         *reinterpret_cast<float4*>(grow + H) = make_float4(in[0], in[1], in[2], in[3]);
+        *reinterpret_cast<float4*>(grow + H + 4) = make_float4(in[4], in[5], in[6], in[7]);
         *reinterpret_cast<float4*>(grow + 2 * H) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(grow + 2 * H + 4) = make_float4(o[4], o[5], o[6], o[7]);
         *reinterpret_cast<float4*>(grow + 3 * H) = make_float4(ch[0], ch[1], ch[2], ch[3]);
+        *reinterpret_cast<float4*>(grow + 3 * H + 4) = make_float4(ch[4], ch[5], ch[6], ch[7]);
         *reinterpret_cast<float4*>(p.cs + hnext) = make_float4(creg[0], creg[1], creg[2], creg[3]);
+        *reinterpret_cast<float4*>(p.cs + hnext + 4) = make_float4(creg[4], creg[5], creg[6], creg[7]);
         *reinterpret_cast<float4*>(p.hs + hnext) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+        *reinterpret_cast<float4*>(p.hs + hnext + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
         if (t + 1 < T) {  // prefetch the next step's x-part
           const float* gn = p.acts + ((size_t)(t + 1) * B + m) * 4 * H + j;
-          gf = *reinterpret_cast<const float4*>(gn); gi = *reinterpret_cast<const float4*>(gn + H);
-          go = *reinterpret_cast<const float4*>(gn + 2 * H); gg = *reinterpret_cast<const float4*>(gn + 3 * H);
+#pragma unroll
+          for (int g = 0; g < 4; g++) { xg[g][0] = *reinterpret_cast<const float4*>(gn + g * H); xg[g][1] = *reinterpret_cast<const float4*>(gn + g * H + 4); }
         }
       }
     }
@@ -669,7 +707,7 @@ lstm_fwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<L_TMEM_COLS>(tmem_base);
+    tmem_dealloc<SEQ_TMEM_COLS>(tmem_base);
   }
 }
 
@@ -699,7 +737,7 @@ lstm_bwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmA_lo); prefetch_tensormap(&tmB_hi); prefetch_tensormap(&tmB_lo);
   }
-  if (warp == 1) tmem_alloc<L_TMEM_COLS>(smem_u32(sm.tmem_slot));
+  if (warp == 1) tmem_alloc<SEQ_TMEM_COLS>(smem_u32(sm.tmem_slot));
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -731,7 +769,7 @@ lstm_bwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     }
   } else if (warp == 1) {
     if (lane == 0 && nkb > 0) {
-      const uint32_t idesc = idesc_bf16(LM, NT, false, false);
+      const uint32_t idesc = idesc_bf16(128, 128, false, false);
       mbar_wait(sm.wbar, 0);
       int it = 0, n = 0;
       for (int t = T - 2; t >= 0; t--, n++) {
@@ -740,15 +778,7 @@ lstm_bwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           const int s = it % BSTAGES;
           mbar_wait(sm.full0 + 8 * s, (it / BSTAGES) & 1);
           tc_fence_after();
-          const uint32_t sa = sm.ring + s * RSTAGE, sb = sm.res + i * 2 * B_HALF;
-#pragma unroll
-          for (int k = 0; k < LBK / 16; k++) {
-            const uint64_t a_hi = desc_kmajor(sa, k), a_lo = desc_kmajor(sa + A_HALF, k);
-            const uint64_t b_hi = desc_kmajor(sb, k), b_lo = desc_kmajor(sb + B_HALF, k);
-            umma_bf16(tmem_base, a_lo, b_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
-            umma_bf16(tmem_base, a_hi, b_lo, idesc, 1u);
-            umma_bf16(tmem_base, a_hi, b_hi, idesc, 1u);
-          }
+          stacked_mma_kblock(tmem_base, sm.ring + s * RSTAGE, sm.res + i * 2 * B_HALF, idesc, i == 0);
           umma_commit(sm.empty0 + 8 * s);
         }
         umma_commit(sm.tfull);
@@ -756,7 +786,8 @@ lstm_bwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     }
   } else {
     const int ew = warp - 2, quad = warp & 3, half = ew >> 2, upper = lane >> 4;
-    const int row = quad * 16 + (lane & 15);
+    // phase-2 ownership (independent of the TMEM layout): 256 threads x 4 units of this CTA's 16 units
+    const int row = (ew & 3) * 16 + (lane & 15);
     const int ug = 2 * half + upper;
     const int m = m0 + row;
     const int j = nt * NT + 16 * (int)rank + 4 * ug;
@@ -780,31 +811,30 @@ lstm_bwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       const bool has_rec = t < T - 1;
       float rec[4] = {0.f, 0.f, 0.f, 0.f};
       if (has_rec) {
-        // phase 1: scatter my partial to the owners (lanes 0-15 hold the rows of this TMEM quadrant)
-        uint32_t v[32];
+        // phase 1: finish my partial (hi*hi + hi*lo + lo*hi) and scatter it to the owners of its columns
+        float part[32];
         if (nkb > 0) {
           mbar_wait(sm.tfull, n & 1);
           tc_fence_after();
-          LRCN_TMEM_LD_32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(32 * half), v);
-          tmem_ld_wait();
+          stacked_collect(sm, tmem_base, quad, half, lane, part);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(sm.tempty);
         } else {
 #pragma unroll
-          for (int c = 0; c < 32; c++) v[c] = 0u;
+          for (int c = 0; c < 32; c++) part[c] = 0.f;
         }
         if (n >= 1) mbar_wait_cluster(sm.redempty, (n - 1) & 1);  // every owner has consumed my previous partial
-        if (lane < 16) {
-          const uint32_t local = smem_u32(sm.red) + (uint32_t)(((int)rank * LM + row) * (NT / CL)) * 4u;
+        if (quad < 2) {
+          const int prow = 32 * quad + lane;  // tile row held by this thread; its columns are [32*half, +32)
+          const uint32_t local = smem_u32(sm.red) + (uint32_t)(((int)rank * LM + prow) * (NT / CL)) * 4u;
 #pragma unroll
           for (int d2 = 0; d2 < 2; d2++) {
             const uint32_t dst = (uint32_t)(2 * half + d2);
             const uint32_t ra = dsmem_addr(local, dst);
 #pragma unroll
             for (int q = 0; q < 4; q++)
-              dsmem_st_f4(ra + 16u * q, make_float4(__uint_as_float(v[16 * d2 + 4 * q]), __uint_as_float(v[16 * d2 + 4 * q + 1]),
-                                                     __uint_as_float(v[16 * d2 + 4 * q + 2]), __uint_as_float(v[16 * d2 + 4 * q + 3])));
+              dsmem_st_f4(ra + 16u * q, make_float4(part[16 * d2 + 4 * q], part[16 * d2 + 4 * q + 1], part[16 * d2 + 4 * q + 2], part[16 * d2 + 4 * q + 3]));
             mbar_arrive_remote(dsmem_addr(sm.redfull, dst));  // release.cluster: orders my stores before the owner's acquire
           }
         }
@@ -870,7 +900,7 @@ lstm_bwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<L_TMEM_COLS>(tmem_base);
+    tmem_dealloc<SEQ_TMEM_COLS>(tmem_base);
   }
 }
 
@@ -879,11 +909,11 @@ constexpr int F_NT = NT, F_NH = NT / 4;  // forward: 16 hidden units x 4 gates p
 constexpr int R_NT = NT;                // backward: 64 hidden units per cluster, 16 finished by each CTA
 
 // forward operand: rows = gate columns n = g*H + j of the layer weight W [4H][ldw] (columns [x_off, x_off+H) = W_h),
-// permuted so that CTA nt's 64 rows are [f i o g] x its 16 units:  row (jt*4 + g)*16 + u  <-  n = g*H + jt*16 + u
+// permuted UNIT-major so that CTA nt's 64 rows are its 16 units x [f i o g]:  row jt*64 + u*4 + g  <-  n = g*H + jt*16 + u
 __global__ void permute_split_kernel(const float* __restrict__ W, int ldw, int x_off, int H, int Hp, __nv_bfloat16* __restrict__ hi,
                                      __nv_bfloat16* __restrict__ lo) {
   const int row = blockIdx.x;
-  const int jt = row / F_NT, r = row % F_NT, g = r / F_NH, u = r % F_NH;
+  const int jt = row / F_NT, r = row % F_NT, u = r / 4, g = r % 4;
   const int j = jt * F_NH + u;
   for (int k = threadIdx.x; k < Hp; k += blockDim.x) {
     float x = 0.f;
