@@ -60,8 +60,10 @@ struct GemmParams {
   __nv_bfloat16* C_hi; __nv_bfloat16* C_lo;
 };
 
-template <bool AK, bool BKM, int BN_>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// CM = cluster size along M: the CM CTAs of a cluster compute M-adjacent tiles of the same N-tile in lockstep; each loads
+// 1/CM of the B tile and multicasts it to the others, cutting the L2->SMEM traffic these GEMMs are bound by.
+template <bool AK, bool BKM, int BN_, int CM>
+__global__ void __cluster_dims__(CM, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                    const GemmParams p) {
@@ -80,11 +82,15 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb_total = (p.K + BK - 1) / BK;
-  const int tiles_mn = p.tiles_m * p.tiles_n;
+  const int tiles_mg = (p.tiles_m + CM - 1) / CM;  // groups of CM M-adjacent tiles
+  const int tiles_mn = tiles_mg * p.tiles_n;
   const int total_work = tiles_mn * p.splits;
+  const int rank = CM > 1 ? (int)cluster_ctarank() : 0;
+  const int cidx = blockIdx.x / CM, ncl = gridDim.x / CM;
+  constexpr uint16_t CMASK = (uint16_t)((1u << CM) - 1);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar0 + 8 * s, 1); mbar_init(empty_bar0 + 8 * s, 1); }
+    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar0 + 8 * s, 1); mbar_init(empty_bar0 + 8 * s, CM); }
     for (int a = 0; a < 2; a++) { mbar_init(tfull_bar0 + 8 * a, 1); mbar_init(tempty_bar0 + 8 * a, 4); }
     mbar_init_fence();
   }
@@ -94,6 +100,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
+  if (CM > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -101,14 +108,14 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     // ===================== TMA producer =====================
     if (lane == 0) {
       int it = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      for (int w = cidx; w < total_work; w += ncl) {
         const int z = w / tiles_mn, rem = w - z * tiles_mn;
-        const int m0 = (rem % p.tiles_m) * BM, n0 = (rem / p.tiles_m) * BN_;
+        const int m0 = ((rem % tiles_mg) * CM + rank) * BM, n0 = (rem / tiles_mg) * BN_;
         const int kb_begin = z * p.kb_per_split, kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
         for (int kb = kb_begin; kb < kb_end; kb++, it++) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(empty_bar0 + 8 * s, ph ^ 1);
+          mbar_wait(empty_bar0 + 8 * s, ph ^ 1);  // every CTA of the cluster has consumed this stage
           const uint32_t full = full_bar0 + 8 * s;
           mbar_expect_tx(full, Cfg::STAGE_BYTES);
           const uint32_t sA_hi = smem_base + s * Cfg::STAGE_BYTES, sA_lo = sA_hi + A_TILE;
@@ -124,14 +131,30 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
               tma_load_2d(sA_lo + b * 8192, &tmA_lo, full, m0 + 64 * b, k0);
             }
           }
-          if (BKM) {
-            tma_load_2d(sB_hi, &tmB_hi, full, k0, n0);
-            tma_load_2d(sB_lo, &tmB_lo, full, k0, n0);
-          } else {
+          if (CM == 1) {
+            if (BKM) {
+              tma_load_2d(sB_hi, &tmB_hi, full, k0, n0);
+              tma_load_2d(sB_lo, &tmB_lo, full, k0, n0);
+            } else {
 #pragma unroll
-            for (int b = 0; b < BN_ / 64; b++) {
-              tma_load_2d(sB_hi + b * 8192, &tmB_hi, full, n0 + 64 * b, k0);
-              tma_load_2d(sB_lo + b * 8192, &tmB_lo, full, n0 + 64 * b, k0);
+              for (int b = 0; b < BN_ / 64; b++) {
+                tma_load_2d(sB_hi + b * 8192, &tmB_hi, full, n0 + 64 * b, k0);
+                tma_load_2d(sB_lo + b * 8192, &tmB_lo, full, n0 + 64 * b, k0);
+              }
+            }
+          } else {  // this CTA fetches its 1/CM share of the B tile and multicasts it to the whole cluster
+            if (BKM) {
+              constexpr int ROWS = BN_ / CM;  // tensor map box = {64, ROWS}
+              tma_load_2d_mcast(sB_hi + rank * ROWS * 128, &tmB_hi, full, k0, n0 + rank * ROWS, CMASK);
+              tma_load_2d_mcast(sB_lo + rank * ROWS * 128, &tmB_lo, full, k0, n0 + rank * ROWS, CMASK);
+            } else {
+              constexpr int NB = BN_ / 64 / CM;  // 64-wide boxes per CTA
+#pragma unroll
+              for (int bb = 0; bb < NB; bb++) {
+                const int b = rank * NB + bb;
+                tma_load_2d_mcast(sB_hi + b * 8192, &tmB_hi, full, n0 + 64 * b, k0, CMASK);
+                tma_load_2d_mcast(sB_lo + b * 8192, &tmB_lo, full, n0 + 64 * b, k0, CMASK);
+              }
             }
           }
         }
@@ -142,7 +165,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     if (lane == 0) {
       const uint32_t idesc = idesc_bf16(BM, BN_, !AK, !BKM);
       int it = 0, local = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x, local++) {
+      for (int w = cidx; w < total_work; w += ncl, local++) {
         const int z = w / tiles_mn;
         const int kb_begin = z * p.kb_per_split, kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
         const int acc = local & 1;
@@ -167,7 +190,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             umma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
             umma_bf16(tmem_d, a_hi, b_hi, idesc, 1u);
           }
-          umma_commit(empty_bar0 + 8 * s);  // frees the smem stage once the MMAs above retire
+          if (CM > 1) umma_commit_mcast(empty_bar0 + 8 * s, CMASK);  // stage consumed in MY smem: tell every producer of the cluster
+          else umma_commit(empty_bar0 + 8 * s);                      // frees the smem stage once the MMAs above retire
         }
         umma_commit(tfull_bar0 + 8 * acc);  // accumulator complete -> epilogue
       }
@@ -180,9 +204,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                         (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
     int local = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x, local++) {
+    for (int w = cidx; w < total_work; w += ncl, local++) {
       const int z = w / tiles_mn, rem = w - z * tiles_mn;
-      const int m0 = (rem % p.tiles_m) * BM, n0 = (rem / p.tiles_m) * BN_;
+      const int m0 = ((rem % tiles_mg) * CM + rank) * BM, n0 = (rem / tiles_mg) * BN_;
       const int acc = local & 1;
       const uint32_t aph = (local >> 1) & 1;
       mbar_wait(tfull_bar0 + 8 * acc, aph);
@@ -258,6 +282,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
+  if (CM > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into its smem / arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
@@ -326,11 +351,13 @@ static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
 }
-static int g_num_sms = 148, g_force_bn = 0;
+static int g_num_sms = 148, g_force_bn = 0, g_force_cm = 0;
 
 template <bool AK, bool BKM, int BN_>
 static cudaError_t set_attr() {
-  return cudaFuncSetAttribute(gemm_bf16x3_kernel<AK, BKM, BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<BN_>::SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(gemm_bf16x3_kernel<AK, BKM, BN_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<BN_>::SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16x3_kernel<AK, BKM, BN_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<BN_>::SMEM_BYTES);
+  return e;
 }
 bool init_gemm_sm100() {
   cudaError_t e = set_attr<true, true, 128>();
@@ -347,13 +374,15 @@ bool init_gemm_sm100() {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   g_force_bn = env_int("LRCN_GEMM_BN", 0);
+  g_force_cm = env_int("LRCN_GEMM_CM", 0);
   return true;
 }
 
 template <bool AK, bool BKM, int BN_>
-static void launch(cudaStream_t s, int grid, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-                   const GemmParams& p) {
-  gemm_bf16x3_kernel<AK, BKM, BN_><<<grid, NUM_THREADS, TileCfg<BN_>::SMEM_BYTES, s>>>(a_hi, a_lo, b_hi, b_lo, p);
+static void launch(cudaStream_t s, int grid, int cm, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                   const CUtensorMap& b_lo, const GemmParams& p) {
+  if (cm == 2) gemm_bf16x3_kernel<AK, BKM, BN_, 2><<<grid, NUM_THREADS, TileCfg<BN_>::SMEM_BYTES, s>>>(a_hi, a_lo, b_hi, b_lo, p);
+  else gemm_bf16x3_kernel<AK, BKM, BN_, 1><<<grid, NUM_THREADS, TileCfg<BN_>::SMEM_BYTES, s>>>(a_hi, a_lo, b_hi, b_lo, p);
 }
 
 bool gemm_bf16x3(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo,
@@ -379,12 +408,15 @@ bool gemm_bf16x3(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int
   }
   const int kb_per = (num_kb + splits - 1) / splits;
   splits = (num_kb + kb_per - 1) / kb_per;
+  // cluster of 2 M-adjacent tiles sharing (multicasting) the B tile whenever there are enough tile pairs to fill the SMs
+  int cm = (tm >= 2 && ((tm + 1) / 2) * tn * splits * 2 >= g_num_sms) ? 2 : 1;
+  if (g_force_cm == 1 || g_force_cm == 2) cm = (tm >= 2) ? g_force_cm : 1;
 
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   bool ok = true;
   if (a_kmajor) ok = ok && get_tensor_map_bf16(&ta_hi, A_hi, K, M, lda, BM) && get_tensor_map_bf16(&ta_lo, A_lo, K, M, lda, BM);
   else          ok = ok && get_tensor_map_bf16(&ta_hi, A_hi, M, K, lda, BK) && get_tensor_map_bf16(&ta_lo, A_lo, M, K, lda, BK);
-  if (b_kmajor) ok = ok && get_tensor_map_bf16(&tb_hi, B_hi, K, N, ldb, bn) && get_tensor_map_bf16(&tb_lo, B_lo, K, N, ldb, bn);
+  if (b_kmajor) ok = ok && get_tensor_map_bf16(&tb_hi, B_hi, K, N, ldb, bn / cm) && get_tensor_map_bf16(&tb_lo, B_lo, K, N, ldb, bn / cm);
   else          ok = ok && get_tensor_map_bf16(&tb_hi, B_hi, N, K, ldb, BK) && get_tensor_map_bf16(&tb_lo, B_lo, N, K, ldb, BK);
   if (!ok) return false;
 
@@ -395,12 +427,13 @@ bool gemm_bf16x3(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.tiles_m = tm; p.tiles_n = tn; p.splits = splits; p.kb_per_split = kb_per;
   p.C = C; p.ldc = ldc; p.bias = bias; p.beta = beta ? 1 : 0; p.C_hi = C_hi; p.C_lo = C_lo;
-  const int total = tm * tn * splits;
-  const int grid = total < g_num_sms ? total : g_num_sms;
-#define LRCN_LAUNCH(AKv, BKv)                                                     \
-  do {                                                                            \
-    if (bn == 256) launch<AKv, BKv, 256>(s, grid, ta_hi, ta_lo, tb_hi, tb_lo, p); \
-    else launch<AKv, BKv, 128>(s, grid, ta_hi, ta_lo, tb_hi, tb_lo, p);           \
+  const int total = ((tm + cm - 1) / cm) * tn * splits;  // work units per cluster
+  const int max_cl = g_num_sms / cm;
+  const int grid = (total < max_cl ? total : max_cl) * cm;
+#define LRCN_LAUNCH(AKv, BKv)                                                         \
+  do {                                                                                \
+    if (bn == 256) launch<AKv, BKv, 256>(s, grid, cm, ta_hi, ta_lo, tb_hi, tb_lo, p); \
+    else launch<AKv, BKv, 128>(s, grid, cm, ta_hi, ta_lo, tb_hi, tb_lo, p);           \
   } while (0)
   if (a_kmajor && b_kmajor) LRCN_LAUNCH(true, true);
   else if (a_kmajor && !b_kmajor) LRCN_LAUNCH(true, false);
