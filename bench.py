@@ -171,8 +171,8 @@ def beam_leg(local_rank, rank, world, prec, max_over_ranks, barrier, n_img=1024,
         g.load_features(1, ids, synth.features(n_img, seed=6 + rank))
         # untrained weights never emit eos (31-step decodes); bisect an eos bias so that the mean decode length is COCO-like
         # (10.4 steps).  Deterministic: same seeds -> same bias on every rank.
-        lo_b, hi_b = -1.0, 1.0
-        for _ in range(14):
+        lo_b, hi_b = -2.0, 14.0
+        for _ in range(16):
             mid = 0.5 * (lo_b + hi_b)
             bout = model[8].copy()
             bout[0, 0] = mid

@@ -49,7 +49,8 @@ void lstm_cell_bwd(cudaStream_t s, float* gates, const float* c_prev, const floa
                    int B, int H);
 // row-wise log-softmax cross-entropy: rowlp[r] = logp(a_r)[y_r]; if train, logits <- (softmax - onehot)*inv_ntok
 void softmax_ce(cudaStream_t s, float* logits, int ld, int R, int V, const int* tgt, float* rowlp,
-                const StepScalars* sc, bool train, __nv_bfloat16* hi = nullptr, __nv_bfloat16* lo = nullptr);
+                const StepScalars* sc, bool train, __nv_bfloat16* hi = nullptr, __nv_bfloat16* lo = nullptr,
+                double* total_out = nullptr /* fp64 sum of rowlp, written by the last CTA */, unsigned int* done_ctr = nullptr);
 void reduce_sum_double(cudaStream_t s, const float* x, int n, double* out);
 void colsum(cudaStream_t s, const float* A, int ld, int R, int N, float* out, bool accumulate);
 // dZ *= dropout mask (site 1); dv[i][j] = sum_t dZ[(t*B+i)][C+j]
@@ -99,9 +100,10 @@ void init_simt_kernels();
 bool init_lstm_sm100();
 size_t lstm_permuted_elems(int H);    // elements of the gate-interleaved forward operand (per hi / lo)
 size_t lstm_transposed_elems(int H);  // elements of the transposed backward operand (per hi / lo)
-// W_h = columns [x_off, x_off+H) of the layer weight W [4H][ldw] -> bf16 hi/lo step operands (tr_* may be null)
-void lstm_prepare_weights(cudaStream_t s, const float* W, int ldw, int x_off, int H, __nv_bfloat16* perm_hi, __nv_bfloat16* perm_lo,
-                          __nv_bfloat16* tr_hi, __nv_bfloat16* tr_lo);
+// W_h = columns [x_off, x_off+H) of each layer weight W [4H][ldw] -> bf16 hi/lo step operands of both layers (t*_ may be null)
+void lstm_prepare_weights2(cudaStream_t s, const float* W1, int ldw1, int x_off1, int H1, __nv_bfloat16* p1_hi, __nv_bfloat16* p1_lo,
+                           __nv_bfloat16* t1_hi, __nv_bfloat16* t1_lo, const float* W2, int ldw2, int x_off2, int H2, __nv_bfloat16* p2_hi,
+                           __nv_bfloat16* p2_lo, __nv_bfloat16* t2_hi, __nv_bfloat16* t2_lo);
 // gates [B][4H] holds x-part + bias on entry and the activated gates on exit; has_rec=false at t=0 (h_0 = 0)
 bool lstm_fwd_step(cudaStream_t s, int B, int H, bool has_rec, const __nv_bfloat16* hprev_hi, const __nv_bfloat16* hprev_lo,
                    const __nv_bfloat16* wperm_hi, const __nv_bfloat16* wperm_lo, float* gates, const float* c_prev, float* c_out,

@@ -305,9 +305,12 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512) softmax_ce_kernel(float* __restrict__ logits, int ld, int V, const int* __restrict__ tgt,
                                                          float* __restrict__ rowlp, const StepScalars* __restrict__ sc, int train,
-                                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+                                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                         double* __restrict__ total_out, unsigned int* __restrict__ done_ctr) {
   extern __shared__ __align__(16) float row[];
   __shared__ float red[32];
+  __shared__ double dred[16];
+  __shared__ int is_last;
   const int r = blockIdx.x;
   float* a = logits + (size_t)r * ld;
   const int V4 = V >> 2;  // ld % 8 == 0 and the arena is 256 B aligned -> rows are 16 B aligned
@@ -342,11 +345,36 @@ __global__ void __launch_bounds__(512) softmax_ce_kernel(float* __restrict__ log
       if (hi) store_split4(hi, lo, base + 4 * q, o);
     }
   }
+  // the last CTA to finish sums the per-row log-probs in a FIXED order (deterministic fp64 total: lrcn.jl:567 `total +=`)
+  if (total_out) {
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned int prev = atomicAdd(done_ctr, 1u);
+      is_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      double acc = 0.0;
+      const int R = gridDim.x;
+      for (int i = threadIdx.x; i < R; i += blockDim.x) acc += (double)__ldcg(rowlp + i);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if ((threadIdx.x & 31) == 0) dred[threadIdx.x >> 5] = acc;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += dred[w];
+        *total_out = t;
+        *done_ctr = 0u;
+      }
+    }
+  }
 }
 void softmax_ce(cudaStream_t s, float* logits, int ld, int R, int V, const int* tgt, float* rowlp, const StepScalars* sc,
-                bool train, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+                bool train, __nv_bfloat16* hi, __nv_bfloat16* lo, double* total_out, unsigned int* done_ctr) {
   size_t smem = (size_t)ld * sizeof(float);
-  softmax_ce_kernel<<<R, 512, smem, s>>>(logits, ld, V, tgt, rowlp, sc, train ? 1 : 0, hi, lo);
+  softmax_ce_kernel<<<R, 512, smem, s>>>(logits, ld, V, tgt, rowlp, sc, train ? 1 : 0, hi, lo, total_out, done_ctr);
   count_launch();
 }
 
@@ -408,25 +436,27 @@ void colsum(cudaStream_t s, const float* A, int ld, int R, int N, float* out, bo
 __global__ void dz_finish_kernel(float* __restrict__ dZ, float* __restrict__ dv, int ldv, int T, int B, int C,
                                  const StepScalars* __restrict__ sc, int train, __nv_bfloat16* __restrict__ z_hi,
                                  __nv_bfloat16* __restrict__ z_lo, __nv_bfloat16* __restrict__ v_hi, __nv_bfloat16* __restrict__ v_lo) {
-  int i = blockIdx.x;  // batch row
-  for (int j = threadIdx.x; j < 2 * C; j += blockDim.x) {
-    float acc = 0.f;
-    for (int t = 0; t < T; t++) {
-      size_t r = (size_t)t * B + i;
-      float x = dZ[r * 2 * C + j];
-      if (train) { x *= drop_scale(sc, 1, (uint64_t)r * 2 * C + j); dZ[r * 2 * C + j] = x; }
-      if (z_hi) { __nv_bfloat16 h, l; split_one(x, h, l); z_hi[r * 2 * C + j] = h; z_lo[r * 2 * C + j] = l; }
-      acc += x;
-    }
-    if (j >= C) {
-      dv[(size_t)i * ldv + (j - C)] = acc;
-      if (v_hi) { __nv_bfloat16 h, l; split_one(acc, h, l); v_hi[(size_t)i * ldv + (j - C)] = h; v_lo[(size_t)i * ldv + (j - C)] = l; }
-    }
+  const int i = blockIdx.x;                                // batch row
+  const int j = blockIdx.y * blockDim.x + threadIdx.x;     // column of Z
+  if (j >= 2 * C) return;
+  float acc = 0.f;
+#pragma unroll 4
+  for (int t = 0; t < T; t++) {
+    const size_t idx = ((size_t)t * B + i) * 2 * C + j;
+    float x = dZ[idx];
+    if (train) { x *= drop_scale(sc, 1, (uint64_t)idx); dZ[idx] = x; }
+    if (z_hi) { __nv_bfloat16 h, l; split_one(x, h, l); z_hi[idx] = h; z_lo[idx] = l; }
+    acc += x;
+  }
+  if (j >= C) {
+    dv[(size_t)i * ldv + (j - C)] = acc;
+    if (v_hi) { __nv_bfloat16 h, l; split_one(acc, h, l); v_hi[(size_t)i * ldv + (j - C)] = h; v_lo[(size_t)i * ldv + (j - C)] = l; }
   }
 }
 void dz_finish(cudaStream_t s, float* dZ, float* dv, int ldv, int T, int B, int C, const StepScalars* sc, bool train,
                __nv_bfloat16* z_hi, __nv_bfloat16* z_lo, __nv_bfloat16* v_hi, __nv_bfloat16* v_lo) {
-  dz_finish_kernel<<<B, 256, 0, s>>>(dZ, dv, ldv, T, B, C, sc, train ? 1 : 0, z_hi, z_lo, v_hi, v_lo);
+  dim3 grid(B, (2 * C + 127) / 128);
+  dz_finish_kernel<<<grid, 128, 0, s>>>(dZ, dv, ldv, T, B, C, sc, train ? 1 : 0, z_hi, z_lo, v_hi, v_lo);
   count_launch();
 }
 

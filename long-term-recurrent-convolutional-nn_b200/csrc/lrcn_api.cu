@@ -316,6 +316,7 @@ static int create_impl(const lrcn_config* cfg, lrcn_handle* h) {
   memset(h->h_sc, 0, sizeof(StepScalars));
   CK(cudaMalloc(&h->d_loss, 8)); CK(cudaMallocHost(&h->h_loss, 8));
   CK(cudaMalloc(&h->d_counters, 64 * sizeof(unsigned int)));
+  CK(cudaMemset(h->d_counters, 0, 64 * sizeof(unsigned int)));
   if (getenv("LRCN_SEQ_TRACE")) { CK(cudaMalloc(&h->d_trace, 64 * 8 * 8)); CK(cudaMemset(h->d_trace, 0, 64 * 8 * 8)); }
   CK(cudaMalloc(&h->g_last, G * 4)); CK(cudaMalloc(&h->g_ctok, G * 16 * 4)); CK(cudaMalloc(&h->g_stok, G * 4)); CK(cudaMalloc(&h->g_spar, G * 4));
   CK(cudaMalloc(&h->g_hista, G * ML * 4)); CK(cudaMalloc(&h->g_histb, G * ML * 4)); CK(cudaMalloc(&h->g_done, G * 4));
@@ -553,16 +554,17 @@ static void enqueue_forward(lrcn_handle* h, int split, int B, int l, bool train)
   gemm(h, true, true, B, C, LRCN_F_CNN, X, LRCN_F_CNN, Wp(h, 6), LRCN_F_CNN, v, ldv, false, nullptr);  // input*Wcnn  lrcn.jl:558
   gather_embed(s, Wp(h, 7), h->d_tok_in, R, E, Eall, h->d_sc, train, SH(h, Eall).hi, SH(h, Eall).lo);
   gemm(h, true, true, R, 4 * H1, E, Eall, E, Wp(h, 1), E + H1, acts1, 4 * H1, false, Wp(h, 2));         // x-part of layer 1, all t
-  if (h->bf16mode) lstm_prepare_weights(s, Wp(h, 1), E + H1, E, H1, h->wp1_hi, h->wp1_lo, train ? h->wt1_hi : nullptr, h->wt1_lo);
+  if (h->bf16mode)
+    lstm_prepare_weights2(s, Wp(h, 1), E + H1, E, H1, h->wp1_hi, h->wp1_lo, train ? h->wt1_hi : nullptr, h->wt1_lo, Wp(h, 3), 2 * H2, 2 * C, H2,
+                          h->wp2_hi, h->wp2_lo, train ? h->wt2_hi : nullptr, h->wt2_lo);
   lstm_layer_fwd(h, 1, T, B, acts1, h1, c1);
   gemm(h, true, true, R, C, H1, h1 + (size_t)B * H1, H1, Wp(h, 5), H1, Z, 2 * C, false, nullptr);         // x*w[end-4]  lrcn.jl:545
   z_finish(s, Z, v, ldv, R, B, C, h->d_sc, train, SH(h, Z).hi, SH(h, Z).lo);  // hcat(x,x_cnn) + dropout          lrcn.jl:546-547
   gemm(h, true, true, R, 4 * H2, 2 * C, Z, 2 * C, Wp(h, 3), 2 * H2, acts2, 4 * H2, false, Wp(h, 4));
-  if (h->bf16mode) lstm_prepare_weights(s, Wp(h, 3), 2 * H2, 2 * C, H2, h->wp2_hi, h->wp2_lo, train ? h->wt2_hi : nullptr, h->wt2_lo);
   lstm_layer_fwd(h, 2, T, B, acts2, h2, c2);
   gemm(h, true, true, R, V, H2, h2 + (size_t)B * H2, H2, Wp(h, 8), H2, logits, ldV, false, Wp(h, 9));      // x*w[end-1] .+ w[end]  lrcn.jl:550
-  softmax_ce(s, logits, ldV, R, V, h->d_tok_tgt, WS(h, o.rowlp), h->d_sc, train, SH(h, logits).hi, SH(h, logits).lo);  // logp + gather  lrcn.jl:562-567
-  reduce_sum_double(s, WS(h, o.rowlp), R, h->d_loss);
+  softmax_ce(s, logits, ldV, R, V, h->d_tok_tgt, WS(h, o.rowlp), h->d_sc, train, SH(h, logits).hi, SH(h, logits).lo, h->d_loss,
+             h->d_counters + 48);  // logp + gather + fp64 total  lrcn.jl:562-567
 }
 
 static void enqueue_backward_seg(lrcn_handle* h, int B, int l, bool train, int seg) {
@@ -920,8 +922,8 @@ extern "C" int lrcn_beam_search(lrcn_handle* h, int split, const int64_t* image_
     CK(cudaStreamSynchronize(h->stream));
     try {
       if (h->bf16mode) {
-        lstm_prepare_weights(h->stream, Wp(h, 1), h->E + h->H1, h->E, h->H1, h->wp1_hi, h->wp1_lo, nullptr, nullptr);
-        lstm_prepare_weights(h->stream, Wp(h, 3), 2 * h->H2, 2 * h->C, h->H2, h->wp2_hi, h->wp2_lo, nullptr, nullptr);
+        lstm_prepare_weights2(h->stream, Wp(h, 1), h->E + h->H1, h->E, h->H1, h->wp1_hi, h->wp1_lo, nullptr, nullptr, Wp(h, 3), 2 * h->H2,
+                              2 * h->C, h->H2, h->wp2_hi, h->wp2_lo, nullptr, nullptr);
       }
       gather_features(h->stream, tb.d, h->g_rows, ni, WS(h, o.gX), SH(h, WS(h, o.gX)).hi, SH(h, WS(h, o.gX)).lo);
       gemm(h, true, true, ni, h->C, LRCN_F_CNN, WS(h, o.gX), LRCN_F_CNN, Wp(h, 6), LRCN_F_CNN, WS(h, o.gv), h->ldv, false, nullptr);  // lrcn.jl:611

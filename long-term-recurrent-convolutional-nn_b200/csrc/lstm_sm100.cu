@@ -892,8 +892,16 @@ constexpr int R_NT = NT;                // backward: 64 hidden units per cluster
 
 // forward operand: rows = gate columns n = g*H + j of the layer weight W [4H][ldw] (columns [x_off, x_off+H) = W_h),
 // permuted UNIT-major so that CTA nt's 64 rows are its 16 units x [f i o g]:  row jt*64 + u*4 + g  <-  n = g*H + jt*16 + u
-__global__ void permute_split_kernel(const float* __restrict__ W, int ldw, int x_off, int H, int Hp, __nv_bfloat16* __restrict__ hi,
-                                     __nv_bfloat16* __restrict__ lo) {
+struct PrepLayer { const float* W; int ldw, x_off, H; __nv_bfloat16 *p_hi, *p_lo, *t_hi, *t_lo; };
+struct PrepArgs { PrepLayer l[2]; };
+
+__global__ void permute_split_kernel(const PrepArgs a) {
+  const PrepLayer& L = a.l[blockIdx.y];
+  const float* __restrict__ W = L.W;
+  const int ldw = L.ldw, x_off = L.x_off, H = L.H, Hp = (L.H + 7) / 8 * 8;
+  __nv_bfloat16* __restrict__ hi = L.p_hi;
+  __nv_bfloat16* __restrict__ lo = L.p_lo;
+  if ((int)blockIdx.x >= (H + F_NH - 1) / F_NH * F_NT) return;
   const int row = blockIdx.x;
   const int jt = row / F_NT, r = row % F_NT, u = r / 4, g = r % 4;
   const int j = jt * F_NH + u;
@@ -907,8 +915,13 @@ __global__ void permute_split_kernel(const float* __restrict__ W, int ldw, int x
   }
 }
 // backward operand: WhT[j][n] = W[n][x_off + j]  ([Hr rows][4H], K-major over the gate columns n)
-__global__ void transpose_split_kernel(const float* __restrict__ W, int ldw, int x_off, int H, __nv_bfloat16* __restrict__ hi,
-                                       __nv_bfloat16* __restrict__ lo) {
+__global__ void transpose_split_kernel(const PrepArgs a) {
+  const PrepLayer& L = a.l[blockIdx.z];
+  const float* __restrict__ W = L.W;
+  const int ldw = L.ldw, x_off = L.x_off, H = L.H;
+  __nv_bfloat16* __restrict__ hi = L.t_hi;
+  __nv_bfloat16* __restrict__ lo = L.t_lo;
+  if (!hi || (int)blockIdx.x * 32 >= 4 * H || (int)blockIdx.y * 32 >= (H + 63) / 64 * 64) return;  // uniform per block
   __shared__ float tile[32][33];
   const int n0 = blockIdx.x * 32, j0 = blockIdx.y * 32;  // n over 4H, j over Hr
   for (int r = threadIdx.y; r < 32; r += 8) {
@@ -931,14 +944,18 @@ static int bwd_rows(int H) { return (H + 63) / 64 * 64; }
 size_t lstm_permuted_elems(int H) { return (size_t)fwd_rows(H) * ((H + 7) / 8 * 8); }
 size_t lstm_transposed_elems(int H) { return (size_t)bwd_rows(H) * 4 * H; }
 
-void lstm_prepare_weights(cudaStream_t s, const float* W, int ldw, int x_off, int H, __nv_bfloat16* perm_hi, __nv_bfloat16* perm_lo,
-                          __nv_bfloat16* tr_hi, __nv_bfloat16* tr_lo) {
-  const int Hp = (H + 7) / 8 * 8;
-  permute_split_kernel<<<fwd_rows(H), 128, 0, s>>>(W, ldw, x_off, H, Hp, perm_hi, perm_lo);
+// both layers in one launch each (perm_* for the forward step, tr_* (may be null) for the backward step)
+void lstm_prepare_weights2(cudaStream_t s, const float* W1, int ldw1, int x_off1, int H1, __nv_bfloat16* p1_hi, __nv_bfloat16* p1_lo,
+                           __nv_bfloat16* t1_hi, __nv_bfloat16* t1_lo, const float* W2, int ldw2, int x_off2, int H2, __nv_bfloat16* p2_hi,
+                           __nv_bfloat16* p2_lo, __nv_bfloat16* t2_hi, __nv_bfloat16* t2_lo) {
+  PrepArgs a;
+  a.l[0] = PrepLayer{W1, ldw1, x_off1, H1, p1_hi, p1_lo, t1_hi, t1_lo};
+  a.l[1] = PrepLayer{W2, ldw2, x_off2, H2, p2_hi, p2_lo, t2_hi, t2_lo};
+  const int Hm = H1 > H2 ? H1 : H2;
+  permute_split_kernel<<<dim3(fwd_rows(Hm), 2), 128, 0, s>>>(a);
   if (g_counter) g_counter->n++;
-  if (tr_hi) {
-    dim3 grid((4 * H + 31) / 32, bwd_rows(H) / 32);
-    transpose_split_kernel<<<grid, dim3(32, 8), 0, s>>>(W, ldw, x_off, H, tr_hi, tr_lo);
+  if (t1_hi || t2_hi) {
+    transpose_split_kernel<<<dim3((4 * Hm + 31) / 32, bwd_rows(Hm) / 32, 2), dim3(32, 8), 0, s>>>(a);
     if (g_counter) g_counter->n++;
   }
 }
@@ -1021,7 +1038,7 @@ bool lstm_fwd_seq(cudaStream_t s, int B, int H, int T, const __nv_bfloat16* wper
   if (!get_tensor_map_bf16(&ta_hi, hs_hi, H, R, H, LM / CL) || !get_tensor_map_bf16(&ta_lo, hs_lo, H, R, H, LM / CL)) return false;
   SeqParams p{};
   p.B = B; p.H = H; p.T = T; p.num_kb = num_kb; p.acts = acts; p.hs = hs; p.cs = cs; p.o_hi = hs_hi; p.o_lo = hs_lo; p.counters = counters; p.trace = trace;
-  cudaMemsetAsync(counters, 0, 64 * sizeof(unsigned int), s);
+  cudaMemsetAsync(counters, 0, 32 * sizeof(unsigned int), s);
   lstm_fwd_seq_kernel<<<grid, L_THREADS, seq_smem_bytes(num_kb, false), s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
   if (g_counter) g_counter->n++;
   *launched = true;
@@ -1045,7 +1062,7 @@ bool lstm_bwd_seq(cudaStream_t s, int B, int H, int T, const __nv_bfloat16* wt_h
   SeqParams p{};
   p.B = B; p.H = H; p.T = T; p.num_kb = num_kb; p.acts = acts; p.cs = cs; p.o_hi = acts_hi; p.o_lo = acts_lo; p.dh_all = dh_all; p.dc = dc;
   p.counters = counters;
-  cudaMemsetAsync(counters, 0, 64 * sizeof(unsigned int), s);
+  cudaMemsetAsync(counters, 0, 32 * sizeof(unsigned int), s);
   lstm_bwd_seq_kernel<<<grid, L_THREADS, seq_smem_bytes(kb_per, true), s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
   if (g_counter) g_counter->n++;
   *launched = true;
