@@ -155,36 +155,27 @@ def cpu_baseline_leg(w):
             "sample": f"{n} oracle train steps (numpy/OpenBLAS fp32) on {rows}-row slices of the workload's batches"}
 
 
-def beam_leg(local_rank, rank, world, prec, max_over_ranks, barrier, n_img=1024, K=3, nword=30):
+def beam_leg(local_rank, rank, world, prec, max_over_ranks, barrier, n_img=1024, K=3, nword=30, train_steps=300):
     """BASELINE.json configs[2]: COCO-shaped beam-search generation (E=H=512, V=10000, beam 3, nword 30), images sharded
-    across ranks with no collective.  eos is biased so decode lengths are COCO-like (~10 steps) instead of the 31 steps an
-    untrained model takes; reported as captions/s over fully decoded images, host buffers in and out (e2e by construction)."""
+    across ranks with no collective.  An untrained model never emits eos (31-step decodes), so the decoder is first trained
+    for `train_steps` steps on COCO-length synthetic captions: it learns the length statistics and decodes stop
+    like real captions do.  Reported as captions/s over fully decoded images; host ids in, host tokens out (e2e by construction)."""
     from lrcn_b200 import abi, synth
     E = H = 512
     V = 10000
-    cfg = abi.default_config(embed=E, hidden1=H, hidden2=H, vocab=V, max_batch=8, max_len=2, max_gen_rows=n_img * K, device=local_rank,
-                             precision=prec, use_graphs=0)
-    model = synth.initweights([H, H], V, E, seed=1)
+    Bt = 256
+    cfg = abi.default_config(embed=E, hidden1=H, hidden2=H, vocab=V, max_batch=Bt, max_len=28, max_gen_rows=n_img * K, device=local_rank,
+                             precision=prec, use_graphs=1)
     with abi.Handle(cfg) as g:
-        g.set_model(model)
-        ids = np.arange(1, n_img + 1, dtype=np.int64) + 100000 * rank
-        g.load_features(1, ids, synth.features(n_img, seed=6 + rank))
-        # untrained weights never emit eos (31-step decodes); bisect an eos bias so that the mean decode length is COCO-like
-        # (10.4 steps, SURVEY §8d).  Deterministic: same seeds -> same bias on every rank.
-        lo_b, hi_b = -2.0, 14.0
-        for _ in range(16):
-            mid = 0.5 * (lo_b + hi_b)
-            bout = model[8].copy()
-            bout[0, 0] = mid
-            g.set_param(9, bout)
-            _, lens, _, _ = g.beam_search(1, ids[:128], K, nword, want_logps=False)
-            if lens.mean() - 1 > 10.4:
-                lo_b = mid
-            else:
-                hi_b = mid
-        bout = model[8].copy()
-        bout[0, 0] = lo_b  # the side whose mean decode length is >= 10.4 steps
-        g.set_param(9, bout)
+        g.set_model(synth.initweights([H, H], V, E, seed=1))
+        ids = np.arange(1, n_img + 1, dtype=np.int64)
+        feats = synth.features(n_img, seed=6 + rank)
+        g.load_features(0, ids, feats)
+        g.load_features(1, ids, feats)
+        ls = synth.lengths(train_steps, "coco", seed=11)
+        for i in range(train_steps):   # same seeds on every rank -> identical replicas, no collective needed
+            l = int(ls[i])
+            g.train_step(0, synth.image_ids(Bt, n_img, seed=100 + i), synth.tokens(l, Bt, V, seed=200 + i, zipf=True), 0.0, i)
         g.beam_search(1, ids, K, nword, want_logps=False)  # warm-up
         barrier()
         t0 = time.perf_counter()
@@ -197,6 +188,7 @@ def beam_leg(local_rank, rank, world, prec, max_over_ranks, barrier, n_img=1024,
         dt = max_over_ranks(time.perf_counter() - t0)
     return {"metric": "beam-3 captions/s", "value": reps * n_img * world / dt, "unit": "captions/s", "images_per_gpu": n_img, "beam_width": K,
             "nword": nword, "vocab": V, "mean_len": float(lens.mean() - 1), "max_steps": steps / reps, "ms_per_batch": 1e3 * dt / reps,
+            "model": f"trained {train_steps} steps on COCO-length synthetic captions so decodes terminate",
             "timing": "wall clock around lrcn_beam_search (host ids in, host tokens out), max over ranks"}
 
 

@@ -408,9 +408,11 @@ bool gemm_bf16x3(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int
   }
   const int kb_per = (num_kb + splits - 1) / splits;
   splits = (num_kb + kb_per - 1) / kb_per;
-  // cluster of 2 M-adjacent tiles sharing (multicasting) the B tile whenever there are enough tile pairs to fill the SMs
-  int cm = (tm >= 2 && ((tm + 1) / 2) * tn * splits * 2 >= g_num_sms) ? 2 : 1;
-  if (g_force_cm == 1 || g_force_cm == 2) cm = (tm >= 2) ? g_force_cm : 1;
+  // optional cluster of 2 M-adjacent tiles sharing (multicasting) the B tile
+  // Measured on B200 (profiles/r01_progress.md): the multicast does NOT speed these GEMMs up -- they are bound by the bytes each
+  // SM can keep in flight (smem capacity / L2 latency), not by L2 read bandwidth -- so it is off unless LRCN_GEMM_CM=2 asks for it.
+  int cm = 1;
+  if (g_force_cm == 2 && tm >= 2) cm = 2;
 
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   bool ok = true;
