@@ -351,7 +351,7 @@ static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
 }
-static int g_num_sms = 148, g_force_bn = 0, g_force_cm = 0;
+static int g_num_sms = 148, g_force_bn = 0, g_force_cm = 0, g_two_cta = 1;
 
 template <bool AK, bool BKM, int BN_>
 static cudaError_t set_attr() {
@@ -375,6 +375,8 @@ bool init_gemm_sm100() {
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   g_force_bn = env_int("LRCN_GEMM_BN", 0);
   g_force_cm = env_int("LRCN_GEMM_CM", 0);
+  g_two_cta = env_int("LRCN_GEMM_2CTA", 1);
+  if (g_two_cta && !init_gemm2_sm100()) return false;
   return true;
 }
 
@@ -390,6 +392,9 @@ bool gemm_bf16x3(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int
                  __nv_bfloat16* C_hi, __nv_bfloat16* C_lo) {
   if (M <= 0 || N <= 0 || K <= 0) return true;
   const int tm = (M + BM - 1) / BM;
+  // CTA-pair kernel (256 x 256 UMMA, half the B bytes per SM) whenever the output is wide enough to fill the pair tiles
+  if (g_two_cta && g_force_bn == 0 && tm >= 2 && N >= 192 && ((tm + 1) / 2) * ((N + 255) / 256) * 2 >= g_num_sms / 2)
+    return gemm2_bf16x3(s, a_kmajor, b_kmajor, M, N, K, A_hi, A_lo, lda, B_hi, B_lo, ldb, C, ldc, beta, bias, C_hi, C_lo);
   // BN = 256 halves the smem operand traffic per MMA (128x128 SS-mode MMAs sit right at the 128 B/clk smem limit);
   // use it when there is enough N to keep every SM busy
   int bn = (N >= 512 && tm * ((N + 255) / 256) >= g_num_sms) ? 256 : 128;

@@ -94,6 +94,11 @@ bool gemm_bf16x3(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int
                  __nv_bfloat16* C_hi, __nv_bfloat16* C_lo /* optional split of the result, same ldc */);
 const char* gemm_bf16x3_last_error();
 bool init_gemm_sm100();   // func attributes + driver entry point; call once outside any capture
+bool init_gemm2_sm100();
+// 2-CTA (cta_group::2) 256x256 pair-tile variant, same contract (gemm2_sm100.cu); gemm_bf16x3 dispatches to it
+bool gemm2_bf16x3(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo,
+                  int lda, const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, int ldb, float* C, int ldc, bool beta, const float* bias,
+                  __nv_bfloat16* C_hi, __nv_bfloat16* C_lo);
 void init_simt_kernels();
 
 // ---------------------------------------------------------------- fused LSTM timestep (lstm_sm100.cu)

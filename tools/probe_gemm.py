@@ -37,16 +37,18 @@ if __name__ == "__main__":
         one(*a)
         sys.exit(0)
     shapes = [(128, 128, 64), (128, 128, 256), (256, 384, 512), (200, 136, 520), (64, 2048, 512), (1344, 8000, 512), (1000, 500, 7731)]
-    envs = [{"LRCN_GEMM_BN": "128"}, {"LRCN_GEMM_BN": "256"}]
+    envs = [{"LRCN_GEMM_2CTA": "0", "LRCN_GEMM_BN": "128"}, {"LRCN_GEMM_2CTA": "0", "LRCN_GEMM_BN": "256"}, {"LRCN_GEMM_2CTA": "1"}]
+    if "--2cta" in sys.argv:
+        envs = [{"LRCN_GEMM_2CTA": "1"}]
     if "--quick" in sys.argv:
-        shapes = [(200, 136, 520), (1344, 8000, 512), (1000, 500, 7731)]
+        shapes = [(200, 136, 520), (1344, 8000, 512), (1000, 500, 7731), (3328, 2048, 512), (257, 300, 64)]
     for env in envs:
         print("== env", env, flush=True)
         for prec in (0, 1):
             for (M, N, K) in shapes:
                 for aK in (1, 0):
                     for bK in (1, 0):
-                        if prec == 0 and env.get("LRCN_GEMM_BN") == "256":
+                        if prec == 0 and env.get("LRCN_GEMM_BN") != "128":
                             continue
                         e = dict(os.environ)
                         e.update(env)
