@@ -42,7 +42,8 @@ void gather_embed(cudaStream_t s, const float* WembT, const int* tok, int R, int
 void z_finish(cudaStream_t s, float* Z, const float* v, int ldv, int R, int B, int C, const StepScalars* sc, bool train,
               __nv_bfloat16* hi = nullptr, __nv_bfloat16* lo = nullptr);
 // LSTM cell forward for one step: gates (pre-activation, [B][4H], order f,i,o,g) are activated in place
-void lstm_cell_fwd(cudaStream_t s, float* gates, const float* c_prev, float* c_out, float* h_out, int B, int H);
+void lstm_cell_fwd(cudaStream_t s, float* gates, const float* c_prev, float* c_out, float* h_out, int B, int H,
+                   __nv_bfloat16* h_hi = nullptr, __nv_bfloat16* h_lo = nullptr);
 // LSTM cell backward for one step; gates buffer holds activations and receives dG in place
 void lstm_cell_bwd(cudaStream_t s, float* gates, const float* c_prev, const float* c_cur, const float* dh_in,
                    const float* dh_rec /*nullable*/, float* dc /*in/out*/, bool first /*dc,dh_rec are zero*/,
@@ -80,6 +81,7 @@ struct BeamAdvanceArgs {
   const int* sel_tok; const int* sel_parent; const float* sel_score; const float* sel_lp;
   const float *h1_in, *c1_in, *h2_in, *c2_in; float *h1_out, *c1_out, *h2_out, *c2_out;
   const int* hist_in; int* hist_out; const float* lp_in; float* lp_out;
+  __nv_bfloat16 *h1_hi, *h1_lo, *h2_hi, *h2_lo;  // optional bf16 split of the gathered h states (null in fp32 mode)
   float* prob; int* last_tok; int* done; int* n_done;
   long long* out_tokens; int* out_len; float* out_prob; float* out_lp;
 };

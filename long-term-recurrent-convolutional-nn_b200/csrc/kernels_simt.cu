@@ -25,6 +25,17 @@ __device__ __forceinline__ float drop_scale(const StepScalars* sc, uint32_t site
   return drop_hash24(sc->seed, site, idx) >= sc->drop_thresh ? sc->keep_scale : 0.0f;
 }
 
+__device__ __forceinline__ void split_one(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+__device__ __forceinline__ void store_split4(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t idx, float4 x) {
+  __nv_bfloat16 h[4], l[4];
+  split_one(x.x, h[0], l[0]); split_one(x.y, h[1], l[1]); split_one(x.z, h[2], l[2]); split_one(x.w, h[3], l[3]);
+  *reinterpret_cast<uint2*>(hi + idx) = *reinterpret_cast<uint2*>(h);
+  *reinterpret_cast<uint2*>(lo + idx) = *reinterpret_cast<uint2*>(l);
+}
+
 // ------------------------------------------------------------------------------------------
 // fp32 GEMM, 64x64x32 tiles, 256 threads, 4x4 micro-tile, register-prefetched k-tiles, split-K
 // ------------------------------------------------------------------------------------------
@@ -152,17 +163,6 @@ void sgemm(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int K, co
 // ------------------------------------------------------------------------------------------
 // gathers
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void split_one(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(x);
-  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-}
-__device__ __forceinline__ void store_split4(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t idx, float4 x) {
-  __nv_bfloat16 h[4], l[4];
-  split_one(x.x, h[0], l[0]); split_one(x.y, h[1], l[1]); split_one(x.z, h[2], l[2]); split_one(x.w, h[3], l[3]);
-  *reinterpret_cast<uint2*>(hi + idx) = *reinterpret_cast<uint2*>(h);
-  *reinterpret_cast<uint2*>(lo + idx) = *reinterpret_cast<uint2*>(l);
-}
-
 __global__ void gather_features_kernel(const float4* __restrict__ table, const int* __restrict__ rows, float4* __restrict__ X,
                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   int i = blockIdx.x;
@@ -222,7 +222,8 @@ void z_finish(cudaStream_t s, float* Z, const float* v, int ldv, int R, int B, i
 __device__ __forceinline__ float sigm_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __global__ void lstm_cell_fwd_kernel(float* __restrict__ gates, const float* __restrict__ c_prev, float* __restrict__ c_out,
-                                     float* __restrict__ h_out, int B, int H) {
+                                     float* __restrict__ h_out, int B, int H, __nv_bfloat16* __restrict__ h_hi,
+                                     __nv_bfloat16* __restrict__ h_lo) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * H) return;
   int i = idx / H, j = idx - i * H;
@@ -231,11 +232,14 @@ __global__ void lstm_cell_fwd_kernel(float* __restrict__ gates, const float* __r
   float c = c_prev[idx] * f + in * ch;
   g[j] = f; g[H + j] = in; g[2 * H + j] = o; g[3 * H + j] = ch;
   c_out[idx] = c;
-  h_out[idx] = o * tanhf(c);
+  const float hv = o * tanhf(c);
+  h_out[idx] = hv;
+  if (h_hi) { __nv_bfloat16 hh, ll; split_one(hv, hh, ll); h_hi[idx] = hh; h_lo[idx] = ll; }
 }
-void lstm_cell_fwd(cudaStream_t s, float* gates, const float* c_prev, float* c_out, float* h_out, int B, int H) {
+void lstm_cell_fwd(cudaStream_t s, float* gates, const float* c_prev, float* c_out, float* h_out, int B, int H, __nv_bfloat16* h_hi,
+                   __nv_bfloat16* h_lo) {
   int n = B * H;
-  lstm_cell_fwd_kernel<<<(n + 255) / 256, 256, 0, s>>>(gates, c_prev, c_out, h_out, B, H);
+  lstm_cell_fwd_kernel<<<(n + 255) / 256, 256, 0, s>>>(gates, c_prev, c_out, h_out, B, H, h_hi, h_lo);
   count_launch();
 }
 
@@ -601,52 +605,99 @@ __device__ __forceinline__ BestPair block_argmax(BestPair p, BestPair* red) {
   return q;
 }
 
+constexpr int TOPK_MAX = 11;
+// per row: probabilities ynorm = exp(logp(ypred,2)) (fp32, lrcn.jl:652-654) and the K largest by (prob desc, index asc)
+// (lrcn.jl:655-656: sortperm(rev=true) breaks ties by index).  Each thread keeps the top K of its strided slice in registers
+// while it computes the probabilities; warps merge by K rounds of shuffle-argmax, warp 0 merges the warp winners.
 template <bool FROM_LOGITS>
-__global__ void __launch_bounds__(256) beam_row_topk_kernel(const float* __restrict__ in, int ld, int V, int K,
+__global__ void __launch_bounds__(512) beam_row_topk_kernel(const float* __restrict__ in, int ld, int V, int K,
                                                             const float* __restrict__ parent_prob, int* __restrict__ cand_tok,
                                                             float* __restrict__ cand_score, float* __restrict__ cand_lp) {
-  extern __shared__ float row[];  // V probabilities
+  extern __shared__ __align__(16) float row[];  // V values (logits, only when FROM_LOGITS)
   __shared__ float red[32];
-  __shared__ BestPair bred[32];
-  int r = blockIdx.x;
+  __shared__ float wv[16][TOPK_MAX];
+  __shared__ int wi[16][TOPK_MAX];
+  const int r = blockIdx.x;
   const float* a = in + (size_t)r * ld;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   float lse = 0.f, mx = 0.f;
   if (FROM_LOGITS) {
     mx = -INFINITY;
-    for (int j = threadIdx.x; j < V; j += blockDim.x) { float x = a[j]; row[j] = x; mx = fmaxf(mx, x); }
+    const int V4 = V >> 2;
+    for (int q = threadIdx.x; q < V4; q += blockDim.x) {
+      const float4 x = *reinterpret_cast<const float4*>(a + 4 * q);
+      *reinterpret_cast<float4*>(row + 4 * q) = x;
+      mx = fmaxf(fmaxf(mx, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
+    }
+    for (int j = 4 * V4 + threadIdx.x; j < V; j += blockDim.x) { const float x = a[j]; row[j] = x; mx = fmaxf(mx, x); }
     mx = block_max(mx, red);
     float sum = 0.f;
     for (int j = threadIdx.x; j < V; j += blockDim.x) sum += expf(row[j] - mx);
     sum = block_sum(sum, red);
     lse = logf(sum);
-    for (int j = threadIdx.x; j < V; j += blockDim.x) row[j] = expf((row[j] - mx) - lse);  // ynorm = exp(logp(ypred,2))
-  } else {
-    for (int j = threadIdx.x; j < V; j += blockDim.x) row[j] = a[j];
+  }
+  // local top-K (sorted descending by (value, -index))
+  float tv[TOPK_MAX];
+  int ti[TOPK_MAX];
+#pragma unroll
+  for (int k = 0; k < TOPK_MAX; k++) { tv[k] = -2.f; ti[k] = 0x7fffffff; }
+  float kth_v = -2.f;  // current K-th best of this thread (kept in scalars: no dynamic register-array indexing)
+  int kth_i = 0x7fffffff;
+  for (int j = threadIdx.x; j < V; j += blockDim.x) {
+    const float pj = FROM_LOGITS ? expf((row[j] - mx) - lse) : a[j];
+    if (pj > kth_v || (pj == kth_v && j < kth_i)) {
+      float cv = pj; int ci = j;  // insert, keeping order
+#pragma unroll
+      for (int k = 0; k < TOPK_MAX; k++) {
+        if (k < K && (cv > tv[k] || (cv == tv[k] && ci < ti[k]))) { const float fv = tv[k]; const int fi = ti[k]; tv[k] = cv; ti[k] = ci; cv = fv; ci = fi; }
+        if (k == K - 1) { kth_v = tv[k]; kth_i = ti[k]; }
+      }
+    }
+  }
+  // warp merge: K rounds; each lane offers its current head
+  int head = 0;
+  for (int k = 0; k < K; k++) {
+    float hv = -2.f; int hi_ = 0x7fffffff;
+#pragma unroll
+    for (int q = 0; q < TOPK_MAX; q++) if (q == head) { hv = tv[q]; hi_ = ti[q]; }
+    float bv = hv; int bi = hi_;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (bi == hi_ && bv == hv) head++;  // my head won (indices are unique per row)
+    if (lane == 0) { wv[warp][k] = bv; wi[warp][k] = bi; }
   }
   __syncthreads();
-  float pp = parent_prob[r];
-  for (int k = 0; k < K; k++) {
-    BestPair p;
-    p.v = -2.f; p.i = 0x7fffffff;
-    for (int j = threadIdx.x; j < V; j += blockDim.x) {
-      BestPair q; q.v = row[j]; q.i = j;
-      p = better(p, q);
+  if (warp == 0) {
+    int whead = 0;  // lane w < nwarps walks warp w's sorted list
+    const float pp = parent_prob[r];
+    for (int k = 0; k < K; k++) {
+      float hv = -2.f; int hi_ = 0x7fffffff;
+      if (lane < nwarps && whead < K) { hv = wv[lane][whead]; hi_ = wi[lane][whead]; }
+      float bv = hv; int bi = hi_;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (bi == hi_ && bv == hv) whead++;
+      if (lane == 0) {
+        cand_tok[(size_t)r * K + k] = bi;
+        cand_score[(size_t)r * K + k] = __fmul_rn(bv, pp);  // pmaxes = ynorm[xmaxes]*current_probability (lrcn.jl:657)
+        cand_lp[(size_t)r * K + k] = FROM_LOGITS ? ((row[bi] - mx) - lse) : logf(bv);
+      }
     }
-    p = block_argmax(p, bred);
-    if (threadIdx.x == 0) {
-      cand_tok[(size_t)r * K + k] = p.i;
-      cand_score[(size_t)r * K + k] = __fmul_rn(p.v, pp);  // pmaxes = ynorm[xmaxes]*current_probability
-      cand_lp[(size_t)r * K + k] = FROM_LOGITS ? ((a[p.i] - mx) - lse) : logf(p.v);
-      row[p.i] = -1.f;  // exclude from later rounds
-    }
-    __syncthreads();
   }
 }
 static void beam_topk_launch(cudaStream_t s, bool from_logits, const float* in, int ld, int R, int V, int K,
                              const float* parent_prob, int* cand_tok, float* cand_score, float* cand_lp) {
-  size_t smem = (size_t)V * sizeof(float);
-  if (from_logits) beam_row_topk_kernel<true><<<R, 256, smem, s>>>(in, ld, V, K, parent_prob, cand_tok, cand_score, cand_lp);
-  else beam_row_topk_kernel<false><<<R, 256, smem, s>>>(in, ld, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+  size_t smem = from_logits ? ((size_t)V + 4) * sizeof(float) : 16;
+  if (from_logits) beam_row_topk_kernel<true><<<R, 512, smem, s>>>(in, ld, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+  else beam_row_topk_kernel<false><<<R, 512, smem, s>>>(in, ld, V, K, parent_prob, cand_tok, cand_score, cand_lp);
   count_launch();
 }
 void beam_row_topk(cudaStream_t s, const float* logits, int ld, int R, int V, int K, const float* parent_prob, int* cand_tok,
@@ -699,12 +750,16 @@ __global__ void __launch_bounds__(128) beam_advance_kernel(BeamAdvanceArgs a) {
   if (a.done[img]) return;
   int parent = img * a.K + a.sel_parent[r];
   for (int j = threadIdx.x; j < a.H1; j += blockDim.x) {
-    a.h1_out[(size_t)r * a.H1 + j] = a.h1_in[(size_t)parent * a.H1 + j];
+    const float hv = a.h1_in[(size_t)parent * a.H1 + j];
+    a.h1_out[(size_t)r * a.H1 + j] = hv;
     a.c1_out[(size_t)r * a.H1 + j] = a.c1_in[(size_t)parent * a.H1 + j];
+    if (a.h1_hi) { __nv_bfloat16 hh, ll; split_one(hv, hh, ll); a.h1_hi[(size_t)r * a.H1 + j] = hh; a.h1_lo[(size_t)r * a.H1 + j] = ll; }
   }
   for (int j = threadIdx.x; j < a.H2; j += blockDim.x) {
-    a.h2_out[(size_t)r * a.H2 + j] = a.h2_in[(size_t)parent * a.H2 + j];
+    const float hv = a.h2_in[(size_t)parent * a.H2 + j];
+    a.h2_out[(size_t)r * a.H2 + j] = hv;
     a.c2_out[(size_t)r * a.H2 + j] = a.c2_in[(size_t)parent * a.H2 + j];
+    if (a.h2_hi) { __nv_bfloat16 hh, ll; split_one(hv, hh, ll); a.h2_hi[(size_t)r * a.H2 + j] = hh; a.h2_lo[(size_t)r * a.H2 + j] = ll; }
   }
   // history so far has a.step tokens (bos + step-1 generated); append one
   int len = a.step;

@@ -838,6 +838,12 @@ extern "C" int lrcn_train_step_staged(lrcn_handle* h, int slot, float pdrop, uin
 static void beam_lstm_step(lrcn_handle* h, int layer, int step, int R, float* g, float* h_in, float* c_in, float* h_out, float* c_out) {
   const int H = layer == 1 ? h->H1 : h->H2;
   const int ldw = layer == 1 ? h->E + h->H1 : 2 * h->H2, x_off = layer == 1 ? h->E : 2 * h->C;
+  if (h->bf16mode && R > 512) {
+    // many rows: throughput matters more than latency -> pair-tile GEMM for the recurrent part + one elementwise cell kernel
+    if (step > 1) gemm(h, true, true, R, 4 * H, H, h_in, H, Wp(h, layer == 1 ? 1 : 3) + x_off, ldw, g, 4 * H, true, nullptr);
+    lstm_cell_fwd(h->stream, g, c_in, c_out, h_out, R, H, SH(h, h_out).hi, SH(h, h_out).lo);
+    return;
+  }
   if (h->bf16mode) {
     bf16 *hi_hi, *hi_lo, *ho_hi, *ho_lo;
     shadow(h, h_in, &hi_hi, &hi_lo);
@@ -874,11 +880,10 @@ static void enqueue_beam_step(lrcn_handle* h, int n_img, int K, int step, int nw
   a.h1_in = h1b; a.c1_in = c1b; a.h2_in = h2b; a.c2_in = c2b; a.h1_out = h1a; a.c1_out = c1a; a.h2_out = h2a; a.c2_out = c2a;
   a.hist_in = flip ? h->g_histb : h->g_hista; a.hist_out = flip ? h->g_hista : h->g_histb;
   a.lp_in = flip ? WS(h, o.glpb) : WS(h, o.glpa); a.lp_out = flip ? WS(h, o.glpa) : WS(h, o.glpb);
+  a.h1_hi = SH(h, h1a).hi; a.h1_lo = SH(h, h1a).lo; a.h2_hi = SH(h, h2a).hi; a.h2_lo = SH(h, h2a).lo;
   a.prob = WS(h, o.gprob); a.last_tok = h->g_last; a.done = h->g_done; a.n_done = h->g_ndone;
   a.out_tokens = h->g_otok; a.out_len = h->g_olen; a.out_prob = WS(h, o.goprob); a.out_lp = out_lp;
-  beam_advance(s, a);                                                                                         // lrcn.jl:670-677
-  split_ws(h, h1a, (size_t)R * H1);  // the gathered parent states feed the next step's recurrent GEMMs
-  split_ws(h, h2a, (size_t)R * H2);
+  beam_advance(s, a);  // reorder/gather parent states (+ their bf16 split for the next recurrent GEMMs)                 lrcn.jl:670-677
 }
 
 __global__ void beam_init_kernel(int R, int maxlen, float* prob, int* last, int* hist, float* lp, int* done, int* n_done, int n_img) {
@@ -935,9 +940,11 @@ extern "C" int lrcn_beam_search(lrcn_handle* h, int split, const int64_t* image_
       for (int step = 1; step <= nword + 1; step++) {
         enqueue_beam_step(h, ni, K, step, nword, maxlen, flip, logp_out ? WS(h, o.golp) : nullptr);
         flip = !flip;
-        CK(cudaMemcpyAsync(h->h_ndone, h->g_ndone, 4, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        if (*h->h_ndone >= ni) break;
+        if ((step & 3) == 0 || step == nword + 1) {  // finished images are frozen on the device; poll the host only every 4 steps
+          CK(cudaMemcpyAsync(h->h_ndone, h->g_ndone, 4, cudaMemcpyDeviceToHost, h->stream));
+          CK(cudaStreamSynchronize(h->stream));
+          if (*h->h_ndone >= ni) break;
+        }
       }
     } catch (GemmFail& f) {
       return fail(LRCN_ERR_CUDA, "%s", f.msg.c_str());
