@@ -607,13 +607,18 @@ __device__ __forceinline__ BestPair block_argmax(BestPair p, BestPair* red) {
 
 constexpr int TOPK_MAX = 11;
 // per row: probabilities ynorm = exp(logp(ypred,2)) (fp32, lrcn.jl:652-654) and the K largest by (prob desc, index asc)
-// (lrcn.jl:655-656: sortperm(rev=true) breaks ties by index).  Each thread keeps the top K of its strided slice in registers
-// while it computes the probabilities; warps merge by K rounds of shuffle-argmax, warp 0 merges the warp winners.
-template <bool FROM_LOGITS>
+// (lrcn.jl:655-656: sortperm(rev=true) breaks ties by index).
+//  * the row is staged once in shared memory (one HBM/L2 read);
+//  * the normaliser uses __expf (its ~1e-7 relative error shifts every probability of the row alike, so no ordering changes);
+//  * a thread only evaluates the precise expf for elements whose LOGIT reaches its current K-th best (exp is monotone), so
+//    the expensive per-element work is O(K log V) instead of O(V);
+//  * each thread keeps its top KT >= K in registers (KT is a template parameter: no dynamic register indexing); warps merge
+//    by K rounds of shuffle-argmax, warp 0 merges the warp winners.
+template <bool FROM_LOGITS, int KT>
 __global__ void __launch_bounds__(512) beam_row_topk_kernel(const float* __restrict__ in, int ld, int V, int K,
                                                             const float* __restrict__ parent_prob, int* __restrict__ cand_tok,
                                                             float* __restrict__ cand_score, float* __restrict__ cand_lp) {
-  extern __shared__ __align__(16) float row[];  // V values (logits, only when FROM_LOGITS)
+  extern __shared__ __align__(16) float row[];  // V logits (only when FROM_LOGITS)
   __shared__ float red[32];
   __shared__ float wv[16][TOPK_MAX];
   __shared__ int wi[16][TOPK_MAX];
@@ -632,34 +637,32 @@ __global__ void __launch_bounds__(512) beam_row_topk_kernel(const float* __restr
     for (int j = 4 * V4 + threadIdx.x; j < V; j += blockDim.x) { const float x = a[j]; row[j] = x; mx = fmaxf(mx, x); }
     mx = block_max(mx, red);
     float sum = 0.f;
-    for (int j = threadIdx.x; j < V; j += blockDim.x) sum += expf(row[j] - mx);
+    for (int j = threadIdx.x; j < V; j += blockDim.x) sum += __expf(row[j] - mx);
     sum = block_sum(sum, red);
     lse = logf(sum);
   }
-  // local top-K (sorted descending by (value, -index))
-  float tv[TOPK_MAX];
-  int ti[TOPK_MAX];
+  float tv[KT], tx[KT];  // probability and (FROM_LOGITS) logit of the kept entries, sorted by (prob desc, index asc)
+  int ti[KT];
 #pragma unroll
-  for (int k = 0; k < TOPK_MAX; k++) { tv[k] = -2.f; ti[k] = 0x7fffffff; }
-  float kth_v = -2.f;  // current K-th best of this thread (kept in scalars: no dynamic register-array indexing)
-  int kth_i = 0x7fffffff;
+  for (int k = 0; k < KT; k++) { tv[k] = -2.f; tx[k] = -INFINITY; ti[k] = 0x7fffffff; }
   for (int j = threadIdx.x; j < V; j += blockDim.x) {
-    const float pj = FROM_LOGITS ? expf((row[j] - mx) - lse) : a[j];
-    if (pj > kth_v || (pj == kth_v && j < kth_i)) {
-      float cv = pj; int ci = j;  // insert, keeping order
+    const float xj = FROM_LOGITS ? row[j] : a[j];
+    if (FROM_LOGITS ? (xj < tx[KT - 1]) : (xj < tv[KT - 1])) continue;  // cannot enter this thread's top KT
+    const float pj = FROM_LOGITS ? expf((xj - mx) - lse) : xj;
+    float cv = pj, cx = xj; int ci = j;
 #pragma unroll
-      for (int k = 0; k < TOPK_MAX; k++) {
-        if (k < K && (cv > tv[k] || (cv == tv[k] && ci < ti[k]))) { const float fv = tv[k]; const int fi = ti[k]; tv[k] = cv; ti[k] = ci; cv = fv; ci = fi; }
-        if (k == K - 1) { kth_v = tv[k]; kth_i = ti[k]; }
+    for (int k = 0; k < KT; k++) {
+      if (cv > tv[k] || (cv == tv[k] && ci < ti[k])) {
+        const float fv = tv[k], fx = tx[k]; const int fi = ti[k];
+        tv[k] = cv; tx[k] = cx; ti[k] = ci; cv = fv; cx = fx; ci = fi;
       }
     }
   }
-  // warp merge: K rounds; each lane offers its current head
   int head = 0;
   for (int k = 0; k < K; k++) {
     float hv = -2.f; int hi_ = 0x7fffffff;
 #pragma unroll
-    for (int q = 0; q < TOPK_MAX; q++) if (q == head) { hv = tv[q]; hi_ = ti[q]; }
+    for (int q = 0; q < KT; q++) if (q == head) { hv = tv[q]; hi_ = ti[q]; }
     float bv = hv; int bi = hi_;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -672,7 +675,7 @@ __global__ void __launch_bounds__(512) beam_row_topk_kernel(const float* __restr
   }
   __syncthreads();
   if (warp == 0) {
-    int whead = 0;  // lane w < nwarps walks warp w's sorted list
+    int whead = 0;
     const float pp = parent_prob[r];
     for (int k = 0; k < K; k++) {
       float hv = -2.f; int hi_ = 0x7fffffff;
@@ -693,11 +696,19 @@ __global__ void __launch_bounds__(512) beam_row_topk_kernel(const float* __restr
     }
   }
 }
+template <bool FL>
+static void beam_topk_dispatch(cudaStream_t s, size_t smem, const float* in, int ld, int R, int V, int K, const float* parent_prob, int* cand_tok,
+                               float* cand_score, float* cand_lp) {
+  if (K <= 1) beam_row_topk_kernel<FL, 1><<<R, 512, smem, s>>>(in, ld, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+  else if (K <= 3) beam_row_topk_kernel<FL, 3><<<R, 512, smem, s>>>(in, ld, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+  else if (K <= 5) beam_row_topk_kernel<FL, 5><<<R, 512, smem, s>>>(in, ld, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+  else beam_row_topk_kernel<FL, TOPK_MAX><<<R, 512, smem, s>>>(in, ld, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+}
 static void beam_topk_launch(cudaStream_t s, bool from_logits, const float* in, int ld, int R, int V, int K,
                              const float* parent_prob, int* cand_tok, float* cand_score, float* cand_lp) {
   size_t smem = from_logits ? ((size_t)V + 4) * sizeof(float) : 16;
-  if (from_logits) beam_row_topk_kernel<true><<<R, 512, smem, s>>>(in, ld, V, K, parent_prob, cand_tok, cand_score, cand_lp);
-  else beam_row_topk_kernel<false><<<R, 512, smem, s>>>(in, ld, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+  if (from_logits) beam_topk_dispatch<true>(s, smem, in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+  else beam_topk_dispatch<false>(s, smem, in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
   count_launch();
 }
 void beam_row_topk(cudaStream_t s, const float* logits, int ld, int R, int V, int K, const float* parent_prob, int* cand_tok,
@@ -811,8 +822,10 @@ void beam_advance(cudaStream_t s, const BeamAdvanceArgs& a) {
 // called once per process from lrcn_create (never inside a stream capture)
 void init_simt_kernels() {
   cudaFuncSetAttribute(softmax_ce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(beam_row_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(beam_row_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(beam_row_topk_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(beam_row_topk_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(beam_row_topk_kernel<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(beam_row_topk_kernel<true, TOPK_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
 }  // namespace lrcn
