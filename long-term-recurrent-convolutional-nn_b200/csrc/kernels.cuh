@@ -37,10 +37,11 @@ void gather_features(cudaStream_t s, const float* table, const int* rows, int B,
                      __nv_bfloat16* lo = nullptr);  // hi/lo: optional bf16 split of the output, same indexing
 // E_all[r][:] = WembT[tok[r]][:] (* dropout mask site 0);  tok 0-based
 void gather_embed(cudaStream_t s, const float* WembT, const int* tok, int R, int E, float* out,
-                  const StepScalars* sc, bool train, __nv_bfloat16* hi = nullptr, __nv_bfloat16* lo = nullptr);
+                  const StepScalars* sc, bool train, __nv_bfloat16* hi = nullptr, __nv_bfloat16* lo = nullptr,
+                  int ld_out = 0 /* row pitch of out (0 = E) */);
 // Z[r][C+j] = v[r % B][j]; then dropout (site 1) over the whole row of 2C
 void z_finish(cudaStream_t s, float* Z, const float* v, int ldv, int R, int B, int C, const StepScalars* sc, bool train,
-              __nv_bfloat16* hi = nullptr, __nv_bfloat16* lo = nullptr);
+              __nv_bfloat16* hi = nullptr, __nv_bfloat16* lo = nullptr, int ldz = 0 /* row pitch of Z (0 = 2C) */);
 // LSTM cell forward for one step: gates (pre-activation, [B][4H], order f,i,o,g) are activated in place
 void lstm_cell_fwd(cudaStream_t s, float* gates, const float* c_prev, float* c_out, float* h_out, int B, int H,
                    __nv_bfloat16* h_hi = nullptr, __nv_bfloat16* h_lo = nullptr);
@@ -78,6 +79,7 @@ void beam_select(cudaStream_t s, const int* cand_tok, const float* cand_score, c
                  int first_step, int* sel_tok, int* sel_parent, float* sel_score, float* sel_lp);
 struct BeamAdvanceArgs {
   int n_img, K, H1, H2, maxlen, step, nword;
+  int ld1, ld2;  // row pitch of h1_out / h2_out (they are the h-columns of the [x|h] GEMM operand buffers)
   const int* sel_tok; const int* sel_parent; const float* sel_score; const float* sel_lp;
   const float *h1_in, *c1_in, *h2_in, *c2_in; float *h1_out, *c1_out, *h2_out, *c2_out;
   const int* hist_in; int* hist_out; const float* lp_in; float* lp_out;

@@ -179,40 +179,40 @@ void gather_features(cudaStream_t s, const float* table, const int* rows, int B,
   count_launch();
 }
 
-__global__ void gather_embed_kernel(const float* __restrict__ W, const int* __restrict__ tok, int R, int E,
+__global__ void gather_embed_kernel(const float* __restrict__ W, const int* __restrict__ tok, int R, int E, int ldo,
                                     float* __restrict__ out, const StepScalars* __restrict__ sc, int train,
                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   int r = blockIdx.x;
   const float* src = W + (size_t)tok[r] * E;
-  float* dst = out + (size_t)r * E;
+  float* dst = out + (size_t)r * ldo;
   for (int e = threadIdx.x; e < E; e += blockDim.x) {
     float v = __ldg(src + e);
     if (train) v *= drop_scale(sc, 0, (uint64_t)r * E + e);
     dst[e] = v;
-    if (hi) { __nv_bfloat16 h, l; split_one(v, h, l); hi[(size_t)r * E + e] = h; lo[(size_t)r * E + e] = l; }
+    if (hi) { __nv_bfloat16 h, l; split_one(v, h, l); hi[(size_t)r * ldo + e] = h; lo[(size_t)r * ldo + e] = l; }
   }
 }
 void gather_embed(cudaStream_t s, const float* WembT, const int* tok, int R, int E, float* out, const StepScalars* sc,
-                  bool train, __nv_bfloat16* hi, __nv_bfloat16* lo) {
-  gather_embed_kernel<<<R, 128, 0, s>>>(WembT, tok, R, E, out, sc, train ? 1 : 0, hi, lo);
+                  bool train, __nv_bfloat16* hi, __nv_bfloat16* lo, int ldo) {
+  gather_embed_kernel<<<R, 128, 0, s>>>(WembT, tok, R, E, ldo > 0 ? ldo : E, out, sc, train ? 1 : 0, hi, lo);
   count_launch();
 }
 
-__global__ void z_finish_kernel(float* __restrict__ Z, const float* __restrict__ v, int ldv, int R, int B, int C,
+__global__ void z_finish_kernel(float* __restrict__ Z, const float* __restrict__ v, int ldv, int R, int B, int C, int ldz,
                                 const StepScalars* __restrict__ sc, int train, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   int r = blockIdx.x;
   int i = B > 0 ? r % B : r / (-B);  // B<0: generation, image index = row / beam_width
-  float* z = Z + (size_t)r * 2 * C;
+  float* z = Z + (size_t)r * ldz;
   for (int j = threadIdx.x; j < 2 * C; j += blockDim.x) {
     float x = (j < C) ? z[j] : v[(size_t)i * ldv + (j - C)];
     if (train) x *= drop_scale(sc, 1, (uint64_t)r * 2 * C + j);
     z[j] = x;
-    if (hi) { __nv_bfloat16 h, l; split_one(x, h, l); hi[(size_t)r * 2 * C + j] = h; lo[(size_t)r * 2 * C + j] = l; }
+    if (hi) { __nv_bfloat16 h, l; split_one(x, h, l); hi[(size_t)r * ldz + j] = h; lo[(size_t)r * ldz + j] = l; }
   }
 }
 void z_finish(cudaStream_t s, float* Z, const float* v, int ldv, int R, int B, int C, const StepScalars* sc, bool train,
-              __nv_bfloat16* hi, __nv_bfloat16* lo) {
-  z_finish_kernel<<<R, 128, 0, s>>>(Z, v, ldv, R, B, C, sc, train ? 1 : 0, hi, lo);
+              __nv_bfloat16* hi, __nv_bfloat16* lo, int ldz) {
+  z_finish_kernel<<<R, 128, 0, s>>>(Z, v, ldv, R, B, C, ldz > 0 ? ldz : 2 * C, sc, train ? 1 : 0, hi, lo);
   count_launch();
 }
 
@@ -615,17 +615,18 @@ constexpr int TOPK_MAX = 11;
 //  * each thread keeps its top KT >= K in registers (KT is a template parameter: no dynamic register indexing); warps merge
 //    by K rounds of shuffle-argmax, warp 0 merges the warp winners.
 template <bool FROM_LOGITS, int KT>
-__global__ void __launch_bounds__(512) beam_row_topk_kernel(const float* __restrict__ in, int ld, int V, int K,
+__global__ void __launch_bounds__(512) beam_row_topk_kernel(const float* __restrict__ in, int ld, int R, int V, int K,
                                                             const float* __restrict__ parent_prob, int* __restrict__ cand_tok,
                                                             float* __restrict__ cand_score, float* __restrict__ cand_lp) {
   extern __shared__ __align__(16) float row[];  // V logits (only when FROM_LOGITS)
   __shared__ float red[32];
   __shared__ float wv[16][TOPK_MAX];
   __shared__ int wi[16][TOPK_MAX];
-  const int r = blockIdx.x;
-  const float* a = in + (size_t)r * ld;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+ for (int r = blockIdx.x; r < R; r += gridDim.x) {  // persistent over rows: one smem allocation / CTA launch per SM slot
+  const float* a = in + (size_t)r * ld;
   float lse = 0.f, mx = 0.f;
+  __syncthreads();  // the previous row's smem (row, wv, wi) is no longer read
   if (FROM_LOGITS) {
     mx = -INFINITY;
     const int V4 = V >> 2;
@@ -695,14 +696,16 @@ __global__ void __launch_bounds__(512) beam_row_topk_kernel(const float* __restr
       }
     }
   }
+ }
 }
 template <bool FL>
 static void beam_topk_dispatch(cudaStream_t s, size_t smem, const float* in, int ld, int R, int V, int K, const float* parent_prob, int* cand_tok,
                                float* cand_score, float* cand_lp) {
-  if (K <= 1) beam_row_topk_kernel<FL, 1><<<R, 512, smem, s>>>(in, ld, V, K, parent_prob, cand_tok, cand_score, cand_lp);
-  else if (K <= 3) beam_row_topk_kernel<FL, 3><<<R, 512, smem, s>>>(in, ld, V, K, parent_prob, cand_tok, cand_score, cand_lp);
-  else if (K <= 5) beam_row_topk_kernel<FL, 5><<<R, 512, smem, s>>>(in, ld, V, K, parent_prob, cand_tok, cand_score, cand_lp);
-  else beam_row_topk_kernel<FL, TOPK_MAX><<<R, 512, smem, s>>>(in, ld, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+  const int grid = R < 148 * 4 ? R : 148 * 4;
+  if (K <= 1) beam_row_topk_kernel<FL, 1><<<grid, 512, smem, s>>>(in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+  else if (K <= 3) beam_row_topk_kernel<FL, 3><<<grid, 512, smem, s>>>(in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+  else if (K <= 5) beam_row_topk_kernel<FL, 5><<<grid, 512, smem, s>>>(in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+  else beam_row_topk_kernel<FL, TOPK_MAX><<<grid, 512, smem, s>>>(in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
 }
 static void beam_topk_launch(cudaStream_t s, bool from_logits, const float* in, int ld, int R, int V, int K,
                              const float* parent_prob, int* cand_tok, float* cand_score, float* cand_lp) {
@@ -762,15 +765,15 @@ __global__ void __launch_bounds__(128) beam_advance_kernel(BeamAdvanceArgs a) {
   int parent = img * a.K + a.sel_parent[r];
   for (int j = threadIdx.x; j < a.H1; j += blockDim.x) {
     const float hv = a.h1_in[(size_t)parent * a.H1 + j];
-    a.h1_out[(size_t)r * a.H1 + j] = hv;
+    a.h1_out[(size_t)r * a.ld1 + j] = hv;
     a.c1_out[(size_t)r * a.H1 + j] = a.c1_in[(size_t)parent * a.H1 + j];
-    if (a.h1_hi) { __nv_bfloat16 hh, ll; split_one(hv, hh, ll); a.h1_hi[(size_t)r * a.H1 + j] = hh; a.h1_lo[(size_t)r * a.H1 + j] = ll; }
+    if (a.h1_hi) { __nv_bfloat16 hh, ll; split_one(hv, hh, ll); a.h1_hi[(size_t)r * a.ld1 + j] = hh; a.h1_lo[(size_t)r * a.ld1 + j] = ll; }
   }
   for (int j = threadIdx.x; j < a.H2; j += blockDim.x) {
     const float hv = a.h2_in[(size_t)parent * a.H2 + j];
-    a.h2_out[(size_t)r * a.H2 + j] = hv;
+    a.h2_out[(size_t)r * a.ld2 + j] = hv;
     a.c2_out[(size_t)r * a.H2 + j] = a.c2_in[(size_t)parent * a.H2 + j];
-    if (a.h2_hi) { __nv_bfloat16 hh, ll; split_one(hv, hh, ll); a.h2_hi[(size_t)r * a.H2 + j] = hh; a.h2_lo[(size_t)r * a.H2 + j] = ll; }
+    if (a.h2_hi) { __nv_bfloat16 hh, ll; split_one(hv, hh, ll); a.h2_hi[(size_t)r * a.ld2 + j] = hh; a.h2_lo[(size_t)r * a.ld2 + j] = ll; }
   }
   // history so far has a.step tokens (bos + step-1 generated); append one
   int len = a.step;

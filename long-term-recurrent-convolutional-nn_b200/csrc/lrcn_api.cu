@@ -98,7 +98,7 @@ struct Slot { int l = 0, B = 0, split = 0; int *tok_in = nullptr, *tok_tgt = nul
 struct Workspace {  // element offsets into the workspace arena
   size_t X, v, dv, Eall, dE, acts1, h1, c1, Z, dZ, acts2, h2, c2, logits, rowlp, dh2, dh1, dhrec1, dc1, dhrec2, dc2;
   // generation
-  size_t gX, gv, ge, gg1, gh1a, gc1a, gh1b, gc1b, gz, gg2, gh2a, gc2a, gh2b, gc2b, glogits, gprob, gcs, gclp, gss, gslp, glpa, glpb, goprob, golp;
+  size_t gX, gv, ge, gg1, gh1a, gc1a, gh1b, gc1b, gz, gg2, gh2a, gc2a, gh2b, gc2b, glogits, gprob, gcs, gclp, gss, gslp, glpa, glpb, goprob, golp, gxh1, gxh2;
 };
 struct lrcn_handle {
   lrcn_config cfg;
@@ -303,6 +303,7 @@ static int create_impl(const lrcn_config* cfg, lrcn_handle* h) {
   o.gh2a = a.take(G * H2); o.gc2a = a.take(G * H2); o.gh2b = a.take(G * H2); o.gc2b = a.take(G * H2);
   o.glogits = a.take(G * ldV); o.gprob = a.take(G); o.gcs = a.take(G * 16); o.gclp = a.take(G * 16); o.gss = a.take(G); o.gslp = a.take(G);
   o.glpa = a.take(G * ML); o.glpb = a.take(G * ML); o.goprob = a.take(G); o.golp = a.take(G * ML);
+  o.gxh1 = a.take(G * (E + H1)); o.gxh2 = a.take(G * (2 * C + H2));  // [x|h] operands of the wide (many-row) generation path
   a.cap = a.used;
   CK(cudaMalloc(&a.f, a.cap * 4));
   CK(cudaMemset(a.f, 0, a.cap * 4));
@@ -838,12 +839,6 @@ extern "C" int lrcn_train_step_staged(lrcn_handle* h, int slot, float pdrop, uin
 static void beam_lstm_step(lrcn_handle* h, int layer, int step, int R, float* g, float* h_in, float* c_in, float* h_out, float* c_out) {
   const int H = layer == 1 ? h->H1 : h->H2;
   const int ldw = layer == 1 ? h->E + h->H1 : 2 * h->H2, x_off = layer == 1 ? h->E : 2 * h->C;
-  if (h->bf16mode && R > 512) {
-    // many rows: throughput matters more than latency -> pair-tile GEMM for the recurrent part + one elementwise cell kernel
-    if (step > 1) gemm(h, true, true, R, 4 * H, H, h_in, H, Wp(h, layer == 1 ? 1 : 3) + x_off, ldw, g, 4 * H, true, nullptr);
-    lstm_cell_fwd(h->stream, g, c_in, c_out, h_out, R, H, SH(h, h_out).hi, SH(h, h_out).lo);
-    return;
-  }
   if (h->bf16mode) {
     bf16 *hi_hi, *hi_lo, *ho_hi, *ho_lo;
     shadow(h, h_in, &hi_hi, &hi_lo);
@@ -856,6 +851,10 @@ static void beam_lstm_step(lrcn_handle* h, int layer, int step, int R, float* g,
   if (step > 1) sgemm(h->stream, true, true, R, 4 * H, H, h_in, H, Wp(h, layer == 1 ? 1 : 3) + x_off, ldw, g, 4 * H, true, nullptr);
   lstm_cell_fwd(h->stream, g, c_in, c_out, h_out, R, H);
 }
+// many rows in flight: throughput path.  The step's two gate GEMMs run on concatenated [x|h] operands (exactly the
+// reference's hcat(input,hidden)*weight, lrcn.jl:529) so there is no accumulate pass over the gates.
+static bool beam_wide(const lrcn_handle* h, int R) { return h->bf16mode && R > 512; }
+
 static void enqueue_beam_step(lrcn_handle* h, int n_img, int K, int step, int nword, int maxlen, bool flip, float* out_lp) {
   const int R = n_img * K, E = h->E, H1 = h->H1, H2 = h->H2, C = h->C, V = h->V, ldV = h->ldV, ldv = h->ldv;
   const Workspace& o = h->o;
@@ -864,18 +863,35 @@ static void enqueue_beam_step(lrcn_handle* h, int n_img, int K, int step, int nw
   // state ping-pong: "a" holds the beams' current states; the cell writes advanced states into "b"; advance gathers b -> a
   float *h1a = WS(h, o.gh1a), *c1a = WS(h, o.gc1a), *h1b = WS(h, o.gh1b), *c1b = WS(h, o.gc1b);
   float *h2a = WS(h, o.gh2a), *c2a = WS(h, o.gc2a), *h2b = WS(h, o.gh2b), *c2b = WS(h, o.gc2b);
-  gather_embed(s, Wp(h, 7), h->g_last, R, E, e, h->d_sc, false, SH(h, e).hi, SH(h, e).lo);                  // Wemb[tok:tok,:]  lrcn.jl:650
-  gemm(h, true, true, R, 4 * H1, E, e, E, Wp(h, 1), E + H1, g1, 4 * H1, false, Wp(h, 2));
-  beam_lstm_step(h, 1, step, R, g1, h1a, c1a, h1b, c1b);
-  gemm(h, true, true, R, C, H1, h1b, H1, Wp(h, 5), H1, z, 2 * C, false, nullptr);
-  z_finish(s, z, v, ldv, R, -K, C, h->d_sc, false, SH(h, z).hi, SH(h, z).lo);  // negative B => image index = row / K
-  gemm(h, true, true, R, 4 * H2, 2 * C, z, 2 * C, Wp(h, 3), 2 * H2, g2, 4 * H2, false, Wp(h, 4));
-  beam_lstm_step(h, 2, step, R, g2, h2a, c2a, h2b, c2b);
+  const bool wide = beam_wide(h, R);
+  int ld1 = H1, ld2 = H2;
+  if (wide) {
+    float *xh1 = WS(h, o.gxh1), *xh2 = WS(h, o.gxh2);
+    ld1 = E + H1; ld2 = 2 * C + H2;
+    gather_embed(s, Wp(h, 7), h->g_last, R, E, xh1, h->d_sc, false, SH(h, xh1).hi, SH(h, xh1).lo, ld1);     // Wemb[tok:tok,:]  lrcn.jl:650
+    gemm(h, true, true, R, 4 * H1, E + H1, xh1, ld1, Wp(h, 1), E + H1, g1, 4 * H1, false, Wp(h, 2));        // hcat(x,h)*W .+ b  lrcn.jl:529
+    lstm_cell_fwd(s, g1, c1a, c1b, h1b, R, H1, SH(h, h1b).hi, SH(h, h1b).lo);
+    gemm(h, true, true, R, C, H1, h1b, H1, Wp(h, 5), H1, xh2, ld2, false, nullptr);                           // x*w[end-4]  lrcn.jl:545
+    z_finish(s, xh2, v, ldv, R, -K, C, h->d_sc, false, SH(h, xh2).hi, SH(h, xh2).lo, ld2);                   // hcat(x,x_cnn)  lrcn.jl:546
+    gemm(h, true, true, R, 4 * H2, 2 * C + H2, xh2, ld2, Wp(h, 3), 2 * H2, g2, 4 * H2, false, Wp(h, 4));
+    lstm_cell_fwd(s, g2, c2a, c2b, h2b, R, H2, SH(h, h2b).hi, SH(h, h2b).lo);
+    h1a = xh1 + E;       // the gathered parent states go straight into the h columns of the next step's operands
+    h2a = xh2 + 2 * C;
+  } else {
+    gather_embed(s, Wp(h, 7), h->g_last, R, E, e, h->d_sc, false, SH(h, e).hi, SH(h, e).lo);                // Wemb[tok:tok,:]  lrcn.jl:650
+    gemm(h, true, true, R, 4 * H1, E, e, E, Wp(h, 1), E + H1, g1, 4 * H1, false, Wp(h, 2));
+    beam_lstm_step(h, 1, step, R, g1, h1a, c1a, h1b, c1b);
+    gemm(h, true, true, R, C, H1, h1b, H1, Wp(h, 5), H1, z, 2 * C, false, nullptr);
+    z_finish(s, z, v, ldv, R, -K, C, h->d_sc, false, SH(h, z).hi, SH(h, z).lo);  // negative B => image index = row / K
+    gemm(h, true, true, R, 4 * H2, 2 * C, z, 2 * C, Wp(h, 3), 2 * H2, g2, 4 * H2, false, Wp(h, 4));
+    beam_lstm_step(h, 2, step, R, g2, h2a, c2a, h2b, c2b);
+  }
   gemm(h, true, true, R, V, H2, h2b, H2, Wp(h, 8), H2, logits, ldV, false, Wp(h, 9));
   beam_row_topk(s, logits, ldV, R, V, K, WS(h, o.gprob), h->g_ctok, WS(h, o.gcs), WS(h, o.gclp));             // lrcn.jl:652-661
   beam_select(s, h->g_ctok, WS(h, o.gcs), WS(h, o.gclp), n_img, K, step == 1, h->g_stok, h->g_spar, WS(h, o.gss), WS(h, o.gslp));  // :667-668
   BeamAdvanceArgs a;
   a.n_img = n_img; a.K = K; a.H1 = H1; a.H2 = H2; a.maxlen = maxlen; a.step = step; a.nword = nword;
+  a.ld1 = ld1; a.ld2 = ld2;
   a.sel_tok = h->g_stok; a.sel_parent = h->g_spar; a.sel_score = WS(h, o.gss); a.sel_lp = WS(h, o.gslp);
   a.h1_in = h1b; a.c1_in = c1b; a.h2_in = h2b; a.c2_in = c2b; a.h1_out = h1a; a.c1_out = c1a; a.h2_out = h2a; a.c2_out = c2a;
   a.hist_in = flip ? h->g_histb : h->g_hista; a.hist_out = flip ? h->g_hista : h->g_histb;
@@ -934,6 +950,12 @@ extern "C" int lrcn_beam_search(lrcn_handle* h, int split, const int64_t* image_
       gemm(h, true, true, ni, h->C, LRCN_F_CNN, WS(h, o.gX), LRCN_F_CNN, Wp(h, 6), LRCN_F_CNN, WS(h, o.gv), h->ldv, false, nullptr);  // lrcn.jl:611
       beam_init_kernel<<<(R + 255) / 256, 256, 0, h->stream>>>(R, maxlen, WS(h, o.gprob), h->g_last, h->g_hista, WS(h, o.glpa), h->g_done, h->g_ndone, ni);
       h->counter.n++;
+      if (beam_wide(h, R)) {  // h_0 = 0 in the h columns of the [x|h] operands (fp32 and bf16 shadows)
+        const size_t n1 = (size_t)R * (h->E + h->H1), n2 = (size_t)R * (2 * h->C + h->H2);
+        CK(cudaMemsetAsync(WS(h, o.gxh1), 0, n1 * 4, h->stream)); CK(cudaMemsetAsync(WS(h, o.gxh2), 0, n2 * 4, h->stream));
+        CK(cudaMemsetAsync(SH(h, WS(h, o.gxh1)).hi, 0, n1 * 2, h->stream)); CK(cudaMemsetAsync(SH(h, WS(h, o.gxh1)).lo, 0, n1 * 2, h->stream));
+        CK(cudaMemsetAsync(SH(h, WS(h, o.gxh2)).hi, 0, n2 * 2, h->stream)); CK(cudaMemsetAsync(SH(h, WS(h, o.gxh2)).lo, 0, n2 * 2, h->stream));
+      }
       CK(cudaMemsetAsync(WS(h, o.gc1a), 0, (size_t)R * h->H1 * 4, h->stream));
       CK(cudaMemsetAsync(WS(h, o.gc2a), 0, (size_t)R * h->H2 * 4, h->stream));
       bool flip = false;

@@ -280,6 +280,32 @@ def test_beam_search_matches_oracle(prec, K):
     assert same >= int(np.ceil(0.99 * n_img)), f"only {same}/{n_img} captions identical"
 
 
+def test_beam_search_many_rows_path_matches_small_batches_and_oracle():
+    # > 512 rows in flight switches generation to the throughput path ([x|h] GEMM operands, elementwise cell kernel)
+    if abi.PREC_BF16X3 not in PRECS:
+        pytest.skip("tcgen05 path only")
+    E, H1, H2, V, n_img, nword, K = 64, 64, 64, 200, 200, 12, 3
+    model = synth.initweights([H1, H2], V, E, seed=7)
+    model = [w * np.float32(6) if w.shape[0] > 1 else w for w in model]
+    model[8][0, O.EOS - 1] = 0.65
+    feats = synth.features(n_img, seed=9) * np.float32(100)
+    ids = np.arange(1, n_img + 1, dtype=np.int64)
+    res = []
+    for gen_rows in (900, 60):
+        with open_handle(E, H1, H2, V, 4, 3, abi.PREC_BF16X3, gen_rows=gen_rows) as h:
+            h.set_model(model)
+            h.load_features(1, ids, feats)
+            res.append(h.beam_search(1, ids, K, nword))
+    (ta, la, pa, _), (tb, lb, pb, _) = res
+    same = sum(int(la[i] == lb[i] and (ta[i, :la[i]] == tb[i, :lb[i]]).all()) for i in range(n_img))
+    assert same >= int(np.ceil(0.99 * n_img)), f"wide vs narrow path: only {same}/{n_img} captions identical"
+    ok = 0
+    for i in range(24):
+        ref_t, ref_p = O.generate(model, feats[i], nword, K)
+        ok += int(ta[i, :la[i]].tolist() == ref_t)
+    assert ok >= 23
+
+
 def test_host_mirror_train_and_generate_text():
     # the reference-facing host API: minibatch format in, caption text out (lrcn.jl:257-297, 585-642)
     import io
