@@ -606,112 +606,141 @@ __device__ __forceinline__ BestPair block_argmax(BestPair p, BestPair* red) {
 }
 
 constexpr int TOPK_MAX = 11;
+constexpr int TOPK_CAP = 256;  // candidate list capacity of the threshold-select path
+struct TopPair { float v; int i; };
+__device__ __forceinline__ TopPair top_better(TopPair a, TopPair b) { return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a; }
+__device__ __forceinline__ TopPair warp_top(TopPair p) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    TopPair q;
+    q.v = __shfl_xor_sync(0xffffffffu, p.v, o);
+    q.i = __shfl_xor_sync(0xffffffffu, p.i, o);
+    p = top_better(p, q);
+  }
+  return p;
+}
+// block-wide (value desc, index asc) argmax; result valid in every thread
+__device__ __forceinline__ TopPair block_top(TopPair p, TopPair* red) {
+  p = warp_top(p);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) red[w] = p;
+  __syncthreads();
+  TopPair q;
+  q.v = -INFINITY; q.i = 0x7fffffff;
+  if (l < nw) q = red[l];
+  return warp_top(q);
+}
+
 // per row: probabilities ynorm = exp(logp(ypred,2)) (fp32, lrcn.jl:652-654) and the K largest by (prob desc, index asc)
-// (lrcn.jl:655-656: sortperm(rev=true) breaks ties by index).
-//  * the row is staged once in shared memory (one HBM/L2 read);
-//  * the normaliser uses __expf (its ~1e-7 relative error shifts every probability of the row alike, so no ordering changes);
-//  * a thread only evaluates the precise expf for elements whose LOGIT reaches its current K-th best (exp is monotone), so
-//    the expensive per-element work is O(K log V) instead of O(V);
-//  * each thread keeps its top KT >= K in registers (KT is a template parameter: no dynamic register indexing); warps merge
-//    by K rounds of shuffle-argmax, warp 0 merges the warp winners.
-template <bool FROM_LOGITS, int KT>
+// (lrcn.jl:655-656: sortperm(rev=true) breaks ties by index).  Threshold select:
+//   1. the row is staged once in shared memory; max and normaliser by block reductions (the normaliser uses __expf: its ~1e-7
+//      relative error shifts every probability of the row alike, so no ordering changes);
+//   2. tau = K-th largest of the per-thread maxima is a lower bound of the K-th largest element, so every top-K element is >= tau;
+//   3. the (few) elements >= tau are appended to a candidate list; one warp evaluates their precise probabilities and picks the
+//      K best by (prob desc, index asc).  Ties at tau are all candidates, so selection on given probabilities is exact.
+//   A row with more than TOPK_CAP candidates (e.g. all-equal logits) falls back to K exact block-argmax rounds.
+template <bool FROM_LOGITS>
 __global__ void __launch_bounds__(512) beam_row_topk_kernel(const float* __restrict__ in, int ld, int R, int V, int K,
                                                             const float* __restrict__ parent_prob, int* __restrict__ cand_tok,
                                                             float* __restrict__ cand_score, float* __restrict__ cand_lp) {
-  extern __shared__ __align__(16) float row[];  // V logits (only when FROM_LOGITS)
+  extern __shared__ __align__(16) float row[];  // V values (logits, or the given probabilities)
   __shared__ float red[32];
-  __shared__ float wv[16][TOPK_MAX];
-  __shared__ int wi[16][TOPK_MAX];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
- for (int r = blockIdx.x; r < R; r += gridDim.x) {  // persistent over rows: one smem allocation / CTA launch per SM slot
-  const float* a = in + (size_t)r * ld;
-  float lse = 0.f, mx = 0.f;
-  __syncthreads();  // the previous row's smem (row, wv, wi) is no longer read
-  if (FROM_LOGITS) {
-    mx = -INFINITY;
-    const int V4 = V >> 2;
+  __shared__ TopPair pred[32];
+  __shared__ float cv[TOPK_CAP];
+  __shared__ int ci[TOPK_CAP];
+  __shared__ int ccount;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = blockIdx.x; r < R; r += gridDim.x) {  // persistent over rows
+    const float* a = in + (size_t)r * ld;
+    __syncthreads();  // previous row's shared state is no longer read
+    if (threadIdx.x == 0) ccount = 0;
+    float tmax = -INFINITY;
+    const int V4 = ((reinterpret_cast<uintptr_t>(a) & 15) == 0) ? (V >> 2) : 0;
     for (int q = threadIdx.x; q < V4; q += blockDim.x) {
       const float4 x = *reinterpret_cast<const float4*>(a + 4 * q);
       *reinterpret_cast<float4*>(row + 4 * q) = x;
-      mx = fmaxf(fmaxf(mx, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
+      tmax = fmaxf(fmaxf(tmax, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
     }
-    for (int j = 4 * V4 + threadIdx.x; j < V; j += blockDim.x) { const float x = a[j]; row[j] = x; mx = fmaxf(mx, x); }
-    mx = block_max(mx, red);
-    float sum = 0.f;
-    for (int j = threadIdx.x; j < V; j += blockDim.x) sum += __expf(row[j] - mx);
-    sum = block_sum(sum, red);
-    lse = logf(sum);
-  }
-  float tv[KT], tx[KT];  // probability and (FROM_LOGITS) logit of the kept entries, sorted by (prob desc, index asc)
-  int ti[KT];
-#pragma unroll
-  for (int k = 0; k < KT; k++) { tv[k] = -2.f; tx[k] = -INFINITY; ti[k] = 0x7fffffff; }
-  for (int j = threadIdx.x; j < V; j += blockDim.x) {
-    const float xj = FROM_LOGITS ? row[j] : a[j];
-    if (FROM_LOGITS ? (xj < tx[KT - 1]) : (xj < tv[KT - 1])) continue;  // cannot enter this thread's top KT
-    const float pj = FROM_LOGITS ? expf((xj - mx) - lse) : xj;
-    float cv = pj, cx = xj; int ci = j;
-#pragma unroll
-    for (int k = 0; k < KT; k++) {
-      if (cv > tv[k] || (cv == tv[k] && ci < ti[k])) {
-        const float fv = tv[k], fx = tx[k]; const int fi = ti[k];
-        tv[k] = cv; tx[k] = cx; ti[k] = ci; cv = fv; cx = fx; ci = fi;
-      }
+    for (int j = 4 * V4 + threadIdx.x; j < V; j += blockDim.x) { const float x = a[j]; row[j] = x; tmax = fmaxf(tmax, x); }
+    float lse = 0.f, mx = 0.f;
+    if (FROM_LOGITS) {
+      mx = block_max(tmax, red);
+      float sum = 0.f;
+      for (int j = threadIdx.x; j < V; j += blockDim.x) sum += __expf(row[j] - mx);
+      sum = block_sum(sum, red);
+      lse = logf(sum);
     }
-  }
-  int head = 0;
-  for (int k = 0; k < K; k++) {
-    float hv = -2.f; int hi_ = 0x7fffffff;
-#pragma unroll
-    for (int q = 0; q < KT; q++) if (q == head) { hv = tv[q]; hi_ = ti[q]; }
-    float bv = hv; int bi = hi_;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-    }
-    if (bi == hi_ && bv == hv) head++;  // my head won (indices are unique per row)
-    if (lane == 0) { wv[warp][k] = bv; wi[warp][k] = bi; }
-  }
-  __syncthreads();
-  if (warp == 0) {
-    int whead = 0;
-    const float pp = parent_prob[r];
+    // tau: K-th largest of the thread maxima (each thread covered a disjoint set of elements)
+    float mine = tmax, tau = 0.f;
     for (int k = 0; k < K; k++) {
-      float hv = -2.f; int hi_ = 0x7fffffff;
-      if (lane < nwarps && whead < K) { hv = wv[lane][whead]; hi_ = wi[lane][whead]; }
-      float bv = hv; int bi = hi_;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      TopPair p; p.v = mine; p.i = threadIdx.x;
+      p = block_top(p, pred);
+      tau = p.v;
+      if (p.i == (int)threadIdx.x) mine = -INFINITY;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < V; j += blockDim.x) {
+      const float x = row[j];
+      if (x >= tau) {
+        const int pos = atomicAdd(&ccount, 1);
+        if (pos < TOPK_CAP) { cv[pos] = x; ci[pos] = j; }
       }
-      if (bi == hi_ && bv == hv) whead++;
-      if (lane == 0) {
-        cand_tok[(size_t)r * K + k] = bi;
-        cand_score[(size_t)r * K + k] = __fmul_rn(bv, pp);  // pmaxes = ynorm[xmaxes]*current_probability (lrcn.jl:657)
-        cand_lp[(size_t)r * K + k] = FROM_LOGITS ? ((row[bi] - mx) - lse) : logf(bv);
+    }
+    __syncthreads();
+    const int nc = ccount;
+    const float pp = parent_prob[r];
+    if (nc <= TOPK_CAP) {
+      if (warp == 0) {
+        constexpr int PER = TOPK_CAP / 32;
+        float pv[PER]; int pi[PER];
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+          const int c = lane + 32 * q;
+          pv[q] = -INFINITY; pi[q] = 0x7fffffff;
+          if (c < nc) { const float x = cv[c]; pv[q] = FROM_LOGITS ? expf((x - mx) - lse) : x; pi[q] = ci[c]; }
+        }
+        for (int k = 0; k < K; k++) {
+          TopPair best; best.v = -INFINITY; best.i = 0x7fffffff;
+#pragma unroll
+          for (int q = 0; q < PER; q++) { TopPair c; c.v = pv[q]; c.i = pi[q]; best = top_better(best, c); }
+          best = warp_top(best);
+#pragma unroll
+          for (int q = 0; q < PER; q++) if (pi[q] == best.i) { pv[q] = -INFINITY; pi[q] = 0x7fffffff; }  // indices are unique
+          if (lane == 0) {
+            cand_tok[(size_t)r * K + k] = best.i;
+            cand_score[(size_t)r * K + k] = __fmul_rn(best.v, pp);  // pmaxes = ynorm[xmaxes]*current_probability (lrcn.jl:657)
+            cand_lp[(size_t)r * K + k] = FROM_LOGITS ? ((row[best.i] - mx) - lse) : logf(best.v);
+          }
+        }
+      }
+    } else {
+      // exact fallback: K rounds of block argmax over the whole row on the probabilities themselves
+      if (FROM_LOGITS) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < V; j += blockDim.x) row[j] = expf((row[j] - mx) - lse);
+      }
+      for (int k = 0; k < K; k++) {
+        __syncthreads();
+        TopPair p; p.v = -INFINITY; p.i = 0x7fffffff;
+        for (int j = threadIdx.x; j < V; j += blockDim.x) { TopPair c; c.v = row[j]; c.i = j; p = top_better(p, c); }
+        p = block_top(p, pred);
+        if (threadIdx.x == 0) {
+          cand_tok[(size_t)r * K + k] = p.i;
+          cand_score[(size_t)r * K + k] = __fmul_rn(p.v, pp);
+          cand_lp[(size_t)r * K + k] = logf(p.v);
+          row[p.i] = -1.f;  // exclude from later rounds
+        }
       }
     }
   }
- }
-}
-template <bool FL>
-static void beam_topk_dispatch(cudaStream_t s, size_t smem, const float* in, int ld, int R, int V, int K, const float* parent_prob, int* cand_tok,
-                               float* cand_score, float* cand_lp) {
-  const int grid = R < 148 * 4 ? R : 148 * 4;
-  if (K <= 1) beam_row_topk_kernel<FL, 1><<<grid, 512, smem, s>>>(in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
-  else if (K <= 3) beam_row_topk_kernel<FL, 3><<<grid, 512, smem, s>>>(in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
-  else if (K <= 5) beam_row_topk_kernel<FL, 5><<<grid, 512, smem, s>>>(in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
-  else beam_row_topk_kernel<FL, TOPK_MAX><<<grid, 512, smem, s>>>(in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
 }
 static void beam_topk_launch(cudaStream_t s, bool from_logits, const float* in, int ld, int R, int V, int K,
                              const float* parent_prob, int* cand_tok, float* cand_score, float* cand_lp) {
-  size_t smem = from_logits ? ((size_t)V + 4) * sizeof(float) : 16;
-  if (from_logits) beam_topk_dispatch<true>(s, smem, in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
-  else beam_topk_dispatch<false>(s, smem, in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+  const size_t smem = ((size_t)V + 4) * sizeof(float);
+  const int grid = R < 148 * 4 ? R : 148 * 4;
+  if (from_logits) beam_row_topk_kernel<true><<<grid, 512, smem, s>>>(in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+  else beam_row_topk_kernel<false><<<grid, 512, smem, s>>>(in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
   count_launch();
 }
 void beam_row_topk(cudaStream_t s, const float* logits, int ld, int R, int V, int K, const float* parent_prob, int* cand_tok,
@@ -825,10 +854,8 @@ void beam_advance(cudaStream_t s, const BeamAdvanceArgs& a) {
 // called once per process from lrcn_create (never inside a stream capture)
 void init_simt_kernels() {
   cudaFuncSetAttribute(softmax_ce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(beam_row_topk_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(beam_row_topk_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(beam_row_topk_kernel<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(beam_row_topk_kernel<true, TOPK_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(beam_row_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(beam_row_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
 }  // namespace lrcn
