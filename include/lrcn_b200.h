@@ -155,6 +155,10 @@ LRCN_API int lrcn_time_kernel(lrcn_handle* h, const char* name, int reps, float*
  * b_kmajor: B is [N][K] else [K][N].  precision selects the fp32 or the tcgen05 bf16x3 kernel. */
 LRCN_API int lrcn_test_gemm(lrcn_handle* h, int precision, int a_kmajor, int b_kmajor, int M, int N, int K,
                    const float* A, const float* B, const float* bias, int beta, float* C);
+/* diagnostics: average ms of `iters` back-to-back bf16x3 GEMM launches on scratch operands of this shape (no L2 flush);
+ * dbg bits (pair kernel only): 1 = no epilogue stores, 2 = no TMA loads after the first ring fill, 4 = no MMAs */
+LRCN_API int lrcn_test_gemm_time(lrcn_handle* h, int a_kmajor, int b_kmajor, int M, int N, int K, int with_shadow_out, int iters,
+                        int dbg, float* avg_ms_out);
 /* beam selection on caller-supplied probabilities: probs [rows][V], parent_prob [rows]; outputs per image */
 LRCN_API int lrcn_test_beam_select(lrcn_handle* h, const float* probs, const float* parent_prob, int n_images, int K,
                           int V, int first_step, int64_t* tok_out, int32_t* parent_out, float* score_out);

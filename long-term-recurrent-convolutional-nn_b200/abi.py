@@ -65,6 +65,7 @@ SIGNATURES = {
     "lrcn_flush_l2": (C.c_int, [_H]),
     "lrcn_get_trace": (C.c_int, [_H, _p(C.c_uint64), C.c_int64]),
     "lrcn_time_kernel": (C.c_int, [_H, C.c_char_p, C.c_int, _f32p, _f64p, _f64p]),
+    "lrcn_test_gemm_time": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]),
     "lrcn_test_gemm": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, C.c_int, _f32p]),
     "lrcn_test_beam_select": (C.c_int, [_H, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _i64p, _i32p, _f32p]),
 }
@@ -291,6 +292,11 @@ class Handle:
         return float(ms.value), float(by.value), float(fl.value)
 
     # ---- kernel-level test hooks
+    def test_gemm_time(self, a_kmajor, b_kmajor, M, N, K, shadow_out=False, iters=20, dbg=0):
+        ms = C.c_float()
+        check(self.lib.lrcn_test_gemm_time(self._h, int(a_kmajor), int(b_kmajor), M, N, K, int(shadow_out), iters, dbg, C.byref(ms)))
+        return ms.value
+
     def test_gemm(self, precision, a_kmajor, b_kmajor, A, B, bias=None, C0=None):
         A = np.ascontiguousarray(A, dtype=np.float32)
         B = np.ascontiguousarray(B, dtype=np.float32)

@@ -27,7 +27,8 @@ constexpr int BM = 128, BNP = 256, BNH = 128, BK = 64, STAGES = 3;
 constexpr int TILE = 128 * BK * 2;               // 16 KiB: 128 rows x 128 B
 constexpr int STAGE_BYTES = 4 * TILE;            // A_hi, A_lo, Bhalf_hi, Bhalf_lo
 constexpr int EPI_LD = 36;
-constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
+constexpr int EPI_WARP_BYTES = 8192;             // two 4 KiB TMA-store staging buffers per epilogue warp (or one transpose buffer)
+constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;      // cute::Sm100MmaPeerBitMask: address the even (leader) CTA of the pair
@@ -69,17 +70,52 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
 
 struct Gemm2Params {
   int M, N, K;
-  int tiles_mp, tiles_n, splits, kb_per_split;  // tiles_mp: pairs of 128-row tiles
+  int tiles_mp, tiles_n;  // tiles_mp: pairs of 128-row tiles
+  int streamk;            // 0: whole 256x256 tiles round-robin; 1: every CTA pair owns an equal contiguous range of (tile, k-block) iterations
   float* C; int ldc;
   const float* bias;
   int beta;
   __nv_bfloat16* C_hi; __nv_bfloat16* C_lo;
+  int tma_epi;  // fp32 result leaves through TMA stores (TMA reduce-adds under split-K)
+  int dbg;  // lrcn_bench_gemm diagnostics: 1 = no epilogue stores, 2 = no TMA loads after the first ring fill, 4 = no MMAs
+};
+
+// One unit of work of a CTA pair: k-blocks [kb0, kb1) of one output tile.  Stream-K ranges are cut at
+// cidx * total / ncl and snapped to the tile boundary when they would leave a sliver of < 3 k-blocks.
+struct Seg { int tile, kb0, kb1; };
+struct SegIter {
+  int streamk, w, ncl, tiles, num_kb, it, it_end;
+  __device__ __forceinline__ static int boundary(int c, int ncl, int tiles, int num_kb) {
+    if (c >= ncl) return tiles * num_kb;
+    int b = (int)(((long long)c * tiles * num_kb) / ncl);
+    const int off = b % num_kb;
+    if (off < 3) b -= off;
+    else if (num_kb - off < 3) b += num_kb - off;
+    return b;
+  }
+  __device__ __forceinline__ SegIter(int streamk_, int cidx, int ncl_, int tiles_, int num_kb_)
+      : streamk(streamk_), w(cidx), ncl(ncl_), tiles(tiles_), num_kb(num_kb_), it(0), it_end(0) {
+    if (streamk) { it = boundary(cidx, ncl, tiles, num_kb); it_end = boundary(cidx + 1, ncl, tiles, num_kb); }
+  }
+  __device__ __forceinline__ bool next(Seg& s) {
+    if (!streamk) {
+      if (w >= tiles) return false;
+      s.tile = w; s.kb0 = 0; s.kb1 = num_kb; w += ncl;
+      return true;
+    }
+    if (it >= it_end) return false;
+    s.tile = it / num_kb; s.kb0 = it - s.tile * num_kb;
+    s.kb1 = min(num_kb, s.kb0 + (it_end - it));
+    it += s.kb1 - s.kb0;
+    return true;
+  }
 };
 
 template <bool AK, bool BKM>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::NUM_THREADS, 1)
 gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const Gemm2Params p) {
+                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                    const __grid_constant__ CUtensorMap tmC, const Gemm2Params p) {
   using namespace g2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -97,7 +133,6 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   const bool leader = rank == 0;
   const int num_kb_total = (p.K + BK - 1) / BK;
   const int tiles_mn = p.tiles_mp * p.tiles_n;
-  const int total_work = tiles_mn * p.splits;
   const int cidx = blockIdx.x >> 1, ncl = gridDim.x >> 1;
 
   if (threadIdx.x == 0) {
@@ -114,21 +149,29 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   cluster_sync_all();  // both CTAs: barriers initialised, TMEM allocated
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       int it = 0;
-      for (int w = cidx; w < total_work; w += ncl) {
-        const int z = w / tiles_mn, rem = w - z * tiles_mn;
+      SegIter si(p.streamk, cidx, ncl, tiles_mn, num_kb_total);
+      Seg sg;
+      while (si.next(sg)) {
+        const int rem = sg.tile;
         const int m0 = ((rem % p.tiles_mp) * 2 + rank) * BM;
         const int nh0 = (rem / p.tiles_mp) * BNP + rank * BNH;  // this CTA's half of the B tile
-        const int kb_begin = z * p.kb_per_split, kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
+        const int kb_begin = sg.kb0, kb_end = sg.kb1;
         for (int kb = kb_begin; kb < kb_end; kb++, it++) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(empty_bar0 + 8 * s, ph ^ 1);
           const uint32_t full = (full_bar0 + 8 * s) & PEER_MASK;  // the leader's barrier collects both CTAs' bytes
+          if ((p.dbg & 2) && it >= STAGES) {
+            if (leader) mbar_arrive(full_bar0 + 8 * s);
+            continue;
+          }
           if (leader) mbar_expect_tx(full_bar0 + 8 * s, 2 * STAGE_BYTES);
           const uint32_t sA_hi = smem_base + s * STAGE_BYTES, sA_lo = sA_hi + TILE, sB_hi = sA_lo + TILE, sB_lo = sB_hi + TILE;
           const int k0 = kb * BK;
@@ -160,9 +203,10 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     if (leader && lane == 0) {
       const uint32_t idesc = idesc_bf16(256, BNP, !AK, !BKM);
       int it = 0, local = 0;
-      for (int w = cidx; w < total_work; w += ncl, local++) {
-        const int z = w / tiles_mn;
-        const int kb_begin = z * p.kb_per_split, kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
+      SegIter si(p.streamk, cidx, ncl, tiles_mn, num_kb_total);
+      Seg sg;
+      for (; si.next(sg); local++) {
+        const int kb_begin = sg.kb0, kb_end = sg.kb1;
         const int acc = local & 1;
         const uint32_t aph = (local >> 1) & 1;
         mbar_wait(tempty_bar0 + 8 * acc, aph ^ 1);  // both CTAs' epilogues have drained this accumulator stage
@@ -176,6 +220,7 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           const uint32_t sA_hi = smem_base + s * STAGE_BYTES, sA_lo = sA_hi + TILE, sB_hi = sA_lo + TILE, sB_lo = sB_hi + TILE;
 #pragma unroll
           for (int k = 0; k < BK / 16; k++) {
+            if (p.dbg & 4) break;
             const uint64_t a_hi = AK ? desc_kmajor(sA_hi, k) : desc_mnmajor(sA_hi, k);
             const uint64_t a_lo = AK ? desc_kmajor(sA_lo, k) : desc_mnmajor(sA_lo, k);
             const uint64_t b_hi = BKM ? desc_kmajor(sB_hi, k) : desc_mnmajor(sB_hi, k);
@@ -192,22 +237,31 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   } else {
     // ===================== epilogue (both CTAs, own 128 TMEM lanes x 256 columns) =====================
     const int quad = warp & 3;
-    float* tb = epi_buf + quad * 32 * EPI_LD;
-    const bool split = p.splits > 1;
+    float* tb = epi_buf + quad * (EPI_WARP_BYTES / 4);
+    const uint32_t stage_buf = smem_u32(tb);
+    if (p.tma_epi && lane == 0) prefetch_tensormap(&tmC);
+    uint32_t chunk_no = 0;
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                         (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
     int local = 0;
-    for (int w = cidx; w < total_work; w += ncl, local++) {
-      const int z = w / tiles_mn, rem = w - z * tiles_mn;
+    SegIter si(p.streamk, cidx, ncl, tiles_mn, num_kb_total);
+    Seg sg;
+    for (; si.next(sg); local++) {
+      const int rem = sg.tile;
       const int m0 = ((rem % p.tiles_mp) * 2 + rank) * BM, n0 = (rem / p.tiles_mp) * BNP;
       const int acc = local & 1;
       const uint32_t aph = (local >> 1) & 1;
+      const bool split = sg.kb0 != 0 || sg.kb1 != num_kb_total;  // partial sum of a tile shared with other CTA pairs
+      const bool use_bias = p.bias && sg.kb0 == 0;
+      float bias_next = (use_bias && n0 + lane < p.N) ? p.bias[n0 + lane] : 0.f;
       mbar_wait(tfull_bar0 + 8 * acc, aph);
       tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < BNP; c += 32) {
         uint32_t v[32];
         LRCN_TMEM_LD_32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BNP + c), v);
+        const float bias_lane = bias_next;
+        if (p.tma_epi && use_bias && c + 32 < BNP && n0 + c + 32 + lane < p.N) bias_next = p.bias[n0 + c + 32 + lane];
         tmem_ld_wait();
         if (c + 32 >= BNP) {  // accumulator stage drained: tell the leader's MMA thread
           tc_fence_before();
@@ -218,7 +272,13 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           }
         }
         const int nb = n0 + c;
-        if (nb >= p.N) continue;
+        if (nb >= p.N || (p.dbg & 1)) continue;
+        if (p.tma_epi) {
+          if (m0 + quad * 32 < p.M)
+            epilogue_chunk_tma(&tmC, stage_buf + (chunk_no & 1u) * 4096u, v, bias_lane, use_bias, nb, m0 + quad * 32, split || p.beta, lane);
+          chunk_no++;
+          continue;
+        }
 #pragma unroll
         for (int q = 0; q < 8; q++)
           *reinterpret_cast<float4*>(tb + lane * EPI_LD + 4 * q) =
@@ -249,7 +309,7 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         } else {
           const int n = nb + lane;
           const bool nok = n < p.N;
-          const float bv = (p.bias && nok && (!split || z == 0)) ? p.bias[n] : 0.f;
+          const float bv = (use_bias && nok) ? p.bias[n] : 0.f;
 #pragma unroll 4
           for (int rr = 0; rr < 32; rr++) {
             const int m = mrow0 + rr;
@@ -274,6 +334,7 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         __syncwarp();
       }
     }
+    if (p.tma_epi && lane == 0) bulk_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -285,6 +346,7 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 }
 
 static int g2_num_sms = 148;
+int g_gemm_dbg = 0;
 bool init_gemm2_sm100() {
   using namespace g2;
   cudaError_t e = cudaFuncSetAttribute(gemm2_bf16x3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -301,24 +363,24 @@ bool init_gemm2_sm100() {
 // same contract as gemm_bf16x3 (kernels.cuh); the caller decides when the pair kernel pays off
 bool gemm2_bf16x3(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo,
                   int lda, const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, int ldb, float* C, int ldc, bool beta, const float* bias,
-                  __nv_bfloat16* C_hi, __nv_bfloat16* C_lo) {
+                  __nv_bfloat16* C_hi, __nv_bfloat16* C_lo, bool c_zeroed) {
   using namespace g2;
   if (M <= 0 || N <= 0 || K <= 0) return true;
   const int tm = (M + BM - 1) / BM, tmp = (tm + 1) / 2, tn = (N + BNP - 1) / BNP;
   const int num_kb = (K + BK - 1) / BK;
   const int max_cl = g2_num_sms / 2;
-  int splits = 1;
-  if (!C_hi) {
-    const int units = tmp * tn;
-    if (units * 2 <= max_cl && num_kb >= 8) {
-      splits = max_cl / units;
-      if (splits > num_kb / 4) splits = num_kb / 4;
-      if (splits < 1) splits = 1;
-      if (splits > 32) splits = 32;
-    }
+  // fewer tiles than CTA pairs: stream-K -- every pair takes an equal share of the (tile, k-block) iterations and partial
+  // tiles are summed in L2 by TMA reduce-adds (fp32 atomics without the TMA epilogue); needs fp32-only output
+  const int tiles = tmp * tn;
+  bool streamk = !C_hi && tiles * 10 <= max_cl * 7 && num_kb >= 8;  // (>= 70 % of the pairs busy with whole tiles: not worth the zero-fill + second epilogue)
+  int ncl = tiles < max_cl ? tiles : max_cl;
+  if (streamk) {
+    const long long total_it = (long long)tiles * num_kb;
+    long long want = total_it / 4;  // at least ~4 k-blocks per pair
+    if (want > max_cl) want = max_cl;
+    if (want <= tiles) streamk = false;
+    else ncl = (int)want;
   }
-  const int kb_per = (num_kb + splits - 1) / splits;
-  splits = (num_kb + kb_per - 1) / kb_per;
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   bool ok = true;
   if (a_kmajor) ok = ok && get_tensor_map_bf16(&ta_hi, A_hi, K, M, lda, BM) && get_tensor_map_bf16(&ta_lo, A_lo, K, M, lda, BM);
@@ -326,19 +388,21 @@ bool gemm2_bf16x3(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, in
   if (b_kmajor) ok = ok && get_tensor_map_bf16(&tb_hi, B_hi, K, N, ldb, BNH) && get_tensor_map_bf16(&tb_lo, B_lo, K, N, ldb, BNH);
   else          ok = ok && get_tensor_map_bf16(&tb_hi, B_hi, N, K, ldb, BK) && get_tensor_map_bf16(&tb_lo, B_lo, N, K, ldb, BK);
   if (!ok) return false;
-  if (splits > 1 && !beta) {
+  const bool tma_epi = gemm_tma_epilogue_ok(C, ldc, beta, C_hi);
+  CUtensorMap tc = ta_hi;
+  if (tma_epi && !get_tensor_map_f32_out(&tc, C, N, M, ldc)) return false;
+  if (streamk && !beta && !c_zeroed) {
     if (ldc == N) cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), s);
     else cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, s);
   }
   Gemm2Params p;
-  p.M = M; p.N = N; p.K = K; p.tiles_mp = tmp; p.tiles_n = tn; p.splits = splits; p.kb_per_split = kb_per;
-  p.C = C; p.ldc = ldc; p.bias = bias; p.beta = beta ? 1 : 0; p.C_hi = C_hi; p.C_lo = C_lo;
-  const int total = tmp * tn * splits;
-  const int grid = (total < max_cl ? total : max_cl) * 2;
-  if (a_kmajor && b_kmajor) gemm2_bf16x3_kernel<true, true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
-  else if (a_kmajor && !b_kmajor) gemm2_bf16x3_kernel<true, false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
-  else if (!a_kmajor && b_kmajor) gemm2_bf16x3_kernel<false, true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
-  else gemm2_bf16x3_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  p.M = M; p.N = N; p.K = K; p.tiles_mp = tmp; p.tiles_n = tn; p.streamk = streamk ? 1 : 0;
+  p.C = C; p.ldc = ldc; p.bias = bias; p.beta = beta ? 1 : 0; p.C_hi = C_hi; p.C_lo = C_lo; p.dbg = g_gemm_dbg; p.tma_epi = tma_epi ? 1 : 0;
+  const int grid = ncl * 2;
+  if (a_kmajor && b_kmajor) launch_pdl(gemm2_bf16x3_kernel<true, true>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, s, ta_hi, ta_lo, tb_hi, tb_lo, tc, p);
+  else if (a_kmajor && !b_kmajor) launch_pdl(gemm2_bf16x3_kernel<true, false>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, s, ta_hi, ta_lo, tb_hi, tb_lo, tc, p);
+  else if (!a_kmajor && b_kmajor) launch_pdl(gemm2_bf16x3_kernel<false, true>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, s, ta_hi, ta_lo, tb_hi, tb_lo, tc, p);
+  else launch_pdl(gemm2_bf16x3_kernel<false, false>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, s, ta_hi, ta_lo, tb_hi, tb_lo, tc, p);
   if (g_counter) g_counter->n++;
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) { set_sm100_error((std::string("gemm2_bf16x3 launch: ") + cudaGetErrorString(e)).c_str()); return false; }

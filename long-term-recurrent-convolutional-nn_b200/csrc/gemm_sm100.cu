@@ -39,8 +39,9 @@ void set_sm100_error(const char* msg) { g_gemm_err = msg; }
 constexpr int BM = 128, BK = 64;
 constexpr int A_TILE = BM * BK * 2;  // 16 KiB
 constexpr int NUM_THREADS = 192;
-constexpr int EPI_LD = 36;                            // padded row (floats) of the per-warp transpose buffer
-constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;        // 18 KiB for the 4 epilogue warps
+constexpr int EPI_LD = 36;                            // padded row (floats) of the per-warp transpose buffer (LSU epilogue)
+constexpr int EPI_WARP_BYTES = 8192;                  // per epilogue warp: two 4 KiB TMA-store staging buffers (or one transpose buffer)
+constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
 
 template <int BN_>
 struct TileCfg {
@@ -58,6 +59,7 @@ struct GemmParams {
   const float* bias;
   int beta;
   __nv_bfloat16* C_hi; __nv_bfloat16* C_lo;
+  int tma_epi;  // fp32 result leaves through TMA stores (TMA reduce-adds under split-K)
 };
 
 // CM = cluster size along M: the CM CTAs of a cluster compute M-adjacent tiles of the same N-tile in lockstep; each loads
@@ -66,7 +68,7 @@ template <bool AK, bool BKM, int BN_, int CM>
 __global__ void __cluster_dims__(CM, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                   const GemmParams p) {
+                   const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   using Cfg = TileCfg<BN_>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -103,6 +105,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   if (CM > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();     // everything above overlapped the previous kernel's tail; its results are visible from here on
+  pdl_trigger();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -199,8 +203,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   } else {
     // ===================== epilogue: TMEM -> registers -> smem transpose -> coalesced global =====================
     const int quad = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
-    float* tb = epi_buf + quad * 32 * EPI_LD;
+    float* tb = epi_buf + quad * (EPI_WARP_BYTES / 4);
+    const uint32_t stage_buf = smem_u32(tb);
     const bool split = p.splits > 1;
+    if (p.tma_epi && lane == 0) prefetch_tensormap(&tmC);
+    uint32_t chunk_no = 0;
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                         (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
     int local = 0;
@@ -209,12 +216,16 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       const int m0 = ((rem % tiles_mg) * CM + rank) * BM, n0 = (rem / tiles_mg) * BN_;
       const int acc = local & 1;
       const uint32_t aph = (local >> 1) & 1;
+      const bool use_bias = p.bias && (!split || z == 0);
+      float bias_next = (use_bias && n0 + lane < p.N) ? p.bias[n0 + lane] : 0.f;
       mbar_wait(tfull_bar0 + 8 * acc, aph);
       tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < BN_; c += 32) {
         uint32_t v[32];
         LRCN_TMEM_LD_32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN_ + c), v);
+        const float bias_lane = bias_next;
+        if (p.tma_epi && use_bias && c + 32 < BN_ && n0 + c + 32 + lane < p.N) bias_next = p.bias[n0 + c + 32 + lane];
         tmem_ld_wait();
         if (c + 32 >= BN_) {  // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
           tc_fence_before();
@@ -223,6 +234,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         }
         const int nb = n0 + c;
         if (nb >= p.N) continue;  // warp-uniform
+        if (p.tma_epi) {
+          if (m0 + quad * 32 < p.M)
+            epilogue_chunk_tma(&tmC, stage_buf + (chunk_no & 1u) * 4096u, v, bias_lane, use_bias, nb, m0 + quad * 32, split || p.beta, lane);
+          chunk_no++;
+          continue;
+        }
         // transpose through smem: lane i holds row i of the 32x32 chunk
 #pragma unroll
         for (int q = 0; q < 8; q++)
@@ -279,6 +296,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         __syncwarp();
       }
     }
+    if (p.tma_epi && lane == 0) bulk_wait<0>();  // all of this warp's stores have been written before the CTA may exit
   }
   tc_fence_before();
   __syncthreads();
@@ -326,8 +344,28 @@ static bool make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t o
   return true;
 }
 
+static bool make_map_f32_out(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { g_gemm_err = "cuTensorMapEncodeTiled unavailable"; return false; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld & 3)) { g_gemm_err = "fp32 output not 16-byte aligned / ld not a multiple of 4"; return false; }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[200];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(f32 out) failed (%d) inner=%llu outer=%llu ld=%llu", (int)r, (unsigned long long)inner,
+             (unsigned long long)outer, (unsigned long long)ld);
+    g_gemm_err = buf;
+    return false;
+  }
+  return true;
+}
+
 struct MapKey {
-  const void* p; uint64_t inner, outer, ld; uint32_t box;
+  const void* p; uint64_t inner, outer, ld; uint32_t box;  // box == 0xF32 marks the fp32 output maps
   bool operator<(const MapKey& o) const { return std::tie(p, inner, outer, ld, box) < std::tie(o.p, o.inner, o.outer, o.ld, o.box); }
 };
 static std::map<MapKey, CUtensorMap>& map_cache() { static std::map<MapKey, CUtensorMap> c; return c; }
@@ -347,11 +385,32 @@ bool get_tensor_map_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint
   return true;
 }
 
+bool get_tensor_map_f32_out(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld) {
+  MapKey k{ptr, inner, outer, ld, 0xF32u};
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  auto& c = map_cache();
+  auto it = c.find(k);
+  if (it != c.end()) { *out = it->second; return true; }
+  CUtensorMap m;
+  if (!make_map_f32_out(&m, ptr, inner, outer, ld)) return false;
+  if (c.size() > 8192) c.clear();
+  c[k] = m;
+  *out = m;
+  return true;
+}
+
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
 }
 static int g_num_sms = 148, g_force_bn = 0, g_force_cm = 0, g_two_cta = 1;
+int g_gemm_tma_epi = 1;
+int g_pdl = 1;  // LRCN_GEMM_TMA_EPI=0 keeps the LSU epilogue everywhere
+
+bool gemm_tma_epilogue_ok(const float* C, int ldc, bool beta, const void* C_hi) {
+  (void)beta;  // beta = accumulate into C = TMA reduce-add
+  return g_gemm_tma_epi && !C_hi && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
+}
 
 template <bool AK, bool BKM, int BN_>
 static cudaError_t set_attr() {
@@ -376,25 +435,29 @@ bool init_gemm_sm100() {
   g_force_bn = env_int("LRCN_GEMM_BN", 0);
   g_force_cm = env_int("LRCN_GEMM_CM", 0);
   g_two_cta = env_int("LRCN_GEMM_2CTA", 1);
+  g_gemm_tma_epi = env_int("LRCN_GEMM_TMA_EPI", 1);
+  g_pdl = env_int("LRCN_PDL", 1);
   if (g_two_cta && !init_gemm2_sm100()) return false;
   return true;
 }
 
 template <bool AK, bool BKM, int BN_>
 static void launch(cudaStream_t s, int grid, int cm, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
-                   const CUtensorMap& b_lo, const GemmParams& p) {
-  if (cm == 2) gemm_bf16x3_kernel<AK, BKM, BN_, 2><<<grid, NUM_THREADS, TileCfg<BN_>::SMEM_BYTES, s>>>(a_hi, a_lo, b_hi, b_lo, p);
-  else gemm_bf16x3_kernel<AK, BKM, BN_, 1><<<grid, NUM_THREADS, TileCfg<BN_>::SMEM_BYTES, s>>>(a_hi, a_lo, b_hi, b_lo, p);
+                   const CUtensorMap& b_lo, const CUtensorMap& c, const GemmParams& p) {
+  if (cm == 2) launch_pdl(gemm_bf16x3_kernel<AK, BKM, BN_, 2>, dim3(grid), dim3(NUM_THREADS), TileCfg<BN_>::SMEM_BYTES, s, a_hi, a_lo, b_hi, b_lo, c, p);
+  else launch_pdl(gemm_bf16x3_kernel<AK, BKM, BN_, 1>, dim3(grid), dim3(NUM_THREADS), TileCfg<BN_>::SMEM_BYTES, s, a_hi, a_lo, b_hi, b_lo, c, p);
 }
 
 bool gemm_bf16x3(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo,
                  int lda, const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, int ldb, float* C, int ldc, bool beta, const float* bias,
-                 __nv_bfloat16* C_hi, __nv_bfloat16* C_lo) {
+                 __nv_bfloat16* C_hi, __nv_bfloat16* C_lo, bool c_zeroed) {
   if (M <= 0 || N <= 0 || K <= 0) return true;
   const int tm = (M + BM - 1) / BM;
   // CTA-pair kernel (256 x 256 UMMA, half the B bytes per SM) whenever the output is wide enough to fill the pair tiles
-  if (g_two_cta && g_force_bn == 0 && tm >= 2 && N >= 192 && ((tm + 1) / 2) * ((N + 255) / 256) * 2 >= g_num_sms / 2)
-    return gemm2_bf16x3(s, a_kmajor, b_kmajor, M, N, K, A_hi, A_lo, lda, B_hi, B_lo, ldb, C, ldc, beta, bias, C_hi, C_lo);
+  const int pair_tiles = ((tm + 1) / 2) * ((N + 255) / 256), pairs = g_num_sms / 2;
+  if (g_two_cta && g_force_bn == 0 && tm >= 2 && N >= 192 &&
+      (pair_tiles * 2 >= pairs || (!C_hi && (long long)pair_tiles * ((K + BK - 1) / BK) >= 6ll * pairs)))
+    return gemm2_bf16x3(s, a_kmajor, b_kmajor, M, N, K, A_hi, A_lo, lda, B_hi, B_lo, ldb, C, ldc, beta, bias, C_hi, C_lo, c_zeroed);
   // BN = 256 halves the smem operand traffic per MMA (128x128 SS-mode MMAs sit right at the 128 B/clk smem limit);
   // use it when there is enough N to keep every SM busy
   int bn = (N >= 512 && tm * ((N + 255) / 256) >= g_num_sms) ? 256 : 128;
@@ -426,21 +489,24 @@ bool gemm_bf16x3(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int
   if (b_kmajor) ok = ok && get_tensor_map_bf16(&tb_hi, B_hi, K, N, ldb, bn / cm) && get_tensor_map_bf16(&tb_lo, B_lo, K, N, ldb, bn / cm);
   else          ok = ok && get_tensor_map_bf16(&tb_hi, B_hi, N, K, ldb, BK) && get_tensor_map_bf16(&tb_lo, B_lo, N, K, ldb, BK);
   if (!ok) return false;
+  const bool tma_epi = gemm_tma_epilogue_ok(C, ldc, beta, C_hi);
+  CUtensorMap tc = ta_hi;  // placeholder when unused
+  if (tma_epi && !get_tensor_map_f32_out(&tc, C, N, M, ldc)) return false;
 
-  if (splits > 1 && !beta) {
+  if (splits > 1 && !beta && !c_zeroed) {
     if (ldc == N) cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), s);
     else cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, s);
   }
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.tiles_m = tm; p.tiles_n = tn; p.splits = splits; p.kb_per_split = kb_per;
-  p.C = C; p.ldc = ldc; p.bias = bias; p.beta = beta ? 1 : 0; p.C_hi = C_hi; p.C_lo = C_lo;
+  p.C = C; p.ldc = ldc; p.bias = bias; p.beta = beta ? 1 : 0; p.C_hi = C_hi; p.C_lo = C_lo; p.tma_epi = tma_epi ? 1 : 0;
   const int total = ((tm + cm - 1) / cm) * tn * splits;  // work units per cluster
   const int max_cl = g_num_sms / cm;
   const int grid = (total < max_cl ? total : max_cl) * cm;
 #define LRCN_LAUNCH(AKv, BKv)                                                         \
   do {                                                                                \
-    if (bn == 256) launch<AKv, BKv, 256>(s, grid, cm, ta_hi, ta_lo, tb_hi, tb_lo, p); \
-    else launch<AKv, BKv, 128>(s, grid, cm, ta_hi, ta_lo, tb_hi, tb_lo, p);           \
+    if (bn == 256) launch<AKv, BKv, 256>(s, grid, cm, ta_hi, ta_lo, tb_hi, tb_lo, tc, p); \
+    else launch<AKv, BKv, 128>(s, grid, cm, ta_hi, ta_lo, tb_hi, tb_lo, tc, p);           \
   } while (0)
   if (a_kmajor && b_kmajor) LRCN_LAUNCH(true, true);
   else if (a_kmajor && !b_kmajor) LRCN_LAUNCH(true, false);

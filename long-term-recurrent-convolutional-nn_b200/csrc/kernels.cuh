@@ -23,6 +23,26 @@ struct StepScalars {
   float one_m_beta2;
 };
 
+// ---- programmatic dependent launch (PDL).  A kernel launched through launch_pdl may be scheduled while its predecessor in
+// the stream is still draining; it must execute pdl_wait() before touching any global memory the predecessor reads or
+// writes, and calls pdl_trigger() AFTER that wait, so at most two consecutive kernels overlap and everything two or more
+// launches upstream is complete when a kernel starts.  LRCN_PDL=0 turns the launch attribute off.
+extern int g_pdl;
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 struct LaunchCounter { long long n = 0; };
 extern thread_local LaunchCounter* g_counter;  // incremented by every launcher below
 
@@ -67,6 +87,10 @@ void adam_flat(cudaStream_t s, float* w, const float* g, float* m, float* v, siz
 void split_bf16(cudaStream_t s, const float* x, size_t n, __nv_bfloat16* hi, __nv_bfloat16* lo);
 void transpose2d(cudaStream_t s, const float* in, int rows, int cols, float* out);  // out[c][r] = in[r][c]
 void fill_l2_scratch(cudaStream_t s, float* buf, size_t n, float val);
+// one launch zeroing up to 8 fp32 ranges (16-byte aligned starts): accumulation targets of the step (split-K / stream-K GEMM
+// outputs, bias-gradient column sums, the embedding-gradient scatter, the LSTM grid-barrier counters)
+struct ZeroSegs { float* p[8]; size_t n[8]; int count = 0; void add(void* ptr, size_t nfloats) { if (nfloats && count < 8) { p[count] = (float*)ptr; n[count] = nfloats; count++; } } };
+void zero_multi(cudaStream_t s, const ZeroSegs& z);
 
 // ---------------------------------------------------------------- beam search
 // per row: prob = exp(logp(a)); top-K by (prob desc, index asc); cand_* are [R][K]
@@ -95,14 +119,17 @@ bool gemm_bf16x3(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int
                  const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo, int lda,
                  const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, int ldb,
                  float* C, int ldc, bool beta, const float* bias,
-                 __nv_bfloat16* C_hi, __nv_bfloat16* C_lo /* optional split of the result, same ldc */);
+                 __nv_bfloat16* C_hi, __nv_bfloat16* C_lo /* optional split of the result, same ldc */,
+                 bool c_zeroed = false /* C is known to be all zero: split-K / stream-K partial sums need no zero-fill */);
 const char* gemm_bf16x3_last_error();
 bool init_gemm_sm100();   // func attributes + driver entry point; call once outside any capture
 bool init_gemm2_sm100();
 // 2-CTA (cta_group::2) 256x256 pair-tile variant, same contract (gemm2_sm100.cu); gemm_bf16x3 dispatches to it
+bool gemm_tma_epilogue_ok(const float* C, int ldc, bool beta, const void* C_hi);
+extern int g_gemm_dbg;  // diagnostics for lrcn_bench_gemm only (0 in production)
 bool gemm2_bf16x3(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo,
                   int lda, const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, int ldb, float* C, int ldc, bool beta, const float* bias,
-                  __nv_bfloat16* C_hi, __nv_bfloat16* C_lo);
+                  __nv_bfloat16* C_hi, __nv_bfloat16* C_lo, bool c_zeroed = false);
 void init_simt_kernels();
 
 // ---------------------------------------------------------------- fused LSTM timestep (lstm_sm100.cu)
@@ -124,7 +151,7 @@ bool lstm_bwd_step(cudaStream_t s, int B, int H, bool has_rec, const __nv_bfloat
 
 // persistent whole-sequence variants (weights resident in smem, grid barrier per step).  *launched = false (and nothing
 // enqueued) when they do not apply (H too large for residency, T < 2, grid not co-resident): use the per-step kernels then.
-// counters: >= 64 zero-able uint32 in device memory.  hs/cs: [(T+1)*B][H] slot buffers; acts: [T*B][4H].
+// counters: 32 uint32 in device memory, ZERO on entry (the caller zeroes them once per step; one region per launch).  hs/cs: [(T+1)*B][H] slot buffers; acts: [T*B][4H].
 bool lstm_fwd_seq(cudaStream_t s, int B, int H, int T, const __nv_bfloat16* wperm_hi, const __nv_bfloat16* wperm_lo, float* acts, float* hs,
                   float* cs, __nv_bfloat16* hs_hi, __nv_bfloat16* hs_lo, unsigned int* counters, bool* launched,
                   unsigned long long* trace = nullptr /* optional [T][8] globaltimer stamps of CTA (0,0) */);

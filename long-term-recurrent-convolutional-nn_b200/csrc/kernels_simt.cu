@@ -569,6 +569,21 @@ __global__ void fill_kernel(float4* buf, size_t n4, float val) {
   float4 v = make_float4(val, val, val, val);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) buf[i] = v;
 }
+__global__ void zero_multi_kernel(const ZeroSegs z) {
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < z.count; k++) {
+    float* p = z.p[k];
+    const size_t n = z.n[k], n4 = n / 4;
+    float4* p4 = reinterpret_cast<float4*>(p);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) p4[i] = zero;
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) p[4 * n4 + threadIdx.x] = 0.f;
+  }
+}
+void zero_multi(cudaStream_t s, const ZeroSegs& z) {
+  if (z.count == 0) return;
+  zero_multi_kernel<<<148 * 4, 256, 0, s>>>(z);
+  count_launch();
+}
 void fill_l2_scratch(cudaStream_t s, float* buf, size_t n, float val) {
   fill_kernel<<<148 * 8, 256, 0, s>>>((float4*)buf, n / 4, val);
 }

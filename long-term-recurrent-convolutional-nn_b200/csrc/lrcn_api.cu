@@ -163,7 +163,7 @@ static void split_ws(lrcn_handle* h, const float* p, size_t n) {
 struct GemmFail { std::string msg; };
 // precision-dispatching GEMM on arena pointers (both are CUDA paths; no CPU fallback exists)
 static void gemm(lrcn_handle* h, bool aK, bool bK, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
-                 int ldc, bool beta, const float* bias, bool split_out = false) {
+                 int ldc, bool beta, const float* bias, bool split_out = false, bool c_zeroed = false) {
   if (!h->bf16mode) {
     sgemm(h->stream, aK, bK, M, N, K, A, lda, B, ldb, C, ldc, beta, bias);
     return;
@@ -172,7 +172,7 @@ static void gemm(lrcn_handle* h, bool aK, bool bK, int M, int N, int K, const fl
   shadow(h, A, &ah, &al);
   shadow(h, B, &bh, &bl);
   if (split_out) shadow(h, C, &ch, &cl);
-  if (!gemm_bf16x3(h->stream, aK, bK, M, N, K, ah, al, lda, bh, bl, ldb, C, ldc, beta, bias, ch, cl))
+  if (!gemm_bf16x3(h->stream, aK, bK, M, N, K, ah, al, lda, bh, bl, ldb, C, ldc, beta, bias, ch, cl, c_zeroed))
     throw GemmFail{gemm_bf16x3_last_error()};
 }
 
@@ -316,8 +316,8 @@ static int create_impl(const lrcn_config* cfg, lrcn_handle* h) {
   CK(cudaMalloc(&h->d_sc, sizeof(StepScalars))); CK(cudaMallocHost(&h->h_sc, sizeof(StepScalars)));
   memset(h->h_sc, 0, sizeof(StepScalars));
   CK(cudaMalloc(&h->d_loss, 8)); CK(cudaMallocHost(&h->h_loss, 8));
-  CK(cudaMalloc(&h->d_counters, 64 * sizeof(unsigned int)));
-  CK(cudaMemset(h->d_counters, 0, 64 * sizeof(unsigned int)));
+  CK(cudaMalloc(&h->d_counters, 256 * sizeof(unsigned int)));  // [0,128): 4 LSTM launches x 32 m-tile barriers; [128,..): softmax
+  CK(cudaMemset(h->d_counters, 0, 256 * sizeof(unsigned int)));
   if (getenv("LRCN_SEQ_TRACE")) { CK(cudaMalloc(&h->d_trace, 64 * 8 * 8)); CK(cudaMemset(h->d_trace, 0, 64 * 8 * 8)); }
   CK(cudaMalloc(&h->g_last, G * 4)); CK(cudaMalloc(&h->g_ctok, G * 16 * 4)); CK(cudaMalloc(&h->g_stok, G * 4)); CK(cudaMalloc(&h->g_spar, G * 4));
   CK(cudaMalloc(&h->g_hista, G * ML * 4)); CK(cudaMalloc(&h->g_histb, G * ML * 4)); CK(cudaMalloc(&h->g_done, G * 4));
@@ -525,7 +525,7 @@ static void lstm_layer_fwd(lrcn_handle* h, int layer, int T, int B, float* acts,
     shadow(h, hs, &hs_hi, &hs_lo);
     bool launched = false;
     if (!lstm_fwd_seq(h->stream, B, H, T, layer == 1 ? h->wp1_hi : h->wp2_hi, layer == 1 ? h->wp1_lo : h->wp2_lo, acts, hs, cs, hs_hi, hs_lo,
-                      h->d_counters, &launched, layer == 2 ? h->d_trace : nullptr))
+                      h->d_counters + (layer == 1 ? 0 : 32), &launched, layer == 2 ? h->d_trace : nullptr))
       throw GemmFail{gemm_bf16x3_last_error()};
     if (launched) return;
   }
@@ -538,7 +538,7 @@ static void lstm_layer_bwd(lrcn_handle* h, int layer, int T, int B, float* acts,
     shadow(h, acts, &a_hi, &a_lo);
     bool launched = false;
     if (!lstm_bwd_seq(h->stream, B, H, T, layer == 1 ? h->wt1_hi : h->wt2_hi, layer == 1 ? h->wt1_lo : h->wt2_lo, acts, a_hi, a_lo, cs, dh_all, dc,
-                      h->d_counters, &launched))
+                      h->d_counters + (layer == 2 ? 64 : 96), &launched))
       throw GemmFail{gemm_bf16x3_last_error()};
     if (launched) return;
   }
@@ -551,13 +551,28 @@ static void enqueue_forward(lrcn_handle* h, int split, int B, int l, bool train)
   cudaStream_t s = h->stream;
   float *X = WS(h, o.X), *v = WS(h, o.v), *Eall = WS(h, o.Eall), *acts1 = WS(h, o.acts1), *h1 = WS(h, o.h1), *c1 = WS(h, o.c1);
   float *Z = WS(h, o.Z), *acts2 = WS(h, o.acts2), *h2 = WS(h, o.h2), *c2 = WS(h, o.c2), *logits = WS(h, o.logits);
+  // Step start: (1) recurrent-weight operands of the persistent LSTM kernels (they load them before their dependency wait, so
+  // these launches must stay more than two kernels upstream of the first LSTM launch); (2) ONE launch zeroing every
+  // accumulation target of the step: grid-barrier counters, and for training the gradient arena behind dWout (bias column
+  // sums, split-K / stream-K weight gradients, the embedding scatter) and the stream-K data-gradient buffers.
+  if (h->bf16mode)
+    lstm_prepare_weights2(s, Wp(h, 1), E + H1, E, H1, h->wp1_hi, h->wp1_lo, train ? h->wt1_hi : nullptr, h->wt1_lo, Wp(h, 3), 2 * H2, 2 * C, H2,
+                          h->wp2_hi, h->wp2_lo, train ? h->wt2_hi : nullptr, h->wt2_lo);
+  {
+    ZeroSegs z;
+    z.add(h->d_counters, 128);
+    if (train) {
+      z.add(h->g + h->off[8], h->P - h->off[8]);  // arena order [Wout, bout | W2, b2, Wf, Wcnn | W1, b1, Wemb]: everything from bout on
+      z.add(WS(h, o.dh2), (size_t)R * H2);
+      z.add(WS(h, o.dZ), (size_t)R * 2 * C);
+      z.add(WS(h, o.dE), (size_t)R * E);
+    }
+    zero_multi(s, z);
+  }
   gather_features(s, h->tab[split].d, h->d_rows, B, X, SH(h, X).hi, SH(h, X).lo);
   gemm(h, true, true, B, C, LRCN_F_CNN, X, LRCN_F_CNN, Wp(h, 6), LRCN_F_CNN, v, ldv, false, nullptr);  // input*Wcnn  lrcn.jl:558
   gather_embed(s, Wp(h, 7), h->d_tok_in, R, E, Eall, h->d_sc, train, SH(h, Eall).hi, SH(h, Eall).lo);
   gemm(h, true, true, R, 4 * H1, E, Eall, E, Wp(h, 1), E + H1, acts1, 4 * H1, false, Wp(h, 2));         // x-part of layer 1, all t
-  if (h->bf16mode)
-    lstm_prepare_weights2(s, Wp(h, 1), E + H1, E, H1, h->wp1_hi, h->wp1_lo, train ? h->wt1_hi : nullptr, h->wt1_lo, Wp(h, 3), 2 * H2, 2 * C, H2,
-                          h->wp2_hi, h->wp2_lo, train ? h->wt2_hi : nullptr, h->wt2_lo);
   lstm_layer_fwd(h, 1, T, B, acts1, h1, c1);
   gemm(h, true, true, R, C, H1, h1 + (size_t)B * H1, H1, Wp(h, 5), H1, Z, 2 * C, false, nullptr);         // x*w[end-4]  lrcn.jl:545
   z_finish(s, Z, v, ldv, R, B, C, h->d_sc, train, SH(h, Z).hi, SH(h, Z).lo);  // hcat(x,x_cnn) + dropout          lrcn.jl:546-547
@@ -565,7 +580,7 @@ static void enqueue_forward(lrcn_handle* h, int split, int B, int l, bool train)
   lstm_layer_fwd(h, 2, T, B, acts2, h2, c2);
   gemm(h, true, true, R, V, H2, h2 + (size_t)B * H2, H2, Wp(h, 8), H2, logits, ldV, false, Wp(h, 9));      // x*w[end-1] .+ w[end]  lrcn.jl:550
   softmax_ce(s, logits, ldV, R, V, h->d_tok_tgt, WS(h, o.rowlp), h->d_sc, train, SH(h, logits).hi, SH(h, logits).lo, h->d_loss,
-             h->d_counters + 48);  // logp + gather + fp64 total  lrcn.jl:562-567
+             h->d_counters + 128);  // logp + gather + fp64 total  lrcn.jl:562-567
 }
 
 static void enqueue_backward_seg(lrcn_handle* h, int B, int l, bool train, int seg) {
@@ -577,27 +592,26 @@ static void enqueue_backward_seg(lrcn_handle* h, int B, int l, bool train, int s
   float *dh2 = WS(h, o.dh2), *dh1 = WS(h, o.dh1), *dv = WS(h, o.dv), *dE = WS(h, o.dE);
   if (seg == 1) {
     gemm(h, false, false, V, H2, R, dA, ldV, h2 + (size_t)B * H2, H2, Gp(h, 8), H2, false, nullptr);      // dWout = h2' * dA
-    colsum(s, dA, ldV, R, V, Gp(h, 9), false);                                                              // dbout
-    gemm(h, true, false, R, H2, V, dA, ldV, Wp(h, 8), H2, dh2, H2, false, nullptr);                        // dh2 = dA * Wout'
+    colsum(s, dA, ldV, R, V, Gp(h, 9), true);                                                                 // dbout
+    gemm(h, true, false, R, H2, V, dA, ldV, Wp(h, 8), H2, dh2, H2, false, nullptr, false, true);                        // dh2 = dA * Wout'
   } else if (seg == 2) {
     float *dhrec = WS(h, o.dhrec2), *dc = WS(h, o.dc2);
     lstm_layer_bwd(h, 2, T, B, acts2, c2, dh2, dhrec, dc);
-    gemm(h, false, false, 4 * H2, 2 * C, R, acts2, 4 * H2, Z, 2 * C, Gp(h, 3), 2 * H2, false, nullptr);          // dW2[:, x-part]
-    gemm(h, false, false, 4 * H2, H2, R, acts2, 4 * H2, h2, H2, Gp(h, 3) + 2 * C, 2 * H2, false, nullptr);       // dW2[:, h-part] (slot 0 = 0)
-    colsum(s, acts2, 4 * H2, R, 4 * H2, Gp(h, 4), false);
-    gemm(h, true, false, R, 2 * C, 4 * H2, acts2, 4 * H2, Wp(h, 3), 2 * H2, dZ, 2 * C, false, nullptr);
+    gemm(h, false, false, 4 * H2, 2 * C, R, acts2, 4 * H2, Z, 2 * C, Gp(h, 3), 2 * H2, false, nullptr, false, true);          // dW2[:, x-part]
+    gemm(h, false, false, 4 * H2, H2, R, acts2, 4 * H2, h2, H2, Gp(h, 3) + 2 * C, 2 * H2, false, nullptr, false, true);       // dW2[:, h-part] (slot 0 = 0)
+    colsum(s, acts2, 4 * H2, R, 4 * H2, Gp(h, 4), true);
+    gemm(h, true, false, R, 2 * C, 4 * H2, acts2, 4 * H2, Wp(h, 3), 2 * H2, dZ, 2 * C, false, nullptr, false, true);
     dz_finish(s, dZ, dv, ldv, T, B, C, h->d_sc, train, SH(h, dZ).hi, SH(h, dZ).lo, SH(h, dv).hi, SH(h, dv).lo);
-    gemm(h, false, false, C, H1, R, dZ, 2 * C, h1 + (size_t)B * H1, H1, Gp(h, 5), H1, false, nullptr);            // dWf
+    gemm(h, false, false, C, H1, R, dZ, 2 * C, h1 + (size_t)B * H1, H1, Gp(h, 5), H1, false, nullptr, false, true);            // dWf
     gemm(h, true, false, R, H1, C, dZ, 2 * C, Wp(h, 5), H1, dh1, H1, false, nullptr);                             // dh1 = dq * Wf'
-    gemm(h, false, false, C, LRCN_F_CNN, B, dv, ldv, X, LRCN_F_CNN, Gp(h, 6), LRCN_F_CNN, false, nullptr);        // dWcnn = X' * dv
+    gemm(h, false, false, C, LRCN_F_CNN, B, dv, ldv, X, LRCN_F_CNN, Gp(h, 6), LRCN_F_CNN, false, nullptr, false, true);        // dWcnn = X' * dv
   } else {
     float *dhrec = WS(h, o.dhrec1), *dc = WS(h, o.dc1);
     lstm_layer_bwd(h, 1, T, B, acts1, c1, dh1, dhrec, dc);
-    gemm(h, false, false, 4 * H1, E, R, acts1, 4 * H1, Eall, E, Gp(h, 1), E + H1, false, nullptr);
-    gemm(h, false, false, 4 * H1, H1, R, acts1, 4 * H1, h1, H1, Gp(h, 1) + E, E + H1, false, nullptr);
-    colsum(s, acts1, 4 * H1, R, 4 * H1, Gp(h, 2), false);
-    gemm(h, true, false, R, E, 4 * H1, acts1, 4 * H1, Wp(h, 1), E + H1, dE, E, false, nullptr);
-    cudaMemsetAsync(Gp(h, 7), 0, h->nel[6] * 4, s);
+    gemm(h, false, false, 4 * H1, E, R, acts1, 4 * H1, Eall, E, Gp(h, 1), E + H1, false, nullptr, false, true);
+    gemm(h, false, false, 4 * H1, H1, R, acts1, 4 * H1, h1, H1, Gp(h, 1) + E, E + H1, false, nullptr, false, true);
+    colsum(s, acts1, 4 * H1, R, 4 * H1, Gp(h, 2), true);
+    gemm(h, true, false, R, E, 4 * H1, acts1, 4 * H1, Wp(h, 1), E + H1, dE, E, false, nullptr, false, true);
     scatter_add_embed(s, Gp(h, 7), h->d_tok_in, dE, R, E, h->d_sc, train);                                         // adjoint of Wemb[idx,:]
   }
 }
@@ -1137,6 +1151,39 @@ extern "C" int lrcn_test_gemm(lrcn_handle* h, int precision, int a_kmajor, int b
   }
   CKT(cudaStreamSynchronize(h->stream));
   CKT(cudaMemcpy(C, dC, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
+  cleanup();
+  return LRCN_OK;
+}
+
+extern "C" int lrcn_test_gemm_time(lrcn_handle* h, int a_kmajor, int b_kmajor, int M, int N, int K, int with_shadow_out, int iters, int dbg,
+                                   float* avg_ms_out) {
+  if (!h || !avg_ms_out || M <= 0 || N <= 0 || K <= 0 || iters < 1) return fail(LRCN_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  g_counter = &h->counter;
+  const int lda = ((a_kmajor ? K : M) + 7) / 8 * 8, ldb = ((b_kmajor ? K : N) + 7) / 8 * 8, ldc = (N + 7) / 8 * 8;
+  const size_t na = (size_t)(a_kmajor ? M : K) * lda, nb = (size_t)(b_kmajor ? N : K) * ldb, nc = (size_t)M * ldc;
+  float* dC = nullptr;
+  bf16 *ah = nullptr, *al = nullptr, *bh = nullptr, *bl = nullptr, *ch = nullptr, *cl = nullptr;
+  int rc = LRCN_OK;
+  auto cleanup = [&] { for (void* p : {(void*)dC, (void*)ah, (void*)al, (void*)bh, (void*)bl, (void*)ch, (void*)cl}) if (p) cudaFree(p); g_gemm_dbg = 0; };
+  CKT(cudaMalloc(&dC, nc * 4)); CKT(cudaMalloc(&ah, na * 2)); CKT(cudaMalloc(&al, na * 2)); CKT(cudaMalloc(&bh, nb * 2)); CKT(cudaMalloc(&bl, nb * 2));
+  if (with_shadow_out) { CKT(cudaMalloc(&ch, nc * 2)); CKT(cudaMalloc(&cl, nc * 2)); }
+  CKT(cudaMemset(ah, 0x3c, na * 2)); CKT(cudaMemset(al, 0x38, na * 2)); CKT(cudaMemset(bh, 0x3c, nb * 2)); CKT(cudaMemset(bl, 0x38, nb * 2));
+  g_gemm_dbg = dbg;
+  for (int i = -2; i < iters; i++) {
+    if (i == 0) CKT(cudaEventRecord(h->ev0, h->stream));
+    if (!gemm_bf16x3(h->stream, a_kmajor, b_kmajor, M, N, K, ah, al, lda, bh, bl, ldb, dC, ldc, false, nullptr, ch, cl)) {
+      rc = fail(LRCN_ERR_CUDA, "%s", gemm_bf16x3_last_error());
+      cudaStreamSynchronize(h->stream);
+      cleanup();
+      return rc;
+    }
+  }
+  CKT(cudaEventRecord(h->ev1, h->stream));
+  CKT(cudaEventSynchronize(h->ev1));
+  float ms = 0.f;
+  CKT(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  *avg_ms_out = ms / iters;
   cleanup();
   return LRCN_OK;
 }

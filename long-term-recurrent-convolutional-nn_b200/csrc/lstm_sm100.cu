@@ -557,13 +557,21 @@ lstm_fwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *sm.tmem_slot;
 
+  // Resident weights, loaded once.  They are written by the weight-prep kernels at the very start of the step, i.e. more
+  // than two launches upstream, so (PDL discipline, kernels.cuh) they are complete before this kernel can start: the load
+  // is issued BEFORE the dependency wait and overlaps the previous kernel's tail.
+  if (warp == 0 && lane == 0) {
+    mbar_expect_tx(sm.wbar, (uint32_t)num_kb * 2 * B_HALF);
+    for (int kb = 0; kb < num_kb; kb++) {
+      tma_load_2d(sm.res + kb * 2 * B_HALF, &tmB_hi, sm.wbar, kb * LBK, nt * NT);
+      tma_load_2d(sm.res + kb * 2 * B_HALF + B_HALF, &tmB_lo, sm.wbar, kb * LBK, nt * NT);
+    }
+  }
+  pdl_wait();
+  pdl_trigger();
+
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(sm.wbar, (uint32_t)num_kb * 2 * B_HALF);  // resident weights: loaded once
-      for (int kb = 0; kb < num_kb; kb++) {
-        tma_load_2d(sm.res + kb * 2 * B_HALF, &tmB_hi, sm.wbar, kb * LBK, nt * NT);
-        tma_load_2d(sm.res + kb * 2 * B_HALF + B_HALF, &tmB_lo, sm.wbar, kb * LBK, nt * NT);
-      }
       int it = 0;
       for (int t = 1; t < T; t++) {
         grid_wait(ctr, (unsigned int)t * ctas_per_mtile);  // h_{t-1} rows of this m-tile are complete in global memory
@@ -726,13 +734,18 @@ lstm_bwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *sm.tmem_slot;
 
+  if (warp == 0 && lane == 0 && nkb > 0) {  // resident weights before the dependency wait (see lstm_fwd_seq_kernel)
+    mbar_expect_tx(sm.wbar, (uint32_t)nkb * 2 * B_HALF);
+    for (int i = 0; i < nkb; i++) {
+      tma_load_2d(sm.res + i * 2 * B_HALF, &tmB_hi, sm.wbar, (kb_begin + i) * LBK, nt * NT);
+      tma_load_2d(sm.res + i * 2 * B_HALF + B_HALF, &tmB_lo, sm.wbar, (kb_begin + i) * LBK, nt * NT);
+    }
+  }
+  pdl_wait();
+  pdl_trigger();
+
   if (warp == 0) {
     if (lane == 0 && nkb > 0) {
-      mbar_expect_tx(sm.wbar, (uint32_t)nkb * 2 * B_HALF);
-      for (int i = 0; i < nkb; i++) {
-        tma_load_2d(sm.res + i * 2 * B_HALF, &tmB_hi, sm.wbar, (kb_begin + i) * LBK, nt * NT);
-        tma_load_2d(sm.res + i * 2 * B_HALF + B_HALF, &tmB_lo, sm.wbar, (kb_begin + i) * LBK, nt * NT);
-      }
       int it = 0;
       for (int t = T - 2; t >= 0; t--) {
         grid_wait(ctr, (unsigned int)(T - 1 - t) * ctas_per_mtile);  // dG_{t+1} rows of this m-tile are complete
@@ -1038,8 +1051,7 @@ bool lstm_fwd_seq(cudaStream_t s, int B, int H, int T, const __nv_bfloat16* wper
   if (!get_tensor_map_bf16(&ta_hi, hs_hi, H, R, H, LM / CL) || !get_tensor_map_bf16(&ta_lo, hs_lo, H, R, H, LM / CL)) return false;
   SeqParams p{};
   p.B = B; p.H = H; p.T = T; p.num_kb = num_kb; p.acts = acts; p.hs = hs; p.cs = cs; p.o_hi = hs_hi; p.o_lo = hs_lo; p.counters = counters; p.trace = trace;
-  cudaMemsetAsync(counters, 0, 32 * sizeof(unsigned int), s);
-  lstm_fwd_seq_kernel<<<grid, L_THREADS, seq_smem_bytes(num_kb, false), s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  launch_pdl(lstm_fwd_seq_kernel, grid, dim3(L_THREADS), seq_smem_bytes(num_kb, false), s, ta_hi, ta_lo, tb_hi, tb_lo, p);
   if (g_counter) g_counter->n++;
   *launched = true;
   return check_launch("lstm_fwd_seq launch");
@@ -1062,8 +1074,7 @@ bool lstm_bwd_seq(cudaStream_t s, int B, int H, int T, const __nv_bfloat16* wt_h
   SeqParams p{};
   p.B = B; p.H = H; p.T = T; p.num_kb = num_kb; p.acts = acts; p.cs = cs; p.o_hi = acts_hi; p.o_lo = acts_lo; p.dh_all = dh_all; p.dc = dc;
   p.counters = counters;
-  cudaMemsetAsync(counters, 0, 32 * sizeof(unsigned int), s);
-  lstm_bwd_seq_kernel<<<grid, L_THREADS, seq_smem_bytes(kb_per, true), s>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  launch_pdl(lstm_bwd_seq_kernel, grid, dim3(L_THREADS), seq_smem_bytes(kb_per, true), s, ta_hi, ta_lo, tb_hi, tb_lo, p);
   if (g_counter) g_counter->n++;
   *launched = true;
   return check_launch("lstm_bwd_seq launch");

@@ -121,6 +121,20 @@ __device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
 }
 
+// ---- TMA stores (smem -> global), bulk async-group completion
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 #define LRCN_TMEM_LD_32(taddr, v)                                                                                  \
   asm volatile(                                                                                                    \
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18," \
@@ -142,6 +156,38 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
 
 // host: cached 2-D bf16 tensor maps (row-major [outer][inner], pitch ld elements, box {64, box_outer}, SWIZZLE_128B)
 bool get_tensor_map_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer);
+// fp32 output map for the TMA-store epilogue: row-major [outer][inner], pitch ld floats (multiple of 4), box {32, 32}, SWIZZLE_128B
+bool get_tensor_map_f32_out(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld);
+
+// Epilogue of one 32-row x 32-column accumulator chunk through a TMA store (or TMA reduce-add for split-K partial sums):
+// lane r holds row r (v[0..31]); `buf` is this warp's 4 KiB, 1024 B-aligned staging buffer for this chunk parity.
+// At most one older bulk group of this thread may still be reading the other buffer.
+__device__ __forceinline__ void epilogue_chunk_tma(const CUtensorMap* tmC, uint32_t buf, const uint32_t (&v)[32], float bias_lane, bool has_bias,
+                                                   int col0, int row0, bool reduce, int lane) {
+  if (lane == 0) ptx::bulk_wait_read<1>();
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    float x0 = __uint_as_float(v[4 * q]), x1 = __uint_as_float(v[4 * q + 1]), x2 = __uint_as_float(v[4 * q + 2]), x3 = __uint_as_float(v[4 * q + 3]);
+    if (has_bias) {
+      x0 += __shfl_sync(0xffffffffu, bias_lane, 4 * q);
+      x1 += __shfl_sync(0xffffffffu, bias_lane, 4 * q + 1);
+      x2 += __shfl_sync(0xffffffffu, bias_lane, 4 * q + 2);
+      x3 += __shfl_sync(0xffffffffu, bias_lane, 4 * q + 3);
+    }
+    // SWIZZLE_128B: 16-byte chunk q of row r lives at chunk (q ^ (r & 7)) -> the 8 lanes of a store phase hit 8 distinct bank groups
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(buf + (uint32_t)lane * 128u + (uint32_t)((q ^ (lane & 7)) << 4)), "f"(x0), "f"(x1),
+                 "f"(x2), "f"(x3)
+                 : "memory");
+  }
+  ptx::fence_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    if (reduce) ptx::tma_reduce_add_2d(tmC, buf, col0, row0);
+    else ptx::tma_store_2d(tmC, buf, col0, row0);
+    ptx::bulk_commit();
+  }
+}
 void set_sm100_error(const char* msg);
 
 }  // namespace lrcn

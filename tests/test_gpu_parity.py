@@ -55,6 +55,27 @@ def test_gemm_kernels(prec, aK, bK, M, N, K):
         assert relerr(out, ref + bias + C0) < 2e-5
 
 
+@pytest.mark.parametrize("aK,bK", [(1, 1), (1, 0), (0, 0), (0, 1)])
+@pytest.mark.parametrize("M,N,K", [(1344, 2056, 512),   # CTA-pair kernel, whole 256x256 tiles, ragged N (TMA store clips)
+                                   (1000, 500, 3840),   # CTA-pair kernel, stream-K: partial tiles summed by TMA reduce-add
+                                   (1536, 520, 4100)])  # stream-K with ragged N and K
+def test_gemm_pair_kernel_and_streamk(aK, bK, M, N, K):
+    if 1 not in PRECS:
+        pytest.skip("bf16x3 precision not selected")
+    rs = np.random.RandomState(M + N + K)
+    A = rs.standard_normal((M, K)).astype(np.float32)
+    B = rs.standard_normal((K, N)).astype(np.float32)
+    bias = rs.standard_normal(N).astype(np.float32)
+    C0 = rs.standard_normal((M, N)).astype(np.float32)
+    ref = A.astype(np.float64) @ B.astype(np.float64)
+    Ain = A if aK else np.ascontiguousarray(A.T)
+    Bin = np.ascontiguousarray(B.T) if bK else B
+    with open_handle(64, 64, 64, 100, 4, 2, 1, 4) as h:
+        assert relerr(h.test_gemm(1, aK, bK, Ain, Bin), ref) < 2e-5
+        assert relerr(h.test_gemm(1, aK, bK, Ain, Bin, bias, None), ref + bias) < 2e-5
+        assert relerr(h.test_gemm(1, aK, bK, Ain, Bin, bias, C0), ref + bias + C0) < 2e-5
+
+
 @pytest.mark.parametrize("prec", PRECS)
 def test_param_roundtrip_bit_exact(prec):
     E, H1, H2, V = 24, 16, 32, 57

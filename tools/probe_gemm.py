@@ -41,7 +41,7 @@ if __name__ == "__main__":
     if "--2cta" in sys.argv:
         envs = [{"LRCN_GEMM_2CTA": "1"}]
     if "--quick" in sys.argv:
-        shapes = [(200, 136, 520), (1344, 8000, 512), (1000, 500, 7731), (3328, 2048, 512), (257, 300, 64)]
+        shapes = [(200, 136, 520), (1344, 8000, 512), (1000, 500, 7731), (3328, 2048, 512), (257, 300, 64), (1536, 520, 4096), (3328, 512, 7731)]
     for env in envs:
         print("== env", env, flush=True)
         for prec in (0, 1):
