@@ -71,6 +71,7 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
 struct Gemm2Params {
   int M, N, K;
   int tiles_mp, tiles_n;  // tiles_mp: pairs of 128-row tiles
+  int n_split;            // > 0: B is the column concatenation [B1 | B2]; tiles with n0 >= n_split read B2 (at n0 - n_split)
   int streamk;            // 0: whole 256x256 tiles round-robin; 1: every CTA pair owns an equal contiguous range of (tile, k-block) iterations
   float* C; int ldc;
   const float* bias;
@@ -115,6 +116,7 @@ template <bool AK, bool BKM>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::NUM_THREADS, 1)
 gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                    const __grid_constant__ CUtensorMap tmB2_hi, const __grid_constant__ CUtensorMap tmB2_lo,
                     const __grid_constant__ CUtensorMap tmC, const Gemm2Params p) {
   using namespace g2;
   extern __shared__ uint8_t smem_raw[];
@@ -142,6 +144,7 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   }
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmA_lo); prefetch_tensormap(&tmB_hi); prefetch_tensormap(&tmB_lo);
+    if (p.n_split > 0) { prefetch_tensormap(&tmB2_hi); prefetch_tensormap(&tmB2_lo); }
   }
   if (warp == 1) tmem_alloc2(smem_u32(tmem_slot));
   tc_fence_before();
@@ -161,7 +164,11 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       while (si.next(sg)) {
         const int rem = sg.tile;
         const int m0 = ((rem % p.tiles_mp) * 2 + rank) * BM;
-        const int nh0 = (rem / p.tiles_mp) * BNP + rank * BNH;  // this CTA's half of the B tile
+        int nh0 = (rem / p.tiles_mp) * BNP + rank * BNH;  // this CTA's half of the B tile
+        const bool second = p.n_split > 0 && nh0 >= p.n_split;
+        if (second) nh0 -= p.n_split;
+        const CUtensorMap* mB_hi = second ? &tmB2_hi : &tmB_hi;
+        const CUtensorMap* mB_lo = second ? &tmB2_lo : &tmB_lo;
         const int kb_begin = sg.kb0, kb_end = sg.kb1;
         for (int kb = kb_begin; kb < kb_end; kb++, it++) {
           const int s = it % STAGES;
@@ -186,13 +193,13 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             }
           }
           if (BKM) {
-            tma_load_2d_2sm(sB_hi, &tmB_hi, full, k0, nh0);
-            tma_load_2d_2sm(sB_lo, &tmB_lo, full, k0, nh0);
+            tma_load_2d_2sm(sB_hi, mB_hi, full, k0, nh0);
+            tma_load_2d_2sm(sB_lo, mB_lo, full, k0, nh0);
           } else {
 #pragma unroll
             for (int b = 0; b < 2; b++) {
-              tma_load_2d_2sm(sB_hi + b * 8192, &tmB_hi, full, nh0 + 64 * b, k0);
-              tma_load_2d_2sm(sB_lo + b * 8192, &tmB_lo, full, nh0 + 64 * b, k0);
+              tma_load_2d_2sm(sB_hi + b * 8192, mB_hi, full, nh0 + 64 * b, k0);
+              tma_load_2d_2sm(sB_lo + b * 8192, mB_lo, full, nh0 + 64 * b, k0);
             }
           }
         }
@@ -346,6 +353,7 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 }
 
 static int g2_num_sms = 148;
+static bool g_gemm2_ready = false;
 int g_gemm_dbg = 0;
 bool init_gemm2_sm100() {
   using namespace g2;
@@ -357,13 +365,15 @@ bool init_gemm2_sm100() {
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g2_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  g_gemm2_ready = true;
   return true;
 }
 
 // same contract as gemm_bf16x3 (kernels.cuh); the caller decides when the pair kernel pays off
-bool gemm2_bf16x3(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo,
-                  int lda, const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, int ldb, float* C, int ldc, bool beta, const float* bias,
-                  __nv_bfloat16* C_hi, __nv_bfloat16* C_lo, bool c_zeroed) {
+static bool gemm2_launch(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo,
+                         int lda, const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, int ldb, int n_split, const __nv_bfloat16* B2_hi,
+                         const __nv_bfloat16* B2_lo, int ldb2, float* C, int ldc, bool beta, const float* bias, __nv_bfloat16* C_hi,
+                         __nv_bfloat16* C_lo, bool c_zeroed) {
   using namespace g2;
   if (M <= 0 || N <= 0 || K <= 0) return true;
   const int tm = (M + BM - 1) / BM, tmp = (tm + 1) / 2, tn = (N + BNP - 1) / BNP;
@@ -385,8 +395,14 @@ bool gemm2_bf16x3(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, in
   bool ok = true;
   if (a_kmajor) ok = ok && get_tensor_map_bf16(&ta_hi, A_hi, K, M, lda, BM) && get_tensor_map_bf16(&ta_lo, A_lo, K, M, lda, BM);
   else          ok = ok && get_tensor_map_bf16(&ta_hi, A_hi, M, K, lda, BK) && get_tensor_map_bf16(&ta_lo, A_lo, M, K, lda, BK);
-  if (b_kmajor) ok = ok && get_tensor_map_bf16(&tb_hi, B_hi, K, N, ldb, BNH) && get_tensor_map_bf16(&tb_lo, B_lo, K, N, ldb, BNH);
-  else          ok = ok && get_tensor_map_bf16(&tb_hi, B_hi, N, K, ldb, BK) && get_tensor_map_bf16(&tb_lo, B_lo, N, K, ldb, BK);
+  const int N1 = n_split > 0 ? n_split : N, N2 = N - N1;
+  if (b_kmajor) ok = ok && get_tensor_map_bf16(&tb_hi, B_hi, K, N1, ldb, BNH) && get_tensor_map_bf16(&tb_lo, B_lo, K, N1, ldb, BNH);
+  else          ok = ok && get_tensor_map_bf16(&tb_hi, B_hi, N1, K, ldb, BK) && get_tensor_map_bf16(&tb_lo, B_lo, N1, K, ldb, BK);
+  CUtensorMap tb2_hi = tb_hi, tb2_lo = tb_lo;
+  if (ok && n_split > 0) {
+    if (b_kmajor) ok = get_tensor_map_bf16(&tb2_hi, B2_hi, K, N2, ldb2, BNH) && get_tensor_map_bf16(&tb2_lo, B2_lo, K, N2, ldb2, BNH);
+    else          ok = get_tensor_map_bf16(&tb2_hi, B2_hi, N2, K, ldb2, BK) && get_tensor_map_bf16(&tb2_lo, B2_lo, N2, K, ldb2, BK);
+  }
   if (!ok) return false;
   const bool tma_epi = gemm_tma_epilogue_ok(C, ldc, beta, C_hi);
   CUtensorMap tc = ta_hi;
@@ -396,17 +412,36 @@ bool gemm2_bf16x3(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, in
     else cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, s);
   }
   Gemm2Params p;
-  p.M = M; p.N = N; p.K = K; p.tiles_mp = tmp; p.tiles_n = tn; p.streamk = streamk ? 1 : 0;
+  p.M = M; p.N = N; p.K = K; p.tiles_mp = tmp; p.tiles_n = tn; p.streamk = streamk ? 1 : 0; p.n_split = n_split;
   p.C = C; p.ldc = ldc; p.bias = bias; p.beta = beta ? 1 : 0; p.C_hi = C_hi; p.C_lo = C_lo; p.dbg = g_gemm_dbg; p.tma_epi = tma_epi ? 1 : 0;
   const int grid = ncl * 2;
-  if (a_kmajor && b_kmajor) launch_pdl(gemm2_bf16x3_kernel<true, true>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, s, ta_hi, ta_lo, tb_hi, tb_lo, tc, p);
-  else if (a_kmajor && !b_kmajor) launch_pdl(gemm2_bf16x3_kernel<true, false>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, s, ta_hi, ta_lo, tb_hi, tb_lo, tc, p);
-  else if (!a_kmajor && b_kmajor) launch_pdl(gemm2_bf16x3_kernel<false, true>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, s, ta_hi, ta_lo, tb_hi, tb_lo, tc, p);
-  else launch_pdl(gemm2_bf16x3_kernel<false, false>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, s, ta_hi, ta_lo, tb_hi, tb_lo, tc, p);
+  if (a_kmajor && b_kmajor) launch_pdl(gemm2_bf16x3_kernel<true, true>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, s, ta_hi, ta_lo, tb_hi, tb_lo, tb2_hi, tb2_lo, tc, p);
+  else if (a_kmajor && !b_kmajor) launch_pdl(gemm2_bf16x3_kernel<true, false>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, s, ta_hi, ta_lo, tb_hi, tb_lo, tb2_hi, tb2_lo, tc, p);
+  else if (!a_kmajor && b_kmajor) launch_pdl(gemm2_bf16x3_kernel<false, true>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, s, ta_hi, ta_lo, tb_hi, tb_lo, tb2_hi, tb2_lo, tc, p);
+  else launch_pdl(gemm2_bf16x3_kernel<false, false>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, s, ta_hi, ta_lo, tb_hi, tb_lo, tb2_hi, tb2_lo, tc, p);
   if (g_counter) g_counter->n++;
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) { set_sm100_error((std::string("gemm2_bf16x3 launch: ") + cudaGetErrorString(e)).c_str()); return false; }
   return true;
+}
+
+bool gemm2_bf16x3(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo,
+                  int lda, const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, int ldb, float* C, int ldc, bool beta, const float* bias,
+                  __nv_bfloat16* C_hi, __nv_bfloat16* C_lo, bool c_zeroed) {
+  return gemm2_launch(s, a_kmajor, b_kmajor, M, N, K, A_hi, A_lo, lda, B_hi, B_lo, ldb, 0, nullptr, nullptr, 0, C, ldc, beta, bias, C_hi, C_lo,
+                      c_zeroed);
+}
+
+// C[M][N1+N2] = A * [B1 | B2]: two B operands sharing A (the x-part and h-part of an LSTM weight gradient) in ONE launch.
+// Applies when the split falls on a tile boundary; returns false WITHOUT launching otherwise (the caller issues two GEMMs).
+bool gemm2_bf16x3_dualB(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N1, int N2, int K, const __nv_bfloat16* A_hi,
+                        const __nv_bfloat16* A_lo, int lda, const __nv_bfloat16* B1_hi, const __nv_bfloat16* B1_lo, int ldb1,
+                        const __nv_bfloat16* B2_hi, const __nv_bfloat16* B2_lo, int ldb2, float* C, int ldc, bool c_zeroed, bool* launched) {
+  *launched = false;
+  if (!g_gemm2_ready || N1 <= 0 || N2 <= 0 || (N1 % g2::BNP) != 0 || M < 256) return true;
+  *launched = true;
+  return gemm2_launch(s, a_kmajor, b_kmajor, M, N1 + N2, K, A_hi, A_lo, lda, B1_hi, B1_lo, ldb1, N1, B2_hi, B2_lo, ldb2, C, ldc, false, nullptr,
+                      nullptr, nullptr, c_zeroed);
 }
 
 }  // namespace lrcn

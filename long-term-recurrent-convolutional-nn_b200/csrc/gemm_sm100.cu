@@ -405,7 +405,7 @@ static int env_int(const char* name, int dflt) {
 }
 static int g_num_sms = 148, g_force_bn = 0, g_force_cm = 0, g_two_cta = 1;
 int g_gemm_tma_epi = 1;
-int g_pdl = 1;  // LRCN_GEMM_TMA_EPI=0 keeps the LSU epilogue everywhere
+int g_pdl = 1;  // measured (profiles/r01_progress.md): PDL on the tcgen05 kernels gains 1.3 %, adding the small SIMT kernels loses 2 %  // LRCN_GEMM_TMA_EPI=0 keeps the LSU epilogue everywhere
 
 bool gemm_tma_epilogue_ok(const float* C, int ldc, bool beta, const void* C_hi) {
   (void)beta;  // beta = accumulate into C = TMA reduce-add

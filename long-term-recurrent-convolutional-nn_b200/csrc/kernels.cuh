@@ -31,13 +31,13 @@ extern int g_pdl;
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-template <typename... KArgs, typename... Args>
+template <int LEVEL = 1, typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = g_pdl >= LEVEL ? 1 : 0;  // LRCN_PDL: 0 off, 1 tcgen05 kernels (default), 2 all
   cfg.attrs = attr; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
@@ -73,6 +73,11 @@ void lstm_cell_bwd(cudaStream_t s, float* gates, const float* c_prev, const floa
 void softmax_ce(cudaStream_t s, float* logits, int ld, int R, int V, const int* tgt, float* rowlp,
                 const StepScalars* sc, bool train, __nv_bfloat16* hi = nullptr, __nv_bfloat16* lo = nullptr,
                 double* total_out = nullptr /* fp64 sum of rowlp, written by the last CTA */, unsigned int* done_ctr = nullptr);
+// bf16x3 training variant: writes only the bf16 hi/lo split of dA and folds the output-bias gradient (column sums of dA) in;
+// colpart: scratch [colpart_rows][ld]; dbias must be zero on entry.  Returns false (nothing launched) if it does not apply.
+bool softmax_ce_fused(cudaStream_t s, const float* logits, int ld, int R, int V, const int* tgt, float* rowlp, const StepScalars* sc,
+                      __nv_bfloat16* hi, __nv_bfloat16* lo, float* colpart, int colpart_rows, float* dbias, double* total_out,
+                      unsigned int* done_ctr);
 void reduce_sum_double(cudaStream_t s, const float* x, int n, double* out);
 void colsum(cudaStream_t s, const float* A, int ld, int R, int N, float* out, bool accumulate);
 // dZ *= dropout mask (site 1); dv[i][j] = sum_t dZ[(t*B+i)][C+j]
@@ -130,6 +135,9 @@ extern int g_gemm_dbg;  // diagnostics for lrcn_bench_gemm only (0 in production
 bool gemm2_bf16x3(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo,
                   int lda, const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, int ldb, float* C, int ldc, bool beta, const float* bias,
                   __nv_bfloat16* C_hi, __nv_bfloat16* C_lo, bool c_zeroed = false);
+bool gemm2_bf16x3_dualB(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N1, int N2, int K, const __nv_bfloat16* A_hi,
+                        const __nv_bfloat16* A_lo, int lda, const __nv_bfloat16* B1_hi, const __nv_bfloat16* B1_lo, int ldb1,
+                        const __nv_bfloat16* B2_hi, const __nv_bfloat16* B2_lo, int ldb2, float* C, int ldc, bool c_zeroed, bool* launched);
 void init_simt_kernels();
 
 // ---------------------------------------------------------------- fused LSTM timestep (lstm_sm100.cu)

@@ -165,6 +165,8 @@ void sgemm(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int K, co
 // ------------------------------------------------------------------------------------------
 __global__ void gather_features_kernel(const float4* __restrict__ table, const int* __restrict__ rows, float4* __restrict__ X,
                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  pdl_wait();  // PDL: launched while the previous kernel drains (kernels.cuh)
+  pdl_trigger();
   int i = blockIdx.x;
   const float4* src = table + (size_t)rows[i] * 1024;
   float4* dst = X + (size_t)i * 1024;
@@ -175,13 +177,15 @@ __global__ void gather_features_kernel(const float4* __restrict__ table, const i
   }
 }
 void gather_features(cudaStream_t s, const float* table, const int* rows, int B, float* X, __nv_bfloat16* hi, __nv_bfloat16* lo) {
-  gather_features_kernel<<<B, 256, 0, s>>>((const float4*)table, rows, (float4*)X, hi, lo);
+  launch_pdl<2>(gather_features_kernel, dim3(B), dim3(256), 0, s, (const float4*)table, rows, (float4*)X, hi, lo);
   count_launch();
 }
 
 __global__ void gather_embed_kernel(const float* __restrict__ W, const int* __restrict__ tok, int R, int E, int ldo,
                                     float* __restrict__ out, const StepScalars* __restrict__ sc, int train,
                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  pdl_wait();  // PDL: launched while the previous kernel drains (kernels.cuh)
+  pdl_trigger();
   int r = blockIdx.x;
   const float* src = W + (size_t)tok[r] * E;
   float* dst = out + (size_t)r * ldo;
@@ -194,12 +198,14 @@ __global__ void gather_embed_kernel(const float* __restrict__ W, const int* __re
 }
 void gather_embed(cudaStream_t s, const float* WembT, const int* tok, int R, int E, float* out, const StepScalars* sc,
                   bool train, __nv_bfloat16* hi, __nv_bfloat16* lo, int ldo) {
-  gather_embed_kernel<<<R, 128, 0, s>>>(WembT, tok, R, E, ldo > 0 ? ldo : E, out, sc, train ? 1 : 0, hi, lo);
+  launch_pdl<2>(gather_embed_kernel, dim3(R), dim3(128), 0, s, WembT, tok, R, E, ldo > 0 ? ldo : E, out, sc, train ? 1 : 0, hi, lo);
   count_launch();
 }
 
 __global__ void z_finish_kernel(float* __restrict__ Z, const float* __restrict__ v, int ldv, int R, int B, int C, int ldz,
                                 const StepScalars* __restrict__ sc, int train, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  pdl_wait();  // PDL: launched while the previous kernel drains (kernels.cuh)
+  pdl_trigger();
   int r = blockIdx.x;
   int i = B > 0 ? r % B : r / (-B);  // B<0: generation, image index = row / beam_width
   float* z = Z + (size_t)r * ldz;
@@ -212,7 +218,7 @@ __global__ void z_finish_kernel(float* __restrict__ Z, const float* __restrict__
 }
 void z_finish(cudaStream_t s, float* Z, const float* v, int ldv, int R, int B, int C, const StepScalars* sc, bool train,
               __nv_bfloat16* hi, __nv_bfloat16* lo, int ldz) {
-  z_finish_kernel<<<R, 128, 0, s>>>(Z, v, ldv, R, B, C, ldz > 0 ? ldz : 2 * C, sc, train ? 1 : 0, hi, lo);
+  launch_pdl<2>(z_finish_kernel, dim3(R), dim3(128), 0, s, Z, v, ldv, R, B, C, ldz > 0 ? ldz : 2 * C, sc, train ? 1 : 0, hi, lo);
   count_launch();
 }
 
@@ -311,6 +317,8 @@ __global__ void __launch_bounds__(512) softmax_ce_kernel(float* __restrict__ log
                                                          float* __restrict__ rowlp, const StepScalars* __restrict__ sc, int train,
                                                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                                          double* __restrict__ total_out, unsigned int* __restrict__ done_ctr) {
+  pdl_wait();  // PDL: launched while the previous kernel drains (kernels.cuh)
+  pdl_trigger();
   extern __shared__ __align__(16) float row[];
   __shared__ float red[32];
   __shared__ double dred[16];
@@ -378,8 +386,125 @@ __global__ void __launch_bounds__(512) softmax_ce_kernel(float* __restrict__ log
 void softmax_ce(cudaStream_t s, float* logits, int ld, int R, int V, const int* tgt, float* rowlp, const StepScalars* sc,
                 bool train, __nv_bfloat16* hi, __nv_bfloat16* lo, double* total_out, unsigned int* done_ctr) {
   size_t smem = (size_t)ld * sizeof(float);
-  softmax_ce_kernel<<<R, 512, smem, s>>>(logits, ld, V, tgt, rowlp, sc, train ? 1 : 0, hi, lo, total_out, done_ctr);
+  launch_pdl<2>(softmax_ce_kernel, dim3(R), dim3(512), smem, s, logits, ld, V, tgt, rowlp, sc, train ? 1 : 0, hi, lo, total_out, done_ctr);
   count_launch();
+}
+
+// ------------------------------------------------------------------------------------------
+// Training variant for the bf16x3 mode: persistent CTAs walk over rows with the row in REGISTERS, write only the bf16
+// hi/lo split of dA = (softmax - onehot)/N (the fp32 dA is never needed: both consumers are tcgen05 GEMMs) and keep the
+// column sums of dA (= the output-bias gradient) in registers, so the separate 100 MB column-sum pass disappears.
+// colpart [gridDim.x][ld] receives one partial column sum per CTA; a (tiny) colsum over those rows finishes dbout.
+// ------------------------------------------------------------------------------------------
+template <int NV4>
+__global__ void __launch_bounds__(512, NV4 <= 4 ? 2 : 1)
+softmax_ce_fused_kernel(const float* __restrict__ logits, int ld, int V, int R, const int* __restrict__ tgt, float* __restrict__ rowlp,
+                        const StepScalars* __restrict__ sc, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                        float* __restrict__ colpart, double* __restrict__ total_out, unsigned int* __restrict__ done_ctr) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float red[32];
+  __shared__ double dred[16];
+  __shared__ int is_last;
+  const int ld4 = ld >> 2;
+  const float inv = sc->inv_ntok;
+  float4 acc[NV4];
+#pragma unroll
+  for (int i = 0; i < NV4; i++) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = blockIdx.x; r < R; r += gridDim.x) {
+    const float* a = logits + (size_t)r * ld;
+    float4 x[NV4];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NV4; i++) {
+      const int q = threadIdx.x + 512 * i;
+      x[i] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      if (q < ld4) {
+        x[i] = *reinterpret_cast<const float4*>(a + 4 * q);
+        const int j = 4 * q;  // padding columns [V, ld) do not take part
+        if (j + 1 >= V) x[i].y = -INFINITY;
+        if (j + 2 >= V) x[i].z = -INFINITY;
+        if (j + 3 >= V) x[i].w = -INFINITY;
+        if (j >= V) x[i].x = -INFINITY;
+      }
+      mx = fmaxf(fmaxf(mx, fmaxf(x[i].x, x[i].y)), fmaxf(x[i].z, x[i].w));
+    }
+    mx = block_max(mx, red);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV4; i++) sum += (expf(x[i].x - mx) + expf(x[i].y - mx)) + (expf(x[i].z - mx) + expf(x[i].w - mx));
+    sum = block_sum(sum, red);
+    const float lse = logf(sum);
+    const int y = tgt[r];
+    const size_t base = (size_t)r * ld;
+#pragma unroll
+    for (int i = 0; i < NV4; i++) {
+      const int q = threadIdx.x + 512 * i;
+      if (q < ld4) {
+        const int j = 4 * q;
+        float p[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          float v = 0.f;
+          if (j + e < V) {
+            const float lp = (p[e] - mx) - lse;
+            if (j + e == y) rowlp[r] = lp;
+            v = expf(lp);
+            if (j + e == y) v -= 1.0f;
+            v *= inv;
+          }
+          p[e] = v;
+        }
+        const float4 o = make_float4(p[0], p[1], p[2], p[3]);
+        store_split4(hi, lo, base + 4 * q, o);
+        acc[i].x += o.x; acc[i].y += o.y; acc[i].z += o.z; acc[i].w += o.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV4; i++) {
+    const int q = threadIdx.x + 512 * i;
+    if (q < ld4) *reinterpret_cast<float4*>(colpart + (size_t)blockIdx.x * ld + 4 * q) = acc[i];
+  }
+  if (total_out) {  // deterministic fp64 total of the row log-probs by the last CTA (as in softmax_ce_kernel)
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned int prev = atomicAdd(done_ctr, 1u);
+      is_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      double t = 0.0;
+      for (int i = threadIdx.x; i < R; i += blockDim.x) t += (double)__ldcg(rowlp + i);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if ((threadIdx.x & 31) == 0) dred[threadIdx.x >> 5] = t;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double tt = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) tt += dred[w];
+        *total_out = tt;
+        *done_ctr = 0u;
+      }
+    }
+  }
+}
+bool softmax_ce_fused(cudaStream_t s, const float* logits, int ld, int R, int V, const int* tgt, float* rowlp, const StepScalars* sc,
+                      __nv_bfloat16* hi, __nv_bfloat16* lo, float* colpart, int colpart_rows, float* dbias, double* total_out,
+                      unsigned int* done_ctr) {
+  const int nv4 = ((ld >> 2) + 511) / 512;
+  if (nv4 > 8 || (ld & 3) || !hi || !colpart) return false;
+  int grid = R < colpart_rows ? R : colpart_rows;
+#define LRCN_SMX(NV) launch_pdl<2>(softmax_ce_fused_kernel<NV>, dim3(grid), dim3(512), 0, s, logits, ld, V, R, tgt, rowlp, sc, hi, lo, colpart, total_out, done_ctr)
+  if (nv4 <= 2) LRCN_SMX(2);
+  else if (nv4 <= 4) LRCN_SMX(4);
+  else if (nv4 <= 6) { if (grid > colpart_rows / 2) grid = colpart_rows / 2; LRCN_SMX(6); }
+  else { if (grid > colpart_rows / 2) grid = colpart_rows / 2; LRCN_SMX(8); }
+#undef LRCN_SMX
+  count_launch();
+  colsum(s, colpart, ld, grid, V, dbias, true);  // dbias is zeroed at step start
+  return true;
 }
 
 __global__ void reduce_sum_double_kernel(const float* __restrict__ x, int n, double* __restrict__ out) {
@@ -401,6 +526,8 @@ void reduce_sum_double(cudaStream_t s, const float* x, int n, double* out) {
 
 // out[n] (+)= sum_r A[r][n] ; block = 32 float4-columns x 8 row-lanes, grid.y splits rows (atomic combine)
 __global__ void colsum_kernel(const float* __restrict__ A, int ld, int R, int N, float* __restrict__ out, int rows_per) {
+  pdl_wait();  // PDL: launched while the previous kernel drains (kernels.cuh)
+  pdl_trigger();
   __shared__ float4 red[8][33];
   const int n4 = blockIdx.x * 32 + threadIdx.x;  // float4 column
   const int n = 4 * n4;
@@ -433,13 +560,15 @@ void colsum(cudaStream_t s, const float* A, int ld, int R, int N, float* out, bo
   int gy = 1;
   while (gx * gy < 592 && gy * 32 < R) gy *= 2;
   int rows_per = (R + gy - 1) / gy;
-  colsum_kernel<<<dim3(gx, gy), dim3(32, 8), 0, s>>>(A, ld, R, N, out, rows_per);
+  launch_pdl<2>(colsum_kernel, dim3(gx, gy), dim3(32, 8), 0, s, A, ld, R, N, out, rows_per);
   count_launch();
 }
 
 __global__ void dz_finish_kernel(float* __restrict__ dZ, float* __restrict__ dv, int ldv, int T, int B, int C,
                                  const StepScalars* __restrict__ sc, int train, __nv_bfloat16* __restrict__ z_hi,
                                  __nv_bfloat16* __restrict__ z_lo, __nv_bfloat16* __restrict__ v_hi, __nv_bfloat16* __restrict__ v_lo) {
+  pdl_wait();  // PDL: launched while the previous kernel drains (kernels.cuh)
+  pdl_trigger();
   const int i = blockIdx.x;                                // batch row
   const int j = blockIdx.y * blockDim.x + threadIdx.x;     // column of Z
   if (j >= 2 * C) return;
@@ -460,12 +589,14 @@ __global__ void dz_finish_kernel(float* __restrict__ dZ, float* __restrict__ dv,
 void dz_finish(cudaStream_t s, float* dZ, float* dv, int ldv, int T, int B, int C, const StepScalars* sc, bool train,
                __nv_bfloat16* z_hi, __nv_bfloat16* z_lo, __nv_bfloat16* v_hi, __nv_bfloat16* v_lo) {
   dim3 grid(B, (2 * C + 127) / 128);
-  dz_finish_kernel<<<grid, 128, 0, s>>>(dZ, dv, ldv, T, B, C, sc, train ? 1 : 0, z_hi, z_lo, v_hi, v_lo);
+  launch_pdl<2>(dz_finish_kernel, grid, dim3(128), 0, s, dZ, dv, ldv, T, B, C, sc, train ? 1 : 0, z_hi, z_lo, v_hi, v_lo);
   count_launch();
 }
 
 __global__ void scatter_add_embed_kernel(float* __restrict__ dW, const int* __restrict__ tok, const float* __restrict__ dE, int R,
                                          int E, const StepScalars* __restrict__ sc, int train) {
+  pdl_wait();  // PDL: launched while the previous kernel drains (kernels.cuh)
+  pdl_trigger();
   int r = blockIdx.x;
   float* dst = dW + (size_t)tok[r] * E;
   const float* src = dE + (size_t)r * E;
@@ -477,7 +608,7 @@ __global__ void scatter_add_embed_kernel(float* __restrict__ dW, const int* __re
 }
 void scatter_add_embed(cudaStream_t s, float* dWembT, const int* tok, const float* dE, int R, int E, const StepScalars* sc,
                        bool train) {
-  scatter_add_embed_kernel<<<R, 128, 0, s>>>(dWembT, tok, dE, R, E, sc, train ? 1 : 0);
+  launch_pdl<2>(scatter_add_embed_kernel, dim3(R), dim3(128), 0, s, dWembT, tok, dE, R, E, sc, train ? 1 : 0);
   count_launch();
 }
 
@@ -488,6 +619,8 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ w, const float4* __restrict__ g, float4* __restrict__ m,
                                                    float4* __restrict__ v, size_t n4, const StepScalars* __restrict__ sc,
                                                    __nv_bfloat16* __restrict__ w_hi, __nv_bfloat16* __restrict__ w_lo) {
+  pdl_wait();  // PDL: launched while the previous kernel drains (kernels.cuh)
+  pdl_trigger();
   const float b1 = sc->beta1, b2 = sc->beta2, lr = sc->lr, eps = sc->eps, d1 = sc->adam_d1, d2 = sc->adam_d2;
   const float ob1 = sc->one_m_beta1, ob2 = sc->one_m_beta2;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -520,8 +653,8 @@ void adam_flat(cudaStream_t s, float* w, const float* g, float* m, float* v, siz
                __nv_bfloat16* w_hi, __nv_bfloat16* w_lo) {
   size_t n4 = n / 4;  // arena sizes are padded to multiples of 4
   int grid = 148 * 8;
-  if (w_hi) adam_kernel<true><<<grid, 256, 0, s>>>((float4*)w, (const float4*)g, (float4*)m, (float4*)v, n4, sc, w_hi, w_lo);
-  else adam_kernel<false><<<grid, 256, 0, s>>>((float4*)w, (const float4*)g, (float4*)m, (float4*)v, n4, sc, nullptr, nullptr);
+  if (w_hi) launch_pdl<2>(adam_kernel<true>, dim3(grid), dim3(256), 0, s, (float4*)w, (const float4*)g, (float4*)m, (float4*)v, n4, sc, w_hi, w_lo);
+  else launch_pdl<2>(adam_kernel<false>, dim3(grid), dim3(256), 0, s, (float4*)w, (const float4*)g, (float4*)m, (float4*)v, n4, sc, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr);
   count_launch();
 }
 
@@ -570,6 +703,8 @@ __global__ void fill_kernel(float4* buf, size_t n4, float val) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) buf[i] = v;
 }
 __global__ void zero_multi_kernel(const ZeroSegs z) {
+  pdl_wait();  // PDL: launched while the previous kernel drains (kernels.cuh)
+  pdl_trigger();
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int k = 0; k < z.count; k++) {
     float* p = z.p[k];
@@ -581,7 +716,7 @@ __global__ void zero_multi_kernel(const ZeroSegs z) {
 }
 void zero_multi(cudaStream_t s, const ZeroSegs& z) {
   if (z.count == 0) return;
-  zero_multi_kernel<<<148 * 4, 256, 0, s>>>(z);
+  launch_pdl<2>(zero_multi_kernel, dim3(148 * 4), dim3(256), 0, s, z);
   count_launch();
 }
 void fill_l2_scratch(cudaStream_t s, float* buf, size_t n, float val) {

@@ -94,9 +94,10 @@ struct Table {
   float* d = nullptr; int64_t n = 0;
   std::unordered_map<int64_t, int> map;
 };
+constexpr int COLPART_ROWS = 296;  // 2 CTAs per SM
 struct Slot { int l = 0, B = 0, split = 0; int *tok_in = nullptr, *tok_tgt = nullptr, *rows = nullptr; };
 struct Workspace {  // element offsets into the workspace arena
-  size_t X, v, dv, Eall, dE, acts1, h1, c1, Z, dZ, acts2, h2, c2, logits, rowlp, dh2, dh1, dhrec1, dc1, dhrec2, dc2;
+  size_t X, v, dv, Eall, dE, acts1, h1, c1, Z, dZ, acts2, h2, c2, logits, rowlp, dh2, dh1, dhrec1, dc1, dhrec2, dc2, colpart;
   // generation
   size_t gX, gv, ge, gg1, gh1a, gc1a, gh1b, gc1b, gz, gg2, gh2a, gc2a, gh2b, gc2b, glogits, gprob, gcs, gclp, gss, gslp, glpa, glpb, goprob, golp, gxh1, gxh2;
 };
@@ -128,6 +129,7 @@ struct lrcn_handle {
   std::map<std::tuple<int, int, int, int>, long long> graph_launches;
   LaunchCounter counter;
   int last_B = 0, last_l = 0;
+  bool dbout_fused = false;  // set by enqueue_forward: the softmax kernel already produced dbout
   // DP
   ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
   // generation int buffers
@@ -174,6 +176,24 @@ static void gemm(lrcn_handle* h, bool aK, bool bK, int M, int N, int K, const fl
   if (split_out) shadow(h, C, &ch, &cl);
   if (!gemm_bf16x3(h->stream, aK, bK, M, N, K, ah, al, lda, bh, bl, ldb, C, ldc, beta, bias, ch, cl, c_zeroed))
     throw GemmFail{gemm_bf16x3_last_error()};
+}
+
+// weight gradient of one LSTM layer: dW[4H][N1+N2] = dG' * [X | Hprev] (column blocks of one matrix).  One CTA-pair launch
+// with two B operands when the block boundary is tile aligned, else two GEMMs.  dW is zero on entry (step-start zeroing).
+static void gemm_dw_dual(lrcn_handle* h, int M, int N1, int N2, int K, const float* dG, int ldg, const float* X, int ldx, const float* Hp, int ldh,
+                         float* dW, int ldw) {
+  if (h->bf16mode && !getenv("LRCN_NO_DUALB")) {
+    bf16 *ah, *al, *b1h, *b1l, *b2h, *b2l;
+    shadow(h, dG, &ah, &al);
+    shadow(h, X, &b1h, &b1l);
+    shadow(h, Hp, &b2h, &b2l);
+    bool launched = false;
+    if (!gemm2_bf16x3_dualB(h->stream, false, false, M, N1, N2, K, ah, al, ldg, b1h, b1l, ldx, b2h, b2l, ldh, dW, ldw, true, &launched))
+      throw GemmFail{gemm_bf16x3_last_error()};
+    if (launched) return;
+  }
+  gemm(h, false, false, M, N1, K, dG, ldg, X, ldx, dW, ldw, false, nullptr, false, true);
+  gemm(h, false, false, M, N2, K, dG, ldg, Hp, ldh, dW + N1, ldw, false, nullptr, false, true);
 }
 
 // ------------------------------------------------------------------------------------------ misc ABI
@@ -293,6 +313,7 @@ static int create_impl(const lrcn_config* cfg, lrcn_handle* h) {
   o.Z = a.take(R * 2 * C); o.dZ = a.take(R * 2 * C);
   o.acts2 = a.take(R * 4 * H2); o.h2 = a.take(R1 * H2); o.c2 = a.take(R1 * H2);
   o.logits = a.take(R * ldV); o.rowlp = a.take(R);
+  o.colpart = a.take((size_t)COLPART_ROWS * ldV);  // per-CTA partial column sums of dA (softmax_ce_fused)
   o.dh2 = a.take(R * H2); o.dh1 = a.take(R * H1);
   o.dhrec1 = a.take(B * H1); o.dc1 = a.take(B * H1); o.dhrec2 = a.take(B * H2); o.dc2 = a.take(B * H2);
   const size_t G = cfg->max_gen_rows > 0 ? cfg->max_gen_rows : 1;
@@ -579,8 +600,14 @@ static void enqueue_forward(lrcn_handle* h, int split, int B, int l, bool train)
   gemm(h, true, true, R, 4 * H2, 2 * C, Z, 2 * C, Wp(h, 3), 2 * H2, acts2, 4 * H2, false, Wp(h, 4));
   lstm_layer_fwd(h, 2, T, B, acts2, h2, c2);
   gemm(h, true, true, R, V, H2, h2 + (size_t)B * H2, H2, Wp(h, 8), H2, logits, ldV, false, Wp(h, 9));      // x*w[end-1] .+ w[end]  lrcn.jl:550
-  softmax_ce(s, logits, ldV, R, V, h->d_tok_tgt, WS(h, o.rowlp), h->d_sc, train, SH(h, logits).hi, SH(h, logits).lo, h->d_loss,
-             h->d_counters + 128);  // logp + gather + fp64 total  lrcn.jl:562-567
+  // logp + gather + fp64 total  lrcn.jl:562-567; training in bf16x3 mode also folds dbout in and never writes dA in fp32
+  h->dbout_fused = false;
+  if (train && h->bf16mode && !getenv("LRCN_NO_FUSED_SOFTMAX"))
+    h->dbout_fused = softmax_ce_fused(s, logits, ldV, R, V, h->d_tok_tgt, WS(h, o.rowlp), h->d_sc, SH(h, logits).hi, SH(h, logits).lo,
+                                      WS(h, o.colpart), COLPART_ROWS, Gp(h, 9), h->d_loss, h->d_counters + 128);
+  if (!h->dbout_fused)
+    softmax_ce(s, logits, ldV, R, V, h->d_tok_tgt, WS(h, o.rowlp), h->d_sc, train, SH(h, logits).hi, SH(h, logits).lo, h->d_loss,
+               h->d_counters + 128);
 }
 
 static void enqueue_backward_seg(lrcn_handle* h, int B, int l, bool train, int seg) {
@@ -592,13 +619,12 @@ static void enqueue_backward_seg(lrcn_handle* h, int B, int l, bool train, int s
   float *dh2 = WS(h, o.dh2), *dh1 = WS(h, o.dh1), *dv = WS(h, o.dv), *dE = WS(h, o.dE);
   if (seg == 1) {
     gemm(h, false, false, V, H2, R, dA, ldV, h2 + (size_t)B * H2, H2, Gp(h, 8), H2, false, nullptr);      // dWout = h2' * dA
-    colsum(s, dA, ldV, R, V, Gp(h, 9), true);                                                                 // dbout
+    if (!h->dbout_fused) colsum(s, dA, ldV, R, V, Gp(h, 9), true);                                                              // dbout
     gemm(h, true, false, R, H2, V, dA, ldV, Wp(h, 8), H2, dh2, H2, false, nullptr, false, true);                        // dh2 = dA * Wout'
   } else if (seg == 2) {
     float *dhrec = WS(h, o.dhrec2), *dc = WS(h, o.dc2);
     lstm_layer_bwd(h, 2, T, B, acts2, c2, dh2, dhrec, dc);
-    gemm(h, false, false, 4 * H2, 2 * C, R, acts2, 4 * H2, Z, 2 * C, Gp(h, 3), 2 * H2, false, nullptr, false, true);          // dW2[:, x-part]
-    gemm(h, false, false, 4 * H2, H2, R, acts2, 4 * H2, h2, H2, Gp(h, 3) + 2 * C, 2 * H2, false, nullptr, false, true);       // dW2[:, h-part] (slot 0 = 0)
+    gemm_dw_dual(h, 4 * H2, 2 * C, H2, R, acts2, 4 * H2, Z, 2 * C, h2, H2, Gp(h, 3), 2 * H2);  // dW2 = dG2' * [Z | h2_{t-1}] (slot 0 = 0)
     colsum(s, acts2, 4 * H2, R, 4 * H2, Gp(h, 4), true);
     gemm(h, true, false, R, 2 * C, 4 * H2, acts2, 4 * H2, Wp(h, 3), 2 * H2, dZ, 2 * C, false, nullptr, false, true);
     dz_finish(s, dZ, dv, ldv, T, B, C, h->d_sc, train, SH(h, dZ).hi, SH(h, dZ).lo, SH(h, dv).hi, SH(h, dv).lo);
@@ -608,8 +634,7 @@ static void enqueue_backward_seg(lrcn_handle* h, int B, int l, bool train, int s
   } else {
     float *dhrec = WS(h, o.dhrec1), *dc = WS(h, o.dc1);
     lstm_layer_bwd(h, 1, T, B, acts1, c1, dh1, dhrec, dc);
-    gemm(h, false, false, 4 * H1, E, R, acts1, 4 * H1, Eall, E, Gp(h, 1), E + H1, false, nullptr, false, true);
-    gemm(h, false, false, 4 * H1, H1, R, acts1, 4 * H1, h1, H1, Gp(h, 1) + E, E + H1, false, nullptr, false, true);
+    gemm_dw_dual(h, 4 * H1, E, H1, R, acts1, 4 * H1, Eall, E, h1, H1, Gp(h, 1), E + H1);       // dW1 = dG1' * [E | h1_{t-1}]
     colsum(s, acts1, 4 * H1, R, 4 * H1, Gp(h, 2), true);
     gemm(h, true, false, R, E, 4 * H1, acts1, 4 * H1, Wp(h, 1), E + H1, dE, E, false, nullptr, false, true);
     scatter_add_embed(s, Gp(h, 7), h->d_tok_in, dE, R, E, h->d_sc, train);                                         // adjoint of Wemb[idx,:]
@@ -1094,8 +1119,13 @@ extern "C" int lrcn_time_kernel(lrcn_handle* h, const char* name, int reps, floa
         gather_embed(h->stream, Wp(h, 7), h->d_tok_in, R, h->E, WS(h, o.Eall), h->d_sc, false);
         bytes = 2.0 * 4.0 * R * h->E;
       } else if (!strcmp(name, "softmax_ce")) {
-        softmax_ce(h->stream, WS(h, o.logits), h->ldV, R, h->V, h->d_tok_tgt, WS(h, o.rowlp), h->d_sc, true, SH(h, WS(h, o.logits)).hi, SH(h, WS(h, o.logits)).lo);
-        bytes = (h->bf16mode ? 12.0 : 8.0) * R * h->V;  // read logits, write dA (+ bf16 hi/lo of dA)
+        bool fused = false;
+        if (h->bf16mode)  // what the training step runs: read logits, write the bf16 hi/lo split of dA, dbout folded in
+          fused = softmax_ce_fused(h->stream, WS(h, o.logits), h->ldV, R, h->V, h->d_tok_tgt, WS(h, o.rowlp), h->d_sc, SH(h, WS(h, o.logits)).hi,
+                                   SH(h, WS(h, o.logits)).lo, WS(h, o.colpart), COLPART_ROWS, Gp(h, 9), nullptr, nullptr);
+        if (!fused)
+          softmax_ce(h->stream, WS(h, o.logits), h->ldV, R, h->V, h->d_tok_tgt, WS(h, o.rowlp), h->d_sc, true, SH(h, WS(h, o.logits)).hi, SH(h, WS(h, o.logits)).lo);
+        bytes = 8.0 * R * h->V;  // read logits (4 B), write dA (fp32, or its bf16 hi/lo split: 4 B)
       } else {
         return fail(LRCN_ERR_ARG, "unknown kernel family '%s'", name);
       }
