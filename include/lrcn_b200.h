@@ -159,6 +159,9 @@ LRCN_API int lrcn_test_gemm(lrcn_handle* h, int precision, int a_kmajor, int b_k
  * dbg bits (pair kernel only): 1 = no epilogue stores, 2 = no TMA loads after the first ring fill, 4 = no MMAs */
 LRCN_API int lrcn_test_gemm_time(lrcn_handle* h, int a_kmajor, int b_kmajor, int M, int N, int K, int with_shadow_out, int iters,
                         int dbg, float* avg_ms_out);
+/* diagnostics: clocks to issue / complete a chain of n_mma tcgen05.mma (M x N x 16, bf16, smem operands) on every SM */
+LRCN_API int lrcn_test_mma_rate(lrcn_handle* h, int M, int N, int n_mma, int commit_every, int issuers, int64_t* issue_clk_out,
+                       int64_t* total_clk_out);
 /* beam selection on caller-supplied probabilities: probs [rows][V], parent_prob [rows]; outputs per image */
 LRCN_API int lrcn_test_beam_select(lrcn_handle* h, const float* probs, const float* parent_prob, int n_images, int K,
                           int V, int first_step, int64_t* tok_out, int32_t* parent_out, float* score_out);

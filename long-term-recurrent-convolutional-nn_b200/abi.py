@@ -65,6 +65,7 @@ SIGNATURES = {
     "lrcn_flush_l2": (C.c_int, [_H]),
     "lrcn_get_trace": (C.c_int, [_H, _p(C.c_uint64), C.c_int64]),
     "lrcn_time_kernel": (C.c_int, [_H, C.c_char_p, C.c_int, _f32p, _f64p, _f64p]),
+    "lrcn_test_mma_rate": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "lrcn_test_gemm_time": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]),
     "lrcn_test_gemm": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, C.c_int, _f32p]),
     "lrcn_test_beam_select": (C.c_int, [_H, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _i64p, _i32p, _f32p]),
@@ -292,6 +293,11 @@ class Handle:
         return float(ms.value), float(by.value), float(fl.value)
 
     # ---- kernel-level test hooks
+    def test_mma_rate(self, M, N, n_mma=512, commit_every=0, issuers=1):
+        a, b = C.c_int64(), C.c_int64()
+        check(self.lib.lrcn_test_mma_rate(self._h, M, N, n_mma, commit_every, issuers, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def test_gemm_time(self, a_kmajor, b_kmajor, M, N, K, shadow_out=False, iters=20, dbg=0):
         ms = C.c_float()
         check(self.lib.lrcn_test_gemm_time(self._h, int(a_kmajor), int(b_kmajor), M, N, K, int(shadow_out), iters, dbg, C.byref(ms)))

@@ -139,6 +139,8 @@ bool gemm2_bf16x3_dualB(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int
                         const __nv_bfloat16* A_lo, int lda, const __nv_bfloat16* B1_hi, const __nv_bfloat16* B1_lo, int ldb1,
                         const __nv_bfloat16* B2_hi, const __nv_bfloat16* B2_lo, int ldb2, float* C, int ldc, bool c_zeroed, bool* launched);
 void init_simt_kernels();
+// diagnostics (probe_mma.cu): clocks to issue / to complete a chain of n_mma tcgen05.mma M x N x 16 from resident smem operands
+bool probe_mma(cudaStream_t s, int M, int N, int n_mma, int commit_every, int issuers, long long* issue_clk, long long* total_clk);
 
 // ---------------------------------------------------------------- fused LSTM timestep (lstm_sm100.cu)
 bool init_lstm_sm100();
@@ -159,12 +161,12 @@ bool lstm_bwd_step(cudaStream_t s, int B, int H, bool has_rec, const __nv_bfloat
 
 // persistent whole-sequence variants (weights resident in smem, grid barrier per step).  *launched = false (and nothing
 // enqueued) when they do not apply (H too large for residency, T < 2, grid not co-resident): use the per-step kernels then.
-// counters: 32 uint32 in device memory, ZERO on entry (the caller zeroes them once per step; one region per launch).  hs/cs: [(T+1)*B][H] slot buffers; acts: [T*B][4H].
+// counters: 64 uint32 in device memory, ZERO on entry (the caller zeroes them once per step; one region per launch).  hs/cs: [(T+1)*B][H] slot buffers; acts: [T*B][4H].
 bool lstm_fwd_seq(cudaStream_t s, int B, int H, int T, const __nv_bfloat16* wperm_hi, const __nv_bfloat16* wperm_lo, float* acts, float* hs,
                   float* cs, __nv_bfloat16* hs_hi, __nv_bfloat16* hs_lo, unsigned int* counters, bool* launched,
                   unsigned long long* trace = nullptr /* optional [T][8] globaltimer stamps of CTA (0,0) */);
 bool lstm_bwd_seq(cudaStream_t s, int B, int H, int T, const __nv_bfloat16* wt_hi, const __nv_bfloat16* wt_lo, float* acts,
                   __nv_bfloat16* acts_hi, __nv_bfloat16* acts_lo, float* cs, const float* dh_all, float* dc, unsigned int* counters,
-                  bool* launched);
+                  bool* launched, float* dbias = nullptr /* optional [4H], zero on entry: receives the bias gradient (column sums of dG) */);
 
 }  // namespace lrcn

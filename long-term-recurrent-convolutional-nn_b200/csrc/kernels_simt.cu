@@ -403,68 +403,81 @@ softmax_ce_fused_kernel(const float* __restrict__ logits, int ld, int V, int R, 
                         float* __restrict__ colpart, double* __restrict__ total_out, unsigned int* __restrict__ done_ctr) {
   pdl_wait();
   pdl_trigger();
+  extern __shared__ __align__(16) float colacc[];  // [ld]: this CTA's column sums (each thread owns its columns: no races)
   __shared__ float red[32];
   __shared__ double dred[16];
   __shared__ int is_last;
   const int ld4 = ld >> 2;
   const float inv = sc->inv_ntok;
-  float4 acc[NV4];
 #pragma unroll
-  for (int i = 0; i < NV4; i++) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int r = blockIdx.x; r < R; r += gridDim.x) {
+  for (int i = 0; i < NV4; i++) {
+    const int q = threadIdx.x + 512 * i;
+    if (q < ld4) *reinterpret_cast<float4*>(colacc + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // the next row is loaded while the current one goes through its two block reductions
+  float4 xn[NV4];
+  auto load_row = [&](int r) {
     const float* a = logits + (size_t)r * ld;
+#pragma unroll
+    for (int i = 0; i < NV4; i++) {
+      const int q = threadIdx.x + 512 * i;
+      xn[i] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      if (q < ld4) xn[i] = __ldcs(reinterpret_cast<const float4*>(a + 4 * q));
+    }
+  };
+  if ((int)blockIdx.x < R) load_row(blockIdx.x);
+  for (int r = blockIdx.x; r < R; r += gridDim.x) {
     float4 x[NV4];
     float mx = -INFINITY;
 #pragma unroll
     for (int i = 0; i < NV4; i++) {
-      const int q = threadIdx.x + 512 * i;
-      x[i] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-      if (q < ld4) {
-        x[i] = *reinterpret_cast<const float4*>(a + 4 * q);
-        const int j = 4 * q;  // padding columns [V, ld) do not take part
-        if (j + 1 >= V) x[i].y = -INFINITY;
-        if (j + 2 >= V) x[i].z = -INFINITY;
-        if (j + 3 >= V) x[i].w = -INFINITY;
-        if (j >= V) x[i].x = -INFINITY;
-      }
+      const int j = 4 * (threadIdx.x + 512 * i);  // padding columns [V, ld) do not take part
+      x[i] = xn[i];
+      if (j + 1 >= V) x[i].y = -INFINITY;
+      if (j + 2 >= V) x[i].z = -INFINITY;
+      if (j + 3 >= V) x[i].w = -INFINITY;
+      if (j >= V) x[i].x = -INFINITY;
       mx = fmaxf(fmaxf(mx, fmaxf(x[i].x, x[i].y)), fmaxf(x[i].z, x[i].w));
     }
+    if (r + (int)gridDim.x < R) load_row(r + gridDim.x);
     mx = block_max(mx, red);
+    // One exponential per element: e = exp(x - max) is kept in registers and scaled by 1/sum afterwards.  This kernel is
+    // instruction bound otherwise (two precise expf per element = 60 us for 26 M logits); __expf (ex2.approx) has ~1e-7
+    // relative error, far inside the 1e-4 budget of the bf16x3 mode (the exact fp32 mode uses softmax_ce_kernel).
+    const int y = tgt[r];
+    float xy = 0.f;  // the target logit, if this thread owns it
+    bool own_y = false;
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV4; i++) sum += (expf(x[i].x - mx) + expf(x[i].y - mx)) + (expf(x[i].z - mx) + expf(x[i].w - mx));
+    for (int i = 0; i < NV4; i++) {
+      const int j = 4 * (threadIdx.x + 512 * i);
+      if (y >= j && y < j + 4) { own_y = true; xy = y == j ? x[i].x : (y == j + 1 ? x[i].y : (y == j + 2 ? x[i].z : x[i].w)); }
+      x[i].x = __expf(x[i].x - mx); x[i].y = __expf(x[i].y - mx); x[i].z = __expf(x[i].z - mx); x[i].w = __expf(x[i].w - mx);
+      sum += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+    }
     sum = block_sum(sum, red);
-    const float lse = logf(sum);
-    const int y = tgt[r];
+    if (own_y) rowlp[r] = (xy - mx) - logf(sum);
+    const float scale = inv / sum;
     const size_t base = (size_t)r * ld;
 #pragma unroll
     for (int i = 0; i < NV4; i++) {
       const int q = threadIdx.x + 512 * i;
       if (q < ld4) {
         const int j = 4 * q;
-        float p[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-          float v = 0.f;
-          if (j + e < V) {
-            const float lp = (p[e] - mx) - lse;
-            if (j + e == y) rowlp[r] = lp;
-            v = expf(lp);
-            if (j + e == y) v -= 1.0f;
-            v *= inv;
-          }
-          p[e] = v;
-        }
+        float p[4] = {x[i].x * scale, x[i].y * scale, x[i].z * scale, x[i].w * scale};  // padding columns: exp(-inf) = 0
+        if (own_y && y >= j && y < j + 4) p[y - j] -= inv;
         const float4 o = make_float4(p[0], p[1], p[2], p[3]);
         store_split4(hi, lo, base + 4 * q, o);
-        acc[i].x += o.x; acc[i].y += o.y; acc[i].z += o.z; acc[i].w += o.w;
+        float4 c = *reinterpret_cast<float4*>(colacc + 4 * q);
+        c.x += o.x; c.y += o.y; c.z += o.z; c.w += o.w;
+        *reinterpret_cast<float4*>(colacc + 4 * q) = c;
       }
     }
   }
 #pragma unroll
   for (int i = 0; i < NV4; i++) {
     const int q = threadIdx.x + 512 * i;
-    if (q < ld4) *reinterpret_cast<float4*>(colpart + (size_t)blockIdx.x * ld + 4 * q) = acc[i];
+    if (q < ld4) *reinterpret_cast<float4*>(colpart + (size_t)blockIdx.x * ld + 4 * q) = *reinterpret_cast<float4*>(colacc + 4 * q);
   }
   if (total_out) {  // deterministic fp64 total of the row log-probs by the last CTA (as in softmax_ce_kernel)
     if (threadIdx.x == 0) {
@@ -496,7 +509,7 @@ bool softmax_ce_fused(cudaStream_t s, const float* logits, int ld, int R, int V,
   const int nv4 = ((ld >> 2) + 511) / 512;
   if (nv4 > 8 || (ld & 3) || !hi || !colpart) return false;
   int grid = R < colpart_rows ? R : colpart_rows;
-#define LRCN_SMX(NV) launch_pdl<2>(softmax_ce_fused_kernel<NV>, dim3(grid), dim3(512), 0, s, logits, ld, V, R, tgt, rowlp, sc, hi, lo, colpart, total_out, done_ctr)
+#define LRCN_SMX(NV) launch_pdl<2>(softmax_ce_fused_kernel<NV>, dim3(grid), dim3(512), (size_t)ld * sizeof(float), s, logits, ld, V, R, tgt, rowlp, sc, hi, lo, colpart, total_out, done_ctr)
   if (nv4 <= 2) LRCN_SMX(2);
   else if (nv4 <= 4) LRCN_SMX(4);
   else if (nv4 <= 6) { if (grid > colpart_rows / 2) grid = colpart_rows / 2; LRCN_SMX(6); }
@@ -1004,6 +1017,10 @@ void beam_advance(cudaStream_t s, const BeamAdvanceArgs& a) {
 // called once per process from lrcn_create (never inside a stream capture)
 void init_simt_kernels() {
   cudaFuncSetAttribute(softmax_ce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(softmax_ce_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(softmax_ce_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(softmax_ce_fused_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+  cudaFuncSetAttribute(softmax_ce_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
   cudaFuncSetAttribute(beam_row_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(beam_row_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }

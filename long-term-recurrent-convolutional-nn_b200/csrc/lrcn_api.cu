@@ -105,7 +105,8 @@ struct lrcn_handle {
   lrcn_config cfg;
   int E, H1, H2, C, V, ldV, ldv;
   bool bf16mode;
-  cudaStream_t stream = nullptr, comm_stream = nullptr;
+  cudaStream_t stream = nullptr, comm_stream = nullptr, side_stream = nullptr;  // side: weight prep, concurrent with the step's first kernels
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_seg[3] = {nullptr, nullptr, nullptr}, ev_comm = nullptr;
   // params
   size_t P = 0, off[9], nel[9], bucket_off[4];
@@ -243,6 +244,9 @@ extern "C" int lrcn_destroy(lrcn_handle* h) {
   if (h->h_ndone) cudaFreeHost(h->h_ndone);
   for (cudaEvent_t e : {h->ev0, h->ev1, h->ev_seg[0], h->ev_seg[1], h->ev_seg[2], h->ev_comm}) if (e) cudaEventDestroy(e);
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return LRCN_OK;
@@ -269,6 +273,9 @@ static int create_impl(const lrcn_config* cfg, lrcn_handle* h) {
   if (h->bf16mode && (!init_gemm_sm100() || !init_lstm_sm100())) return fail(LRCN_ERR_CUDA, "%s", gemm_bf16x3_last_error());
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
   for (int i = 0; i < 3; i++) CK(cudaEventCreateWithFlags(&h->ev_seg[i], cudaEventDisableTiming));
@@ -337,8 +344,8 @@ static int create_impl(const lrcn_config* cfg, lrcn_handle* h) {
   CK(cudaMalloc(&h->d_sc, sizeof(StepScalars))); CK(cudaMallocHost(&h->h_sc, sizeof(StepScalars)));
   memset(h->h_sc, 0, sizeof(StepScalars));
   CK(cudaMalloc(&h->d_loss, 8)); CK(cudaMallocHost(&h->h_loss, 8));
-  CK(cudaMalloc(&h->d_counters, 256 * sizeof(unsigned int)));  // [0,128): 4 LSTM launches x 32 m-tile barriers; [128,..): softmax
-  CK(cudaMemset(h->d_counters, 0, 256 * sizeof(unsigned int)));
+  CK(cudaMalloc(&h->d_counters, 320 * sizeof(unsigned int)));  // [0,256): 4 LSTM launches x 64 (half-)tile barriers; [256,..): softmax
+  CK(cudaMemset(h->d_counters, 0, 320 * sizeof(unsigned int)));
   if (getenv("LRCN_SEQ_TRACE")) { CK(cudaMalloc(&h->d_trace, 64 * 8 * 8)); CK(cudaMemset(h->d_trace, 0, 64 * 8 * 8)); }
   CK(cudaMalloc(&h->g_last, G * 4)); CK(cudaMalloc(&h->g_ctok, G * 16 * 4)); CK(cudaMalloc(&h->g_stok, G * 4)); CK(cudaMalloc(&h->g_spar, G * 4));
   CK(cudaMalloc(&h->g_hista, G * ML * 4)); CK(cudaMalloc(&h->g_histb, G * ML * 4)); CK(cudaMalloc(&h->g_done, G * 4));
@@ -546,24 +553,26 @@ static void lstm_layer_fwd(lrcn_handle* h, int layer, int T, int B, float* acts,
     shadow(h, hs, &hs_hi, &hs_lo);
     bool launched = false;
     if (!lstm_fwd_seq(h->stream, B, H, T, layer == 1 ? h->wp1_hi : h->wp2_hi, layer == 1 ? h->wp1_lo : h->wp2_lo, acts, hs, cs, hs_hi, hs_lo,
-                      h->d_counters + (layer == 1 ? 0 : 32), &launched, layer == 2 ? h->d_trace : nullptr))
+                      h->d_counters + (layer == 1 ? 0 : 64), &launched, layer == 2 ? h->d_trace : nullptr))
       throw GemmFail{gemm_bf16x3_last_error()};
     if (launched) return;
   }
   for (int t = 0; t < T; t++) lstm_step_fwd(h, layer, t, B, acts, hs, cs);
 }
-static void lstm_layer_bwd(lrcn_handle* h, int layer, int T, int B, float* acts, float* cs, float* dh_all, float* dhrec, float* dc) {
+// returns true when the bias gradient (column sums of dG) has already been accumulated into `dbias` by the LSTM kernel
+static bool lstm_layer_bwd(lrcn_handle* h, int layer, int T, int B, float* acts, float* cs, float* dh_all, float* dhrec, float* dc, float* dbias) {
   if (h->bf16mode && !getenv("LRCN_NO_PERSISTENT")) {
     const int H = layer == 1 ? h->H1 : h->H2;
     bf16 *a_hi, *a_lo;
     shadow(h, acts, &a_hi, &a_lo);
     bool launched = false;
     if (!lstm_bwd_seq(h->stream, B, H, T, layer == 1 ? h->wt1_hi : h->wt2_hi, layer == 1 ? h->wt1_lo : h->wt2_lo, acts, a_hi, a_lo, cs, dh_all, dc,
-                      h->d_counters + (layer == 2 ? 64 : 96), &launched))
+                      h->d_counters + (layer == 2 ? 128 : 192), &launched, dbias))
       throw GemmFail{gemm_bf16x3_last_error()};
-    if (launched) return;
+    if (launched) return true;
   }
   for (int t = T - 1; t >= 0; t--) lstm_step_bwd(h, layer, t, T, B, acts, cs, dh_all, dhrec, dc);
+  return false;
 }
 
 static void enqueue_forward(lrcn_handle* h, int split, int B, int l, bool train) {
@@ -572,16 +581,23 @@ static void enqueue_forward(lrcn_handle* h, int split, int B, int l, bool train)
   cudaStream_t s = h->stream;
   float *X = WS(h, o.X), *v = WS(h, o.v), *Eall = WS(h, o.Eall), *acts1 = WS(h, o.acts1), *h1 = WS(h, o.h1), *c1 = WS(h, o.c1);
   float *Z = WS(h, o.Z), *acts2 = WS(h, o.acts2), *h2 = WS(h, o.h2), *c2 = WS(h, o.c2), *logits = WS(h, o.logits);
-  // Step start: (1) recurrent-weight operands of the persistent LSTM kernels (they load them before their dependency wait, so
-  // these launches must stay more than two kernels upstream of the first LSTM launch); (2) ONE launch zeroing every
-  // accumulation target of the step: grid-barrier counters, and for training the gradient arena behind dWout (bias column
-  // sums, split-K / stream-K weight gradients, the embedding scatter) and the stream-K data-gradient buffers.
-  if (h->bf16mode)
-    lstm_prepare_weights2(s, Wp(h, 1), E + H1, E, H1, h->wp1_hi, h->wp1_lo, train ? h->wt1_hi : nullptr, h->wt1_lo, Wp(h, 3), 2 * H2, 2 * C, H2,
-                          h->wp2_hi, h->wp2_lo, train ? h->wt2_hi : nullptr, h->wt2_lo);
+  // Step start.  (1) The recurrent-weight operands of the persistent LSTM kernels are rebuilt from the fp32 weights on a SIDE
+  // stream (a fork/join that stream capture turns into a parallel graph branch): they depend on nothing but the weights, so
+  // they overlap the zero-fill, the feature gather and the first GEMM.  The join sits before gather_embed, a kernel without
+  // the PDL attribute, more than two launches upstream of the first LSTM kernel (which loads its weights before its
+  // dependency wait).  (2) ONE launch zeroes every accumulation target of the step: grid-barrier counters and, for training,
+  // the gradient arena behind dWout (bias column sums, split-K / stream-K weight gradients, the embedding scatter) and the
+  // stream-K data-gradient buffers.
+  if (h->bf16mode) {
+    cudaEventRecord(h->ev_fork, s);
+    cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0);
+    lstm_prepare_weights2(h->side_stream, Wp(h, 1), E + H1, E, H1, h->wp1_hi, h->wp1_lo, train ? h->wt1_hi : nullptr, h->wt1_lo, Wp(h, 3), 2 * H2,
+                          2 * C, H2, h->wp2_hi, h->wp2_lo, train ? h->wt2_hi : nullptr, h->wt2_lo);
+    cudaEventRecord(h->ev_join, h->side_stream);
+  }
   {
     ZeroSegs z;
-    z.add(h->d_counters, 128);
+    z.add(h->d_counters, 256);
     if (train) {
       z.add(h->g + h->off[8], h->P - h->off[8]);  // arena order [Wout, bout | W2, b2, Wf, Wcnn | W1, b1, Wemb]: everything from bout on
       z.add(WS(h, o.dh2), (size_t)R * H2);
@@ -592,6 +608,7 @@ static void enqueue_forward(lrcn_handle* h, int split, int B, int l, bool train)
   }
   gather_features(s, h->tab[split].d, h->d_rows, B, X, SH(h, X).hi, SH(h, X).lo);
   gemm(h, true, true, B, C, LRCN_F_CNN, X, LRCN_F_CNN, Wp(h, 6), LRCN_F_CNN, v, ldv, false, nullptr);  // input*Wcnn  lrcn.jl:558
+  if (h->bf16mode) cudaStreamWaitEvent(s, h->ev_join, 0);
   gather_embed(s, Wp(h, 7), h->d_tok_in, R, E, Eall, h->d_sc, train, SH(h, Eall).hi, SH(h, Eall).lo);
   gemm(h, true, true, R, 4 * H1, E, Eall, E, Wp(h, 1), E + H1, acts1, 4 * H1, false, Wp(h, 2));         // x-part of layer 1, all t
   lstm_layer_fwd(h, 1, T, B, acts1, h1, c1);
@@ -604,10 +621,10 @@ static void enqueue_forward(lrcn_handle* h, int split, int B, int l, bool train)
   h->dbout_fused = false;
   if (train && h->bf16mode && !getenv("LRCN_NO_FUSED_SOFTMAX"))
     h->dbout_fused = softmax_ce_fused(s, logits, ldV, R, V, h->d_tok_tgt, WS(h, o.rowlp), h->d_sc, SH(h, logits).hi, SH(h, logits).lo,
-                                      WS(h, o.colpart), COLPART_ROWS, Gp(h, 9), h->d_loss, h->d_counters + 128);
+                                      WS(h, o.colpart), COLPART_ROWS, Gp(h, 9), h->d_loss, h->d_counters + 256);
   if (!h->dbout_fused)
     softmax_ce(s, logits, ldV, R, V, h->d_tok_tgt, WS(h, o.rowlp), h->d_sc, train, SH(h, logits).hi, SH(h, logits).lo, h->d_loss,
-               h->d_counters + 128);
+               h->d_counters + 256);
 }
 
 static void enqueue_backward_seg(lrcn_handle* h, int B, int l, bool train, int seg) {
@@ -623,9 +640,9 @@ static void enqueue_backward_seg(lrcn_handle* h, int B, int l, bool train, int s
     gemm(h, true, false, R, H2, V, dA, ldV, Wp(h, 8), H2, dh2, H2, false, nullptr, false, true);                        // dh2 = dA * Wout'
   } else if (seg == 2) {
     float *dhrec = WS(h, o.dhrec2), *dc = WS(h, o.dc2);
-    lstm_layer_bwd(h, 2, T, B, acts2, c2, dh2, dhrec, dc);
+    const bool db_done = lstm_layer_bwd(h, 2, T, B, acts2, c2, dh2, dhrec, dc, Gp(h, 4));
     gemm_dw_dual(h, 4 * H2, 2 * C, H2, R, acts2, 4 * H2, Z, 2 * C, h2, H2, Gp(h, 3), 2 * H2);  // dW2 = dG2' * [Z | h2_{t-1}] (slot 0 = 0)
-    colsum(s, acts2, 4 * H2, R, 4 * H2, Gp(h, 4), true);
+    if (!db_done) colsum(s, acts2, 4 * H2, R, 4 * H2, Gp(h, 4), true);
     gemm(h, true, false, R, 2 * C, 4 * H2, acts2, 4 * H2, Wp(h, 3), 2 * H2, dZ, 2 * C, false, nullptr, false, true);
     dz_finish(s, dZ, dv, ldv, T, B, C, h->d_sc, train, SH(h, dZ).hi, SH(h, dZ).lo, SH(h, dv).hi, SH(h, dv).lo);
     gemm(h, false, false, C, H1, R, dZ, 2 * C, h1 + (size_t)B * H1, H1, Gp(h, 5), H1, false, nullptr, false, true);            // dWf
@@ -633,9 +650,9 @@ static void enqueue_backward_seg(lrcn_handle* h, int B, int l, bool train, int s
     gemm(h, false, false, C, LRCN_F_CNN, B, dv, ldv, X, LRCN_F_CNN, Gp(h, 6), LRCN_F_CNN, false, nullptr, false, true);        // dWcnn = X' * dv
   } else {
     float *dhrec = WS(h, o.dhrec1), *dc = WS(h, o.dc1);
-    lstm_layer_bwd(h, 1, T, B, acts1, c1, dh1, dhrec, dc);
+    const bool db_done = lstm_layer_bwd(h, 1, T, B, acts1, c1, dh1, dhrec, dc, Gp(h, 2));
     gemm_dw_dual(h, 4 * H1, E, H1, R, acts1, 4 * H1, Eall, E, h1, H1, Gp(h, 1), E + H1);       // dW1 = dG1' * [E | h1_{t-1}]
-    colsum(s, acts1, 4 * H1, R, 4 * H1, Gp(h, 2), true);
+    if (!db_done) colsum(s, acts1, 4 * H1, R, 4 * H1, Gp(h, 2), true);
     gemm(h, true, false, R, E, 4 * H1, acts1, 4 * H1, Wp(h, 1), E + H1, dE, E, false, nullptr, false, true);
     scatter_add_embed(s, Gp(h, 7), h->d_tok_in, dE, R, E, h->d_sc, train);                                         // adjoint of Wemb[idx,:]
   }
@@ -1215,6 +1232,17 @@ extern "C" int lrcn_test_gemm_time(lrcn_handle* h, int a_kmajor, int b_kmajor, i
   CKT(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   *avg_ms_out = ms / iters;
   cleanup();
+  return LRCN_OK;
+}
+
+extern "C" int lrcn_test_mma_rate(lrcn_handle* h, int M, int N, int n_mma, int commit_every, int issuers, int64_t* issue_clk_out,
+                                  int64_t* total_clk_out) {
+  if (!h || !issue_clk_out || !total_clk_out || (M != 64 && M != 128) || N < 16 || N > 256 || (N % 16) || n_mma < 1 || issuers < 1 || issuers > 2 || commit_every < 0)
+    return fail(LRCN_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  long long a = 0, b = 0;
+  if (!probe_mma(h->stream, M, N, n_mma, commit_every, issuers, &a, &b)) return fail(LRCN_ERR_CUDA, "probe_mma failed: %s", cudaGetErrorString(cudaGetLastError()));
+  *issue_clk_out = a; *total_clk_out = b;
   return LRCN_OK;
 }
 

@@ -102,6 +102,24 @@ __device__ __forceinline__ uint32_t idesc_bf16(int M, int N, bool a_mn, bool b_m
          ((uint32_t)(M >> 4) << 24);
 }
 
+// Cheap descriptor arithmetic for MMA issue loops.  One thread issues every tcgen05.mma; rebuilding the 64-bit descriptors
+// with shifts and masks costs ~14 dependent uniform-datapath instructions (~85-100 clk, measured with tools/probe_mma_rate.py)
+// per MMA -- more than a 128x128x16 MMA takes on the tensor pipe (64 clk).  The high word of a descriptor is constant per
+// layout; the low word is (addr >> 4) | (LBO >> 4) << 16, so advancing k is ONE 32-bit add.
+constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo_kmajor(uint32_t tile) { return ((tile & 0x3FFFFu) >> 4) | (1u << 16); }   // +2 per k16 step (32 B)
+__device__ __forceinline__ uint32_t desc_lo_mnmajor(uint32_t tile) { return ((tile & 0x3FFFFu) >> 4) | (512u << 16); }  // +128 per k16 step (2048 B)
+__device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI_SW128)
+      : "memory");
+}
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

@@ -23,11 +23,11 @@ for i in range(4):
     h.train_step_staged(0, 0.0, i)
 h.sync()
 tr = h.get_trace(l + 1).astype(np.int64)
-names = ["grid_wait done", "first A k-block landed", "MMAs issued+commit", "epilogue: tfull seen", "epi: hi/lo stored", "fences done", "bar.sync done"]
+names = ["0 grid_wait done", "1 kb0 landed", "2 MMAs issued+commit", "3 epilogue: tfull seen", "4 all epilogue warps done (bar.sync)", "5 kb3 landed", "6 release done", "7 last kb landed"]
 print("step | " + " | ".join(names) + "   (ns relative to this step's grid_wait)")
 for t in range(1, l + 1):
     base = tr[t, 0]
-    row = [tr[t, k] - base if tr[t, k] else -1 for k in range(7)]
+    row = [int(tr[t, k] - base) if tr[t, k] else -1 for k in range(8)]
     nxt = tr[t + 1, 0] - base if t + 1 <= l and tr[t + 1, 0] else -1
     print(t, row, "next grid_wait at", nxt)
 h.close()
