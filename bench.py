@@ -223,6 +223,7 @@ def main():
     h = abi.Handle(cfg)
     h.set_model(synth.initweights([w["H1"], w["H2"]], w["V"], w["E"], seed=1))
     h.load_features(0, np.arange(1, N_IMG + 1, dtype=np.int64), synth.features(N_IMG, seed=2))
+    dp_exchange = None
     if world > 1:
         import torch
         uid = torch.zeros(abi.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
@@ -230,6 +231,17 @@ def main():
             uid = torch.frombuffer(bytearray(abi.Handle.comm_unique_id()), dtype=torch.uint8).cuda()
         dist.broadcast(uid, 0)
         h.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+        # peer-memory gradient exchange (csrc/dp_p2p.cu): every rank exports its IPC blob, all-gather, import
+        mine = torch.frombuffer(bytearray(h.p2p_export()), dtype=torch.uint8).cuda()
+        blobs = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(blobs, mine)
+        try:
+            h.p2p_import(b"".join(bytes(b.cpu().numpy().tobytes()) for b in blobs), rank, world)
+            dp_exchange = "p2p" if not os.environ.get("LRCN_DP_NCCL") else "nccl"
+        except abi.LrcnError as e:  # no peer access between these GPUs: NCCL allreduce
+            if rank == 0:
+                print(f"[bench] peer memory unavailable ({e}); using NCCL", file=sys.stderr)
+            dp_exchange = "nccl"
 
     batches = make_batches(w, rank, N_SLOTS)
     for s, (img, tok, l) in enumerate(batches):
@@ -331,7 +343,7 @@ def main():
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16x3 (bf16 hi/lo split on tcgen05, fp32 accumulate; fp32-equivalent)" if prec else "f32", "data": "synthetic",
                 "config": {"workload": args.workload, **{k: w[k] for k in ("E", "H1", "H2", "V")}, "batch_per_gpu": w["B"],
-                           "global_batch": w["B"] * world, "lengths": w["shape"], "parallelism": f"dp{world}",
+                           "global_batch": w["B"] * world, "lengths": w["shape"], "parallelism": f"dp{world}" + (f" ({dp_exchange} gradient exchange)" if dp_exchange else ""),
                            "l2": "per-step working set (params+grads+Adam 4x53 MB, logits ~100 MB) exceeds the 126 MB L2; no explicit flush"},
                 "e2e": {"value": e2e_val, "unit": "tokens/s", "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
                         "ms_per_step": ms_e / args.steps},
@@ -342,6 +354,8 @@ def main():
             line["beam"] = beam
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg(w)
+    if dist is not None:
+        dist.barrier()  # nobody unmaps its arenas while a peer may still be inside an exchange kernel
     h.close()
     if dist is not None:
         dist.barrier()

@@ -137,6 +137,13 @@ LRCN_API int lrcn_beam_search(lrcn_handle* h, int split, const int64_t* image_id
 #define LRCN_COMM_ID_BYTES 128
 LRCN_API int lrcn_comm_unique_id(char id[LRCN_COMM_ID_BYTES]);
 LRCN_API int lrcn_comm_init(lrcn_handle* h, const char id[LRCN_COMM_ID_BYTES], int rank, int nranks);
+/* Peer-memory data-parallel exchange (one process per GPU, all on one NVLink node).  Every rank exports a blob describing
+ * its gradient arena (CUDA IPC handles), the launcher all-gathers the blobs, every rank imports all of them.  Afterwards
+ * the gradient allreduce of lrcn_train_step / lrcn_grad is ONE owner-computes kernel over NVLink peer memory between two
+ * flag barriers (csrc/dp_p2p.cu) instead of NCCL kernels; lrcn_comm_init is then optional.  LRCN_DP_NCCL=1 keeps NCCL. */
+#define LRCN_P2P_BLOB_BYTES 256
+LRCN_API int lrcn_p2p_export(lrcn_handle* h, char blob[LRCN_P2P_BLOB_BYTES]);
+LRCN_API int lrcn_p2p_import(lrcn_handle* h, const char* blobs /* nranks x LRCN_P2P_BLOB_BYTES, rank order */, int rank, int nranks);
 
 /* ---- measurement helpers: CUDA events on the library's own compute stream */
 LRCN_API int lrcn_sync(lrcn_handle* h);

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "liblrcn_b200.so")
 PREC_FP32, PREC_BF16X3 = 0, 1
 OK, ERR_ARG, ERR_CUDA, ERR_NCCL, ERR_MISSING, ERR_STATE = 0, 1, 2, 3, 4, 5
 COMM_ID_BYTES = 128
+P2P_BLOB_BYTES = 256
 
 
 class LrcnError(RuntimeError):
@@ -58,6 +59,8 @@ SIGNATURES = {
     "lrcn_beam_search": (C.c_int, [_H, C.c_int, _i64p, C.c_int64, C.c_int, C.c_int, _i64p, _i32p, _f32p, _f32p]),
     "lrcn_comm_unique_id": (C.c_int, [C.c_char_p]),
     "lrcn_comm_init": (C.c_int, [_H, C.c_char_p, C.c_int, C.c_int]),
+    "lrcn_p2p_export": (C.c_int, [_H, C.c_char_p]),
+    "lrcn_p2p_import": (C.c_int, [_H, C.c_char_p, C.c_int, C.c_int]),
     "lrcn_sync": (C.c_int, [_H]),
     "lrcn_timer_start": (C.c_int, [_H]),
     "lrcn_timer_stop": (C.c_int, [_H, _f32p]),
@@ -261,6 +264,15 @@ class Handle:
     def comm_init(self, uid: bytes, rank: int, nranks: int):
         assert len(uid) == COMM_ID_BYTES
         check(self.lib.lrcn_comm_init(self._h, uid, rank, nranks))
+
+    def p2p_export(self) -> bytes:
+        buf = C.create_string_buffer(P2P_BLOB_BYTES)
+        check(self.lib.lrcn_p2p_export(self._h, buf))
+        return buf.raw
+
+    def p2p_import(self, blobs: bytes, rank: int, nranks: int):
+        assert len(blobs) == nranks * P2P_BLOB_BYTES
+        check(self.lib.lrcn_p2p_import(self._h, blobs, rank, nranks))
 
     # ---- measurement
     def sync(self):

@@ -1,0 +1,87 @@
+// dp_p2p.cu -- data-parallel gradient exchange over NVLink peer memory, without NCCL kernels.
+//
+// One process per GPU; every rank maps its peers' gradient arenas (CUDA IPC).  Rank r OWNS a contiguous 1/N shard of the
+// arena: it loads that shard from every rank over NVLink (fixed rank order, so the sum is deterministic and identical
+// everywhere), and stores the sum back into every rank's arena in place -- reduce-scatter and all-gather fused in one
+// kernel with owner-computes semantics (nobody else touches an owner's elements, so no staging buffers are needed).
+// Cross-GPU ordering is two flag barriers in peer memory (system-scope release / acquire):
+//   B1  every rank's backward pass is complete  ->  exchange kernel  ->  B2  every rank's stores have landed.
+// Why not NCCL here: its kernels compete for SMs with the persistent tcgen05 GEMM / LSTM kernels (which need their whole
+// grid co-resident), so a "bucketed, overlapped" allreduce ends up serialising; measured in profiles/r01_progress.md.
+#include "kernels.cuh"
+
+#include <stdio.h>
+
+namespace lrcn {
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_peer_f4(const float4* p) {  // peer memory is cached in L1 only and L1 is not coherent: bypass it
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+// one warp: lane q signals rank q and waits for rank q's signal
+__global__ void xgpu_barrier_kernel(P2PPeers peers, unsigned int* epoch_ctr) {
+  __shared__ unsigned int epoch;
+  if (threadIdx.x == 0) { epoch = *epoch_ctr + 1u; *epoch_ctr = epoch; }
+  __syncwarp();
+  const unsigned int e = epoch;
+  const int q = threadIdx.x;
+  __threadfence_system();
+  if (q < peers.nranks) {
+    st_release_sys(&peers.ctl[q]->flags[peers.rank], e);
+    const unsigned int* mine = &peers.ctl[peers.rank]->flags[q];
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(mine) - e) < 0) {
+      if (clock64() - t0 > 40000000000ll) {  // ~20 s: a peer died or never reached the barrier
+        printf("lrcn dp_p2p: barrier timeout, rank %d waiting for rank %d (epoch %u)\n", peers.rank, q, e);
+        __trap();
+      }
+    }
+  }
+}
+
+// in-place allreduce(sum) of the gradient arena by owner-computes shards + fp64 loss total
+__global__ void __launch_bounds__(256) allreduce_p2p_kernel(P2PPeers peers, size_t begin4, size_t end4, double* loss_total) {
+  const int N = peers.nranks;
+  for (size_t i = begin4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < end4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int p = 0; p < N; p++) {
+      const float4 x = ld_peer_f4(reinterpret_cast<const float4*>(peers.g[p]) + i);
+      acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+    }
+    for (int p = 0; p < N; p++) reinterpret_cast<float4*>(peers.g[p])[i] = acc;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && loss_total) {
+    double t = 0.0;
+    for (int p = 0; p < N; p++) {
+      double v;
+      asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(&peers.ctl[p]->loss_partial) : "memory");
+      t += v;
+    }
+    *loss_total = t;
+  }
+  __threadfence_system();  // my stores into peer memory are performed before this kernel ends (B2 follows)
+}
+
+void dp_p2p_allreduce(cudaStream_t s, const P2PPeers& peers, size_t n_floats, unsigned int* epoch_ctr, double* loss_total) {
+  const size_t n4 = n_floats / 4;  // arena sizes are multiples of 64 floats
+  const size_t per = (n4 + peers.nranks - 1) / peers.nranks;
+  const size_t b = per * peers.rank < n4 ? per * peers.rank : n4;
+  const size_t e = b + per < n4 ? b + per : n4;
+  xgpu_barrier_kernel<<<1, 32, 0, s>>>(peers, epoch_ctr);
+  allreduce_p2p_kernel<<<148 * 4, 256, 0, s>>>(peers, b, e, loss_total);
+  xgpu_barrier_kernel<<<1, 32, 0, s>>>(peers, epoch_ctr);
+  if (g_counter) g_counter->n += 3;
+}
+
+}  // namespace lrcn

@@ -139,6 +139,16 @@ bool gemm2_bf16x3_dualB(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int
                         const __nv_bfloat16* A_lo, int lda, const __nv_bfloat16* B1_hi, const __nv_bfloat16* B1_lo, int ldb1,
                         const __nv_bfloat16* B2_hi, const __nv_bfloat16* B2_lo, int ldb2, float* C, int ldc, bool c_zeroed, bool* launched);
 void init_simt_kernels();
+
+// ---------------------------------------------------------------- data-parallel exchange over peer memory (dp_p2p.cu)
+constexpr int LRCN_P2P_MAX_RANKS = 8;
+struct P2PCtl {              // one per rank, in a small exported allocation
+  unsigned int flags[64];    // flags[q]: last barrier epoch signalled by rank q
+  double loss_partial;       // this rank's fp64 sum of token log-probs of the current step
+};
+struct P2PPeers { float* g[LRCN_P2P_MAX_RANKS]; P2PCtl* ctl[LRCN_P2P_MAX_RANKS]; int nranks, rank; };
+// barrier, in-place allreduce(sum) of the gradient arena (n_floats) + loss total, barrier
+void dp_p2p_allreduce(cudaStream_t s, const P2PPeers& peers, size_t n_floats, unsigned int* epoch_ctr, double* loss_total);
 // diagnostics (probe_mma.cu): clocks to issue / to complete a chain of n_mma tcgen05.mma M x N x 16 from resident smem operands
 bool probe_mma(cudaStream_t s, int M, int N, int n_mma, int commit_every, int issuers, long long* issue_clk, long long* total_clk);
 

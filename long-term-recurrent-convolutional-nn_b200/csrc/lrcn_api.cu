@@ -122,7 +122,15 @@ struct lrcn_handle {
   int *d_tok_in = nullptr, *d_tok_tgt = nullptr, *d_rows = nullptr;
   int* h_stage = nullptr;  // pinned: tok_in | tok_tgt | rows
   StepScalars *d_sc = nullptr, *h_sc = nullptr;
-  double *d_loss = nullptr, *h_loss = nullptr;
+  double *d_loss = nullptr, *h_loss = nullptr;  // d_loss lives inside p2p_ctl (peers read it)
+  // peer-memory data parallelism (dp_p2p.cu)
+  P2PCtl* p2p_ctl = nullptr;          // exported control block: barrier flags + this rank's loss partial
+  double* d_loss_total = nullptr;     // sum over ranks, written by the exchange kernel
+  unsigned int* d_epoch = nullptr;    // barrier epoch counter (local)
+  P2PPeers peers{};
+  bool p2p_ready = false;
+  bool loss_is_total = false;       // last step summed the loss over ranks into d_loss_total
+  void* p2p_opened[2 * LRCN_P2P_MAX_RANKS] = {};  // IPC mappings to close
   unsigned int* d_counters = nullptr;  // per-m-tile grid-barrier counters of the persistent LSTM kernels
   unsigned long long* d_trace = nullptr;  // LRCN_SEQ_TRACE=1: per-step timeline of the layer-2 forward sequence kernel
   Slot slots[64];
@@ -233,8 +241,9 @@ extern "C" int lrcn_destroy(lrcn_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
   if (h->comm && nccl_api()) nccl_api()->CommDestroy(h->comm);
+  for (void* q : h->p2p_opened) if (q) cudaIpcCloseMemHandle(q);
   void* ptrs[] = {h->w, h->g, h->m, h->v, h->w_hi, h->w_lo, h->wp1_hi, h->wp1_lo, h->wp2_hi, h->wp2_lo, h->tab[0].d, h->tab[1].d, h->ws.f, h->ws.hi, h->ws.lo, h->d_tok_in,
-                  h->d_tok_tgt, h->d_rows, h->d_sc, h->d_loss, h->d_counters, h->d_trace, h->g_last, h->g_ctok, h->g_stok, h->g_spar, h->g_hista, h->g_histb,
+                  h->d_tok_tgt, h->d_rows, h->d_sc, h->p2p_ctl, h->d_loss_total, h->d_epoch, h->d_counters, h->d_trace, h->g_last, h->g_ctok, h->g_stok, h->g_spar, h->g_hista, h->g_histb,
                   h->g_done, h->g_ndone, h->g_olen, h->g_rows, h->g_otok, h->l2_scratch};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& s : h->slots) { if (s.tok_in) cudaFree(s.tok_in); if (s.tok_tgt) cudaFree(s.tok_tgt); if (s.rows) cudaFree(s.rows); }
@@ -343,7 +352,10 @@ static int create_impl(const lrcn_config* cfg, lrcn_handle* h) {
   CK(cudaMallocHost(&h->h_stage, (2 * R + B) * 4));
   CK(cudaMalloc(&h->d_sc, sizeof(StepScalars))); CK(cudaMallocHost(&h->h_sc, sizeof(StepScalars)));
   memset(h->h_sc, 0, sizeof(StepScalars));
-  CK(cudaMalloc(&h->d_loss, 8)); CK(cudaMallocHost(&h->h_loss, 8));
+  CK(cudaMalloc(&h->p2p_ctl, 4096)); CK(cudaMemset(h->p2p_ctl, 0, 4096));
+  h->d_loss = &h->p2p_ctl->loss_partial;
+  CK(cudaMalloc(&h->d_loss_total, 8)); CK(cudaMalloc(&h->d_epoch, 4)); CK(cudaMemset(h->d_epoch, 0, 4));
+  CK(cudaMallocHost(&h->h_loss, 8));
   CK(cudaMalloc(&h->d_counters, 320 * sizeof(unsigned int)));  // [0,256): 4 LSTM launches x 64 (half-)tile barriers; [256,..): softmax
   CK(cudaMemset(h->d_counters, 0, 320 * sizeof(unsigned int)));
   if (getenv("LRCN_SEQ_TRACE")) { CK(cudaMalloc(&h->d_trace, 64 * 8 * 8)); CK(cudaMemset(h->d_trace, 0, 64 * 8 * 8)); }
@@ -729,6 +741,7 @@ static int run_step(lrcn_handle* h, int split, int B, int l, float pdrop, uint64
   h->last_B = B; h->last_l = l;
   const int fl = (split << 1) | (drop ? 1 : 0);
   int rc;
+  h->loss_is_total = false;
   if (mode == 0) {
     return run_cached(h, std::make_tuple(0, B, l, fl), [&] { enqueue_forward(h, split, B, l, false); });
   }
@@ -739,8 +752,40 @@ static int run_step(lrcn_handle* h, int split, int B, int l, float pdrop, uint64
       if (mode == 2) enqueue_adam(h);
     });
   }
-  // data-parallel: bucketed allreduce on the comm stream, overlapped with the remaining backward segments
+  static const bool force_nccl = getenv("LRCN_DP_NCCL") != nullptr;
+  if (h->p2p_ready && !force_nccl) {
+    h->loss_is_total = true;
+    // backward pass, then ONE owner-computes exchange kernel over NVLink peer memory between two flag barriers (dp_p2p.cu),
+    // then the replicated Adam: no NCCL kernels competing for SMs with the persistent GEMM / LSTM kernels
+    return run_cached(h, std::make_tuple(mode == 2 ? 22 : 21, B, l, fl), [&] {
+      enqueue_forward(h, split, B, l, true);
+      for (int seg = 1; seg <= 3; seg++) enqueue_backward_seg(h, B, l, true, seg);
+      dp_p2p_allreduce(h->stream, h->peers, h->P, h->d_epoch, h->d_loss_total);
+      if (mode == 2) enqueue_adam(h);
+    });
+  }
+  if (!h->comm) return fail(LRCN_ERR_ARG, "data-parallel group not initialised (lrcn_comm_init or lrcn_p2p_import)");
   NcclApi* n = nccl_api();
+  static const bool bucketed = getenv("LRCN_DP_BUCKETS") != nullptr;  // measured: one allreduce after the backward pass beats 3 overlapped buckets
+  if (!bucketed) {
+    // one allreduce over the whole gradient arena after the backward pass (no overlap, but no SM contention between the NCCL
+    // kernels and the persistent GEMM / LSTM kernels either)
+    rc = run_cached(h, std::make_tuple(20, B, l, fl), [&] {
+      enqueue_forward(h, split, B, l, true);
+      for (int seg = 1; seg <= 3; seg++) enqueue_backward_seg(h, B, l, true, seg);
+    });
+    if (rc) return rc;
+    rc = nccl_check(n->GroupStart(), "ncclGroupStart"); if (rc) return rc;
+    rc = nccl_check(n->AllReduce(h->g, h->g, h->P, NCCL_FLOAT32, NCCL_SUM, h->comm, h->stream), "ncclAllReduce(grad)"); if (rc) return rc;
+    rc = nccl_check(n->AllReduce(h->d_loss, h->d_loss, 1, NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream), "ncclAllReduce(loss)"); if (rc) return rc;
+    rc = nccl_check(n->GroupEnd(), "ncclGroupEnd"); if (rc) return rc;
+    if (mode == 2) {
+      rc = run_cached(h, std::make_tuple(14, 0, 0, 0), [&] { enqueue_adam(h); });
+      if (rc) return rc;
+    }
+    return LRCN_OK;
+  }
+  // data-parallel: bucketed allreduce on the comm stream, overlapped with the remaining backward segments
   rc = run_cached(h, std::make_tuple(10, B, l, fl), [&] { enqueue_forward(h, split, B, l, true); enqueue_backward_seg(h, B, l, true, 1); });
   if (rc) return rc;
   for (int seg = 1; seg <= 3; seg++) {
@@ -772,7 +817,7 @@ static int run_step(lrcn_handle* h, int split, int B, int l, float pdrop, uint64
 }
 
 static int finish_loss(lrcn_handle* h, int B, int l, double* total_out) {
-  CK(cudaMemcpyAsync(h->h_loss, h->d_loss, 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_loss, h->loss_is_total ? h->d_loss_total : h->d_loss, 8, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   *total_out = *h->h_loss;
   return LRCN_OK;
@@ -1062,6 +1107,50 @@ extern "C" int lrcn_comm_init(lrcn_handle* h, const char id[LRCN_COMM_ID_BYTES],
   int rc = nccl_check(n->CommInitRank(&h->comm, nranks, u, rank), "ncclCommInitRank");
   if (rc) return rc;
   h->rank = rank; h->nranks = nranks;
+  return LRCN_OK;
+}
+
+struct P2PBlob {  // LRCN_P2P_BLOB_BYTES
+  int magic, device;
+  unsigned long long arena_floats;
+  cudaIpcMemHandle_t g, ctl;
+};
+static_assert(sizeof(P2PBlob) <= LRCN_P2P_BLOB_BYTES, "blob too large");
+extern "C" int lrcn_p2p_export(lrcn_handle* h, char blob[LRCN_P2P_BLOB_BYTES]) {
+  if (!h || !blob) return fail(LRCN_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  P2PBlob b;
+  memset(&b, 0, sizeof b);
+  b.magic = 0x4C524350; b.device = h->cfg.device; b.arena_floats = h->P;
+  CK(cudaIpcGetMemHandle(&b.g, h->g));
+  CK(cudaIpcGetMemHandle(&b.ctl, h->p2p_ctl));
+  memset(blob, 0, LRCN_P2P_BLOB_BYTES);
+  memcpy(blob, &b, sizeof b);
+  return LRCN_OK;
+}
+extern "C" int lrcn_p2p_import(lrcn_handle* h, const char* blobs, int rank, int nranks) {
+  if (!h || !blobs || nranks < 1 || nranks > LRCN_P2P_MAX_RANKS || rank < 0 || rank >= nranks)
+    return fail(LRCN_ERR_ARG, "bad rank/nranks (at most %d ranks)", LRCN_P2P_MAX_RANKS);
+  if (h->comm && (h->rank != rank || h->nranks != nranks)) return fail(LRCN_ERR_ARG, "rank/nranks differ from lrcn_comm_init");
+  if (h->p2p_ready) return fail(LRCN_ERR_ARG, "peer memory already imported");
+  CK(cudaSetDevice(h->cfg.device));
+  P2PPeers pe{};
+  pe.nranks = nranks; pe.rank = rank;
+  for (int p = 0; p < nranks; p++) {
+    P2PBlob b;
+    memcpy(&b, blobs + (size_t)p * LRCN_P2P_BLOB_BYTES, sizeof b);
+    if (b.magic != 0x4C524350 || b.arena_floats != h->P) return fail(LRCN_ERR_ARG, "blob %d does not describe a handle of this model", p);
+    if (p == rank) { pe.g[p] = h->g; pe.ctl[p] = h->p2p_ctl; continue; }
+    void *pg = nullptr, *pc = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&pg, b.g, cudaIpcMemLazyEnablePeerAccess);
+    if (e == cudaSuccess) { h->p2p_opened[2 * p] = pg; e = cudaIpcOpenMemHandle(&pc, b.ctl, cudaIpcMemLazyEnablePeerAccess); }
+    if (e != cudaSuccess) return fail(LRCN_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d, device %d) -> %s (peer access over NVLink required)", p, b.device, cudaGetErrorString(e));
+    h->p2p_opened[2 * p + 1] = pc;
+    pe.g[p] = (float*)pg; pe.ctl[p] = (P2PCtl*)pc;
+  }
+  h->peers = pe;
+  h->rank = rank; h->nranks = nranks;
+  h->p2p_ready = true;
   return LRCN_OK;
 }
 

@@ -37,20 +37,32 @@ def main():
             uid = torch.frombuffer(bytearray(abi.Handle.comm_unique_id()), dtype=torch.uint8).cuda()
         dist.broadcast(uid, 0)
         h.comm_init(uid.cpu().numpy().tobytes(), rank, world)
+        mine = torch.frombuffer(bytearray(h.p2p_export()), dtype=torch.uint8).cuda()
+        blobs = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(blobs, mine)
+        h.p2p_import(b"".join(bytes(x.cpu().numpy().tobytes()) for x in blobs), rank, world)
         sl = slice(rank * b, (rank + 1) * b)
         L = h.grad(0, img[sl], np.ascontiguousarray(tok[:, sl]))
         g = [h.get_grad(k) for k in range(1, 10)]
         L2 = h.train_step(0, img[sl], np.ascontiguousarray(tok[:, sl]))
         w_after = h.get_model()
+        for it in range(3):  # a few more steps: barrier epochs, graph replays
+            h.train_step(0, img[sl], np.ascontiguousarray(tok[:, sl]))
+        final = np.concatenate([x.ravel() for x in h.get_model()])
+        digest = torch.tensor([float(np.abs(final).sum()), float((final * np.arange(1, final.size + 1, dtype=np.float64) % 7).sum())], dtype=torch.float64, device="cuda")
+        digests = [torch.zeros_like(digest) for _ in range(world)]
+        dist.all_gather(digests, digest)
+        same = all(bool(torch.equal(d, digests[0])) for d in digests)
         if rank == 0:
             g_ref, L_ref = O.lossgradient(model, O.initstate(model, Bg), feats[img - 1], list(tok), range(0, l))
             errs = [float(np.linalg.norm(g[k] - g_ref[k]) / np.linalg.norm(g_ref[k])) for k in range(9)]
             ref = [w.copy() for w in model]
             O.update(ref, g_ref, O.initparams(ref))
             derr = [float(np.linalg.norm((w_after[k] - model[k]) - (ref[k] - model[k])) / (np.linalg.norm(ref[k] - model[k]) + 1e-30)) for k in range(9)]
-            good = abs(L - L_ref) < 1e-4 * abs(L_ref) and max(errs) < 1e-4 and abs(L2 - L_ref) < 1e-4 * abs(L_ref) and max(derr) < 5e-3
+            good = abs(L - L_ref) < 1e-4 * abs(L_ref) and max(errs) < 1e-4 and abs(L2 - L_ref) < 1e-4 * abs(L_ref) and max(derr) < 5e-3 and same
             ok = ok and good
-            print(f"dp_check world={world} prec={prec}: loss {L:.6f} vs {L_ref:.6f}; max grad relerr {max(errs):.2e}; max update relerr {max(derr):.2e} -> {'OK' if good else 'FAIL'}", flush=True)
+            print(f"dp_check world={world} prec={prec}: loss {L:.6f} vs {L_ref:.6f}; max grad relerr {max(errs):.2e}; max update relerr {max(derr):.2e}; replicas identical after 4 steps: {same} -> {'OK' if good else 'FAIL'}", flush=True)
+        dist.barrier()
         h.close()
     dist.barrier()
     dist.destroy_process_group()
