@@ -72,7 +72,7 @@ struct Gemm2Params {
   int M, N, K;
   int tiles_mp, tiles_n;  // tiles_mp: pairs of 128-row tiles
   int n_split;            // > 0: B is the column concatenation [B1 | B2]; tiles with n0 >= n_split read B2 (at n0 - n_split)
-  int streamk;            // 0: whole 256x256 tiles round-robin; 1: every CTA pair owns an equal contiguous range of (tile, k-block) iterations
+  int sk_tile0, sk_tiles, dp_end;  // SegIter: stream-K tiles [sk_tile0, +sk_tiles), whole tiles [0, dp_end)
   float* C; int ldc;
   const float* bias;
   int beta;
@@ -84,8 +84,11 @@ struct Gemm2Params {
 // One unit of work of a CTA pair: k-blocks [kb0, kb1) of one output tile.  Stream-K ranges are cut at
 // cidx * total / ncl and snapped to the tile boundary when they would leave a sliver of < 3 k-blocks.
 struct Seg { int tile, kb0, kb1; };
+// Work of one CTA pair: first its share of the stream-K tiles [sk_tile0, sk_tile0 + sk_tiles) -- an equal contiguous range
+// of their (tile, k-block) iterations -- then whole tiles cidx, cidx + ncl, ... below dp_end.  Pure data-parallel: sk_tiles = 0;
+// pure stream-K: dp_end = 0; hybrid (a last partial wave of tiles): both.
 struct SegIter {
-  int streamk, w, ncl, tiles, num_kb, it, it_end;
+  int w, ncl, num_kb, it, it_end, sk_tile0, dp_end;
   __device__ __forceinline__ static int boundary(int c, int ncl, int tiles, int num_kb) {
     if (c >= ncl) return tiles * num_kb;
     int b = (int)(((long long)c * tiles * num_kb) / ncl);
@@ -94,20 +97,20 @@ struct SegIter {
     else if (num_kb - off < 3) b += num_kb - off;
     return b;
   }
-  __device__ __forceinline__ SegIter(int streamk_, int cidx, int ncl_, int tiles_, int num_kb_)
-      : streamk(streamk_), w(cidx), ncl(ncl_), tiles(tiles_), num_kb(num_kb_), it(0), it_end(0) {
-    if (streamk) { it = boundary(cidx, ncl, tiles, num_kb); it_end = boundary(cidx + 1, ncl, tiles, num_kb); }
+  __device__ __forceinline__ SegIter(int cidx, int ncl_, int num_kb_, int sk_tile0_, int sk_tiles, int dp_end_)
+      : w(cidx), ncl(ncl_), num_kb(num_kb_), it(0), it_end(0), sk_tile0(sk_tile0_), dp_end(dp_end_) {
+    if (sk_tiles > 0) { it = boundary(cidx, ncl, sk_tiles, num_kb); it_end = boundary(cidx + 1, ncl, sk_tiles, num_kb); }
   }
   __device__ __forceinline__ bool next(Seg& s) {
-    if (!streamk) {
-      if (w >= tiles) return false;
-      s.tile = w; s.kb0 = 0; s.kb1 = num_kb; w += ncl;
+    if (it < it_end) {
+      const int t = it / num_kb;
+      s.tile = sk_tile0 + t; s.kb0 = it - t * num_kb;
+      s.kb1 = min(num_kb, s.kb0 + (it_end - it));
+      it += s.kb1 - s.kb0;
       return true;
     }
-    if (it >= it_end) return false;
-    s.tile = it / num_kb; s.kb0 = it - s.tile * num_kb;
-    s.kb1 = min(num_kb, s.kb0 + (it_end - it));
-    it += s.kb1 - s.kb0;
+    if (w >= dp_end) return false;
+    s.tile = w; s.kb0 = 0; s.kb1 = num_kb; w += ncl;
     return true;
   }
 };
@@ -159,7 +162,7 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       int it = 0;
-      SegIter si(p.streamk, cidx, ncl, tiles_mn, num_kb_total);
+      SegIter si(cidx, ncl, num_kb_total, p.sk_tile0, p.sk_tiles, p.dp_end);
       Seg sg;
       while (si.next(sg)) {
         const int rem = sg.tile;
@@ -210,7 +213,7 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     if (leader && lane == 0) {
       const uint32_t idesc = idesc_bf16(256, BNP, !AK, !BKM);
       int it = 0, local = 0;
-      SegIter si(p.streamk, cidx, ncl, tiles_mn, num_kb_total);
+      SegIter si(cidx, ncl, num_kb_total, p.sk_tile0, p.sk_tiles, p.dp_end);
       Seg sg;
       for (; si.next(sg); local++) {
         const int kb_begin = sg.kb0, kb_end = sg.kb1;
@@ -251,7 +254,7 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                         (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
     int local = 0;
-    SegIter si(p.streamk, cidx, ncl, tiles_mn, num_kb_total);
+    SegIter si(cidx, ncl, num_kb_total, p.sk_tile0, p.sk_tiles, p.dp_end);
     Seg sg;
     for (; si.next(sg); local++) {
       const int rem = sg.tile;
@@ -379,17 +382,25 @@ static bool gemm2_launch(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, in
   const int tm = (M + BM - 1) / BM, tmp = (tm + 1) / 2, tn = (N + BNP - 1) / BNP;
   const int num_kb = (K + BK - 1) / BK;
   const int max_cl = g2_num_sms / 2;
-  // fewer tiles than CTA pairs: stream-K -- every pair takes an equal share of the (tile, k-block) iterations and partial
-  // tiles are summed in L2 by TMA reduce-adds (fp32 atomics without the TMA epilogue); needs fp32-only output
+  // Fewer tiles than CTA pairs: stream-K -- every pair takes an equal share of the (tile, k-block) iterations and partial
+  // tiles are summed in L2 by TMA reduce-adds (fp32 atomics without the TMA epilogue); needs fp32-only output.
+  // Between one and three waves of tiles: hybrid -- the whole waves run as whole tiles, the last partial wave as stream-K.
   const int tiles = tmp * tn;
-  bool streamk = !C_hi && tiles * 10 <= max_cl * 7 && num_kb >= 8;  // (>= 70 % of the pairs busy with whole tiles: not worth the zero-fill + second epilogue)
+  int sk_tile0 = 0, sk_tiles = 0, dp_end = tiles;
   int ncl = tiles < max_cl ? tiles : max_cl;
-  if (streamk) {
-    const long long total_it = (long long)tiles * num_kb;
-    long long want = total_it / 4;  // at least ~4 k-blocks per pair
+  bool zero_all = false;
+  int zero_col0 = -1;  // hybrid: zero the output columns from here on
+  static const bool no_hybrid = getenv("LRCN_GEMM_HYBRID") == nullptr;  // measured: no gain on the decoder's shapes (zero-fill + second epilogue), so opt-in
+  if (!C_hi && tiles * 10 <= max_cl * 7 && num_kb >= 8) {  // (>= 70 % of the pairs busy with whole tiles: not worth the zero-fill + second epilogue)
+    long long want = (long long)tiles * num_kb / 4;  // at least ~4 k-blocks per pair
     if (want > max_cl) want = max_cl;
-    if (want <= tiles) streamk = false;
-    else ncl = (int)want;
+    if (want > tiles) { ncl = (int)want; sk_tiles = tiles; dp_end = 0; zero_all = true; }
+  } else if (!C_hi && !no_hybrid && tiles > max_cl && tiles < 3 * max_cl && (tiles % max_cl) != 0) {
+    const int rem = tiles % max_cl;
+    if ((long long)rem * num_kb >= 3ll * max_cl && rem * 10 <= max_cl * 7) {
+      sk_tile0 = tiles - rem; sk_tiles = rem; dp_end = sk_tile0;
+      zero_col0 = (sk_tile0 / tmp) * BNP;
+    }
   }
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   bool ok = true;
@@ -407,12 +418,14 @@ static bool gemm2_launch(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, in
   const bool tma_epi = gemm_tma_epilogue_ok(C, ldc, beta, C_hi);
   CUtensorMap tc = ta_hi;
   if (tma_epi && !get_tensor_map_f32_out(&tc, C, N, M, ldc)) return false;
-  if (streamk && !beta && !c_zeroed) {
+  if (zero_all && !beta && !c_zeroed) {
     if (ldc == N) cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), s);
     else cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, s);
+  } else if (zero_col0 >= 0 && !beta && !c_zeroed) {
+    cudaMemset2DAsync(C + zero_col0, (size_t)ldc * sizeof(float), 0, (size_t)(N - zero_col0) * sizeof(float), M, s);
   }
   Gemm2Params p;
-  p.M = M; p.N = N; p.K = K; p.tiles_mp = tmp; p.tiles_n = tn; p.streamk = streamk ? 1 : 0; p.n_split = n_split;
+  p.M = M; p.N = N; p.K = K; p.tiles_mp = tmp; p.tiles_n = tn; p.sk_tile0 = sk_tile0; p.sk_tiles = sk_tiles; p.dp_end = dp_end; p.n_split = n_split;
   p.C = C; p.ldc = ldc; p.bias = bias; p.beta = beta ? 1 : 0; p.C_hi = C_hi; p.C_lo = C_lo; p.dbg = g_gemm_dbg; p.tma_epi = tma_epi ? 1 : 0;
   const int grid = ncl * 2;
   if (a_kmajor && b_kmajor) launch_pdl(gemm2_bf16x3_kernel<true, true>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, s, ta_hi, ta_lo, tb_hi, tb_lo, tb2_hi, tb2_lo, tc, p);

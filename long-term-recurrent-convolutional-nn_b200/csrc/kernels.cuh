@@ -65,6 +65,9 @@ void z_finish(cudaStream_t s, float* Z, const float* v, int ldv, int R, int B, i
 // LSTM cell forward for one step: gates (pre-activation, [B][4H], order f,i,o,g) are activated in place
 void lstm_cell_fwd(cudaStream_t s, float* gates, const float* c_prev, float* c_out, float* h_out, int B, int H,
                    __nv_bfloat16* h_hi = nullptr, __nv_bfloat16* h_lo = nullptr);
+// generation-only cell (bf16x3 mode, H % 4 == 0): 4 units per thread, fast sigmoid/tanh, gate activations not written back
+void lstm_cell_gen(cudaStream_t s, const float* gates, const float* c_prev, float* c_out, float* h_out, int B, int H, __nv_bfloat16* h_hi,
+                   __nv_bfloat16* h_lo);
 // LSTM cell backward for one step; gates buffer holds activations and receives dG in place
 void lstm_cell_bwd(cudaStream_t s, float* gates, const float* c_prev, const float* c_cur, const float* dh_in,
                    const float* dh_rec /*nullable*/, float* dc /*in/out*/, bool first /*dc,dh_rec are zero*/,

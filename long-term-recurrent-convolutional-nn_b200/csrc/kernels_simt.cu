@@ -3,6 +3,8 @@
 // scatter-add, fused Adam (+bf16 hi/lo shadow refresh), beam-search selection kernels.
 // Reference semantics: lrcn.jl:528-581 (lstm, lrcn, loss), :644-678 (beam_search), Knet Adam.
 #include "kernels.cuh"
+
+#include <stdlib.h>
 #include <math.h>
 
 namespace lrcn {
@@ -241,6 +243,46 @@ __global__ void lstm_cell_fwd_kernel(float* __restrict__ gates, const float* __r
   const float hv = o * tanhf(c);
   h_out[idx] = hv;
   if (h_hi) { __nv_bfloat16 hh, ll; split_one(hv, hh, ll); h_hi[idx] = hh; h_lo[idx] = ll; }
+}
+// generation (bf16x3 mode, H % 4 == 0): 4 units per thread, fast sigmoid / tanh like the tcgen05 step kernels, and the gate
+// activations are NOT written back (only training's backward pass needs them)
+__device__ __forceinline__ float sigm_fast_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast_f(float x) {
+  const float ax = fabsf(x), e = __expf(-2.0f * ax);
+  return copysignf(__fdividef(1.0f - e, 1.0f + e), x);
+}
+__global__ void lstm_cell_gen_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev, float* __restrict__ c_out,
+                                     float* __restrict__ h_out, int B, int H, __nv_bfloat16* __restrict__ h_hi,
+                                     __nv_bfloat16* __restrict__ h_lo) {
+  const int H4 = H >> 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * H4) return;
+  const int i = idx / H4, j = 4 * (idx - i * H4);
+  const float* g = gates + (size_t)i * 4 * H + j;
+  const float4 gf = *reinterpret_cast<const float4*>(g), gi = *reinterpret_cast<const float4*>(g + H);
+  const float4 go = *reinterpret_cast<const float4*>(g + 2 * H), gc = *reinterpret_cast<const float4*>(g + 3 * H);
+  const float4 cp = *reinterpret_cast<const float4*>(c_prev + (size_t)i * H + j);
+  const float xf[4] = {gf.x, gf.y, gf.z, gf.w}, xi[4] = {gi.x, gi.y, gi.z, gi.w}, xo[4] = {go.x, go.y, go.z, go.w}, xc[4] = {gc.x, gc.y, gc.z, gc.w};
+  const float cpv[4] = {cp.x, cp.y, cp.z, cp.w};
+  float c[4], hv[4];
+  __nv_bfloat16 hh[4], ll[4];
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    c[e] = cpv[e] * sigm_fast_f(xf[e]) + sigm_fast_f(xi[e]) * tanh_fast_f(xc[e]);
+    hv[e] = sigm_fast_f(xo[e]) * tanh_fast_f(c[e]);
+    split_one(hv[e], hh[e], ll[e]);
+  }
+  const size_t o = (size_t)i * H + j;
+  *reinterpret_cast<float4*>(c_out + o) = make_float4(c[0], c[1], c[2], c[3]);
+  *reinterpret_cast<float4*>(h_out + o) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+  *reinterpret_cast<uint2*>(h_hi + o) = *reinterpret_cast<uint2*>(hh);
+  *reinterpret_cast<uint2*>(h_lo + o) = *reinterpret_cast<uint2*>(ll);
+}
+void lstm_cell_gen(cudaStream_t s, const float* gates, const float* c_prev, float* c_out, float* h_out, int B, int H, __nv_bfloat16* h_hi,
+                   __nv_bfloat16* h_lo) {
+  const int n = B * (H / 4);
+  lstm_cell_gen_kernel<<<(n + 255) / 256, 256, 0, s>>>(gates, c_prev, c_out, h_out, B, H, h_hi, h_lo);
+  count_launch();
 }
 void lstm_cell_fwd(cudaStream_t s, float* gates, const float* c_prev, float* c_out, float* h_out, int B, int H, __nv_bfloat16* h_hi,
                    __nv_bfloat16* h_lo) {
@@ -898,10 +940,185 @@ __global__ void __launch_bounds__(512) beam_row_topk_kernel(const float* __restr
     }
   }
 }
+// Second-generation threshold select.  Like beam_row_topk_kernel the row is staged once in shared memory (40 KB at V = 10000,
+// so 4 CTAs share an SM), but max and normaliser come from ONE block reduction of per-thread (max, sum exp) pairs and tau from
+// per-warp top-K lists of the thread maxima: 4 block barriers per row instead of ~12.  Same results on given probabilities.
+constexpr int TOPK_MAXK = 11;
+template <bool FROM_LOGITS, int THREADS>
+__global__ void __launch_bounds__(THREADS) beam_row_topk2_kernel(const float* __restrict__ in, int ld, int R, int V, int K,
+                                                             const float* __restrict__ parent_prob, int* __restrict__ cand_tok,
+                                                             float* __restrict__ cand_score, float* __restrict__ cand_lp) {
+  extern __shared__ __align__(16) float row[];
+  constexpr int NW = THREADS / 32;
+  __shared__ float2 wred[NW];
+  __shared__ float wtop[NW][TOPK_MAXK + 1];
+  __shared__ float cv[TOPK_CAP];
+  __shared__ int ci[TOPK_CAP];
+  __shared__ int ccount;
+  __shared__ TopPair pred[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = blockIdx.x; r < R; r += gridDim.x) {  // persistent over rows
+    const float* a = in + (size_t)r * ld;
+    __syncthreads();  // the previous row's shared state is no longer read
+    if (threadIdx.x == 0) ccount = 0;
+    float tmax = -INFINITY;
+    const int V4 = ((reinterpret_cast<uintptr_t>(a) & 15) == 0) ? (V >> 2) : 0;
+    for (int q = threadIdx.x; q < V4; q += blockDim.x) {
+      const float4 x = *reinterpret_cast<const float4*>(a + 4 * q);
+      *reinterpret_cast<float4*>(row + 4 * q) = x;
+      tmax = fmaxf(fmaxf(tmax, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
+    }
+    for (int j = 4 * V4 + threadIdx.x; j < V; j += blockDim.x) { const float x = a[j]; row[j] = x; tmax = fmaxf(tmax, x); }
+    // (max, sum exp) of this thread's own elements (it re-reads what it wrote: no barrier needed), then of the warp
+    if (FROM_LOGITS) {
+      float m = tmax, ssum = 0.f;
+      if (tmax != -INFINITY) {
+        for (int q = threadIdx.x; q < V4; q += blockDim.x) {
+          const float4 x = *reinterpret_cast<const float4*>(row + 4 * q);
+          ssum += (__expf(x.x - tmax) + __expf(x.y - tmax)) + (__expf(x.z - tmax) + __expf(x.w - tmax));
+        }
+        for (int j = 4 * V4 + threadIdx.x; j < V; j += blockDim.x) ssum += __expf(row[j] - tmax);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, ssum, o);
+        const float mn = fmaxf(m, m2);
+        ssum = (m == -INFINITY ? 0.f : ssum * __expf(m - mn)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mn));
+        m = mn;
+      }
+      if (lane == 0) wred[warp] = make_float2(m, ssum);
+    }
+    // per-warp top-K of the thread maxima (K rounds, one lane removed per round)
+    {
+      float cur = tmax;
+      for (int k = 0; k < K; k++) {
+        float best = cur;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+        const unsigned int holders = __ballot_sync(0xffffffffu, cur == best);
+        if (lane == __ffs(holders) - 1) { cur = -INFINITY; wtop[warp][k] = best; }
+      }
+    }
+    __syncthreads();
+    float mx = 0.f, lse = 0.f;
+    if (FROM_LOGITS) {
+      float mm = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < NW; w++) mm = fmaxf(mm, wred[w].x);
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; w++) tot += wred[w].x == -INFINITY ? 0.f : wred[w].y * __expf(wred[w].x - mm);
+      mx = mm; lse = logf(tot);
+    }
+    // tau = K-th largest of the NW*K per-warp values (every warp computes it redundantly): a lower bound of the K-th largest element
+    float tau;
+    {
+      float mine[6];  // 16 * 11 = 176 <= 6 * 32
+#pragma unroll
+      for (int q = 0; q < 6; q++) {
+        const int c = lane + 32 * q;
+        mine[q] = (c < NW * K) ? wtop[c / K][c % K] : -INFINITY;
+      }
+      tau = -INFINITY;
+      for (int k = 0; k < K; k++) {
+        float best = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < 6; q++) best = fmaxf(best, mine[q]);
+        float wb = best;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wb = fmaxf(wb, __shfl_xor_sync(0xffffffffu, wb, o));
+        tau = wb;
+        const unsigned int holders = __ballot_sync(0xffffffffu, best == wb);
+        if (lane == __ffs(holders) - 1) {
+          bool removed = false;
+#pragma unroll
+          for (int q = 0; q < 6; q++) if (!removed && mine[q] == wb) { mine[q] = -INFINITY; removed = true; }
+        }
+      }
+    }
+    // candidates: every element >= tau (own elements again)
+    for (int q = threadIdx.x; q < V4; q += blockDim.x) {
+      const float4 x = *reinterpret_cast<const float4*>(row + 4 * q);
+      const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int e = 0; e < 4; e++)
+        if (xs[e] >= tau) {
+          const int pos = atomicAdd(&ccount, 1);
+          if (pos < TOPK_CAP) { cv[pos] = xs[e]; ci[pos] = 4 * q + e; }
+        }
+    }
+    for (int j = 4 * V4 + threadIdx.x; j < V; j += blockDim.x) {
+      const float x = row[j];
+      if (x >= tau) {
+        const int pos = atomicAdd(&ccount, 1);
+        if (pos < TOPK_CAP) { cv[pos] = x; ci[pos] = j; }
+      }
+    }
+    __syncthreads();
+    const int nc = ccount;
+    const float pp = parent_prob[r];
+    if (nc <= TOPK_CAP) {
+      if (warp == 0) {
+        constexpr int PER = TOPK_CAP / 32;
+        float pv[PER]; int pi[PER];
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+          const int c = lane + 32 * q;
+          pv[q] = -INFINITY; pi[q] = 0x7fffffff;
+          if (c < nc) { const float x = cv[c]; pv[q] = FROM_LOGITS ? expf((x - mx) - lse) : x; pi[q] = ci[c]; }
+        }
+        for (int k = 0; k < K; k++) {
+          TopPair best; best.v = -INFINITY; best.i = 0x7fffffff;
+#pragma unroll
+          for (int q = 0; q < PER; q++) { TopPair c; c.v = pv[q]; c.i = pi[q]; best = top_better(best, c); }
+          best = warp_top(best);
+#pragma unroll
+          for (int q = 0; q < PER; q++) if (pi[q] == best.i) { pv[q] = -INFINITY; pi[q] = 0x7fffffff; }  // indices are unique
+          if (lane == 0) {
+            cand_tok[(size_t)r * K + k] = best.i;
+            cand_score[(size_t)r * K + k] = __fmul_rn(best.v, pp);  // pmaxes = ynorm[xmaxes]*current_probability (lrcn.jl:657)
+            cand_lp[(size_t)r * K + k] = FROM_LOGITS ? ((row[best.i] - mx) - lse) : logf(best.v);
+          }
+        }
+      }
+    } else {
+      // exact fallback: K rounds of block argmax over the whole row on the probabilities themselves
+      if (FROM_LOGITS) {
+        for (int j = threadIdx.x; j < V; j += blockDim.x) row[j] = expf((row[j] - mx) - lse);
+      }
+      for (int k = 0; k < K; k++) {
+        __syncthreads();
+        TopPair p; p.v = -INFINITY; p.i = 0x7fffffff;
+        for (int j = threadIdx.x; j < V; j += blockDim.x) { TopPair c; c.v = row[j]; c.i = j; p = top_better(p, c); }
+        p = block_top(p, pred);
+        if (threadIdx.x == 0) {
+          cand_tok[(size_t)r * K + k] = p.i;
+          cand_score[(size_t)r * K + k] = __fmul_rn(p.v, pp);
+          cand_lp[(size_t)r * K + k] = logf(p.v);
+          row[p.i] = -1.f;  // exclude from later rounds
+        }
+      }
+    }
+  }
+}
 static void beam_topk_launch(cudaStream_t s, bool from_logits, const float* in, int ld, int R, int V, int K,
                              const float* parent_prob, int* cand_tok, float* cand_score, float* cand_lp) {
   const size_t smem = ((size_t)V + 4) * sizeof(float);
   const int grid = R < 148 * 4 ? R : 148 * 4;
+  static const bool v1 = getenv("LRCN_TOPK_V1") != nullptr;
+  if (!v1 && K <= TOPK_MAXK) {
+    static const int th = getenv("LRCN_TOPK_THREADS") ? atoi(getenv("LRCN_TOPK_THREADS")) : 256;
+    const int g2 = R < 148 * 8 ? R : 148 * 8;
+    if (th == 512) {
+      if (from_logits) beam_row_topk2_kernel<true, 512><<<grid, 512, smem, s>>>(in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+      else beam_row_topk2_kernel<false, 512><<<grid, 512, smem, s>>>(in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+    } else {
+      if (from_logits) beam_row_topk2_kernel<true, 256><<<g2, 256, smem, s>>>(in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+      else beam_row_topk2_kernel<false, 256><<<g2, 256, smem, s>>>(in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+    }
+    count_launch();
+    return;
+  }
   if (from_logits) beam_row_topk_kernel<true><<<grid, 512, smem, s>>>(in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
   else beam_row_topk_kernel<false><<<grid, 512, smem, s>>>(in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
   count_launch();
@@ -1023,6 +1240,10 @@ void init_simt_kernels() {
   cudaFuncSetAttribute(softmax_ce_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
   cudaFuncSetAttribute(beam_row_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(beam_row_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(beam_row_topk2_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(beam_row_topk2_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(beam_row_topk2_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(beam_row_topk2_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
 }  // namespace lrcn

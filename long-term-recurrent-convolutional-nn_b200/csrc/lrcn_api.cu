@@ -971,11 +971,13 @@ static void enqueue_beam_step(lrcn_handle* h, int n_img, int K, int step, int nw
     ld1 = E + H1; ld2 = 2 * C + H2;
     gather_embed(s, Wp(h, 7), h->g_last, R, E, xh1, h->d_sc, false, SH(h, xh1).hi, SH(h, xh1).lo, ld1);     // Wemb[tok:tok,:]  lrcn.jl:650
     gemm(h, true, true, R, 4 * H1, E + H1, xh1, ld1, Wp(h, 1), E + H1, g1, 4 * H1, false, Wp(h, 2));        // hcat(x,h)*W .+ b  lrcn.jl:529
-    lstm_cell_fwd(s, g1, c1a, c1b, h1b, R, H1, SH(h, h1b).hi, SH(h, h1b).lo);
+    if (H1 % 4 == 0) lstm_cell_gen(s, g1, c1a, c1b, h1b, R, H1, SH(h, h1b).hi, SH(h, h1b).lo);
+    else lstm_cell_fwd(s, g1, c1a, c1b, h1b, R, H1, SH(h, h1b).hi, SH(h, h1b).lo);
     gemm(h, true, true, R, C, H1, h1b, H1, Wp(h, 5), H1, xh2, ld2, false, nullptr);                           // x*w[end-4]  lrcn.jl:545
     z_finish(s, xh2, v, ldv, R, -K, C, h->d_sc, false, SH(h, xh2).hi, SH(h, xh2).lo, ld2);                   // hcat(x,x_cnn)  lrcn.jl:546
     gemm(h, true, true, R, 4 * H2, 2 * C + H2, xh2, ld2, Wp(h, 3), 2 * H2, g2, 4 * H2, false, Wp(h, 4));
-    lstm_cell_fwd(s, g2, c2a, c2b, h2b, R, H2, SH(h, h2b).hi, SH(h, h2b).lo);
+    if (H2 % 4 == 0) lstm_cell_gen(s, g2, c2a, c2b, h2b, R, H2, SH(h, h2b).hi, SH(h, h2b).lo);
+    else lstm_cell_fwd(s, g2, c2a, c2b, h2b, R, H2, SH(h, h2b).hi, SH(h, h2b).lo);
     h1a = xh1 + E;       // the gathered parent states go straight into the h columns of the next step's operands
     h2a = xh2 + 2 * C;
   } else {
