@@ -394,3 +394,68 @@ def test_golden_fixture_through_the_c_abi(prec):
                 same += 1
                 assert abs(prob[i] - z["beam_prob"][i]) <= 1e-4 * abs(z["beam_prob"][i])
         assert same >= B - 1  # an untrained net has near-ties; the bit-exact selection logic is tested on identical probabilities
+
+
+def test_full_size_properties_flickr30k_config():
+    """BASELINE.json configs[1] at full size (E=H=512, V=7731, 256 captions, l=12), where the oracle is too slow to run:
+    size-independent properties of the hot path instead (SURVEY section 8c / task section 3)."""
+    if abi.PREC_BF16X3 not in PRECS:
+        pytest.skip("tcgen05 path only")
+    E = H = 512
+    V, B, l, n_img = 7731, 256, 12, 512
+    T = l + 1
+    model = synth.initweights([H, H], V, E, seed=1)
+    feats = synth.features(n_img, seed=2)
+    ids = np.arange(1, n_img + 1, dtype=np.int64)
+    img = synth.image_ids(B, n_img)
+    tok = synth.tokens(l, B, V, zipf=True)
+    with open_handle(E, H, H, V, B, 28, abi.PREC_BF16X3) as h:
+        h.set_model(model)
+        h.load_features(0, ids, feats)
+        # (1) reproducibility of the forward pass (split-K partial sums land in any order: not bitwise) and a fixed answer
+        #     for Wout = 0, bout = 0: loss = ln V (lrcn.jl:562-580)
+        s1, n1 = h.loss(0, img, tok)
+        s2, n2 = h.loss(0, img, tok)
+        assert abs(s1 - s2) <= 1e-6 * abs(s1) and n1 == n2 == B * T
+        m0 = [w.copy() for w in model]
+        m0[7][:] = 0
+        m0[8][:] = 0
+        h.set_model(m0)
+        s0, _ = h.loss(0, img, tok)
+        assert abs(-s0 / (B * T) - np.log(V)) < 1e-5 * np.log(V)
+        # (2) softmax - onehot sums to zero over the vocabulary: so does the output-bias gradient
+        h.set_model(model)
+        L = h.grad(0, img, tok)
+        g = [h.get_grad(k) for k in range(1, 10)]
+        assert abs(L - (-s1 / (B * T))) < 1e-6 * abs(L)
+        assert abs(g[8].astype(np.float64).sum()) < 1e-4 * np.abs(g[8]).astype(np.float64).sum()
+        # every embedding row that is not an input token has exactly zero gradient (dense zero + add-at-index adjoint)
+        used = np.zeros(V, bool)
+        used[tok.ravel() - 1] = True
+        used[O.BOS - 1] = True
+        assert not g[6][~used].any() and np.abs(g[6][used]).max() > 0
+        # (3) gradients are sums over captions: the gradient of the batch is the mean of the gradients of its two halves
+        #     (different tile counts / stream-K decompositions / LSTM tile occupancy on the same kernels)
+        ga = [None] * 9
+        gb = [None] * 9
+        La = h.grad(0, img[:B // 2], np.ascontiguousarray(tok[:, :B // 2]))
+        ga = [h.get_grad(k) for k in range(1, 10)]
+        Lb = h.grad(0, img[B // 2:], np.ascontiguousarray(tok[:, B // 2:]))
+        gb = [h.get_grad(k) for k in range(1, 10)]
+        assert abs(0.5 * (La + Lb) - L) < 1e-5 * abs(L)
+        for k in range(9):
+            assert relerr(0.5 * (ga[k] + gb[k]), g[k]) < 1e-4, k
+        # (4) first Adam step moves every weight with a non-negligible gradient by lr (Knet Adam, lrcn.jl:394,402)
+        h.grad(0, img, tok)
+        g = [h.get_grad(k) for k in range(1, 10)]
+        h.train_step(0, img, tok)
+        w1 = h.get_model()
+        for k in (0, 2, 7):  # step 1: m/(1-b1) = g, v/(1-b2) = g^2  =>  dw = -lr * g / (|g| + eps)
+            ga_ = np.abs(g[k].astype(np.float64))
+            want = 1e-3 * ga_ / (ga_ + 1e-8)
+            got = np.abs(w1[k].astype(np.float64) - model[k].astype(np.float64))
+            assert (ga_ > 1e-7).any()
+            # fp32 weight ulp ~4e-9; the step recomputes the gradient and partial sums land in any order, so entries that are
+            # sums cancelling to ~1e-12 carry percent-level noise: check where the gradient is well above that
+            bad = (np.abs(got - want) > 1e-2 * want + 1e-8) & (ga_ > 1e-9)
+            assert bad.sum() == 0, (k, int(bad.sum()), float(np.abs(got - want).max()), got[bad][:4], want[bad][:4], ga_[bad][:4])
