@@ -262,6 +262,16 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # ---- setup: capture the CUDA graph of every step shape (one per distinct caption length) before anything is timed --
+    # graph capture + instantiation is this framework's "compile" step and costs milliseconds per shape
+    seen = set()
+    for s_, (_, _, l_) in enumerate(batches):
+        if l_ not in seen:
+            seen.add(l_)
+            h.train_step_staged(s_, 0.0, 7)
+    h.sync()
+    barrier()
+
     # ---- device-resident run: `value`
     for i in range(args.warmup):
         h.train_step_staged(i % N_SLOTS, 0.0, i)
