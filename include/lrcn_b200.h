@@ -141,7 +141,7 @@ LRCN_API int lrcn_comm_init(lrcn_handle* h, const char id[LRCN_COMM_ID_BYTES], i
  * its gradient arena (CUDA IPC handles), the launcher all-gathers the blobs, every rank imports all of them.  Afterwards
  * the gradient allreduce of lrcn_train_step / lrcn_grad is ONE owner-computes kernel over NVLink peer memory between two
  * flag barriers (csrc/dp_p2p.cu) instead of NCCL kernels; lrcn_comm_init is then optional.  LRCN_DP_NCCL=1 keeps NCCL. */
-#define LRCN_P2P_BLOB_BYTES 256
+#define LRCN_P2P_BLOB_BYTES 512
 LRCN_API int lrcn_p2p_export(lrcn_handle* h, char blob[LRCN_P2P_BLOB_BYTES]);
 LRCN_API int lrcn_p2p_import(lrcn_handle* h, const char* blobs /* nranks x LRCN_P2P_BLOB_BYTES, rank order */, int rank, int nranks);
 

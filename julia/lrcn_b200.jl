@@ -172,9 +172,9 @@ function comm_unique_id()
     check(ccall((:lrcn_comm_unique_id, lib), Cint, (Ptr{UInt8},), id)); return id
 end
 comm_init!(net, id, rank, nranks) = check(ccall((:lrcn_comm_init, lib), Cint, (Ptr{Void}, Ptr{UInt8}, Cint, Cint), net.handle, id, rank, nranks))
-# peer-memory exchange: every rank exports a 256-byte blob, the launcher all-gathers them (rank order), every rank imports all
+# peer-memory exchange: every rank exports a 512-byte blob, the launcher all-gathers them (rank order), every rank imports all
 function p2p_export(net)
-    blob = zeros(UInt8, 256)
+    blob = zeros(UInt8, 512)
     check(ccall((:lrcn_p2p_export, lib), Cint, (Ptr{Void}, Ptr{UInt8}), net.handle, blob)); return blob
 end
 p2p_import!(net, blobs::Vector{UInt8}, rank, nranks) = check(ccall((:lrcn_p2p_import, lib), Cint, (Ptr{Void}, Ptr{UInt8}, Cint, Cint), net.handle, blobs, rank, nranks))

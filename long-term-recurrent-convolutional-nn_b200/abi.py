@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "liblrcn_b200.so")
 PREC_FP32, PREC_BF16X3 = 0, 1
 OK, ERR_ARG, ERR_CUDA, ERR_NCCL, ERR_MISSING, ERR_STATE = 0, 1, 2, 3, 4, 5
 COMM_ID_BYTES = 128
-P2P_BLOB_BYTES = 256
+P2P_BLOB_BYTES = 512
 
 
 class LrcnError(RuntimeError):

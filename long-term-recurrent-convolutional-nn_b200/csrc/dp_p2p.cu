@@ -73,13 +73,73 @@ __global__ void __launch_bounds__(256) allreduce_p2p_kernel(P2PPeers peers, size
   __threadfence_system();  // my stores into peer memory are performed before this kernel ends (B2 follows)
 }
 
-void dp_p2p_allreduce(cudaStream_t s, const P2PPeers& peers, size_t n_floats, unsigned int* epoch_ctr, double* loss_total) {
-  const size_t n4 = n_floats / 4;  // arena sizes are multiples of 64 floats
-  const size_t per = (n4 + peers.nranks - 1) / peers.nranks;
-  const size_t b = per * peers.rank < n4 ? per * peers.rank : n4;
+// reduce-scatter + Adam + all-gather in one kernel: the owner of a shard sums its gradients over all ranks, updates ITS slice of
+// m, v and w exactly like adam_kernel (same operation order: replicas stay bit-identical to the replicated update) and stores
+// the new weights into every rank's arena.  Adam costs 1/N per GPU and the NVLink volume is the same as the allreduce's.
+__global__ void __launch_bounds__(256) adam_p2p_kernel(P2PPeers peers, size_t begin4, size_t end4, float4* __restrict__ m, float4* __restrict__ v,
+                                                       const StepScalars* __restrict__ sc, double* loss_total) {
+  const int N = peers.nranks;
+  const float b1 = sc->beta1, b2 = sc->beta2, lr = sc->lr, eps = sc->eps, d1 = sc->adam_d1, d2 = sc->adam_d2;
+  const float ob1 = sc->one_m_beta1, ob2 = sc->one_m_beta2;
+  const float4* wl = reinterpret_cast<const float4*>(peers.w[peers.rank]);
+  for (size_t i = begin4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < end4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int p = 0; p < N; p++) {
+      const float4 x = ld_peer_f4(reinterpret_cast<const float4*>(peers.g[p]) + i);
+      G.x += x.x; G.y += x.y; G.z += x.z; G.w += x.w;
+    }
+    float4 W = wl[i], Mv = m[i], Vv = v[i];
+    float* wp = reinterpret_cast<float*>(&W);
+    const float* gp = reinterpret_cast<const float*>(&G);
+    float* mp = reinterpret_cast<float*>(&Mv);
+    float* vp = reinterpret_cast<float*>(&Vv);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float mm = __fadd_rn(__fmul_rn(b1, mp[k]), __fmul_rn(ob1, gp[k]));
+      const float vv = __fadd_rn(__fmul_rn(b2, vp[k]), __fmul_rn(ob2, __fmul_rn(gp[k], gp[k])));
+      const float upd = __fdiv_rn(__fdiv_rn(mm, d1), __fadd_rn(__fsqrt_rn(__fdiv_rn(vv, d2)), eps));
+      wp[k] = __fsub_rn(wp[k], __fmul_rn(lr, upd));
+      mp[k] = mm; vp[k] = vv;
+    }
+    m[i] = Mv; v[i] = Vv;
+    for (int p = 0; p < N; p++) reinterpret_cast<float4*>(peers.w[p])[i] = W;
+    reinterpret_cast<float4*>(peers.g[peers.rank])[i] = G;  // the summed gradient of the owned shard stays readable (lrcn_get_grad)
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && loss_total) {
+    double t = 0.0;
+    for (int p = 0; p < N; p++) {
+      double x;
+      asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(x) : "l"(&peers.ctl[p]->loss_partial) : "memory");
+      t += x;
+    }
+    *loss_total = t;
+  }
+  __threadfence_system();
+}
+
+void dp_p2p_shard(size_t n_floats, int nranks, int r, size_t* begin, size_t* end) {
+  const size_t n4 = n_floats / 4, per = (n4 + nranks - 1) / nranks;
+  const size_t b = per * r < n4 ? per * r : n4;
   const size_t e = b + per < n4 ? b + per : n4;
+  *begin = 4 * b; *end = 4 * e;
+}
+
+void dp_p2p_adam(cudaStream_t s, const P2PPeers& peers, size_t n_floats, unsigned int* epoch_ctr, double* loss_total, float* m, float* v,
+                 const StepScalars* sc) {
+  size_t b, e;
+  dp_p2p_shard(n_floats, peers.nranks, peers.rank, &b, &e);
   xgpu_barrier_kernel<<<1, 32, 0, s>>>(peers, epoch_ctr);
-  allreduce_p2p_kernel<<<148 * 4, 256, 0, s>>>(peers, b, e, loss_total);
+  adam_p2p_kernel<<<148 * 4, 256, 0, s>>>(peers, b / 4, e / 4, reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), sc, loss_total);
+  xgpu_barrier_kernel<<<1, 32, 0, s>>>(peers, epoch_ctr);
+  if (g_counter) g_counter->n += 3;
+}
+
+void dp_p2p_allreduce(cudaStream_t s, const P2PPeers& peers, size_t n_floats, unsigned int* epoch_ctr, double* loss_total) {
+  size_t b, e;  // arena sizes are multiples of 64 floats
+  dp_p2p_shard(n_floats, peers.nranks, peers.rank, &b, &e);
+  xgpu_barrier_kernel<<<1, 32, 0, s>>>(peers, epoch_ctr);
+  allreduce_p2p_kernel<<<148 * 4, 256, 0, s>>>(peers, b / 4, e / 4, loss_total);
   xgpu_barrier_kernel<<<1, 32, 0, s>>>(peers, epoch_ctr);
   if (g_counter) g_counter->n += 3;
 }

@@ -149,9 +149,15 @@ struct P2PCtl {              // one per rank, in a small exported allocation
   unsigned int flags[64];    // flags[q]: last barrier epoch signalled by rank q
   double loss_partial;       // this rank's fp64 sum of token log-probs of the current step
 };
-struct P2PPeers { float* g[LRCN_P2P_MAX_RANKS]; P2PCtl* ctl[LRCN_P2P_MAX_RANKS]; int nranks, rank; };
+struct P2PPeers { float* g[LRCN_P2P_MAX_RANKS]; float* w[LRCN_P2P_MAX_RANKS]; P2PCtl* ctl[LRCN_P2P_MAX_RANKS]; int nranks, rank; };
 // barrier, in-place allreduce(sum) of the gradient arena (n_floats) + loss total, barrier
 void dp_p2p_allreduce(cudaStream_t s, const P2PPeers& peers, size_t n_floats, unsigned int* epoch_ctr, double* loss_total);
+// training step: barrier, then every rank sums ITS shard of the gradient over all ranks, applies Adam to that shard (m, v are
+// this rank's arrays; only the owned shard is kept current) and stores the new weights into every rank's arena, barrier
+void dp_p2p_adam(cudaStream_t s, const P2PPeers& peers, size_t n_floats, unsigned int* epoch_ctr, double* loss_total, float* m, float* v,
+                 const StepScalars* sc);
+// [begin, end) of rank r's shard, in floats
+void dp_p2p_shard(size_t n_floats, int nranks, int r, size_t* begin, size_t* end);
 // diagnostics (probe_mma.cu): clocks to issue / to complete a chain of n_mma tcgen05.mma M x N x 16 from resident smem operands
 bool probe_mma(cudaStream_t s, int M, int N, int n_mma, int commit_every, int issuers, long long* issue_clk, long long* total_clk);
 

@@ -130,7 +130,10 @@ struct lrcn_handle {
   P2PPeers peers{};
   bool p2p_ready = false;
   bool loss_is_total = false;       // last step summed the loss over ranks into d_loss_total
-  void* p2p_opened[2 * LRCN_P2P_MAX_RANKS] = {};  // IPC mappings to close
+  void* p2p_opened[5 * LRCN_P2P_MAX_RANKS] = {};  // IPC mappings to close
+  float* peer_m[LRCN_P2P_MAX_RANKS] = {};
+  float* peer_v[LRCN_P2P_MAX_RANKS] = {};
+  bool adam_sharded = false;          // m, v are current only in each owner's shard (gathered on lrcn_get_adam_state)
   unsigned int* d_counters = nullptr;  // per-m-tile grid-barrier counters of the persistent LSTM kernels
   unsigned long long* d_trace = nullptr;  // LRCN_SEQ_TRACE=1: per-step timeline of the layer-2 forward sequence kernel
   Slot slots[64];
@@ -462,6 +465,22 @@ extern "C" int lrcn_get_adam_state(lrcn_handle* h, int idx, int which, float* p,
   int rc = check_shape(h, idx, p, rows, cols);
   if (rc) return rc;
   if (which != 0 && which != 1) return fail(LRCN_ERR_ARG, "which must be 0 (m) or 1 (v)");
+  if (h->adam_sharded) {
+    // peer-memory data parallelism keeps m, v current only in each owner's shard: collect the other shards from their owners
+    // (all ranks must be idle, e.g. at a checkpoint barrier)
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < h->nranks; r++) {
+      if (r == h->rank) continue;
+      size_t b, e;
+      dp_p2p_shard(h->P, h->nranks, r, &b, &e);
+      if (e > b) {
+        CK(cudaMemcpy(h->m + b, h->peer_m[r] + b, (e - b) * 4, cudaMemcpyDefault));
+        CK(cudaMemcpy(h->v + b, h->peer_v[r] + b, (e - b) * 4, cudaMemcpyDefault));
+      }
+    }
+    h->adam_sharded = false;
+  }
   return download(h, which ? h->v : h->m, idx, p);
 }
 extern "C" int lrcn_set_adam_state(lrcn_handle* h, int idx, int which, const float* p, int64_t rows, int64_t cols) {
@@ -755,13 +774,21 @@ static int run_step(lrcn_handle* h, int split, int B, int l, float pdrop, uint64
   static const bool force_nccl = getenv("LRCN_DP_NCCL") != nullptr;
   if (h->p2p_ready && !force_nccl) {
     h->loss_is_total = true;
+    static const bool replicated = getenv("LRCN_DP_REPLICATED_ADAM") != nullptr;
+    if (mode == 2 && !replicated) h->adam_sharded = true;
     // backward pass, then ONE owner-computes exchange kernel over NVLink peer memory between two flag barriers (dp_p2p.cu),
     // then the replicated Adam: no NCCL kernels competing for SMs with the persistent GEMM / LSTM kernels
     return run_cached(h, std::make_tuple(mode == 2 ? 22 : 21, B, l, fl), [&] {
       enqueue_forward(h, split, B, l, true);
       for (int seg = 1; seg <= 3; seg++) enqueue_backward_seg(h, B, l, true, seg);
-      dp_p2p_allreduce(h->stream, h->peers, h->P, h->d_epoch, h->d_loss_total);
-      if (mode == 2) enqueue_adam(h);
+      if (mode == 2 && !replicated) {
+        // reduce-scatter + Adam on the owned shard + all-gather of the new weights in one kernel; then the local bf16 shadows
+        dp_p2p_adam(h->stream, h->peers, h->P, h->d_epoch, h->d_loss_total, h->m, h->v, h->d_sc);
+        if (h->bf16mode) split_bf16(h->stream, h->w, h->P, h->w_hi, h->w_lo);
+      } else {
+        dp_p2p_allreduce(h->stream, h->peers, h->P, h->d_epoch, h->d_loss_total);
+        if (mode == 2) enqueue_adam(h);
+      }
     });
   }
   if (!h->comm) return fail(LRCN_ERR_ARG, "data-parallel group not initialised (lrcn_comm_init or lrcn_p2p_import)");
@@ -1115,7 +1142,7 @@ extern "C" int lrcn_comm_init(lrcn_handle* h, const char id[LRCN_COMM_ID_BYTES],
 struct P2PBlob {  // LRCN_P2P_BLOB_BYTES
   int magic, device;
   unsigned long long arena_floats;
-  cudaIpcMemHandle_t g, ctl;
+  cudaIpcMemHandle_t g, ctl, w, m, v;
 };
 static_assert(sizeof(P2PBlob) <= LRCN_P2P_BLOB_BYTES, "blob too large");
 extern "C" int lrcn_p2p_export(lrcn_handle* h, char blob[LRCN_P2P_BLOB_BYTES]) {
@@ -1126,6 +1153,9 @@ extern "C" int lrcn_p2p_export(lrcn_handle* h, char blob[LRCN_P2P_BLOB_BYTES]) {
   b.magic = 0x4C524350; b.device = h->cfg.device; b.arena_floats = h->P;
   CK(cudaIpcGetMemHandle(&b.g, h->g));
   CK(cudaIpcGetMemHandle(&b.ctl, h->p2p_ctl));
+  CK(cudaIpcGetMemHandle(&b.w, h->w));
+  CK(cudaIpcGetMemHandle(&b.m, h->m));
+  CK(cudaIpcGetMemHandle(&b.v, h->v));
   memset(blob, 0, LRCN_P2P_BLOB_BYTES);
   memcpy(blob, &b, sizeof b);
   return LRCN_OK;
@@ -1142,13 +1172,16 @@ extern "C" int lrcn_p2p_import(lrcn_handle* h, const char* blobs, int rank, int 
     P2PBlob b;
     memcpy(&b, blobs + (size_t)p * LRCN_P2P_BLOB_BYTES, sizeof b);
     if (b.magic != 0x4C524350 || b.arena_floats != h->P) return fail(LRCN_ERR_ARG, "blob %d does not describe a handle of this model", p);
-    if (p == rank) { pe.g[p] = h->g; pe.ctl[p] = h->p2p_ctl; continue; }
-    void *pg = nullptr, *pc = nullptr;
-    cudaError_t e = cudaIpcOpenMemHandle(&pg, b.g, cudaIpcMemLazyEnablePeerAccess);
-    if (e == cudaSuccess) { h->p2p_opened[2 * p] = pg; e = cudaIpcOpenMemHandle(&pc, b.ctl, cudaIpcMemLazyEnablePeerAccess); }
-    if (e != cudaSuccess) return fail(LRCN_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d, device %d) -> %s (peer access over NVLink required)", p, b.device, cudaGetErrorString(e));
-    h->p2p_opened[2 * p + 1] = pc;
-    pe.g[p] = (float*)pg; pe.ctl[p] = (P2PCtl*)pc;
+    if (p == rank) { pe.g[p] = h->g; pe.w[p] = h->w; pe.ctl[p] = h->p2p_ctl; h->peer_m[p] = h->m; h->peer_v[p] = h->v; continue; }
+    void* q[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    const cudaIpcMemHandle_t hs[5] = {b.g, b.ctl, b.w, b.m, b.v};
+    for (int k = 0; k < 5; k++) {
+      cudaError_t e = cudaIpcOpenMemHandle(&q[k], hs[k], cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess)
+        return fail(LRCN_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d, device %d) -> %s (peer access over NVLink required)", p, b.device, cudaGetErrorString(e));
+      h->p2p_opened[5 * p + k] = q[k];
+    }
+    pe.g[p] = (float*)q[0]; pe.ctl[p] = (P2PCtl*)q[1]; pe.w[p] = (float*)q[2]; h->peer_m[p] = (float*)q[3]; h->peer_v[p] = (float*)q[4];
   }
   h->peers = pe;
   h->rank = rank; h->nranks = nranks;

@@ -48,6 +48,11 @@ def main():
         w_after = h.get_model()
         for it in range(3):  # a few more steps: barrier epochs, graph replays
             h.train_step(0, img[sl], np.ascontiguousarray(tok[:, sl]))
+        # Adam state after 4 steps (peer-memory mode keeps m, v sharded by owner: get_adam_state gathers them)
+        dist.barrier()
+        m_got = [h.get_adam_state(k, 0) for k in range(1, 10)]
+        v_got = [h.get_adam_state(k, 1) for k in range(1, 10)]
+        dist.barrier()
         final = np.concatenate([x.ravel() for x in h.get_model()])
         digest = torch.tensor([float(np.abs(final).sum()), float((final * np.arange(1, final.size + 1, dtype=np.float64) % 7).sum())], dtype=torch.float64, device="cuda")
         digests = [torch.zeros_like(digest) for _ in range(world)]
@@ -59,9 +64,17 @@ def main():
             ref = [w.copy() for w in model]
             O.update(ref, g_ref, O.initparams(ref))
             derr = [float(np.linalg.norm((w_after[k] - model[k]) - (ref[k] - model[k])) / (np.linalg.norm(ref[k] - model[k]) + 1e-30)) for k in range(9)]
+            ref4 = [w.copy() for w in model]
+            opt4 = O.initparams(ref4)
+            for _ in range(4):
+                g4, _ = O.lossgradient(ref4, O.initstate(ref4, Bg), feats[img - 1], list(tok), range(0, l))
+                O.update(ref4, g4, opt4)
+            merr = max(float(np.linalg.norm(m_got[k] - opt4[k].fstm) / (np.linalg.norm(opt4[k].fstm) + 1e-30)) for k in range(9))
+            verr = max(float(np.linalg.norm(v_got[k] - opt4[k].scndm) / (np.linalg.norm(opt4[k].scndm) + 1e-30)) for k in range(9))
+            same = same and merr < 2e-3 and verr < 2e-3
             good = abs(L - L_ref) < 1e-4 * abs(L_ref) and max(errs) < 1e-4 and abs(L2 - L_ref) < 1e-4 * abs(L_ref) and max(derr) < 5e-3 and same
             ok = ok and good
-            print(f"dp_check world={world} prec={prec}: loss {L:.6f} vs {L_ref:.6f}; max grad relerr {max(errs):.2e}; max update relerr {max(derr):.2e}; replicas identical after 4 steps: {same} -> {'OK' if good else 'FAIL'}", flush=True)
+            print(f"dp_check world={world} prec={prec}: loss {L:.6f} vs {L_ref:.6f}; max grad relerr {max(errs):.2e}; max update relerr {max(derr):.2e}; replicas identical + Adam state (m {merr:.1e}, v {verr:.1e}) after 4 steps: {same} -> {'OK' if good else 'FAIL'}", flush=True)
         dist.barrier()
         h.close()
     dist.barrier()
