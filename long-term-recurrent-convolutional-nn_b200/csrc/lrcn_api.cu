@@ -475,10 +475,12 @@ extern "C" int lrcn_get_adam_state(lrcn_handle* h, int idx, int which, float* p,
       size_t b, e;
       dp_p2p_shard(h->P, h->nranks, r, &b, &e);
       if (e > b) {
-        CK(cudaMemcpy(h->m + b, h->peer_m[r] + b, (e - b) * 4, cudaMemcpyDefault));
-        CK(cudaMemcpy(h->v + b, h->peer_v[r] + b, (e - b) * 4, cudaMemcpyDefault));
+        // on the handle's stream: device-to-device cudaMemcpy does not synchronise the host, and the download below is stream-ordered
+        CK(cudaMemcpyAsync(h->m + b, h->peer_m[r] + b, (e - b) * 4, cudaMemcpyDefault, h->stream));
+        CK(cudaMemcpyAsync(h->v + b, h->peer_v[r] + b, (e - b) * 4, cudaMemcpyDefault, h->stream));
       }
     }
+    CK(cudaStreamSynchronize(h->stream));
     h->adam_sharded = false;
   }
   return download(h, which ? h->v : h->m, idx, p);
@@ -1182,6 +1184,7 @@ extern "C" int lrcn_p2p_import(lrcn_handle* h, const char* blobs, int rank, int 
       h->p2p_opened[5 * p + k] = q[k];
     }
     pe.g[p] = (float*)q[0]; pe.ctl[p] = (P2PCtl*)q[1]; pe.w[p] = (float*)q[2]; h->peer_m[p] = (float*)q[3]; h->peer_v[p] = (float*)q[4];
+    if (getenv("LRCN_P2P_DEBUG")) fprintf(stderr, "[lrcn p2p] rank %d maps rank %d: g %p ctl %p w %p m %p v %p\n", rank, p, q[0], q[1], q[2], q[3], q[4]);
   }
   h->peers = pe;
   h->rank = rank; h->nranks = nranks;

@@ -71,6 +71,12 @@ def main():
                 O.update(ref4, g4, opt4)
             merr = max(float(np.linalg.norm(m_got[k] - opt4[k].fstm) / (np.linalg.norm(opt4[k].fstm) + 1e-30)) for k in range(9))
             verr = max(float(np.linalg.norm(v_got[k] - opt4[k].scndm) / (np.linalg.norm(opt4[k].scndm) + 1e-30)) for k in range(9))
+            if merr >= 2e-3 or verr >= 2e-3:
+                for k in range(9):
+                    a_, b_ = m_got[k].ravel(), opt4[k].fstm.ravel()
+                    bad = np.nonzero(np.abs(a_ - b_) > 1e-3 * np.abs(b_).max())[0]
+                    print(f"  tensor {k + 1} shape {m_got[k].shape}: m relerr {np.linalg.norm(a_ - b_) / (np.linalg.norm(b_) + 1e-30):.2e}, "
+                          f"{bad.size} bad of {a_.size}, first bad {bad[:3]}, got {a_[bad[:3]]}, want {b_[bad[:3]]}", flush=True)
             same = same and merr < 2e-3 and verr < 2e-3
             good = abs(L - L_ref) < 1e-4 * abs(L_ref) and max(errs) < 1e-4 and abs(L2 - L_ref) < 1e-4 * abs(L_ref) and max(derr) < 5e-3 and same
             ok = ok and good
