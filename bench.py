@@ -235,13 +235,17 @@ def main():
         mine = torch.frombuffer(bytearray(h.p2p_export()), dtype=torch.uint8).cuda()
         blobs = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(blobs, mine)
+        ok = 1
         try:
             h.p2p_import(b"".join(bytes(b.cpu().numpy().tobytes()) for b in blobs), rank, world)
-            dp_exchange = "p2p" if not os.environ.get("LRCN_DP_NCCL") else "nccl"
-        except abi.LrcnError as e:  # no peer access between these GPUs: NCCL allreduce
-            if rank == 0:
-                print(f"[bench] peer memory unavailable ({e}); using NCCL", file=sys.stderr)
-            dp_exchange = "nccl"
+        except abi.LrcnError as e:  # no peer access between these GPUs
+            ok = 0
+            print(f"[bench] rank {rank}: peer memory unavailable ({e})", file=sys.stderr)
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # the choice must be the same on every rank
+        if int(flag.item()) == 0:
+            os.environ["LRCN_DP_NCCL"] = "1"  # read by the library at the first data-parallel step
+        dp_exchange = "nccl" if os.environ.get("LRCN_DP_NCCL") else "p2p"
 
     batches = make_batches(w, rank, N_SLOTS)
     for s, (img, tok, l) in enumerate(batches):
