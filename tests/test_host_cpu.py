@@ -1,0 +1,102 @@
+"""Host-side mirror of the reference's epoch drivers (lrcn.jl:330-397 train1, :407-486 average_loss, :585-642 generate),
+exercised on CPU against a recording stand-in for the C-ABI handle: which batches are visited, with which token rows,
+image ids and options.  The numeric path itself is covered by the GPU parity tests."""
+import io
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import lrcn_b200  # noqa: E402,F401
+from lrcn_b200 import abi, host  # noqa: E402
+
+
+class FakeHandle:
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.calls = []
+
+    def close(self):
+        pass
+
+    def train_step(self, split, ids, tok, pdrop, seed):
+        self.calls.append(("train", split, np.array(ids), np.array(tok), pdrop, seed))
+        return float(tok.shape[0])
+
+    def loss(self, split, ids, tok):
+        self.calls.append(("loss", split, np.array(ids), np.array(tok)))
+        l, B = tok.shape
+        return -2.0 * B * (l + 1), B * (l + 1)  # every token costs 2 nats
+
+    def beam_search(self, split, ids, K, nword):
+        if int(ids[0]) == 404:
+            raise abi.LrcnError(abi.ERR_MISSING, "no features for image 404")
+        toks = np.array([[2, 5, 4, 1, 7, 0]], dtype=np.int64)
+        return toks, np.array([5]), np.array([0.25], np.float32), np.zeros((1, 5), np.float32)
+
+
+@pytest.fixture
+def net(monkeypatch):
+    monkeypatch.setattr(abi, "Handle", FakeHandle)
+    return host.LRCN([8, 8], 20, 8, 2)
+
+
+def make_seq(lengths_per_batch, B=2):
+    """(sequence, input_ids, lengths) in the reference's format (lrcn.jl:257-297) for batches of the given caption lengths."""
+    sequence, input_ids, lengths = [], [], []
+    tok = 4
+    for b, l in enumerate(lengths_per_batch):
+        for _ in range(l):
+            sequence.append(np.arange(tok, tok + B, dtype=np.int64))
+            tok += B
+        input_ids.append(np.arange(100 * b, 100 * b + B, dtype=np.int64))
+        lengths += [l] * B
+    return sequence, input_ids, lengths
+
+
+def test_two_layers_only():
+    with pytest.raises(ValueError):
+        host.LRCN([8], 20, 8, 2)
+
+
+def test_train1_visits_every_batch_once_in_shuffled_order_and_skips_long_captions(net):
+    per_batch = [3, 5, 29, 7, 28]  # 29 > 28 is skipped (lrcn.jl:353)
+    seq = make_seq(per_batch)
+    losses = net.train1(seq, pdrop=0.4, shuffle_seed=3)
+    calls = [c for c in net.h.calls if c[0] == "train"]
+    assert len(calls) == 4 and len(losses) == 4
+    seen = sorted(c[3].shape[0] for c in calls)
+    assert seen == [3, 5, 7, 28]
+    starts = np.concatenate([[0], np.cumsum(per_batch)])
+    for _, split, ids, tok, pdrop, seed in calls:
+        l = tok.shape[0]
+        b = per_batch.index(l)
+        assert split == 0 and pdrop == 0.4
+        assert np.array_equal(ids, seq[1][b])                                   # image ids of that batch
+        assert np.array_equal(tok, np.stack(seq[0][starts[b]:starts[b] + l]))    # its l token rows, time-major
+    assert [c[5] for c in calls] == [1, 2, 3, 4]                                # a fresh dropout seed per step
+    again = host.LRCN([8, 8], 20, 8, 2)
+    again.train1(seq, pdrop=0.4, shuffle_seed=3)
+    assert [c[3].shape[0] for c in again.h.calls] == [c[3].shape[0] for c in calls]  # the shuffled order is a function of the seed
+
+
+def test_average_loss_is_token_weighted_and_skips_long_captions(net):
+    seq = make_seq([3, 29, 6])
+    val = net.average_loss(seq)
+    calls = [c for c in net.h.calls if c[0] == "loss"]
+    assert [c[3].shape[0] for c in calls] == [3, 6]
+    assert abs(val - 2.0) < 1e-12  # -(sum of log-probs) / (number of tokens), pooled over batches (lrcn.jl:476-486)
+
+
+def test_generate_prints_id_line_and_caption_like_the_reference(net):
+    vocab = {f"w{k}": k for k in range(1, 21)}
+    out, ids = io.StringIO(), io.StringIO()
+    hyp = net.generate(17, vocab, 30, 3, out=out, in_out=ids)
+    assert ids.getvalue() == "17\n"
+    assert out.getvalue() == "w5 w4 .\n"       # tokens after bos up to the first eos, each + ' ', then '.' (lrcn.jl:633-640)
+    assert hyp == [2, 5, 4, 1, 7]
+    with pytest.raises(RuntimeError, match="misssing features"):  # sic, lrcn.jl:603
+        net.generate(404, vocab, 30, 3, out=io.StringIO(), in_out=io.StringIO())
