@@ -100,3 +100,27 @@ def test_generate_prints_id_line_and_caption_like_the_reference(net):
     assert hyp == [2, 5, 4, 1, 7]
     with pytest.raises(RuntimeError, match="misssing features"):  # sic, lrcn.jl:603
         net.generate(404, vocab, 30, 3, out=io.StringIO(), in_out=io.StringIO())
+
+
+def test_delete_unbatchable_captions_leaves_whole_equal_length_batches():
+    """Property of lrcn.jl:299-327 that minibatch (lrcn.jl:276-293) relies on: what survives is an order-preserving subset made
+    of consecutive groups of batch_size captions of one length.  (A list no longer than batch_size passes through unchanged,
+    as in the reference.)"""
+    rs = np.random.RandomState(11)
+    for _ in range(3000):
+        bs = int(rs.randint(1, 6))
+        n = int(rs.randint(1, 80))
+        lengths = sorted(rs.randint(1, 8, size=n).tolist())
+        caps = [((i, ["w"] * l), l) for i, l in enumerate(lengths)]
+        out = host.delete_unbatchable_captions(caps, bs)
+        ids = [t[0][0] for t in out]
+        assert ids == sorted(ids) and set(ids) <= set(range(n))
+        if n <= bs:
+            assert len(out) == n
+            continue
+        L = [t[1] for t in out]
+        assert len(L) % bs == 0
+        assert all(len(set(L[i:i + bs])) == 1 for i in range(0, len(L), bs))
+        # nothing batchable from the front of a length class is thrown away except by the reference's tail rule
+        for length in set(lengths):
+            assert L.count(length) <= lengths.count(length) - lengths.count(length) % bs
