@@ -352,6 +352,9 @@ def delete_unbatchable_captions(lengths, batch_size):
                     current_index = lengths.index(current_length) + 1
                 except ValueError:
                     current_index = 0
+            if current_index == 0:
+                # lrcn.jl:311-318: findfirst found no longer caption; the reference's outer loop then never advances
+                raise RuntimeError("reference does not terminate on this input (unbatchable tail with no longer caption)")
             drop.extend(range(old_index, current_index))
         if current_index >= limit:
             drop.extend(range(current_index, n + 1))

@@ -124,3 +124,23 @@ def test_delete_unbatchable_captions_leaves_whole_equal_length_batches():
         # nothing batchable from the front of a length class is thrown away except by the reference's tail rule
         for length in set(lengths):
             assert L.count(length) <= lengths.count(length) - lengths.count(length) % bs
+
+
+def test_delete_unbatchable_captions_equals_the_restated_reference_whenever_it_terminates():
+    from oracle import lrcn_oracle as O
+    rs = np.random.RandomState(5)
+    compared = skipped = 0
+    for _ in range(4000):
+        bs = int(rs.randint(1, 6))
+        n = int(rs.randint(bs + 1, 70))
+        lengths = sorted(rs.randint(1, 9, size=n).tolist())
+        caps = [((i, ["w"] * l), l) for i, l in enumerate(lengths)]
+        try:
+            keep = O.delete_unbatchable_captions(lengths, bs)
+        except RuntimeError:
+            skipped += 1  # lrcn.jl:311-318 loops forever here; the host mirror drops the tail instead
+            continue
+        got = [t[0][0] for t in host.delete_unbatchable_captions(caps, bs)]
+        assert got == keep
+        compared += 1
+    assert compared > 1000
