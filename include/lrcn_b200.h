@@ -16,8 +16,14 @@
  *  - the library owns all device memory, streams, CUDA graphs and NCCL communicators; the
  *    caller owns every host buffer and may free it as soon as the call returns (all calls
  *    are synchronous on return unless the name ends in _async).
- *  - one host thread per handle; one handle per GPU (one process per GPU under
- *    torch.distributed / MPI; lrcn_comm_init joins the handles into a data-parallel group).
+ *  - one host thread per handle.  Two ways to use several GPUs of one NVLink node:
+ *      (a) ONE process, ONE handle: set cfg.n_gpus / cfg.device_ids and the library drives all GPUs itself
+ *          (peer access between its own devices, worker threads for generation): an unmodified single-process
+ *          lrcn.jl gets data parallelism from lrcn_train_step alone -- batches are global, the library shards rows;
+ *      (b) one process per GPU (torch.distributed / MPI launchers): one handle per rank, joined by
+ *          lrcn_p2p_export/import (CUDA IPC) or lrcn_comm_init (NCCL).
+ *  - CUDA / NCCL errors and device-side barrier time-outs are STICKY: once a handle has failed that way every later
+ *    call on it returns the same code and message (the context may be unusable); destroy the handle.
  */
 #ifndef LRCN_B200_H
 #define LRCN_B200_H
@@ -34,14 +40,14 @@ extern "C" {
 #define LRCN_API
 #endif
 
-#define LRCN_ABI_VERSION 1
+#define LRCN_ABI_VERSION 2
 #define LRCN_F_CNN 4096 /* lrcn.jl:28  const cnnout = 4096 */
 #define LRCN_NUM_PARAMS 9
 
 enum {
   LRCN_OK = 0,
   LRCN_ERR_ARG = 1,     /* bad argument / shape mismatch (the reference would throw) */
-  LRCN_ERR_CUDA = 2,    /* CUDA runtime/driver error, incl. "no device"; sticky on the handle */
+  LRCN_ERR_CUDA = 2,    /* CUDA runtime/driver error, incl. "no device" and device-side barrier time-outs; sticky on the handle */
   LRCN_ERR_NCCL = 3,
   LRCN_ERR_MISSING = 4, /* unknown image id: lrcn.jl:602-605 error("misssing features!!!!!!") */
   LRCN_ERR_STATE = 5
@@ -69,6 +75,8 @@ typedef struct {
   int32_t precision;    /* LRCN_PREC_* */
   int32_t use_graphs;   /* 1: replay each (B,l) step shape as a CUDA graph */
   double lr, beta1, beta2, eps; /* Float64 like Knet's Adam fields: (float)(1-beta) must equal Knet's axpy! scalar */
+  int32_t n_gpus;       /* 0 or 1: one GPU (`device`).  2..8: single-process data parallelism over device_ids[0..n_gpus) */
+  int32_t device_ids[8];/* CUDA ordinals of the group; max_batch and max_gen_rows are then GLOBAL (summed over the GPUs) */
 } lrcn_config;
 
 LRCN_API int lrcn_abi_version(void);
@@ -132,6 +140,16 @@ LRCN_API int lrcn_train_step_staged(lrcn_handle* h, int slot, float pdrop, uint6
 LRCN_API int lrcn_beam_search(lrcn_handle* h, int split, const int64_t* image_ids, int64_t n, int beam_width, int nword,
                      int64_t* tokens_out, int32_t* len_out, float* prob_out, float* logp_out);
 
+/* ---- checkpoint sidecar.  Replaces save(file,"model",model,"vocab",vocab) lrcn.jl:185,230 and
+ * load(file) lrcn.jl:88-93 (JLD/HDF5 is not available to a C library): a raw little-endian file
+ *   "LRCNB2CK" | u32 version=1 | u32 flags (1 = Adam state) | i32 E,H1,H2,V | i64 adam_t | i64 aux_bytes |
+ *   9 x {i64 rows, i64 cols, float32 column-major} [| 9 x m | 9 x v] | aux bytes
+ * holding exactly the 9 matrices JLD holds, optionally Knet-Adam's m, v and step (which the reference never saved), and
+ * `aux`: caller bytes (the hosts store the vocab Dict as "word\tindex\n" lines).  load validates magic, version, dims and
+ * every shape; aux_out may be NULL to query aux_bytes_out first.  julia/lrcn_b200.jl has a pure-Julia reader/writer. */
+LRCN_API int lrcn_checkpoint_save(lrcn_handle* h, const char* path, int with_adam, const void* aux, int64_t aux_bytes);
+LRCN_API int lrcn_checkpoint_load(lrcn_handle* h, const char* path, int* had_adam, void* aux_out, int64_t aux_cap, int64_t* aux_bytes_out);
+
 /* ---- data-parallel group (new; the reference is single-GPU).  One handle per rank.  The id is
  * produced on rank 0 and distributed by the host's own mechanism (torch.distributed, MPI, file). */
 #define LRCN_COMM_ID_BYTES 128
@@ -156,22 +174,6 @@ LRCN_API int lrcn_get_trace(lrcn_handle* h, uint64_t* out, int64_t n);          
 /* time `reps` launches of one named kernel family on the current buffers: "adam", "vocab_gemm", "gather" ... */
 LRCN_API int lrcn_time_kernel(lrcn_handle* h, const char* name, int reps, float* avg_ms_out, double* algo_bytes_out,
                      double* algo_flops_out);
-
-/* ---- kernel-level test hooks (parity tests call single kernels through the ABI) ---------------
- * C[M][N] (row-major, ldc=N) = op(A) * op(B) (+ C if beta) (+ bias[n]); a_kmajor: A is [M][K] else [K][M];
- * b_kmajor: B is [N][K] else [K][N].  precision selects the fp32 or the tcgen05 bf16x3 kernel. */
-LRCN_API int lrcn_test_gemm(lrcn_handle* h, int precision, int a_kmajor, int b_kmajor, int M, int N, int K,
-                   const float* A, const float* B, const float* bias, int beta, float* C);
-/* diagnostics: average ms of `iters` back-to-back bf16x3 GEMM launches on scratch operands of this shape (no L2 flush);
- * dbg bits (pair kernel only): 1 = no epilogue stores, 2 = no TMA loads after the first ring fill, 4 = no MMAs */
-LRCN_API int lrcn_test_gemm_time(lrcn_handle* h, int a_kmajor, int b_kmajor, int M, int N, int K, int with_shadow_out, int iters,
-                        int dbg, float* avg_ms_out);
-/* diagnostics: clocks to issue / complete a chain of n_mma tcgen05.mma (M x N x 16, bf16, smem operands) on every SM */
-LRCN_API int lrcn_test_mma_rate(lrcn_handle* h, int M, int N, int n_mma, int commit_every, int issuers, int64_t* issue_clk_out,
-                       int64_t* total_clk_out);
-/* beam selection on caller-supplied probabilities: probs [rows][V], parent_prob [rows]; outputs per image */
-LRCN_API int lrcn_test_beam_select(lrcn_handle* h, const float* probs, const float* parent_prob, int n_images, int K,
-                          int V, int first_step, int64_t* tok_out, int32_t* parent_out, float* score_out);
 
 #ifdef __cplusplus
 }

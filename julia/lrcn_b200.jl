@@ -20,6 +20,8 @@ type Config          # mirrors lrcn_config in include/lrcn_b200.h, field for fie
     max_batch::Int32; max_len::Int32; max_gen_rows::Int32; device::Int32
     precision::Int32; use_graphs::Int32
     lr::Float64; beta1::Float64; beta2::Float64; eps::Float64
+    n_gpus::Int32                        # 0/1: one GPU; 2..8: the library drives device_ids[1:n_gpus] itself
+    device_ids::NTuple{8,Int32}
 end
 
 type Net
@@ -32,16 +34,21 @@ check(rc) = rc == 0 ? nothing : error(lasterror())     # reference convention: e
 abi_version() = ccall((:lrcn_abi_version, lib), Cint, ())
 
 function default_config()
-    c = Ref(Config(0,0,0,0,0,0,0,0,0,0,0.0,0.0,0.0,0.0))
+    c = Ref(Config(0,0,0,0,0,0,0,0,0,0,0.0,0.0,0.0,0.0,0,ntuple(i->Int32(0),8)))
     check(ccall((:lrcn_config_default, lib), Cint, (Ptr{Config},), c))
     return c[]
 end
 
-function create(embed, hidden, vocab_size, batchsize; max_len=28, max_gen_rows=1024, device=0, precision=1)
+# gpus: vector of CUDA ordinals.  One entry = one GPU.  Several = single-process data parallelism: lrcn.jl stays ONE
+# process with ONE net; train_step!/loss take the GLOBAL batch (batchsize = global rows) and the library shards the rows,
+# exchanges gradients over NVLink peer memory and shards beam search by image -- no launcher, no MPI.
+function create(embed, hidden, vocab_size, batchsize; max_len=28, max_gen_rows=1024, gpus=[0], precision=1)
     c = default_config()
     c.embed = embed; c.hidden1 = hidden[1]; c.hidden2 = hidden[2]; c.vocab = vocab_size
     c.max_batch = batchsize; c.max_len = max_len; c.max_gen_rows = max_gen_rows
-    c.device = device; c.precision = precision
+    c.device = gpus[1]; c.precision = precision
+    c.n_gpus = length(gpus)
+    c.device_ids = ntuple(i -> Int32(i <= length(gpus) ? gpus[i] : 0), 8)
     h = Ref{Ptr{Void}}(C_NULL)
     check(ccall((:lrcn_create, lib), Cint, (Ptr{Config}, Ptr{Ptr{Void}}), Ref(c), h))
     net = Net(h[], vocab_size)
@@ -164,6 +171,49 @@ function beam_search(net, split, ids, beam_width, nword)
                 (Ptr{Void}, Cint, Ptr{Int64}, Int64, Cint, Cint, Ptr{Int64}, Ptr{Int32}, Ptr{Float32}, Ptr{Float32}),
                 net.handle, split, convert(Vector{Int64}, ids), n, beam_width, nword, tokens, lens, prob, lps))
     return [tokens[1:lens[i], i] for i = 1:n], prob, lps
+end
+
+# ---- checkpoint sidecar (replaces save(file,"model",model,"vocab",vocab) lrcn.jl:185,230 and load(file) lrcn.jl:88-93).
+# Format: include/lrcn_b200.h.  vocab travels as "word\tindex\n" lines.
+vocab_bytes(vocab) = convert(Vector{UInt8}, join(["$(w)\t$(i)\n" for (w, i) in sort(collect(vocab), by=last)]))
+function vocab_from_bytes(b)
+    vocab = Dict{String,Int}()
+    for line in split(String(copy(b)), "\n")
+        isempty(line) && continue
+        k = rsearch(line, '\t'); vocab[line[1:k-1]] = parse(Int, line[k+1:end])
+    end
+    return vocab
+end
+function save!(net, path, vocab; with_adam=true)          # weights + Adam m,v,t from the GPU(s) + vocab
+    aux = vocab_bytes(vocab)
+    check(ccall((:lrcn_checkpoint_save, lib), Cint, (Ptr{Void}, Cstring, Cint, Ptr{UInt8}, Int64), net.handle, path, with_adam ? 1 : 0, aux, length(aux)))
+end
+function load!(net, path)                                 # -> vocab Dict; restores Adam state when the file has it
+    had = Ref{Cint}(0); n = Ref{Int64}(0); aux = zeros(UInt8, filesize(path))
+    check(ccall((:lrcn_checkpoint_load, lib), Cint, (Ptr{Void}, Cstring, Ptr{Cint}, Ptr{UInt8}, Int64, Ptr{Int64}), net.handle, path, had, aux, length(aux), n))
+    return vocab_from_bytes(aux[1:n[]])
+end
+# pure-Julia reader of the same file (no library, no GPU): -> (model::Array{Any}(9), vocab, (m, v, t) or nothing),
+# e.g. to convert a sidecar back into a .jld with save(file,"model",model,"vocab",vocab)
+function read_checkpoint(path)
+    open(path) do f
+        String(read(f, UInt8, 8)) == "LRCNB2CK" || error("not an LRCNB2CK checkpoint")
+        version = read(f, UInt32); flags = read(f, UInt32); dims = read(f, Int32, 4)
+        adam_t = read(f, Int64); aux_bytes = read(f, Int64)
+        version == 1 || error("unsupported checkpoint version $version")
+        function mats()
+            out = Array(Any, 9)
+            for k = 1:9
+                r = read(f, Int64); c = read(f, Int64)
+                out[k] = read(f, Float32, (Int(r), Int(c)))          # column-major on disk, like Julia
+            end
+            return out
+        end
+        model = mats()
+        adam = (flags & 1) == 1 ? (mats(), mats(), adam_t) : nothing
+        vocab = vocab_from_bytes(read(f, UInt8, aux_bytes))
+        return model, vocab, adam
+    end
 end
 
 # data-parallel group: rank 0 creates the id, the launcher (MPI.jl / files) distributes it

@@ -9,7 +9,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblrcn_b200.so")
+LIB_PATH = os.path.join(_HERE, "liblrcn_b200.so")            # the product: include/lrcn_b200.h
+TEST_LIB_PATH = os.path.join(_HERE, "liblrcn_b200_test.so")  # + kernel-level test hooks: include/lrcn_b200_testhooks.h
+ABI_VERSION = 2
 
 PREC_FP32, PREC_BF16X3 = 0, 1
 OK, ERR_ARG, ERR_CUDA, ERR_NCCL, ERR_MISSING, ERR_STATE = 0, 1, 2, 3, 4, 5
@@ -26,7 +28,8 @@ class LrcnError(RuntimeError):
 class Config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("embed", "hidden1", "hidden2", "vocab", "max_batch", "max_len",
                                          "max_gen_rows", "device", "precision", "use_graphs")] + \
-               [(n, C.c_double) for n in ("lr", "beta1", "beta2", "eps")]
+               [(n, C.c_double) for n in ("lr", "beta1", "beta2", "eps")] + \
+               [("n_gpus", C.c_int32), ("device_ids", C.c_int32 * 8)]
 
 
 _p = C.POINTER
@@ -57,6 +60,8 @@ SIGNATURES = {
     "lrcn_stage_batch": (C.c_int, [_H, C.c_int, C.c_int, _i64p, _i64p, C.c_int, C.c_int]),
     "lrcn_train_step_staged": (C.c_int, [_H, C.c_int, C.c_float, C.c_uint64, _f64p]),
     "lrcn_beam_search": (C.c_int, [_H, C.c_int, _i64p, C.c_int64, C.c_int, C.c_int, _i64p, _i32p, _f32p, _f32p]),
+    "lrcn_checkpoint_save": (C.c_int, [_H, C.c_char_p, C.c_int, C.c_char_p, C.c_int64]),
+    "lrcn_checkpoint_load": (C.c_int, [_H, C.c_char_p, _i32p, C.c_char_p, C.c_int64, _i64p]),
     "lrcn_comm_unique_id": (C.c_int, [C.c_char_p]),
     "lrcn_comm_init": (C.c_int, [_H, C.c_char_p, C.c_int, C.c_int]),
     "lrcn_p2p_export": (C.c_int, [_H, C.c_char_p]),
@@ -68,13 +73,19 @@ SIGNATURES = {
     "lrcn_flush_l2": (C.c_int, [_H]),
     "lrcn_get_trace": (C.c_int, [_H, _p(C.c_uint64), C.c_int64]),
     "lrcn_time_kernel": (C.c_int, [_H, C.c_char_p, C.c_int, _f32p, _f64p, _f64p]),
+}
+
+# kernel-level test hooks: exported by liblrcn_b200_test.so only
+TEST_SIGNATURES = {
     "lrcn_test_mma_rate": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "lrcn_test_gemm_time": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]),
     "lrcn_test_gemm": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, C.c_int, _f32p]),
     "lrcn_test_beam_select": (C.c_int, [_H, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _i64p, _i32p, _f32p]),
+    "lrcn_test_beam_topk_logits": (C.c_int, [_H, _f32p, _f32p, C.c_int, C.c_int, C.c_int, _i64p, _f32p, _f32p]),
 }
 
 _lib = None
+_test_lib = None
 
 
 def load():
@@ -93,9 +104,47 @@ def load():
     return _lib
 
 
+def load_test():
+    """Load liblrcn_b200_test.so: the product objects plus the kernel-level test hooks (tests only)."""
+    global _test_lib
+    if _test_lib is None:
+        if not os.path.exists(TEST_LIB_PATH):
+            raise FileNotFoundError(f"{TEST_LIB_PATH} is not built; run `python -c 'import __graft_entry__ as g; g.build()'`.")
+        lib = C.CDLL(TEST_LIB_PATH)
+        for name, (res, args) in {**SIGNATURES, **TEST_SIGNATURES}.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _test_lib = lib
+    return _test_lib
+
+
+_last_lib = None  # the library called last (each of the two has its own thread-local error message)
+
+
+class _Lib:
+    """Thin proxy over a CDLL that remembers which library was called last, so check() reads the right message."""
+
+    def __init__(self, lib):
+        object.__setattr__(self, "_lib", lib)
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        lib = self._lib
+
+        def call(*a):
+            global _last_lib
+            _last_lib = lib
+            return fn(*a)
+
+        object.__setattr__(self, name, call)
+        return call
+
+
 def check(rc):
     if rc != OK:
-        raise LrcnError(rc, load().lrcn_last_error().decode("utf-8", "replace"))
+        lib = _last_lib or load()
+        raise LrcnError(rc, lib.lrcn_last_error().decode("utf-8", "replace"))
 
 
 def _f32(a):
@@ -108,7 +157,7 @@ def _i64(a):
 
 def default_config(**kw) -> Config:
     cfg = Config()
-    check(load().lrcn_config_default(C.byref(cfg)))
+    check(_Lib(load()).lrcn_config_default(C.byref(cfg)))
     for k, v in kw.items():
         if not hasattr(cfg, k):
             raise AttributeError(k)
@@ -117,10 +166,11 @@ def default_config(**kw) -> Config:
 
 
 class Handle:
-    """Owns one lrcn_handle (one GPU)."""
+    """Owns one lrcn_handle: one GPU, or (cfg.n_gpus > 1) a single-process data-parallel group.
+    hooks=True binds the handle to liblrcn_b200_test.so so that the test_* methods are available."""
 
-    def __init__(self, cfg: Config):
-        self.lib = load()
+    def __init__(self, cfg: Config, hooks: bool = False):
+        self.lib = _Lib(load_test() if hooks else load())
         self.cfg = cfg
         self._h = _H()
         check(self.lib.lrcn_create(C.byref(cfg), C.byref(self._h)))
@@ -254,11 +304,24 @@ class Handle:
                                         lens.ctypes.data_as(_i32p), _f32(prob), _f32(lps) if want_logps else None))
         return toks, lens, prob, lps
 
+    # ---- checkpoint sidecar (f-2)
+    def checkpoint_save(self, path: str, with_adam: bool = True, aux: bytes = b""):
+        check(self.lib.lrcn_checkpoint_save(self._h, path.encode(), 1 if with_adam else 0, aux if aux else None, len(aux)))
+
+    def checkpoint_load(self, path: str):
+        """Loads weights (+ Adam state if stored) into the handle; returns (had_adam, aux bytes)."""
+        had, n = C.c_int32(), C.c_int64()
+        # the sizes are in the header: a first pass with no aux buffer would load the weights twice, so size the buffer from the file
+        size = os.path.getsize(path)
+        buf = C.create_string_buffer(max(size, 1))
+        check(self.lib.lrcn_checkpoint_load(self._h, path.encode(), C.byref(had), buf, size, C.byref(n)))
+        return bool(had.value), buf.raw[:n.value]
+
     # ---- data parallel
     @staticmethod
     def comm_unique_id() -> bytes:
         buf = C.create_string_buffer(COMM_ID_BYTES)
-        check(load().lrcn_comm_unique_id(buf))
+        check(_Lib(load()).lrcn_comm_unique_id(buf))
         return buf.raw
 
     def comm_init(self, uid: bytes, rank: int, nranks: int):
@@ -326,6 +389,16 @@ class Handle:
         check(self.lib.lrcn_test_gemm(self._h, precision, int(a_kmajor), int(b_kmajor), M, N, K, _f32(A), _f32(B),
                                       _f32(b) if b is not None else None, 0 if C0 is None else 1, _f32(out)))
         return out
+
+    def test_beam_topk_logits(self, logits, parent_prob, K):
+        logits = np.ascontiguousarray(logits, dtype=np.float32)
+        parent_prob = np.ascontiguousarray(parent_prob, dtype=np.float32)
+        R, V = logits.shape
+        tok = np.zeros((R, K), dtype=np.int64)
+        sc = np.zeros((R, K), dtype=np.float32)
+        lp = np.zeros((R, K), dtype=np.float32)
+        check(self.lib.lrcn_test_beam_topk_logits(self._h, _f32(logits), _f32(parent_prob), R, V, K, _i64(tok), _f32(sc), _f32(lp)))
+        return tok, sc, lp
 
     def test_beam_select(self, probs, parent_prob, n_images, K, first_step):
         probs = np.ascontiguousarray(probs, dtype=np.float32)

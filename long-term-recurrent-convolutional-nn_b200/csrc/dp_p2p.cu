@@ -41,9 +41,11 @@ __global__ void xgpu_barrier_kernel(P2PPeers peers, unsigned int* epoch_ctr) {
     const unsigned int* mine = &peers.ctl[peers.rank]->flags[q];
     const long long t0 = clock64();
     while ((int)(ld_acquire_sys(mine) - e) < 0) {
+      if (dev_aborted()) break;
       if (clock64() - t0 > 40000000000ll) {  // ~20 s: a peer died or never reached the barrier
         printf("lrcn dp_p2p: barrier timeout, rank %d waiting for rank %d (epoch %u)\n", peers.rank, q, e);
-        __trap();
+        dev_abort_set();  // flag + drain instead of a trap (kernels.cuh): the ABI reports a sticky error
+        break;
       }
     }
   }
@@ -117,6 +119,8 @@ __global__ void __launch_bounds__(256) adam_p2p_kernel(P2PPeers peers, size_t be
   }
   __threadfence_system();
 }
+
+bool dp_bind_abort(unsigned int* host_flag) { return dev_abort_bind(host_flag) == cudaSuccess; }
 
 void dp_p2p_shard(size_t n_floats, int nranks, int r, size_t* begin, size_t* end) {
   const size_t n4 = n_floats / 4, per = (n4 + nranks - 1) / nranks;

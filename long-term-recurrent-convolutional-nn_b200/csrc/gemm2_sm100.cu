@@ -457,4 +457,6 @@ bool gemm2_bf16x3_dualB(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int
                       nullptr, nullptr, c_zeroed);
 }
 
+bool gemm2_bind_abort(unsigned int* host_flag) { return dev_abort_bind(host_flag) == cudaSuccess; }
+
 }  // namespace lrcn

@@ -519,4 +519,6 @@ bool gemm_bf16x3(cudaStream_t s, bool a_kmajor, bool b_kmajor, int M, int N, int
   return true;
 }
 
+bool gemm_bind_abort(unsigned int* host_flag) { return dev_abort_bind(host_flag) == cudaSuccess; }
+
 }  // namespace lrcn

@@ -43,6 +43,32 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
 }
 #endif
 
+// ---- device-side time-outs.  Every spin wait in the persistent kernels (mbarrier, grid barrier, cross-GPU flag barrier) is
+// clock-bounded.  A wait that times out does NOT trap (a trap destroys the CUDA context and every later call fails
+// undiagnosed): it raises a flag -- one copy per translation unit in device memory, so that every other wait of that unit
+// returns at once and the kernels drain, plus ONE process-wide word in mapped host memory that the C ABI checks after every
+// synchronisation and turns into a sticky LRCN_ERR_CUDA "device-side barrier time-out" on the handle.
+#ifdef __CUDACC__
+static __device__ unsigned int g_dev_abort = 0;
+static __device__ unsigned int* g_dev_abort_host = nullptr;
+__device__ __forceinline__ bool dev_aborted() { return *reinterpret_cast<volatile unsigned int*>(&g_dev_abort) != 0u; }
+static __device__ __noinline__ void dev_abort_set() {
+  atomicExch(&g_dev_abort, 1u);
+  if (g_dev_abort_host) { *reinterpret_cast<volatile unsigned int*>(g_dev_abort_host) = 1u; __threadfence_system(); }
+}
+// host: bind this translation unit's flag pointer on the CURRENT device (called from lrcn_create, never inside a capture)
+static inline cudaError_t dev_abort_bind(unsigned int* host_flag) {
+  const unsigned int zero = 0;
+  cudaError_t e = cudaMemcpyToSymbol(g_dev_abort_host, &host_flag, sizeof host_flag);
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_dev_abort, &zero, sizeof zero);
+  return e;
+}
+#endif
+bool gemm_bind_abort(unsigned int* host_flag);   // gemm_sm100.cu
+bool gemm2_bind_abort(unsigned int* host_flag);  // gemm2_sm100.cu
+bool lstm_bind_abort(unsigned int* host_flag);   // lstm_sm100.cu
+bool dp_bind_abort(unsigned int* host_flag);     // dp_p2p.cu
+
 struct LaunchCounter { long long n = 0; };
 extern thread_local LaunchCounter* g_counter;  // incremented by every launcher below
 
@@ -95,9 +121,9 @@ void adam_flat(cudaStream_t s, float* w, const float* g, float* m, float* v, siz
 void split_bf16(cudaStream_t s, const float* x, size_t n, __nv_bfloat16* hi, __nv_bfloat16* lo);
 void transpose2d(cudaStream_t s, const float* in, int rows, int cols, float* out);  // out[c][r] = in[r][c]
 void fill_l2_scratch(cudaStream_t s, float* buf, size_t n, float val);
-// one launch zeroing up to 8 fp32 ranges (16-byte aligned starts): accumulation targets of the step (split-K / stream-K GEMM
+// one launch zeroing up to 16 fp32 ranges (16-byte aligned starts): accumulation targets of the step (split-K / stream-K GEMM
 // outputs, bias-gradient column sums, the embedding-gradient scatter, the LSTM grid-barrier counters)
-struct ZeroSegs { float* p[8]; size_t n[8]; int count = 0; void add(void* ptr, size_t nfloats) { if (nfloats && count < 8) { p[count] = (float*)ptr; n[count] = nfloats; count++; } } };
+struct ZeroSegs { float* p[16]; size_t n[16]; int count = 0; void add(void* ptr, size_t nfloats) { if (ptr && nfloats && count < 16) { p[count] = (float*)ptr; n[count] = nfloats; count++; } } };
 void zero_multi(cudaStream_t s, const ZeroSegs& z);
 
 // ---------------------------------------------------------------- beam search

@@ -12,43 +12,38 @@
 //   workspace arena: time-major activations, row r = t*B + i (see Workspace below) + bf16 shadows.
 // Reference call sites replaced: lrcn.jl:378 (lossgradient), :394 (update!), :452-474 (average_loss body),
 // :585-678 (generate/beam_search).
-#include "../../include/lrcn_b200.h"
-#include "kernels.cuh"
+#include "lrcn_internal.h"
 
 #include <dlfcn.h>
 #include <math.h>
-#include <stdarg.h>
-#include <stdio.h>
-#include <stdlib.h>
-#include <string.h>
-
-#include <map>
-#include <string>
-#include <tuple>
-#include <unordered_map>
-#include <vector>
-
-using namespace lrcn;
-typedef __nv_bfloat16 bf16;
 
 static thread_local std::string g_err;
-static int fail(int code, const char* fmt, ...) {
+static thread_local int g_last_code = 0;  // code of the last fail() on this thread (read by ApiGuard)
+int fail(int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(buf, sizeof buf, fmt, ap);
   va_end(ap);
   g_err = buf;
+  g_last_code = code;
   return code;
 }
-#define CK(call)                                                                                      \
-  do {                                                                                                \
-    cudaError_t e_ = (call);                                                                          \
-    if (e_ != cudaSuccess) return fail(LRCN_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
-  } while (0)
+
+// process-wide word in mapped host memory raised by a device-side wait that timed out (kernels.cuh)
+static unsigned int* g_abort_host = nullptr;
+static int check_device_abort() {
+  if (g_abort_host && *reinterpret_cast<volatile unsigned int*>(g_abort_host))
+    return fail(LRCN_ERR_CUDA, "device-side barrier time-out inside a persistent kernel (see stderr of the process); results are invalid");
+  return LRCN_OK;
+}
+// stream synchronisation used by every ABI call: CUDA errors and device-side time-outs surface here
+static int sync_stream(lrcn_handle* h) {
+  CK(cudaStreamSynchronize(h->stream));
+  return check_device_abort();
+}
 
 // ------------------------------------------------------------------------------------------ NCCL via dlopen
-typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 struct NcclApi {
   void* lib = nullptr;
@@ -83,96 +78,6 @@ static NcclApi* nccl_api() {
   return (api.lib && api.GetUniqueId && api.CommInitRank && api.AllReduce) ? &api : nullptr;
 }
 enum { NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
-
-// ------------------------------------------------------------------------------------------ handle
-struct Arena {
-  float* f = nullptr; bf16* hi = nullptr; bf16* lo = nullptr;
-  size_t cap = 0, used = 0;
-  size_t take(size_t n) { size_t o = used; used += (n + 63) / 64 * 64; return o; }
-};
-struct Table {
-  float* d = nullptr; int64_t n = 0;
-  std::unordered_map<int64_t, int> map;
-};
-constexpr int COLPART_ROWS = 296;  // 2 CTAs per SM
-struct Slot { int l = 0, B = 0, split = 0; int *tok_in = nullptr, *tok_tgt = nullptr, *rows = nullptr; };
-struct Workspace {  // element offsets into the workspace arena
-  size_t X, v, dv, Eall, dE, acts1, h1, c1, Z, dZ, acts2, h2, c2, logits, rowlp, dh2, dh1, dhrec1, dc1, dhrec2, dc2, colpart;
-  // generation
-  size_t gX, gv, ge, gg1, gh1a, gc1a, gh1b, gc1b, gz, gg2, gh2a, gc2a, gh2b, gc2b, glogits, gprob, gcs, gclp, gss, gslp, glpa, glpb, goprob, golp, gxh1, gxh2;
-};
-struct lrcn_handle {
-  lrcn_config cfg;
-  int E, H1, H2, C, V, ldV, ldv;
-  bool bf16mode;
-  cudaStream_t stream = nullptr, comm_stream = nullptr, side_stream = nullptr;  // side: weight prep, concurrent with the step's first kernels
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_seg[3] = {nullptr, nullptr, nullptr}, ev_comm = nullptr;
-  // params
-  size_t P = 0, off[9], nel[9], bucket_off[4];
-  int64_t rows[9], cols[9];
-  float *w = nullptr, *g = nullptr, *m = nullptr, *v = nullptr;
-  bf16 *w_hi = nullptr, *w_lo = nullptr;
-  bf16 *wp1_hi = nullptr, *wp1_lo = nullptr, *wp2_hi = nullptr, *wp2_lo = nullptr;  // gate-interleaved recurrent weights (lstm_sm100.cu)
-  bf16 *wt1_hi = nullptr, *wt1_lo = nullptr, *wt2_hi = nullptr, *wt2_lo = nullptr;  // transposed recurrent weights for the backward step
-  int64_t adam_t = 0;
-  Table tab[2];
-  Arena ws;
-  Workspace o;
-  int *d_tok_in = nullptr, *d_tok_tgt = nullptr, *d_rows = nullptr;
-  int* h_stage = nullptr;  // pinned: tok_in | tok_tgt | rows
-  StepScalars *d_sc = nullptr, *h_sc = nullptr;
-  double *d_loss = nullptr, *h_loss = nullptr;  // d_loss lives inside p2p_ctl (peers read it)
-  // peer-memory data parallelism (dp_p2p.cu)
-  P2PCtl* p2p_ctl = nullptr;          // exported control block: barrier flags + this rank's loss partial
-  double* d_loss_total = nullptr;     // sum over ranks, written by the exchange kernel
-  unsigned int* d_epoch = nullptr;    // barrier epoch counter (local)
-  P2PPeers peers{};
-  bool p2p_ready = false;
-  bool loss_is_total = false;       // last step summed the loss over ranks into d_loss_total
-  void* p2p_opened[5 * LRCN_P2P_MAX_RANKS] = {};  // IPC mappings to close
-  float* peer_m[LRCN_P2P_MAX_RANKS] = {};
-  float* peer_v[LRCN_P2P_MAX_RANKS] = {};
-  bool adam_sharded = false;          // m, v are current only in each owner's shard (gathered on lrcn_get_adam_state)
-  unsigned int* d_counters = nullptr;  // per-m-tile grid-barrier counters of the persistent LSTM kernels
-  unsigned long long* d_trace = nullptr;  // LRCN_SEQ_TRACE=1: per-step timeline of the layer-2 forward sequence kernel
-  Slot slots[64];
-  std::map<std::tuple<int, int, int, int>, cudaGraphExec_t> graphs;
-  std::map<std::tuple<int, int, int, int>, long long> graph_launches;
-  LaunchCounter counter;
-  int last_B = 0, last_l = 0;
-  bool dbout_fused = false;  // set by enqueue_forward: the softmax kernel already produced dbout
-  // DP
-  ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
-  // generation int buffers
-  int *g_last = nullptr, *g_ctok = nullptr, *g_stok = nullptr, *g_spar = nullptr, *g_hista = nullptr, *g_histb = nullptr, *g_done = nullptr,
-      *g_ndone = nullptr, *g_olen = nullptr, *g_rows = nullptr;
-  long long* g_otok = nullptr;
-  int* h_ndone = nullptr;
-  float* l2_scratch = nullptr; size_t l2_n = 0;
-};
-
-static inline float* WS(lrcn_handle* h, size_t off) { return h->ws.f + off; }
-static inline float* Wp(lrcn_handle* h, int idx1) { return h->w + h->off[idx1 - 1]; }
-static inline float* Gp(lrcn_handle* h, int idx1) { return h->g + h->off[idx1 - 1]; }
-
-static void shadow(lrcn_handle* h, const float* p, bf16** hi, bf16** lo) {
-  if (p >= h->w && p < h->w + h->P) { *hi = h->w_hi + (p - h->w); *lo = h->w_lo + (p - h->w); return; }
-  *hi = h->ws.hi + (p - h->ws.f);
-  *lo = h->ws.lo + (p - h->ws.f);
-}
-struct ShadowPair { bf16* hi; bf16* lo; };
-static ShadowPair SH(lrcn_handle* h, const float* p) {  // null pair in fp32 mode: producers then skip the split
-  ShadowPair sp{nullptr, nullptr};
-  if (h->bf16mode) shadow(h, p, &sp.hi, &sp.lo);
-  return sp;
-}
-static void split_ws(lrcn_handle* h, const float* p, size_t n) {
-  if (!h->bf16mode) return;
-  bf16 *hi, *lo;
-  shadow(h, p, &hi, &lo);
-  split_bf16(h->stream, p, n, hi, lo);
-}
 
 struct GemmFail { std::string msg; };
 // precision-dispatching GEMM on arena pointers (both are CUDA paths; no CPU fallback exists)
@@ -220,6 +125,8 @@ extern "C" int lrcn_config_default(lrcn_config* c) {
   c->max_gen_rows = 1024; c->device = 0;
   c->precision = LRCN_PREC_BF16X3; c->use_graphs = 1;
   c->lr = 1e-3; c->beta1 = 0.9; c->beta2 = 0.999; c->eps = 1e-8;  // Knet Adam() via lrcn.jl:402 (Float64 hyper-parameters)
+  c->n_gpus = 1;
+  for (int i = 0; i < 8; i++) c->device_ids[i] = i;
   return LRCN_OK;
 }
 
@@ -238,14 +145,21 @@ static void param_dims(const lrcn_handle* h, int k, int64_t* r, int64_t* c) {
   }
 }
 
-extern "C" int lrcn_destroy(lrcn_handle* h) {
+static int s_destroy(lrcn_handle* h) {
   if (!h) return LRCN_OK;
+  if (!h->members.empty()) {  // single-process group: the parent owns only its members
+    for (lrcn_handle* m : h->members) if (m) cudaSetDevice(m->cfg.device), cudaStreamSynchronize(m->stream);  // nobody unmaps while a peer may still run
+    for (lrcn_handle* m : h->members) s_destroy(m);
+    delete h;
+    return LRCN_OK;
+  }
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
   if (h->comm && nccl_api()) nccl_api()->CommDestroy(h->comm);
-  for (void* q : h->p2p_opened) if (q) cudaIpcCloseMemHandle(q);
-  void* ptrs[] = {h->w, h->g, h->m, h->v, h->w_hi, h->w_lo, h->wp1_hi, h->wp1_lo, h->wp2_hi, h->wp2_lo, h->tab[0].d, h->tab[1].d, h->ws.f, h->ws.hi, h->ws.lo, h->d_tok_in,
+  if (!h->peers_direct) for (void* q : h->p2p_opened) if (q) cudaIpcCloseMemHandle(q);
+  for (cudaEvent_t e : h->sc_ev) if (e) cudaEventDestroy(e);
+  void* ptrs[] = {h->w, h->g, h->m, h->v, h->w_hi, h->w_lo, h->wp1_hi, h->wp1_lo, h->wp2_hi, h->wp2_lo, h->wt1_hi, h->wt1_lo, h->wt2_hi, h->wt2_lo, h->tab[0].d, h->tab[1].d, h->ws.f, h->ws.hi, h->ws.lo, h->d_tok_in,
                   h->d_tok_tgt, h->d_rows, h->d_sc, h->p2p_ctl, h->d_loss_total, h->d_epoch, h->d_counters, h->d_trace, h->g_last, h->g_ctok, h->g_stok, h->g_spar, h->g_hista, h->g_histb,
                   h->g_done, h->g_ndone, h->g_olen, h->g_rows, h->g_otok, h->l2_scratch};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -283,6 +197,12 @@ static int create_impl(const lrcn_config* cfg, lrcn_handle* h) {
     return fail(LRCN_ERR_CUDA, "precision bf16x3 needs sm_100a (tcgen05); device is sm_%d%d", prop.major, prop.minor);
   init_simt_kernels();
   if (h->bf16mode && (!init_gemm_sm100() || !init_lstm_sm100())) return fail(LRCN_ERR_CUDA, "%s", gemm_bf16x3_last_error());
+  if (!g_abort_host) {
+    CK(cudaHostAlloc(&g_abort_host, sizeof(unsigned int), cudaHostAllocMapped | cudaHostAllocPortable));
+    *g_abort_host = 0u;
+  }
+  if (!gemm_bind_abort(g_abort_host) || !gemm2_bind_abort(g_abort_host) || !lstm_bind_abort(g_abort_host) || !dp_bind_abort(g_abort_host))
+    return fail(LRCN_ERR_CUDA, "binding the device-side time-out flag failed: %s", cudaGetErrorString(cudaGetLastError()));
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
@@ -353,8 +273,9 @@ static int create_impl(const lrcn_config* cfg, lrcn_handle* h) {
   }
   CK(cudaMalloc(&h->d_tok_in, R * 4)); CK(cudaMalloc(&h->d_tok_tgt, R * 4)); CK(cudaMalloc(&h->d_rows, B * 4));
   CK(cudaMallocHost(&h->h_stage, (2 * R + B) * 4));
-  CK(cudaMalloc(&h->d_sc, sizeof(StepScalars))); CK(cudaMallocHost(&h->h_sc, sizeof(StepScalars)));
-  memset(h->h_sc, 0, sizeof(StepScalars));
+  CK(cudaMalloc(&h->d_sc, sizeof(StepScalars))); CK(cudaMallocHost(&h->h_sc, lrcn_handle::SC_RING * sizeof(StepScalars)));
+  memset(h->h_sc, 0, lrcn_handle::SC_RING * sizeof(StepScalars));
+  for (int i = 0; i < lrcn_handle::SC_RING; i++) CK(cudaEventCreateWithFlags(&h->sc_ev[i], cudaEventDisableTiming));
   CK(cudaMalloc(&h->p2p_ctl, 4096)); CK(cudaMemset(h->p2p_ctl, 0, 4096));
   h->d_loss = &h->p2p_ctl->loss_partial;
   CK(cudaMalloc(&h->d_loss_total, 8)); CK(cudaMalloc(&h->d_epoch, 4)); CK(cudaMemset(h->d_epoch, 0, 4));
@@ -372,8 +293,7 @@ static int create_impl(const lrcn_config* cfg, lrcn_handle* h) {
   return LRCN_OK;
 }
 
-extern "C" int lrcn_create(const lrcn_config* cfg, lrcn_handle** out) {
-  if (!cfg || !out) return fail(LRCN_ERR_ARG, "null argument");
+static int validate_config(const lrcn_config* cfg) {
   if (cfg->embed <= 0 || cfg->hidden1 <= 0 || cfg->hidden2 <= 0 || cfg->vocab < 4 || cfg->max_batch <= 0 || cfg->max_len <= 0)
     return fail(LRCN_ERR_ARG, "non-positive dimension in config");
   if (cfg->hidden2 % 2) return fail(LRCN_ERR_ARG, "hidden2 must be even (lrcn.jl:496-498,545-546: [x*Wf, x_cnn] must be H2 wide)");
@@ -381,15 +301,75 @@ extern "C" int lrcn_create(const lrcn_config* cfg, lrcn_handle** out) {
   if (cfg->precision != LRCN_PREC_FP32 && cfg->precision != LRCN_PREC_BF16X3) return fail(LRCN_ERR_ARG, "unknown precision %d", cfg->precision);
   if (cfg->precision == LRCN_PREC_BF16X3 && (cfg->embed % 8 || cfg->hidden1 % 8 || cfg->hidden2 % 8))
     return fail(LRCN_ERR_ARG, "precision bf16x3 needs embed, hidden1, hidden2 to be multiples of 8 (TMA 16-byte pitch); use LRCN_PREC_FP32");
+  // softmax-CE and the beam top-K kernel stage one padded logits row in shared memory (200 KiB opt-in limit per CTA)
+  if (((size_t)cfg->vocab + 8) * 4 > 200 * 1024)
+    return fail(LRCN_ERR_ARG, "vocab %d too large: one logits row (%zu B) must fit the 200 KiB shared-memory row buffer of the softmax / top-K kernels (vocab <= 51192)",
+                cfg->vocab, ((size_t)cfg->vocab + 8) * 4);
+  if (cfg->n_gpus < 0 || cfg->n_gpus > LRCN_P2P_MAX_RANKS) return fail(LRCN_ERR_ARG, "n_gpus %d outside [0,%d]", cfg->n_gpus, LRCN_P2P_MAX_RANKS);
+  return LRCN_OK;
+}
+
+// single-process data-parallel group: one member handle per GPU, direct peer pointers (no IPC, no launcher)
+static int create_group(const lrcn_config* cfg, lrcn_handle* g) {
+  const int N = cfg->n_gpus;
+  g->cfg = *cfg;
+  g->nranks = N;
+  for (int i = 0; i < N; i++)
+    for (int j = 0; j < i; j++)
+      if (cfg->device_ids[i] == cfg->device_ids[j]) return fail(LRCN_ERR_ARG, "device_ids[%d] == device_ids[%d] == %d", i, j, cfg->device_ids[i]);
+  for (int i = 0; i < N; i++) {
+    lrcn_config c = *cfg;
+    c.n_gpus = 1;
+    c.device = cfg->device_ids[i];
+    c.max_batch = (cfg->max_batch + N - 1) / N;
+    c.max_gen_rows = (cfg->max_gen_rows + N - 1) / N;
+    lrcn_handle* m = new lrcn_handle();
+    g->members.push_back(m);
+    m->parent = g;
+    int rc = create_impl(&c, m);
+    if (rc) return rc;
+    m->rank = i; m->nranks = N;
+  }
+  for (int i = 0; i < N; i++) {
+    CK(cudaSetDevice(cfg->device_ids[i]));
+    for (int j = 0; j < N; j++) {
+      if (i == j) continue;
+      int can = 0;
+      CK(cudaDeviceCanAccessPeer(&can, cfg->device_ids[i], cfg->device_ids[j]));
+      if (!can) return fail(LRCN_ERR_CUDA, "GPU %d cannot access GPU %d as a peer (NVLink / P2P required for n_gpus > 1)", cfg->device_ids[i], cfg->device_ids[j]);
+      cudaError_t e = cudaDeviceEnablePeerAccess(cfg->device_ids[j], 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else if (e != cudaSuccess) return fail(LRCN_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", cfg->device_ids[i], cfg->device_ids[j], cudaGetErrorString(e));
+    }
+  }
+  for (int i = 0; i < N; i++) {
+    lrcn_handle* m = g->members[i];
+    P2PPeers pe{};
+    pe.nranks = N; pe.rank = i;
+    for (int p = 0; p < N; p++) {
+      lrcn_handle* q = g->members[p];
+      pe.g[p] = q->g; pe.w[p] = q->w; pe.ctl[p] = q->p2p_ctl; m->peer_m[p] = q->m; m->peer_v[p] = q->v;
+    }
+    m->peers = pe;
+    m->peers_direct = true;
+    m->p2p_ready = true;
+  }
+  return LRCN_OK;
+}
+
+extern "C" int lrcn_create(const lrcn_config* cfg, lrcn_handle** out) {
+  if (!cfg || !out) return fail(LRCN_ERR_ARG, "null argument");
+  int rc = validate_config(cfg);
+  if (rc) return rc;
   lrcn_handle* h = new lrcn_handle();
-  int rc = create_impl(cfg, h);
-  if (rc != LRCN_OK) { std::string keep = g_err; lrcn_destroy(h); g_err = keep; return rc; }
+  rc = cfg->n_gpus > 1 ? create_group(cfg, h) : create_impl(cfg, h);
+  if (rc != LRCN_OK) { std::string keep = g_err; s_destroy(h); g_err = keep; return rc; }
   *out = h;
   return LRCN_OK;
 }
 
 // ------------------------------------------------------------------------------------------ weights
-extern "C" int lrcn_param_shape(const lrcn_handle* h, int idx, int64_t* rows, int64_t* cols) {
+static int s_param_shape(const lrcn_handle* h, int idx, int64_t* rows, int64_t* cols) {
   if (!h || idx < 1 || idx > 9 || !rows || !cols) return fail(LRCN_ERR_ARG, "bad param index %d", idx);
   *rows = h->rows[idx - 1]; *cols = h->cols[idx - 1];
   return LRCN_OK;
@@ -440,7 +420,7 @@ static int download(lrcn_handle* h, const float* arena, int idx, float* dst) {
   CK(cudaStreamSynchronize(h->stream));
   return LRCN_OK;
 }
-extern "C" int lrcn_set_param(lrcn_handle* h, int idx, const float* p, int64_t rows, int64_t cols) {
+static int s_set_param(lrcn_handle* h, int idx, const float* p, int64_t rows, int64_t cols) {
   int rc = check_shape(h, idx, p, rows, cols);
   if (rc) return rc;
   g_counter = &h->counter;
@@ -453,50 +433,59 @@ extern "C" int lrcn_set_param(lrcn_handle* h, int idx, const float* p, int64_t r
   }
   return LRCN_OK;
 }
-extern "C" int lrcn_get_param(lrcn_handle* h, int idx, float* p, int64_t rows, int64_t cols) {
+static int s_get_param(lrcn_handle* h, int idx, float* p, int64_t rows, int64_t cols) {
   int rc = check_shape(h, idx, p, rows, cols);
   return rc ? rc : download(h, h->w, idx, p);
 }
-extern "C" int lrcn_get_grad(lrcn_handle* h, int idx, float* p, int64_t rows, int64_t cols) {
-  int rc = check_shape(h, idx, p, rows, cols);
-  return rc ? rc : download(h, h->g, idx, p);
+// Peer-memory data parallelism (dp_p2p.cu) leaves m, v -- and after a sharded train step the summed gradient -- current only
+// in each owner's shard: collect the other shards from their owners.  All ranks must be idle (e.g. at a checkpoint barrier).
+static int gather_shards(lrcn_handle* h, bool adam, bool grad) {
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int r = 0; r < h->nranks; r++) {
+    if (r == h->rank) continue;
+    size_t b, e;
+    dp_p2p_shard(h->P, h->nranks, r, &b, &e);
+    if (e <= b) continue;
+    // on the handle's stream: device-to-device cudaMemcpy does not synchronise the host, and the download that follows is stream-ordered
+    if (adam) {
+      CK(cudaMemcpyAsync(h->m + b, h->peer_m[r] + b, (e - b) * 4, cudaMemcpyDefault, h->stream));
+      CK(cudaMemcpyAsync(h->v + b, h->peer_v[r] + b, (e - b) * 4, cudaMemcpyDefault, h->stream));
+    }
+    if (grad) CK(cudaMemcpyAsync(h->g + b, h->peers.g[r] + b, (e - b) * 4, cudaMemcpyDefault, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  if (adam) h->adam_sharded = false;
+  if (grad) h->grad_sharded = false;
+  return LRCN_OK;
 }
-extern "C" int lrcn_get_adam_state(lrcn_handle* h, int idx, int which, float* p, int64_t rows, int64_t cols) {
+static int s_get_grad(lrcn_handle* h, int idx, float* p, int64_t rows, int64_t cols) {
+  int rc = check_shape(h, idx, p, rows, cols);
+  if (rc) return rc;
+  if (h->grad_sharded) { rc = gather_shards(h, false, true); if (rc) return rc; }
+  return download(h, h->g, idx, p);
+}
+static int s_get_adam_state(lrcn_handle* h, int idx, int which, float* p, int64_t rows, int64_t cols) {
   int rc = check_shape(h, idx, p, rows, cols);
   if (rc) return rc;
   if (which != 0 && which != 1) return fail(LRCN_ERR_ARG, "which must be 0 (m) or 1 (v)");
-  if (h->adam_sharded) {
-    // peer-memory data parallelism keeps m, v current only in each owner's shard: collect the other shards from their owners
-    // (all ranks must be idle, e.g. at a checkpoint barrier)
-    CK(cudaSetDevice(h->cfg.device));
-    CK(cudaStreamSynchronize(h->stream));
-    for (int r = 0; r < h->nranks; r++) {
-      if (r == h->rank) continue;
-      size_t b, e;
-      dp_p2p_shard(h->P, h->nranks, r, &b, &e);
-      if (e > b) {
-        // on the handle's stream: device-to-device cudaMemcpy does not synchronise the host, and the download below is stream-ordered
-        CK(cudaMemcpyAsync(h->m + b, h->peer_m[r] + b, (e - b) * 4, cudaMemcpyDefault, h->stream));
-        CK(cudaMemcpyAsync(h->v + b, h->peer_v[r] + b, (e - b) * 4, cudaMemcpyDefault, h->stream));
-      }
-    }
-    CK(cudaStreamSynchronize(h->stream));
-    h->adam_sharded = false;
-  }
+  if (h->adam_sharded) { rc = gather_shards(h, true, false); if (rc) return rc; }
   return download(h, which ? h->v : h->m, idx, p);
 }
-extern "C" int lrcn_set_adam_state(lrcn_handle* h, int idx, int which, const float* p, int64_t rows, int64_t cols) {
+static int s_set_adam_state(lrcn_handle* h, int idx, int which, const float* p, int64_t rows, int64_t cols) {
   int rc = check_shape(h, idx, p, rows, cols);
   if (rc) return rc;
   if (which != 0 && which != 1) return fail(LRCN_ERR_ARG, "which must be 0 (m) or 1 (v)");
+  // a partial overwrite of sharded state would mix current and stale shards: make the local copy whole first
+  if (h->adam_sharded) { rc = gather_shards(h, true, false); if (rc) return rc; }
   g_counter = &h->counter;
   return upload(h, which ? h->v : h->m, idx, p);
 }
-extern "C" int lrcn_get_adam_step(lrcn_handle* h, int64_t* t) { if (!h || !t) return fail(LRCN_ERR_ARG, "null"); *t = h->adam_t; return LRCN_OK; }
-extern "C" int lrcn_set_adam_step(lrcn_handle* h, int64_t t) { if (!h || t < 0) return fail(LRCN_ERR_ARG, "bad step"); h->adam_t = t; return LRCN_OK; }
+static int s_get_adam_step(lrcn_handle* h, int64_t* t) { if (!h || !t) return fail(LRCN_ERR_ARG, "null"); *t = h->adam_t; return LRCN_OK; }
+static int s_set_adam_step(lrcn_handle* h, int64_t t) { if (!h || t < 0) return fail(LRCN_ERR_ARG, "bad step"); h->adam_t = t; return LRCN_OK; }
 
 // ------------------------------------------------------------------------------------------ features
-extern "C" int lrcn_load_features(lrcn_handle* h, int split, const int64_t* ids, const float* feats, int64_t n) {
+static int s_load_features(lrcn_handle* h, int split, const int64_t* ids, const float* feats, int64_t n) {
   if (!h || !ids || !feats || n <= 0 || split < 0 || split > 1) return fail(LRCN_ERR_ARG, "bad argument to lrcn_load_features");
   CK(cudaSetDevice(h->cfg.device));
   Table& t = h->tab[split];
@@ -631,6 +620,14 @@ static void enqueue_forward(lrcn_handle* h, int split, int B, int l, bool train)
   {
     ZeroSegs z;
     z.add(h->d_counters, 256);
+    // slot 0 of the h / c slot buffers is h_0 = c_0 = 0 (initstate, lrcn.jl:512-526).  Its POSITION is fixed (rows [0, B)), but
+    // slot t of a call with a smaller B lands on rows [t*B_small, ...) -- inside slot 0 of a later, larger batch (average_loss
+    // runs B = 10 on the handle that trains at 256).  So the first B rows (fp32 and bf16 shadows) are cleared every step.
+    z.add(h1, (size_t)B * H1); z.add(c1, (size_t)B * H1); z.add(h2, (size_t)B * H2); z.add(c2, (size_t)B * H2);
+    if (h->bf16mode) {  // two bf16 per float; B*H is even (H % 8 == 0 in this mode)
+      z.add(SH(h, h1).hi, (size_t)B * H1 / 2); z.add(SH(h, h1).lo, (size_t)B * H1 / 2);
+      z.add(SH(h, h2).hi, (size_t)B * H2 / 2); z.add(SH(h, h2).lo, (size_t)B * H2 / 2);
+    }
     if (train) {
       z.add(h->g + h->off[8], h->P - h->off[8]);  // arena order [Wout, bout | W2, b2, Wf, Wcnn | W1, b1, Wemb]: everything from bout on
       z.add(WS(h, o.dh2), (size_t)R * H2);
@@ -729,14 +726,22 @@ static int run_cached(lrcn_handle* h, std::tuple<int, int, int, int> key, F fn) 
   return LRCN_OK;
 }
 
-static void fill_scalars(lrcn_handle* h, int B, int l, float pdrop, uint64_t seed, bool bump_adam) {
-  StepScalars* sc = h->h_sc;
-  const double ntok = (double)B * (l + 1) * h->nranks;
+// rows of the GLOBAL batch this step belongs to: the group dispatcher sets global_B; one process per GPU: equal shards
+static double global_rows(const lrcn_handle* h, int B) { return h->global_B > 0 ? (double)h->global_B : (double)B * h->nranks; }
+
+// fills the next pinned copy of the step scalars and enqueues its H2D copy; waits only if that ring entry's previous copy
+// (SC_RING steps ago) has not executed yet
+static int push_scalars(lrcn_handle* h, int B, int l, float pdrop, uint64_t seed, bool bump_adam) {
+  const int slot = h->sc_next;
+  h->sc_next = (slot + 1) % lrcn_handle::SC_RING;
+  if (h->sc_busy[slot]) CK(cudaEventSynchronize(h->sc_ev[slot]));
+  StepScalars* sc = h->h_sc + slot;
+  const double ntok = global_rows(h, B) * (l + 1);
   sc->inv_ntok = (float)(1.0 / ntok);
   sc->pdrop = pdrop;
   sc->keep_scale = pdrop > 0.f ? 1.0f / (1.0f - pdrop) : 1.0f;
   sc->drop_thresh = pdrop > 0.f ? (uint32_t)((double)pdrop * 16777216.0) : 0u;
-  sc->seed = seed;
+  sc->seed = seed + 0x9E3779B97F4A7C15ull * (uint64_t)h->rank;  // shards of one global batch draw different masks
   if (bump_adam) h->adam_t += 1;
   const int64_t t = h->adam_t > 0 ? h->adam_t : 1;
   sc->adam_d1 = (float)(1.0 - pow(h->cfg.beta1, (double)t));
@@ -744,6 +749,10 @@ static void fill_scalars(lrcn_handle* h, int B, int l, float pdrop, uint64_t see
   sc->lr = (float)h->cfg.lr; sc->beta1 = (float)h->cfg.beta1; sc->beta2 = (float)h->cfg.beta2; sc->eps = (float)h->cfg.eps;
   sc->one_m_beta1 = (float)(1.0 - h->cfg.beta1);
   sc->one_m_beta2 = (float)(1.0 - h->cfg.beta2);
+  CK(cudaMemcpyAsync(h->d_sc, sc, sizeof(StepScalars), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaEventRecord(h->sc_ev[slot], h->stream));
+  h->sc_busy[slot] = true;
+  return LRCN_OK;
 }
 
 static int nccl_check(int r, const char* what) {
@@ -757,8 +766,7 @@ static int run_step(lrcn_handle* h, int split, int B, int l, float pdrop, uint64
   CK(cudaSetDevice(h->cfg.device));
   const bool train = mode >= 1;
   const bool drop = train && pdrop > 0.f;
-  fill_scalars(h, B, l, train ? pdrop : 0.f, seed, mode == 2);
-  CK(cudaMemcpyAsync(h->d_sc, h->h_sc, sizeof(StepScalars), cudaMemcpyHostToDevice, h->stream));
+  { int rc0 = push_scalars(h, B, l, train ? pdrop : 0.f, seed, mode == 2); if (rc0) return rc0; }
   h->last_B = B; h->last_l = l;
   const int fl = (split << 1) | (drop ? 1 : 0);
   int rc;
@@ -777,7 +785,8 @@ static int run_step(lrcn_handle* h, int split, int B, int l, float pdrop, uint64
   if (h->p2p_ready && !force_nccl) {
     h->loss_is_total = true;
     static const bool replicated = getenv("LRCN_DP_REPLICATED_ADAM") != nullptr;
-    if (mode == 2 && !replicated) h->adam_sharded = true;
+    if (mode == 2 && !replicated) h->adam_sharded = h->grad_sharded = true;
+    else h->grad_sharded = false;
     // backward pass, then ONE owner-computes exchange kernel over NVLink peer memory between two flag barriers (dp_p2p.cu),
     // then the replicated Adam: no NCCL kernels competing for SMs with the persistent GEMM / LSTM kernels
     return run_cached(h, std::make_tuple(mode == 2 ? 22 : 21, B, l, fl), [&] {
@@ -847,7 +856,8 @@ static int run_step(lrcn_handle* h, int split, int B, int l, float pdrop, uint64
 
 static int finish_loss(lrcn_handle* h, int B, int l, double* total_out) {
   CK(cudaMemcpyAsync(h->h_loss, h->loss_is_total ? h->d_loss_total : h->d_loss, 8, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  int rc = sync_stream(h);
+  if (rc) return rc;
   *total_out = *h->h_loss;
   return LRCN_OK;
 }
@@ -867,7 +877,7 @@ static int stage_current(lrcn_handle* h, int split, const int64_t* image_ids, co
   return LRCN_OK;
 }
 
-extern "C" int lrcn_loss(lrcn_handle* h, int split, const int64_t* image_ids, const int64_t* tokens, int l, int B, double* sum_logp_out,
+static int s_loss(lrcn_handle* h, int split, const int64_t* image_ids, const int64_t* tokens, int l, int B, double* sum_logp_out,
                          int64_t* count_out) {
   int rc = stage_current(h, split, image_ids, tokens, l, B);
   if (rc) return rc;
@@ -880,7 +890,7 @@ extern "C" int lrcn_loss(lrcn_handle* h, int split, const int64_t* image_ids, co
   if (count_out) *count_out = (int64_t)B * (l + 1);
   return LRCN_OK;
 }
-extern "C" int lrcn_grad(lrcn_handle* h, int split, const int64_t* image_ids, const int64_t* tokens, int l, int B, float pdrop, uint64_t seed,
+static int s_grad(lrcn_handle* h, int split, const int64_t* image_ids, const int64_t* tokens, int l, int B, float pdrop, uint64_t seed,
                          double* loss_out) {
   if (pdrop < 0.f || pdrop >= 1.f) return fail(LRCN_ERR_ARG, "pdrop must be in [0,1)");
   int rc = stage_current(h, split, image_ids, tokens, l, B);
@@ -890,10 +900,10 @@ extern "C" int lrcn_grad(lrcn_handle* h, int split, const int64_t* image_ids, co
   double total;
   rc = finish_loss(h, B, l, &total);
   if (rc) return rc;
-  if (loss_out) *loss_out = -total / ((double)B * (l + 1) * h->nranks);
+  if (loss_out) *loss_out = -total / (global_rows(h, B) * (l + 1));
   return LRCN_OK;
 }
-extern "C" int lrcn_train_step(lrcn_handle* h, int split, const int64_t* image_ids, const int64_t* tokens, int l, int B, float pdrop,
+static int s_train_step(lrcn_handle* h, int split, const int64_t* image_ids, const int64_t* tokens, int l, int B, float pdrop,
                                uint64_t seed, double* loss_out) {
   if (pdrop < 0.f || pdrop >= 1.f) return fail(LRCN_ERR_ARG, "pdrop must be in [0,1)");
   int rc = stage_current(h, split, image_ids, tokens, l, B);
@@ -903,20 +913,23 @@ extern "C" int lrcn_train_step(lrcn_handle* h, int split, const int64_t* image_i
   double total;
   rc = finish_loss(h, B, l, &total);
   if (rc) return rc;
-  if (loss_out) *loss_out = -total / ((double)B * (l + 1) * h->nranks);
+  if (loss_out) *loss_out = -total / (global_rows(h, B) * (l + 1));
   return LRCN_OK;
 }
-extern "C" int lrcn_adam_update(lrcn_handle* h) {
+static int s_adam_update(lrcn_handle* h) {
   if (!h) return fail(LRCN_ERR_ARG, "null handle");
   CK(cudaSetDevice(h->cfg.device));
-  fill_scalars(h, 1, 0, 0.f, 0, true);
-  CK(cudaMemcpyAsync(h->d_sc, h->h_sc, sizeof(StepScalars), cudaMemcpyHostToDevice, h->stream));
+  // Peer-memory data parallelism keeps m, v current only in each owner's shard, and after a sharded train step the summed
+  // gradient too: a dense local Adam over the whole arena would silently diverge the replicas.
+  if (h->nranks > 1 && h->adam_sharded)
+    return fail(LRCN_ERR_STATE, "lrcn_adam_update after a sharded data-parallel train step: Adam state is distributed over the ranks; "
+                                "call lrcn_get_adam_state (gathers it) on every rank first, or keep using lrcn_train_step");
+  { int rc0 = push_scalars(h, 1, 0, 0.f, 0, true); if (rc0) return rc0; }
   g_counter = &h->counter;
   enqueue_adam(h);
-  CK(cudaStreamSynchronize(h->stream));
-  return LRCN_OK;
+  return sync_stream(h);
 }
-extern "C" int lrcn_get_token_logps(lrcn_handle* h, float* out, int64_t n) {
+static int s_get_token_logps(lrcn_handle* h, float* out, int64_t n) {
   if (!h || !out) return fail(LRCN_ERR_ARG, "null");
   int64_t have = (int64_t)h->last_B * (h->last_l + 1);
   if (n != have) return fail(LRCN_ERR_ARG, "expected %lld values", (long long)have);
@@ -926,7 +939,7 @@ extern "C" int lrcn_get_token_logps(lrcn_handle* h, float* out, int64_t n) {
   return LRCN_OK;
 }
 
-extern "C" int lrcn_stage_batch(lrcn_handle* h, int slot, int split, const int64_t* image_ids, const int64_t* tokens, int l, int B) {
+static int s_stage_batch(lrcn_handle* h, int slot, int split, const int64_t* image_ids, const int64_t* tokens, int l, int B) {
   if (!h || slot < 0 || slot >= 64) return fail(LRCN_ERR_ARG, "slot outside [0,64)");
   const size_t R = (size_t)(l + 1) * B;
   CK(cudaSetDevice(h->cfg.device));
@@ -945,7 +958,7 @@ extern "C" int lrcn_stage_batch(lrcn_handle* h, int slot, int split, const int64
   CK(cudaStreamSynchronize(h->stream));
   return LRCN_OK;
 }
-extern "C" int lrcn_train_step_staged(lrcn_handle* h, int slot, float pdrop, uint64_t seed, double* loss_out) {
+static int s_train_step_staged(lrcn_handle* h, int slot, float pdrop, uint64_t seed, double* loss_out) {
   if (!h || slot < 0 || slot >= 64 || !h->slots[slot].tok_in) return fail(LRCN_ERR_ARG, "slot %d not staged", slot);
   if (pdrop < 0.f || pdrop >= 1.f) return fail(LRCN_ERR_ARG, "pdrop must be in [0,1)");
   Slot& s = h->slots[slot];
@@ -960,7 +973,7 @@ extern "C" int lrcn_train_step_staged(lrcn_handle* h, int slot, float pdrop, uin
     double total;
     rc = finish_loss(h, s.B, s.l, &total);
     if (rc) return rc;
-    *loss_out = -total / ((double)s.B * (s.l + 1) * h->nranks);
+    *loss_out = -total / (global_rows(h, s.B) * (s.l + 1));
   }
   return LRCN_OK;
 }
@@ -1045,7 +1058,7 @@ __global__ void beam_init_kernel(int R, int maxlen, float* prob, int* last, int*
   lp[(size_t)r * maxlen] = 0.f;
 }
 
-extern "C" int lrcn_beam_search(lrcn_handle* h, int split, const int64_t* image_ids, int64_t n, int K, int nword, int64_t* tokens_out,
+static int s_beam_search(lrcn_handle* h, int split, const int64_t* image_ids, int64_t n, int K, int nword, int64_t* tokens_out,
                                 int32_t* len_out, float* prob_out, float* logp_out) {
   if (!h || !image_ids || !tokens_out || !len_out || !prob_out || n <= 0) return fail(LRCN_ERR_ARG, "bad argument to lrcn_beam_search");
   if (K < 1 || K > 11) return fail(LRCN_ERR_ARG, "beam_width %d outside [1,11]", K);
@@ -1069,8 +1082,7 @@ extern "C" int lrcn_beam_search(lrcn_handle* h, int split, const int64_t* image_
       if (it == tb.map.end()) return fail(LRCN_ERR_MISSING, "missing features for image id %lld (lrcn.jl:602-605)", (long long)image_ids[base + i]);
       rows[i] = it->second;
     }
-    fill_scalars(h, 1, 0, 0.f, 0, false);
-    CK(cudaMemcpyAsync(h->d_sc, h->h_sc, sizeof(StepScalars), cudaMemcpyHostToDevice, h->stream));
+    { int rc0 = push_scalars(h, 1, 0, 0.f, 0, false); if (rc0) return rc0; }
     CK(cudaMemcpyAsync(h->g_rows, rows.data(), (size_t)ni * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     try {
@@ -1128,7 +1140,7 @@ extern "C" int lrcn_comm_unique_id(char id[LRCN_COMM_ID_BYTES]) {
   memcpy(id, u.internal, LRCN_COMM_ID_BYTES);
   return LRCN_OK;
 }
-extern "C" int lrcn_comm_init(lrcn_handle* h, const char id[LRCN_COMM_ID_BYTES], int rank, int nranks) {
+static int s_comm_init(lrcn_handle* h, const char id[LRCN_COMM_ID_BYTES], int rank, int nranks) {
   if (!h || !id || nranks < 1 || rank < 0 || rank >= nranks) return fail(LRCN_ERR_ARG, "bad rank/nranks");
   NcclApi* n = nccl_api();
   if (!n) return fail(LRCN_ERR_NCCL, "libnccl.so.2 not loadable");
@@ -1147,7 +1159,7 @@ struct P2PBlob {  // LRCN_P2P_BLOB_BYTES
   cudaIpcMemHandle_t g, ctl, w, m, v;
 };
 static_assert(sizeof(P2PBlob) <= LRCN_P2P_BLOB_BYTES, "blob too large");
-extern "C" int lrcn_p2p_export(lrcn_handle* h, char blob[LRCN_P2P_BLOB_BYTES]) {
+static int s_p2p_export(lrcn_handle* h, char blob[LRCN_P2P_BLOB_BYTES]) {
   if (!h || !blob) return fail(LRCN_ERR_ARG, "null argument");
   CK(cudaSetDevice(h->cfg.device));
   P2PBlob b;
@@ -1162,7 +1174,7 @@ extern "C" int lrcn_p2p_export(lrcn_handle* h, char blob[LRCN_P2P_BLOB_BYTES]) {
   memcpy(blob, &b, sizeof b);
   return LRCN_OK;
 }
-extern "C" int lrcn_p2p_import(lrcn_handle* h, const char* blobs, int rank, int nranks) {
+static int s_p2p_import(lrcn_handle* h, const char* blobs, int rank, int nranks) {
   if (!h || !blobs || nranks < 1 || nranks > LRCN_P2P_MAX_RANKS || rank < 0 || rank >= nranks)
     return fail(LRCN_ERR_ARG, "bad rank/nranks (at most %d ranks)", LRCN_P2P_MAX_RANKS);
   if (h->comm && (h->rank != rank || h->nranks != nranks)) return fail(LRCN_ERR_ARG, "rank/nranks differ from lrcn_comm_init");
@@ -1193,20 +1205,19 @@ extern "C" int lrcn_p2p_import(lrcn_handle* h, const char* blobs, int rank, int 
 }
 
 // ------------------------------------------------------------------------------------------ measurement
-extern "C" int lrcn_sync(lrcn_handle* h) {
+static int s_sync(lrcn_handle* h) {
   if (!h) return fail(LRCN_ERR_ARG, "null handle");
   CK(cudaSetDevice(h->cfg.device));
-  CK(cudaStreamSynchronize(h->stream));
   CK(cudaStreamSynchronize(h->comm_stream));
-  return LRCN_OK;
+  return sync_stream(h);
 }
-extern "C" int lrcn_timer_start(lrcn_handle* h) {
+static int s_timer_start(lrcn_handle* h) {
   if (!h) return fail(LRCN_ERR_ARG, "null handle");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaEventRecord(h->ev0, h->stream));
   return LRCN_OK;
 }
-extern "C" int lrcn_timer_stop(lrcn_handle* h, float* ms) {
+static int s_timer_stop(lrcn_handle* h, float* ms) {
   if (!h || !ms) return fail(LRCN_ERR_ARG, "null");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaEventRecord(h->ev1, h->stream));
@@ -1214,12 +1225,12 @@ extern "C" int lrcn_timer_stop(lrcn_handle* h, float* ms) {
   CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
   return LRCN_OK;
 }
-extern "C" int lrcn_kernel_launches(lrcn_handle* h, int64_t* n) {
+static int s_kernel_launches(lrcn_handle* h, int64_t* n) {
   if (!h || !n) return fail(LRCN_ERR_ARG, "null");
   *n = h->counter.n;
   return LRCN_OK;
 }
-extern "C" int lrcn_get_trace(lrcn_handle* h, uint64_t* out, int64_t n) {
+static int s_get_trace(lrcn_handle* h, uint64_t* out, int64_t n) {
   if (!h || !out || n <= 0 || n > 512) return fail(LRCN_ERR_ARG, "bad argument");
   if (!h->d_trace) return fail(LRCN_ERR_STATE, "create the handle with LRCN_SEQ_TRACE=1 in the environment");
   CK(cudaSetDevice(h->cfg.device));
@@ -1227,14 +1238,14 @@ extern "C" int lrcn_get_trace(lrcn_handle* h, uint64_t* out, int64_t n) {
   CK(cudaMemcpy(out, h->d_trace, (size_t)n * 8, cudaMemcpyDeviceToHost));
   return LRCN_OK;
 }
-extern "C" int lrcn_flush_l2(lrcn_handle* h) {
+static int s_flush_l2(lrcn_handle* h) {
   if (!h) return fail(LRCN_ERR_ARG, "null handle");
   CK(cudaSetDevice(h->cfg.device));
   fill_l2_scratch(h->stream, h->l2_scratch, h->l2_n, 0.f);
   return LRCN_OK;
 }
 
-extern "C" int lrcn_time_kernel(lrcn_handle* h, const char* name, int reps, float* avg_ms, double* algo_bytes, double* algo_flops) {
+static int s_time_kernel(lrcn_handle* h, const char* name, int reps, float* avg_ms, double* algo_bytes, double* algo_flops) {
   if (!h || !name || reps < 1 || !avg_ms) return fail(LRCN_ERR_ARG, "bad argument");
   CK(cudaSetDevice(h->cfg.device));
   g_counter = &h->counter;
@@ -1288,114 +1299,371 @@ extern "C" int lrcn_time_kernel(lrcn_handle* h, const char* name, int reps, floa
   return LRCN_OK;
 }
 
-// ------------------------------------------------------------------------------------------ test hooks
-extern "C" int lrcn_test_gemm(lrcn_handle* h, int precision, int a_kmajor, int b_kmajor, int M, int N, int K, const float* A, const float* B,
-                              const float* bias, int beta, float* C) {
-  if (!h || !A || !B || !C || M <= 0 || N <= 0 || K <= 0) return fail(LRCN_ERR_ARG, "bad argument");
-  CK(cudaSetDevice(h->cfg.device));
-  g_counter = &h->counter;
-  // padded leading dimensions (multiples of 8) so the same buffers serve both kernels
-  const int lda = ((a_kmajor ? K : M) + 7) / 8 * 8, ldb = ((b_kmajor ? K : N) + 7) / 8 * 8;
-  const int ra = a_kmajor ? M : K, rb = b_kmajor ? N : K;
-  const int ca = a_kmajor ? K : M, cb = b_kmajor ? K : N;
-  float *dA = nullptr, *dB = nullptr, *dC = nullptr, *dbias = nullptr;
-  bf16 *ah = nullptr, *al = nullptr, *bh = nullptr, *bl = nullptr;
+// ------------------------------------------------------------------------------------------ ABI wrappers
+// Every exported call: argument check, sticky-failure check, dispatch (one GPU, or the members of a single-process group),
+// and -- through ApiGuard -- promotion of a CUDA / NCCL failure to the handle's sticky state.
+#include <thread>
+
+struct ApiGuard {
+  lrcn_handle* h;
+  explicit ApiGuard(lrcn_handle* h_) : h(h_) { g_last_code = 0; }
+  ~ApiGuard() {
+    if (h && !h->sticky_code && (g_last_code == LRCN_ERR_CUDA || g_last_code == LRCN_ERR_NCCL)) { h->sticky_code = g_last_code; h->sticky_msg = g_err; }
+  }
+};
+#define ENTER(h)                                                                                               \
+  if (!(h)) return fail(LRCN_ERR_ARG, "null handle");                                                          \
+  if ((h)->sticky_code) return fail((h)->sticky_code, "handle failed earlier and is unusable: %s", (h)->sticky_msg.c_str()); \
+  ApiGuard guard_(const_cast<lrcn_handle*>(h))
+static inline bool is_group(const lrcn_handle* h) { return !h->members.empty(); }
+#define FOR_ALL(h, call)                                       \
+  do {                                                         \
+    for (lrcn_handle* m : (h)->members) { int rc_ = (call); if (rc_) return rc_; } \
+    return LRCN_OK;                                            \
+  } while (0)
+
+// rows [off, off+b) of member i when a global batch of B rows is split over N members (sizes differ by at most one)
+static inline void shard_rows(int B, int N, int i, int* off, int* b) {
+  const int q = B / N, r = B % N;
+  *b = q + (i < r ? 1 : 0);
+  *off = i * q + (i < r ? i : r);
+}
+struct ShardBuf { std::vector<int64_t> tok; };
+static const int64_t* shard_tokens(const int64_t* tokens, int l, int B, int off, int b, ShardBuf& buf) {
+  if (!tokens || l == 0) return tokens;
+  buf.tok.resize((size_t)l * b);
+  for (int t = 0; t < l; t++) memcpy(buf.tok.data() + (size_t)t * b, tokens + (size_t)t * B + off, (size_t)b * sizeof(int64_t));
+  return buf.tok.data();
+}
+
+extern "C" int lrcn_destroy(lrcn_handle* h) { return s_destroy(h); }
+extern "C" int lrcn_param_shape(const lrcn_handle* h, int idx, int64_t* rows, int64_t* cols) {
+  ENTER(h);
+  return s_param_shape(is_group(h) ? h->members[0] : h, idx, rows, cols);
+}
+extern "C" int lrcn_set_param(lrcn_handle* h, int idx, const float* p, int64_t rows, int64_t cols) {
+  ENTER(h);
+  if (is_group(h)) FOR_ALL(h, s_set_param(m, idx, p, rows, cols));
+  return s_set_param(h, idx, p, rows, cols);
+}
+extern "C" int lrcn_get_param(lrcn_handle* h, int idx, float* p, int64_t rows, int64_t cols) {
+  ENTER(h);
+  return s_get_param(is_group(h) ? h->members[0] : h, idx, p, rows, cols);
+}
+extern "C" int lrcn_get_grad(lrcn_handle* h, int idx, float* p, int64_t rows, int64_t cols) {
+  ENTER(h);
+  return s_get_grad(is_group(h) ? h->members[0] : h, idx, p, rows, cols);
+}
+extern "C" int lrcn_get_adam_state(lrcn_handle* h, int idx, int which, float* p, int64_t rows, int64_t cols) {
+  ENTER(h);
+  return s_get_adam_state(is_group(h) ? h->members[0] : h, idx, which, p, rows, cols);
+}
+extern "C" int lrcn_set_adam_state(lrcn_handle* h, int idx, int which, const float* p, int64_t rows, int64_t cols) {
+  ENTER(h);
+  if (is_group(h)) FOR_ALL(h, s_set_adam_state(m, idx, which, p, rows, cols));
+  return s_set_adam_state(h, idx, which, p, rows, cols);
+}
+extern "C" int lrcn_get_adam_step(lrcn_handle* h, int64_t* t) {
+  ENTER(h);
+  return s_get_adam_step(is_group(h) ? h->members[0] : h, t);
+}
+extern "C" int lrcn_set_adam_step(lrcn_handle* h, int64_t t) {
+  ENTER(h);
+  if (is_group(h)) FOR_ALL(h, s_set_adam_step(m, t));
+  return s_set_adam_step(h, t);
+}
+extern "C" int lrcn_load_features(lrcn_handle* h, int split, const int64_t* ids, const float* feats, int64_t n) {
+  ENTER(h);
+  if (is_group(h)) FOR_ALL(h, s_load_features(m, split, ids, feats, n));  // replicated: 0.5 GB (Flickr30k) / 2 GB (COCO) per GPU
+  return s_load_features(h, split, ids, feats, n);
+}
+
+// forward / gradient / train step on a global batch, sharded by rows over the members of a group
+static int group_step(lrcn_handle* g, int mode, int split, const int64_t* image_ids, const int64_t* tokens, int l, int B, float pdrop, uint64_t seed,
+                      double* loss_or_sum, int64_t* count_out) {
+  const int N = (int)g->members.size();
+  if (!image_ids || (!tokens && l > 0)) return fail(LRCN_ERR_ARG, "null argument");
+  if (B <= 0 || B > g->cfg.max_batch) return fail(LRCN_ERR_ARG, "B=%d outside [1,%d]", B, g->cfg.max_batch);
+  if (mode > 0 && B < N) return fail(LRCN_ERR_ARG, "a training batch of %d rows cannot be split over %d GPUs", B, N);
+  std::vector<ShardBuf> bufs(N);
+  // stage every member first (a bad token / unknown image id fails the call before anything is launched), then launch all
+  for (int i = 0; i < N; i++) {
+    int off, b;
+    shard_rows(B, N, i, &off, &b);
+    if (b == 0) continue;
+    lrcn_handle* m = g->members[i];
+    int rc = stage_current(m, split, image_ids + off, shard_tokens(tokens, l, B, off, b, bufs[i]), l, b);
+    if (rc) return rc;
+  }
+  for (int i = 0; i < N; i++) {
+    int off, b;
+    shard_rows(B, N, i, &off, &b);
+    if (b == 0) continue;
+    lrcn_handle* m = g->members[i];
+    m->global_B = B;
+    int rc = run_step(m, split, b, l, pdrop, seed, mode);
+    if (rc) return rc;
+  }
+  double total = 0.0;
+  for (int i = 0; i < N; i++) {
+    int off, b;
+    shard_rows(B, N, i, &off, &b);
+    if (b == 0) continue;
+    double t;
+    int rc = finish_loss(g->members[i], b, l, &t);  // synchronises member i
+    if (rc) return rc;
+    if (mode == 0 || i == 0) total = mode == 0 ? total + t : t;  // training: the exchange kernel already summed the loss over the members
+  }
+  if (mode == 0) {
+    if (loss_or_sum) *loss_or_sum = total;
+    if (count_out) *count_out = (int64_t)B * (l + 1);
+  } else if (loss_or_sum) {
+    *loss_or_sum = -total / ((double)B * (l + 1));
+  }
+  g->last_B = B; g->last_l = l;
+  return LRCN_OK;
+}
+
+extern "C" int lrcn_loss(lrcn_handle* h, int split, const int64_t* image_ids, const int64_t* tokens, int l, int B, double* sum_logp_out,
+                         int64_t* count_out) {
+  ENTER(h);
+  if (is_group(h)) return group_step(h, 0, split, image_ids, tokens, l, B, 0.f, 0, sum_logp_out, count_out);
+  return s_loss(h, split, image_ids, tokens, l, B, sum_logp_out, count_out);
+}
+extern "C" int lrcn_grad(lrcn_handle* h, int split, const int64_t* image_ids, const int64_t* tokens, int l, int B, float pdrop, uint64_t seed,
+                         double* loss_out) {
+  ENTER(h);
+  if (pdrop < 0.f || pdrop >= 1.f) return fail(LRCN_ERR_ARG, "pdrop must be in [0,1)");
+  if (is_group(h)) return group_step(h, 1, split, image_ids, tokens, l, B, pdrop, seed, loss_out, nullptr);
+  return s_grad(h, split, image_ids, tokens, l, B, pdrop, seed, loss_out);
+}
+extern "C" int lrcn_train_step(lrcn_handle* h, int split, const int64_t* image_ids, const int64_t* tokens, int l, int B, float pdrop,
+                               uint64_t seed, double* loss_out) {
+  ENTER(h);
+  if (pdrop < 0.f || pdrop >= 1.f) return fail(LRCN_ERR_ARG, "pdrop must be in [0,1)");
+  if (is_group(h)) return group_step(h, 2, split, image_ids, tokens, l, B, pdrop, seed, loss_out, nullptr);
+  return s_train_step(h, split, image_ids, tokens, l, B, pdrop, seed, loss_out);
+}
+extern "C" int lrcn_adam_update(lrcn_handle* h) {
+  ENTER(h);
+  if (is_group(h)) {
+    // every member holds the all-reduced gradient after lrcn_grad; make the Adam state whole everywhere first (all idle here)
+    for (lrcn_handle* m : h->members) if (m->adam_sharded) { int rc = gather_shards(m, true, false); if (rc) return rc; }
+    FOR_ALL(h, s_adam_update(m));
+  }
+  return s_adam_update(h);
+}
+extern "C" int lrcn_get_token_logps(lrcn_handle* h, float* out, int64_t n) {
+  ENTER(h);
+  if (!is_group(h)) return s_get_token_logps(h, out, n);
+  if (!out) return fail(LRCN_ERR_ARG, "null");
+  const int B = h->last_B, T = h->last_l + 1, N = (int)h->members.size();
+  if (n != (int64_t)B * T) return fail(LRCN_ERR_ARG, "expected %lld values", (long long)B * T);
+  std::vector<float> tmp;
+  for (int i = 0; i < N; i++) {
+    int off, b;
+    shard_rows(B, N, i, &off, &b);
+    if (b == 0) continue;
+    tmp.resize((size_t)b * T);
+    int rc = s_get_token_logps(h->members[i], tmp.data(), (int64_t)b * T);
+    if (rc) return rc;
+    for (int t = 0; t < T; t++) memcpy(out + (size_t)t * B + off, tmp.data() + (size_t)t * b, (size_t)b * sizeof(float));
+  }
+  return LRCN_OK;
+}
+extern "C" int lrcn_stage_batch(lrcn_handle* h, int slot, int split, const int64_t* image_ids, const int64_t* tokens, int l, int B) {
+  ENTER(h);
+  if (!is_group(h)) return s_stage_batch(h, slot, split, image_ids, tokens, l, B);
+  const int N = (int)h->members.size();
+  if (!image_ids || (!tokens && l > 0)) return fail(LRCN_ERR_ARG, "null argument");
+  if (B < N || B > h->cfg.max_batch) return fail(LRCN_ERR_ARG, "B=%d outside [%d,%d]", B, N, h->cfg.max_batch);
+  if (slot < 0 || slot >= 64) return fail(LRCN_ERR_ARG, "slot outside [0,64)");
+  ShardBuf buf;
+  for (int i = 0; i < N; i++) {
+    int off, b;
+    shard_rows(B, N, i, &off, &b);
+    int rc = s_stage_batch(h->members[i], slot, split, image_ids + off, shard_tokens(tokens, l, B, off, b, buf), l, b);
+    if (rc) return rc;
+  }
+  h->slots[slot].B = B; h->slots[slot].l = l;
+  return LRCN_OK;
+}
+extern "C" int lrcn_train_step_staged(lrcn_handle* h, int slot, float pdrop, uint64_t seed, double* loss_out) {
+  ENTER(h);
+  if (!is_group(h)) return s_train_step_staged(h, slot, pdrop, seed, loss_out);
+  if (slot < 0 || slot >= 64 || h->slots[slot].B == 0) return fail(LRCN_ERR_ARG, "slot %d not staged", slot);
+  for (lrcn_handle* m : h->members) {
+    m->global_B = h->slots[slot].B;
+    int rc = s_train_step_staged(m, slot, pdrop, seed, m == h->members[0] ? loss_out : nullptr);
+    if (rc) return rc;
+  }
+  return LRCN_OK;
+}
+
+extern "C" int lrcn_beam_search(lrcn_handle* h, int split, const int64_t* image_ids, int64_t n, int K, int nword, int64_t* tokens_out,
+                                int32_t* len_out, float* prob_out, float* logp_out) {
+  ENTER(h);
+  if (!is_group(h)) return s_beam_search(h, split, image_ids, n, K, nword, tokens_out, len_out, prob_out, logp_out);
+  // images are independent (lrcn.jl:152-155 loops them serially): contiguous slices, one worker thread per GPU, no collective
+  if (!image_ids || !tokens_out || !len_out || !prob_out || n <= 0) return fail(LRCN_ERR_ARG, "bad argument to lrcn_beam_search");
+  if (nword < 1 || nword + 2 > 64) return fail(LRCN_ERR_ARG, "nword %d outside [1,62]", nword);
+  const int N = (int)h->members.size();
+  const int maxlen = nword + 2;
+  std::vector<int> rcs(N, LRCN_OK);
+  std::vector<std::string> msgs(N);
+  std::vector<std::thread> th;
+  for (int i = 0; i < N; i++) {
+    const int64_t lo = n * i / N, hi = n * (i + 1) / N;
+    if (hi <= lo) continue;
+    th.emplace_back([&, i, lo, hi] {
+      rcs[i] = s_beam_search(h->members[i], split, image_ids + lo, hi - lo, K, nword, tokens_out + lo * maxlen, len_out + lo, prob_out + lo,
+                             logp_out ? logp_out + lo * (maxlen - 1) : nullptr);
+      if (rcs[i]) msgs[i] = g_err;  // thread-local message of the worker
+    });
+  }
+  for (auto& t : th) t.join();
+  for (int i = 0; i < N; i++) if (rcs[i]) return fail(rcs[i], "GPU %d: %s", h->members[i]->cfg.device, msgs[i].c_str());
+  return LRCN_OK;
+}
+
+extern "C" int lrcn_comm_init(lrcn_handle* h, const char id[LRCN_COMM_ID_BYTES], int rank, int nranks) {
+  ENTER(h);
+  if (is_group(h)) return fail(LRCN_ERR_STATE, "this handle already drives %d GPUs by itself (cfg.n_gpus)", (int)h->members.size());
+  return s_comm_init(h, id, rank, nranks);
+}
+extern "C" int lrcn_p2p_export(lrcn_handle* h, char blob[LRCN_P2P_BLOB_BYTES]) {
+  ENTER(h);
+  if (is_group(h)) return fail(LRCN_ERR_STATE, "this handle already drives %d GPUs by itself (cfg.n_gpus)", (int)h->members.size());
+  return s_p2p_export(h, blob);
+}
+extern "C" int lrcn_p2p_import(lrcn_handle* h, const char* blobs, int rank, int nranks) {
+  ENTER(h);
+  if (is_group(h)) return fail(LRCN_ERR_STATE, "this handle already drives %d GPUs by itself (cfg.n_gpus)", (int)h->members.size());
+  return s_p2p_import(h, blobs, rank, nranks);
+}
+extern "C" int lrcn_sync(lrcn_handle* h) {
+  ENTER(h);
+  if (is_group(h)) FOR_ALL(h, s_sync(m));
+  return s_sync(h);
+}
+extern "C" int lrcn_timer_start(lrcn_handle* h) {
+  ENTER(h);
+  return s_timer_start(is_group(h) ? h->members[0] : h);
+}
+extern "C" int lrcn_timer_stop(lrcn_handle* h, float* ms) {
+  ENTER(h);
+  if (!is_group(h)) return s_timer_stop(h, ms);
+  int rc = s_timer_stop(h->members[0], ms);  // the steps of all members end together (cross-GPU barrier inside the step)
+  if (rc) return rc;
+  FOR_ALL(h, s_sync(m));
+}
+extern "C" int lrcn_kernel_launches(lrcn_handle* h, int64_t* n) {
+  ENTER(h);
+  if (!is_group(h)) return s_kernel_launches(h, n);
+  if (!n) return fail(LRCN_ERR_ARG, "null");
+  *n = 0;
+  for (lrcn_handle* m : h->members) *n += m->counter.n;
+  return LRCN_OK;
+}
+extern "C" int lrcn_get_trace(lrcn_handle* h, uint64_t* out, int64_t n) {
+  ENTER(h);
+  return s_get_trace(is_group(h) ? h->members[0] : h, out, n);
+}
+extern "C" int lrcn_flush_l2(lrcn_handle* h) {
+  ENTER(h);
+  if (is_group(h)) FOR_ALL(h, s_flush_l2(m));
+  return s_flush_l2(h);
+}
+extern "C" int lrcn_time_kernel(lrcn_handle* h, const char* name, int reps, float* avg_ms, double* algo_bytes, double* algo_flops) {
+  ENTER(h);
+  return s_time_kernel(is_group(h) ? h->members[0] : h, name, reps, avg_ms, algo_bytes, algo_flops);
+}
+
+// ------------------------------------------------------------------------------------------ checkpoint
+// The reference saves `model` (Any[9] of Float32 matrices) and `vocab` (Dict) through JLD/HDF5 (lrcn.jl:88-93,183-186,
+// 228-231,775-781).  No HDF5 exists in this image, so the library reads and writes a raw little-endian SIDECAR file with the
+// same content plus the Adam state the reference never saved (resuming otherwise restarts Adam from zero):
+//   "LRCNB2CK" | u32 version=1 | u32 flags (1: Adam state present) | i32 E,H1,H2,V | i64 adam_t | i64 aux_bytes
+//   9 x { i64 rows, i64 cols, rows*cols float32 column-major }                    -- model[1..9], exactly what JLD holds
+//   if flags&1: 9 x m then 9 x v in the same layout                               -- Knet Adam fstm / scndm
+//   aux_bytes of caller data (the host writes the vocab Dict as "word\tindex\n" lines, UTF-8)
+// julia/lrcn_b200.jl carries a pure-Julia reader/writer of the same file (read_checkpoint / write_checkpoint).
+static int ck_write(FILE* f, const void* p, size_t n) { return fwrite(p, 1, n, f) == n ? 0 : 1; }
+static int ck_read(FILE* f, void* p, size_t n) { return fread(p, 1, n, f) == n ? 0 : 1; }
+
+extern "C" int lrcn_checkpoint_save(lrcn_handle* h, const char* path, int with_adam, const void* aux, int64_t aux_bytes) {
+  ENTER(h);
+  if (!path || aux_bytes < 0 || (aux_bytes > 0 && !aux)) return fail(LRCN_ERR_ARG, "bad argument to lrcn_checkpoint_save");
+  lrcn_handle* m0 = is_group(h) ? h->members[0] : h;
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(LRCN_ERR_ARG, "cannot open %s for writing", path);
+  const uint32_t version = 1, flags = with_adam ? 1u : 0u;
+  const int32_t dims[4] = {m0->E, m0->H1, m0->H2, m0->V};
+  int bad = ck_write(f, "LRCNB2CK", 8) | ck_write(f, &version, 4) | ck_write(f, &flags, 4) | ck_write(f, dims, 16) | ck_write(f, &m0->adam_t, 8) |
+            ck_write(f, &aux_bytes, 8);
+  std::vector<float> buf;
   int rc = LRCN_OK;
-  auto cleanup = [&] { for (void* p : {(void*)dA, (void*)dB, (void*)dC, (void*)dbias, (void*)ah, (void*)al, (void*)bh, (void*)bl}) if (p) cudaFree(p); };
-#define CKT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(LRCN_ERR_CUDA, "%s -> %s", #call, cudaGetErrorString(e_)); cleanup(); return rc; } } while (0)
-  const size_t na = ((size_t)ra * lda + 63) / 64 * 64, nb = ((size_t)rb * ldb + 63) / 64 * 64;
-  CKT(cudaMalloc(&dA, na * 4)); CKT(cudaMalloc(&dB, nb * 4)); CKT(cudaMalloc(&dC, (size_t)M * N * 4));
-  CKT(cudaMemset(dA, 0, na * 4)); CKT(cudaMemset(dB, 0, nb * 4));
-  CKT(cudaMemcpy2D(dA, (size_t)lda * 4, A, (size_t)ca * 4, (size_t)ca * 4, ra, cudaMemcpyHostToDevice));
-  CKT(cudaMemcpy2D(dB, (size_t)ldb * 4, B, (size_t)cb * 4, (size_t)cb * 4, rb, cudaMemcpyHostToDevice));
-  CKT(cudaMemcpy(dC, C, (size_t)M * N * 4, cudaMemcpyHostToDevice));
-  if (bias) { CKT(cudaMalloc(&dbias, (size_t)N * 4)); CKT(cudaMemcpy(dbias, bias, (size_t)N * 4, cudaMemcpyHostToDevice)); }
-  if (precision == LRCN_PREC_FP32) {
-    sgemm(h->stream, a_kmajor, b_kmajor, M, N, K, dA, lda, dB, ldb, dC, N, beta != 0, dbias);
-  } else {
-    CKT(cudaMalloc(&ah, na * 2)); CKT(cudaMalloc(&al, na * 2)); CKT(cudaMalloc(&bh, nb * 2)); CKT(cudaMalloc(&bl, nb * 2));
-    split_bf16(h->stream, dA, na, ah, al);
-    split_bf16(h->stream, dB, nb, bh, bl);
-    if (!gemm_bf16x3(h->stream, a_kmajor, b_kmajor, M, N, K, ah, al, lda, bh, bl, ldb, dC, N, beta != 0, dbias, nullptr, nullptr)) {
-      rc = fail(LRCN_ERR_CUDA, "%s", gemm_bf16x3_last_error());
-      cudaStreamSynchronize(h->stream);
-      cleanup();
-      return rc;
+  for (int sect = 0; sect < (with_adam ? 3 : 1) && !bad && !rc; sect++)
+    for (int k = 1; k <= 9 && !bad && !rc; k++) {
+      const int64_t r = m0->rows[k - 1], c = m0->cols[k - 1];
+      buf.resize((size_t)(r * c));
+      rc = sect == 0 ? s_get_param(m0, k, buf.data(), r, c) : s_get_adam_state(m0, k, sect - 1, buf.data(), r, c);
+      if (!rc) bad = ck_write(f, &r, 8) | ck_write(f, &c, 8) | ck_write(f, buf.data(), buf.size() * 4);
+    }
+  if (!bad && !rc && aux_bytes > 0) bad = ck_write(f, aux, (size_t)aux_bytes);
+  if (fclose(f) != 0) bad = 1;
+  if (rc) return rc;
+  if (bad) return fail(LRCN_ERR_ARG, "short write to %s", path);
+  return LRCN_OK;
+}
+
+extern "C" int lrcn_checkpoint_load(lrcn_handle* h, const char* path, int* had_adam, void* aux_out, int64_t aux_cap, int64_t* aux_bytes_out) {
+  ENTER(h);
+  if (!path) return fail(LRCN_ERR_ARG, "null path");
+  lrcn_handle* m0 = is_group(h) ? h->members[0] : h;
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(LRCN_ERR_ARG, "cannot open %s", path);
+  char magic[8];
+  uint32_t version = 0, flags = 0;
+  int32_t dims[4];
+  int64_t adam_t = 0, aux_bytes = 0;
+  int rc = LRCN_OK;
+  if (ck_read(f, magic, 8) || memcmp(magic, "LRCNB2CK", 8) || ck_read(f, &version, 4) || version != 1 || ck_read(f, &flags, 4) || ck_read(f, dims, 16) ||
+      ck_read(f, &adam_t, 8) || ck_read(f, &aux_bytes, 8) || adam_t < 0 || aux_bytes < 0) {
+    fclose(f);
+    return fail(LRCN_ERR_ARG, "%s is not an LRCNB2CK version-1 checkpoint", path);
+  }
+  if (dims[0] != m0->E || dims[1] != m0->H1 || dims[2] != m0->H2 || dims[3] != m0->V) {
+    fclose(f);
+    return fail(LRCN_ERR_ARG, "checkpoint is for embed %d hidden %d %d vocab %d; this handle has %d / %d %d / %d", dims[0], dims[1], dims[2], dims[3], m0->E,
+                m0->H1, m0->H2, m0->V);
+  }
+  std::vector<float> buf;
+  for (int sect = 0; sect < ((flags & 1u) ? 3 : 1) && !rc; sect++)
+    for (int k = 1; k <= 9 && !rc; k++) {
+      int64_t r = 0, c = 0;
+      if (ck_read(f, &r, 8) || ck_read(f, &c, 8) || r != m0->rows[k - 1] || c != m0->cols[k - 1]) { rc = fail(LRCN_ERR_ARG, "%s: matrix %d has the wrong shape", path, k); break; }
+      buf.resize((size_t)(r * c));
+      if (ck_read(f, buf.data(), buf.size() * 4)) { rc = fail(LRCN_ERR_ARG, "%s is truncated", path); break; }
+      if (is_group(h)) {
+        for (lrcn_handle* m : h->members) { rc = sect == 0 ? s_set_param(m, k, buf.data(), r, c) : s_set_adam_state(m, k, sect - 1, buf.data(), r, c); if (rc) break; }
+      } else {
+        rc = sect == 0 ? s_set_param(h, k, buf.data(), r, c) : s_set_adam_state(h, k, sect - 1, buf.data(), r, c);
+      }
+    }
+  if (!rc) {
+    if (aux_bytes_out) *aux_bytes_out = aux_bytes;
+    if (aux_out && aux_bytes > 0) {
+      if (aux_cap < aux_bytes) rc = fail(LRCN_ERR_ARG, "aux buffer of %lld bytes < %lld stored", (long long)aux_cap, (long long)aux_bytes);
+      else if (ck_read(f, aux_out, (size_t)aux_bytes)) rc = fail(LRCN_ERR_ARG, "%s is truncated", path);
     }
   }
-  CKT(cudaStreamSynchronize(h->stream));
-  CKT(cudaMemcpy(C, dC, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
-  cleanup();
-  return LRCN_OK;
-}
-
-extern "C" int lrcn_test_gemm_time(lrcn_handle* h, int a_kmajor, int b_kmajor, int M, int N, int K, int with_shadow_out, int iters, int dbg,
-                                   float* avg_ms_out) {
-  if (!h || !avg_ms_out || M <= 0 || N <= 0 || K <= 0 || iters < 1) return fail(LRCN_ERR_ARG, "bad argument");
-  CK(cudaSetDevice(h->cfg.device));
-  g_counter = &h->counter;
-  const int lda = ((a_kmajor ? K : M) + 7) / 8 * 8, ldb = ((b_kmajor ? K : N) + 7) / 8 * 8, ldc = (N + 7) / 8 * 8;
-  const size_t na = (size_t)(a_kmajor ? M : K) * lda, nb = (size_t)(b_kmajor ? N : K) * ldb, nc = (size_t)M * ldc;
-  float* dC = nullptr;
-  bf16 *ah = nullptr, *al = nullptr, *bh = nullptr, *bl = nullptr, *ch = nullptr, *cl = nullptr;
-  int rc = LRCN_OK;
-  auto cleanup = [&] { for (void* p : {(void*)dC, (void*)ah, (void*)al, (void*)bh, (void*)bl, (void*)ch, (void*)cl}) if (p) cudaFree(p); g_gemm_dbg = 0; };
-  CKT(cudaMalloc(&dC, nc * 4)); CKT(cudaMalloc(&ah, na * 2)); CKT(cudaMalloc(&al, na * 2)); CKT(cudaMalloc(&bh, nb * 2)); CKT(cudaMalloc(&bl, nb * 2));
-  if (with_shadow_out) { CKT(cudaMalloc(&ch, nc * 2)); CKT(cudaMalloc(&cl, nc * 2)); }
-  CKT(cudaMemset(ah, 0x3c, na * 2)); CKT(cudaMemset(al, 0x38, na * 2)); CKT(cudaMemset(bh, 0x3c, nb * 2)); CKT(cudaMemset(bl, 0x38, nb * 2));
-  g_gemm_dbg = dbg;
-  for (int i = -2; i < iters; i++) {
-    if (i == 0) CKT(cudaEventRecord(h->ev0, h->stream));
-    if (!gemm_bf16x3(h->stream, a_kmajor, b_kmajor, M, N, K, ah, al, lda, bh, bl, ldb, dC, ldc, false, nullptr, ch, cl)) {
-      rc = fail(LRCN_ERR_CUDA, "%s", gemm_bf16x3_last_error());
-      cudaStreamSynchronize(h->stream);
-      cleanup();
-      return rc;
-    }
+  fclose(f);
+  if (rc) return rc;
+  if (had_adam) *had_adam = (flags & 1u) ? 1 : 0;
+  if (flags & 1u) {  // resume Adam where it stopped; a model-only file leaves the optimizer as it is (the reference restarts it)
+    if (is_group(h)) { for (lrcn_handle* m : h->members) m->adam_t = adam_t; }
+    else h->adam_t = adam_t;
   }
-  CKT(cudaEventRecord(h->ev1, h->stream));
-  CKT(cudaEventSynchronize(h->ev1));
-  float ms = 0.f;
-  CKT(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-  *avg_ms_out = ms / iters;
-  cleanup();
-  return LRCN_OK;
-}
-
-extern "C" int lrcn_test_mma_rate(lrcn_handle* h, int M, int N, int n_mma, int commit_every, int issuers, int64_t* issue_clk_out,
-                                  int64_t* total_clk_out) {
-  if (!h || !issue_clk_out || !total_clk_out || (M != 64 && M != 128) || N < 16 || N > 256 || (N % 16) || n_mma < 1 || issuers < 1 || issuers > 2 || commit_every < 0)
-    return fail(LRCN_ERR_ARG, "bad argument");
-  CK(cudaSetDevice(h->cfg.device));
-  long long a = 0, b = 0;
-  if (!probe_mma(h->stream, M, N, n_mma, commit_every, issuers, &a, &b)) return fail(LRCN_ERR_CUDA, "probe_mma failed: %s", cudaGetErrorString(cudaGetLastError()));
-  *issue_clk_out = a; *total_clk_out = b;
-  return LRCN_OK;
-}
-
-extern "C" int lrcn_test_beam_select(lrcn_handle* h, const float* probs, const float* parent_prob, int n_images, int K, int V, int first_step,
-                                     int64_t* tok_out, int32_t* parent_out, float* score_out) {
-  if (!h || !probs || !parent_prob || n_images <= 0 || K < 1 || K > 11 || V < K) return fail(LRCN_ERR_ARG, "bad argument");
-  CK(cudaSetDevice(h->cfg.device));
-  g_counter = &h->counter;
-  const int R = n_images * K;
-  float *dp = nullptr, *dpp = nullptr, *cs = nullptr, *clp = nullptr, *ss = nullptr, *slp = nullptr;
-  int *ct = nullptr, *st = nullptr, *sp = nullptr;
-  int rc = LRCN_OK;
-  auto cleanup = [&] { for (void* p : {(void*)dp, (void*)dpp, (void*)cs, (void*)clp, (void*)ss, (void*)slp, (void*)ct, (void*)st, (void*)sp}) if (p) cudaFree(p); };
-  CKT(cudaMalloc(&dp, (size_t)R * V * 4)); CKT(cudaMalloc(&dpp, (size_t)R * 4)); CKT(cudaMalloc(&cs, (size_t)R * K * 4)); CKT(cudaMalloc(&clp, (size_t)R * K * 4));
-  CKT(cudaMalloc(&ss, (size_t)R * 4)); CKT(cudaMalloc(&slp, (size_t)R * 4)); CKT(cudaMalloc(&ct, (size_t)R * K * 4)); CKT(cudaMalloc(&st, (size_t)R * 4));
-  CKT(cudaMalloc(&sp, (size_t)R * 4));
-  CKT(cudaMemcpy(dp, probs, (size_t)R * V * 4, cudaMemcpyHostToDevice));
-  CKT(cudaMemcpy(dpp, parent_prob, (size_t)R * 4, cudaMemcpyHostToDevice));
-  beam_row_topk_probs(h->stream, dp, V, R, V, K, dpp, ct, cs, clp);
-  beam_select(h->stream, ct, cs, clp, n_images, K, first_step, st, sp, ss, slp);
-  CKT(cudaStreamSynchronize(h->stream));
-  std::vector<int> t(R), p(R);
-  CKT(cudaMemcpy(t.data(), st, (size_t)R * 4, cudaMemcpyDeviceToHost));
-  CKT(cudaMemcpy(p.data(), sp, (size_t)R * 4, cudaMemcpyDeviceToHost));
-  CKT(cudaMemcpy(score_out, ss, (size_t)R * 4, cudaMemcpyDeviceToHost));
-  for (int i = 0; i < R; i++) { tok_out[i] = (int64_t)t[i] + 1; parent_out[i] = p[i]; }
-  cleanup();
   return LRCN_OK;
 }

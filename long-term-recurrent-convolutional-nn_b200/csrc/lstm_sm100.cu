@@ -431,21 +431,37 @@ __device__ __forceinline__ void grid_arrive(unsigned int* ctr) {
 }
 __device__ __forceinline__ void grid_wait(const unsigned int* ctr, unsigned int target) {
   const long long t0 = clock64();
+  unsigned int spins = 0;
   while (true) {
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
     if (v >= target) break;
-    if (clock64() - t0 > 4000000000ll) { printf("lrcn lstm_seq: grid barrier timeout (block %d,%d have %u want %u)\n", blockIdx.x, blockIdx.y, v, target); __trap(); }
+    if ((++spins & 63u) == 0u) {
+      if (dev_aborted()) break;
+      if (clock64() - t0 > WAIT_LIMIT_CLK) {
+        printf("lrcn lstm_seq: grid barrier timeout (block %d,%d have %u want %u)\n", blockIdx.x, blockIdx.y, v, target);
+        dev_abort_set();
+        break;
+      }
+    }
   }
 }
 // poll with relaxed loads, acquire once the target is reached
 __device__ __forceinline__ void grid_wait_relaxed(const unsigned int* ctr, unsigned int target) {
   const long long t0 = clock64();
+  unsigned int spins = 0;
   while (true) {
     unsigned int v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
     if (v >= target) break;
-    if (clock64() - t0 > 4000000000ll) { printf("lrcn lstm_seq: grid barrier timeout (block %d,%d have %u want %u)\n", blockIdx.x, blockIdx.y, v, target); __trap(); }
+    if ((++spins & 63u) == 0u) {
+      if (dev_aborted()) break;
+      if (clock64() - t0 > WAIT_LIMIT_CLK) {
+        printf("lrcn lstm_seq: grid barrier timeout (block %d,%d have %u want %u)\n", blockIdx.x, blockIdx.y, v, target);
+        dev_abort_set();
+        break;
+      }
+    }
   }
   asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
@@ -464,12 +480,18 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
+  unsigned int spins = 0;
   while (true) {
     uint32_t done;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (done) break;
-    if (clock64() - t0 > 4000000000ll) { printf("lrcn lstm_seq: cluster mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
+    if ((++spins & 255u) == 0u && dev_aborted()) break;
+    if (clock64() - t0 > WAIT_LIMIT_CLK) {
+      printf("lrcn lstm_seq: cluster mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      dev_abort_set();
+      break;
+    }
   }
 }
 
@@ -1430,6 +1452,8 @@ bool lstm_bwd_seq(cudaStream_t s, int B, int H, int T, const __nv_bfloat16* wt_h
   *launched = true;
   return check_launch("lstm_bwd_seq launch");
 }
+
+bool lstm_bind_abort(unsigned int* host_flag) { return dev_abort_bind(host_flag) == cudaSuccess; }
 
 bool init_lstm_sm100() {
   cudaError_t e = cudaFuncSetAttribute(lstm_fwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM);

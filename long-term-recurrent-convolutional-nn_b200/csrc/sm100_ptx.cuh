@@ -9,6 +9,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include "kernels.cuh"
+
 namespace lrcn {
 namespace ptx {
 
@@ -38,14 +40,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
-// bounded wait: a protocol bug must trap (launch failure) instead of hanging the GPU box
+// bounded wait: a protocol bug must end the kernel (flag + drain, kernels.cuh) instead of hanging the GPU box
+constexpr long long WAIT_LIMIT_CLK = 4000000000ll;  // ~2 s
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+  unsigned int spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) {
+    if ((++spins & 255u) == 0u && dev_aborted()) return;
+    if (clock64() - t0 > WAIT_LIMIT_CLK) {
       printf("lrcn sm100: mbarrier timeout (block %d,%d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
-      __trap();
+      dev_abort_set();
+      return;
     }
   }
 }

@@ -13,6 +13,7 @@ liblrcn_b200.so -- this module only marshals the reference's data formats:
 """
 from __future__ import annotations
 
+import struct
 import sys
 
 import numpy as np
@@ -56,6 +57,16 @@ class LRCN:
     def model(self):
         """Host copy of the 9 matrices, e.g. for save(file,"model",model,...) (lrcn.jl:185,230)."""
         return self.h.get_model()
+
+    # ---- checkpoint (lrcn.jl:88-93 load, :183-186 / :228-231 save; sidecar format of include/lrcn_b200.h)
+    def save(self, path, vocab=None, with_adam=True):
+        """save(file,"model",model,"vocab",vocab): weights (+ Adam m, v, t) and the vocab Dict in one sidecar file."""
+        self.h.checkpoint_save(path, with_adam, vocab_to_bytes(vocab) if vocab else b"")
+
+    def load(self, path):
+        """load(file): restores the weights (and the optimizer state when the file has it); returns the vocab dict or None."""
+        _, aux = self.h.checkpoint_load(path)
+        return vocab_from_bytes(aux) if aux else None
 
     # ---- features (lrcn.jl:121-123)
     def load_features(self, feats: dict, split=0):
@@ -160,6 +171,71 @@ class LRCN:
             raise
         print(caption_text(hyps[0], index_to_char), file=out)
         return hyps[0]
+
+
+# ---- checkpoint sidecar: pure-host reader / writer of the library's format (no GPU needed; the Julia shim has the same pair)
+CKPT_MAGIC = b"LRCNB2CK"
+
+
+def vocab_to_bytes(vocab: dict) -> bytes:
+    """vocab Dict{String,Int} (lrcn.jl:98-118) as "word\tindex\n" lines, UTF-8, in index order."""
+    return "".join(f"{w}\t{i}\n" for w, i in sorted(vocab.items(), key=lambda kv: kv[1])).encode("utf-8")
+
+
+def vocab_from_bytes(b: bytes) -> dict:
+    out = {}
+    for line in b.decode("utf-8").split("\n"):
+        if line:
+            w, i = line.rsplit("\t", 1)
+            out[w] = int(i)
+    return out
+
+
+def write_checkpoint(path, model, dims, vocab=None, adam=None):
+    """model: 9 column-major float32 matrices; dims = (E, H1, H2, V); adam = (m[9], v[9], t) or None."""
+    aux = vocab_to_bytes(vocab) if vocab else b""
+    with open(path, "wb") as f:
+        f.write(CKPT_MAGIC)
+        f.write(struct.pack("<II4iqq", 1, 1 if adam else 0, *[int(d) for d in dims], int(adam[2]) if adam else 0, len(aux)))
+        sections = [model] + ([adam[0], adam[1]] if adam else [])
+        for mats in sections:
+            for w in mats:
+                w = np.asfortranarray(w, dtype=np.float32)
+                f.write(struct.pack("<qq", *w.shape))
+                f.write(w.tobytes(order="F"))
+        f.write(aux)
+
+
+def read_checkpoint(path):
+    """-> dict(dims, adam_t, model[9], m[9] | None, v[9] | None, vocab | None).  Validates magic, version and sizes."""
+    with open(path, "rb") as f:
+        if f.read(8) != CKPT_MAGIC:
+            raise ValueError(f"{path}: not an LRCNB2CK checkpoint")
+        version, flags, E, H1, H2, V, adam_t, aux_bytes = struct.unpack("<II4iqq", f.read(40))
+        if version != 1:
+            raise ValueError(f"{path}: unsupported checkpoint version {version}")
+        shapes = synth.param_shapes(E, [H1, H2], V)
+
+        def mats():
+            out = []
+            for k in range(9):
+                r, c = struct.unpack("<qq", f.read(16))
+                if (r, c) != shapes[k]:
+                    raise ValueError(f"{path}: matrix {k + 1} is {r}x{c}, expected {shapes[k]} (lrcn.jl:489-510)")
+                raw = f.read(4 * r * c)
+                if len(raw) != 4 * r * c:
+                    raise ValueError(f"{path}: truncated")
+                out.append(np.frombuffer(raw, dtype="<f4").reshape((r, c), order="F").copy(order="F"))
+            return out
+
+        model = mats()
+        m = v = None
+        if flags & 1:
+            m, v = mats(), mats()
+        aux = f.read(aux_bytes)
+        if len(aux) != aux_bytes:
+            raise ValueError(f"{path}: truncated")
+    return dict(dims=(E, H1, H2, V), adam_t=adam_t, model=model, m=m, v=v, vocab=vocab_from_bytes(aux) if aux else None)
 
 
 def caption_text(word_indices, index_to_char):

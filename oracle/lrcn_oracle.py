@@ -13,7 +13,10 @@ Knet.jl (+AutoGrad.jl; Julia-0.5-era syntax in lrcn.jl => Knet ~0.8.x).  The Kne
 primitives used by the path are therefore restated from their published semantics:
   logp(x,2)   : x - max_row(x) - log(sum_row(exp(x - max_row(x))))
   sigm(x)     : 1/(1+exp(-x))
-  dropout(x,p): identity at p=0 (parity is defined at p=0; Knet's RNG is not reproducible)
+  dropout(x,p): x .* (rand(size(x)) .> p) ./ (1-p); identity at p=0.  Knet's RNG stream is not reproducible, so the
+               oracle takes the two masks of every step (lrcn.jl:542,547) EXPLICITLY (`masks=`): tests hand it the
+               masks the CUDA path draws (dropout_masks() restates its counter hash) and compare at p=0.4, the
+               reference's only training setting (lrcn.jl:227)
   xavier      : uniform(+-sqrt(2/(rows+cols)))
   Adam/update!: m=b1*m+(1-b1)*g; v=b2*v+(1-b2)*g.*g; w-=lr*(m/(1-b1^t))./(sqrt(v/(1-b2^t))+eps)
   x[idx,:]    : row gather; adjoint = dense zeros + add-at-index (accumulates repeats)
@@ -153,9 +156,40 @@ def _cell_bwd(W, cache, dh, dc_next):
     return dW, db, dxh, dc_prev
 
 
-def lossgradient(param, state, input, sequence, rng):
+def drop_hash24(seed, site, idx):
+    """The CUDA path's counter-based dropout hash (csrc/kernels_simt.cu drop_hash24), restated: SplitMix64 finaliser of
+    (seed, site, element index) -> 24 random bits.  idx: uint64 array."""
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15) * (idx.astype(np.uint64) + np.uint64(1)) \
+            + np.uint64(0xD1B54A32D192ED03) * np.uint64(site + 1)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(40)).astype(np.uint32)
+
+
+def dropout_masks(pdrop, seed, T, B, E, C2, rank=0, dtype=np.float32):
+    """The two dropout masks of every decoder step as the CUDA path draws them, already scaled by 1/(1-p) like Knet's
+    dropout (lrcn.jl:542 on the word embedding, :547 on hcat(x*Wf, x_cnn)): (M0 [T][B][E], M1 [T][B][C2]).
+    Element index = (t*B + i)*width + column; keep iff hash24 >= uint32(p * 2^24); the rank is mixed into the seed so that
+    the shards of a data-parallel batch draw different masks."""
+    p32 = np.float32(pdrop)
+    thresh = np.uint32(int(float(p32) * 16777216.0))
+    keep = dtype(np.float32(1.0) / (np.float32(1.0) - p32))
+    with np.errstate(over="ignore"):
+        s = np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15) * np.uint64(rank)
+    out = []
+    for site, width in ((0, E), (1, C2)):
+        idx = np.arange(T * B * width, dtype=np.uint64)
+        m = np.where(drop_hash24(s, site, idx) >= thresh, keep, dtype(0)).astype(dtype)
+        out.append(m.reshape(T, B, width))
+    return out
+
+
+def lossgradient(param, state, input, sequence, rng, masks=None):
     """What `lossgradient = grad(loss)` (lrcn.jl:583) returns: d loss / d param[k] for all 9
-    tensors, hand-derived BPTT.  Also returns the loss.  h0/c0 constant."""
+    tensors, hand-derived BPTT.  Also returns the loss.  h0/c0 constant.
+    masks = (M0, M1): explicit, pre-scaled dropout masks of the two sites lrcn.jl:542,547 (None = pdrop 0)."""
     W1, b1, W2, b2, Wf, Wcnn, Wemb, Wout, bout = param
     dt = W1.dtype
     batch = input.shape[0]
@@ -168,11 +202,15 @@ def lossgradient(param, state, input, sequence, rng):
     v = input @ Wcnn
     caches = []
     total = 0.0
-    for u, y in zip(ins, tgt):
+    for t, (u, y) in enumerate(zip(ins, tgt)):
         e = Wemb[u, :]
+        if masks is not None:
+            e = e * masks[0][t]          # x = dropout(x_lstm, pdrop)            lrcn.jl:542
         h1, c1, k1 = _cell_fwd(W1, b1, e, h1, c1)
         q = h1 @ Wf
         z = np.hstack([q, v])
+        if masks is not None:
+            z = z * masks[1][t]          # x = dropout(hcat(x, x_cnn), pdrop)    lrcn.jl:547
         h2, c2, k2 = _cell_fwd(W2, b2, z, h2, c2)
         a = h2 @ Wout + bout
         lp = logp(a)
@@ -184,7 +222,8 @@ def lossgradient(param, state, input, sequence, rng):
     dh1r = np.zeros_like(h1); dc1 = np.zeros_like(c1)
     dh2r = np.zeros_like(h2); dc2 = np.zeros_like(c2)
     inv = dt.type(1.0 / n_tok) if dt == np.float32 else 1.0 / n_tok
-    for (u, y, k1, h1t, k2, h2t, lp) in reversed(caches):
+    for t in range(T - 1, -1, -1):
+        (u, y, k1, h1t, k2, h2t, lp) = caches[t]
         dA = np.exp(lp)
         dA[rows, y] -= dt.type(1)
         dA *= inv
@@ -193,6 +232,8 @@ def lossgradient(param, state, input, sequence, rng):
         dh2 = dA @ Wout.T + dh2r
         dW, db, dxh, dc2 = _cell_bwd(W2, k2, dh2, dc2)
         g[2] += dW; g[3] += db
+        if masks is not None:
+            dxh[:, :2 * C] *= masks[1][t]
         dq = dxh[:, :C]
         dv += dxh[:, C:2 * C]
         dh2r = dxh[:, 2 * C:]
@@ -201,6 +242,8 @@ def lossgradient(param, state, input, sequence, rng):
         dW, db, dxh, dc1 = _cell_bwd(W1, k1, dh1, dc1)
         g[0] += dW; g[1] += db
         de = dxh[:, :E]
+        if masks is not None:
+            de = de * masks[0][t]
         dh1r = dxh[:, E:]
         np.add.at(g[6], u, de)  # accumulates over repeated ids (bos row gets B contributions)
     g[5] = input.T @ dv

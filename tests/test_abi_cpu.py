@@ -15,8 +15,8 @@ from oracle import lrcn_oracle as O
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def header_symbols():
-    src = open(os.path.join(ROOT, "include", "lrcn_b200.h")).read()
+def header_symbols(name="lrcn_b200.h"):
+    src = open(os.path.join(ROOT, "include", name)).read()
     return sorted(set(re.findall(r"LRCN_API\s+[\w\s\*]+?\b(lrcn_\w+)\s*\(", src)))
 
 
@@ -27,14 +27,30 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/lrcn_b200.h but not exported"
     assert sorted(abi.SIGNATURES) == syms, "abi.py must bind exactly the header's symbols"
-    assert lib.lrcn_abi_version() == 1
+    assert lib.lrcn_abi_version() == abi.ABI_VERSION == 2
+
+
+def test_test_hooks_live_only_in_the_test_library():
+    hooks = header_symbols("lrcn_b200_testhooks.h")
+    assert hooks and all(s.startswith("lrcn_test_") for s in hooks)
+    assert sorted(abi.TEST_SIGNATURES) == hooks
+    tl = abi.load_test()
+    for s in hooks + header_symbols():
+        assert hasattr(tl, s), f"{s} missing from liblrcn_b200_test.so"
+    prod = abi.load()
+    for s in hooks:
+        assert not hasattr(prod, s), f"the product library exports the test hook {s}"
+    # the config struct mirrors lrcn_config field for field (v2: + n_gpus, device_ids[8])
+    assert [f[0] for f in abi.Config._fields_][-2:] == ["n_gpus", "device_ids"]
+    cfg = abi.default_config()
+    assert cfg.n_gpus == 1 and list(cfg.device_ids) == list(range(8))
 
 
 def test_julia_shim_binds_every_symbol():
     jl = open(os.path.join(ROOT, "julia", "lrcn_b200.jl")).read()
     for s in header_symbols():
-        if s.startswith("lrcn_test_") or s in ("lrcn_time_kernel", "lrcn_flush_l2", "lrcn_kernel_launches", "lrcn_get_trace"):
-            continue  # measurement / test hooks are not part of the reference-facing surface
+        if s in ("lrcn_time_kernel", "lrcn_flush_l2", "lrcn_kernel_launches", "lrcn_get_trace"):
+            continue  # measurement helpers are not part of the reference-facing surface
         assert f":{s}" in jl, f"julia/lrcn_b200.jl has no ccall for {s}"
 
 
@@ -61,6 +77,49 @@ def test_argument_validation_needs_no_gpu():
     with pytest.raises(abi.LrcnError) as ei:
         abi.Handle(abi.default_config(embed=750, precision=abi.PREC_BF16X3))
     assert ei.value.code == abi.ERR_ARG
+
+
+def test_config_validation_vocab_bound_and_group():
+    with pytest.raises(abi.LrcnError) as ei:
+        abi.Handle(abi.default_config(vocab=60000))
+    assert ei.value.code == abi.ERR_ARG and "shared-memory" in str(ei.value)
+    with pytest.raises(abi.LrcnError) as ei:
+        abi.Handle(abi.default_config(n_gpus=9))
+    assert ei.value.code == abi.ERR_ARG
+
+
+def test_checkpoint_sidecar_format_roundtrip(tmp_path):
+    # f-2: the sidecar that replaces save(file,"model",model,"vocab",vocab) (lrcn.jl:185,230) -- pure-host writer/reader
+    E, H1, H2, V = 8, 16, 24, 57
+    model = synth.initweights([H1, H2], V, E, seed=3)
+    vocab = {"~~": 1, "``": 2, "##": 3, "a": 4, "caf\u00e9": 5, "tab\tword": 6}
+    rs = np.random.RandomState(0)
+    m = [rs.standard_normal(w.shape).astype(np.float32) for w in model]
+    v = [np.abs(rs.standard_normal(w.shape)).astype(np.float32) for w in model]
+    p = str(tmp_path / "model.lrcnck")
+    host.write_checkpoint(p, model, (E, H1, H2, V), vocab=vocab, adam=(m, v, 41))
+    r = host.read_checkpoint(p)
+    assert r["dims"] == (E, H1, H2, V) and r["adam_t"] == 41 and r["vocab"] == vocab
+    for a, b in zip(model + m + v, r["model"] + r["m"] + r["v"]):
+        assert a.shape == b.shape and np.array_equal(a, b) and b.flags.f_contiguous
+    # header layout is the documented one (include/lrcn_b200.h): magic, version, flags, dims, adam_t, aux_bytes
+    raw = open(p, "rb").read()
+    assert raw[:8] == b"LRCNB2CK" and np.frombuffer(raw[8:16], "<u4").tolist() == [1, 1]
+    assert np.frombuffer(raw[16:32], "<i4").tolist() == [E, H1, H2, V]
+    assert np.frombuffer(raw[48:64], "<i8").tolist() == list(model[0].shape)
+    assert np.array_equal(np.frombuffer(raw[64:64 + 4 * model[0].size], "<f4"), model[0].ravel(order="F"))
+    # model-only file; truncated and foreign files fail loudly
+    host.write_checkpoint(p, model, (E, H1, H2, V))
+    r = host.read_checkpoint(p)
+    assert r["m"] is None and r["vocab"] is None and r["adam_t"] == 0
+    open(p, "wb").write(raw[:200])
+    with pytest.raises(ValueError):
+        host.read_checkpoint(p)
+    open(p, "wb").write(b"NOTACKPT" + raw[8:])
+    with pytest.raises(ValueError):
+        host.read_checkpoint(p)
+    jl = open(os.path.join(ROOT, "julia", "lrcn_b200.jl")).read()
+    assert "LRCNB2CK" in jl and "read_checkpoint" in jl
 
 
 def test_product_never_imports_oracle():

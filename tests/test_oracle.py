@@ -77,7 +77,7 @@ def test_shapes_match_weight_contract():
     assert all(w.flags.f_contiguous for w in synth.initweights([4, 4], 7, 4))
 
 
-def _torch_loss(params, X, seq, rng, B):
+def _torch_loss(params, X, seq, rng, B, masks=None):
     W1, b1, W2, b2, Wf, Wcnn, Wemb, Wout, bout = params
     ins, tgt = O._step_inputs_targets(seq, rng, B)
     H1 = b1.shape[1] // 4; H2 = b2.shape[1] // 4
@@ -93,10 +93,14 @@ def _torch_loss(params, X, seq, rng, B):
         c = c * f + i * g
         return o * torch.tanh(c), c
 
-    for u, y in zip(ins, tgt):
+    for t, (u, y) in enumerate(zip(ins, tgt)):
         e = Wemb[torch.from_numpy(u)]
+        if masks is not None:
+            e = e * torch.from_numpy(masks[0][t])      # dropout site lrcn.jl:542
         h1, c1 = cell(W1, b1, e, h1, c1)
         z = torch.cat([h1 @ Wf, v], 1)
+        if masks is not None:
+            z = z * torch.from_numpy(masks[1][t])      # dropout site lrcn.jl:547
         h2, c2 = cell(W2, b2, z, h2, c2)
         a = h2 @ Wout + bout
         lp = torch.log_softmax(a, 1)
@@ -118,6 +122,49 @@ def test_gradient_matches_torch_autograd_fp64():
     assert np.abs(g[6][O.BOS - 1]).sum() > 0
     untouched = sorted(set(range(11)) - {O.BOS - 1} - {int(t) - 1 for s in seq for t in s})
     assert np.abs(g[6][untouched]).sum() == 0
+
+
+def test_dropout_masked_gradient_matches_torch_autograd_fp64():
+    # the two dropout sites of lrcn.jl:542,547 with EXPLICIT masks (Knet: x .* mask ./ (1-p)): hand BPTT == autograd
+    m, X, seq, rng = tiny()
+    B, T, E, C2 = 3, 5, 4, 8
+    masks = O.dropout_masks(0.4, 12345, T, B, E, C2, dtype=np.float64)
+    assert masks[0].shape == (T, B, E) and masks[1].shape == (T, B, C2)
+    assert set(np.unique(masks[0])) <= {0.0, float(np.float32(1) / (np.float32(1) - np.float32(0.4)))}
+    g, L = O.lossgradient(m, O.initstate(m, B), X, seq, rng, masks=masks)
+    g0, L0 = O.lossgradient(m, O.initstate(m, B), X, seq, rng)
+    assert abs(L - L0) > 1e-6  # the masks do something
+    tp = [torch.tensor(np.ascontiguousarray(w), requires_grad=True) for w in m]
+    Lt = _torch_loss(tp, torch.tensor(X), seq, rng, B, masks=masks)
+    Lt.backward()
+    assert abs(float(Lt.detach()) - L) < 1e-12
+    for k in range(9):
+        np.testing.assert_allclose(g[k], tp[k].grad.numpy(), rtol=1e-9, atol=1e-14, err_msg=f"param {k + 1}")
+
+
+def test_dropout_hash_known_answers_and_keep_rate():
+    # drop_hash24 restates csrc/kernels_simt.cu: SplitMix64 finaliser of seed + G*(idx+1) + S*(site+1), top 24 bits
+    def scalar(seed, site, idx):
+        M = (1 << 64) - 1
+        z = (seed + 0x9E3779B97F4A7C15 * (idx + 1) + 0xD1B54A32D192ED03 * (site + 1)) & M
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+        z ^= z >> 31
+        return z >> 40
+    idx = np.array([0, 1, 77, 2 ** 33 + 5], dtype=np.uint64)
+    for seed, site in ((0, 0), (7, 1), (2 ** 63 + 11, 0)):
+        got = O.drop_hash24(seed, site, idx)
+        assert got.tolist() == [scalar(seed, site, int(i)) for i in idx]
+    # empirical keep rate of a big mask: Bernoulli(0.6) within 4 sigma; survivors carry exactly 1/(1-p) in fp32
+    M0, M1 = O.dropout_masks(0.4, 99, 13, 64, 128, 96)
+    for M in (M0, M1):
+        n = M.size
+        rate = float((M > 0).mean())
+        assert abs(rate - 0.6) < 4 * np.sqrt(0.24 / n)
+        assert np.unique(M).tolist() == [0.0, float(np.float32(1) / np.float32(0.6))]
+    # different rank / seed / site -> different masks
+    assert (O.dropout_masks(0.4, 99, 2, 4, 8, 8, rank=1)[0] != O.dropout_masks(0.4, 99, 2, 4, 8, 8, rank=0)[0]).any()
+    assert (O.dropout_masks(0.4, 98, 2, 4, 8, 8)[0] != O.dropout_masks(0.4, 99, 2, 4, 8, 8)[0]).any()
 
 
 def test_gradient_finite_difference_fp64():
