@@ -183,24 +183,41 @@ void gather_features(cudaStream_t s, const float* table, const int* rows, int B,
   count_launch();
 }
 
-__global__ void gather_embed_kernel(const float* __restrict__ W, const int* __restrict__ tok, int R, int E, int ldo,
-                                    float* __restrict__ out, const StepScalars* __restrict__ sc, int train,
-                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+// K1 (north_star): vectorised, coalesced word-embedding gather.  One warp per output row: 128-bit loads of the [V][E]
+// row-major table (a word vector is one contiguous row), 128-bit fp32 stores and packed 64-bit bf16x4 hi / lo stores; the
+// dropout mask of lrcn.jl:542 is applied on the fly.  Scalar tail / unaligned pitches fall back to 32-bit accesses.
+__global__ void __launch_bounds__(256) gather_embed_kernel(const float* __restrict__ W, const int* __restrict__ tok, int R, int E, int ldo,
+                                                           float* __restrict__ out, const StepScalars* __restrict__ sc, int train,
+                                                           __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   pdl_wait();  // PDL: launched while the previous kernel drains (kernels.cuh)
   pdl_trigger();
-  int r = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
   const float* src = W + (size_t)tok[r] * E;
   float* dst = out + (size_t)r * ldo;
-  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+  const bool drop = train && sc->drop_thresh != 0;
+  const bool vec = ((E | ldo) & 3) == 0;  // rows of W, out and the shadows are then 16 B (8 B for bf16) aligned
+  const int E4 = vec ? (E >> 2) : 0;
+  for (int q = lane; q < E4; q += 32) {
+    float4 x = __ldg(reinterpret_cast<const float4*>(src) + q);
+    if (drop) {
+      const uint64_t idx = (uint64_t)r * E + 4 * q;
+      x.x *= drop_scale(sc, 0, idx); x.y *= drop_scale(sc, 0, idx + 1); x.z *= drop_scale(sc, 0, idx + 2); x.w *= drop_scale(sc, 0, idx + 3);
+    }
+    reinterpret_cast<float4*>(dst)[q] = x;
+    if (hi) store_split4(hi, lo, (size_t)r * ldo + 4 * q, x);
+  }
+  for (int e = 4 * E4 + lane; e < E; e += 32) {
     float v = __ldg(src + e);
-    if (train) v *= drop_scale(sc, 0, (uint64_t)r * E + e);
+    if (drop) v *= drop_scale(sc, 0, (uint64_t)r * E + e);
     dst[e] = v;
     if (hi) { __nv_bfloat16 h, l; split_one(v, h, l); hi[(size_t)r * ldo + e] = h; lo[(size_t)r * ldo + e] = l; }
   }
 }
 void gather_embed(cudaStream_t s, const float* WembT, const int* tok, int R, int E, float* out, const StepScalars* sc,
                   bool train, __nv_bfloat16* hi, __nv_bfloat16* lo, int ldo) {
-  launch_pdl<2>(gather_embed_kernel, dim3(R), dim3(128), 0, s, WembT, tok, R, E, ldo > 0 ? ldo : E, out, sc, train ? 1 : 0, hi, lo);
+  launch_pdl<2>(gather_embed_kernel, dim3((R + 7) / 8), dim3(256), 0, s, WembT, tok, R, E, ldo > 0 ? ldo : E, out, sc, train ? 1 : 0, hi, lo);
   count_launch();
 }
 
@@ -522,6 +539,9 @@ softmax_ce_fused_kernel(const float* __restrict__ logits, int ld, int V, int R, 
     if (q < ld4) *reinterpret_cast<float4*>(colpart + (size_t)blockIdx.x * ld + 4 * q) = *reinterpret_cast<float4*>(colacc + 4 * q);
   }
   if (total_out) {  // deterministic fp64 total of the row log-probs by the last CTA (as in softmax_ce_kernel)
+    // rowlp[r] is written by whichever thread owns the target column: every thread's stores must be ordered before thread 0's
+    // release (fence + atomic) below, or the last CTA may sum a stale row log-prob
+    __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
       const unsigned int prev = atomicAdd(done_ctr, 1u);

@@ -1270,6 +1270,16 @@ static int s_time_kernel(lrcn_handle* h, const char* name, int reps, float* avg_
         gemm(h, true, true, R, 4 * h->H1, h->E, WS(h, o.Eall), h->E, Wp(h, 1), h->E + h->H1, WS(h, o.acts1), 4 * h->H1, false, Wp(h, 2));
         flops = 2.0 * R * 4 * h->H1 * h->E;
         bytes = 4.0 * ((double)R * h->E + 4.0 * h->H1 * h->E + (double)R * 4 * h->H1);
+      } else if (!strcmp(name, "lstm_bwd") || !strcmp(name, "lstm_fwd")) {
+        // the layer-2 sequence kernel of the last step shape, alone: T-1 dependent recurrent steps (latency bound).  The buffers
+        // hold whatever the last step left (timing is data independent); the grid-barrier counters must be zero on entry.
+        CK(cudaMemsetAsync(h->d_counters, 0, 256 * sizeof(unsigned int), h->stream));
+        CK(cudaEventRecord(h->ev0, h->stream));
+        const int H = h->H2;
+        if (!strcmp(name, "lstm_fwd")) lstm_layer_fwd(h, 2, T, B, WS(h, o.acts2), WS(h, o.h2), WS(h, o.c2));
+        else lstm_layer_bwd(h, 2, T, B, WS(h, o.acts2), WS(h, o.c2), WS(h, o.dh2), WS(h, o.dhrec2), WS(h, o.dc2), Gp(h, 4));
+        flops = 2.0 * B * 4.0 * H * H * (T - 1);
+        bytes = 0;
       } else if (!strcmp(name, "gather")) {
         gather_embed(h->stream, Wp(h, 7), h->d_tok_in, R, h->E, WS(h, o.Eall), h->d_sc, false);
         bytes = 2.0 * 4.0 * R * h->E;

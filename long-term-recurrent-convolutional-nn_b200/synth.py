@@ -82,6 +82,34 @@ def initweights(hidden, vocab: int, embed: int, seed: int = 1, dtype=np.float32)
     return model
 
 
+def eos_timed_model(hidden, vocab: int, embed: int, seed: int = 7, scale: float = 6.0, n_counters: int = 32,
+                    w_eos: float = 0.12, g_bias: float = 0.12, v_scale: float = 0.012):
+    """A synthetic model whose beam-search decodes END like real captions do ("bias bout[eos] or train").
+
+    Random (untrained) weights never make eos the best continuation, so every decode would run the full nword+1 steps.
+    Here `n_counters` units of layer 2 are turned into slow integrators (forget ~ 1, a steady positive change whose size
+    depends on the image through the x_cnn half of the layer-2 input, no other inputs) and feed the eos logit, which
+    therefore grows step by step and overtakes the other words after an image-dependent number of steps.  With the
+    defaults at E = H = 512, V = 10000 (BASELINE configs[2]) beam-3 decode lengths spread over 2..32 tokens with a mean
+    near the ~10.4 steps of COCO captions.  Everything else is initweights() scaled by `scale`."""
+    h1, h2 = int(hidden[0]), int(hidden[1])
+    c = (h2 + 1) // 2
+    model = initweights(hidden, vocab, embed, seed=seed)
+    model = [w * np.float32(scale) if w.shape[0] > 1 else w for w in model]
+    W2, b2, Wout = model[2], model[3], model[7]
+    u = np.arange(n_counters)
+    for g in range(4):
+        W2[:, g * h2 + u] = 0                      # counters see no q, no recurrent input ...
+    b2[0, u] = 6.0                                 # forget ~ 1: the cell integrates
+    b2[0, h2 + u] = 0.0                            # ingate = 0.5
+    b2[0, 2 * h2 + u] = 3.0                        # outgate ~ 0.95
+    b2[0, 3 * h2 + u] = g_bias                     # steady positive change
+    col = (2.0 * uniform01(seed * 16 + 11, c) - 1.0) * 1.7 * v_scale
+    W2[c:2 * c, 3 * h2:3 * h2 + n_counters] = col.astype(np.float32)[:, None]   # ... but the image (x_cnn) sets their rate
+    Wout[u, EOS - 1] = w_eos                       # eos logit grows with the counters
+    return model
+
+
 def features(n_img: int, seed: int = 2) -> np.ndarray:
     """n_img x 4096 fp32, post-ReLU-like and L1-normalised like the reference's `featsn`
     (lrcn.jl:597 `input/sum(input)`). Row-major: one image's 4096 floats are contiguous."""

@@ -31,10 +31,10 @@ def make_case(E, H1, H2, V, B, l, n_img=32, scale=3.0, fscale=50.0, seed=1, zipf
     return model, feats, ids, img, tok, X
 
 
-def open_handle(E, H1, H2, V, B, l, prec, gen_rows=64, graphs=1):
+def open_handle(E, H1, H2, V, B, l, prec, gen_rows=64, graphs=1, hooks=False):
     cfg = abi.default_config(embed=E, hidden1=H1, hidden2=H2, vocab=V, max_batch=B, max_len=max(l, 1), max_gen_rows=gen_rows,
                              precision=prec, use_graphs=graphs)
-    return abi.Handle(cfg)
+    return abi.Handle(cfg, hooks=hooks)  # hooks=True: liblrcn_b200_test.so (product objects + kernel-level test hooks)
 
 
 # ----------------------------------------------------------------------------- kernels
@@ -48,7 +48,7 @@ def test_gemm_kernels(prec, aK, bK, M, N, K):
     bias = rs.standard_normal(N).astype(np.float32)
     C0 = rs.standard_normal((M, N)).astype(np.float32)
     ref = A.astype(np.float64) @ B.astype(np.float64)
-    with open_handle(64, 64, 64, 100, 4, 2, prec, 4) as h:
+    with open_handle(64, 64, 64, 100, 4, 2, prec, 4, hooks=True) as h:
         out = h.test_gemm(prec, aK, bK, A if aK else np.ascontiguousarray(A.T), np.ascontiguousarray(B.T) if bK else B)
         assert relerr(out, ref) < 2e-5
         out = h.test_gemm(prec, aK, bK, A if aK else np.ascontiguousarray(A.T), np.ascontiguousarray(B.T) if bK else B, bias, C0)
@@ -70,7 +70,7 @@ def test_gemm_pair_kernel_and_streamk(aK, bK, M, N, K):
     ref = A.astype(np.float64) @ B.astype(np.float64)
     Ain = A if aK else np.ascontiguousarray(A.T)
     Bin = np.ascontiguousarray(B.T) if bK else B
-    with open_handle(64, 64, 64, 100, 4, 2, 1, 4) as h:
+    with open_handle(64, 64, 64, 100, 4, 2, 1, 4, hooks=True) as h:
         assert relerr(h.test_gemm(1, aK, bK, Ain, Bin), ref) < 2e-5
         assert relerr(h.test_gemm(1, aK, bK, Ain, Bin, bias, None), ref + bias) < 2e-5
         assert relerr(h.test_gemm(1, aK, bK, Ain, Bin, bias, C0), ref + bias + C0) < 2e-5
@@ -102,7 +102,7 @@ def test_beam_selection_bit_exact_given_identical_probs():
         probs[4] = probs[3]                                                  # exact ties across beams
         parent = rs.uniform(0.1, 1, n_img * K).astype(np.float32)
         parent[4] = parent[3]
-        with open_handle(64, 64, 64, 100, 4, 2, abi.PREC_FP32) as h:
+        with open_handle(64, 64, 64, 100, 4, 2, abi.PREC_FP32, hooks=True) as h:
             tok, par, sc = h.test_beam_select(probs, parent, n_img, K, first)
         for img in range(n_img):
             cands = []
@@ -234,24 +234,117 @@ def test_adam_kernel_exact_on_given_gradient():
 
 
 @pytest.mark.parametrize("prec", PRECS)
-def test_dropout_is_seeded_and_unbiased(prec):
-    E, H1, H2, V, B, l = 64, 64, 64, 300, 16, 5
-    model, feats, ids, img, tok, X = make_case(E, H1, H2, V, B, l)
-    with open_handle(E, H1, H2, V, B, l, prec) as h:
+@pytest.mark.parametrize("case", [dict(E=64, H1=64, H2=64, V=300, B=16, l=5), dict(E=128, H1=192, H2=128, V=1111, B=24, l=11, zipf=True),
+                                  dict(E=64, H1=512, H2=512, V=300, B=80, l=7, scale=1.5)])
+def test_dropout_matches_oracle_with_the_same_masks(prec, case):
+    """The reference trains at pdrop = 0.4 only (lrcn.jl:227; sites lrcn.jl:542,547).  Knet's RNG is not reproducible, so the
+    oracle is handed the masks the CUDA path draws (its counter hash restated in oracle.dropout_masks): loss and the nine
+    gradients must agree to 1e-4 like at p = 0; plus seed determinism, the Bernoulli keep rate and the 1/(1-p) scale."""
+    c = dict(case)
+    zipf = c.pop("zipf", False)
+    model, feats, ids, img, tok, X = make_case(**c, zipf=zipf)
+    E, H2, B, l = c["E"], c["H2"], c["B"], c["l"]
+    T, p, seed = l + 1, 0.4, 20240611
+    masks = O.dropout_masks(p, seed, T, B, E, H2)
+    for M in masks:  # empirical keep rate (Bernoulli(1-p) within 4 sigma) and Knet's survivor scale 1/(1-p)
+        assert abs(float((M > 0).mean()) - (1 - p)) < 4 * np.sqrt(p * (1 - p) / M.size)
+        assert np.unique(M).tolist() == [0.0, float(np.float32(1) / (np.float32(1) - np.float32(p)))]
+    g_ref, L_ref = O.lossgradient(model, O.initstate(model, B), X, list(tok), range(0, l), masks=masks)
+    g0_ref, L0_ref = O.lossgradient(model, O.initstate(model, B), X, list(tok), range(0, l))
+    assert abs(L_ref - L0_ref) > 1e-4 * abs(L0_ref)
+    with open_handle(c["E"], c["H1"], c["H2"], c["V"], B, l, prec) as h:
         h.set_model(model)
         h.load_features(0, ids, feats)
-        L0 = h.grad(0, img, tok, 0.0, 1)
-        a = h.grad(0, img, tok, 0.4, 1)
-        ga = h.get_grad(1)
-        b = h.grad(0, img, tok, 0.4, 1)
-        gb = h.get_grad(1)
-        c = h.grad(0, img, tok, 0.4, 2)
-        # same seed -> same masks in forward and backward (split-K atomics only reorder fp32 sums)
-        assert abs(a - b) < 1e-6 * abs(a) and relerr(ga, gb) < 1e-5
-        assert abs(a - c) > 1e-5 * abs(a) and abs(a - L0) > 1e-6 * abs(a)
-        assert np.isfinite(ga).all()
+        for rep in range(2):  # second call replays the CUDA graph: the seed travels in the step scalars, not in the graph
+            L = h.grad(0, img, tok, p, seed)
+            assert abs(L - L_ref) < RTOL * abs(L_ref), (L, L_ref, L0_ref)
+            for k in range(1, 10):
+                assert relerr(h.get_grad(k), g_ref[k - 1]) < RTOL, f"gradient of param {k} at pdrop {p} (rep {rep})"
+        other = h.grad(0, img, tok, p, seed + 1)
+        assert abs(other - L) > 1e-6 * abs(L)          # another seed draws other masks
+        assert abs(h.grad(0, img, tok, 0.0, seed) - L0_ref) < RTOL * abs(L0_ref)  # p = 0 is the identity
+        # a train step at p = 0.4 is the oracle's Adam step on the masked gradient
+        ref = [w.copy() for w in model]
+        O.update(ref, g_ref, O.initparams(ref))
+        Lt = h.train_step(0, img, tok, p, seed)
+        assert abs(Lt - L_ref) < RTOL * abs(L_ref)
+        for k in (1, 3, 7, 8):
+            d_ref = ref[k - 1] - model[k - 1]
+            assert relerr(h.get_param(k) - model[k - 1], d_ref) < 5e-3, f"Adam update of param {k}"
         with pytest.raises(abi.LrcnError):
             h.grad(0, img, tok, 1.0, 1)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_small_batch_then_large_batch_on_one_handle(prec):
+    """average_loss runs B = 10 (lrcn.jl:260-269) on the handle that trains at a larger batch: slot t of the small call lands
+    inside slot 0 (= h_0 = c_0 = 0, lrcn.jl:512-526) of the next larger one, which must therefore be re-zeroed every step."""
+    E, H1, H2, V, l = 64, 128, 128, 300, 6
+    model, feats, ids, img, tok, X = make_case(E, H1, H2, V, 48, l)
+    for graphs in (1, 0):
+        with open_handle(E, H1, H2, V, 48, l, prec, graphs=graphs) as h:
+            h.set_model(model)
+            h.load_features(0, ids, feats)
+            for B in (10, 48, 7, 48):
+                g_ref, L_ref = O.lossgradient(model, O.initstate(model, B), X[:B], list(tok[:, :B]), range(0, l))
+                s, n = h.loss(0, img[:B], np.ascontiguousarray(tok[:, :B]))
+                assert abs(-s / n - L_ref) < RTOL * abs(L_ref), (B, graphs)
+                L = h.grad(0, img[:B], np.ascontiguousarray(tok[:, :B]))
+                assert abs(L - L_ref) < RTOL * abs(L_ref), (B, graphs)
+                for k in range(1, 10):
+                    assert relerr(h.get_grad(k), g_ref[k - 1]) < RTOL, f"B={B} graphs={graphs} param {k}"
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_staged_train_steps_match_host_buffer_steps_and_oracle(prec):
+    """lrcn_train_step_staged (the call bench.py's `value` is timed on) == lrcn_train_step == the oracle, including
+    back-to-back un-synchronised calls on slots of different lengths (the step scalars travel through a pinned ring)."""
+    E, H1, H2, V, B = 64, 64, 64, 300, 8
+    model, feats, ids, _, _, _ = make_case(E, H1, H2, V, B, 5)
+    batches = []
+    for s_, l in enumerate((5, 3, 7, 5)):
+        img = ids[synth.image_ids(B, len(ids), seed=50 + s_) - 1]
+        batches.append((img, synth.tokens(l, B, V, seed=60 + s_), l))
+    ref = [w.copy() for w in model]
+    opt = O.initparams(ref)
+    with open_handle(E, H1, H2, V, B, 8, prec) as h, open_handle(E, H1, H2, V, B, 8, prec) as h2:
+        for x in (h, h2):
+            x.set_model(model)
+            x.load_features(0, ids, feats)
+        for s_, (img, tok, l) in enumerate(batches):
+            h.stage_batch(s_, 0, img, tok)
+        losses = []
+        for rep in range(2):
+            for s_, (img, tok, l) in enumerate(batches):
+                Xb = feats[(img - 100) // 7 - 1]
+                L_ref = O.train_step(ref, opt, Xb, list(tok), range(0, l))
+                if rep == 0:
+                    L = h.train_step_staged(s_, 0.0, 0, want_loss=True)
+                    assert abs(L - L_ref) < RTOL * abs(L_ref), (s_, L, L_ref)
+                else:
+                    h.train_step_staged(s_, 0.0, 0)  # no D2H, no synchronisation between the four steps
+                L2 = h2.train_step(0, img, tok)
+                losses.append((L_ref, L2))
+                assert abs(L2 - L_ref) < 2 * RTOL * abs(L_ref)
+        h.sync()
+        assert h.get_adam_step() == h2.get_adam_step() == 8
+        for k in range(1, 10):
+            a, b = h.get_param(k), h2.get_param(k)
+            assert relerr(a - model[k - 1], b - model[k - 1]) < 1e-3, f"staged vs host-buffer steps, param {k}"
+            assert relerr(a - model[k - 1], ref[k - 1] - model[k - 1]) < 2e-2, f"staged steps vs oracle, param {k}"
+
+
+def test_sticky_error_state_and_adam_update_guard():
+    with open_handle(16, 16, 16, 40, 4, 3, abi.PREC_FP32) as h:
+        h.load_features(0, np.arange(1, 9), synth.features(8))
+        tok = synth.tokens(3, 4, 40)
+        h.grad(0, np.arange(1, 5), tok)
+        h.adam_update()  # single GPU: fine
+        with pytest.raises(abi.LrcnError) as ei:   # argument errors are NOT sticky
+            h.loss(0, np.array([1, 2, 3, 999]), tok)
+        assert ei.value.code == abi.ERR_MISSING
+        s, n = h.loss(0, np.arange(1, 5), tok)
+        assert n == 16 and np.isfinite(s)
 
 
 def test_errors_are_loud():
