@@ -1,0 +1,23 @@
+#!/bin/bash
+# Round-2 GPU-box visit (1 GPU): parity tests, smoke, bench, ncu launch list + full captures of the LSTM sequence kernels.
+mkdir -p gpurun_out
+nvidia-smi > gpurun_out/nvidia_smi.txt 2>&1
+if [ -z "$SKIP_TESTS" ]; then
+  echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -q -x -p no:cacheprovider --durations=15 > gpurun_out/r02_pytest.log 2>&1; tail -25 gpurun_out/r02_pytest.log
+  echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke.log 2>&1; tail -3 gpurun_out/r02_smoke.log
+fi
+if [ -z "$SKIP_BENCH" ]; then
+  echo "== bench"; timeout 900 python bench.py --steps ${STEPS:-100} --warmup 5 > gpurun_out/r02_bench.log 2>&1; tail -c 6000 gpurun_out/r02_bench.log
+fi
+if [ -z "$SKIP_NCU" ]; then
+  echo "== ncu launch list"
+  PROFILE_STEP=1 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_step_launches.csv \
+      python tools/prof_kernels.py none > gpurun_out/r02_ncu_step.log 2>&1
+  python tools/summarize_launches.py gpurun_out/r02_step_launches.csv > gpurun_out/r02_step_launches.md 2>&1; cat gpurun_out/r02_step_launches.md
+  echo "== ncu full: LSTM sequence kernels"
+  timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"lstm_.*seq" -c 4 \
+      -o gpurun_out/r02_prof_lstm -f python tools/prof_kernels.py lstm_fwd lstm_bwd > gpurun_out/r02_ncu_lstm.log 2>&1
+  tail -5 gpurun_out/r02_ncu_lstm.log
+  ncu -i gpurun_out/r02_prof_lstm.ncu-rep --page raw --csv > gpurun_out/r02_prof_lstm_raw.csv 2>/dev/null
+  ls -la gpurun_out/r02_* | head
+fi

@@ -24,7 +24,7 @@ def one(prec, aK, bK, M, N, K, beta, bias):
     if beta:
         ref += C0
     cfg = abi.default_config(embed=64, hidden1=64, hidden2=64, vocab=100, max_batch=4, max_len=2, max_gen_rows=4, precision=prec)
-    with abi.Handle(cfg) as h:
+    with abi.Handle(cfg, hooks=True) as h:
         out = h.test_gemm(prec, aK, bK, A if aK else np.ascontiguousarray(A.T), np.ascontiguousarray(B.T) if bK else B, bvec, C0)
     err = np.linalg.norm(out - ref) / np.linalg.norm(ref)
     mx = np.abs(out - ref).max()

@@ -28,7 +28,7 @@ if __name__ == "__main__":
     only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
     dbgs = [int(sys.argv[sys.argv.index("--dbg") + 1])] if "--dbg" in sys.argv else [0, 1, 2, 4, 3, 6]
     cfg = abi.default_config(embed=64, hidden1=64, hidden2=64, vocab=100, max_batch=4, max_len=2, max_gen_rows=4, precision=1)
-    with abi.Handle(cfg) as h:
+    with abi.Handle(cfg, hooks=True) as h:
         for (name, aK, bK, M, N, K, sh) in SHAPES:
             if (only is None and name.startswith("square")) or (only is not None and not name.startswith(only)):
                 continue

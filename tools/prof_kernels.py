@@ -22,19 +22,20 @@ l = 12
 img = synth.image_ids(w["B"], 1024)
 tok = synth.tokens(l, w["B"], w["V"], zipf=True)
 h.stage_batch(0, 0, img, tok)
+PDROP = float(os.environ.get("PDROP", "0.4"))  # lrcn.jl:227
 for i in range(2):
-    h.train_step_staged(0, 0.0, i)
+    h.train_step_staged(0, PDROP, i)
 h.sync()
 cuda = ctypes.CDLL("libcuda.so.1")
 cuda.cuProfilerStart()
-names = sys.argv[1:] or ["vocab_gemm", "gate_gemm", "adam", "softmax_ce", "gather"]
+names = sys.argv[1:] or ["vocab_gemm", "gate_gemm", "adam", "softmax_ce", "gather", "lstm_fwd", "lstm_bwd"]
 for nm in names:
     if nm == "none":
         continue
     ms, by, fl = h.time_kernel(nm, 1)
     print(nm, "ms", ms, "GB/s", by / ms / 1e6, "TFLOP/s", fl / ms / 1e9, flush=True)
 if os.environ.get("PROFILE_STEP"):
-    h.train_step_staged(0, 0.0, 5)
+    h.train_step_staged(0, PDROP, 5)
     h.sync()
 cuda.cuProfilerStop()
 h.close()
