@@ -251,7 +251,7 @@ def test_dropout_matches_oracle_with_the_same_masks(prec, case):
         assert np.unique(M).tolist() == [0.0, float(np.float32(1) / (np.float32(1) - np.float32(p)))]
     g_ref, L_ref = O.lossgradient(model, O.initstate(model, B), X, list(tok), range(0, l), masks=masks)
     g0_ref, L0_ref = O.lossgradient(model, O.initstate(model, B), X, list(tok), range(0, l))
-    assert abs(L_ref - L0_ref) > 1e-4 * abs(L0_ref)
+    assert abs(L_ref - L0_ref) > 1e-6 * abs(L0_ref)  # the masks do change the loss
     with open_handle(c["E"], c["H1"], c["H2"], c["V"], B, l, prec) as h:
         h.set_model(model)
         h.load_features(0, ids, feats)

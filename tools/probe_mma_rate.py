@@ -10,7 +10,7 @@ from lrcn_b200 import abi  # noqa: E402
 if __name__ == "__main__":
     cfg = abi.default_config(embed=64, hidden1=64, hidden2=64, vocab=100, max_batch=4, max_len=2, max_gen_rows=4, precision=1)
     with abi.Handle(cfg, hooks=True) as h:
-        for (M, N) in ((64, 128), (128, 64), (128, 128), (128, 256)):
+        for (M, N) in ((128, 16), (128, 32), (128, 64), (64, 32), (64, 128), (128, 128)):
             for (ce, iss) in ((0, 1), (4, 1), (8, 1), (16, 1), (0, 2), (4, 2)):
                 n = 512
                 h.test_mma_rate(M, N, n, ce, iss)
