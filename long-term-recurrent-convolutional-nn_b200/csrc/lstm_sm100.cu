@@ -1018,6 +1018,260 @@ lstm_fwd_seq2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   }
 }
 
+// ============================================================================================================
+// TRANSPOSED, MULTI-CHAIN forward sequence kernel ("seq4", round 2).
+//
+// What bounded seq2 (ncu, profiles/r02_lstm_ncu.md; tools/probe_mma_rate.py): a step is a dependent CHAIN -- grid barrier ->
+// TMA of the new h tile -> 32 MMAs -> cell epilogue -> release -- of ~6-7 us, during which each SM's tensor pipe is busy
+// for ~25 % of the time; a single thread issues one tcgen05.mma per ~69 clk whatever its shape, and M = 64 instructions
+// cost as much as M = 128 ones.  Batch rows are independent, so the fix is MORE, SHORTER chains per CTA:
+//   * roles swapped: the resident weight block {W_hi 64 gate rows; W_lo 64 gate rows} is the A operand (M = 128, K-major,
+//     SWIZZLE_128B -- the same smem image as before), the streamed activation chunk {h_hi 16 batch rows; h_lo 16 batch rows}
+//     is the B operand (N = 32).  One 128 x 32 x 16 MMA per k-step yields W_hi*h_hi, W_hi*h_lo, W_lo*h_hi (and an ignored
+//     W_lo*h_lo): accumulator lane = gate column (0-63: W_hi, 64-127: W_lo), column = batch row (0-15: h_hi, 16-31: h_lo);
+//   * a CTA's m-tile of 16*NCH rows is NCH <= 4 independent chains of 16 rows, each with its own grid-barrier counter, TMEM
+//     accumulator (32 columns) and hand-over buffer; a chain streams 32 KiB per step instead of 64 / 128 KiB, so its
+//     data-arrival phase shrinks accordingly while the other chains fill the SM;
+//   * TWO MMA-issuing warps (chains 0,2 and 1,3) lift the single-thread issue limit; two epilogue TEAMS of four warps (one
+//     per TMEM lane quadrant) finish two chains concurrently; ALL 128 threads of a team run the cell update (2 units x 1 row
+//     each) after a transposing hand-over through shared memory, with 64-byte-contiguous global accesses per (row, gate);
+//   * small batches get parallelism from the same mechanism: B <= 64 runs NCH = 1 (16-row m-tiles, 4x more CTAs).
+// Shared-memory budget per CTA: weights 128 KiB + 16-stage ring of 4 KiB chunks + 2 x 8.5 KiB hand-over buffers.
+// ============================================================================================================
+constexpr int T4_MAXCH = 4;                       // chains per CTA (upper bound)
+constexpr int T4_ROWS = 16;                       // batch rows per chain
+constexpr int T4_BHALF = T4_ROWS * LBK * 2;       // 2 KiB: {hi | lo} of one k-block of a chain
+constexpr int T4_BSTAGE = 2 * T4_BHALF;           // 4 KiB
+constexpr int T4_STAGES = 16;
+constexpr int T4_SLD = 17;                        // padded row (floats) of the transposing hand-over buffer [128 lanes][16 rows]
+constexpr int T4_SBYTES = 128 * T4_SLD * 4;       // 8704 B per team
+constexpr int T4_THREADS = 352;                   // warp 0 TMA, warps 1-2 MMA issue (warp 1 owns TMEM), warps 3-10 epilogue (2 teams x 4 quadrants)
+constexpr int T4_TEAM = 128;
+constexpr uint32_t T4_TMEM_COLS = 128;            // 4 accumulators x 32 columns
+
+struct Seq4Smem {
+  uint32_t res, ring, full0, empty0, wbar, tfull0, tempty0;
+  uint32_t* tmem_slot;
+  float* S;  // [2 teams][128][T4_SLD]
+};
+__device__ __forceinline__ Seq4Smem seq4_smem(uint8_t* smem_raw, int res_kb) {
+  Seq4Smem s;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* al = smem_raw + (base - smem_u32(smem_raw));
+  s.res = base;
+  s.ring = base + (uint32_t)res_kb * 2 * B_HALF;
+  uint8_t* after = al + (size_t)res_kb * 2 * B_HALF + T4_STAGES * T4_BSTAGE;
+  s.S = reinterpret_cast<float*>(after);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(after + 2 * T4_SBYTES);
+  s.full0 = smem_u32(bars);
+  s.empty0 = smem_u32(bars + T4_STAGES);
+  s.wbar = smem_u32(bars + 2 * T4_STAGES);
+  s.tfull0 = smem_u32(bars + 2 * T4_STAGES + 1);               // [4]
+  s.tempty0 = smem_u32(bars + 2 * T4_STAGES + 1 + T4_MAXCH);   // [4]
+  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * T4_STAGES + 1 + 2 * T4_MAXCH);
+  return s;
+}
+static int seq4_smem_bytes(int res_kb) { return res_kb * 2 * B_HALF + T4_STAGES * T4_BSTAGE + 2 * T4_SBYTES + 1024 + 512; }
+
+// named barriers of an epilogue team (128 threads): 2 + team
+__device__ __forceinline__ void team_bar_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(2 + team), "n"(T4_TEAM) : "memory"); }
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T4_THREADS, 1)
+lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const SeqParams p, const int nch) {
+  extern __shared__ uint8_t smem_raw[];
+  const Seq4Smem sm = seq4_smem(smem_raw, p.num_kb);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int nt = blockIdx.x, mt = blockIdx.y, m0 = mt * T4_ROWS * nch;
+  const int num_kb = p.num_kb, T = p.T, B = p.B, H = p.H;
+  const unsigned int ctas_per_mtile = gridDim.x;
+  unsigned int* ctr = p.counters + T4_MAXCH * mt;  // [chain]
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < T4_STAGES; s++) { mbar_init(sm.full0 + 8 * s, 1); mbar_init(sm.empty0 + 8 * s, CL); }
+    mbar_init(sm.wbar, 1);
+    for (int c = 0; c < T4_MAXCH; c++) { mbar_init(sm.tfull0 + 8 * c, 1); mbar_init(sm.tempty0 + 8 * c, 1); }
+    mbar_init_fence();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmA_lo); prefetch_tensormap(&tmB_hi); prefetch_tensormap(&tmB_lo);
+  }
+  if (warp == 1) tmem_alloc<T4_TMEM_COLS>(smem_u32(sm.tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *sm.tmem_slot;
+
+  if (warp == 0 && lane == 0) {  // resident weights before the dependency wait (see lstm_fwd_seq_kernel)
+    mbar_expect_tx(sm.wbar, (uint32_t)num_kb * 2 * B_HALF);
+    for (int kb = 0; kb < num_kb; kb++) {
+      tma_load_2d(sm.res + kb * 2 * B_HALF, &tmB_hi, sm.wbar, kb * LBK, nt * NT);
+      tma_load_2d(sm.res + kb * 2 * B_HALF + B_HALF, &tmB_lo, sm.wbar, kb * LBK, nt * NT);
+    }
+  }
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 0) {
+    // ===================== TMA producer: chunks in (t, chain, k-block) order =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int t = 1; t < T; t++) {
+        for (int c = 0; c < nch; c++) {
+          grid_wait(ctr + c, (unsigned int)t * ctas_per_mtile);  // h_{t-1} rows of this chain are complete in global memory
+          fence_proxy_async_global();
+          const int arow = t * B + m0 + T4_ROWS * c;  // slot t of hs = h_{t-1}
+          for (int kb = 0; kb < num_kb; kb++, it++) {
+            const int s = it % T4_STAGES;
+            mbar_wait(sm.empty0 + 8 * s, ((it / T4_STAGES) & 1) ^ 1);  // every CTA of the cluster has consumed this stage
+            const uint32_t full = sm.full0 + 8 * s;
+            mbar_expect_tx(full, T4_BSTAGE);
+            if ((uint32_t)(kb % CL) == rank) {  // k-block kb is fetched by one rank and multicast to the cluster
+              const uint32_t st = sm.ring + s * T4_BSTAGE;
+              tma_load_2d_mcast(st, &tmA_hi, full, kb * LBK, arow, (uint16_t)((1u << CL) - 1));
+              tma_load_2d_mcast(st + T4_BHALF, &tmA_lo, full, kb * LBK, arow, (uint16_t)((1u << CL) - 1));
+            }
+          }
+        }
+      }
+    }
+  } else if (warp <= 2) {
+    // ===================== MMA issuers: warp 1 -> chains 0, 2;  warp 2 -> chains 1, 3 =====================
+    if (lane == 0) {
+      const int iss = warp - 1;
+      const uint32_t idesc = idesc_bf16(128, 2 * T4_ROWS, false, false);
+      mbar_wait(sm.wbar, 0);
+      for (int t = 1; t < T; t++) {
+        for (int c = iss; c < nch; c += 2) {
+          if (t >= 2) { mbar_wait(sm.tempty0 + 8 * c, (t - 2) & 1); tc_fence_after(); }  // epilogue (t-1, c) has drained this accumulator
+          const uint32_t acc = tmem_base + (uint32_t)(2 * T4_ROWS * c);
+          int it = ((t - 1) * nch + c) * num_kb;
+          for (int kb = 0; kb < num_kb; kb++, it++) {
+            const int s = it % T4_STAGES;
+            mbar_wait(sm.full0 + 8 * s, (it / T4_STAGES) & 1);
+            tc_fence_after();
+            stacked_mma_kblock(acc, sm.res + kb * 2 * B_HALF, sm.ring + s * T4_BSTAGE, idesc, kb == 0);  // A = weights, B = h chunk
+            umma_commit_mcast(sm.empty0 + 8 * s, (uint16_t)((1u << CL) - 1));
+          }
+          umma_commit(sm.tfull0 + 8 * c);
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue teams: team 0 -> chains 0, 2;  team 1 -> chains 1, 3 =====================
+    const int ew = warp - 3, quad = warp & 3, team = ew >> 2;
+    const int tid = ((quad + 1) & 3) * 32 + lane;   // 0..127 inside the team (warps 3,4,5,6 have quadrants 3,0,1,2)
+    float* S = sm.S + (size_t)team * 128 * T4_SLD;
+    // cell ownership: row rr of the chain, units 2*up, 2*up+1 of the CTA's 16
+    const int rr = tid >> 3, up = tid & 7;
+    const int j = nt * (NT / 4) + 2 * up;
+    float creg[2][2];
+    float2 xg[2][4];
+    bool active[2];
+    int mrow[2];
+#pragma unroll
+    for (int sl = 0; sl < 2; sl++) {
+      const int c = team + 2 * sl;
+      mrow[sl] = m0 + T4_ROWS * c + rr;
+      active[sl] = c < nch && mrow[sl] < B && j < H;
+      creg[sl][0] = creg[sl][1] = 0.f;
+#pragma unroll
+      for (int g = 0; g < 4; g++) xg[sl][g] = make_float2(0.f, 0.f);
+      if (active[sl]) {
+        const float* g0 = p.acts + (size_t)mrow[sl] * 4 * H + j;
+#pragma unroll
+        for (int g = 0; g < 4; g++) xg[sl][g] = *reinterpret_cast<const float2*>(g0 + g * H);
+      }
+    }
+    for (int t = 0; t < T; t++) {
+#pragma unroll
+      for (int sl = 0; sl < 2; sl++) {
+        const int c = team + 2 * sl;
+        if (c >= nch) continue;  // uniform over the team
+        float a[4][2];  // [gate][unit] recurrent part of the pre-activations
+        if (t > 0) {
+          mbar_wait(sm.tfull0 + 8 * c, (t - 1) & 1);
+          tc_fence_after();
+          uint32_t v[32];
+          LRCN_TMEM_LD_32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * T4_ROWS * c), v);
+          tmem_ld_wait();
+          tc_fence_before();
+          // accumulator lane = 32*quad + lane: gate column (W_hi: 0-63 | W_lo: 64-127); columns 0-15: * h_hi, 16-31: * h_lo
+          float* dst = S + (size_t)(32 * quad + lane) * T4_SLD;
+          if (quad < 2) {
+#pragma unroll
+            for (int r = 0; r < T4_ROWS; r++) dst[r] = __uint_as_float(v[r]) + __uint_as_float(v[T4_ROWS + r]);
+          } else {
+#pragma unroll
+            for (int r = 0; r < T4_ROWS; r++) dst[r] = __uint_as_float(v[r]);
+          }
+          team_bar_sync(team);
+#pragma unroll
+          for (int e = 0; e < 2; e++)
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+              const int gl = 4 * (2 * up + e) + g;  // weight rows are unit-major: row u*4 + gate
+              a[g][e] = S[(size_t)gl * T4_SLD + rr] + S[(size_t)(64 + gl) * T4_SLD + rr];
+            }
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; g++) a[g][0] = a[g][1] = 0.f;
+        }
+        float gf[2], gi[2], go[2], gc[2], hn[2];
+        const size_t hnext = ((size_t)(t + 1) * B + mrow[sl]) * H + j;
+        if (active[sl]) {
+          const float xf[2] = {xg[sl][0].x, xg[sl][0].y}, xi[2] = {xg[sl][1].x, xg[sl][1].y};
+          const float xo[2] = {xg[sl][2].x, xg[sl][2].y}, xc[2] = {xg[sl][3].x, xg[sl][3].y};
+          __nv_bfloat16 hh[2], ll[2];
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            gf[e] = sigm_fast(xf[e] + a[0][e]);
+            gi[e] = sigm_fast(xi[e] + a[1][e]);
+            go[e] = sigm_fast(xo[e] + a[2][e]);
+            gc[e] = tanh_fast(xc[e] + a[3][e]);
+            creg[sl][e] = creg[sl][e] * gf[e] + gi[e] * gc[e];
+            hn[e] = go[e] * tanh_fast(creg[sl][e]);
+            split_bf16(hn[e], hh[e], ll[e]);
+          }
+          *reinterpret_cast<uint32_t*>(p.o_hi + hnext) = *reinterpret_cast<uint32_t*>(hh);
+          *reinterpret_cast<uint32_t*>(p.o_lo + hnext) = *reinterpret_cast<uint32_t*>(ll);
+        }
+        // every thread of the team is past its reads of S and its h stores: one thread frees the accumulator for the issuer
+        // and publishes h_t of this chain (bar.sync orders the team's stores before the gpu-scope release; the reading
+        // producers fence generic->async proxy after their acquire)
+        team_bar_sync(team);
+        if (tid == 0) {
+          if (t > 0) mbar_arrive(sm.tempty0 + 8 * c);
+          if (t + 1 < T) { fence_proxy_async_global(); grid_arrive(ctr + c); }
+        }
+        if (active[sl]) {  // off the critical path: what only later kernels read
+          float* grow = p.acts + ((size_t)t * B + mrow[sl]) * 4 * H + j;
+          *reinterpret_cast<float2*>(grow) = make_float2(gf[0], gf[1]);
+          *reinterpret_cast<float2*>(grow + H) = make_float2(gi[0], gi[1]);
+          *reinterpret_cast<float2*>(grow + 2 * H) = make_float2(go[0], go[1]);
+          *reinterpret_cast<float2*>(grow + 3 * H) = make_float2(gc[0], gc[1]);
+          *reinterpret_cast<float2*>(p.cs + hnext) = make_float2(creg[sl][0], creg[sl][1]);
+          *reinterpret_cast<float2*>(p.hs + hnext) = make_float2(hn[0], hn[1]);
+          if (t + 1 < T) {  // prefetch the next step's x-part
+            const float* gn = p.acts + ((size_t)(t + 1) * B + mrow[sl]) * 4 * H + j;
+#pragma unroll
+            for (int g = 0; g < 4; g++) xg[sl][g] = *reinterpret_cast<const float2*>(gn + g * H);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<T4_TMEM_COLS>(tmem_base);
+  }
+}
+
 // ---- backward: all T steps of one layer, t = T-1 .. 0.  grid = (n-tiles*CL, m-tiles); the CL CTAs of a cluster are the
 // K-slices of one 64x64 output tile; partials are exchanged through DSMEM with remote mbarrier arrives.
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(L_THREADS, 1)
@@ -1386,10 +1640,10 @@ bool lstm_bwd_step(cudaStream_t s, int B, int H, bool has_rec, const __nv_bfloat
 
 static int g_lstm_sms = 0;
 // Can the persistent kernels be used?  (weights must fit beside the ring; the whole grid must be co-resident)
-static bool seq_fits(const void* kernel, int res_kb, dim3 grid, int smem_bytes) {
+static bool seq_fits(const void* kernel, int res_kb, dim3 grid, int smem_bytes, int threads = L_THREADS) {
   if (res_kb > MAX_RES_KB) return false;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid; cfg.blockDim = dim3(L_THREADS); cfg.dynamicSmemBytes = smem_bytes;
+  cfg.gridDim = grid; cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem_bytes;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
@@ -1404,6 +1658,27 @@ bool lstm_fwd_seq(cudaStream_t s, int B, int H, int T, const __nv_bfloat16* wper
   *launched = false;
   const int num_kb = (H + LBK - 1) / LBK;
   const int nt = (H + F_NH - 1) / F_NH;
+  static const bool no_seq4 = getenv("LRCN_SEQ_V2") != nullptr || getenv("LRCN_SEQ_V1") != nullptr;  // round-1 kernels
+  if (!no_seq4 && T >= 2) {
+    // transposed multi-chain kernel: the fewest chains per CTA (= the most CTAs) whose grid is still co-resident
+    for (int nch = 1; nch <= T4_MAXCH; nch *= 2) {
+      const int rows = T4_ROWS * nch;
+      dim3 grid4((nt + CL - 1) / CL * CL, (B + rows - 1) / rows);
+      if (grid4.y * T4_MAXCH > 64) continue;  // one counter per (m-tile, chain)
+      if (!seq_fits((const void*)lstm_fwd_seq4_kernel, num_kb, grid4, seq4_smem_bytes(num_kb), T4_THREADS)) continue;
+      const int Hp = (H + 7) / 8 * 8, wrows = fwd_rows(H);
+      CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+      if (!get_tensor_map_bf16(&tb_hi, wperm_hi, H, wrows, Hp, F_NT) || !get_tensor_map_bf16(&tb_lo, wperm_lo, H, wrows, Hp, F_NT)) return false;
+      const uint64_t R = (uint64_t)(T + 1) * B;
+      if (!get_tensor_map_bf16(&ta_hi, hs_hi, H, R, H, T4_ROWS) || !get_tensor_map_bf16(&ta_lo, hs_lo, H, R, H, T4_ROWS)) return false;
+      SeqParams p{};
+      p.B = B; p.H = H; p.T = T; p.num_kb = num_kb; p.acts = acts; p.hs = hs; p.cs = cs; p.o_hi = hs_hi; p.o_lo = hs_lo; p.counters = counters;
+      launch_pdl(lstm_fwd_seq4_kernel, grid4, dim3(T4_THREADS), seq4_smem_bytes(num_kb), s, ta_hi, ta_lo, tb_hi, tb_lo, p, nch);
+      if (g_counter) g_counter->n++;
+      *launched = true;
+      return check_launch("lstm_fwd_seq4 launch");
+    }
+  }
   dim3 grid((nt + CL - 1) / CL * CL, (B + LM - 1) / LM);
   static const bool v1 = getenv("LRCN_SEQ_V1") != nullptr;  // the single-chain kernel (one 64-row tile per step)
   const bool two = !v1 && grid.y * 2 <= 64;                // seq2: two interleaved 32-row chains, one counter per half tile
@@ -1461,6 +1736,7 @@ bool init_lstm_sm100() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_fwd_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seq_smem_bytes(MAX_RES_KB, false));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_bwd_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seq_smem_bytes(MAX_RES_KB, true));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_fwd_seq2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seq2_smem_bytes(MAX_RES_KB));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_fwd_seq4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seq4_smem_bytes(MAX_RES_KB));
   if (e != cudaSuccess) { set_sm100_error((std::string("cudaFuncSetAttribute(lstm): ") + cudaGetErrorString(e)).c_str()); return false; }
   return true;
 }
