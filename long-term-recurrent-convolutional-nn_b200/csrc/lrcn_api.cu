@@ -282,7 +282,7 @@ static int create_impl(const lrcn_config* cfg, lrcn_handle* h) {
   CK(cudaMallocHost(&h->h_loss, 8));
   CK(cudaMalloc(&h->d_counters, 320 * sizeof(unsigned int)));  // [0,256): 4 LSTM launches x 64 (half-)tile barriers; [256,..): softmax
   CK(cudaMemset(h->d_counters, 0, 320 * sizeof(unsigned int)));
-  if (getenv("LRCN_SEQ_TRACE")) { CK(cudaMalloc(&h->d_trace, 64 * 8 * 8)); CK(cudaMemset(h->d_trace, 0, 64 * 8 * 8)); }
+  if (getenv("LRCN_SEQ_TRACE")) { CK(cudaMalloc(&h->d_trace, 64 * 32 * 8)); CK(cudaMemset(h->d_trace, 0, 64 * 32 * 8)); }
   CK(cudaMalloc(&h->g_last, G * 4)); CK(cudaMalloc(&h->g_ctok, G * 16 * 4)); CK(cudaMalloc(&h->g_stok, G * 4)); CK(cudaMalloc(&h->g_spar, G * 4));
   CK(cudaMalloc(&h->g_hista, G * ML * 4)); CK(cudaMalloc(&h->g_histb, G * ML * 4)); CK(cudaMalloc(&h->g_done, G * 4));
   CK(cudaMalloc(&h->g_ndone, 4)); CK(cudaMalloc(&h->g_olen, G * 4)); CK(cudaMalloc(&h->g_rows, G * 4)); CK(cudaMalloc(&h->g_otok, G * ML * 8));
@@ -1231,7 +1231,7 @@ static int s_kernel_launches(lrcn_handle* h, int64_t* n) {
   return LRCN_OK;
 }
 static int s_get_trace(lrcn_handle* h, uint64_t* out, int64_t n) {
-  if (!h || !out || n <= 0 || n > 512) return fail(LRCN_ERR_ARG, "bad argument");
+  if (!h || !out || n <= 0 || n > 2048) return fail(LRCN_ERR_ARG, "bad argument");
   if (!h->d_trace) return fail(LRCN_ERR_STATE, "create the handle with LRCN_SEQ_TRACE=1 in the environment");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaStreamSynchronize(h->stream));

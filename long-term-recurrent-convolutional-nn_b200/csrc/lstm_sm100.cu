@@ -1073,6 +1073,7 @@ __device__ __forceinline__ Seq4Smem seq4_smem(uint8_t* smem_raw, int res_kb) {
 }
 static int seq4_smem_bytes(int res_kb) { return res_kb * 2 * B_HALF + T4_STAGES * T4_BSTAGE + 2 * T4_SBYTES + 1024 + 512; }
 
+#define T4_TRACE(c, slot) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[((size_t)t * T4_MAXCH + (c)) * 8 + (slot)] = gtime(); } while (0)
 // named barriers of an epilogue team (128 threads): 2 + team
 __device__ __forceinline__ void team_bar_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(2 + team), "n"(T4_TEAM) : "memory"); }
 
@@ -1121,6 +1122,7 @@ lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       for (int t = 1; t < T; t++) {
         for (int c = 0; c < nch; c++) {
           grid_wait(ctr + c, (unsigned int)t * ctas_per_mtile);  // h_{t-1} rows of this chain are complete in global memory
+          T4_TRACE(c, 0);
           fence_proxy_async_global();
           const int arow = t * B + m0 + T4_ROWS * c;  // slot t of hs = h_{t-1}
           for (int kb = 0; kb < num_kb; kb++, it++) {
@@ -1134,6 +1136,7 @@ lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
               tma_load_2d_mcast(st + T4_BHALF, &tmA_lo, full, kb * LBK, arow, (uint16_t)((1u << CL) - 1));
             }
           }
+          T4_TRACE(c, 1);
         }
       }
     }
@@ -1151,11 +1154,13 @@ lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
           for (int kb = 0; kb < num_kb; kb++, it++) {
             const int s = it % T4_STAGES;
             mbar_wait(sm.full0 + 8 * s, (it / T4_STAGES) & 1);
+            if (kb == 0) T4_TRACE(c, 2); else if (kb == num_kb - 1) T4_TRACE(c, 3);
             tc_fence_after();
             stacked_mma_kblock(acc, sm.res + kb * 2 * B_HALF, sm.ring + s * T4_BSTAGE, idesc, kb == 0);  // A = weights, B = h chunk
             umma_commit_mcast(sm.empty0 + 8 * s, (uint16_t)((1u << CL) - 1));
           }
           umma_commit(sm.tfull0 + 8 * c);
+          T4_TRACE(c, 4);
         }
       }
     }
@@ -1193,6 +1198,7 @@ lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
         float a[4][2];  // [gate][unit] recurrent part of the pre-activations
         if (t > 0) {
           mbar_wait(sm.tfull0 + 8 * c, (t - 1) & 1);
+          if (tid == 0) T4_TRACE(c, 5);
           tc_fence_after();
           uint32_t v[32];
           LRCN_TMEM_LD_32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * T4_ROWS * c), v);
@@ -1243,8 +1249,10 @@ lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
         // producers fence generic->async proxy after their acquire)
         team_bar_sync(team);
         if (tid == 0) {
+          T4_TRACE(c, 6);
           if (t > 0) mbar_arrive(sm.tempty0 + 8 * c);
           if (t + 1 < T) { fence_proxy_async_global(); grid_arrive(ctr + c); }
+          T4_TRACE(c, 7);
         }
         if (active[sl]) {  // off the critical path: what only later kernels read
           float* grow = p.acts + ((size_t)t * B + mrow[sl]) * 4 * H + j;
@@ -1673,6 +1681,7 @@ bool lstm_fwd_seq(cudaStream_t s, int B, int H, int T, const __nv_bfloat16* wper
       if (!get_tensor_map_bf16(&ta_hi, hs_hi, H, R, H, T4_ROWS) || !get_tensor_map_bf16(&ta_lo, hs_lo, H, R, H, T4_ROWS)) return false;
       SeqParams p{};
       p.B = B; p.H = H; p.T = T; p.num_kb = num_kb; p.acts = acts; p.hs = hs; p.cs = cs; p.o_hi = hs_hi; p.o_lo = hs_lo; p.counters = counters;
+      p.trace = trace;
       launch_pdl(lstm_fwd_seq4_kernel, grid4, dim3(T4_THREADS), seq4_smem_bytes(num_kb), s, ta_hi, ta_lo, tb_hi, tb_lo, p, nch);
       if (g_counter) g_counter->n++;
       *launched = true;
