@@ -1045,7 +1045,8 @@ constexpr int T4_BSTAGE = 2 * T4_BHALF;           // 4 KiB
 constexpr int T4_STAGES = 16;
 constexpr int T4_SLD = 17;                        // padded row (floats) of the transposing hand-over buffer [128 lanes][16 rows]
 constexpr int T4_SBYTES = 128 * T4_SLD * 4;       // 8704 B per team
-constexpr int T4_THREADS = 352;                   // warp 0 TMA, warps 1-2 MMA issue (warp 1 owns TMEM), warps 3-10 epilogue (2 teams x 4 quadrants)
+constexpr int T4_ISSUERS = 4;                     // MMA-issuing warps: one per chain (a thread issues one tcgen05.mma per ~70-100 clk whatever its shape)
+constexpr int T4_THREADS = 32 * (1 + T4_ISSUERS + 8);  // warp 0 TMA, warps 1..4 MMA issue (warp 1 owns TMEM), 8 epilogue warps (2 teams x 4 quadrants)
 constexpr int T4_TEAM = 128;
 constexpr uint32_t T4_TMEM_COLS = 128;            // 4 accumulators x 32 columns
 
@@ -1140,14 +1141,14 @@ lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
         }
       }
     }
-  } else if (warp <= 2) {
-    // ===================== MMA issuers: warp 1 -> chains 0, 2;  warp 2 -> chains 1, 3 =====================
+  } else if (warp <= T4_ISSUERS) {
+    // ===================== MMA issuers: warp 1 + i -> chains i, i + T4_ISSUERS, ... =====================
     if (lane == 0) {
       const int iss = warp - 1;
       const uint32_t idesc = idesc_bf16(128, 2 * T4_ROWS, false, false);
       mbar_wait(sm.wbar, 0);
       for (int t = 1; t < T; t++) {
-        for (int c = iss; c < nch; c += 2) {
+        for (int c = iss; c < nch; c += T4_ISSUERS) {
           if (t >= 2) { mbar_wait(sm.tempty0 + 8 * c, (t - 2) & 1); tc_fence_after(); }  // epilogue (t-1, c) has drained this accumulator
           const uint32_t acc = tmem_base + (uint32_t)(2 * T4_ROWS * c);
           int it = ((t - 1) * nch + c) * num_kb;
@@ -1166,8 +1167,8 @@ lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
     }
   } else {
     // ===================== epilogue teams: team 0 -> chains 0, 2;  team 1 -> chains 1, 3 =====================
-    const int ew = warp - 3, quad = warp & 3, team = ew >> 2;
-    const int tid = ((quad + 1) & 3) * 32 + lane;   // 0..127 inside the team (warps 3,4,5,6 have quadrants 3,0,1,2)
+    const int ew = warp - 1 - T4_ISSUERS, quad = warp & 3, team = ew >> 2;
+    const int tid = (ew & 3) * 32 + lane;           // 0..127 inside the team (its four warps cover the four TMEM lane quadrants)
     float* S = sm.S + (size_t)team * 128 * T4_SLD;
     // cell ownership: row rr of the chain, units 2*up, 2*up+1 of the CTA's 16
     const int rr = tid >> 3, up = tid & 7;
