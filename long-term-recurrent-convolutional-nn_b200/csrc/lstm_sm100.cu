@@ -1019,70 +1019,90 @@ lstm_fwd_seq2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
 }
 
 // ============================================================================================================
-// TRANSPOSED, MULTI-CHAIN forward sequence kernel ("seq4", round 2).
+// TRANSPOSED, MULTI-CHAIN forward sequence kernel with the recurrent weights resident in TENSOR MEMORY ("seq4", round 2).
 //
-// What bounded seq2 (ncu, profiles/r02_lstm_ncu.md; tools/probe_mma_rate.py): a step is a dependent CHAIN -- grid barrier ->
-// TMA of the new h tile -> 32 MMAs -> cell epilogue -> release -- of ~6-7 us, during which each SM's tensor pipe is busy
-// for ~25 % of the time; a single thread issues one tcgen05.mma per ~69 clk whatever its shape, and M = 64 instructions
-// cost as much as M = 128 ones.  Batch rows are independent, so the fix is MORE, SHORTER chains per CTA:
-//   * roles swapped: the resident weight block {W_hi 64 gate rows; W_lo 64 gate rows} is the A operand (M = 128, K-major,
-//     SWIZZLE_128B -- the same smem image as before), the streamed activation chunk {h_hi 16 batch rows; h_lo 16 batch rows}
-//     is the B operand (N = 32).  One 128 x 32 x 16 MMA per k-step yields W_hi*h_hi, W_hi*h_lo, W_lo*h_hi (and an ignored
-//     W_lo*h_lo): accumulator lane = gate column (0-63: W_hi, 64-127: W_lo), column = batch row (0-15: h_hi, 16-31: h_lo);
-//   * a CTA's m-tile of 16*NCH rows is NCH <= 4 independent chains of 16 rows, each with its own grid-barrier counter, TMEM
-//     accumulator (32 columns) and hand-over buffer; a chain streams 32 KiB per step instead of 64 / 128 KiB, so its
-//     data-arrival phase shrinks accordingly while the other chains fill the SM;
-//   * TWO MMA-issuing warps (chains 0,2 and 1,3) lift the single-thread issue limit; two epilogue TEAMS of four warps (one
-//     per TMEM lane quadrant) finish two chains concurrently; ALL 128 threads of a team run the cell update (2 units x 1 row
-//     each) after a transposing hand-over through shared memory, with 64-byte-contiguous global accesses per (row, gate);
+// What bounded the round-1 kernels (ncu + globaltimer traces, profiles/r02_lstm.md; tools/probe_mma_rate.py):
+//   * a step is a dependent CHAIN -- grid barrier -> TMA of the new h tile -> 32 MMAs -> cell epilogue -> release -- of 6-7 us
+//     during which the SM's tensor pipe is busy a quarter of the time;
+//   * ONE thread issues a tcgen05.mma every ~69 clk whatever the instruction's shape (M = 64 costs as much as M = 128), and
+//     in situ every k-block costs ~290 ns of wait + 4 MMAs + commit: the issue loop, not the tensor pipe, sets the pace;
+//   * 128 KiB of resident weights leave ~80 KiB of shared memory: a ring that cannot hold a step's activations, whose
+//     stage-reuse dependencies serialise the TMA producer behind the MMA consumer.
+// Hence:
+//   * roles swapped: the weight block {W_hi 64 gate rows; W_lo 64 gate rows} is the A operand (M = 128) and lives in TMEM
+//     (tcgen05.mma A-from-TMEM form): 128 lanes x 256 columns hold K = 512 of bf16 pairs.  Shared memory holds NO weights,
+//     the MMAs read only the small B operand from it, and every chain's whole activation chunk has a fixed home;
+//   * the streamed chunk {h_hi 16 batch rows; h_lo 16 batch rows} is the B operand (N = 32): one 128 x 32 x 16 MMA per
+//     k-step yields W_hi*h_hi, W_hi*h_lo, W_lo*h_hi (and an ignored W_lo*h_lo); accumulator lane = gate column
+//     (0-63: W_hi, 64-127: W_lo), column = batch row (0-15: h_hi, 16-31: h_lo);
+//   * a CTA's m-tile of 16*NCH rows is NCH <= 4 independent chains of 16 rows, each with its own grid-barrier counter, its
+//     own TMA-producer warp, MMA-issuer warp, TMEM accumulator and chunk buffer -- four issue loops run in parallel and a
+//     chain streams 32 KiB per step instead of 64 / 128 KiB.  No stage ring and no "empty" barriers: chunk (t+1, c) may
+//     overwrite chunk (t, c) once chain c's grid barrier for step t+1 is open, because every CTA of the cluster (the
+//     multicast group) arrives on that barrier only after ITS MMAs of step t have completed;
+//   * two epilogue TEAMS of four warps (one per TMEM lane quadrant) finish two chains concurrently; all 128 threads of a
+//     team run the cell update (2 units x 1 row each) after a transposing hand-over through shared memory, with
+//     64-byte-contiguous global accesses per (row, gate);
 //   * small batches get parallelism from the same mechanism: B <= 64 runs NCH = 1 (16-row m-tiles, 4x more CTAs).
-// Shared-memory budget per CTA: weights 128 KiB + 16-stage ring of 4 KiB chunks + 2 x 8.5 KiB hand-over buffers.
 // ============================================================================================================
 constexpr int T4_MAXCH = 4;                       // chains per CTA (upper bound)
 constexpr int T4_ROWS = 16;                       // batch rows per chain
 constexpr int T4_BHALF = T4_ROWS * LBK * 2;       // 2 KiB: {hi | lo} of one k-block of a chain
 constexpr int T4_BSTAGE = 2 * T4_BHALF;           // 4 KiB
-constexpr int T4_STAGES = 16;
+constexpr int T4_CHUNK = MAX_RES_KB * T4_BSTAGE;  // 32 KiB: a chain's activations of one step
 constexpr int T4_SLD = 17;                        // padded row (floats) of the transposing hand-over buffer [128 lanes][16 rows]
 constexpr int T4_SBYTES = 128 * T4_SLD * 4;       // 8704 B per team
-constexpr int T4_ISSUERS = 4;                     // MMA-issuing warps: one per chain (a thread issues one tcgen05.mma per ~70-100 clk whatever its shape)
-constexpr int T4_THREADS = 32 * (1 + T4_ISSUERS + 8);  // warp 0 TMA, warps 1..4 MMA issue (warp 1 owns TMEM), 8 epilogue warps (2 teams x 4 quadrants)
+constexpr int T4_THREADS = 32 * (T4_MAXCH + T4_MAXCH + 8);  // warps 0-3 TMA producers, 4-7 MMA issuers (warp 4 owns TMEM), 8-15 epilogue (2 teams x 4 quadrants)
 constexpr int T4_TEAM = 128;
-constexpr uint32_t T4_TMEM_COLS = 128;            // 4 accumulators x 32 columns
+constexpr uint32_t T4_TMEM_COLS = 512;            // [0,128): 4 accumulators x 32 columns; [256,512): the stacked weight block, K = 512
+constexpr uint32_t T4_WCOL = 256;
 
 struct Seq4Smem {
-  uint32_t res, ring, full0, empty0, wbar, tfull0, tempty0;
+  uint32_t chunk, full0, tfull0, tempty0;
   uint32_t* tmem_slot;
   float* S;  // [2 teams][128][T4_SLD]
 };
-__device__ __forceinline__ Seq4Smem seq4_smem(uint8_t* smem_raw, int res_kb) {
+__device__ __forceinline__ Seq4Smem seq4_smem(uint8_t* smem_raw) {
   Seq4Smem s;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* al = smem_raw + (base - smem_u32(smem_raw));
-  s.res = base;
-  s.ring = base + (uint32_t)res_kb * 2 * B_HALF;
-  uint8_t* after = al + (size_t)res_kb * 2 * B_HALF + T4_STAGES * T4_BSTAGE;
+  s.chunk = base;  // [chain][k-block]{hi 2 KiB | lo 2 KiB}
+  uint8_t* after = al + (size_t)T4_MAXCH * T4_CHUNK;
   s.S = reinterpret_cast<float*>(after);
   uint64_t* bars = reinterpret_cast<uint64_t*>(after + 2 * T4_SBYTES);
-  s.full0 = smem_u32(bars);
-  s.empty0 = smem_u32(bars + T4_STAGES);
-  s.wbar = smem_u32(bars + 2 * T4_STAGES);
-  s.tfull0 = smem_u32(bars + 2 * T4_STAGES + 1);               // [4]
-  s.tempty0 = smem_u32(bars + 2 * T4_STAGES + 1 + T4_MAXCH);   // [4]
-  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * T4_STAGES + 1 + 2 * T4_MAXCH);
+  s.full0 = smem_u32(bars);                                        // [chain][k-block]
+  s.tfull0 = smem_u32(bars + T4_MAXCH * MAX_RES_KB);               // [chain]
+  s.tempty0 = smem_u32(bars + T4_MAXCH * MAX_RES_KB + T4_MAXCH);   // [chain]
+  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + T4_MAXCH * MAX_RES_KB + 2 * T4_MAXCH);
   return s;
 }
-static int seq4_smem_bytes(int res_kb) { return res_kb * 2 * B_HALF + T4_STAGES * T4_BSTAGE + 2 * T4_SBYTES + 1024 + 512; }
+static int seq4_smem_bytes() { return T4_MAXCH * T4_CHUNK + 2 * T4_SBYTES + 1024 + 512; }
 
 #define T4_TRACE(c, slot) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[((size_t)t * T4_MAXCH + (c)) * 8 + (slot)] = gtime(); } while (0)
 // named barriers of an epilogue team (128 threads): 2 + team
 __device__ __forceinline__ void team_bar_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(2 + team), "n"(T4_TEAM) : "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]: A is 128 lanes x 8 columns (16 bf16 of K per lane, two per 32-bit column, K ascending)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI_SW128)
+      : "memory");
+}
+#define LRCN_TMEM_ST_16(taddr, v)                                                                                       \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" \
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), \
+                 "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])                      \
+               : "memory")
 
+// wp_hi / wp_lo: the gate-interleaved recurrent weights [rows][Hp] (lstm_prepare_weights2), K contiguous
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T4_THREADS, 1)
-lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const SeqParams p, const int nch) {
+lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo, const __nv_bfloat16* __restrict__ wp_hi,
+                     const __nv_bfloat16* __restrict__ wp_lo, const int w_rows, const int w_ld, const SeqParams p, const int nch) {
   extern __shared__ uint8_t smem_raw[];
-  const Seq4Smem sm = seq4_smem(smem_raw, p.num_kb);
+  const Seq4Smem sm = seq4_smem(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int nt = blockIdx.x, mt = blockIdx.y, m0 = mt * T4_ROWS * nch;
@@ -1091,83 +1111,94 @@ lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   unsigned int* ctr = p.counters + T4_MAXCH * mt;  // [chain]
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < T4_STAGES; s++) { mbar_init(sm.full0 + 8 * s, 1); mbar_init(sm.empty0 + 8 * s, CL); }
-    mbar_init(sm.wbar, 1);
+    for (int i = 0; i < T4_MAXCH * MAX_RES_KB; i++) mbar_init(sm.full0 + 8 * i, 1);
     for (int c = 0; c < T4_MAXCH; c++) { mbar_init(sm.tfull0 + 8 * c, 1); mbar_init(sm.tempty0 + 8 * c, 1); }
     mbar_init_fence();
   }
-  if (warp == 0 && lane == 0) {
-    prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmA_lo); prefetch_tensormap(&tmB_hi); prefetch_tensormap(&tmB_lo);
-  }
-  if (warp == 1) tmem_alloc<T4_TMEM_COLS>(smem_u32(sm.tmem_slot));
+  if (warp == 0 && lane == 0) { prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmA_lo); }
+  if (warp == T4_MAXCH) tmem_alloc<T4_TMEM_COLS>(smem_u32(sm.tmem_slot));
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *sm.tmem_slot;
 
-  if (warp == 0 && lane == 0) {  // resident weights before the dependency wait (see lstm_fwd_seq_kernel)
-    mbar_expect_tx(sm.wbar, (uint32_t)num_kb * 2 * B_HALF);
-    for (int kb = 0; kb < num_kb; kb++) {
-      tma_load_2d(sm.res + kb * 2 * B_HALF, &tmB_hi, sm.wbar, kb * LBK, nt * NT);
-      tma_load_2d(sm.res + kb * 2 * B_HALF + B_HALF, &tmB_lo, sm.wbar, kb * LBK, nt * NT);
+  // Resident weights -> TMEM, once.  The epilogue warps own the TMEM lanes of their quadrant: lane = stacked weight row
+  // (0-63: W_hi rows of this n-tile, 64-127: W_lo rows), 32-bit column j = K elements 2j, 2j+1 -- exactly the uint32 words of
+  // the K-contiguous bf16 row.  The weights were written by the prep kernels more than two launches upstream (PDL discipline,
+  // kernels.cuh), so they are read BEFORE the dependency wait and the load overlaps the previous kernel's tail.
+  if (warp >= 2 * T4_MAXCH) {
+    const int quad = warp & 3, khalf = (warp - 2 * T4_MAXCH) >> 2;  // the two warps of a quadrant split the K range
+    const int srow = 32 * quad + lane;                              // stacked row = TMEM lane
+    const int wrow = nt * NT + (srow & 63);
+    const __nv_bfloat16* src = (srow < 64 ? wp_hi : wp_lo) + (size_t)wrow * w_ld;
+    const bool row_ok = wrow < w_rows;
+    const int ncol = num_kb * (LBK / 2);                            // 32-bit columns in use (32 per k-block)
+    for (int c0 = khalf * 16; c0 < ncol; c0 += 32) {
+      uint32_t v[16];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        uint4 x = make_uint4(0u, 0u, 0u, 0u);
+        const int k0 = 2 * (c0 + 4 * q);  // first K element of this 16-byte piece; rows are padded to multiples of 8 elements
+        if (row_ok && k0 < w_ld) x = __ldg(reinterpret_cast<const uint4*>(src + k0));
+        v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+      }
+      LRCN_TMEM_ST_16(tmem_base + ((uint32_t)(quad * 32) << 16) + T4_WCOL + (uint32_t)c0, v);
     }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // every CTA's barriers are initialised before any peer multicasts into them
+  tc_fence_after();
   pdl_wait();
   pdl_trigger();
 
-  if (warp == 0) {
-    // ===================== TMA producer: chunks in (t, chain, k-block) order =====================
-    if (lane == 0) {
-      int it = 0;
+  if (warp < T4_MAXCH) {
+    // ===================== TMA producers: warp c serves chain c =====================
+    const int c = warp;
+    if (lane == 0 && c < nch) {
+      const uint32_t buf = sm.chunk + (uint32_t)c * T4_CHUNK;
+      const uint32_t fullc = sm.full0 + 8 * (c * MAX_RES_KB);
       for (int t = 1; t < T; t++) {
-        for (int c = 0; c < nch; c++) {
-          grid_wait(ctr + c, (unsigned int)t * ctas_per_mtile);  // h_{t-1} rows of this chain are complete in global memory
-          T4_TRACE(c, 0);
-          fence_proxy_async_global();
-          const int arow = t * B + m0 + T4_ROWS * c;  // slot t of hs = h_{t-1}
-          for (int kb = 0; kb < num_kb; kb++, it++) {
-            const int s = it % T4_STAGES;
-            mbar_wait(sm.empty0 + 8 * s, ((it / T4_STAGES) & 1) ^ 1);  // every CTA of the cluster has consumed this stage
-            const uint32_t full = sm.full0 + 8 * s;
-            mbar_expect_tx(full, T4_BSTAGE);
-            if ((uint32_t)(kb % CL) == rank) {  // k-block kb is fetched by one rank and multicast to the cluster
-              const uint32_t st = sm.ring + s * T4_BSTAGE;
-              tma_load_2d_mcast(st, &tmA_hi, full, kb * LBK, arow, (uint16_t)((1u << CL) - 1));
-              tma_load_2d_mcast(st + T4_BHALF, &tmA_lo, full, kb * LBK, arow, (uint16_t)((1u << CL) - 1));
-            }
-          }
-          T4_TRACE(c, 1);
+        grid_wait(ctr + c, (unsigned int)t * ctas_per_mtile);  // h_{t-1} rows of this chain are complete; the cluster's MMAs of step t-1 are done
+        T4_TRACE(c, 0);
+        fence_proxy_async_global();
+        const int arow = t * B + m0 + T4_ROWS * c;  // slot t of hs = h_{t-1}
+        for (int kb = 0; kb < num_kb; kb++) mbar_expect_tx(fullc + 8 * kb, T4_BSTAGE);
+        for (int kb = (int)rank; kb < num_kb; kb += CL) {  // k-block kb is fetched by rank kb % CL and multicast to the cluster
+          const uint32_t st = buf + kb * T4_BSTAGE;
+          tma_load_2d_mcast(st, &tmA_hi, fullc + 8 * kb, kb * LBK, arow, (uint16_t)((1u << CL) - 1));
+          tma_load_2d_mcast(st + T4_BHALF, &tmA_lo, fullc + 8 * kb, kb * LBK, arow, (uint16_t)((1u << CL) - 1));
         }
+        T4_TRACE(c, 1);
       }
     }
-  } else if (warp <= T4_ISSUERS) {
-    // ===================== MMA issuers: warp 1 + i -> chains i, i + T4_ISSUERS, ... =====================
-    if (lane == 0) {
-      const int iss = warp - 1;
+  } else if (warp < 2 * T4_MAXCH) {
+    // ===================== MMA issuers: warp 4 + c serves chain c =====================
+    const int c = warp - T4_MAXCH;
+    if (lane == 0 && c < nch) {
       const uint32_t idesc = idesc_bf16(128, 2 * T4_ROWS, false, false);
-      mbar_wait(sm.wbar, 0);
+      const uint32_t acc = tmem_base + (uint32_t)(2 * T4_ROWS * c);
+      const uint32_t buf = sm.chunk + (uint32_t)c * T4_CHUNK;
+      const uint32_t fullc = sm.full0 + 8 * (c * MAX_RES_KB);
       for (int t = 1; t < T; t++) {
-        for (int c = iss; c < nch; c += T4_ISSUERS) {
-          if (t >= 2) { mbar_wait(sm.tempty0 + 8 * c, (t - 2) & 1); tc_fence_after(); }  // epilogue (t-1, c) has drained this accumulator
-          const uint32_t acc = tmem_base + (uint32_t)(2 * T4_ROWS * c);
-          int it = ((t - 1) * nch + c) * num_kb;
-          for (int kb = 0; kb < num_kb; kb++, it++) {
-            const int s = it % T4_STAGES;
-            mbar_wait(sm.full0 + 8 * s, (it / T4_STAGES) & 1);
-            if (kb == 0) T4_TRACE(c, 2); else if (kb == num_kb - 1) T4_TRACE(c, 3);
-            tc_fence_after();
-            stacked_mma_kblock(acc, sm.res + kb * 2 * B_HALF, sm.ring + s * T4_BSTAGE, idesc, kb == 0);  // A = weights, B = h chunk
-            umma_commit_mcast(sm.empty0 + 8 * s, (uint16_t)((1u << CL) - 1));
-          }
-          umma_commit(sm.tfull0 + 8 * c);
-          T4_TRACE(c, 4);
+        if (t >= 2) { mbar_wait(sm.tempty0 + 8 * c, (t - 2) & 1); tc_fence_after(); }  // epilogue (t-1, c) has drained this accumulator
+        for (int kb = 0; kb < num_kb; kb++) {
+          mbar_wait(fullc + 8 * kb, (t - 1) & 1);
+          if (kb == 0) T4_TRACE(c, 2); else if (kb == num_kb - 1) T4_TRACE(c, 3);
+          tc_fence_after();
+          const uint32_t b_lo = desc_lo_kmajor(buf + kb * T4_BSTAGE);
+          const uint32_t a_col = tmem_base + T4_WCOL + (uint32_t)(kb * (LBK / 2));
+#pragma unroll
+          for (int k = 0; k < LBK / 16; k++) umma_bf16_ts(acc, a_col + 8u * k, b_lo + 2u * k, idesc, (kb | k) ? 1u : 0u);
         }
+        umma_commit(sm.tfull0 + 8 * c);
+        T4_TRACE(c, 4);
       }
     }
   } else {
     // ===================== epilogue teams: team 0 -> chains 0, 2;  team 1 -> chains 1, 3 =====================
-    const int ew = warp - 1 - T4_ISSUERS, quad = warp & 3, team = ew >> 2;
+    const int ew = warp - 2 * T4_MAXCH, quad = warp & 3, team = ew >> 2;
     const int tid = (ew & 3) * 32 + lane;           // 0..127 inside the team (its four warps cover the four TMEM lane quadrants)
     float* S = sm.S + (size_t)team * 128 * T4_SLD;
     // cell ownership: row rr of the chain, units 2*up, 2*up+1 of the CTA's 16
@@ -1274,8 +1305,8 @@ lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   }
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();
-  if (warp == 1) {
+  cluster_sync_all();  // no CTA leaves while a peer may still multicast into its shared memory
+  if (warp == T4_MAXCH) {
     tc_fence_after();
     tmem_dealloc<T4_TMEM_COLS>(tmem_base);
   }
@@ -1674,16 +1705,15 @@ bool lstm_fwd_seq(cudaStream_t s, int B, int H, int T, const __nv_bfloat16* wper
       const int rows = T4_ROWS * nch;
       dim3 grid4((nt + CL - 1) / CL * CL, (B + rows - 1) / rows);
       if (grid4.y * T4_MAXCH > 64) continue;  // one counter per (m-tile, chain)
-      if (!seq_fits((const void*)lstm_fwd_seq4_kernel, num_kb, grid4, seq4_smem_bytes(num_kb), T4_THREADS)) continue;
+      if (!seq_fits((const void*)lstm_fwd_seq4_kernel, num_kb, grid4, seq4_smem_bytes(), T4_THREADS)) continue;
       const int Hp = (H + 7) / 8 * 8, wrows = fwd_rows(H);
-      CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
-      if (!get_tensor_map_bf16(&tb_hi, wperm_hi, H, wrows, Hp, F_NT) || !get_tensor_map_bf16(&tb_lo, wperm_lo, H, wrows, Hp, F_NT)) return false;
+      CUtensorMap ta_hi, ta_lo;
       const uint64_t R = (uint64_t)(T + 1) * B;
       if (!get_tensor_map_bf16(&ta_hi, hs_hi, H, R, H, T4_ROWS) || !get_tensor_map_bf16(&ta_lo, hs_lo, H, R, H, T4_ROWS)) return false;
       SeqParams p{};
       p.B = B; p.H = H; p.T = T; p.num_kb = num_kb; p.acts = acts; p.hs = hs; p.cs = cs; p.o_hi = hs_hi; p.o_lo = hs_lo; p.counters = counters;
       p.trace = trace;
-      launch_pdl(lstm_fwd_seq4_kernel, grid4, dim3(T4_THREADS), seq4_smem_bytes(num_kb), s, ta_hi, ta_lo, tb_hi, tb_lo, p, nch);
+      launch_pdl(lstm_fwd_seq4_kernel, grid4, dim3(T4_THREADS), seq4_smem_bytes(), s, ta_hi, ta_lo, wperm_hi, wperm_lo, wrows, Hp, p, nch);
       if (g_counter) g_counter->n++;
       *launched = true;
       return check_launch("lstm_fwd_seq4 launch");
@@ -1746,7 +1776,7 @@ bool init_lstm_sm100() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_fwd_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seq_smem_bytes(MAX_RES_KB, false));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_bwd_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seq_smem_bytes(MAX_RES_KB, true));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_fwd_seq2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seq2_smem_bytes(MAX_RES_KB));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_fwd_seq4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seq4_smem_bytes(MAX_RES_KB));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_fwd_seq4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seq4_smem_bytes());
   if (e != cudaSuccess) { set_sm100_error((std::string("cudaFuncSetAttribute(lstm): ") + cudaGetErrorString(e)).c_str()); return false; }
   return true;
 }
