@@ -1183,9 +1183,13 @@ lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       const uint32_t fullc = sm.full0 + 8 * (c * MAX_RES_KB);
       for (int t = 1; t < T; t++) {
         if (t >= 2) { mbar_wait(sm.tempty0 + 8 * c, (t - 2) & 1); tc_fence_after(); }  // epilogue (t-1, c) has drained this accumulator
+        if (p.sync_flags & 8) {  // diagnostics: wait for the whole chunk first, so that slot 3 = data arrival and slot 4 - slot 3 = pure MMA issue
+          for (int kb = 0; kb < num_kb; kb++) { mbar_wait(fullc + 8 * kb, (t - 1) & 1); if (kb == 0) T4_TRACE(c, 2); }
+          T4_TRACE(c, 3);
+        }
         for (int kb = 0; kb < num_kb; kb++) {
           mbar_wait(fullc + 8 * kb, (t - 1) & 1);
-          if (kb == 0) T4_TRACE(c, 2); else if (kb == num_kb - 1) T4_TRACE(c, 3);
+          if (!(p.sync_flags & 8)) { if (kb == 0) T4_TRACE(c, 2); else if (kb == num_kb - 1) T4_TRACE(c, 3); }
           tc_fence_after();
           const uint32_t b_lo = desc_lo_kmajor(buf + kb * T4_BSTAGE);
           const uint32_t a_col = tmem_base + T4_WCOL + (uint32_t)(kb * (LBK / 2));
@@ -1713,6 +1717,8 @@ bool lstm_fwd_seq(cudaStream_t s, int B, int H, int T, const __nv_bfloat16* wper
       SeqParams p{};
       p.B = B; p.H = H; p.T = T; p.num_kb = num_kb; p.acts = acts; p.hs = hs; p.cs = cs; p.o_hi = hs_hi; p.o_lo = hs_lo; p.counters = counters;
       p.trace = trace;
+      static const int dbg_flags = getenv("LRCN_SEQ_SYNC") ? atoi(getenv("LRCN_SEQ_SYNC")) : 0;
+      p.sync_flags = dbg_flags;
       launch_pdl(lstm_fwd_seq4_kernel, grid4, dim3(T4_THREADS), seq4_smem_bytes(), s, ta_hi, ta_lo, wperm_hi, wperm_lo, wrows, Hp, p, nch);
       if (g_counter) g_counter->n++;
       *launched = true;
