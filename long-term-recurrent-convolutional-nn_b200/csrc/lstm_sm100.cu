@@ -1019,46 +1019,48 @@ lstm_fwd_seq2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
 }
 
 // ============================================================================================================
-// TRANSPOSED, MULTI-CHAIN forward sequence kernel with the recurrent weights resident in TENSOR MEMORY ("seq4", round 2).
+// TRANSPOSED, TWO-CHAIN forward sequence kernel, recurrent weights resident in TENSOR MEMORY + shared memory ("seq4", round 2).
 //
-// What bounded the round-1 kernels (ncu + globaltimer traces, profiles/r02_lstm.md; tools/probe_mma_rate.py):
+// What bounded the round-1 kernels (ncu, globaltimer traces and probes: profiles/r02_lstm.md, tools/probe_mma_rate.py):
 //   * a step is a dependent CHAIN -- grid barrier -> TMA of the new h tile -> 32 MMAs -> cell epilogue -> release -- of 6-7 us
 //     during which the SM's tensor pipe is busy a quarter of the time;
-//   * ONE thread issues a tcgen05.mma every ~69 clk whatever the instruction's shape (M = 64 costs as much as M = 128), and
-//     in situ every k-block costs ~290 ns of wait + 4 MMAs + commit: the issue loop, not the tensor pipe, sets the pace;
-//   * 128 KiB of resident weights leave ~80 KiB of shared memory: a ring that cannot hold a step's activations, whose
-//     stage-reuse dependencies serialise the TMA producer behind the MMA consumer.
+//   * the MMA phase is bound by INSTRUCTIONS, not flops: one thread issues a tcgen05.mma every ~69 clk whatever its shape, and
+//     the tensor pipe needs >= 40-64 clk per instruction just to fetch the 128-row operand (M = 64 costs as much as M = 128;
+//     A from TMEM costs 64 clk per instruction).  So the number of MMAs per CTA and step is the currency: 32 k-steps per
+//     row group, and every extra row group re-fetches the whole weight block;
+//   * 128 KiB of weights in shared memory leave ~80 KiB: a ring that cannot hold a step's activations, whose stage-reuse
+//     dependencies (cluster-wide "empty" barriers) serialise the TMA producer behind the MMA consumer.
 // Hence:
-//   * roles swapped: the weight block {W_hi 64 gate rows; W_lo 64 gate rows} is the A operand (M = 128) and lives in TMEM
-//     (tcgen05.mma A-from-TMEM form): 128 lanes x 256 columns hold K = 512 of bf16 pairs.  Shared memory holds NO weights,
-//     the MMAs read only the small B operand from it, and every chain's whole activation chunk has a fixed home;
-//   * the streamed chunk {h_hi 16 batch rows; h_lo 16 batch rows} is the B operand (N = 32): one 128 x 32 x 16 MMA per
-//     k-step yields W_hi*h_hi, W_hi*h_lo, W_lo*h_hi (and an ignored W_lo*h_lo); accumulator lane = gate column
-//     (0-63: W_hi, 64-127: W_lo), column = batch row (0-15: h_hi, 16-31: h_lo);
-//   * a CTA's m-tile of 16*NCH rows is NCH <= 4 independent chains of 16 rows, each with its own grid-barrier counter, its
-//     own TMA-producer warp, MMA-issuer warp, TMEM accumulator and chunk buffer -- four issue loops run in parallel and a
-//     chain streams 32 KiB per step instead of 64 / 128 KiB.  No stage ring and no "empty" barriers: chunk (t+1, c) may
-//     overwrite chunk (t, c) once chain c's grid barrier for step t+1 is open, because every CTA of the cluster (the
-//     multicast group) arrives on that barrier only after ITS MMAs of step t have completed;
-//   * two epilogue TEAMS of four warps (one per TMEM lane quadrant) finish two chains concurrently; all 128 threads of a
-//     team run the cell update (2 units x 1 row each) after a transposing hand-over through shared memory, with
-//     64-byte-contiguous global accesses per (row, gate);
-//   * small batches get parallelism from the same mechanism: B <= 64 runs NCH = 1 (16-row m-tiles, 4x more CTAs).
+//   * roles swapped: the weight block {W_hi 64 gate rows; W_lo 64 gate rows} is the A operand (M = 128); its first
+//     T4_KB_TMEM k-blocks live in TMEM (tcgen05.mma A-from-TMEM form: 128 lanes x 32 columns per k-block), the rest in
+//     shared memory -- which frees enough shared memory for BOTH chains' whole activation chunks to have a fixed home;
+//   * the CTA's 64 rows are two independent chains of 32 rows: the streamed chunk {h_hi 32 rows; h_lo 32 rows} is the B
+//     operand (N = 64), so one 128 x 64 x 16 MMA per k-step yields W_hi*h_hi, W_hi*h_lo, W_lo*h_hi (and an ignored
+//     W_lo*h_lo): accumulator lane = gate column (0-63: W_hi, 64-127: W_lo), column = batch row (0-31: h_hi, 32-63: h_lo);
+//   * every chain has its own grid-barrier counter, TMA-producer warp, MMA-issuer warp, TMEM accumulator, chunk buffer and
+//     epilogue team: two issue loops and two epilogues run in parallel, one chain computes while the other communicates.
+//     No stage ring and no "empty" barriers: chunk (t+1, c) may overwrite chunk (t, c) once chain c's grid barrier for step
+//     t+1 is open, because every CTA of the cluster (the multicast group) arrives on it only after ITS MMAs of step t;
+//   * all 128 threads of a team run the cell update (2 units x 2 rows each) after a transposing hand-over through shared
+//     memory, with 64-byte-contiguous global accesses per (row, gate);
+//   * small batches: B <= 128 runs ONE chain per CTA (32-row m-tiles, twice the CTAs).
 // ============================================================================================================
-constexpr int T4_MAXCH = 4;                       // chains per CTA (upper bound)
-constexpr int T4_ROWS = 16;                       // batch rows per chain
-constexpr int T4_BHALF = T4_ROWS * LBK * 2;       // 2 KiB: {hi | lo} of one k-block of a chain
-constexpr int T4_BSTAGE = 2 * T4_BHALF;           // 4 KiB
-constexpr int T4_CHUNK = MAX_RES_KB * T4_BSTAGE;  // 32 KiB: a chain's activations of one step
-constexpr int T4_SLD = 17;                        // padded row (floats) of the transposing hand-over buffer [128 lanes][16 rows]
-constexpr int T4_SBYTES = 128 * T4_SLD * 4;       // 8704 B per team
-constexpr int T4_THREADS = 32 * (T4_MAXCH + T4_MAXCH + 8);  // warps 0-3 TMA producers, 4-7 MMA issuers (warp 4 owns TMEM), 8-15 epilogue (2 teams x 4 quadrants)
+constexpr int T4_MAXCH = 2;                       // chains per CTA (upper bound)
+constexpr int T4_ROWS = 32;                       // batch rows per chain
+constexpr int T4_BHALF = T4_ROWS * LBK * 2;       // 4 KiB: {hi | lo} of one k-block of a chain
+constexpr int T4_BSTAGE = 2 * T4_BHALF;           // 8 KiB
+constexpr int T4_CHUNK = MAX_RES_KB * T4_BSTAGE;  // 64 KiB: a chain's activations of one step
+constexpr int T4_KB_TMEM = 4;                     // weight k-blocks held in TMEM; k-blocks [T4_KB_TMEM, 8) are held in shared memory
+constexpr int T4_WSMEM = (MAX_RES_KB - T4_KB_TMEM) * 2 * B_HALF;  // 64 KiB
+constexpr int T4_SLD = 33;                        // padded row (floats) of the transposing hand-over buffer [128 lanes][32 rows]
+constexpr int T4_SBYTES = 128 * T4_SLD * 4;       // 16896 B per team
+constexpr int T4_THREADS = 32 * (T4_MAXCH + T4_MAXCH + 4 * T4_MAXCH);  // warps 0-1 TMA producers, 2-3 MMA issuers (warp 2 owns TMEM), 4-11 epilogue (2 teams x 4 quadrants)
 constexpr int T4_TEAM = 128;
-constexpr uint32_t T4_TMEM_COLS = 512;            // [0,128): 4 accumulators x 32 columns; [256,512): the stacked weight block, K = 512
-constexpr uint32_t T4_WCOL = 256;
+constexpr uint32_t T4_TMEM_COLS = 256;            // [0,128): 2 accumulators x 64 columns; [128,256): the first 4 k-blocks of the stacked weight block
+constexpr uint32_t T4_WCOL = 128;
 
 struct Seq4Smem {
-  uint32_t chunk, full0, tfull0, tempty0;
+  uint32_t wres, chunk, full0, wbar, tfull0, tempty0;
   uint32_t* tmem_slot;
   float* S;  // [2 teams][128][T4_SLD]
 };
@@ -1066,19 +1068,21 @@ __device__ __forceinline__ Seq4Smem seq4_smem(uint8_t* smem_raw) {
   Seq4Smem s;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* al = smem_raw + (base - smem_u32(smem_raw));
-  s.chunk = base;  // [chain][k-block]{hi 2 KiB | lo 2 KiB}
-  uint8_t* after = al + (size_t)T4_MAXCH * T4_CHUNK;
+  s.wres = base;                       // weight k-blocks [T4_KB_TMEM, 8): {W_hi 8 KiB | W_lo 8 KiB} each
+  s.chunk = base + T4_WSMEM;           // [chain][k-block]{hi 4 KiB | lo 4 KiB}
+  uint8_t* after = al + (size_t)T4_WSMEM + (size_t)T4_MAXCH * T4_CHUNK;
   s.S = reinterpret_cast<float*>(after);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(after + 2 * T4_SBYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(after + T4_MAXCH * T4_SBYTES);
   s.full0 = smem_u32(bars);                                        // [chain][k-block]
-  s.tfull0 = smem_u32(bars + T4_MAXCH * MAX_RES_KB);               // [chain]
-  s.tempty0 = smem_u32(bars + T4_MAXCH * MAX_RES_KB + T4_MAXCH);   // [chain]
-  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + T4_MAXCH * MAX_RES_KB + 2 * T4_MAXCH);
+  s.wbar = smem_u32(bars + T4_MAXCH * MAX_RES_KB);
+  s.tfull0 = smem_u32(bars + T4_MAXCH * MAX_RES_KB + 1);           // [chain]
+  s.tempty0 = smem_u32(bars + T4_MAXCH * MAX_RES_KB + 1 + T4_MAXCH);
+  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + T4_MAXCH * MAX_RES_KB + 1 + 2 * T4_MAXCH);
   return s;
 }
-static int seq4_smem_bytes() { return T4_MAXCH * T4_CHUNK + 2 * T4_SBYTES + 1024 + 512; }
+static int seq4_smem_bytes() { return T4_WSMEM + T4_MAXCH * T4_CHUNK + T4_MAXCH * T4_SBYTES + 1024 + 256; }
 
-#define T4_TRACE(c, slot) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[((size_t)t * T4_MAXCH + (c)) * 8 + (slot)] = gtime(); } while (0)
+#define T4_TRACE(c, slot) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[((size_t)t * 4 + (c)) * 8 + (slot)] = gtime(); } while (0)
 // named barriers of an epilogue team (128 threads): 2 + team
 __device__ __forceinline__ void team_bar_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(2 + team), "n"(T4_TEAM) : "memory"); }
 // D[tmem] (+)= A[tmem] * B[smem]: A is 128 lanes x 8 columns (16 bf16 of K per lane, two per 32-bit column, K ascending)
@@ -1097,9 +1101,10 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
                  "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])                      \
                : "memory")
 
-// wp_hi / wp_lo: the gate-interleaved recurrent weights [rows][Hp] (lstm_prepare_weights2), K contiguous
+// wp_hi / wp_lo: the gate-interleaved recurrent weights [rows][w_ld] (lstm_prepare_weights2), K contiguous; tmB_*: their tensor maps
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T4_THREADS, 1)
-lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo, const __nv_bfloat16* __restrict__ wp_hi,
+lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const __nv_bfloat16* __restrict__ wp_hi,
                      const __nv_bfloat16* __restrict__ wp_lo, const int w_rows, const int w_ld, const SeqParams p, const int nch) {
   extern __shared__ uint8_t smem_raw[];
   const Seq4Smem sm = seq4_smem(smem_raw);
@@ -1107,32 +1112,48 @@ lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   const uint32_t rank = cluster_ctarank();
   const int nt = blockIdx.x, mt = blockIdx.y, m0 = mt * T4_ROWS * nch;
   const int num_kb = p.num_kb, T = p.T, B = p.B, H = p.H;
+  const int kb_tmem = min(num_kb, T4_KB_TMEM);
   const unsigned int ctas_per_mtile = gridDim.x;
   unsigned int* ctr = p.counters + T4_MAXCH * mt;  // [chain]
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < T4_MAXCH * MAX_RES_KB; i++) mbar_init(sm.full0 + 8 * i, 1);
+    mbar_init(sm.wbar, 1);
     for (int c = 0; c < T4_MAXCH; c++) { mbar_init(sm.tfull0 + 8 * c, 1); mbar_init(sm.tempty0 + 8 * c, 1); }
     mbar_init_fence();
   }
-  if (warp == 0 && lane == 0) { prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmA_lo); }
+  if (warp == 0 && lane == 0) { prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmA_lo); prefetch_tensormap(&tmB_hi); prefetch_tensormap(&tmB_lo); }
   if (warp == T4_MAXCH) tmem_alloc<T4_TMEM_COLS>(smem_u32(sm.tmem_slot));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *sm.tmem_slot;
 
-  // Resident weights -> TMEM, once.  The epilogue warps own the TMEM lanes of their quadrant: lane = stacked weight row
-  // (0-63: W_hi rows of this n-tile, 64-127: W_lo rows), 32-bit column j = K elements 2j, 2j+1 -- exactly the uint32 words of
-  // the K-contiguous bf16 row.  The weights were written by the prep kernels more than two launches upstream (PDL discipline,
-  // kernels.cuh), so they are read BEFORE the dependency wait and the load overlaps the previous kernel's tail.
+  // Resident weights, once.  They were written by the prep kernels more than two launches upstream (PDL discipline, kernels.cuh),
+  // so they are read BEFORE the dependency wait and the load overlaps the previous kernel's tail.
+  // (1) k-blocks [T4_KB_TMEM, num_kb) -> shared memory by TMA;
+  if (warp == 0 && lane == 0) {
+    const int n_sm = num_kb - kb_tmem;
+    if (n_sm > 0) {
+      mbar_expect_tx(sm.wbar, (uint32_t)n_sm * 2 * B_HALF);
+      for (int i = 0; i < n_sm; i++) {
+        tma_load_2d(sm.wres + i * 2 * B_HALF, &tmB_hi, sm.wbar, (kb_tmem + i) * LBK, nt * NT);
+        tma_load_2d(sm.wres + i * 2 * B_HALF + B_HALF, &tmB_lo, sm.wbar, (kb_tmem + i) * LBK, nt * NT);
+      }
+    } else {
+      mbar_arrive(sm.wbar);
+    }
+  }
+  // (2) k-blocks [0, kb_tmem) -> TMEM by the epilogue warps, which own the TMEM lanes of their quadrant: lane = stacked weight row
+  // (0-63: W_hi rows of this n-tile, 64-127: W_lo rows), 32-bit column j = K elements 2j, 2j+1 -- exactly the uint32 words of the
+  // K-contiguous bf16 row.
   if (warp >= 2 * T4_MAXCH) {
     const int quad = warp & 3, khalf = (warp - 2 * T4_MAXCH) >> 2;  // the two warps of a quadrant split the K range
     const int srow = 32 * quad + lane;                              // stacked row = TMEM lane
     const int wrow = nt * NT + (srow & 63);
     const __nv_bfloat16* src = (srow < 64 ? wp_hi : wp_lo) + (size_t)wrow * w_ld;
     const bool row_ok = wrow < w_rows;
-    const int ncol = num_kb * (LBK / 2);                            // 32-bit columns in use (32 per k-block)
+    const int ncol = kb_tmem * (LBK / 2);                           // 32-bit columns in use (32 per k-block)
     for (int c0 = khalf * 16; c0 < ncol; c0 += 32) {
       uint32_t v[16];
 #pragma unroll
@@ -1174,13 +1195,14 @@ lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       }
     }
   } else if (warp < 2 * T4_MAXCH) {
-    // ===================== MMA issuers: warp 4 + c serves chain c =====================
+    // ===================== MMA issuers: warp 2 + c serves chain c =====================
     const int c = warp - T4_MAXCH;
     if (lane == 0 && c < nch) {
       const uint32_t idesc = idesc_bf16(128, 2 * T4_ROWS, false, false);
       const uint32_t acc = tmem_base + (uint32_t)(2 * T4_ROWS * c);
       const uint32_t buf = sm.chunk + (uint32_t)c * T4_CHUNK;
       const uint32_t fullc = sm.full0 + 8 * (c * MAX_RES_KB);
+      mbar_wait(sm.wbar, 0);
       for (int t = 1; t < T; t++) {
         if (t >= 2) { mbar_wait(sm.tempty0 + 8 * c, (t - 2) & 1); tc_fence_after(); }  // epilogue (t-1, c) has drained this accumulator
         if (p.sync_flags & 8) {  // diagnostics: wait for the whole chunk first, so that slot 3 = data arrival and slot 4 - slot 3 = pure MMA issue
@@ -1192,116 +1214,126 @@ lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
           if (!(p.sync_flags & 8)) { if (kb == 0) T4_TRACE(c, 2); else if (kb == num_kb - 1) T4_TRACE(c, 3); }
           tc_fence_after();
           const uint32_t b_lo = desc_lo_kmajor(buf + kb * T4_BSTAGE);
-          const uint32_t a_col = tmem_base + T4_WCOL + (uint32_t)(kb * (LBK / 2));
+          if (kb < T4_KB_TMEM) {
+            const uint32_t a_col = tmem_base + T4_WCOL + (uint32_t)(kb * (LBK / 2));
 #pragma unroll
-          for (int k = 0; k < LBK / 16; k++) umma_bf16_ts(acc, a_col + 8u * k, b_lo + 2u * k, idesc, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < LBK / 16; k++) umma_bf16_ts(acc, a_col + 8u * k, b_lo + 2u * k, idesc, (kb | k) ? 1u : 0u);
+          } else {
+            const uint32_t a_lo = desc_lo_kmajor(sm.wres + (kb - T4_KB_TMEM) * 2 * B_HALF);
+#pragma unroll
+            for (int k = 0; k < LBK / 16; k++) umma_bf16_lo(acc, a_lo + 2u * k, b_lo + 2u * k, idesc, 1u);
+          }
         }
         umma_commit(sm.tfull0 + 8 * c);
         T4_TRACE(c, 4);
       }
     }
   } else {
-    // ===================== epilogue teams: team 0 -> chains 0, 2;  team 1 -> chains 1, 3 =====================
-    const int ew = warp - 2 * T4_MAXCH, quad = warp & 3, team = ew >> 2;
+    // ===================== epilogue teams: team c finishes chain c =====================
+    const int ew = warp - 2 * T4_MAXCH, quad = warp & 3, c = ew >> 2;
     const int tid = (ew & 3) * 32 + lane;           // 0..127 inside the team (its four warps cover the four TMEM lane quadrants)
-    float* S = sm.S + (size_t)team * 128 * T4_SLD;
-    // cell ownership: row rr of the chain, units 2*up, 2*up+1 of the CTA's 16
-    const int rr = tid >> 3, up = tid & 7;
-    const int j = nt * (NT / 4) + 2 * up;
-    float creg[2][2];
-    float2 xg[2][4];
-    bool active[2];
-    int mrow[2];
+    float* S = sm.S + (size_t)c * 128 * T4_SLD;
+    if (c < nch) {
+      // cell ownership: rows rr and rr + 16 of the chain, units 2*up, 2*up+1 of the CTA's 16
+      const int rr = tid >> 3, up = tid & 7;
+      const int j = nt * (NT / 4) + 2 * up;
+      float creg[2][2];
+      float2 xg[2][4];
+      bool active[2];
+      int mrow[2];
 #pragma unroll
-    for (int sl = 0; sl < 2; sl++) {
-      const int c = team + 2 * sl;
-      mrow[sl] = m0 + T4_ROWS * c + rr;
-      active[sl] = c < nch && mrow[sl] < B && j < H;
-      creg[sl][0] = creg[sl][1] = 0.f;
+      for (int q = 0; q < 2; q++) {
+        mrow[q] = m0 + T4_ROWS * c + rr + 16 * q;
+        active[q] = mrow[q] < B && j < H;
+        creg[q][0] = creg[q][1] = 0.f;
 #pragma unroll
-      for (int g = 0; g < 4; g++) xg[sl][g] = make_float2(0.f, 0.f);
-      if (active[sl]) {
-        const float* g0 = p.acts + (size_t)mrow[sl] * 4 * H + j;
+        for (int g = 0; g < 4; g++) xg[q][g] = make_float2(0.f, 0.f);
+        if (active[q]) {
+          const float* g0 = p.acts + (size_t)mrow[q] * 4 * H + j;
 #pragma unroll
-        for (int g = 0; g < 4; g++) xg[sl][g] = *reinterpret_cast<const float2*>(g0 + g * H);
+          for (int g = 0; g < 4; g++) xg[q][g] = *reinterpret_cast<const float2*>(g0 + g * H);
+        }
       }
-    }
-    for (int t = 0; t < T; t++) {
-#pragma unroll
-      for (int sl = 0; sl < 2; sl++) {
-        const int c = team + 2 * sl;
-        if (c >= nch) continue;  // uniform over the team
-        float a[4][2];  // [gate][unit] recurrent part of the pre-activations
+      for (int t = 0; t < T; t++) {
         if (t > 0) {
           mbar_wait(sm.tfull0 + 8 * c, (t - 1) & 1);
           if (tid == 0) T4_TRACE(c, 5);
           tc_fence_after();
-          uint32_t v[32];
-          LRCN_TMEM_LD_32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * T4_ROWS * c), v);
-          tmem_ld_wait();
-          tc_fence_before();
-          // accumulator lane = 32*quad + lane: gate column (W_hi: 0-63 | W_lo: 64-127); columns 0-15: * h_hi, 16-31: * h_lo
+          // accumulator lane = 32*quad + lane: gate column (W_hi: 0-63 | W_lo: 64-127); columns 0-31: * h_hi, 32-63: * h_lo
+          const uint32_t tl = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * T4_ROWS * c);
           float* dst = S + (size_t)(32 * quad + lane) * T4_SLD;
+          uint32_t v[32];
+          LRCN_TMEM_LD_32(tl, v);
           if (quad < 2) {
+            uint32_t w[32];
+            LRCN_TMEM_LD_32(tl + T4_ROWS, w);
+            tmem_ld_wait();
 #pragma unroll
-            for (int r = 0; r < T4_ROWS; r++) dst[r] = __uint_as_float(v[r]) + __uint_as_float(v[T4_ROWS + r]);
+            for (int r = 0; r < T4_ROWS; r++) dst[r] = __uint_as_float(v[r]) + __uint_as_float(w[r]);
           } else {
+            tmem_ld_wait();
 #pragma unroll
             for (int r = 0; r < T4_ROWS; r++) dst[r] = __uint_as_float(v[r]);
           }
-          team_bar_sync(team);
+          tc_fence_before();
+          team_bar_sync(c);
+        }
+        float gf[2][2], gi[2][2], go[2][2], gc[2][2], hn[2][2];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          float a[4][2];  // [gate][unit] recurrent part of the pre-activations
 #pragma unroll
           for (int e = 0; e < 2; e++)
 #pragma unroll
             for (int g = 0; g < 4; g++) {
               const int gl = 4 * (2 * up + e) + g;  // weight rows are unit-major: row u*4 + gate
-              a[g][e] = S[(size_t)gl * T4_SLD + rr] + S[(size_t)(64 + gl) * T4_SLD + rr];
+              a[g][e] = t > 0 ? S[(size_t)gl * T4_SLD + rr + 16 * q] + S[(size_t)(64 + gl) * T4_SLD + rr + 16 * q] : 0.f;
             }
-        } else {
+          if (active[q]) {
+            const float xf[2] = {xg[q][0].x, xg[q][0].y}, xi[2] = {xg[q][1].x, xg[q][1].y};
+            const float xo[2] = {xg[q][2].x, xg[q][2].y}, xc[2] = {xg[q][3].x, xg[q][3].y};
+            __nv_bfloat16 hh[2], ll[2];
 #pragma unroll
-          for (int g = 0; g < 4; g++) a[g][0] = a[g][1] = 0.f;
-        }
-        float gf[2], gi[2], go[2], gc[2], hn[2];
-        const size_t hnext = ((size_t)(t + 1) * B + mrow[sl]) * H + j;
-        if (active[sl]) {
-          const float xf[2] = {xg[sl][0].x, xg[sl][0].y}, xi[2] = {xg[sl][1].x, xg[sl][1].y};
-          const float xo[2] = {xg[sl][2].x, xg[sl][2].y}, xc[2] = {xg[sl][3].x, xg[sl][3].y};
-          __nv_bfloat16 hh[2], ll[2];
-#pragma unroll
-          for (int e = 0; e < 2; e++) {
-            gf[e] = sigm_fast(xf[e] + a[0][e]);
-            gi[e] = sigm_fast(xi[e] + a[1][e]);
-            go[e] = sigm_fast(xo[e] + a[2][e]);
-            gc[e] = tanh_fast(xc[e] + a[3][e]);
-            creg[sl][e] = creg[sl][e] * gf[e] + gi[e] * gc[e];
-            hn[e] = go[e] * tanh_fast(creg[sl][e]);
-            split_bf16(hn[e], hh[e], ll[e]);
+            for (int e = 0; e < 2; e++) {
+              gf[q][e] = sigm_fast(xf[e] + a[0][e]);
+              gi[q][e] = sigm_fast(xi[e] + a[1][e]);
+              go[q][e] = sigm_fast(xo[e] + a[2][e]);
+              gc[q][e] = tanh_fast(xc[e] + a[3][e]);
+              creg[q][e] = creg[q][e] * gf[q][e] + gi[q][e] * gc[q][e];
+              hn[q][e] = go[q][e] * tanh_fast(creg[q][e]);
+              split_bf16(hn[q][e], hh[e], ll[e]);
+            }
+            const size_t hnext = ((size_t)(t + 1) * B + mrow[q]) * H + j;
+            *reinterpret_cast<uint32_t*>(p.o_hi + hnext) = *reinterpret_cast<uint32_t*>(hh);
+            *reinterpret_cast<uint32_t*>(p.o_lo + hnext) = *reinterpret_cast<uint32_t*>(ll);
           }
-          *reinterpret_cast<uint32_t*>(p.o_hi + hnext) = *reinterpret_cast<uint32_t*>(hh);
-          *reinterpret_cast<uint32_t*>(p.o_lo + hnext) = *reinterpret_cast<uint32_t*>(ll);
         }
         // every thread of the team is past its reads of S and its h stores: one thread frees the accumulator for the issuer
         // and publishes h_t of this chain (bar.sync orders the team's stores before the gpu-scope release; the reading
         // producers fence generic->async proxy after their acquire)
-        team_bar_sync(team);
+        team_bar_sync(c);
         if (tid == 0) {
           T4_TRACE(c, 6);
           if (t > 0) mbar_arrive(sm.tempty0 + 8 * c);
           if (t + 1 < T) { fence_proxy_async_global(); grid_arrive(ctr + c); }
           T4_TRACE(c, 7);
         }
-        if (active[sl]) {  // off the critical path: what only later kernels read
-          float* grow = p.acts + ((size_t)t * B + mrow[sl]) * 4 * H + j;
-          *reinterpret_cast<float2*>(grow) = make_float2(gf[0], gf[1]);
-          *reinterpret_cast<float2*>(grow + H) = make_float2(gi[0], gi[1]);
-          *reinterpret_cast<float2*>(grow + 2 * H) = make_float2(go[0], go[1]);
-          *reinterpret_cast<float2*>(grow + 3 * H) = make_float2(gc[0], gc[1]);
-          *reinterpret_cast<float2*>(p.cs + hnext) = make_float2(creg[sl][0], creg[sl][1]);
-          *reinterpret_cast<float2*>(p.hs + hnext) = make_float2(hn[0], hn[1]);
-          if (t + 1 < T) {  // prefetch the next step's x-part
-            const float* gn = p.acts + ((size_t)(t + 1) * B + mrow[sl]) * 4 * H + j;
 #pragma unroll
-            for (int g = 0; g < 4; g++) xg[sl][g] = *reinterpret_cast<const float2*>(gn + g * H);
+        for (int q = 0; q < 2; q++) {
+          if (active[q]) {  // off the critical path: what only later kernels read
+            const size_t hnext = ((size_t)(t + 1) * B + mrow[q]) * H + j;
+            float* grow = p.acts + ((size_t)t * B + mrow[q]) * 4 * H + j;
+            *reinterpret_cast<float2*>(grow) = make_float2(gf[q][0], gf[q][1]);
+            *reinterpret_cast<float2*>(grow + H) = make_float2(gi[q][0], gi[q][1]);
+            *reinterpret_cast<float2*>(grow + 2 * H) = make_float2(go[q][0], go[q][1]);
+            *reinterpret_cast<float2*>(grow + 3 * H) = make_float2(gc[q][0], gc[q][1]);
+            *reinterpret_cast<float2*>(p.cs + hnext) = make_float2(creg[q][0], creg[q][1]);
+            *reinterpret_cast<float2*>(p.hs + hnext) = make_float2(hn[q][0], hn[q][1]);
+            if (t + 1 < T) {  // prefetch the next step's x-part
+              const float* gn = p.acts + ((size_t)(t + 1) * B + mrow[q]) * 4 * H + j;
+#pragma unroll
+              for (int g = 0; g < 4; g++) xg[q][g] = *reinterpret_cast<const float2*>(gn + g * H);
+            }
           }
         }
       }
@@ -1711,7 +1743,8 @@ bool lstm_fwd_seq(cudaStream_t s, int B, int H, int T, const __nv_bfloat16* wper
       if (grid4.y * T4_MAXCH > 64) continue;  // one counter per (m-tile, chain)
       if (!seq_fits((const void*)lstm_fwd_seq4_kernel, num_kb, grid4, seq4_smem_bytes(), T4_THREADS)) continue;
       const int Hp = (H + 7) / 8 * 8, wrows = fwd_rows(H);
-      CUtensorMap ta_hi, ta_lo;
+      CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+      if (!get_tensor_map_bf16(&tb_hi, wperm_hi, H, wrows, Hp, F_NT) || !get_tensor_map_bf16(&tb_lo, wperm_lo, H, wrows, Hp, F_NT)) return false;
       const uint64_t R = (uint64_t)(T + 1) * B;
       if (!get_tensor_map_bf16(&ta_hi, hs_hi, H, R, H, T4_ROWS) || !get_tensor_map_bf16(&ta_lo, hs_lo, H, R, H, T4_ROWS)) return false;
       SeqParams p{};
@@ -1719,7 +1752,7 @@ bool lstm_fwd_seq(cudaStream_t s, int B, int H, int T, const __nv_bfloat16* wper
       p.trace = trace;
       static const int dbg_flags = getenv("LRCN_SEQ_SYNC") ? atoi(getenv("LRCN_SEQ_SYNC")) : 0;
       p.sync_flags = dbg_flags;
-      launch_pdl(lstm_fwd_seq4_kernel, grid4, dim3(T4_THREADS), seq4_smem_bytes(), s, ta_hi, ta_lo, wperm_hi, wperm_lo, wrows, Hp, p, nch);
+      launch_pdl(lstm_fwd_seq4_kernel, grid4, dim3(T4_THREADS), seq4_smem_bytes(), s, ta_hi, ta_lo, tb_hi, tb_lo, wperm_hi, wperm_lo, wrows, Hp, p, nch);
       if (g_counter) g_counter->n++;
       *launched = true;
       return check_launch("lstm_fwd_seq4 launch");
