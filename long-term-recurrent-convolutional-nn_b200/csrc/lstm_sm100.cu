@@ -1210,8 +1210,10 @@ lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
           T4_TRACE(c, 3);
         }
         for (int kb = 0; kb < num_kb; kb++) {
-          mbar_wait(fullc + 8 * kb, (t - 1) & 1);
-          if (!(p.sync_flags & 8)) { if (kb == 0) T4_TRACE(c, 2); else if (kb == num_kb - 1) T4_TRACE(c, 3); }
+          if (!(p.sync_flags & 8)) {
+            mbar_wait(fullc + 8 * kb, (t - 1) & 1);
+            if (kb == 0) T4_TRACE(c, 2); else if (kb == num_kb - 1) T4_TRACE(c, 3);
+          }
           if (kb == 0 || (p.sync_flags & 32)) tc_fence_after();
           const uint32_t b_lo = desc_lo_kmajor(buf + kb * T4_BSTAGE);
           if (kb < T4_KB_TMEM) {
