@@ -79,7 +79,7 @@ extern "C" int lrcn_test_gemm_time(lrcn_handle* h, int a_kmajor, int b_kmajor, i
 
 extern "C" int lrcn_test_mma_rate(lrcn_handle* h, int M, int N, int n_mma, int commit_every, int issuers, int64_t* issue_clk_out,
                                   int64_t* total_clk_out) {
-  if (!h || !issue_clk_out || !total_clk_out || (M != 64 && M != 128) || N < 16 || N > 256 || (N % 16) || n_mma < 1 || issuers < 1 || issuers > 2 || commit_every < 0)
+  if (!h || !issue_clk_out || !total_clk_out || (M != 64 && M != 128) || N < 16 || N > 256 || (N % 16) || n_mma < 1 || (issuers & 15) < 1 || (issuers & 15) > 2 || commit_every < 0)
     return fail(LRCN_ERR_ARG, "bad argument");
   CK(cudaSetDevice(h->cfg.device));
   long long a = 0, b = 0;
