@@ -1196,38 +1196,47 @@ lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
     }
   } else if (warp < 2 * T4_MAXCH) {
     // ===================== MMA issuers: warp 2 + c serves chain c =====================
-    const int c = warp - T4_MAXCH;
-    if (lane == 0 && c < nch) {
+    // The whole warp runs the loops CONVERGED on warp-uniform values and one elected lane issues (see elect_one()).
+    const int c = __shfl_sync(0xffffffffu, warp - T4_MAXCH, 0);
+    if (c < nch) {
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc = idesc_bf16(128, 2 * T4_ROWS, false, false);
-      const uint32_t acc = tmem_base + (uint32_t)(2 * T4_ROWS * c);
+      const uint32_t acc = tb + (uint32_t)(2 * T4_ROWS * c);
       const uint32_t buf = sm.chunk + (uint32_t)c * T4_CHUNK;
       const uint32_t fullc = sm.full0 + 8 * (c * MAX_RES_KB);
       mbar_wait(sm.wbar, 0);
       for (int t = 1; t < T; t++) {
-        if (t >= 2) { mbar_wait(sm.tempty0 + 8 * c, (t - 2) & 1); tc_fence_after(); }  // epilogue (t-1, c) has drained this accumulator
+        if (t >= 2) mbar_wait(sm.tempty0 + 8 * c, (t - 2) & 1);  // epilogue (t-1, c) has drained this accumulator
+        tc_fence_after();
         if (p.sync_flags & 8) {  // diagnostics: wait for the whole chunk first, so that slot 3 = data arrival and slot 4 - slot 3 = pure MMA issue
-          for (int kb = 0; kb < num_kb; kb++) { mbar_wait(fullc + 8 * kb, (t - 1) & 1); if (kb == 0) T4_TRACE(c, 2); }
-          T4_TRACE(c, 3);
+          for (int kb = 0; kb < num_kb; kb++) { mbar_wait(fullc + 8 * kb, (t - 1) & 1); if (kb == 0 && lane == 0) T4_TRACE(c, 2); }
+          if (lane == 0) T4_TRACE(c, 3);
         }
         for (int kb = 0; kb < num_kb; kb++) {
           if (!(p.sync_flags & 8)) {
             mbar_wait(fullc + 8 * kb, (t - 1) & 1);
-            if (kb == 0) T4_TRACE(c, 2); else if (kb == num_kb - 1) T4_TRACE(c, 3);
+            if (lane == 0) { if (kb == 0) T4_TRACE(c, 2); else if (kb == num_kb - 1) T4_TRACE(c, 3); }
           }
-          if (kb == 0 || (p.sync_flags & 32)) tc_fence_after();
+          tc_fence_after();
           const uint32_t b_lo = desc_lo_kmajor(buf + kb * T4_BSTAGE);
           if (kb < T4_KB_TMEM) {
-            const uint32_t a_col = tmem_base + T4_WCOL + (uint32_t)(kb * (LBK / 2));
+            const uint32_t a_col = tb + T4_WCOL + (uint32_t)(kb * (LBK / 2));
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < LBK / 16; k++) umma_bf16_ts(acc, a_col + 8u * k, b_lo + 2u * k, idesc, (kb | k) ? 1u : 0u);
+              for (int k = 0; k < LBK / 16; k++) umma_bf16_ts(acc, a_col + 8u * k, b_lo + 2u * k, idesc, (kb | k) ? 1u : 0u);
+            }
           } else {
             const uint32_t a_lo = desc_lo_kmajor(sm.wres + (kb - T4_KB_TMEM) * 2 * B_HALF);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < LBK / 16; k++) umma_bf16_lo(acc, a_lo + 2u * k, b_lo + 2u * k, idesc, 1u);
+              for (int k = 0; k < LBK / 16; k++) umma_bf16_lo(acc, a_lo + 2u * k, b_lo + 2u * k, idesc, 1u);
+            }
           }
+          __syncwarp();
         }
-        umma_commit(sm.tfull0 + 8 * c);
-        T4_TRACE(c, 4);
+        if (elect_one()) umma_commit(sm.tfull0 + 8 * c);
+        __syncwarp();
+        if (lane == 0) T4_TRACE(c, 4);
       }
     }
   } else {

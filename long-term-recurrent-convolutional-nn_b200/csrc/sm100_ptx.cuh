@@ -126,6 +126,15 @@ __device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uin
       : "memory");
 }
 
+// One lane of a CONVERGED warp.  tcgen05.mma takes its descriptors from uniform registers: inside `if (lane == 0)` the compiler
+// cannot prove that a single thread is active and wraps every MMA in an ELECT / R2UR x4 / branch "waterfall" (~125 clk per MMA
+// in the LSTM issue loops); warp-converged loops over warp-uniform values + elect.sync let it keep the descriptors in uniform
+// registers and advance them with uniform-datapath adds.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
