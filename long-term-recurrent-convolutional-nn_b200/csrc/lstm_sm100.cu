@@ -1605,6 +1605,328 @@ lstm_bwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   }
 }
 
+// ============================================================================================================
+// TRANSPOSED, TWO-CHAIN backward sequence kernel, recurrent weights resident in TENSOR MEMORY ("bwd4", round 2).
+// Same construction as lstm_fwd_seq4_kernel (see there for the measurements behind it), for
+//   dh_rec[m][j] = sum_n dG_{t+1}[m][n] * W_h[j][n],  K = 4H.
+//   * the 4 CTAs of a cluster are the K-quarters of one 64-unit output tile (K = 4H is too long for one CTA's weights);
+//     each holds its slice of the transposed weights {WhT_hi 64 units; WhT_lo 64 units} x K/4 as the A operand (M = 128)
+//     entirely in TMEM (128 lanes x 32 columns per k-block, <= 8 k-blocks) -- shared memory holds no weights;
+//   * the CTA's 64 batch rows are two independent chains of 32 rows: B operand = {dG_hi 32 rows; dG_lo 32 rows} (N = 64) of
+//     the K-slice, 64 KiB per chain and step with a fixed home (plain TMA: every K-quarter streams different bytes);
+//     accumulator lane = unit (0-63: * WhT_hi, 64-127: * WhT_lo), column = batch row (0-31: dG_hi, 32-63: dG_lo);
+//   * per chain: own grid-barrier counter, producer warp, issuer warp (converged elect loop), accumulator and epilogue team.
+//     The team sums the three split products through a transposing shared-memory buffer, SENDS every cluster rank the
+//     16 units it finishes (fp32 partials over this K-quarter, st.shared::cluster + one remote mbarrier arrive per rank),
+//     waits for the four partials of ITS 16 units, and runs the cell adjoint (4 units x 1 row per thread, 16-byte global
+//     accesses).  No "buffer free" handshake is needed: a rank sends step n+1 only after the grid barrier of that step,
+//     which every CTA of the m-tile passes after it has consumed the partials of step n.
+// ============================================================================================================
+constexpr int B4_RLD = 34;                          // floats per unit row of the receive buffer [src][16 units][32 rows (+2)]: conflict-free reads
+constexpr int B4_RED = CL * 16 * B4_RLD * 4;        // 8704 B per chain
+constexpr uint32_t B4_TMEM_COLS = 512;              // [0,128): 2 accumulators x 64 columns; [128,384): the weight slice, up to 8 k-blocks
+constexpr uint32_t B4_WCOL = 128;
+
+struct Bwd4Smem {
+  uint32_t chunk, full0, tfull0, tempty0, redfull0;
+  uint32_t* tmem_slot;
+  float* S;    // [2 teams][128][T4_SLD]
+  float* red;  // [2 chains][CL src][16][B4_RLD]
+};
+__device__ __forceinline__ Bwd4Smem bwd4_smem(uint8_t* smem_raw) {
+  Bwd4Smem s;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* al = smem_raw + (base - smem_u32(smem_raw));
+  s.chunk = base;  // [chain][k-block]{hi 4 KiB | lo 4 KiB}
+  uint8_t* after = al + (size_t)T4_MAXCH * T4_CHUNK;
+  s.S = reinterpret_cast<float*>(after);
+  s.red = reinterpret_cast<float*>(after + T4_MAXCH * T4_SBYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(after + T4_MAXCH * T4_SBYTES + T4_MAXCH * B4_RED);
+  s.full0 = smem_u32(bars);                                        // [chain][k-block]
+  s.tfull0 = smem_u32(bars + T4_MAXCH * MAX_RES_KB);               // [chain]
+  s.tempty0 = smem_u32(bars + T4_MAXCH * MAX_RES_KB + T4_MAXCH);
+  s.redfull0 = smem_u32(bars + T4_MAXCH * MAX_RES_KB + 2 * T4_MAXCH);
+  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + T4_MAXCH * MAX_RES_KB + 3 * T4_MAXCH);
+  return s;
+}
+static int bwd4_smem_bytes() { return T4_MAXCH * T4_CHUNK + T4_MAXCH * T4_SBYTES + T4_MAXCH * B4_RED + 1024 + 256; }
+__device__ __forceinline__ void dsmem_st_f2(uint32_t addr, float x, float y) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(x), "f"(y) : "memory");
+}
+
+// wt_hi / wt_lo: transposed recurrent weights [w_rows units][K = 4H] (lstm_prepare_weights2), K contiguous
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(T4_THREADS, 1)
+lstm_bwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo, const __nv_bfloat16* __restrict__ wt_hi,
+                     const __nv_bfloat16* __restrict__ wt_lo, const int w_rows, const SeqParams p, const int nch) {
+  extern __shared__ uint8_t smem_raw[];
+  const Bwd4Smem sm = bwd4_smem(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int nt = blockIdx.x / CL, mt = blockIdx.y, m0 = mt * T4_ROWS * nch;
+  const int T = p.T, B = p.B, H = p.H;
+  const int kb_per = (p.num_kb + CL - 1) / CL;                                   // k-blocks of the full K = 4H per rank (<= 8)
+  const int kb_begin = (int)rank * kb_per;
+  const int nkb = max(0, min(p.num_kb, kb_begin + kb_per) - kb_begin);
+  const unsigned int ctas_per_mtile = gridDim.x;
+  unsigned int* ctr = p.counters + T4_MAXCH * mt;  // [chain]
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < T4_MAXCH * MAX_RES_KB; i++) mbar_init(sm.full0 + 8 * i, 1);
+    for (int c = 0; c < T4_MAXCH; c++) { mbar_init(sm.tfull0 + 8 * c, 1); mbar_init(sm.tempty0 + 8 * c, 1); mbar_init(sm.redfull0 + 8 * c, CL); }
+    mbar_init_fence();
+  }
+  if (warp == 0 && lane == 0) { prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmA_lo); }
+  if (warp == T4_MAXCH) tmem_alloc<B4_TMEM_COLS>(smem_u32(sm.tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *sm.tmem_slot;
+
+  // Resident weight slice -> TMEM, once, by the epilogue warps (lane = stacked weight row: 0-63 WhT_hi units of this tile,
+  // 64-127 WhT_lo; 32-bit column j = K elements 2j, 2j+1 of this rank's K-quarter).  Written by the prep kernels more than two
+  // launches upstream (PDL discipline, kernels.cuh): read BEFORE the dependency wait.
+  if (warp >= 2 * T4_MAXCH) {
+    const int quad = warp & 3, khalf = (warp - 2 * T4_MAXCH) >> 2;
+    const int srow = 32 * quad + lane;
+    const int wrow = nt * NT + (srow & 63);
+    const size_t K = 4 * (size_t)H;
+    const __nv_bfloat16* src = (srow < 64 ? wt_hi : wt_lo) + (size_t)wrow * K + (size_t)kb_begin * LBK;
+    const bool row_ok = wrow < w_rows;
+    const int klim = (int)K - kb_begin * LBK;                        // K elements of this row from the slice start (K % 32 == 0)
+    const int ncol = nkb * (LBK / 2);
+    for (int c0 = khalf * 16; c0 < ncol; c0 += 32) {
+      uint32_t v[16];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        uint4 x = make_uint4(0u, 0u, 0u, 0u);
+        const int k0 = 2 * (c0 + 4 * q);
+        if (row_ok && k0 < klim) x = __ldg(reinterpret_cast<const uint4*>(src + k0));
+        v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+      }
+      LRCN_TMEM_ST_16(tmem_base + ((uint32_t)(quad * 32) << 16) + B4_WCOL + (uint32_t)c0, v);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // every CTA's barriers are initialised before any peer arrives on them
+  tc_fence_after();
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp < T4_MAXCH) {
+    // ===================== TMA producers: warp c serves chain c =====================
+    const int c = warp;
+    if (lane == 0 && c < nch && nkb > 0) {
+      const uint32_t buf = sm.chunk + (uint32_t)c * T4_CHUNK;
+      const uint32_t fullc = sm.full0 + 8 * (c * MAX_RES_KB);
+      for (int t = T - 2; t >= 0; t--) {
+        grid_wait(ctr + c, (unsigned int)(T - 1 - t) * ctas_per_mtile);  // dG_{t+1} rows of this chain are complete
+        fence_proxy_async_global();
+        const int arow = (t + 1) * B + m0 + T4_ROWS * c;
+        for (int i = 0; i < nkb; i++) {
+          const uint32_t full = fullc + 8 * i, st = buf + i * T4_BSTAGE;
+          mbar_expect_tx(full, T4_BSTAGE);
+          tma_load_2d(st, &tmA_hi, full, (kb_begin + i) * LBK, arow);
+          tma_load_2d(st + T4_BHALF, &tmA_lo, full, (kb_begin + i) * LBK, arow);
+        }
+      }
+    }
+  } else if (warp < 2 * T4_MAXCH) {
+    // ===================== MMA issuers: warp 2 + c serves chain c (converged warp, elected lane: see elect_one()) =====================
+    const int c = __shfl_sync(0xffffffffu, warp - T4_MAXCH, 0);
+    if (c < nch && nkb > 0) {
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t idesc = idesc_bf16(128, 2 * T4_ROWS, false, false);
+      const uint32_t acc = tb + (uint32_t)(2 * T4_ROWS * c);
+      const uint32_t buf = sm.chunk + (uint32_t)c * T4_CHUNK;
+      const uint32_t fullc = sm.full0 + 8 * (c * MAX_RES_KB);
+      int n = 0;  // index of the recurrent step
+      for (int t = T - 2; t >= 0; t--, n++) {
+        if (n >= 1) mbar_wait(sm.tempty0 + 8 * c, (n - 1) & 1);  // the epilogue of the previous step has drained this accumulator
+        tc_fence_after();
+        for (int i = 0; i < nkb; i++) {
+          mbar_wait(fullc + 8 * i, n & 1);
+          tc_fence_after();
+          const uint32_t b_lo = desc_lo_kmajor(buf + i * T4_BSTAGE);
+          const uint32_t a_col = tb + B4_WCOL + (uint32_t)(i * (LBK / 2));
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < LBK / 16; k++) umma_bf16_ts(acc, a_col + 8u * k, b_lo + 2u * k, idesc, (i | k) ? 1u : 0u);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit(sm.tfull0 + 8 * c);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue teams: team c finishes chain c =====================
+    const int ew = warp - 2 * T4_MAXCH, quad = warp & 3, c = ew >> 2;
+    const int tid = (ew & 3) * 32 + lane;  // 0..127 inside the team
+    float* S = sm.S + (size_t)c * 128 * T4_SLD;
+    float* red = sm.red + (size_t)c * CL * 16 * B4_RLD;
+    if (c < nch) {
+      // sender mapping: unit su of a destination's 16, rows sr4 .. sr4+3;  finisher mapping: row fr of the chain, units 4*ug .. 4*ug+3
+      const int su = tid >> 3, sr4 = (tid & 7) * 4;
+      const int fr = tid >> 2, ug = tid & 3;
+      const int m = m0 + T4_ROWS * c + fr;
+      const int j = nt * NT + 16 * (int)rank + 4 * ug;
+      const bool active = m < B && j < H;
+      float dcreg[4] = {0.f, 0.f, 0.f, 0.f};
+      float bsum[4][4];  // [gate][unit]: this thread's share of the bias gradient (sum of dG over its row and all steps)
+#pragma unroll
+      for (int g = 0; g < 4; g++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) bsum[g][e] = 0.f;
+      float4 pf, pi, po, pg, pcp, pcc, pdh;
+      pf = pi = po = pg = pcp = pcc = pdh = make_float4(0.f, 0.f, 0.f, 0.f);
+      auto prefetch = [&](int tt) {
+        const float* g0 = p.acts + ((size_t)tt * B + m) * 4 * H + j;
+        pf = *reinterpret_cast<const float4*>(g0); pi = *reinterpret_cast<const float4*>(g0 + H);
+        po = *reinterpret_cast<const float4*>(g0 + 2 * H); pg = *reinterpret_cast<const float4*>(g0 + 3 * H);
+        pcp = *reinterpret_cast<const float4*>(p.cs + ((size_t)tt * B + m) * H + j);
+        pcc = *reinterpret_cast<const float4*>(p.cs + ((size_t)(tt + 1) * B + m) * H + j);
+        pdh = *reinterpret_cast<const float4*>(p.dh_all + ((size_t)tt * B + m) * H + j);
+      };
+      if (active) prefetch(T - 1);
+      int n = 0;
+      for (int t = T - 1; t >= 0; t--) {
+        const bool has_rec = t < T - 1;
+        float rec[4] = {0.f, 0.f, 0.f, 0.f};
+        if (has_rec) {
+          // phase 1: accumulator -> S (the three split products summed: lanes 0-63 hold hi*hi + hi*lo, lanes 64-127 lo*hi)
+          float* dst = S + (size_t)(32 * quad + lane) * T4_SLD;
+          if (nkb > 0) {
+            mbar_wait(sm.tfull0 + 8 * c, n & 1);
+            tc_fence_after();
+            const uint32_t tl = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * T4_ROWS * c);
+            uint32_t v[32];
+            LRCN_TMEM_LD_32(tl, v);
+            if (quad < 2) {
+              uint32_t w[32];
+              LRCN_TMEM_LD_32(tl + T4_ROWS, w);
+              tmem_ld_wait();
+#pragma unroll
+              for (int r = 0; r < T4_ROWS; r++) dst[r] = __uint_as_float(v[r]) + __uint_as_float(w[r]);
+            } else {
+              tmem_ld_wait();
+#pragma unroll
+              for (int r = 0; r < T4_ROWS; r++) dst[r] = __uint_as_float(v[r]);
+            }
+            tc_fence_before();
+          } else {
+#pragma unroll
+            for (int r = 0; r < T4_ROWS; r++) dst[r] = 0.f;
+          }
+          team_bar_sync(c);
+          // phase 2: send every rank the partials (over this K-quarter) of the 16 units it finishes
+          const uint32_t red_local = smem_u32(red) + (uint32_t)((((int)rank * 16 + su) * B4_RLD + sr4) * 4);
+#pragma unroll
+          for (int d = 0; d < CL; d++) {
+            const float* s0 = S + (size_t)(16 * d + su) * T4_SLD + sr4;
+            const float* s1 = s0 + 64 * T4_SLD;
+            const uint32_t ra = dsmem_addr(red_local, (uint32_t)d);
+            dsmem_st_f2(ra, s0[0] + s1[0], s0[1] + s1[1]);
+            dsmem_st_f2(ra + 8u, s0[2] + s1[2], s0[3] + s1[3]);
+          }
+          team_bar_sync(c);  // the team's DSMEM stores are ordered before thread 0's cluster-scope releases (cumulativity)
+          if (tid == 0) {
+            if (nkb > 0) mbar_arrive(sm.tempty0 + 8 * c);  // every thread of the team is past its TMEM and S reads
+#pragma unroll
+            for (int d = 0; d < CL; d++) mbar_arrive_remote(dsmem_addr(sm.redfull0 + 8 * c, (uint32_t)d));
+          }
+          // phase 3: the four partials of my units
+          mbar_wait_cluster(sm.redfull0 + 8 * c, n & 1);
+#pragma unroll
+          for (int src = 0; src < CL; src++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) rec[e] += red[(size_t)(src * 16 + 4 * ug + e) * B4_RLD + fr];
+          n++;
+        }
+        float r0[4], r1[4], r2[4], r3[4];
+        const size_t gidx = ((size_t)t * B + m) * 4 * H + j;
+        if (active) {
+          const float f[4] = {pf.x, pf.y, pf.z, pf.w}, in[4] = {pi.x, pi.y, pi.z, pi.w}, o[4] = {po.x, po.y, po.z, po.w}, ch[4] = {pg.x, pg.y, pg.z, pg.w};
+          const float cpv[4] = {pcp.x, pcp.y, pcp.z, pcp.w}, ccv[4] = {pcc.x, pcc.y, pcc.z, pcc.w}, dhv[4] = {pdh.x, pdh.y, pdh.z, pdh.w};
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const float dh = dhv[e] + rec[e];
+            const float tc = tanh_fast(ccv[e]);
+            const float dcv = dcreg[e] + dh * o[e] * (1.f - tc * tc);
+            const float dO = dh * tc, dF = dcv * cpv[e], dI = dcv * ch[e], dG = dcv * in[e];
+            dcreg[e] = dcv * f[e];
+            r0[e] = dF * f[e] * (1.f - f[e]);
+            r1[e] = dI * in[e] * (1.f - in[e]);
+            r2[e] = dO * o[e] * (1.f - o[e]);
+            r3[e] = dG * (1.f - ch[e] * ch[e]);
+          }
+          const float* rr[4] = {r0, r1, r2, r3};
+#pragma unroll
+          for (int g = 0; g < 4; g++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) bsum[g][e] += rr[g][e];
+#pragma unroll
+          for (int g = 0; g < 4; g++) {  // the bf16 split of dG_t is what the next step's TMA reads: store it first
+            __nv_bfloat16 hh[4], ll[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) split_bf16(rr[g][e], hh[e], ll[e]);
+            *reinterpret_cast<uint2*>(p.o_hi + gidx + (size_t)g * H) = *reinterpret_cast<uint2*>(hh);
+            *reinterpret_cast<uint2*>(p.o_lo + gidx + (size_t)g * H) = *reinterpret_cast<uint2*>(ll);
+          }
+        }
+        if (t > 0) {  // publish dG_t of this chain
+          team_bar_sync(c);  // orders the team's stores before the release below; also: every reader is done with `red`
+          if (tid == 0) { fence_proxy_async_global(); grid_arrive(ctr + c); }
+        }
+        if (active) {  // off the critical path
+          float* grow = p.acts + gidx;
+          *reinterpret_cast<float4*>(grow) = make_float4(r0[0], r0[1], r0[2], r0[3]);
+          *reinterpret_cast<float4*>(grow + H) = make_float4(r1[0], r1[1], r1[2], r1[3]);
+          *reinterpret_cast<float4*>(grow + 2 * H) = make_float4(r2[0], r2[1], r2[2], r2[3]);
+          *reinterpret_cast<float4*>(grow + 3 * H) = make_float4(r3[0], r3[1], r3[2], r3[3]);
+          if (t > 0) prefetch(t - 1);
+        }
+      }
+      if (p.dbias) {
+        // bias gradient: sum over the rows of a warp by shuffles (lanes with equal ug), over the team's four warps through S
+        // (free now), then one atomic per (gate, unit) and team onto the zero-initialised gradient
+#pragma unroll
+        for (int g = 0; g < 4; g++)
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            float v = active ? bsum[g][e] : 0.f;
+            v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+            bsum[g][e] = v;
+          }
+        team_bar_sync(c);
+        if (lane < 4) {
+#pragma unroll
+          for (int g = 0; g < 4; g++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) S[((ew & 3) * 4 + lane) * 16 + g * 4 + e] = bsum[g][e];  // [warp][ug][gate][unit]
+        }
+        team_bar_sync(c);
+        if (tid < 64) {
+          const int ugq = tid >> 4, ge = tid & 15, g = ge >> 2, e = ge & 3;
+          float v = 0.f;
+#pragma unroll
+          for (int w4 = 0; w4 < 4; w4++) v += S[(w4 * 4 + ugq) * 16 + ge];
+          const int jj = nt * NT + 16 * (int)rank + 4 * ugq + e;
+          if (jj < H) atomicAdd(p.dbias + (size_t)g * H + jj, v);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // no CTA leaves while a peer may still store into its shared memory / arrive on its barriers
+  if (warp == T4_MAXCH) {
+    tc_fence_after();
+    tmem_dealloc<B4_TMEM_COLS>(tmem_base);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- weight copies
 constexpr int F_NT = NT, F_NH = NT / 4;  // forward: 16 hidden units x 4 gates per CTA
 constexpr int R_NT = NT;                // backward: 64 hidden units per cluster, 16 finished by each CTA
@@ -1810,6 +2132,25 @@ bool lstm_bwd_seq(cudaStream_t s, int B, int H, int T, const __nv_bfloat16* wt_h
   const int num_kb = (int)((K + LBK - 1) / LBK);
   const int kb_per = (num_kb + CL - 1) / CL;
   const int nt = (H + R_NT - 1) / R_NT;
+  static const bool no_seq4 = getenv("LRCN_SEQ_V2") != nullptr || getenv("LRCN_SEQ_V1") != nullptr;  // round-1 kernel
+  if (!no_seq4 && T >= 2 && kb_per <= MAX_RES_KB) {
+    for (int nch = 1; nch <= T4_MAXCH; nch *= 2) {
+      const int rows = T4_ROWS * nch;
+      dim3 grid4(nt * CL, (B + rows - 1) / rows);
+      if (grid4.y * T4_MAXCH > 64) continue;  // one counter per (m-tile, chain)
+      if (!seq_fits((const void*)lstm_bwd_seq4_kernel, kb_per, grid4, bwd4_smem_bytes(), T4_THREADS)) continue;
+      CUtensorMap ta_hi, ta_lo;
+      const uint64_t R = (uint64_t)T * B;
+      if (!get_tensor_map_bf16(&ta_hi, acts_hi, K, R, K, T4_ROWS) || !get_tensor_map_bf16(&ta_lo, acts_lo, K, R, K, T4_ROWS)) return false;
+      SeqParams p{};
+      p.B = B; p.H = H; p.T = T; p.num_kb = num_kb; p.acts = acts; p.cs = cs; p.o_hi = acts_hi; p.o_lo = acts_lo; p.dh_all = dh_all; p.dc = dc;
+      p.counters = counters; p.dbias = dbias;
+      launch_pdl(lstm_bwd_seq4_kernel, grid4, dim3(T4_THREADS), bwd4_smem_bytes(), s, ta_hi, ta_lo, wt_hi, wt_lo, bwd_rows(H), p, nch);
+      if (g_counter) g_counter->n++;
+      *launched = true;
+      return check_launch("lstm_bwd_seq4 launch");
+    }
+  }
   dim3 grid(nt * CL, (B + LM - 1) / LM);
   if (T < 2 || !seq_fits((const void*)lstm_bwd_seq_kernel, kb_per, grid, seq_smem_bytes(kb_per, true))) return true;
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
@@ -1834,6 +2175,7 @@ bool init_lstm_sm100() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_bwd_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seq_smem_bytes(MAX_RES_KB, true));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_fwd_seq2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seq2_smem_bytes(MAX_RES_KB));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_fwd_seq4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, seq4_smem_bytes());
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_bwd_seq4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd4_smem_bytes());
   if (e != cudaSuccess) { set_sm100_error((std::string("cudaFuncSetAttribute(lstm): ") + cudaGetErrorString(e)).c_str()); return false; }
   return true;
 }
