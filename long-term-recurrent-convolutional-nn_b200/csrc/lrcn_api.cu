@@ -575,7 +575,7 @@ static void lstm_layer_fwd(lrcn_handle* h, int layer, int T, int B, float* acts,
     shadow(h, hs, &hs_hi, &hs_lo);
     bool launched = false;
     if (!lstm_fwd_seq(h->stream, B, H, T, layer == 1 ? h->wp1_hi : h->wp2_hi, layer == 1 ? h->wp1_lo : h->wp2_lo, acts, hs, cs, hs_hi, hs_lo,
-                      h->d_counters + (layer == 1 ? 0 : 64), &launched, layer == 2 ? h->d_trace : nullptr))
+                      h->d_counters + (layer == 1 ? 0 : 64), &launched, (layer == 2 && !getenv("LRCN_TRACE_BWD")) ? h->d_trace : nullptr))
       throw GemmFail{gemm_bf16x3_last_error()};
     if (launched) return;
   }
@@ -589,7 +589,7 @@ static bool lstm_layer_bwd(lrcn_handle* h, int layer, int T, int B, float* acts,
     shadow(h, acts, &a_hi, &a_lo);
     bool launched = false;
     if (!lstm_bwd_seq(h->stream, B, H, T, layer == 1 ? h->wt1_hi : h->wt2_hi, layer == 1 ? h->wt1_lo : h->wt2_lo, acts, a_hi, a_lo, cs, dh_all, dc,
-                      h->d_counters + (layer == 2 ? 128 : 192), &launched, dbias))
+                      h->d_counters + (layer == 2 ? 128 : 192), &launched, dbias, (layer == 2 && getenv("LRCN_TRACE_BWD")) ? h->d_trace : nullptr))
       throw GemmFail{gemm_bf16x3_last_error()};
     if (launched) return true;
   }

@@ -1722,6 +1722,7 @@ lstm_bwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       const uint32_t fullc = sm.full0 + 8 * (c * MAX_RES_KB);
       for (int t = T - 2; t >= 0; t--) {
         grid_wait(ctr + c, (unsigned int)(T - 1 - t) * ctas_per_mtile);  // dG_{t+1} rows of this chain are complete
+        T4_TRACE(c, 0);
         fence_proxy_async_global();
         const int arow = (t + 1) * B + m0 + T4_ROWS * c;
         for (int i = 0; i < nkb; i++) {
@@ -1730,6 +1731,7 @@ lstm_bwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
           tma_load_2d(st, &tmA_hi, full, (kb_begin + i) * LBK, arow);
           tma_load_2d(st + T4_BHALF, &tmA_lo, full, (kb_begin + i) * LBK, arow);
         }
+        T4_TRACE(c, 1);
       }
     }
   } else if (warp < 2 * T4_MAXCH) {
@@ -1747,6 +1749,7 @@ lstm_bwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
         tc_fence_after();
         for (int i = 0; i < nkb; i++) {
           mbar_wait(fullc + 8 * i, n & 1);
+          if (lane == 0) { if (i == 0) T4_TRACE(c, 2); else if (i == nkb - 1) T4_TRACE(c, 3); }
           tc_fence_after();
           const uint32_t b_lo = desc_lo_kmajor(buf + i * T4_BSTAGE);
           const uint32_t a_col = tb + B4_WCOL + (uint32_t)(i * (LBK / 2));
@@ -1758,6 +1761,7 @@ lstm_bwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
         }
         if (elect_one()) umma_commit(sm.tfull0 + 8 * c);
         __syncwarp();
+        if (lane == 0) T4_TRACE(c, 4);
       }
     }
   } else {
@@ -1799,6 +1803,7 @@ lstm_bwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
           float* dst = S + (size_t)(32 * quad + lane) * T4_SLD;
           if (nkb > 0) {
             mbar_wait(sm.tfull0 + 8 * c, n & 1);
+            if (tid == 0) T4_TRACE(c, 5);
             tc_fence_after();
             const uint32_t tl = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * T4_ROWS * c);
             uint32_t v[32];
@@ -1837,7 +1842,9 @@ lstm_bwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
             for (int d = 0; d < CL; d++) mbar_arrive_remote(dsmem_addr(sm.redfull0 + 8 * c, (uint32_t)d));
           }
           // phase 3: the four partials of my units
+          if (tid == 0) T4_TRACE(c, 6);   // partials sent
           mbar_wait_cluster(sm.redfull0 + 8 * c, n & 1);
+          if (tid == 0) T4_TRACE(c, 7);   // partials of my units received
 #pragma unroll
           for (int src = 0; src < CL; src++)
 #pragma unroll
@@ -1877,7 +1884,14 @@ lstm_bwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
         }
         if (t > 0) {  // publish dG_t of this chain
           team_bar_sync(c);  // orders the team's stores before the release below; also: every reader is done with `red`
-          if (tid == 0) { fence_proxy_async_global(); grid_arrive(ctr + c); }
+          if (tid == 0) {
+            // anti-phase the two chains once (see lstm_fwd_seq4_kernel)
+            if (t == T - 1 && c == 1 && nch > 1 && !(p.sync_flags & 16)) {
+              const unsigned long long t0 = gtime();
+              while (gtime() - t0 < (unsigned long long)(p.sync_flags >> 8 ? (p.sync_flags >> 8) : 4000)) {}
+            }
+            fence_proxy_async_global(); grid_arrive(ctr + c);
+          }
         }
         if (active) {  // off the critical path
           float* grow = p.acts + gidx;
@@ -2126,7 +2140,7 @@ bool lstm_fwd_seq(cudaStream_t s, int B, int H, int T, const __nv_bfloat16* wper
 
 bool lstm_bwd_seq(cudaStream_t s, int B, int H, int T, const __nv_bfloat16* wt_hi, const __nv_bfloat16* wt_lo, float* acts,
                   __nv_bfloat16* acts_hi, __nv_bfloat16* acts_lo, float* cs, const float* dh_all, float* dc, unsigned int* counters,
-                  bool* launched, float* dbias) {
+                  bool* launched, float* dbias, unsigned long long* trace) {
   *launched = false;
   const uint64_t K = 4 * (uint64_t)H;
   const int num_kb = (int)((K + LBK - 1) / LBK);
@@ -2144,7 +2158,9 @@ bool lstm_bwd_seq(cudaStream_t s, int B, int H, int T, const __nv_bfloat16* wt_h
       if (!get_tensor_map_bf16(&ta_hi, acts_hi, K, R, K, T4_ROWS) || !get_tensor_map_bf16(&ta_lo, acts_lo, K, R, K, T4_ROWS)) return false;
       SeqParams p{};
       p.B = B; p.H = H; p.T = T; p.num_kb = num_kb; p.acts = acts; p.cs = cs; p.o_hi = acts_hi; p.o_lo = acts_lo; p.dh_all = dh_all; p.dc = dc;
-      p.counters = counters; p.dbias = dbias;
+      p.counters = counters; p.dbias = dbias; p.trace = trace;
+      static const int dbg_flags = getenv("LRCN_SEQ_SYNC") ? atoi(getenv("LRCN_SEQ_SYNC")) : 0;
+      p.sync_flags = dbg_flags;
       launch_pdl(lstm_bwd_seq4_kernel, grid4, dim3(T4_THREADS), bwd4_smem_bytes(), s, ta_hi, ta_lo, wt_hi, wt_lo, bwd_rows(H), p, nch);
       if (g_counter) g_counter->n++;
       *launched = true;

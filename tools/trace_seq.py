@@ -38,6 +38,16 @@ else:
     raw = np.zeros((T * 4, 8), dtype=np.uint64)
     abi.check(h.lib.lrcn_get_trace(h._h, raw.ctypes.data_as(abi._p(abi.C.c_uint64)), raw.size))
     tr = raw.astype(np.int64).reshape(T, 4, 8)
+    if os.environ.get("LRCN_TRACE_BWD"):
+        print("BACKWARD kernel. ns relative to chain 0's barrier-open of the step; per chain: open, tma_issued, kb0, kbLast, tfull_commit, epi_start, sent, received")
+        for t in range(T - 2, -1, -1):
+            base = tr[t, 0, 0]
+            for c in range(2):
+                print(f"t={t:2d} c={c}", [int(x - base) if x else -1 for x in tr[t, c]])
+            if t > 0:
+                print("      next step's chain-0 barrier opens at", int(tr[t - 1, 0, 0] - base))
+        h.close()
+        sys.exit(0)
     print("ns relative to chain 0's barrier-open of the step; per chain: open, tma_issued, kb0, kbLast, tfull_commit, epi_start, team_done, released")
     for t in range(1, T):
         base = tr[t, 0, 0]
