@@ -1616,14 +1616,15 @@ lstm_bwd_seq_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 //     the K-slice, 64 KiB per chain and step with a fixed home (plain TMA: every K-quarter streams different bytes);
 //     accumulator lane = unit (0-63: * WhT_hi, 64-127: * WhT_lo), column = batch row (0-31: dG_hi, 32-63: dG_lo);
 //   * per chain: own grid-barrier counter, producer warp, issuer warp (converged elect loop), accumulator and epilogue team.
-//     The team sums the three split products through a transposing shared-memory buffer, SENDS every cluster rank the
-//     16 units it finishes (fp32 partials over this K-quarter, st.shared::cluster + one remote mbarrier arrive per rank),
-//     waits for the four partials of ITS 16 units, and runs the cell adjoint (4 units x 1 row per thread, 16-byte global
-//     accesses).  No "buffer free" handshake is needed: a rank sends step n+1 only after the grid barrier of that step,
+//     The team drops the accumulator into a shared-memory buffer [128 lanes][32 rows] and one thread SENDS every cluster
+//     rank the rows of the 16 units that rank finishes (W_hi part and W_lo part: two 2 KiB cp.async.bulk copies
+//     shared::cta -> shared::cluster per rank, completing bytes on the receiver's mbarrier -- per-thread st.shared::cluster
+//     stores cost 3 us per step here); every thread then waits for the 4 x 2 partials of ITS units, sums them and runs the
+//     cell adjoint (4 units x 1 row per thread, 16-byte global accesses).  No "buffer free" handshake is needed: a rank sends step n+1 only after the grid barrier of that step,
 //     which every CTA of the m-tile passes after it has consumed the partials of step n.
 // ============================================================================================================
-constexpr int B4_RLD = 34;                          // floats per unit row of the receive buffer [src][16 units][32 rows (+2)]: conflict-free reads
-constexpr int B4_RED = CL * 16 * B4_RLD * 4;        // 8704 B per chain
+constexpr int B4_PART = 16 * T4_SLD * 4;            // 2112 B: 16 unit rows of the hand-over buffer = one bulk copy
+constexpr int B4_RED = CL * 2 * B4_PART;            // 16896 B per chain: receive buffer [src][hi-part | lo-part][16 units][T4_SLD]
 constexpr uint32_t B4_TMEM_COLS = 512;              // [0,128): 2 accumulators x 64 columns; [128,384): the weight slice, up to 8 k-blocks
 constexpr uint32_t B4_WCOL = 128;
 
@@ -1631,7 +1632,7 @@ struct Bwd4Smem {
   uint32_t chunk, full0, tfull0, tempty0, redfull0;
   uint32_t* tmem_slot;
   float* S;    // [2 teams][128][T4_SLD]
-  float* red;  // [2 chains][CL src][16][B4_RLD]
+  float* red;  // [2 chains][CL src][2 parts][16][T4_SLD]
 };
 __device__ __forceinline__ Bwd4Smem bwd4_smem(uint8_t* smem_raw) {
   Bwd4Smem s;
@@ -1650,8 +1651,10 @@ __device__ __forceinline__ Bwd4Smem bwd4_smem(uint8_t* smem_raw) {
   return s;
 }
 static int bwd4_smem_bytes() { return T4_MAXCH * T4_CHUNK + T4_MAXCH * T4_SBYTES + T4_MAXCH * B4_RED + 1024 + 256; }
-__device__ __forceinline__ void dsmem_st_f2(uint32_t addr, float x, float y) {
-  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(x), "f"(y) : "memory");
+// bulk copy of local shared memory into a cluster peer's shared memory (DMA engine); completes bytes on the PEER's mbarrier
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes, uint32_t mbar_cluster_addr) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_cluster_addr), "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr) : "memory");
 }
 
 // wt_hi / wt_lo: transposed recurrent weights [w_rows units][K = 4H] (lstm_prepare_weights2), K contiguous
@@ -1672,7 +1675,7 @@ lstm_bwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < T4_MAXCH * MAX_RES_KB; i++) mbar_init(sm.full0 + 8 * i, 1);
-    for (int c = 0; c < T4_MAXCH; c++) { mbar_init(sm.tfull0 + 8 * c, 1); mbar_init(sm.tempty0 + 8 * c, 1); mbar_init(sm.redfull0 + 8 * c, CL); }
+    for (int c = 0; c < T4_MAXCH; c++) { mbar_init(sm.tfull0 + 8 * c, 1); mbar_init(sm.tempty0 + 8 * c, 1); mbar_init(sm.redfull0 + 8 * c, 1); }
     mbar_init_fence();
   }
   if (warp == 0 && lane == 0) { prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmA_lo); }
@@ -1769,10 +1772,9 @@ lstm_bwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
     const int ew = warp - 2 * T4_MAXCH, quad = warp & 3, c = ew >> 2;
     const int tid = (ew & 3) * 32 + lane;  // 0..127 inside the team
     float* S = sm.S + (size_t)c * 128 * T4_SLD;
-    float* red = sm.red + (size_t)c * CL * 16 * B4_RLD;
+    float* red = sm.red + (size_t)c * (B4_RED / 4);
     if (c < nch) {
-      // sender mapping: unit su of a destination's 16, rows sr4 .. sr4+3;  finisher mapping: row fr of the chain, units 4*ug .. 4*ug+3
-      const int su = tid >> 3, sr4 = (tid & 7) * 4;
+      // finisher mapping: row fr of the chain, units 4*ug .. 4*ug+3 of this rank's 16
       const int fr = tid >> 2, ug = tid & 3;
       const int m = m0 + T4_ROWS * c + fr;
       const int j = nt * NT + 16 * (int)rank + 4 * ug;
@@ -1824,31 +1826,29 @@ lstm_bwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
 #pragma unroll
             for (int r = 0; r < T4_ROWS; r++) dst[r] = 0.f;
           }
+          fence_async_smem();  // the team's generic-proxy writes of S become visible to the bulk-copy (async proxy) reads
           team_bar_sync(c);
-          // phase 2: send every rank the partials (over this K-quarter) of the 16 units it finishes
-          const uint32_t red_local = smem_u32(red) + (uint32_t)((((int)rank * 16 + su) * B4_RLD + sr4) * 4);
-#pragma unroll
-          for (int d = 0; d < CL; d++) {
-            const float* s0 = S + (size_t)(16 * d + su) * T4_SLD + sr4;
-            const float* s1 = s0 + 64 * T4_SLD;
-            const uint32_t ra = dsmem_addr(red_local, (uint32_t)d);
-            dsmem_st_f2(ra, s0[0] + s1[0], s0[1] + s1[1]);
-            dsmem_st_f2(ra + 8u, s0[2] + s1[2], s0[3] + s1[3]);
-          }
-          team_bar_sync(c);  // the team's DSMEM stores are ordered before thread 0's cluster-scope releases (cumulativity)
+          // phase 2: one thread sends every rank the partials (over this K-quarter) of the 16 units it finishes
           if (tid == 0) {
-            if (nkb > 0) mbar_arrive(sm.tempty0 + 8 * c);  // every thread of the team is past its TMEM and S reads
+            if (nkb > 0) mbar_arrive(sm.tempty0 + 8 * c);  // every thread of the team is past its TMEM reads
+            mbar_expect_tx(sm.redfull0 + 8 * c, B4_RED);   // what the four ranks (this one included) will deliver to me
+            const uint32_t s_hi = smem_u32(S), s_lo = smem_u32(S) + 64 * T4_SLD * 4;
+            const uint32_t r_mine = smem_u32(red) + (uint32_t)((int)rank * 2 * B4_PART);
 #pragma unroll
-            for (int d = 0; d < CL; d++) mbar_arrive_remote(dsmem_addr(sm.redfull0 + 8 * c, (uint32_t)d));
+            for (int d = 0; d < CL; d++) {
+              const uint32_t dst = dsmem_addr(r_mine, (uint32_t)d), bar = dsmem_addr(sm.redfull0 + 8 * c, (uint32_t)d);
+              dsmem_bulk_copy(dst, s_hi + (uint32_t)(d * B4_PART), B4_PART, bar);
+              dsmem_bulk_copy(dst + B4_PART, s_lo + (uint32_t)(d * B4_PART), B4_PART, bar);
+            }
+            T4_TRACE(c, 6);   // partials sent
           }
-          // phase 3: the four partials of my units
-          if (tid == 0) T4_TRACE(c, 6);   // partials sent
-          mbar_wait_cluster(sm.redfull0 + 8 * c, n & 1);
-          if (tid == 0) T4_TRACE(c, 7);   // partials of my units received
+          // phase 3: the 4 x 2 partials of my units
+          mbar_wait(sm.redfull0 + 8 * c, n & 1);
+          if (tid == 0) T4_TRACE(c, 7);   // received
 #pragma unroll
-          for (int src = 0; src < CL; src++)
+          for (int q = 0; q < 2 * CL; q++)
 #pragma unroll
-            for (int e = 0; e < 4; e++) rec[e] += red[(size_t)(src * 16 + 4 * ug + e) * B4_RLD + fr];
+            for (int e = 0; e < 4; e++) rec[e] += red[(size_t)(q * 16 + 4 * ug + e) * T4_SLD + fr];
           n++;
         }
         float r0[4], r1[4], r2[4], r3[4];
