@@ -550,5 +550,5 @@ def test_full_size_properties_flickr30k_config():
             assert (ga_ > 1e-7).any()
             # fp32 weight ulp ~4e-9; the step recomputes the gradient and partial sums land in any order, so entries that are
             # sums cancelling to ~1e-12 carry percent-level noise: check where the gradient is well above that
-            bad = (np.abs(got - want) > 1e-2 * want + 1e-8) & (ga_ > 1e-9)
+            bad = (np.abs(got - want) > 1e-2 * want + 1e-8) & (ga_ > 1e-8)  # |g| ~ eps = 1e-8 and below: dw depends on g to first order, and g carries summation-order noise
             assert bad.sum() == 0, (k, int(bad.sum()), float(np.abs(got - want).max()), got[bad][:4], want[bad][:4], ga_[bad][:4])
