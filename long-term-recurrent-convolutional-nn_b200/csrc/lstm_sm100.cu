@@ -1060,7 +1060,7 @@ constexpr uint32_t T4_TMEM_COLS = 256;            // [0,128): 2 accumulators x 6
 constexpr uint32_t T4_WCOL = 128;
 
 struct Seq4Smem {
-  uint32_t wres, chunk, full0, wbar, tfull0, tempty0;
+  uint32_t wres, chunk, full0, wbar, tfull0, tempty0, started0;
   uint32_t* tmem_slot;
   float* S;  // [2 teams][128][T4_SLD]
 };
@@ -1077,7 +1077,8 @@ __device__ __forceinline__ Seq4Smem seq4_smem(uint8_t* smem_raw) {
   s.wbar = smem_u32(bars + T4_MAXCH * MAX_RES_KB);
   s.tfull0 = smem_u32(bars + T4_MAXCH * MAX_RES_KB + 1);           // [chain]
   s.tempty0 = smem_u32(bars + T4_MAXCH * MAX_RES_KB + 1 + T4_MAXCH);
-  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + T4_MAXCH * MAX_RES_KB + 1 + 2 * T4_MAXCH);
+  s.started0 = smem_u32(bars + T4_MAXCH * MAX_RES_KB + 1 + 2 * T4_MAXCH);
+  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + T4_MAXCH * MAX_RES_KB + 1 + 3 * T4_MAXCH);
   return s;
 }
 static int seq4_smem_bytes() { return T4_WSMEM + T4_MAXCH * T4_CHUNK + T4_MAXCH * T4_SBYTES + 1024 + 256; }
@@ -1119,7 +1120,7 @@ lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   if (threadIdx.x == 0) {
     for (int i = 0; i < T4_MAXCH * MAX_RES_KB; i++) mbar_init(sm.full0 + 8 * i, 1);
     mbar_init(sm.wbar, 1);
-    for (int c = 0; c < T4_MAXCH; c++) { mbar_init(sm.tfull0 + 8 * c, 1); mbar_init(sm.tempty0 + 8 * c, 1); }
+    for (int c = 0; c < T4_MAXCH; c++) { mbar_init(sm.tfull0 + 8 * c, 2); mbar_init(sm.tempty0 + 8 * c, 1); mbar_init(sm.started0 + 8 * c, 1); }
     mbar_init_fence();
   }
   if (warp == 0 && lane == 0) { prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmA_lo); prefetch_tensormap(&tmB_hi); prefetch_tensormap(&tmB_lo); }
@@ -1175,23 +1176,59 @@ lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   pdl_trigger();
 
   if (warp < T4_MAXCH) {
-    // ===================== TMA producers: warp c serves chain c =====================
-    const int c = warp;
-    if (lane == 0 && c < nch) {
+    // ===================== TMA producers: warp c serves chain c -- and issues the SECOND half of the chain's MMAs =====================
+    // 32 dependent-issue MMAs at ~80 clk each were the longest phase of a step.  The producer warp is idle between its TMA
+    // issue and the next grid barrier, so it issues k-blocks [num_kb/2, num_kb) into the SAME accumulator while the issuer
+    // warp does [0, num_kb/2): tcgen05.mma executes in issue order, so accumulating from two threads is safe once the
+    // issuer's first MMA of the step (the one that overwrites the accumulator) has been issued (`started` barrier).
+    const int c = __shfl_sync(0xffffffffu, warp, 0);
+    if (c < nch) {
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t idesc = idesc_bf16(128, 2 * T4_ROWS, false, false);
+      const uint32_t acc = tb + (uint32_t)(2 * T4_ROWS * c);
       const uint32_t buf = sm.chunk + (uint32_t)c * T4_CHUNK;
       const uint32_t fullc = sm.full0 + 8 * (c * MAX_RES_KB);
+      const int kb_split = (num_kb + 1) / 2;
+      mbar_wait(sm.wbar, 0);
       for (int t = 1; t < T; t++) {
-        grid_wait(ctr + c, (unsigned int)t * ctas_per_mtile);  // h_{t-1} rows of this chain are complete; the cluster's MMAs of step t-1 are done
-        T4_TRACE(c, 0);
-        fence_proxy_async_global();
-        const int arow = t * B + m0 + T4_ROWS * c;  // slot t of hs = h_{t-1}
-        for (int kb = 0; kb < num_kb; kb++) mbar_expect_tx(fullc + 8 * kb, T4_BSTAGE);
-        for (int kb = (int)rank; kb < num_kb; kb += CL) {  // k-block kb is fetched by rank kb % CL and multicast to the cluster
-          const uint32_t st = buf + kb * T4_BSTAGE;
-          tma_load_2d_mcast(st, &tmA_hi, fullc + 8 * kb, kb * LBK, arow, (uint16_t)((1u << CL) - 1));
-          tma_load_2d_mcast(st + T4_BHALF, &tmA_lo, fullc + 8 * kb, kb * LBK, arow, (uint16_t)((1u << CL) - 1));
+        if (lane == 0) {
+          grid_wait(ctr + c, (unsigned int)t * ctas_per_mtile);  // h_{t-1} rows of this chain are complete; the cluster's MMAs of step t-1 are done
+          T4_TRACE(c, 0);
+          fence_proxy_async_global();
+          const int arow = t * B + m0 + T4_ROWS * c;  // slot t of hs = h_{t-1}
+          for (int kb = 0; kb < num_kb; kb++) mbar_expect_tx(fullc + 8 * kb, T4_BSTAGE);
+          for (int kb = (int)rank; kb < num_kb; kb += CL) {  // k-block kb is fetched by rank kb % CL and multicast to the cluster
+            const uint32_t st = buf + kb * T4_BSTAGE;
+            tma_load_2d_mcast(st, &tmA_hi, fullc + 8 * kb, kb * LBK, arow, (uint16_t)((1u << CL) - 1));
+            tma_load_2d_mcast(st + T4_BHALF, &tmA_lo, fullc + 8 * kb, kb * LBK, arow, (uint16_t)((1u << CL) - 1));
+          }
+          T4_TRACE(c, 1);
         }
-        T4_TRACE(c, 1);
+        __syncwarp();
+        // second half of the k-blocks (converged warp, elected lane: see elect_one())
+        mbar_wait(sm.started0 + 8 * c, (t - 1) & 1);  // the issuer warp has issued this step's first (overwriting) MMA
+        tc_fence_after();
+        for (int kb = kb_split; kb < num_kb; kb++) {
+          mbar_wait(fullc + 8 * kb, (t - 1) & 1);
+          tc_fence_after();
+          const uint32_t b_lo = desc_lo_kmajor(buf + kb * T4_BSTAGE);
+          if (kb < T4_KB_TMEM) {
+            const uint32_t a_col = tb + T4_WCOL + (uint32_t)(kb * (LBK / 2));
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < LBK / 16; k++) umma_bf16_ts(acc, a_col + 8u * k, b_lo + 2u * k, idesc, 1u);
+            }
+          } else {
+            const uint32_t a_lo = desc_lo_kmajor(sm.wres + (kb - T4_KB_TMEM) * 2 * B_HALF);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < LBK / 16; k++) umma_bf16_lo(acc, a_lo + 2u * k, b_lo + 2u * k, idesc, 1u);
+            }
+          }
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit(sm.tfull0 + 8 * c);  // tfull counts two commits: this warp's and the issuer warp's
+        __syncwarp();
       }
     }
   } else if (warp < 2 * T4_MAXCH) {
@@ -1212,10 +1249,11 @@ lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
           for (int kb = 0; kb < num_kb; kb++) { mbar_wait(fullc + 8 * kb, (t - 1) & 1); if (kb == 0 && lane == 0) T4_TRACE(c, 2); }
           if (lane == 0) T4_TRACE(c, 3);
         }
-        for (int kb = 0; kb < num_kb; kb++) {
+        const int kb_split = (num_kb + 1) / 2;  // this warp: k-blocks [0, kb_split); the producer warp: the rest
+        for (int kb = 0; kb < kb_split; kb++) {
           if (!(p.sync_flags & 8)) {
             mbar_wait(fullc + 8 * kb, (t - 1) & 1);
-            if (lane == 0) { if (kb == 0) T4_TRACE(c, 2); else if (kb == num_kb - 1) T4_TRACE(c, 3); }
+            if (lane == 0) { if (kb == 0) T4_TRACE(c, 2); else if (kb == kb_split - 1) T4_TRACE(c, 3); }
           }
           tc_fence_after();
           const uint32_t b_lo = desc_lo_kmajor(buf + kb * T4_BSTAGE);
@@ -1224,6 +1262,7 @@ lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
             if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < LBK / 16; k++) umma_bf16_ts(acc, a_col + 8u * k, b_lo + 2u * k, idesc, (kb | k) ? 1u : 0u);
+              if (kb == 0) mbar_arrive(sm.started0 + 8 * c);
             }
           } else {
             const uint32_t a_lo = desc_lo_kmajor(sm.wres + (kb - T4_KB_TMEM) * 2 * B_HALF);
