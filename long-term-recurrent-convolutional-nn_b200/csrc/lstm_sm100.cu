@@ -1369,7 +1369,7 @@ lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
           // first publish by about half a step makes one chain compute while the other communicates; nothing pulls them back.
           if (t == 0 && c == 1 && nch > 1 && !(p.sync_flags & 16)) {
             const unsigned long long t0 = gtime();
-            while (gtime() - t0 < (unsigned long long)(p.sync_flags >> 8 ? (p.sync_flags >> 8) : 2600)) {}
+            while (gtime() - t0 < (unsigned long long)(p.sync_flags >> 8 ? (p.sync_flags >> 8) : 2000)) {}
           }
           if (t > 0) mbar_arrive(sm.tempty0 + 8 * c);
           if (t + 1 < T) { fence_proxy_async_global(); grid_arrive(ctr + c); }
@@ -1668,7 +1668,7 @@ constexpr uint32_t B4_TMEM_COLS = 512;              // [0,128): 2 accumulators x
 constexpr uint32_t B4_WCOL = 128;
 
 struct Bwd4Smem {
-  uint32_t chunk, full0, tfull0, tempty0, redfull0;
+  uint32_t chunk, full0, tfull0, tempty0, redfull0, started0;
   uint32_t* tmem_slot;
   float* S;    // [2 teams][128][T4_SLD]
   float* red;  // [2 chains][CL src][2 parts][16][T4_SLD]
@@ -1686,7 +1686,8 @@ __device__ __forceinline__ Bwd4Smem bwd4_smem(uint8_t* smem_raw) {
   s.tfull0 = smem_u32(bars + T4_MAXCH * MAX_RES_KB);               // [chain]
   s.tempty0 = smem_u32(bars + T4_MAXCH * MAX_RES_KB + T4_MAXCH);
   s.redfull0 = smem_u32(bars + T4_MAXCH * MAX_RES_KB + 2 * T4_MAXCH);
-  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + T4_MAXCH * MAX_RES_KB + 3 * T4_MAXCH);
+  s.started0 = smem_u32(bars + T4_MAXCH * MAX_RES_KB + 3 * T4_MAXCH);
+  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + T4_MAXCH * MAX_RES_KB + 4 * T4_MAXCH);
   return s;
 }
 static int bwd4_smem_bytes() { return T4_MAXCH * T4_CHUNK + T4_MAXCH * T4_SBYTES + T4_MAXCH * B4_RED + 1024 + 256; }
@@ -1714,7 +1715,9 @@ lstm_bwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < T4_MAXCH * MAX_RES_KB; i++) mbar_init(sm.full0 + 8 * i, 1);
-    for (int c = 0; c < T4_MAXCH; c++) { mbar_init(sm.tfull0 + 8 * c, 1); mbar_init(sm.tempty0 + 8 * c, 1); mbar_init(sm.redfull0 + 8 * c, 1); }
+    for (int c = 0; c < T4_MAXCH; c++) {
+      mbar_init(sm.tfull0 + 8 * c, 2); mbar_init(sm.tempty0 + 8 * c, 1); mbar_init(sm.redfull0 + 8 * c, 1); mbar_init(sm.started0 + 8 * c, 1);
+    }
     mbar_init_fence();
   }
   if (warp == 0 && lane == 0) { prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmA_lo); }
@@ -1757,23 +1760,46 @@ lstm_bwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   pdl_trigger();
 
   if (warp < T4_MAXCH) {
-    // ===================== TMA producers: warp c serves chain c =====================
-    const int c = warp;
-    if (lane == 0 && c < nch && nkb > 0) {
+    // ===================== TMA producers: warp c serves chain c -- and issues the second half of the chain's MMAs (see the forward kernel) =====================
+    const int c = __shfl_sync(0xffffffffu, warp, 0);
+    if (c < nch && nkb > 0) {
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t idesc = idesc_bf16(128, 2 * T4_ROWS, false, false);
+      const uint32_t acc = tb + (uint32_t)(2 * T4_ROWS * c);
       const uint32_t buf = sm.chunk + (uint32_t)c * T4_CHUNK;
       const uint32_t fullc = sm.full0 + 8 * (c * MAX_RES_KB);
-      for (int t = T - 2; t >= 0; t--) {
-        grid_wait(ctr + c, (unsigned int)(T - 1 - t) * ctas_per_mtile);  // dG_{t+1} rows of this chain are complete
-        T4_TRACE(c, 0);
-        fence_proxy_async_global();
-        const int arow = (t + 1) * B + m0 + T4_ROWS * c;
-        for (int i = 0; i < nkb; i++) {
-          const uint32_t full = fullc + 8 * i, st = buf + i * T4_BSTAGE;
-          mbar_expect_tx(full, T4_BSTAGE);
-          tma_load_2d(st, &tmA_hi, full, (kb_begin + i) * LBK, arow);
-          tma_load_2d(st + T4_BHALF, &tmA_lo, full, (kb_begin + i) * LBK, arow);
+      const int kb_split = (nkb + 1) / 2;
+      int n = 0;
+      for (int t = T - 2; t >= 0; t--, n++) {
+        if (lane == 0) {
+          grid_wait(ctr + c, (unsigned int)(T - 1 - t) * ctas_per_mtile);  // dG_{t+1} rows of this chain are complete
+          T4_TRACE(c, 0);
+          fence_proxy_async_global();
+          const int arow = (t + 1) * B + m0 + T4_ROWS * c;
+          for (int i = 0; i < nkb; i++) {
+            const uint32_t full = fullc + 8 * i, st = buf + i * T4_BSTAGE;
+            mbar_expect_tx(full, T4_BSTAGE);
+            tma_load_2d(st, &tmA_hi, full, (kb_begin + i) * LBK, arow);
+            tma_load_2d(st + T4_BHALF, &tmA_lo, full, (kb_begin + i) * LBK, arow);
+          }
+          T4_TRACE(c, 1);
         }
-        T4_TRACE(c, 1);
+        __syncwarp();
+        mbar_wait(sm.started0 + 8 * c, n & 1);  // the issuer warp has issued this step's first (overwriting) MMA
+        tc_fence_after();
+        for (int i = kb_split; i < nkb; i++) {
+          mbar_wait(fullc + 8 * i, n & 1);
+          tc_fence_after();
+          const uint32_t b_lo = desc_lo_kmajor(buf + i * T4_BSTAGE);
+          const uint32_t a_col = tb + B4_WCOL + (uint32_t)(i * (LBK / 2));
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < LBK / 16; k++) umma_bf16_ts(acc, a_col + 8u * k, b_lo + 2u * k, idesc, 1u);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit(sm.tfull0 + 8 * c);  // tfull counts two commits
+        __syncwarp();
       }
     }
   } else if (warp < 2 * T4_MAXCH) {
@@ -1789,15 +1815,17 @@ lstm_bwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       for (int t = T - 2; t >= 0; t--, n++) {
         if (n >= 1) mbar_wait(sm.tempty0 + 8 * c, (n - 1) & 1);  // the epilogue of the previous step has drained this accumulator
         tc_fence_after();
-        for (int i = 0; i < nkb; i++) {
+        const int kb_split = (nkb + 1) / 2;  // this warp: k-blocks [0, kb_split); the producer warp: the rest
+        for (int i = 0; i < kb_split; i++) {
           mbar_wait(fullc + 8 * i, n & 1);
-          if (lane == 0) { if (i == 0) T4_TRACE(c, 2); else if (i == nkb - 1) T4_TRACE(c, 3); }
+          if (lane == 0) { if (i == 0) T4_TRACE(c, 2); else if (i == kb_split - 1) T4_TRACE(c, 3); }
           tc_fence_after();
           const uint32_t b_lo = desc_lo_kmajor(buf + i * T4_BSTAGE);
           const uint32_t a_col = tb + B4_WCOL + (uint32_t)(i * (LBK / 2));
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < LBK / 16; k++) umma_bf16_ts(acc, a_col + 8u * k, b_lo + 2u * k, idesc, (i | k) ? 1u : 0u);
+            if (i == 0) mbar_arrive(sm.started0 + 8 * c);
           }
           __syncwarp();
         }
@@ -1927,7 +1955,7 @@ lstm_bwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
             // anti-phase the two chains once (see lstm_fwd_seq4_kernel)
             if (t == T - 1 && c == 1 && nch > 1 && !(p.sync_flags & 16)) {
               const unsigned long long t0 = gtime();
-              while (gtime() - t0 < (unsigned long long)(p.sync_flags >> 8 ? (p.sync_flags >> 8) : 4000)) {}
+              while (gtime() - t0 < (unsigned long long)(p.sync_flags >> 8 ? (p.sync_flags >> 8) : 2800)) {}
             }
             fence_proxy_async_global(); grid_arrive(ctr + c);
           }
