@@ -1369,7 +1369,7 @@ lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
           // first publish by about half a step makes one chain compute while the other communicates; nothing pulls them back.
           if (t == 0 && c == 1 && nch > 1 && !(p.sync_flags & 16)) {
             const unsigned long long t0 = gtime();
-            while (gtime() - t0 < (unsigned long long)(p.sync_flags >> 8 ? (p.sync_flags >> 8) : 2000)) {}
+            while (gtime() - t0 < (unsigned long long)(p.sync_flags >> 8 ? (p.sync_flags >> 8) : 2800)) {}
           }
           if (t > 0) mbar_arrive(sm.tempty0 + 8 * c);
           if (t + 1 < T) { fence_proxy_async_global(); grid_arrive(ctr + c); }
