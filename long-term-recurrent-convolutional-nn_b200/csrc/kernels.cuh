@@ -184,6 +184,12 @@ void dp_p2p_adam(cudaStream_t s, const P2PPeers& peers, size_t n_floats, unsigne
                  const StepScalars* sc);
 // [begin, end) of rank r's shard, in floats
 void dp_p2p_shard(size_t n_floats, int nranks, int r, size_t* begin, size_t* end);
+// copy-engine exchange (dp_p2p.cu): flag barrier on one of 4 independent flag sets; owner-side sum of the staged
+// contributions + Adam over the arena range [b, e) (floats, multiples of 4); stage rows have `stride` floats, the range's
+// contributions start at stage_off inside a row
+void dp_xgpu_barrier(cudaStream_t s, const P2PPeers& peers, unsigned int* epoch_ctr, int flagset);
+void dp_adam_staged(cudaStream_t s, float* w, float* g, float* m, float* v, const float* stage, size_t stride, size_t stage_off, size_t b, size_t e,
+                    const P2PPeers& peers, const StepScalars* sc, double* loss_total);
 // diagnostics (probe_mma.cu): clocks to issue / to complete a chain of n_mma tcgen05.mma M x N x 16 from resident smem operands
 bool probe_mma(cudaStream_t s, int M, int N, int n_mma, int commit_every, int issuers, long long* issue_clk, long long* total_clk);
 

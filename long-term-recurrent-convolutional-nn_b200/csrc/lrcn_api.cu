@@ -160,7 +160,7 @@ static int s_destroy(lrcn_handle* h) {
   if (!h->peers_direct) for (void* q : h->p2p_opened) if (q) cudaIpcCloseMemHandle(q);
   for (cudaEvent_t e : h->sc_ev) if (e) cudaEventDestroy(e);
   void* ptrs[] = {h->w, h->g, h->m, h->v, h->w_hi, h->w_lo, h->wp1_hi, h->wp1_lo, h->wp2_hi, h->wp2_lo, h->wt1_hi, h->wt1_lo, h->wt2_hi, h->wt2_lo, h->tab[0].d, h->tab[1].d, h->ws.f, h->ws.hi, h->ws.lo, h->d_tok_in,
-                  h->d_tok_tgt, h->d_rows, h->d_sc, h->p2p_ctl, h->d_loss_total, h->d_epoch, h->d_counters, h->d_trace, h->g_last, h->g_ctok, h->g_stok, h->g_spar, h->g_hista, h->g_histb,
+                  h->d_tok_tgt, h->d_rows, h->d_sc, h->p2p_ctl, h->d_loss_total, h->d_epoch, h->d_epoch_side, h->stage, h->d_counters, h->d_trace, h->g_last, h->g_ctok, h->g_stok, h->g_spar, h->g_hista, h->g_histb,
                   h->g_done, h->g_ndone, h->g_olen, h->g_rows, h->g_otok, h->l2_scratch};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& s : h->slots) { if (s.tok_in) cudaFree(s.tok_in); if (s.tok_tgt) cudaFree(s.tok_tgt); if (s.rows) cudaFree(s.rows); }
@@ -279,6 +279,8 @@ static int create_impl(const lrcn_config* cfg, lrcn_handle* h) {
   CK(cudaMalloc(&h->p2p_ctl, 4096)); CK(cudaMemset(h->p2p_ctl, 0, 4096));
   h->d_loss = &h->p2p_ctl->loss_partial;
   CK(cudaMalloc(&h->d_loss_total, 8)); CK(cudaMalloc(&h->d_epoch, 4)); CK(cudaMemset(h->d_epoch, 0, 4));
+  CK(cudaMalloc(&h->d_epoch_side, 4)); CK(cudaMemset(h->d_epoch_side, 0, 4));
+  CK(cudaMalloc(&h->stage, (h->P + 1024) * 4));  // N staging rows of ~P/N floats each for the copy-engine gradient exchange
   CK(cudaMallocHost(&h->h_loss, 8));
   CK(cudaMalloc(&h->d_counters, 320 * sizeof(unsigned int)));  // [0,256): 4 LSTM launches x 64 (half-)tile barriers; [256,..): softmax
   CK(cudaMemset(h->d_counters, 0, 320 * sizeof(unsigned int)));
@@ -348,7 +350,7 @@ static int create_group(const lrcn_config* cfg, lrcn_handle* g) {
     pe.nranks = N; pe.rank = i;
     for (int p = 0; p < N; p++) {
       lrcn_handle* q = g->members[p];
-      pe.g[p] = q->g; pe.w[p] = q->w; pe.ctl[p] = q->p2p_ctl; m->peer_m[p] = q->m; m->peer_v[p] = q->v;
+      pe.g[p] = q->g; pe.w[p] = q->w; pe.ctl[p] = q->p2p_ctl; m->peer_m[p] = q->m; m->peer_v[p] = q->v; m->peer_stage[p] = q->stage;
     }
     m->peers = pe;
     m->peers_direct = true;
@@ -439,13 +441,34 @@ static int s_get_param(lrcn_handle* h, int idx, float* p, int64_t rows, int64_t 
 }
 // Peer-memory data parallelism (dp_p2p.cu) leaves m, v -- and after a sharded train step the summed gradient -- current only
 // in each owner's shard: collect the other shards from their owners.  All ranks must be idle (e.g. at a checkpoint barrier).
+// copy-engine exchange: every gradient bucket k (arena range [bucket_off[k], bucket_off[k+1])) is split into N slices of
+// per_k floats (multiples of 4); rank r owns [b, e) of it and its contributions sit at row offset pre_k of a staging row
+struct BucketShard { size_t b, e, pre, per; };
+static BucketShard bucket_shard(const lrcn_handle* h, int k, int r) {
+  BucketShard s{};
+  const int N = h->nranks;
+  size_t pre = 0;
+  for (int kk = 0; kk <= k; kk++) {
+    const size_t n4 = (h->bucket_off[kk + 1] - h->bucket_off[kk]) / 4, per4 = (n4 + N - 1) / N;
+    if (kk == k) {
+      const size_t b4 = per4 * r < n4 ? per4 * r : n4, e4 = b4 + per4 < n4 ? b4 + per4 : n4;
+      s.b = h->bucket_off[k] + 4 * b4; s.e = h->bucket_off[k] + 4 * e4; s.pre = pre; s.per = 4 * per4;
+    }
+    pre += 4 * per4;
+  }
+  return s;
+}
+static size_t stage_stride(const lrcn_handle* h) { return bucket_shard(h, 2, 0).pre + bucket_shard(h, 2, 0).per; }
+
 static int gather_shards(lrcn_handle* h, bool adam, bool grad) {
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaStreamSynchronize(h->stream));
   for (int r = 0; r < h->nranks; r++) {
     if (r == h->rank) continue;
+    for (int k = 0; k < (h->shard_by_bucket ? 3 : 1); k++) {
     size_t b, e;
-    dp_p2p_shard(h->P, h->nranks, r, &b, &e);
+    if (h->shard_by_bucket) { const BucketShard bs = bucket_shard(h, k, r); b = bs.b; e = bs.e; }
+    else dp_p2p_shard(h->P, h->nranks, r, &b, &e);
     if (e <= b) continue;
     // on the handle's stream: device-to-device cudaMemcpy does not synchronise the host, and the download that follows is stream-ordered
     if (adam) {
@@ -453,6 +476,7 @@ static int gather_shards(lrcn_handle* h, bool adam, bool grad) {
       CK(cudaMemcpyAsync(h->v + b, h->peer_v[r] + b, (e - b) * 4, cudaMemcpyDefault, h->stream));
     }
     if (grad) CK(cudaMemcpyAsync(h->g + b, h->peers.g[r] + b, (e - b) * 4, cudaMemcpyDefault, h->stream));
+    }
   }
   CK(cudaStreamSynchronize(h->stream));
   if (adam) h->adam_sharded = false;
@@ -785,8 +809,46 @@ static int run_step(lrcn_handle* h, int split, int B, int l, float pdrop, uint64
   if (h->p2p_ready && !force_nccl) {
     h->loss_is_total = true;
     static const bool replicated = getenv("LRCN_DP_REPLICATED_ADAM") != nullptr;
-    if (mode == 2 && !replicated) h->adam_sharded = h->grad_sharded = true;
+    static const bool kernel_exchange = getenv("LRCN_DP_KERNEL_EXCHANGE") != nullptr;  // round-1 SM-driven exchange after the backward pass
+    if (mode == 2 && !replicated) { h->adam_sharded = h->grad_sharded = true; h->shard_by_bucket = !kernel_exchange; }
     else h->grad_sharded = false;
+    if (mode == 2 && !replicated && !kernel_exchange) {
+      // copy-engine exchange (dp_p2p.cu): bucket 1 (Wout, bout) travels under the layer-2 BPTT, bucket 2 (W2, b2, Wf, Wcnn)
+      // under the layer-1 BPTT on a side stream (a parallel branch of the step's graph); only bucket 3 (W1, b1, Wemb) is exposed
+      return run_cached(h, std::make_tuple(23, B, l, fl), [&] {
+        const size_t stride = stage_stride(h);
+        auto exchange_bucket = [&](int k, cudaStream_t st, unsigned int* epoch, int flagset, bool last) {
+          for (int r = 0; r < h->nranks; r++) {  // reduce-scatter: push my gradient slices to their owners
+            if (r == h->rank) continue;
+            const BucketShard bs = bucket_shard(h, k, r);
+            if (bs.e > bs.b) cudaMemcpyAsync(h->peer_stage[r] + (size_t)h->rank * stride + bs.pre, h->g + bs.b, (bs.e - bs.b) * 4, cudaMemcpyDeviceToDevice, st);
+          }
+          dp_xgpu_barrier(st, h->peers, epoch, flagset);  // every rank's pushes of this bucket have landed (and every rank is past its last use of the bucket's weights)
+          const BucketShard me = bucket_shard(h, k, h->rank);
+          if (me.e > me.b || last)
+            dp_adam_staged(st, h->w, h->g, h->m, h->v, h->stage, stride, me.pre, me.b, me.e, h->peers, h->d_sc, last ? h->d_loss_total : nullptr);
+          for (int r = 0; r < h->nranks; r++) {  // all-gather: push the new weights of my slice
+            if (r == h->rank || me.e <= me.b) continue;
+            cudaMemcpyAsync(h->peers.w[r] + me.b, h->w + me.b, (me.e - me.b) * 4, cudaMemcpyDeviceToDevice, st);
+          }
+        };
+        enqueue_forward(h, split, B, l, true);
+        enqueue_backward_seg(h, B, l, true, 1);
+        cudaEventRecord(h->ev_seg[0], h->stream);
+        cudaStreamWaitEvent(h->comm_stream, h->ev_seg[0], 0);
+        exchange_bucket(0, h->comm_stream, h->d_epoch_side, 1, false);
+        enqueue_backward_seg(h, B, l, true, 2);
+        cudaEventRecord(h->ev_seg[1], h->stream);
+        cudaStreamWaitEvent(h->comm_stream, h->ev_seg[1], 0);
+        exchange_bucket(1, h->comm_stream, h->d_epoch_side, 1, false);
+        cudaEventRecord(h->ev_comm, h->comm_stream);
+        enqueue_backward_seg(h, B, l, true, 3);
+        exchange_bucket(2, h->stream, h->d_epoch, 0, true);
+        cudaStreamWaitEvent(h->stream, h->ev_comm, 0);
+        dp_xgpu_barrier(h->stream, h->peers, h->d_epoch, 0);  // every owner's new weights have landed everywhere
+        if (h->bf16mode) split_bf16(h->stream, h->w, h->P, h->w_hi, h->w_lo);
+      });
+    }
     // backward pass, then ONE owner-computes exchange kernel over NVLink peer memory between two flag barriers (dp_p2p.cu),
     // then the replicated Adam: no NCCL kernels competing for SMs with the persistent GEMM / LSTM kernels
     return run_cached(h, std::make_tuple(mode == 2 ? 22 : 21, B, l, fl), [&] {
@@ -1156,7 +1218,7 @@ static int s_comm_init(lrcn_handle* h, const char id[LRCN_COMM_ID_BYTES], int ra
 struct P2PBlob {  // LRCN_P2P_BLOB_BYTES
   int magic, device;
   unsigned long long arena_floats;
-  cudaIpcMemHandle_t g, ctl, w, m, v;
+  cudaIpcMemHandle_t g, ctl, w, m, v, stage;
 };
 static_assert(sizeof(P2PBlob) <= LRCN_P2P_BLOB_BYTES, "blob too large");
 static int s_p2p_export(lrcn_handle* h, char blob[LRCN_P2P_BLOB_BYTES]) {
@@ -1170,6 +1232,7 @@ static int s_p2p_export(lrcn_handle* h, char blob[LRCN_P2P_BLOB_BYTES]) {
   CK(cudaIpcGetMemHandle(&b.w, h->w));
   CK(cudaIpcGetMemHandle(&b.m, h->m));
   CK(cudaIpcGetMemHandle(&b.v, h->v));
+  CK(cudaIpcGetMemHandle(&b.stage, h->stage));
   memset(blob, 0, LRCN_P2P_BLOB_BYTES);
   memcpy(blob, &b, sizeof b);
   return LRCN_OK;
@@ -1186,16 +1249,17 @@ static int s_p2p_import(lrcn_handle* h, const char* blobs, int rank, int nranks)
     P2PBlob b;
     memcpy(&b, blobs + (size_t)p * LRCN_P2P_BLOB_BYTES, sizeof b);
     if (b.magic != 0x4C524350 || b.arena_floats != h->P) return fail(LRCN_ERR_ARG, "blob %d does not describe a handle of this model", p);
-    if (p == rank) { pe.g[p] = h->g; pe.w[p] = h->w; pe.ctl[p] = h->p2p_ctl; h->peer_m[p] = h->m; h->peer_v[p] = h->v; continue; }
-    void* q[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    const cudaIpcMemHandle_t hs[5] = {b.g, b.ctl, b.w, b.m, b.v};
-    for (int k = 0; k < 5; k++) {
+    if (p == rank) { pe.g[p] = h->g; pe.w[p] = h->w; pe.ctl[p] = h->p2p_ctl; h->peer_m[p] = h->m; h->peer_v[p] = h->v; h->peer_stage[p] = h->stage; continue; }
+    void* q[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    const cudaIpcMemHandle_t hs[6] = {b.g, b.ctl, b.w, b.m, b.v, b.stage};
+    for (int k = 0; k < 6; k++) {
       cudaError_t e = cudaIpcOpenMemHandle(&q[k], hs[k], cudaIpcMemLazyEnablePeerAccess);
       if (e != cudaSuccess)
         return fail(LRCN_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d, device %d) -> %s (peer access over NVLink required)", p, b.device, cudaGetErrorString(e));
-      h->p2p_opened[5 * p + k] = q[k];
+      h->p2p_opened[6 * p + k] = q[k];
     }
     pe.g[p] = (float*)q[0]; pe.ctl[p] = (P2PCtl*)q[1]; pe.w[p] = (float*)q[2]; h->peer_m[p] = (float*)q[3]; h->peer_v[p] = (float*)q[4];
+    h->peer_stage[p] = (float*)q[5];
     if (getenv("LRCN_P2P_DEBUG")) fprintf(stderr, "[lrcn p2p] rank %d maps rank %d: g %p ctl %p w %p m %p v %p\n", rank, p, q[0], q[1], q[2], q[3], q[4]);
   }
   h->peers = pe;

@@ -86,10 +86,15 @@ struct lrcn_handle {
   P2PPeers peers{};
   bool p2p_ready = false;
   bool loss_is_total = false;       // last step summed the loss over ranks into d_loss_total
-  void* p2p_opened[5 * LRCN_P2P_MAX_RANKS] = {};  // IPC mappings to close
+  void* p2p_opened[6 * LRCN_P2P_MAX_RANKS] = {};  // IPC mappings to close
   float* peer_m[LRCN_P2P_MAX_RANKS] = {};
   float* peer_v[LRCN_P2P_MAX_RANKS] = {};
   bool adam_sharded = false;          // m, v are current only in each owner's shard (gathered on lrcn_get_adam_state)
+  // copy-engine exchange (dp_p2p.cu): staging rows for the gradient slices the peers push to this rank, and the peers' rows
+  float* stage = nullptr;
+  float* peer_stage[LRCN_P2P_MAX_RANKS] = {};
+  bool shard_by_bucket = false;       // how the last sharded step split the arena: per gradient bucket (copy engines) or as a whole
+  unsigned int* d_epoch_side = nullptr;  // epoch counter of the side-stream barriers
   unsigned int* d_counters = nullptr;  // per-m-tile grid-barrier counters of the persistent LSTM kernels
   unsigned long long* d_trace = nullptr;  // LRCN_SEQ_TRACE=1: per-step timeline of the layer-2 forward sequence kernel
   Slot slots[64];
