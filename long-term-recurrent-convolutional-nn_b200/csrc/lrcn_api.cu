@@ -169,6 +169,8 @@ static int s_destroy(lrcn_handle* h) {
   if (h->h_loss) cudaFreeHost(h->h_loss);
   if (h->h_ndone) cudaFreeHost(h->h_ndone);
   for (cudaEvent_t e : {h->ev0, h->ev1, h->ev_seg[0], h->ev_seg[1], h->ev_seg[2], h->ev_comm}) if (e) cudaEventDestroy(e);
+  if (h->ev_xfork) cudaEventDestroy(h->ev_xfork);
+  for (int i = 0; i < lrcn_handle::NXFER; i++) { if (h->ev_xjoin[i]) cudaEventDestroy(h->ev_xjoin[i]); if (h->xfer[i]) cudaStreamDestroy(h->xfer[i]); }
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -212,6 +214,11 @@ static int create_impl(const lrcn_config* cfg, lrcn_handle* h) {
   CK(cudaEventCreate(&h->ev1));
   for (int i = 0; i < 3; i++) CK(cudaEventCreateWithFlags(&h->ev_seg[i], cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_xfork, cudaEventDisableTiming));
+  for (int i = 0; i < lrcn_handle::NXFER; i++) {
+    CK(cudaStreamCreateWithFlags(&h->xfer[i], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_xjoin[i], cudaEventDisableTiming));
+  }
 
   // ---- parameter arenas, bucket order (1-based model index): [8,9 | 3,4,5,6 | 1,2,7]
   const int order[9] = {8, 9, 3, 4, 5, 6, 1, 2, 7};
@@ -817,19 +824,32 @@ static int run_step(lrcn_handle* h, int split, int B, int l, float pdrop, uint64
       // under the layer-1 BPTT on a side stream (a parallel branch of the step's graph); only bucket 3 (W1, b1, Wemb) is exposed
       return run_cached(h, std::make_tuple(23, B, l, fl), [&] {
         const size_t stride = stage_stride(h);
+        // the N-1 copies of a phase run on parallel branches of the graph (several DMA engines), forked from / joined into `st`
+        auto parallel_copies = [&](cudaStream_t st, auto&& issue /* (rank r, stream) */) {
+          if (h->nranks <= 2) { for (int r = 0; r < h->nranks; r++) if (r != h->rank) issue(r, st); return; }
+          cudaEventRecord(h->ev_xfork, st);
+          for (int i = 0; i < lrcn_handle::NXFER; i++) cudaStreamWaitEvent(h->xfer[i], h->ev_xfork, 0);
+          int n = 0;
+          for (int d = 1; d < h->nranks; d++, n++) issue((h->rank + d) % h->nranks, h->xfer[n % lrcn_handle::NXFER]);  // staggered targets: no two ranks start on the same peer
+          for (int i = 0; i < lrcn_handle::NXFER; i++) { cudaEventRecord(h->ev_xjoin[i], h->xfer[i]); cudaStreamWaitEvent(st, h->ev_xjoin[i], 0); }
+        };
         auto exchange_bucket = [&](int k, cudaStream_t st, unsigned int* epoch, int flagset, bool last) {
-          for (int r = 0; r < h->nranks; r++) {  // reduce-scatter: push my gradient slices to their owners
-            if (r == h->rank) continue;
+          parallel_copies(st, [&](int r, cudaStream_t cs) {  // reduce-scatter: push my gradient slices to their owners
             const BucketShard bs = bucket_shard(h, k, r);
-            if (bs.e > bs.b) cudaMemcpyAsync(h->peer_stage[r] + (size_t)h->rank * stride + bs.pre, h->g + bs.b, (bs.e - bs.b) * 4, cudaMemcpyDeviceToDevice, st);
-          }
+            if (bs.e > bs.b) cudaMemcpyAsync(h->peer_stage[r] + (size_t)h->rank * stride + bs.pre, h->g + bs.b, (bs.e - bs.b) * 4, cudaMemcpyDeviceToDevice, cs);
+          });
           dp_xgpu_barrier(st, h->peers, epoch, flagset);  // every rank's pushes of this bucket have landed (and every rank is past its last use of the bucket's weights)
           const BucketShard me = bucket_shard(h, k, h->rank);
           if (me.e > me.b || last)
             dp_adam_staged(st, h->w, h->g, h->m, h->v, h->stage, stride, me.pre, me.b, me.e, h->peers, h->d_sc, last ? h->d_loss_total : nullptr);
-          for (int r = 0; r < h->nranks; r++) {  // all-gather: push the new weights of my slice
-            if (r == h->rank || me.e <= me.b) continue;
-            cudaMemcpyAsync(h->peers.w[r] + me.b, h->w + me.b, (me.e - me.b) * 4, cudaMemcpyDeviceToDevice, st);
+          if (me.e > me.b)
+            parallel_copies(st, [&](int r, cudaStream_t cs) {  // all-gather: push the new weights of my slice
+              cudaMemcpyAsync(h->peers.w[r] + me.b, h->w + me.b, (me.e - me.b) * 4, cudaMemcpyDeviceToDevice, cs);
+            });
+          dp_xgpu_barrier(st, h->peers, epoch, flagset);  // every owner's new weights of this bucket have landed everywhere
+          if (h->bf16mode) {  // refresh the bf16 hi / lo shadows of the bucket (the exposed pass shrinks to the last bucket)
+            const size_t b0 = h->bucket_off[k], n = h->bucket_off[k + 1] - b0;
+            split_bf16(st, h->w + b0, n, h->w_hi + b0, h->w_lo + b0);
           }
         };
         enqueue_forward(h, split, B, l, true);
@@ -844,9 +864,7 @@ static int run_step(lrcn_handle* h, int split, int B, int l, float pdrop, uint64
         cudaEventRecord(h->ev_comm, h->comm_stream);
         enqueue_backward_seg(h, B, l, true, 3);
         exchange_bucket(2, h->stream, h->d_epoch, 0, true);
-        cudaStreamWaitEvent(h->stream, h->ev_comm, 0);
-        dp_xgpu_barrier(h->stream, h->peers, h->d_epoch, 0);  // every owner's new weights have landed everywhere
-        if (h->bf16mode) split_bf16(h->stream, h->w, h->P, h->w_hi, h->w_lo);
+        cudaStreamWaitEvent(h->stream, h->ev_comm, 0);  // join the side branch
       });
     }
     // backward pass, then ONE owner-computes exchange kernel over NVLink peer memory between two flag barriers (dp_p2p.cu),

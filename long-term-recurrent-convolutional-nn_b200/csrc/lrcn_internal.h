@@ -95,6 +95,9 @@ struct lrcn_handle {
   float* peer_stage[LRCN_P2P_MAX_RANKS] = {};
   bool shard_by_bucket = false;       // how the last sharded step split the arena: per gradient bucket (copy engines) or as a whole
   unsigned int* d_epoch_side = nullptr;  // epoch counter of the side-stream barriers
+  static constexpr int NXFER = 4;        // parallel copy branches (so that several DMA engines work on the N-1 slices of a phase)
+  cudaStream_t xfer[NXFER] = {};
+  cudaEvent_t ev_xfork = nullptr, ev_xjoin[NXFER] = {};
   unsigned int* d_counters = nullptr;  // per-m-tile grid-barrier counters of the persistent LSTM kernels
   unsigned long long* d_trace = nullptr;  // LRCN_SEQ_TRACE=1: per-step timeline of the layer-2 forward sequence kernel
   Slot slots[64];
