@@ -207,6 +207,12 @@ void dp_adam_staged(cudaStream_t s, float* w, float* g, float* m, float* v, cons
                                           reinterpret_cast<const float4*>(stage), stride / 4, stage_off / 4, b / 4, e / 4, peers.nranks, peers.rank, sc, peers, loss_total);
   if (g_counter) g_counter->n++;
 }
+// SM-driven exchange of ONE arena range [b, e) owned by this rank (reduce-scatter + Adam + all-gather in one kernel, no
+// barriers: the caller brackets it with dp_xgpu_barrier).  grid_ctas bounds the SMs it may take.
+void dp_p2p_adam_range(cudaStream_t s, const P2PPeers& peers, size_t b, size_t e, float* m, float* v, const StepScalars* sc, double* loss_total, int grid_ctas) {
+  adam_p2p_kernel<<<grid_ctas, 256, 0, s>>>(peers, b / 4, e / 4, reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), sc, loss_total);
+  if (g_counter) g_counter->n++;
+}
 void dp_xgpu_barrier(cudaStream_t s, const P2PPeers& peers, unsigned int* epoch_ctr, int flagset) {
   xgpu_barrier_kernel<<<1, 32, 0, s>>>(peers, epoch_ctr, 16 * flagset);
   if (g_counter) g_counter->n++;

@@ -188,6 +188,7 @@ void dp_p2p_shard(size_t n_floats, int nranks, int r, size_t* begin, size_t* end
 // contributions + Adam over the arena range [b, e) (floats, multiples of 4); stage rows have `stride` floats, the range's
 // contributions start at stage_off inside a row
 void dp_xgpu_barrier(cudaStream_t s, const P2PPeers& peers, unsigned int* epoch_ctr, int flagset);
+void dp_p2p_adam_range(cudaStream_t s, const P2PPeers& peers, size_t b, size_t e, float* m, float* v, const StepScalars* sc, double* loss_total, int grid_ctas);
 void dp_adam_staged(cudaStream_t s, float* w, float* g, float* m, float* v, const float* stage, size_t stride, size_t stage_off, size_t b, size_t e,
                     const P2PPeers& peers, const StepScalars* sc, double* loss_total);
 // diagnostics (probe_mma.cu): clocks to issue / to complete a chain of n_mma tcgen05.mma M x N x 16 from resident smem operands

@@ -817,8 +817,42 @@ static int run_step(lrcn_handle* h, int split, int B, int l, float pdrop, uint64
     h->loss_is_total = true;
     static const bool replicated = getenv("LRCN_DP_REPLICATED_ADAM") != nullptr;
     static const bool kernel_exchange = getenv("LRCN_DP_KERNEL_EXCHANGE") != nullptr;  // round-1 SM-driven exchange after the backward pass
+    static const bool ce_exchange = getenv("LRCN_DP_CE") != nullptr;  // copy-engine exchange: measured slower (many small copies), kept for reference
     if (mode == 2 && !replicated) { h->adam_sharded = h->grad_sharded = true; h->shard_by_bucket = !kernel_exchange; }
     else h->grad_sharded = false;
+    if (mode == 2 && !replicated && !kernel_exchange && !ce_exchange) {
+      // Bucketed SM-driven exchange overlapped with the backward pass.  The owner-computes kernel of bucket 1 (Wout, bout) runs
+      // on a side stream (a parallel branch of the step's graph) under the layer-2 BPTT kernel, that of bucket 2 (W2, b2, Wf, Wcnn)
+      // under the layer-1 BPTT kernel: the persistent LSTM kernels hold 128 of the 148 SMs with one (register-file-filling) CTA
+      // each, so the exchange CTAs land on the 20 SMs they leave free -- and because every exchange starts with a cross-GPU flag
+      // barrier (a 1-warp kernel that co-resides anywhere), the LSTM grid is resident before the exchange kernel is launched.
+      // Only bucket 3 (W1, b1, Wemb), which is complete at the very end of the backward pass, is exposed.
+      return run_cached(h, std::make_tuple(24, B, l, fl), [&] {
+        auto exchange_bucket = [&](int k, cudaStream_t st, unsigned int* epoch, int flagset, bool last) {
+          dp_xgpu_barrier(st, h->peers, epoch, flagset);  // every rank's gradients of this bucket are complete, and every rank is past its last use of the bucket's weights
+          const BucketShard me = bucket_shard(h, k, h->rank);
+          if (me.e > me.b || last) dp_p2p_adam_range(st, h->peers, me.b, me.e, h->m, h->v, h->d_sc, last ? h->d_loss_total : nullptr, last ? 148 * 4 : 20 * 8);
+          dp_xgpu_barrier(st, h->peers, epoch, flagset);  // every owner's new weights of this bucket have landed everywhere
+          if (h->bf16mode) {
+            const size_t b0 = h->bucket_off[k], n = h->bucket_off[k + 1] - b0;
+            split_bf16(st, h->w + b0, n, h->w_hi + b0, h->w_lo + b0);
+          }
+        };
+        enqueue_forward(h, split, B, l, true);
+        enqueue_backward_seg(h, B, l, true, 1);
+        cudaEventRecord(h->ev_seg[0], h->stream);
+        cudaStreamWaitEvent(h->comm_stream, h->ev_seg[0], 0);
+        exchange_bucket(0, h->comm_stream, h->d_epoch_side, 1, false);
+        enqueue_backward_seg(h, B, l, true, 2);
+        cudaEventRecord(h->ev_seg[1], h->stream);
+        cudaStreamWaitEvent(h->comm_stream, h->ev_seg[1], 0);
+        exchange_bucket(1, h->comm_stream, h->d_epoch_side, 1, false);
+        cudaEventRecord(h->ev_comm, h->comm_stream);
+        enqueue_backward_seg(h, B, l, true, 3);
+        exchange_bucket(2, h->stream, h->d_epoch, 0, true);
+        cudaStreamWaitEvent(h->stream, h->ev_comm, 0);  // join the side branch
+      });
+    }
     if (mode == 2 && !replicated && !kernel_exchange) {
       // copy-engine exchange (dp_p2p.cu): bucket 1 (Wout, bout) travels under the layer-2 BPTT, bucket 2 (W2, b2, Wf, Wcnn)
       // under the layer-1 BPTT on a side stream (a parallel branch of the step's graph); only bucket 3 (W1, b1, Wemb) is exposed
