@@ -144,8 +144,22 @@ struct BeamAdvanceArgs {
   __nv_bfloat16 *h1_hi, *h1_lo, *h2_hi, *h2_lo;  // optional bf16 split of the gathered h states (null in fp32 mode)
   float* prob; int* last_tok; int* done; int* n_done;
   long long* out_tokens; int* out_len; float* out_prob; float* out_lp;
+  const int* out_map;  // compacted image index -> image index of the caller's chunk (outputs are written there); null = identity
 };
 void beam_advance(cudaStream_t s, const BeamAdvanceArgs& a);
+// Compaction of the generation batch: images whose best hypothesis has ended (lrcn.jl:670) leave the batch, the survivors'
+// K rows (states, histories, scores) and per-image data move to the front.  Two launches (gather into scratch, copy back)
+// because a parallel in-place move is not safe.
+struct BeamCompactArgs {
+  int n_keep, K, H1, H2, ld1, ld2, ldv, maxlen, hist_len;
+  const int* keep;                                   // [n_keep] old (compacted) image index of the survivors, ascending
+  float *h1, *c1, *h2, *c2;                          // current states: h with row pitch ld1 / ld2, c with H1 / H2
+  float *h1_s, *c1_s, *h2_s, *c2_s;                  // scratch, contiguous rows
+  __nv_bfloat16 *h1_hi, *h1_lo, *h2_hi, *h2_lo;      // bf16 split of h (row pitch ld1 / ld2), rebuilt on copy-back; may be null
+  const int* hist_src; int* hist_dst; const float* lp_src; float* lp_dst;   // ping-pong history buffers: gathered into the other one
+  float *prob, *prob_s; int *last, *last_s; float *v, *v_s; int *out_map, *out_map_s; int* done;
+};
+void beam_compact(cudaStream_t s, const BeamCompactArgs& a);
 
 // ---------------------------------------------------------------- tcgen05 path (gemm_sm100.cu)
 // Same contract as sgemm, operands given as pre-split bf16 hi/lo pairs (ld in elements, multiple of 8).

@@ -1222,13 +1222,14 @@ __global__ void __launch_bounds__(128) beam_advance_kernel(BeamAdvanceArgs a) {
     if (stop) {
       __syncthreads();
       int total = len + 1;
+      const int oimg = a.out_map ? a.out_map[img] : img;  // where the caller's chunk expects this image
       for (int j = threadIdx.x; j < total; j += blockDim.x) {
-        a.out_tokens[(size_t)img * a.maxlen + j] = (long long)a.hist_out[(size_t)r * a.maxlen + j] + 1;
-        if (a.out_lp && j >= 1) a.out_lp[(size_t)img * (a.maxlen - 1) + (j - 1)] = a.lp_out[(size_t)r * a.maxlen + j];
+        a.out_tokens[(size_t)oimg * a.maxlen + j] = (long long)a.hist_out[(size_t)r * a.maxlen + j] + 1;
+        if (a.out_lp && j >= 1) a.out_lp[(size_t)oimg * (a.maxlen - 1) + (j - 1)] = a.lp_out[(size_t)r * a.maxlen + j];
       }
       if (threadIdx.x == 0) {
-        a.out_len[img] = total;
-        a.out_prob[img] = a.sel_score[r];
+        a.out_len[oimg] = total;
+        a.out_prob[oimg] = a.sel_score[r];
       }
     }
   }
@@ -1244,6 +1245,55 @@ __global__ void beam_mark_done_kernel(const int* __restrict__ sel_tok, int n_img
     atomicAdd(n_done, 1);
   }
 }
+__global__ void __launch_bounds__(128) beam_compact_gather_kernel(BeamCompactArgs a) {
+  const int rn = blockIdx.x, img = rn / a.K, k = rn - img * a.K;
+  const int ro = a.keep[img] * a.K + k;
+  for (int j = threadIdx.x; j < a.H1; j += blockDim.x) {
+    a.h1_s[(size_t)rn * a.H1 + j] = a.h1[(size_t)ro * a.ld1 + j];
+    a.c1_s[(size_t)rn * a.H1 + j] = a.c1[(size_t)ro * a.H1 + j];
+  }
+  for (int j = threadIdx.x; j < a.H2; j += blockDim.x) {
+    a.h2_s[(size_t)rn * a.H2 + j] = a.h2[(size_t)ro * a.ld2 + j];
+    a.c2_s[(size_t)rn * a.H2 + j] = a.c2[(size_t)ro * a.H2 + j];
+  }
+  for (int j = threadIdx.x; j < a.hist_len; j += blockDim.x) {
+    a.hist_dst[(size_t)rn * a.maxlen + j] = a.hist_src[(size_t)ro * a.maxlen + j];
+    a.lp_dst[(size_t)rn * a.maxlen + j] = a.lp_src[(size_t)ro * a.maxlen + j];
+  }
+  if (threadIdx.x == 0) { a.prob_s[rn] = a.prob[ro]; a.last_s[rn] = a.last[ro]; }
+  if (k == 0) {
+    const int io = a.keep[img];
+    for (int j = threadIdx.x; j < a.ldv; j += blockDim.x) a.v_s[(size_t)img * a.ldv + j] = a.v[(size_t)io * a.ldv + j];
+    if (threadIdx.x == 0) a.out_map_s[img] = a.out_map[io];
+  }
+}
+__global__ void __launch_bounds__(128) beam_compact_scatter_kernel(BeamCompactArgs a) {
+  const int rn = blockIdx.x, img = rn / a.K, k = rn - img * a.K;
+  for (int j = threadIdx.x; j < a.H1; j += blockDim.x) {
+    const float hv = a.h1_s[(size_t)rn * a.H1 + j];
+    a.h1[(size_t)rn * a.ld1 + j] = hv;
+    a.c1[(size_t)rn * a.H1 + j] = a.c1_s[(size_t)rn * a.H1 + j];
+    if (a.h1_hi) { __nv_bfloat16 hh, ll; split_one(hv, hh, ll); a.h1_hi[(size_t)rn * a.ld1 + j] = hh; a.h1_lo[(size_t)rn * a.ld1 + j] = ll; }
+  }
+  for (int j = threadIdx.x; j < a.H2; j += blockDim.x) {
+    const float hv = a.h2_s[(size_t)rn * a.H2 + j];
+    a.h2[(size_t)rn * a.ld2 + j] = hv;
+    a.c2[(size_t)rn * a.H2 + j] = a.c2_s[(size_t)rn * a.H2 + j];
+    if (a.h2_hi) { __nv_bfloat16 hh, ll; split_one(hv, hh, ll); a.h2_hi[(size_t)rn * a.ld2 + j] = hh; a.h2_lo[(size_t)rn * a.ld2 + j] = ll; }
+  }
+  if (threadIdx.x == 0) { a.prob[rn] = a.prob_s[rn]; a.last[rn] = a.last_s[rn]; }
+  if (k == 0) {
+    for (int j = threadIdx.x; j < a.ldv; j += blockDim.x) a.v[(size_t)img * a.ldv + j] = a.v_s[(size_t)img * a.ldv + j];
+    if (threadIdx.x == 0) { a.out_map[img] = a.out_map_s[img]; a.done[img] = 0; }
+  }
+}
+void beam_compact(cudaStream_t s, const BeamCompactArgs& a) {
+  if (a.n_keep <= 0) return;
+  beam_compact_gather_kernel<<<a.n_keep * a.K, 128, 0, s>>>(a);
+  beam_compact_scatter_kernel<<<a.n_keep * a.K, 128, 0, s>>>(a);
+  if (g_counter) g_counter->n += 2;
+}
+
 void beam_advance(cudaStream_t s, const BeamAdvanceArgs& a) {
   beam_advance_kernel<<<a.n_img * a.K, 128, 0, s>>>(a);
   count_launch();

@@ -161,7 +161,7 @@ static int s_destroy(lrcn_handle* h) {
   for (cudaEvent_t e : h->sc_ev) if (e) cudaEventDestroy(e);
   void* ptrs[] = {h->w, h->g, h->m, h->v, h->w_hi, h->w_lo, h->wp1_hi, h->wp1_lo, h->wp2_hi, h->wp2_lo, h->wt1_hi, h->wt1_lo, h->wt2_hi, h->wt2_lo, h->tab[0].d, h->tab[1].d, h->ws.f, h->ws.hi, h->ws.lo, h->d_tok_in,
                   h->d_tok_tgt, h->d_rows, h->d_sc, h->p2p_ctl, h->d_loss_total, h->d_epoch, h->d_epoch_side, h->stage, h->d_counters, h->d_trace, h->g_last, h->g_ctok, h->g_stok, h->g_spar, h->g_hista, h->g_histb,
-                  h->g_done, h->g_ndone, h->g_olen, h->g_rows, h->g_otok, h->l2_scratch};
+                  h->g_done, h->g_ndone, h->g_olen, h->g_rows, h->g_otok, h->l2_scratch, h->g_keep, h->g_omap, h->g_omap_s};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& s : h->slots) { if (s.tok_in) cudaFree(s.tok_in); if (s.tok_tgt) cudaFree(s.tok_tgt); if (s.rows) cudaFree(s.rows); }
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -295,7 +295,8 @@ static int create_impl(const lrcn_config* cfg, lrcn_handle* h) {
   CK(cudaMalloc(&h->g_last, G * 4)); CK(cudaMalloc(&h->g_ctok, G * 16 * 4)); CK(cudaMalloc(&h->g_stok, G * 4)); CK(cudaMalloc(&h->g_spar, G * 4));
   CK(cudaMalloc(&h->g_hista, G * ML * 4)); CK(cudaMalloc(&h->g_histb, G * ML * 4)); CK(cudaMalloc(&h->g_done, G * 4));
   CK(cudaMalloc(&h->g_ndone, 4)); CK(cudaMalloc(&h->g_olen, G * 4)); CK(cudaMalloc(&h->g_rows, G * 4)); CK(cudaMalloc(&h->g_otok, G * ML * 8));
-  CK(cudaMallocHost(&h->h_ndone, 4));
+  CK(cudaMallocHost(&h->h_ndone, (G + 1) * 4));
+  CK(cudaMalloc(&h->g_keep, G * 4)); CK(cudaMalloc(&h->g_omap, G * 4)); CK(cudaMalloc(&h->g_omap_s, G * 4));
   h->l2_n = (size_t)64 << 20;  // 256 MiB of floats > 126 MB L2
   CK(cudaMalloc(&h->l2_scratch, h->l2_n * 4));
   CK(cudaDeviceSynchronize());
@@ -1112,7 +1113,7 @@ static void beam_lstm_step(lrcn_handle* h, int layer, int step, int R, float* g,
 // reference's hcat(input,hidden)*weight, lrcn.jl:529) so there is no accumulate pass over the gates.
 static bool beam_wide(const lrcn_handle* h, int R) { return h->bf16mode && R > 512; }
 
-static void enqueue_beam_step(lrcn_handle* h, int n_img, int K, int step, int nword, int maxlen, bool flip, float* out_lp) {
+static void enqueue_beam_step(lrcn_handle* h, int n_img, int K, int step, int nword, int maxlen, bool flip, float* out_lp, bool wide, const int* out_map) {
   const int R = n_img * K, E = h->E, H1 = h->H1, H2 = h->H2, C = h->C, V = h->V, ldV = h->ldV, ldv = h->ldv;
   const Workspace& o = h->o;
   cudaStream_t s = h->stream;
@@ -1120,7 +1121,6 @@ static void enqueue_beam_step(lrcn_handle* h, int n_img, int K, int step, int nw
   // state ping-pong: "a" holds the beams' current states; the cell writes advanced states into "b"; advance gathers b -> a
   float *h1a = WS(h, o.gh1a), *c1a = WS(h, o.gc1a), *h1b = WS(h, o.gh1b), *c1b = WS(h, o.gc1b);
   float *h2a = WS(h, o.gh2a), *c2a = WS(h, o.gc2a), *h2b = WS(h, o.gh2b), *c2b = WS(h, o.gc2b);
-  const bool wide = beam_wide(h, R);
   int ld1 = H1, ld2 = H2;
   if (wide) {
     float *xh1 = WS(h, o.gxh1), *xh2 = WS(h, o.gxh2);
@@ -1157,7 +1157,7 @@ static void enqueue_beam_step(lrcn_handle* h, int n_img, int K, int step, int nw
   a.lp_in = flip ? WS(h, o.glpb) : WS(h, o.glpa); a.lp_out = flip ? WS(h, o.glpa) : WS(h, o.glpb);
   a.h1_hi = SH(h, h1a).hi; a.h1_lo = SH(h, h1a).lo; a.h2_hi = SH(h, h2a).hi; a.h2_lo = SH(h, h2a).lo;
   a.prob = WS(h, o.gprob); a.last_tok = h->g_last; a.done = h->g_done; a.n_done = h->g_ndone;
-  a.out_tokens = h->g_otok; a.out_len = h->g_olen; a.out_prob = WS(h, o.goprob); a.out_lp = out_lp;
+  a.out_tokens = h->g_otok; a.out_len = h->g_olen; a.out_prob = WS(h, o.goprob); a.out_lp = out_lp; a.out_map = out_map;
   beam_advance(s, a);  // reorder/gather parent states (+ their bf16 split for the next recurrent GEMMs)                 lrcn.jl:670-677
 }
 
@@ -1217,13 +1217,54 @@ static int s_beam_search(lrcn_handle* h, int split, const int64_t* image_ids, in
       CK(cudaMemsetAsync(WS(h, o.gc1a), 0, (size_t)R * h->H1 * 4, h->stream));
       CK(cudaMemsetAsync(WS(h, o.gc2a), 0, (size_t)R * h->H2 * 4, h->stream));
       bool flip = false;
+      const bool wide = beam_wide(h, R);  // fixed for the chunk: the two paths keep the states in different buffers
+      int n_act = ni;                     // images still in flight (compacted to the front)
+      bool mapped = false;                // g_omap is in use (after the first compaction)
+      static const bool no_compact = getenv("LRCN_BEAM_NO_COMPACT") != nullptr;
       for (int step = 1; step <= nword + 1; step++) {
-        enqueue_beam_step(h, ni, K, step, nword, maxlen, flip, logp_out ? WS(h, o.golp) : nullptr);
+        enqueue_beam_step(h, n_act, K, step, nword, maxlen, flip, logp_out ? WS(h, o.golp) : nullptr, wide, mapped ? h->g_omap : nullptr);
         flip = !flip;
         if ((step & 3) == 0 || step == nword + 1) {  // finished images are frozen on the device; poll the host only every 4 steps
           CK(cudaMemcpyAsync(h->h_ndone, h->g_ndone, 4, cudaMemcpyDeviceToHost, h->stream));
+          CK(cudaMemcpyAsync(h->h_ndone + 1, h->g_done, (size_t)n_act * 4, cudaMemcpyDeviceToHost, h->stream));
           CK(cudaStreamSynchronize(h->stream));
           if (*h->h_ndone >= ni) break;
+          // Compaction: the reference decodes image by image and simply stops when an image ends (lrcn.jl:670); in a batch the
+          // finished images would ride along until the slowest one ends (COCO captions end after ~10 of the 31 possible steps).
+          // When at least a quarter of the images in flight have ended, the survivors move to the front and every later step
+          // (three GEMMs, top-K, state gather) runs on the smaller batch.
+          int n_keep = 0;
+          for (int i = 0; i < n_act; i++) n_keep += h->h_ndone[1 + i] ? 0 : 1;
+          if (!no_compact && step < nword + 1 && n_keep > 0 && n_keep * 4 <= n_act * 3) {
+            std::vector<int> keep;
+            keep.reserve(n_keep);
+            for (int i = 0; i < n_act; i++) if (!h->h_ndone[1 + i]) keep.push_back(i);
+            CK(cudaMemcpyAsync(h->g_keep, keep.data(), (size_t)n_keep * 4, cudaMemcpyHostToDevice, h->stream));
+            if (!mapped) {  // identity map before the first compaction
+              std::vector<int> ident(n_act);
+              for (int i = 0; i < n_act; i++) ident[i] = i;
+              CK(cudaMemcpyAsync(h->g_omap, ident.data(), (size_t)n_act * 4, cudaMemcpyHostToDevice, h->stream));
+              CK(cudaStreamSynchronize(h->stream));  // `ident` is a stack-lifetime host buffer
+              mapped = true;
+            }
+            BeamCompactArgs ca{};
+            ca.n_keep = n_keep; ca.K = K; ca.H1 = h->H1; ca.H2 = h->H2; ca.ldv = h->ldv; ca.maxlen = maxlen; ca.hist_len = step + 1;
+            ca.ld1 = wide ? h->E + h->H1 : h->H1; ca.ld2 = wide ? 2 * h->C + h->H2 : h->H2;
+            ca.keep = h->g_keep;
+            ca.h1 = wide ? WS(h, o.gxh1) + h->E : WS(h, o.gh1a); ca.h2 = wide ? WS(h, o.gxh2) + 2 * h->C : WS(h, o.gh2a);
+            ca.c1 = WS(h, o.gc1a); ca.c2 = WS(h, o.gc2a);
+            ca.h1_s = WS(h, o.gh1b); ca.c1_s = WS(h, o.gc1b); ca.h2_s = WS(h, o.gh2b); ca.c2_s = WS(h, o.gc2b);  // the "advanced state" buffers are free between steps
+            ca.h1_hi = SH(h, ca.h1).hi; ca.h1_lo = SH(h, ca.h1).lo; ca.h2_hi = SH(h, ca.h2).hi; ca.h2_lo = SH(h, ca.h2).lo;
+            ca.hist_src = flip ? h->g_histb : h->g_hista; ca.hist_dst = flip ? h->g_hista : h->g_histb;
+            ca.lp_src = flip ? WS(h, o.glpb) : WS(h, o.glpa); ca.lp_dst = flip ? WS(h, o.glpa) : WS(h, o.glpb);
+            ca.prob = WS(h, o.gprob); ca.prob_s = WS(h, o.gss); ca.last = h->g_last; ca.last_s = h->g_stok;
+            ca.v = WS(h, o.gv); ca.v_s = WS(h, o.gX);  // the gathered features are dead once v = X * Wcnn exists
+            ca.out_map = h->g_omap; ca.out_map_s = h->g_omap_s; ca.done = h->g_done;
+            beam_compact(h->stream, ca);
+            CK(cudaStreamSynchronize(h->stream));  // `keep` is a stack-lifetime host buffer
+            flip = !flip;  // the compacted histories live in the other ping-pong buffer
+            n_act = n_keep;
+          }
         }
       }
     } catch (GemmFail& f) {

@@ -1898,11 +1898,12 @@ lstm_bwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
           // phase 2: one thread sends every rank the partials (over this K-quarter) of the 16 units it finishes
           if (tid == 0) {
             if (nkb > 0) mbar_arrive(sm.tempty0 + 8 * c);  // every thread of the team is past its TMEM reads
-            mbar_expect_tx(sm.redfull0 + 8 * c, B4_RED);   // what the four ranks (this one included) will deliver to me
+            mbar_expect_tx(sm.redfull0 + 8 * c, (CL - 1) * 2 * B4_PART);   // what the three other ranks will deliver to me (my own part stays in S)
             const uint32_t s_hi = smem_u32(S), s_lo = smem_u32(S) + 64 * T4_SLD * 4;
             const uint32_t r_mine = smem_u32(red) + (uint32_t)((int)rank * 2 * B4_PART);
 #pragma unroll
             for (int d = 0; d < CL; d++) {
+              if (d == (int)rank) continue;
               const uint32_t dst = dsmem_addr(r_mine, (uint32_t)d), bar = dsmem_addr(sm.redfull0 + 8 * c, (uint32_t)d);
               dsmem_bulk_copy(dst, s_hi + (uint32_t)(d * B4_PART), B4_PART, bar);
               dsmem_bulk_copy(dst + B4_PART, s_lo + (uint32_t)(d * B4_PART), B4_PART, bar);
@@ -1913,9 +1914,13 @@ lstm_bwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
           mbar_wait(sm.redfull0 + 8 * c, n & 1);
           if (tid == 0) T4_TRACE(c, 7);   // received
 #pragma unroll
-          for (int q = 0; q < 2 * CL; q++)
+          for (int src = 0; src < CL; src++) {  // fixed order: deterministic sums
+            // the other ranks' partials arrived in `red`; this rank's own (W_hi part, W_lo part) are still in S
+            const float* p_hi = src == (int)rank ? S + (size_t)(16 * src) * T4_SLD : red + (size_t)(2 * src) * 16 * T4_SLD;
+            const float* p_lo = src == (int)rank ? S + (size_t)(64 + 16 * src) * T4_SLD : red + (size_t)(2 * src + 1) * 16 * T4_SLD;
 #pragma unroll
-            for (int e = 0; e < 4; e++) rec[e] += red[(size_t)(q * 16 + 4 * ug + e) * T4_SLD + fr];
+            for (int e = 0; e < 4; e++) rec[e] += p_hi[(size_t)(4 * ug + e) * T4_SLD + fr] + p_lo[(size_t)(4 * ug + e) * T4_SLD + fr];
+          }
           n++;
         }
         float r0[4], r1[4], r2[4], r3[4];
