@@ -55,6 +55,17 @@ __device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// descriptors as (low word, constant high word): see desc_lo_kmajor / desc_lo_mnmajor in sm100_ptx.cuh
+__device__ __forceinline__ void umma2_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI_SW128)
+      : "memory");
+}
 __device__ __forceinline__ void umma2_commit_mcast(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
 }
@@ -210,8 +221,13 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && lane == 0) {
+    // The whole warp runs the loop CONVERGED on warp-uniform values and one elected lane issues: the descriptors then live in
+    // uniform registers and advance by one uniform add per k-step (inside `if (lane == 0)` every tcgen05.mma is wrapped in an
+    // ELECT / R2UR / branch waterfall -- ~125 clk per instruction, as much as a 256x256x16 pair MMA takes on the tensor pipe).
+    if (__shfl_sync(0xffffffffu, leader ? 1 : 0, 0)) {
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc = idesc_bf16(256, BNP, !AK, !BKM);
+      constexpr uint32_t A_STEP = AK ? 2u : 128u, B_STEP = BKM ? 2u : 128u;  // low-word advance per 16 k-elements (32 B K-major, 2048 B MN-major)
       int it = 0, local = 0;
       SegIter si(cidx, ncl, num_kb_total, p.sk_tile0, p.sk_tiles, p.dp_end);
       Seg sg;
@@ -221,27 +237,30 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         const uint32_t aph = (local >> 1) & 1;
         mbar_wait(tempty_bar0 + 8 * acc, aph ^ 1);  // both CTAs' epilogues have drained this accumulator stage
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BNP);
+        const uint32_t tmem_d = tb + (uint32_t)(acc * BNP);
         for (int kb = kb_begin; kb < kb_end; kb++, it++) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(full_bar0 + 8 * s, ph);
           tc_fence_after();
           const uint32_t sA_hi = smem_base + s * STAGE_BYTES, sA_lo = sA_hi + TILE, sB_hi = sA_lo + TILE, sB_lo = sB_hi + TILE;
+          const uint32_t a_hi = AK ? desc_lo_kmajor(sA_hi) : desc_lo_mnmajor(sA_hi), a_lo = AK ? desc_lo_kmajor(sA_lo) : desc_lo_mnmajor(sA_lo);
+          const uint32_t b_hi = BKM ? desc_lo_kmajor(sB_hi) : desc_lo_mnmajor(sB_hi), b_lo = BKM ? desc_lo_kmajor(sB_lo) : desc_lo_mnmajor(sB_lo);
+          if (elect_one()) {
+            if (!(p.dbg & 4)) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; k++) {
-            if (p.dbg & 4) break;
-            const uint64_t a_hi = AK ? desc_kmajor(sA_hi, k) : desc_mnmajor(sA_hi, k);
-            const uint64_t a_lo = AK ? desc_kmajor(sA_lo, k) : desc_mnmajor(sA_lo, k);
-            const uint64_t b_hi = BKM ? desc_kmajor(sB_hi, k) : desc_mnmajor(sB_hi, k);
-            const uint64_t b_lo = BKM ? desc_kmajor(sB_lo, k) : desc_mnmajor(sB_lo, k);
-            umma2_bf16(tmem_d, a_lo, b_hi, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
-            umma2_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
-            umma2_bf16(tmem_d, a_hi, b_hi, idesc, 1u);
+              for (int k = 0; k < BK / 16; k++) {
+                umma2_bf16_lo(tmem_d, a_lo + A_STEP * k, b_hi + B_STEP * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+                umma2_bf16_lo(tmem_d, a_hi + A_STEP * k, b_lo + B_STEP * k, idesc, 1u);
+                umma2_bf16_lo(tmem_d, a_hi + A_STEP * k, b_hi + B_STEP * k, idesc, 1u);
+              }
+            }
+            umma2_commit_mcast(empty_bar0 + 8 * s, (uint16_t)3);  // frees this stage in BOTH CTAs
           }
-          umma2_commit_mcast(empty_bar0 + 8 * s, (uint16_t)3);  // frees this stage in BOTH CTAs
+          __syncwarp();
         }
-        umma2_commit_mcast(tfull_bar0 + 8 * acc, (uint16_t)3);  // accumulators complete in BOTH CTAs
+        if (elect_one()) umma2_commit_mcast(tfull_bar0 + 8 * acc, (uint16_t)3);  // accumulators complete in BOTH CTAs
+        __syncwarp();
       }
     }
   } else {

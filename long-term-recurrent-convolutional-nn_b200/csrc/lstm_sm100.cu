@@ -96,26 +96,33 @@ __device__ __forceinline__ StepSmem step_smem(uint8_t* smem_raw) {
   s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
   return s;
 }
-// MMA issue loop shared by both directions (one elected lane)
-__device__ __forceinline__ void step_mma_loop(const StepSmem& sm, uint32_t tmem_base, int num_kb, bool mcast_release) {
+// MMA issue loop shared by both directions.  Called by the WHOLE (converged) warp: the loop runs on warp-uniform values and one
+// elected lane issues, so the descriptors stay in uniform registers (see elect_one(); inside `if (lane == 0)` every
+// tcgen05.mma was wrapped in an ELECT / R2UR / branch waterfall: ~125 clk per MMA instead of ~80).
+__device__ __forceinline__ void step_mma_loop(const StepSmem& sm, uint32_t tmem_base_any, int num_kb, bool mcast_release) {
   const uint32_t idesc = idesc_bf16(LM, NT, false, false);
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_any, 0);
   for (int i = 0; i < num_kb; i++) {
     const int s = i % STAGES;
     mbar_wait(sm.full_bar0 + 8 * s, (i / STAGES) & 1);
     tc_fence_after();
     const uint32_t st = sm.base + s * STAGE;
+    const uint32_t a_hi = desc_lo_kmajor(st), a_lo = desc_lo_kmajor(st + A_HALF);
+    const uint32_t b_hi = desc_lo_kmajor(st + 2 * A_HALF), b_lo = desc_lo_kmajor(st + 2 * A_HALF + B_HALF);
+    if (elect_one()) {
 #pragma unroll
-    for (int k = 0; k < LBK / 16; k++) {
-      const uint64_t a_hi = desc_kmajor(st, k), a_lo = desc_kmajor(st + A_HALF, k);
-      const uint64_t b_hi = desc_kmajor(st + 2 * A_HALF, k), b_lo = desc_kmajor(st + 2 * A_HALF + B_HALF, k);
-      umma_bf16(tmem_base, a_lo, b_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
-      umma_bf16(tmem_base, a_hi, b_lo, idesc, 1u);
-      umma_bf16(tmem_base, a_hi, b_hi, idesc, 1u);
+      for (int k = 0; k < LBK / 16; k++) {
+        umma_bf16_lo(tmem_base, a_lo + 2u * k, b_hi + 2u * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        umma_bf16_lo(tmem_base, a_hi + 2u * k, b_lo + 2u * k, idesc, 1u);
+        umma_bf16_lo(tmem_base, a_hi + 2u * k, b_hi + 2u * k, idesc, 1u);
+      }
+      if (mcast_release) umma_commit_mcast(sm.empty_bar0 + 8 * s, (uint16_t)((1u << CL) - 1));  // free in MY smem: tell all CL producers
+      else umma_commit(sm.empty_bar0 + 8 * s);
     }
-    if (mcast_release) umma_commit_mcast(sm.empty_bar0 + 8 * s, (uint16_t)((1u << CL) - 1));  // free in MY smem: tell all CL producers
-    else umma_commit(sm.empty_bar0 + 8 * s);
+    __syncwarp();
   }
-  umma_commit(sm.tfull_bar);
+  if (elect_one()) umma_commit(sm.tfull_bar);
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------- forward step
@@ -165,7 +172,7 @@ lstm_fwd_step_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && num_kb > 0) step_mma_loop(sm, tmem_base, num_kb, true);
+    if (num_kb > 0) step_mma_loop(sm, tmem_base, num_kb, true);
   } else {
     const int ew = warp - 2, quad = warp & 3, half = ew >> 2;  // warp%4 fixes the TMEM lane quadrant
     constexpr int NH = NT / 4;                                 // 16 units per CTA; columns are unit-major: col = u*4 + gate
@@ -283,7 +290,7 @@ lstm_bwd_step_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && num_kb > 0) step_mma_loop(sm, tmem_base, num_kb, false);
+    if (num_kb > 0) step_mma_loop(sm, tmem_base, num_kb, false);
   } else if (p.has_rec) {
     // phase 1: scatter this CTA's partial (64 rows x 64 units) to the four owners through DSMEM.
     // receive buffer layout in every CTA: red[src][row][16] fp32
