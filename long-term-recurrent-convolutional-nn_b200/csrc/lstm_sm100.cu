@@ -1201,7 +1201,8 @@ lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
         if (lane == 0) { grid_wait(ctr + c, (unsigned int)t * ctas_per_mtile); T4_TRACE(c, 0); }  // h_{t-1} rows of this chain are complete; the cluster's MMAs of step t-1 are done
         __syncwarp();
         if (lane < num_kb) {  // one lane per k-block: arm its barrier and (rank kb % CL) fetch + multicast it -- 8 lanes issue in parallel
-          fence_proxy_async_global();  // (lane 0's acquire + __syncwarp order the other ranks' h stores before this lane's TMA)
+          grid_wait(ctr + c, (unsigned int)t * ctas_per_mtile);  // every issuing lane performs its own acquire (returns at once)
+          fence_proxy_async_global();
           const int kb = lane;
           const int arow = t * B + m0 + T4_ROWS * c;  // slot t of hs = h_{t-1}
           mbar_expect_tx(fullc + 8 * kb, T4_BSTAGE);
@@ -1782,7 +1783,8 @@ lstm_bwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
         if (lane == 0) { grid_wait(ctr + c, (unsigned int)(T - 1 - t) * ctas_per_mtile); T4_TRACE(c, 0); }  // dG_{t+1} rows of this chain are complete
         __syncwarp();
         if (lane < nkb) {  // one lane per k-block: 8 lanes issue their TMA pairs in parallel
-          fence_proxy_async_global();  // (lane 0's acquire + __syncwarp order the other ranks' dG stores before this lane's TMA)
+          grid_wait(ctr + c, (unsigned int)(T - 1 - t) * ctas_per_mtile);  // every issuing lane performs its own acquire (returns at once)
+          fence_proxy_async_global();
           const int i = lane;
           const int arow = (t + 1) * B + m0 + T4_ROWS * c;
           const uint32_t full = fullc + 8 * i, st = buf + i * T4_BSTAGE;
