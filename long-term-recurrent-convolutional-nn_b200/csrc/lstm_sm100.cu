@@ -1198,22 +1198,20 @@ lstm_fwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       const int kb_split = (num_kb + 1) / 2;
       mbar_wait(sm.wbar, 0);
       for (int t = 1; t < T; t++) {
-        if (lane == 0) { grid_wait(ctr + c, (unsigned int)t * ctas_per_mtile); T4_TRACE(c, 0); }  // h_{t-1} rows of this chain are complete; the cluster's MMAs of step t-1 are done
-        __syncwarp();
-        if (lane < num_kb) {  // one lane per k-block: arm its barrier and (rank kb % CL) fetch + multicast it -- 8 lanes issue in parallel
-          grid_wait(ctr + c, (unsigned int)t * ctas_per_mtile);  // every issuing lane performs its own acquire (returns at once)
+        if (lane == 0) {
+          grid_wait(ctr + c, (unsigned int)t * ctas_per_mtile);  // h_{t-1} rows of this chain are complete; the cluster's MMAs of step t-1 are done
+          T4_TRACE(c, 0);
           fence_proxy_async_global();
-          const int kb = lane;
           const int arow = t * B + m0 + T4_ROWS * c;  // slot t of hs = h_{t-1}
-          mbar_expect_tx(fullc + 8 * kb, T4_BSTAGE);
-          if ((uint32_t)(kb % CL) == rank) {
+          for (int kb = 0; kb < num_kb; kb++) mbar_expect_tx(fullc + 8 * kb, T4_BSTAGE);
+          for (int kb = (int)rank; kb < num_kb; kb += CL) {  // k-block kb is fetched by rank kb % CL and multicast to the cluster
             const uint32_t st = buf + kb * T4_BSTAGE;
             tma_load_2d_mcast(st, &tmA_hi, fullc + 8 * kb, kb * LBK, arow, (uint16_t)((1u << CL) - 1));
             tma_load_2d_mcast(st + T4_BHALF, &tmA_lo, fullc + 8 * kb, kb * LBK, arow, (uint16_t)((1u << CL) - 1));
           }
+          T4_TRACE(c, 1);
         }
         __syncwarp();
-        if (lane == 0) T4_TRACE(c, 1);
         // second half of the k-blocks (converged warp, elected lane: see elect_one())
         mbar_wait(sm.started0 + 8 * c, (t - 1) & 1);  // the issuer warp has issued this step's first (overwriting) MMA
         tc_fence_after();
@@ -1780,20 +1778,20 @@ lstm_bwd_seq4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       const int kb_split = (nkb + 1) / 2;
       int n = 0;
       for (int t = T - 2; t >= 0; t--, n++) {
-        if (lane == 0) { grid_wait(ctr + c, (unsigned int)(T - 1 - t) * ctas_per_mtile); T4_TRACE(c, 0); }  // dG_{t+1} rows of this chain are complete
-        __syncwarp();
-        if (lane < nkb) {  // one lane per k-block: 8 lanes issue their TMA pairs in parallel
-          grid_wait(ctr + c, (unsigned int)(T - 1 - t) * ctas_per_mtile);  // every issuing lane performs its own acquire (returns at once)
+        if (lane == 0) {
+          grid_wait(ctr + c, (unsigned int)(T - 1 - t) * ctas_per_mtile);  // dG_{t+1} rows of this chain are complete
+          T4_TRACE(c, 0);
           fence_proxy_async_global();
-          const int i = lane;
           const int arow = (t + 1) * B + m0 + T4_ROWS * c;
-          const uint32_t full = fullc + 8 * i, st = buf + i * T4_BSTAGE;
-          mbar_expect_tx(full, T4_BSTAGE);
-          tma_load_2d(st, &tmA_hi, full, (kb_begin + i) * LBK, arow);
-          tma_load_2d(st + T4_BHALF, &tmA_lo, full, (kb_begin + i) * LBK, arow);
+          for (int i = 0; i < nkb; i++) {
+            const uint32_t full = fullc + 8 * i, st = buf + i * T4_BSTAGE;
+            mbar_expect_tx(full, T4_BSTAGE);
+            tma_load_2d(st, &tmA_hi, full, (kb_begin + i) * LBK, arow);
+            tma_load_2d(st + T4_BHALF, &tmA_lo, full, (kb_begin + i) * LBK, arow);
+          }
+          T4_TRACE(c, 1);
         }
         __syncwarp();
-        if (lane == 0) T4_TRACE(c, 1);
         mbar_wait(sm.started0 + 8 * c, n & 1);  // the issuer warp has issued this step's first (overwriting) MMA
         tc_fence_after();
         for (int i = kb_split; i < nkb; i++) {
