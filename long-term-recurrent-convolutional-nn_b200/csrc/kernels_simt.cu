@@ -235,9 +235,36 @@ __global__ void z_finish_kernel(float* __restrict__ Z, const float* __restrict__
     if (hi) { __nv_bfloat16 h, l; split_one(x, h, l); hi[(size_t)r * ldz + j] = h; lo[(size_t)r * ldz + j] = l; }
   }
 }
+// vectorised variant (C, ldz, ldv multiples of 4): one warp per row, 128-bit accesses, packed bf16x4 shadow stores
+__global__ void __launch_bounds__(256) z_finish_vec_kernel(float* __restrict__ Z, const float* __restrict__ v, int ldv, int R, int B, int C, int ldz,
+                                                           const StepScalars* __restrict__ sc, int train, __nv_bfloat16* __restrict__ hi,
+                                                           __nv_bfloat16* __restrict__ lo) {
+  pdl_wait();
+  pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const int i = B > 0 ? r % B : r / (-B);  // B<0: generation, image index = row / beam_width
+  float* z = Z + (size_t)r * ldz;
+  const bool drop = train && sc->drop_thresh != 0;
+  const int C4 = C >> 2;
+  for (int q = lane; q < 2 * C4; q += 32) {
+    float4 x = q < C4 ? reinterpret_cast<const float4*>(z)[q] : __ldg(reinterpret_cast<const float4*>(v + (size_t)i * ldv) + (q - C4));
+    if (drop) {
+      const uint64_t idx = (uint64_t)r * 2 * C + 4 * q;
+      x.x *= drop_scale(sc, 1, idx); x.y *= drop_scale(sc, 1, idx + 1); x.z *= drop_scale(sc, 1, idx + 2); x.w *= drop_scale(sc, 1, idx + 3);
+    }
+    if (q >= C4 || drop) reinterpret_cast<float4*>(z)[q] = x;
+    if (hi) store_split4(hi, lo, (size_t)r * ldz + 4 * q, x);
+  }
+}
 void z_finish(cudaStream_t s, float* Z, const float* v, int ldv, int R, int B, int C, const StepScalars* sc, bool train,
               __nv_bfloat16* hi, __nv_bfloat16* lo, int ldz) {
-  launch_pdl<2>(z_finish_kernel, dim3(R), dim3(128), 0, s, Z, v, ldv, R, B, C, ldz > 0 ? ldz : 2 * C, sc, train ? 1 : 0, hi, lo);
+  const int ld = ldz > 0 ? ldz : 2 * C;
+  if (((C | ld | ldv) & 3) == 0)
+    launch_pdl<2>(z_finish_vec_kernel, dim3((R + 7) / 8), dim3(256), 0, s, Z, v, ldv, R, B, C, ld, sc, train ? 1 : 0, hi, lo);
+  else
+    launch_pdl<2>(z_finish_kernel, dim3(R), dim3(128), 0, s, Z, v, ldv, R, B, C, ld, sc, train ? 1 : 0, hi, lo);
   count_launch();
 }
 
@@ -661,10 +688,51 @@ __global__ void dz_finish_kernel(float* __restrict__ dZ, float* __restrict__ dv,
     if (v_hi) { __nv_bfloat16 h, l; split_one(acc, h, l); v_hi[(size_t)i * ldv + (j - C)] = h; v_lo[(size_t)i * ldv + (j - C)] = l; }
   }
 }
+// vectorised variant (C, ldv multiples of 4): a thread owns 4 columns of one batch row and walks the T steps with all loads of
+// a group of steps in flight (the scalar kernel serialised T dependent load -> store round trips per thread)
+__global__ void __launch_bounds__(128) dz_finish_vec_kernel(float* __restrict__ dZ, float* __restrict__ dv, int ldv, int T, int B, int C,
+                                                            const StepScalars* __restrict__ sc, int train, __nv_bfloat16* __restrict__ z_hi,
+                                                            __nv_bfloat16* __restrict__ z_lo, __nv_bfloat16* __restrict__ v_hi, __nv_bfloat16* __restrict__ v_lo) {
+  pdl_wait();
+  pdl_trigger();
+  const int i = blockIdx.x;                                      // batch row
+  const int q = blockIdx.y * blockDim.x + threadIdx.x;           // float4 column of Z
+  if (q >= (2 * C) >> 2) return;
+  const bool drop = train && sc->drop_thresh != 0;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  constexpr int U = 4;
+  for (int t0 = 0; t0 < T; t0 += U) {
+    float4 x[U];
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (t0 + u < T) x[u] = reinterpret_cast<const float4*>(dZ + ((size_t)(t0 + u) * B + i) * 2 * C)[q];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (t0 + u >= T) break;
+      const size_t idx = ((size_t)(t0 + u) * B + i) * 2 * C + 4 * q;
+      if (drop) {
+        x[u].x *= drop_scale(sc, 1, idx); x[u].y *= drop_scale(sc, 1, idx + 1); x[u].z *= drop_scale(sc, 1, idx + 2); x[u].w *= drop_scale(sc, 1, idx + 3);
+        *reinterpret_cast<float4*>(dZ + idx) = x[u];
+      }
+      if (z_hi) store_split4(z_hi, z_lo, idx, x[u]);
+      acc.x += x[u].x; acc.y += x[u].y; acc.z += x[u].z; acc.w += x[u].w;
+    }
+  }
+  const int j = 4 * q;
+  if (j >= C) {
+    *reinterpret_cast<float4*>(dv + (size_t)i * ldv + (j - C)) = acc;
+    if (v_hi) store_split4(v_hi, v_lo, (size_t)i * ldv + (j - C), acc);
+  }
+}
 void dz_finish(cudaStream_t s, float* dZ, float* dv, int ldv, int T, int B, int C, const StepScalars* sc, bool train,
                __nv_bfloat16* z_hi, __nv_bfloat16* z_lo, __nv_bfloat16* v_hi, __nv_bfloat16* v_lo) {
-  dim3 grid(B, (2 * C + 127) / 128);
-  launch_pdl<2>(dz_finish_kernel, grid, dim3(128), 0, s, dZ, dv, ldv, T, B, C, sc, train ? 1 : 0, z_hi, z_lo, v_hi, v_lo);
+  if (((C | ldv) & 3) == 0) {
+    dim3 grid(B, ((2 * C) / 4 + 127) / 128);
+    launch_pdl<2>(dz_finish_vec_kernel, grid, dim3(128), 0, s, dZ, dv, ldv, T, B, C, sc, train ? 1 : 0, z_hi, z_lo, v_hi, v_lo);
+  } else {
+    dim3 grid(B, (2 * C + 127) / 128);
+    launch_pdl<2>(dz_finish_kernel, grid, dim3(128), 0, s, dZ, dv, ldv, T, B, C, sc, train ? 1 : 0, z_hi, z_lo, v_hi, v_lo);
+  }
   count_launch();
 }
 

@@ -175,6 +175,7 @@ static int s_destroy(lrcn_handle* h) {
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->ev_zero) cudaEventDestroy(h->ev_zero);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return LRCN_OK;
@@ -210,6 +211,7 @@ static int create_impl(const lrcn_config* cfg, lrcn_handle* h) {
   CK(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_zero, cudaEventDisableTiming));
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
   for (int i = 0; i < 3; i++) CK(cudaEventCreateWithFlags(&h->ev_seg[i], cudaEventDisableTiming));
@@ -650,7 +652,11 @@ static void enqueue_forward(lrcn_handle* h, int split, int B, int l, bool train)
     cudaEventRecord(h->ev_join, h->side_stream);
   }
   {
-    ZeroSegs z;
+    // Two zeroing launches.  What the FORWARD pass needs (grid-barrier counters, slot 0 of the state buffers) is zeroed on the
+    // main stream; the accumulation targets of the BACKWARD pass (~60 MB: the gradient arena behind dWout, the stream-K
+    // data-gradient buffers) are zeroed on the side stream under the forward pass and joined before the softmax kernel, the
+    // first kernel that accumulates into the gradient arena (dbout).
+    ZeroSegs z, zb;
     z.add(h->d_counters, 256);
     // slot 0 of the h / c slot buffers is h_0 = c_0 = 0 (initstate, lrcn.jl:512-526).  Its POSITION is fixed (rows [0, B)), but
     // slot t of a call with a smaller B lands on rows [t*B_small, ...) -- inside slot 0 of a later, larger batch (average_loss
@@ -661,12 +667,17 @@ static void enqueue_forward(lrcn_handle* h, int split, int B, int l, bool train)
       z.add(SH(h, h2).hi, (size_t)B * H2 / 2); z.add(SH(h, h2).lo, (size_t)B * H2 / 2);
     }
     if (train) {
-      z.add(h->g + h->off[8], h->P - h->off[8]);  // arena order [Wout, bout | W2, b2, Wf, Wcnn | W1, b1, Wemb]: everything from bout on
-      z.add(WS(h, o.dh2), (size_t)R * H2);
-      z.add(WS(h, o.dZ), (size_t)R * 2 * C);
-      z.add(WS(h, o.dE), (size_t)R * E);
+      ZeroSegs& t = h->bf16mode ? zb : z;
+      t.add(h->g + h->off[8], h->P - h->off[8]);  // arena order [Wout, bout | W2, b2, Wf, Wcnn | W1, b1, Wemb]: everything from bout on
+      t.add(WS(h, o.dh2), (size_t)R * H2);
+      t.add(WS(h, o.dZ), (size_t)R * 2 * C);
+      t.add(WS(h, o.dE), (size_t)R * E);
     }
     zero_multi(s, z);
+    if (zb.count) {
+      zero_multi(h->side_stream, zb);
+      cudaEventRecord(h->ev_zero, h->side_stream);
+    }
   }
   gather_features(s, h->tab[split].d, h->d_rows, B, X, SH(h, X).hi, SH(h, X).lo);
   gemm(h, true, true, B, C, LRCN_F_CNN, X, LRCN_F_CNN, Wp(h, 6), LRCN_F_CNN, v, ldv, false, nullptr);  // input*Wcnn  lrcn.jl:558
@@ -681,6 +692,7 @@ static void enqueue_forward(lrcn_handle* h, int split, int B, int l, bool train)
   gemm(h, true, true, R, V, H2, h2 + (size_t)B * H2, H2, Wp(h, 8), H2, logits, ldV, false, Wp(h, 9));      // x*w[end-1] .+ w[end]  lrcn.jl:550
   // logp + gather + fp64 total  lrcn.jl:562-567; training in bf16x3 mode also folds dbout in and never writes dA in fp32
   h->dbout_fused = false;
+  if (train && h->bf16mode) cudaStreamWaitEvent(s, h->ev_zero, 0);  // the backward pass's accumulation targets are zero from here on
   if (train && h->bf16mode && !getenv("LRCN_NO_FUSED_SOFTMAX"))
     h->dbout_fused = softmax_ce_fused(s, logits, ldV, R, V, h->d_tok_tgt, WS(h, o.rowlp), h->d_sc, SH(h, logits).hi, SH(h, logits).lo,
                                       WS(h, o.colpart), COLPART_ROWS, Gp(h, 9), h->d_loss, h->d_counters + 256);

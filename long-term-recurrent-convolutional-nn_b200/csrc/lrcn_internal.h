@@ -47,7 +47,7 @@ struct lrcn_handle {
   int E, H1, H2, C, V, ldV, ldv;
   bool bf16mode;
   cudaStream_t stream = nullptr, comm_stream = nullptr, side_stream = nullptr;  // side: weight prep, concurrent with the step's first kernels
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_zero = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_seg[3] = {nullptr, nullptr, nullptr}, ev_comm = nullptr;
   // params
   size_t P = 0, off[9], nel[9], bucket_off[4];
