@@ -123,6 +123,16 @@ LRCN_API int lrcn_grad(lrcn_handle* h, int split, const int64_t* image_ids, cons
 LRCN_API int lrcn_adam_update(lrcn_handle* h);
 LRCN_API int lrcn_train_step(lrcn_handle* h, int split, const int64_t* image_ids, const int64_t* tokens, int l, int B,
                     float pdrop, uint64_t seed, double* loss_out);
+/* ---- one epoch of the train1 hot loop in ONE call (lrcn.jl:336-396; SURVEY 8 row f-1: batch staging on the device).
+ * sequence: the [n_rows][B] time-major token matrix minibatch() builds (lrcn.jl:257-297: batch b owns lengths[b] consecutive
+ * rows), input_ids: [n_batches][B], lengths: [n_batches], order: the host's shuffled batch order (lrcn.jl:351; NULL = 0..n-1).
+ * The epoch is uploaded once, image ids are resolved to feature rows on the device, every batch is staged by a kernel from
+ * the resident data, batches with l > max_len are skipped (lrcn.jl:353) and no step synchronises with the host.
+ * losses_out (optional, n_order values): loss of every executed step, in execution order; steps_out: how many ran.
+ * Step k uses dropout seed `seed + k`. */
+LRCN_API int lrcn_train_epoch(lrcn_handle* h, int split, const int64_t* sequence, int64_t n_rows, const int64_t* input_ids,
+                     const int64_t* lengths, int64_t n_batches, int B, const int64_t* order, int64_t n_order, float pdrop,
+                     uint64_t seed, double* losses_out, int64_t* steps_out);
 /* per-token target log-probs of the last lrcn_loss/lrcn_grad call, (l+1) x B time-major */
 LRCN_API int lrcn_get_token_logps(lrcn_handle* h, float* out, int64_t n);
 

@@ -145,6 +145,21 @@ function train_step!(net, split, ids, sequence, range; pdrop=0.0, seed=0)   # lr
     return l[]
 end
 
+# One epoch of the hot loop of train1 (lrcn.jl:351-396) in ONE call: `sequence`, `input_ids`, `lengths` are what minibatch()
+# returned (lrcn.jl:257-297), `order` the shuffled batch starts `shuffle(1:batchsize:length(lengths))` of lrcn.jl:351.  The
+# library uploads the epoch once, stages every batch on the device and skips l > 28 batches like lrcn.jl:353.
+function train_epoch!(net, split, sequence, input_ids, lengths, batchsize, order; pdrop=0.0, seed=0)
+    seq = convert(Matrix{Int64}, hcat(sequence...))        # B x n_rows, column-major = the C side's [n_rows][B]
+    ids = convert(Matrix{Int64}, hcat(input_ids...))       # B x n_batches
+    blens = convert(Vector{Int64}, lengths[1:batchsize:end])
+    ord = convert(Vector{Int64}, [div(t - 1, batchsize) for t in order])   # 0-based batch numbers
+    losses = zeros(Float64, length(ord)); steps = Ref{Int64}(0)
+    check(ccall((:lrcn_train_epoch, lib), Cint,
+                (Ptr{Void}, Cint, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Int64}, Int64, Cint, Ptr{Int64}, Int64, Cfloat, UInt64, Ptr{Float64}, Ptr{Int64}),
+                net.handle, split, seq, size(seq,2), ids, blens, length(blens), size(ids,1), ord, length(ord), pdrop, seed, losses, steps))
+    return losses[1:steps[]]
+end
+
 function token_logps(net, l, B)
     out = Array(Float32, B, l+1)
     check(ccall((:lrcn_get_token_logps, lib), Cint, (Ptr{Void}, Ptr{Float32}, Int64), net.handle, out, length(out)))

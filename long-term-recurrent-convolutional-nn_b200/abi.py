@@ -56,6 +56,8 @@ SIGNATURES = {
     "lrcn_grad": (C.c_int, [_H, C.c_int, _i64p, _i64p, C.c_int, C.c_int, C.c_float, C.c_uint64, _f64p]),
     "lrcn_adam_update": (C.c_int, [_H]),
     "lrcn_train_step": (C.c_int, [_H, C.c_int, _i64p, _i64p, C.c_int, C.c_int, C.c_float, C.c_uint64, _f64p]),
+    "lrcn_train_epoch": (C.c_int, [_H, C.c_int, _i64p, C.c_int64, _i64p, _i64p, C.c_int64, C.c_int, _i64p, C.c_int64, C.c_float, C.c_uint64,
+                                   _f64p, _i64p]),
     "lrcn_get_token_logps": (C.c_int, [_H, _f32p, C.c_int64]),
     "lrcn_stage_batch": (C.c_int, [_H, C.c_int, C.c_int, _i64p, _i64p, C.c_int, C.c_int]),
     "lrcn_train_step_staged": (C.c_int, [_H, C.c_int, C.c_float, C.c_uint64, _f64p]),
@@ -271,6 +273,28 @@ class Handle:
         out = C.c_double()
         check(self.lib.lrcn_train_step(self._h, split, _i64(ids), _i64(tok), l, B, pdrop, seed, C.byref(out)))
         return float(out.value)
+
+    def train_epoch(self, split, sequence, input_ids, lengths, order=None, pdrop=0.0, seed=0):
+        """One epoch of train steps with the batches staged on the device (lrcn_train_epoch).  sequence: [n_rows][B] time-major
+        tokens (1-based), input_ids: [n_batches][B], lengths: [n_batches] rows per batch, order: batch indices to run.
+        Returns the per-step losses in execution order (batches longer than max_len are skipped)."""
+        seq = np.ascontiguousarray(sequence, dtype=np.int64)
+        ids = np.ascontiguousarray(input_ids, dtype=np.int64)
+        lens = np.ascontiguousarray(lengths, dtype=np.int64)
+        if ids.ndim != 2 or (seq.size and (seq.ndim != 2 or seq.shape[1] != ids.shape[1])) or lens.shape != (ids.shape[0],):
+            raise ValueError("sequence [n_rows][B], input_ids [n_batches][B], lengths [n_batches] expected")
+        n_batches, B = ids.shape
+        n_rows = seq.shape[0] if seq.size else 0
+        if n_rows == 0:
+            seq = np.zeros((1, B), dtype=np.int64)
+        ordr = None if order is None else np.ascontiguousarray(order, dtype=np.int64)
+        n_order = 0 if ordr is None else len(ordr)
+        losses = np.zeros(max(n_order if ordr is not None else n_batches, 1), dtype=np.float64)
+        steps = C.c_int64()
+        check(self.lib.lrcn_train_epoch(self._h, split, _i64(seq), n_rows, _i64(ids), _i64(lens), n_batches, B,
+                                        _i64(ordr) if n_order else None, n_order, pdrop, seed,
+                                        losses.ctypes.data_as(_f64p), C.byref(steps)))
+        return losses[:steps.value].tolist()
 
     def adam_update(self):
         check(self.lib.lrcn_adam_update(self._h))

@@ -119,6 +119,13 @@ void scatter_add_embed(cudaStream_t s, float* dWembT, const int* tok, const floa
 void adam_flat(cudaStream_t s, float* w, const float* g, float* m, float* v, size_t n, const StepScalars* sc,
                __nv_bfloat16* w_hi, __nv_bfloat16* w_lo);
 void split_bf16(cudaStream_t s, const float* x, size_t n, __nv_bfloat16* hi, __nv_bfloat16* lo);
+// ---- batch staging on the device (lrcn.jl:351-376): the epoch's token matrix and image ids are resident
+// image id -> feature-table row for a whole epoch: ids [n] (1-based wire ids), sorted_ids/rowof [n_tab]; unknown ids raise *err
+void epoch_lookup_rows(cudaStream_t s, const long long* ids, size_t n, const long long* sorted_ids, const int* rowof, int n_tab, int* rows_out, int* err);
+// inputs [bos, w1..wl] / targets [w1..wl, eos] / feature rows of ONE batch from the resident epoch data (lrcn.jl:556,563-577):
+// seq rows [row0, row0+l) of the [n_rows][ldB] int64 matrix, columns [col0, col0+B); tokens outside [1, V] raise *err
+void epoch_stage_batch(cudaStream_t s, const long long* seq, size_t row0, int l, int ldB, int col0, int B, int V, const int* rows_all, size_t rows_off,
+                       int* tok_in, int* tok_tgt, int* rows, int* err);
 void transpose2d(cudaStream_t s, const float* in, int rows, int cols, float* out);  // out[c][r] = in[r][c]
 void fill_l2_scratch(cudaStream_t s, float* buf, size_t n, float val);
 // one launch zeroing up to 16 fp32 ranges (16-byte aligned starts): accumulation targets of the step (split-K / stream-K GEMM

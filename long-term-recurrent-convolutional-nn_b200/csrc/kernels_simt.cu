@@ -821,6 +821,54 @@ void split_bf16(cudaStream_t s, const float* x, size_t n, __nv_bfloat16* hi, __n
   count_launch();
 }
 
+// ------------------------------------------------------------------------------------------
+// batch staging on the device (row f-1)
+// ------------------------------------------------------------------------------------------
+__global__ void epoch_lookup_rows_kernel(const long long* __restrict__ ids, size_t n, const long long* __restrict__ sorted_ids,
+                                         const int* __restrict__ rowof, int n_tab, int* __restrict__ rows_out, int* __restrict__ err) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long id = ids[i];
+  int lo = 0, hi = n_tab - 1, found = -1;
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1;
+    const long long v = sorted_ids[mid];
+    if (v == id) { found = mid; break; }
+    if (v < id) lo = mid + 1; else hi = mid - 1;
+  }
+  if (found < 0) { atomicExch(err, 1); rows_out[i] = 0; }  // lrcn.jl:602-605 "misssing features"
+  else rows_out[i] = rowof[found];
+}
+void epoch_lookup_rows(cudaStream_t s, const long long* ids, size_t n, const long long* sorted_ids, const int* rowof, int n_tab, int* rows_out, int* err) {
+  if (n == 0) return;
+  epoch_lookup_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ids, n, sorted_ids, rowof, n_tab, rows_out, err);
+  count_launch();
+}
+__global__ void epoch_stage_batch_kernel(const long long* __restrict__ seq, size_t row0, int l, int ldB, int col0, int B, int V,
+                                         const int* __restrict__ rows_all, size_t rows_off, int* __restrict__ tok_in, int* __restrict__ tok_tgt,
+                                         int* __restrict__ rows, int* __restrict__ err) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int T = l + 1;
+  if (idx >= T * B) return;
+  const int t = idx / B, i = idx - t * B;
+  if (t == 0) { tok_in[i] = 1; rows[i] = rows_all[rows_off + col0 + i]; }  // bos (0-based 1)   lrcn.jl:556
+  if (t < l) {
+    const long long tk = seq[(row0 + t) * (size_t)ldB + col0 + i];
+    int v = (int)tk - 1;
+    if (tk < 1 || tk > V) { atomicExch(err, 2); v = 2; }  // out-of-range token: flagged, replaced by unk so that no kernel reads out of bounds
+    tok_in[(size_t)(t + 1) * B + i] = v;   // next input              lrcn.jl:569
+    tok_tgt[(size_t)t * B + i] = v;        // target of step t         lrcn.jl:563-566
+  } else {
+    tok_tgt[(size_t)t * B + i] = 0;        // eos                      lrcn.jl:572-577
+  }
+}
+void epoch_stage_batch(cudaStream_t s, const long long* seq, size_t row0, int l, int ldB, int col0, int B, int V, const int* rows_all, size_t rows_off,
+                       int* tok_in, int* tok_tgt, int* rows, int* err) {
+  const int n = (l + 1) * B;
+  epoch_stage_batch_kernel<<<(n + 255) / 256, 256, 0, s>>>(seq, row0, l, ldB, col0, B, V, rows_all, rows_off, tok_in, tok_tgt, rows, err);
+  count_launch();
+}
+
 __global__ void transpose_kernel(const float* __restrict__ in, int rows, int cols, float* __restrict__ out) {
   __shared__ float tile[32][33];
   int c = blockIdx.x * 32 + threadIdx.x;

@@ -17,6 +17,8 @@
 #include <dlfcn.h>
 #include <math.h>
 
+#include <algorithm>
+
 static thread_local std::string g_err;
 static thread_local int g_last_code = 0;  // code of the last fail() on this thread (read by ApiGuard)
 int fail(int code, const char* fmt, ...) {
@@ -163,6 +165,9 @@ static int s_destroy(lrcn_handle* h) {
                   h->d_tok_tgt, h->d_rows, h->d_sc, h->p2p_ctl, h->d_loss_total, h->d_epoch, h->d_epoch_side, h->stage, h->d_counters, h->d_trace, h->g_last, h->g_ctok, h->g_stok, h->g_spar, h->g_hista, h->g_histb,
                   h->g_done, h->g_ndone, h->g_olen, h->g_rows, h->g_otok, h->l2_scratch, h->g_keep, h->g_omap, h->g_omap_s};
   for (void* p : ptrs) if (p) cudaFree(p);
+  for (void* q : {(void*)h->ep_seq, (void*)h->ep_ids, (void*)h->ep_rows, (void*)h->ep_loss, (void*)h->ep_err, (void*)h->tab[0].d_ids, (void*)h->tab[0].d_rowof,
+                  (void*)h->tab[1].d_ids, (void*)h->tab[1].d_rowof})
+    if (q) cudaFree(q);
   for (auto& s : h->slots) { if (s.tok_in) cudaFree(s.tok_in); if (s.tok_tgt) cudaFree(s.tok_tgt); if (s.rows) cudaFree(s.rows); }
   if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->h_sc) cudaFreeHost(h->h_sc);
@@ -523,13 +528,25 @@ static int s_load_features(lrcn_handle* h, int split, const int64_t* ids, const 
   if (!h || !ids || !feats || n <= 0 || split < 0 || split > 1) return fail(LRCN_ERR_ARG, "bad argument to lrcn_load_features");
   CK(cudaSetDevice(h->cfg.device));
   Table& t = h->tab[split];
-  if (t.d) { CK(cudaStreamSynchronize(h->stream)); cudaFree(t.d); t.d = nullptr; }
+  if (t.d) { CK(cudaStreamSynchronize(h->stream)); cudaFree(t.d); t.d = nullptr; cudaFree(t.d_ids); cudaFree(t.d_rowof); t.d_ids = nullptr; t.d_rowof = nullptr; }
   t.map.clear();
   CK(cudaMalloc(&t.d, (size_t)n * LRCN_F_CNN * 4));
   CK(cudaMemcpy(t.d, feats, (size_t)n * LRCN_F_CNN * 4, cudaMemcpyHostToDevice));
   t.n = n;
   t.map.reserve((size_t)n * 2);
   for (int64_t i = 0; i < n; i++) t.map[ids[i]] = (int)i;
+  {  // device-side lookup for the epoch-level calls: ids sorted ascending + the table row of each (later duplicates win, like the map)
+    std::vector<std::pair<long long, int>> pr;
+    pr.reserve(t.map.size());
+    for (auto& kv : t.map) pr.emplace_back((long long)kv.first, kv.second);
+    std::sort(pr.begin(), pr.end());
+    std::vector<long long> si(pr.size());
+    std::vector<int> ro(pr.size());
+    for (size_t i = 0; i < pr.size(); i++) { si[i] = pr[i].first; ro[i] = pr[i].second; }
+    CK(cudaMalloc(&t.d_ids, si.size() * 8)); CK(cudaMalloc(&t.d_rowof, ro.size() * 4));
+    CK(cudaMemcpy(t.d_ids, si.data(), si.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(t.d_rowof, ro.data(), ro.size() * 4, cudaMemcpyHostToDevice));
+  }
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);  // graphs bake the table pointer
   h->graphs.clear();
   return LRCN_OK;
@@ -1756,6 +1773,99 @@ extern "C" int lrcn_flush_l2(lrcn_handle* h) {
 extern "C" int lrcn_time_kernel(lrcn_handle* h, const char* name, int reps, float* avg_ms, double* algo_bytes, double* algo_flops) {
   ENTER(h);
   return s_time_kernel(is_group(h) ? h->members[0] : h, name, reps, avg_ms, algo_bytes, algo_flops);
+}
+
+// ------------------------------------------------------------------------------------------ epoch-level training
+// The hot loop of train1 (lrcn.jl:351-396) for one epoch in ONE call: the epoch's token matrix and image ids are uploaded
+// once, image ids are resolved to feature-table rows on the device, and every batch is staged by a small kernel from the
+// resident data (inputs [bos, w..], targets [w.., eos], feature rows: lrcn.jl:369-376,556,563-577) right before its step
+// graph -- no per-step host marshalling, H2D copy or synchronisation.  Batches longer than max_len are skipped like
+// lrcn.jl:353 skips l > 28.  ldB / col0: this handle's columns of a wider (global) batch in the single-process group mode.
+static int epoch_upload(lrcn_handle* h, int split, const int64_t* sequence, int64_t n_rows, const int64_t* input_ids, int64_t n_batches, int ldB) {
+  CK(cudaSetDevice(h->cfg.device));
+  if (split < 0 || split > 1 || !h->tab[split].d) return fail(LRCN_ERR_STATE, "no features loaded for split %d", split);
+  const size_t ns = (size_t)n_rows * ldB, ni = (size_t)n_batches * ldB;
+  if (ns > h->ep_seq_cap) { if (h->ep_seq) cudaFree(h->ep_seq); h->ep_seq = nullptr; CK(cudaMalloc(&h->ep_seq, ns * 8)); h->ep_seq_cap = ns; }
+  if (ni > h->ep_ids_cap) {
+    if (h->ep_ids) cudaFree(h->ep_ids);
+    if (h->ep_rows) cudaFree(h->ep_rows);
+    h->ep_ids = nullptr; h->ep_rows = nullptr;
+    CK(cudaMalloc(&h->ep_ids, ni * 8)); CK(cudaMalloc(&h->ep_rows, ni * 4)); h->ep_ids_cap = ni;
+  }
+  if (!h->ep_err) { CK(cudaMalloc(&h->ep_err, 4)); }
+  CK(cudaMemsetAsync(h->ep_err, 0, 4, h->stream));
+  CK(cudaMemcpyAsync(h->ep_seq, sequence, ns * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->ep_ids, input_ids, ni * 8, cudaMemcpyHostToDevice, h->stream));
+  g_counter = &h->counter;
+  epoch_lookup_rows(h->stream, h->ep_ids, ni, h->tab[split].d_ids, h->tab[split].d_rowof, (int)h->tab[split].map.size(), h->ep_rows, h->ep_err);
+  return LRCN_OK;
+}
+static int epoch_check(lrcn_handle* h) {
+  int err = 0;
+  CK(cudaMemcpyAsync(&err, h->ep_err, 4, cudaMemcpyDeviceToHost, h->stream));
+  int rc = sync_stream(h);
+  if (rc) return rc;
+  if (err == 1) return fail(LRCN_ERR_MISSING, "missing features for an image id of the epoch (lrcn.jl:602-605)");
+  if (err == 2) return fail(LRCN_ERR_ARG, "a token of the epoch lies outside [1,%d]", h->V);
+  return LRCN_OK;
+}
+
+extern "C" int lrcn_train_epoch(lrcn_handle* h, int split, const int64_t* sequence, int64_t n_rows, const int64_t* input_ids, const int64_t* lengths,
+                                int64_t n_batches, int B, const int64_t* order, int64_t n_order, float pdrop, uint64_t seed, double* losses_out,
+                                int64_t* steps_out) {
+  ENTER(h);
+  if (!sequence || !input_ids || !lengths || n_rows < 0 || n_batches <= 0 || B <= 0 || (n_order > 0 && !order))
+    return fail(LRCN_ERR_ARG, "bad argument to lrcn_train_epoch");
+  if (pdrop < 0.f || pdrop >= 1.f) return fail(LRCN_ERR_ARG, "pdrop must be in [0,1)");
+  std::vector<lrcn_handle*> hs;
+  if (is_group(h)) hs = h->members; else hs.push_back(h);
+  const int N = (int)hs.size();
+  const int maxB = h->cfg.max_batch, max_len = h->cfg.max_len;
+  if (B > maxB || B < N) return fail(LRCN_ERR_ARG, "B=%d outside [%d,%d]", B, N, maxB);
+  // start row of every batch in `sequence` (prefix sum of the lengths: lrcn.jl:336-342)
+  std::vector<int64_t> start((size_t)n_batches + 1, 0);
+  for (int64_t b = 0; b < n_batches; b++) {
+    if (lengths[b] < 0) return fail(LRCN_ERR_ARG, "negative caption length");
+    start[b + 1] = start[b] + lengths[b];
+  }
+  if (start[n_batches] > n_rows) return fail(LRCN_ERR_ARG, "lengths sum to %lld rows, sequence has %lld", (long long)start[n_batches], (long long)n_rows);
+  int rc;
+  for (lrcn_handle* m : hs) { rc = epoch_upload(m, split, sequence, n_rows, input_ids, n_batches, B); if (rc) return rc; }
+  for (lrcn_handle* m : hs) { rc = epoch_check(m); if (rc) return rc; }  // unknown ids fail the call before any step runs (like the per-step call)
+  const int64_t n_run_max = n_order > 0 ? n_order : n_batches;
+  for (lrcn_handle* m : hs)
+    if ((size_t)n_run_max > m->ep_loss_cap) { CK(cudaSetDevice(m->cfg.device)); if (m->ep_loss) cudaFree(m->ep_loss); m->ep_loss = nullptr; CK(cudaMalloc(&m->ep_loss, (size_t)n_run_max * 8)); m->ep_loss_cap = (size_t)n_run_max; }
+  int64_t steps = 0;
+  std::vector<double> denom;
+  for (int64_t k = 0; k < n_run_max; k++) {
+    const int64_t b = n_order > 0 ? order[k] : k;
+    if (b < 0 || b >= n_batches) return fail(LRCN_ERR_ARG, "order[%lld] = %lld outside [0,%lld)", (long long)k, (long long)b, (long long)n_batches);
+    const int l = (int)lengths[b];
+    if (l > max_len) continue;  // lrcn.jl:353: batches of captions longer than 28 are skipped
+    for (int i = 0; i < N; i++) {
+      lrcn_handle* m = hs[i];
+      int off = 0, bw = B;
+      if (N > 1) shard_rows(B, N, i, &off, &bw);
+      CK(cudaSetDevice(m->cfg.device));
+      g_counter = &m->counter;
+      epoch_stage_batch(m->stream, m->ep_seq, (size_t)start[b], l, B, off, bw, m->V, m->ep_rows, (size_t)b * B, m->d_tok_in, m->d_tok_tgt, m->d_rows, m->ep_err);
+      m->global_B = N > 1 ? B : 0;
+      rc = run_step(m, split, bw, l, pdrop, seed + (uint64_t)steps, 2);
+      if (rc) return rc;
+      CK(cudaMemcpyAsync(m->ep_loss + steps, m->loss_is_total ? m->d_loss_total : m->d_loss, 8, cudaMemcpyDeviceToDevice, m->stream));
+    }
+    denom.push_back((double)B * (l + 1) * (N > 1 ? 1 : hs[0]->nranks));
+    steps++;
+  }
+  for (lrcn_handle* m : hs) { rc = epoch_check(m); if (rc) return rc; }  // synchronises; out-of-range tokens surface here
+  if (losses_out && steps > 0) {
+    std::vector<double> tot((size_t)steps);
+    CK(cudaSetDevice(hs[0]->cfg.device));
+    CK(cudaMemcpy(tot.data(), hs[0]->ep_loss, (size_t)steps * 8, cudaMemcpyDeviceToHost));
+    for (int64_t k = 0; k < steps; k++) losses_out[k] = -tot[k] / denom[k];
+  }
+  if (steps_out) *steps_out = steps;
+  return LRCN_OK;
 }
 
 // ------------------------------------------------------------------------------------------ checkpoint

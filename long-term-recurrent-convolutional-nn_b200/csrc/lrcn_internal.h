@@ -34,6 +34,8 @@ struct Arena {
 struct Table {
   float* d = nullptr; int64_t n = 0;
   std::unordered_map<int64_t, int> map;
+  // device-side id -> row lookup (epoch-level calls): ids sorted ascending + the row of each
+  long long* d_ids = nullptr; int* d_rowof = nullptr;
 };
 constexpr int COLPART_ROWS = 296;  // 2 CTAs per SM
 struct Slot { int l = 0, B = 0, split = 0; int *tok_in = nullptr, *tok_tgt = nullptr, *rows = nullptr; };
@@ -61,6 +63,9 @@ struct lrcn_handle {
   Arena ws;
   Workspace o;
   int *d_tok_in = nullptr, *d_tok_tgt = nullptr, *d_rows = nullptr;
+  // epoch-resident data of lrcn_train_epoch (row f-1: batch staging on the device)
+  long long *ep_seq = nullptr, *ep_ids = nullptr; int* ep_rows = nullptr; double* ep_loss = nullptr; int* ep_err = nullptr;
+  size_t ep_seq_cap = 0, ep_ids_cap = 0, ep_loss_cap = 0;
   int* h_stage = nullptr;  // pinned: tok_in | tok_tgt | rows
   // step scalars: one device struct (graphs read it through a fixed pointer), fed from a RING of pinned host copies so that
   // the host never rewrites a pinned buffer whose H2D copy has not executed yet (calls that do not synchronise, e.g.

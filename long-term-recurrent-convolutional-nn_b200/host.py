@@ -110,14 +110,23 @@ class LRCN:
             index += int(lengths[t])
         return starts
 
-    def train1(self, seq, batch_size=None, pdrop=0.0, shuffle_seed=0, split=0, progress=None):
+    def train1(self, seq, batch_size=None, pdrop=0.0, shuffle_seed=0, split=0, progress=None, per_step=False):
         """One epoch of the hot loop lrcn.jl:351-396: shuffled batch order, skip l>28,
-        gradient + Adam per batch.  `lr`/`gclip` are ignored by the reference and so not taken."""
+        gradient + Adam per batch.  `lr`/`gclip` are ignored by the reference and so not taken.
+        Default: ONE library call for the epoch (batches staged on the device, no per-step host work; SURVEY 8 row f-1);
+        per_step=True or a progress callback drives one lrcn_train_step per batch instead.  Both give the same losses."""
         sequence, input_ids, lengths = seq
         batch_size = batch_size or self.batchsize
         starts = self._start_indices(lengths, batch_size)
         order = np.arange(0, len(lengths), batch_size)
         np.random.RandomState(shuffle_seed).shuffle(order)
+        if not per_step and progress is None and len(order):
+            blens = np.asarray(lengths, dtype=np.int64)[::batch_size]
+            seq_m = np.stack([np.asarray(r, dtype=np.int64) for r in sequence]) if len(sequence) else np.zeros((0, batch_size), np.int64)
+            ids_m = np.stack([np.asarray(r, dtype=np.int64) for r in input_ids])
+            losses = self.h.train_epoch(split, seq_m, ids_m, blens, order // batch_size, pdrop, self._step + 1)
+            self._step += len(losses)
+            return losses
         losses = []
         for t in order:
             l = int(lengths[t])

@@ -96,6 +96,24 @@ def test_single_process_group_matches_oracle_and_single_gpu(prec):
             assert merr < 2e-3 and verr < 2e-3
             # the summed gradient of the last train step is gathered from its owners
             assert all(np.isfinite(h.get_grad(k)).all() for k in range(1, 10))
+            # the epoch call on the group (each member stages its columns of the global batch on its own GPU) == per-step calls
+            h.set_model(model)
+            h.set_adam_step(0)
+            for k in range(1, 10):
+                h.set_adam_state(k, 0, np.zeros_like(model[k - 1])); h.set_adam_state(k, 1, np.zeros_like(model[k - 1]))
+            blens = [l, 2, 4]
+            seq_e = np.concatenate([synth.tokens(bl, Bg, V, seed=40 + i) for i, bl in enumerate(blens)])
+            img_e = np.stack([synth.image_ids(Bg, 32, seed=50 + i) for i in range(3)])
+            ep = h.train_epoch(0, seq_e, img_e, blens, np.array([2, 0, 1]), 0.4, seed=5)
+            w_ep = [h.get_param(k) for k in range(1, 10)]
+            h.set_model(model)
+            h.set_adam_step(0)
+            for k in range(1, 10):
+                h.set_adam_state(k, 0, np.zeros_like(model[k - 1])); h.set_adam_state(k, 1, np.zeros_like(model[k - 1]))
+            st = np.concatenate([[0], np.cumsum(blens)])
+            per = [h.train_step(0, img_e[b], seq_e[st[b]:st[b] + blens[b]], 0.4, 5 + i) for i, b in enumerate([2, 0, 1])]
+            np.testing.assert_allclose(ep, per, rtol=1e-6)
+            assert max(relerr(a - model[k], h.get_param(k + 1) - model[k]) for k, a in enumerate(w_ep)) < 1e-3
             # generation: images sharded over the GPUs, no collective; same captions as one GPU
             h.set_model(model)
             toks, lens, prob, _ = h.beam_search(1, ids[:4 * N + 1], 3, 6)

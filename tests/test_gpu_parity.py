@@ -334,6 +334,68 @@ def test_staged_train_steps_match_host_buffer_steps_and_oracle(prec):
             assert relerr(a - model[k - 1], ref[k - 1] - model[k - 1]) < 2e-2, f"staged steps vs oracle, param {k}"
 
 
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("pdrop", [0.0, 0.4])
+def test_train_epoch_on_device_equals_per_step_calls_and_oracle(prec, pdrop):
+    """lrcn_train_epoch (the epoch's batches are staged by a device kernel from resident data, image ids are
+    resolved on the device, no per-step host work) == the same batches through lrcn_train_step, step for step: same losses,
+    same weights, same Adam state -- and == the oracle's epoch at pdrop 0.  Covers the shuffled order, a batch that is
+    skipped because l > max_len (lrcn.jl:353), a repeated batch, an l = 1 batch and non-contiguous image ids."""
+    E, H1, H2, V, B = 64, 64, 64, 300, 8
+    model, feats, ids, _, _, _ = make_case(E, H1, H2, V, B, 5)
+    blens = [5, 3, 9, 1, 7, 8]          # 9 > max_len = 8: skipped
+    seq = np.concatenate([synth.tokens(l, B, V, seed=70 + b) for b, l in enumerate(blens)])          # [sum l][B], 1-based
+    img = np.stack([ids[synth.image_ids(B, len(ids), seed=80 + b) - 1] for b in range(len(blens))])   # [n_batches][B]
+    order = np.array([4, 0, 2, 5, 3, 1, 0], dtype=np.int64)
+    starts = np.concatenate([[0], np.cumsum(blens)])
+    with open_handle(E, H1, H2, V, B, 8, prec) as h, open_handle(E, H1, H2, V, B, 8, prec) as h2:
+        for x in (h, h2):
+            x.set_model(model)
+            x.load_features(0, ids, feats)
+        losses = h.train_epoch(0, seq, img, blens, order, pdrop, seed=11)
+        ref = [w.copy() for w in model]
+        opt = O.initparams(ref)
+        want, n = [], 0
+        for b in order:
+            l = blens[b]
+            if l > 8:
+                continue
+            tok = seq[starts[b]:starts[b] + l]
+            want.append(h2.train_step(0, img[b], tok, pdrop, 11 + n))
+            n += 1
+            if pdrop == 0.0:
+                L_ref = O.train_step(ref, opt, feats[(img[b] - 100) // 7 - 1], list(tok), range(0, l))
+                assert abs(want[-1] - L_ref) < 2 * RTOL * abs(L_ref)
+        assert len(losses) == 6 and h.get_adam_step() == h2.get_adam_step() == 6
+        # the same kernels on the same staged integers; fp32 atomics (loss sum, embedding gradient) reorder between runs
+        np.testing.assert_allclose(losses, want, rtol=1e-6)
+        for k in range(1, 10):
+            assert relerr(h.get_param(k) - model[k - 1], h2.get_param(k) - model[k - 1]) < 1e-3, f"param {k}"
+            assert relerr(h.get_adam_state(k, 0), h2.get_adam_state(k, 0)) < 1e-3, f"adam m {k}"
+            if pdrop == 0.0:
+                assert relerr(h.get_param(k) - model[k - 1], ref[k - 1] - model[k - 1]) < 2e-2, f"epoch vs oracle, param {k}"
+        # natural order (order = None) and a second epoch on the same handle (buffers are reused)
+        l2 = h.train_epoch(0, seq, img, blens, None, pdrop, seed=30)
+        w2 = [h2.train_step(0, img[b], seq[starts[b]:starts[b] + blens[b]], pdrop, 30 + i)
+              for i, b in enumerate(b for b in range(len(blens)) if blens[b] <= 8)]
+        np.testing.assert_allclose(l2, w2, rtol=1e-5)
+        # an image id without features fails the call before any step runs; a token outside the vocabulary is reported
+        before = h.get_param(9).copy()
+        bad = img.copy()
+        bad[3, 2] = 999999
+        with pytest.raises(abi.LrcnError) as ei:
+            h.train_epoch(0, seq, bad, blens, order, pdrop, seed=1)
+        assert ei.value.code == abi.ERR_MISSING
+        assert np.array_equal(h.get_param(9), before) and h.get_adam_step() == 11
+        badseq = seq.copy()
+        badseq[2, 1] = V + 1
+        with pytest.raises(abi.LrcnError) as ei:
+            h.train_epoch(0, badseq, img, blens, np.array([0]), pdrop, seed=1)
+        assert ei.value.code == abi.ERR_ARG
+        with pytest.raises(abi.LrcnError):
+            h.train_epoch(0, seq, img, blens, np.array([6]), pdrop, seed=1)   # order entry outside [0, n_batches)
+
+
 def test_sticky_error_state_and_adam_update_guard():
     with open_handle(16, 16, 16, 40, 4, 3, abi.PREC_FP32) as h:
         h.load_features(0, np.arange(1, 9), synth.features(8))

@@ -26,6 +26,18 @@ class FakeHandle:
         self.calls.append(("train", split, np.array(ids), np.array(tok), pdrop, seed))
         return float(tok.shape[0])
 
+    def train_epoch(self, split, sequence, input_ids, lengths, order, pdrop, seed):
+        """What lrcn_train_epoch does with its arguments, restated: batch b owns lengths[b] rows of `sequence` from the prefix sum."""
+        self.calls.append(("epoch", split, len(order)))
+        starts = np.concatenate([[0], np.cumsum(lengths)])
+        out = []
+        for b in order:
+            l = int(lengths[b])
+            if l > 28:
+                continue
+            out.append(self.train_step(split, input_ids[b], sequence[starts[b]:starts[b] + l], pdrop, seed + len(out)))
+        return out
+
     def loss(self, split, ids, tok):
         self.calls.append(("loss", split, np.array(ids), np.array(tok)))
         l, B = tok.shape
@@ -62,10 +74,12 @@ def test_two_layers_only():
         host.LRCN([8], 20, 8, 2)
 
 
-def test_train1_visits_every_batch_once_in_shuffled_order_and_skips_long_captions(net):
+@pytest.mark.parametrize("per_step", [False, True])
+def test_train1_visits_every_batch_once_in_shuffled_order_and_skips_long_captions(net, per_step):
     per_batch = [3, 5, 29, 7, 28]  # 29 > 28 is skipped (lrcn.jl:353)
     seq = make_seq(per_batch)
-    losses = net.train1(seq, pdrop=0.4, shuffle_seed=3)
+    losses = net.train1(seq, pdrop=0.4, shuffle_seed=3, per_step=per_step)
+    assert len([c for c in net.h.calls if c[0] == "epoch"]) == (0 if per_step else 1)  # default: one library call per epoch
     calls = [c for c in net.h.calls if c[0] == "train"]
     assert len(calls) == 4 and len(losses) == 4
     seen = sorted(c[3].shape[0] for c in calls)
@@ -78,9 +92,11 @@ def test_train1_visits_every_batch_once_in_shuffled_order_and_skips_long_caption
         assert np.array_equal(ids, seq[1][b])                                   # image ids of that batch
         assert np.array_equal(tok, np.stack(seq[0][starts[b]:starts[b] + l]))    # its l token rows, time-major
     assert [c[5] for c in calls] == [1, 2, 3, 4]                                # a fresh dropout seed per step
+    net.train1(seq, pdrop=0.4, shuffle_seed=4, per_step=per_step)
+    assert [c[5] for c in net.h.calls if c[0] == "train"][4:] == [5, 6, 7, 8]   # ... continuing over epochs
     again = host.LRCN([8, 8], 20, 8, 2)
-    again.train1(seq, pdrop=0.4, shuffle_seed=3)
-    assert [c[3].shape[0] for c in again.h.calls] == [c[3].shape[0] for c in calls]  # the shuffled order is a function of the seed
+    again.train1(seq, pdrop=0.4, shuffle_seed=3, per_step=not per_step)
+    assert [c[3].shape[0] for c in again.h.calls if c[0] == "train"] == [c[3].shape[0] for c in calls]  # the shuffled order is a function of the seed
 
 
 def test_average_loss_is_token_weighted_and_skips_long_captions(net):
