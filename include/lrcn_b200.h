@@ -133,6 +133,11 @@ LRCN_API int lrcn_train_step(lrcn_handle* h, int split, const int64_t* image_ids
 LRCN_API int lrcn_train_epoch(lrcn_handle* h, int split, const int64_t* sequence, int64_t n_rows, const int64_t* input_ids,
                      const int64_t* lengths, int64_t n_batches, int B, const int64_t* order, int64_t n_order, float pdrop,
                      uint64_t seed, double* losses_out, int64_t* steps_out);
+/* ---- average_loss over a whole split in ONE call (lrcn.jl:407-486): forward only, pdrop 0, batches in natural order, staged on
+ * the device like lrcn_train_epoch; l > max_len batches are skipped (lrcn.jl:431).  Returns the sum of the target log-probs and
+ * the token count, like lrcn_loss: average_loss = -sum / count (lrcn.jl:476-486). */
+LRCN_API int lrcn_loss_epoch(lrcn_handle* h, int split, const int64_t* sequence, int64_t n_rows, const int64_t* input_ids,
+                    const int64_t* lengths, int64_t n_batches, int B, double* sum_logp_out, int64_t* count_out);
 /* per-token target log-probs of the last lrcn_loss/lrcn_grad call, (l+1) x B time-major */
 LRCN_API int lrcn_get_token_logps(lrcn_handle* h, float* out, int64_t n);
 

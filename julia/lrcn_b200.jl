@@ -160,6 +160,15 @@ function train_epoch!(net, split, sequence, input_ids, lengths, batchsize, order
     return losses[1:steps[]]
 end
 
+# average_loss (lrcn.jl:407-486) over a whole split in one call; returns -sum(logp)/count like the reference
+function average_loss(net, split, sequence, input_ids, lengths, batchsize)
+    seq = convert(Matrix{Int64}, hcat(sequence...)); ids = convert(Matrix{Int64}, hcat(input_ids...))
+    blens = convert(Vector{Int64}, lengths[1:batchsize:end]); s = Ref{Float64}(0); n = Ref{Int64}(0)
+    check(ccall((:lrcn_loss_epoch, lib), Cint, (Ptr{Void}, Cint, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Int64}, Int64, Cint, Ptr{Float64}, Ptr{Int64}),
+                net.handle, split, seq, size(seq,2), ids, blens, length(blens), size(ids,1), s, n))
+    return -s[] / n[]
+end
+
 function token_logps(net, l, B)
     out = Array(Float32, B, l+1)
     check(ccall((:lrcn_get_token_logps, lib), Cint, (Ptr{Void}, Ptr{Float32}, Int64), net.handle, out, length(out)))

@@ -58,6 +58,7 @@ SIGNATURES = {
     "lrcn_train_step": (C.c_int, [_H, C.c_int, _i64p, _i64p, C.c_int, C.c_int, C.c_float, C.c_uint64, _f64p]),
     "lrcn_train_epoch": (C.c_int, [_H, C.c_int, _i64p, C.c_int64, _i64p, _i64p, C.c_int64, C.c_int, _i64p, C.c_int64, C.c_float, C.c_uint64,
                                    _f64p, _i64p]),
+    "lrcn_loss_epoch": (C.c_int, [_H, C.c_int, _i64p, C.c_int64, _i64p, _i64p, C.c_int64, C.c_int, _f64p, _i64p]),
     "lrcn_get_token_logps": (C.c_int, [_H, _f32p, C.c_int64]),
     "lrcn_stage_batch": (C.c_int, [_H, C.c_int, C.c_int, _i64p, _i64p, C.c_int, C.c_int]),
     "lrcn_train_step_staged": (C.c_int, [_H, C.c_int, C.c_float, C.c_uint64, _f64p]),
@@ -295,6 +296,19 @@ class Handle:
                                         _i64(ordr) if n_order else None, n_order, pdrop, seed,
                                         losses.ctypes.data_as(_f64p), C.byref(steps)))
         return losses[:steps.value].tolist()
+
+    def loss_epoch(self, split, sequence, input_ids, lengths):
+        """Sum of target log-probs and token count over all batches of a split in one call (lrcn_loss_epoch)."""
+        seq = np.ascontiguousarray(sequence, dtype=np.int64)
+        ids = np.ascontiguousarray(input_ids, dtype=np.int64)
+        lens = np.ascontiguousarray(lengths, dtype=np.int64)
+        n_batches, B = ids.shape
+        n_rows = seq.shape[0] if seq.size else 0
+        if n_rows == 0:
+            seq = np.zeros((1, B), dtype=np.int64)
+        s, n = C.c_double(), C.c_int64()
+        check(self.lib.lrcn_loss_epoch(self._h, split, _i64(seq), n_rows, _i64(ids), _i64(lens), n_batches, B, C.byref(s), C.byref(n)))
+        return float(s.value), int(n.value)
 
     def adam_update(self):
         check(self.lib.lrcn_adam_update(self._h))

@@ -1237,11 +1237,182 @@ __global__ void __launch_bounds__(THREADS) beam_row_topk2_kernel(const float* __
     }
   }
 }
+// Third generation: the row lives in REGISTERS (NV4 float4 per thread, every load of the row in flight at once), shared memory
+// holds only the candidate list; the row is dumped to shared memory only for the exact fallback.  The shared-memory staging of
+// topk2 serialised a global round trip, three shared-memory passes and four block barriers per row with 4-5 CTAs per SM (0.30 of
+// HBM at V = 10000); here the passes run on registers.  Same arithmetic in the same order per element => same results.
+// Needs V % 4 == 0, 16-byte aligned rows and V <= 4 * THREADS * NV4.
+template <bool FROM_LOGITS, int NV4>
+__global__ void __launch_bounds__(256, 3) beam_row_topk3_kernel(const float* __restrict__ in, int ld, int R, int V, int K,
+                                                             const float* __restrict__ parent_prob, int* __restrict__ cand_tok,
+                                                             float* __restrict__ cand_score, float* __restrict__ cand_lp) {
+  extern __shared__ __align__(16) float row[];  // fallback only
+  constexpr int THREADS = 256, NW = THREADS / 32;
+  __shared__ float2 wred[NW];
+  __shared__ float wtop[NW][TOPK_MAXK + 1];
+  __shared__ float cv[TOPK_CAP];
+  __shared__ int ci[TOPK_CAP];
+  __shared__ int ccount;
+  __shared__ TopPair pred[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int V4 = V >> 2;
+  for (int r = blockIdx.x; r < R; r += gridDim.x) {  // persistent over rows
+    const float4* a4 = reinterpret_cast<const float4*>(in + (size_t)r * ld);
+    float4 x[NV4];
+#pragma unroll
+    for (int i = 0; i < NV4; i++) {
+      const int q = threadIdx.x + THREADS * i;
+      x[i] = q < V4 ? __ldg(a4 + q) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+    __syncthreads();  // the previous row's shared state is no longer read
+    if (threadIdx.x == 0) ccount = 0;
+    float tmax = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NV4; i++) tmax = fmaxf(fmaxf(tmax, fmaxf(x[i].x, x[i].y)), fmaxf(x[i].z, x[i].w));
+    if (FROM_LOGITS) {
+      float m = tmax, ssum = 0.f;
+      if (tmax != -INFINITY) {
+#pragma unroll
+        for (int i = 0; i < NV4; i++)
+          if (threadIdx.x + THREADS * i < V4) ssum += (__expf(x[i].x - tmax) + __expf(x[i].y - tmax)) + (__expf(x[i].z - tmax) + __expf(x[i].w - tmax));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, ssum, o);
+        const float mn = fmaxf(m, m2);
+        ssum = (m == -INFINITY ? 0.f : ssum * __expf(m - mn)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mn));
+        m = mn;
+      }
+      if (lane == 0) wred[warp] = make_float2(m, ssum);
+    }
+    {  // per-warp top-K of the thread maxima (K rounds, one lane removed per round)
+      float cur = tmax;
+      for (int k = 0; k < K; k++) {
+        float best = cur;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+        const unsigned int holders = __ballot_sync(0xffffffffu, cur == best);
+        if (lane == __ffs(holders) - 1) { cur = -INFINITY; wtop[warp][k] = best; }
+      }
+    }
+    __syncthreads();
+    float mx = 0.f, lse = 0.f;
+    if (FROM_LOGITS) {
+      float mm = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < NW; w++) mm = fmaxf(mm, wred[w].x);
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; w++) tot += wred[w].x == -INFINITY ? 0.f : wred[w].y * __expf(wred[w].x - mm);
+      mx = mm; lse = logf(tot);
+    }
+    float tau;  // K-th largest of the NW*K per-warp values: a lower bound of the K-th largest element
+    {
+      float mine[3];  // 8 * 11 = 88 <= 3 * 32
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        const int c = lane + 32 * q;
+        mine[q] = (c < NW * K) ? wtop[c / K][c % K] : -INFINITY;
+      }
+      tau = -INFINITY;
+      for (int k = 0; k < K; k++) {
+        float best = fmaxf(fmaxf(mine[0], mine[1]), mine[2]);
+        float wb = best;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wb = fmaxf(wb, __shfl_xor_sync(0xffffffffu, wb, o));
+        tau = wb;
+        const unsigned int holders = __ballot_sync(0xffffffffu, best == wb);
+        if (lane == __ffs(holders) - 1) {
+          bool removed = false;
+#pragma unroll
+          for (int q = 0; q < 3; q++) if (!removed && mine[q] == wb) { mine[q] = -INFINITY; removed = true; }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV4; i++) {  // candidates: every element >= tau (padding is -inf: never a candidate unless tau = -inf, where q < V4 guards)
+      const int q = threadIdx.x + THREADS * i;
+      const float xs[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+#pragma unroll
+      for (int e = 0; e < 4; e++)
+        if (xs[e] >= tau && q < V4) {
+          const int pos = atomicAdd(&ccount, 1);
+          if (pos < TOPK_CAP) { cv[pos] = xs[e]; ci[pos] = 4 * q + e; }
+        }
+    }
+    __syncthreads();
+    const int nc = ccount;
+    const float pp = parent_prob[r];
+    if (nc <= TOPK_CAP) {
+      if (warp == 0) {
+        constexpr int PER = TOPK_CAP / 32;
+        float pv[PER], pl[PER]; int pi[PER];
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+          const int c = lane + 32 * q;
+          pv[q] = -INFINITY; pi[q] = 0x7fffffff; pl[q] = 0.f;
+          if (c < nc) {
+            const float xc = cv[c];
+            pl[q] = FROM_LOGITS ? ((xc - mx) - lse) : 0.f;
+            pv[q] = FROM_LOGITS ? expf((xc - mx) - lse) : xc;
+            pi[q] = ci[c];
+          }
+        }
+        for (int k = 0; k < K; k++) {
+          TopPair best; best.v = -INFINITY; best.i = 0x7fffffff;
+#pragma unroll
+          for (int q = 0; q < PER; q++) { TopPair c; c.v = pv[q]; c.i = pi[q]; best = top_better(best, c); }
+          best = warp_top(best);
+#pragma unroll
+          for (int q = 0; q < PER; q++)
+            if (pi[q] == best.i) {  // indices are unique: exactly one lane owns the winner and writes it
+              cand_tok[(size_t)r * K + k] = best.i;
+              cand_score[(size_t)r * K + k] = __fmul_rn(best.v, pp);  // pmaxes = ynorm[xmaxes]*current_probability (lrcn.jl:657)
+              cand_lp[(size_t)r * K + k] = FROM_LOGITS ? pl[q] : logf(best.v);
+              pv[q] = -INFINITY; pi[q] = 0x7fffffff;
+            }
+        }
+      }
+    } else {
+      // exact fallback: K rounds of block argmax over the whole row on the probabilities themselves (row dumped to shared memory)
+#pragma unroll
+      for (int i = 0; i < NV4; i++) {
+        const int q = threadIdx.x + THREADS * i;
+        if (q < V4) {
+          float4 y = x[i];
+          if (FROM_LOGITS) { y.x = expf((y.x - mx) - lse); y.y = expf((y.y - mx) - lse); y.z = expf((y.z - mx) - lse); y.w = expf((y.w - mx) - lse); }
+          *reinterpret_cast<float4*>(row + 4 * q) = y;
+        }
+      }
+      for (int k = 0; k < K; k++) {
+        __syncthreads();
+        TopPair p; p.v = -INFINITY; p.i = 0x7fffffff;
+        for (int j = threadIdx.x; j < V; j += blockDim.x) { TopPair c; c.v = row[j]; c.i = j; p = top_better(p, c); }
+        p = block_top(p, pred);
+        if (threadIdx.x == 0) {
+          cand_tok[(size_t)r * K + k] = p.i;
+          cand_score[(size_t)r * K + k] = __fmul_rn(p.v, pp);
+          cand_lp[(size_t)r * K + k] = logf(p.v);
+          row[p.i] = -1.f;  // exclude from later rounds
+        }
+      }
+    }
+  }
+}
 static void beam_topk_launch(cudaStream_t s, bool from_logits, const float* in, int ld, int R, int V, int K,
                              const float* parent_prob, int* cand_tok, float* cand_score, float* cand_lp) {
   const size_t smem = ((size_t)V + 4) * sizeof(float);
   const int grid = R < 148 * 4 ? R : 148 * 4;
   static const bool v1 = getenv("LRCN_TOPK_V1") != nullptr;
+  static const bool no_v3 = getenv("LRCN_TOPK_V2") != nullptr;
+  constexpr int NV4 = 11;  // V <= 11264 (COCO: 10000 / 10636)
+  if (!v1 && !no_v3 && K <= TOPK_MAXK && V % 4 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && V > 4096 && V <= 4 * 256 * NV4) {
+    const int g3 = R < 148 * 3 ? R : 148 * 3;  // 3 CTAs per SM (registers)
+    if (from_logits) beam_row_topk3_kernel<true, NV4><<<g3, 256, smem, s>>>(in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+    else beam_row_topk3_kernel<false, NV4><<<g3, 256, smem, s>>>(in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+    count_launch();
+    return;
+  }
   if (!v1 && K <= TOPK_MAXK) {
     static const int th = getenv("LRCN_TOPK_THREADS") ? atoi(getenv("LRCN_TOPK_THREADS")) : 256;
     const int g2 = R < 148 * 8 ? R : 148 * 8;

@@ -1810,18 +1810,20 @@ static int epoch_check(lrcn_handle* h) {
   return LRCN_OK;
 }
 
-extern "C" int lrcn_train_epoch(lrcn_handle* h, int split, const int64_t* sequence, int64_t n_rows, const int64_t* input_ids, const int64_t* lengths,
-                                int64_t n_batches, int B, const int64_t* order, int64_t n_order, float pdrop, uint64_t seed, double* losses_out,
-                                int64_t* steps_out) {
-  ENTER(h);
+// mode 2: train steps (losses_out = mean NLL per step); mode 0: forward only (losses_out = SUM of log-probs per step, count_out = tokens)
+static int epoch_run(lrcn_handle* h, int mode, int split, const int64_t* sequence, int64_t n_rows, const int64_t* input_ids, const int64_t* lengths,
+                     int64_t n_batches, int B, const int64_t* order, int64_t n_order, float pdrop, uint64_t seed, double* losses_out,
+                     int64_t* steps_out, int64_t* count_out) {
   if (!sequence || !input_ids || !lengths || n_rows < 0 || n_batches <= 0 || B <= 0 || (n_order > 0 && !order))
-    return fail(LRCN_ERR_ARG, "bad argument to lrcn_train_epoch");
+    return fail(LRCN_ERR_ARG, "bad argument to lrcn_train_epoch / lrcn_loss_epoch");
   if (pdrop < 0.f || pdrop >= 1.f) return fail(LRCN_ERR_ARG, "pdrop must be in [0,1)");
   std::vector<lrcn_handle*> hs;
   if (is_group(h)) hs = h->members; else hs.push_back(h);
   const int N = (int)hs.size();
   const int maxB = h->cfg.max_batch, max_len = h->cfg.max_len;
   if (B > maxB || B < N) return fail(LRCN_ERR_ARG, "B=%d outside [%d,%d]", B, N, maxB);
+  int64_t count = 0;
+  int last_l_run = -1;
   // start row of every batch in `sequence` (prefix sum of the lengths: lrcn.jl:336-342)
   std::vector<int64_t> start((size_t)n_batches + 1, 0);
   for (int64_t b = 0; b < n_batches; b++) {
@@ -1850,21 +1852,48 @@ extern "C" int lrcn_train_epoch(lrcn_handle* h, int split, const int64_t* sequen
       g_counter = &m->counter;
       epoch_stage_batch(m->stream, m->ep_seq, (size_t)start[b], l, B, off, bw, m->V, m->ep_rows, (size_t)b * B, m->d_tok_in, m->d_tok_tgt, m->d_rows, m->ep_err);
       m->global_B = N > 1 ? B : 0;
-      rc = run_step(m, split, bw, l, pdrop, seed + (uint64_t)steps, 2);
+      rc = run_step(m, split, bw, l, pdrop, seed + (uint64_t)steps, mode);
       if (rc) return rc;
       CK(cudaMemcpyAsync(m->ep_loss + steps, m->loss_is_total ? m->d_loss_total : m->d_loss, 8, cudaMemcpyDeviceToDevice, m->stream));
     }
     denom.push_back((double)B * (l + 1) * (N > 1 ? 1 : hs[0]->nranks));
+    count += (int64_t)B * (l + 1);
+    last_l_run = l;
     steps++;
   }
   for (lrcn_handle* m : hs) { rc = epoch_check(m); if (rc) return rc; }  // synchronises; out-of-range tokens surface here
   if (losses_out && steps > 0) {
     std::vector<double> tot((size_t)steps);
-    CK(cudaSetDevice(hs[0]->cfg.device));
-    CK(cudaMemcpy(tot.data(), hs[0]->ep_loss, (size_t)steps * 8, cudaMemcpyDeviceToHost));
-    for (int64_t k = 0; k < steps; k++) losses_out[k] = -tot[k] / denom[k];
+    // training: the exchange kernel already summed the loss over the members; forward only: every member holds its columns' sum
+    for (int i = 0; i < (mode == 0 ? N : 1); i++) {
+      CK(cudaSetDevice(hs[i]->cfg.device));
+      CK(cudaMemcpy(tot.data(), hs[i]->ep_loss, (size_t)steps * 8, cudaMemcpyDeviceToHost));
+      for (int64_t k = 0; k < steps; k++) losses_out[k] = mode == 0 ? (i == 0 ? tot[k] : losses_out[k] + tot[k]) : -tot[k] / denom[k];
+    }
   }
   if (steps_out) *steps_out = steps;
+  if (count_out) *count_out = count;
+  if (N > 1 && last_l_run >= 0) { h->last_B = B; h->last_l = last_l_run; }
+  return LRCN_OK;
+}
+extern "C" int lrcn_train_epoch(lrcn_handle* h, int split, const int64_t* sequence, int64_t n_rows, const int64_t* input_ids, const int64_t* lengths,
+                                int64_t n_batches, int B, const int64_t* order, int64_t n_order, float pdrop, uint64_t seed, double* losses_out,
+                                int64_t* steps_out) {
+  ENTER(h);
+  return epoch_run(h, 2, split, sequence, n_rows, input_ids, lengths, n_batches, B, order, n_order, pdrop, seed, losses_out, steps_out, nullptr);
+}
+// average_loss (lrcn.jl:407-486) for a whole split in one call: forward only, pdrop = 0, batches in natural order
+extern "C" int lrcn_loss_epoch(lrcn_handle* h, int split, const int64_t* sequence, int64_t n_rows, const int64_t* input_ids, const int64_t* lengths,
+                               int64_t n_batches, int B, double* sum_logp_out, int64_t* count_out) {
+  ENTER(h);
+  if (n_batches <= 0) return fail(LRCN_ERR_ARG, "bad argument to lrcn_loss_epoch");
+  std::vector<double> sums((size_t)n_batches, 0.0);
+  int64_t steps = 0;
+  int rc = epoch_run(h, 0, split, sequence, n_rows, input_ids, lengths, n_batches, B, nullptr, 0, 0.f, 0, sums.data(), &steps, count_out);
+  if (rc) return rc;
+  double s = 0.0;
+  for (int64_t k = 0; k < steps; k++) s += sums[k];
+  if (sum_logp_out) *sum_logp_out = s;
   return LRCN_OK;
 }
 

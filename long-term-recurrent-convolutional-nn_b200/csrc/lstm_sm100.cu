@@ -38,10 +38,11 @@ constexpr int A_SLICE = (LM / CL) * LBK * 2;  // 2 KiB: the 16 rows this CTA loa
 constexpr int NT = 64;                        // accumulator columns per CTA (fwd: 16 units x 4 gates; bwd: 64 units)
 constexpr int B_HALF = NT * LBK * 2;          // 8 KiB
 constexpr int STAGE = 2 * A_HALF + 2 * B_HALF;  // 32 KiB
-constexpr int STAGES = 6;
+constexpr int STAGES = 3;                       // 96 KiB of stages: TWO step CTAs are resident per SM (the grid of a large layer is > 148 CTAs)
 constexpr int RED_BYTES = CL * LM * (NT / CL) * 4;  // 16 KiB: split-K partials received from the cluster (backward)
-constexpr int L_SMEM = STAGES * STAGE + RED_BYTES + 1024 + 256;
-constexpr uint32_t L_TMEM_COLS = 64;
+constexpr int L_SMEM = STAGES * STAGE + RED_BYTES + 256 + 768;  // 115712 B = (228 KiB - 2 x 1 KiB reserved) / 2
+constexpr uint32_t L_TMEM_COLS = 128;           // stacked accumulator: 128 lanes {hi rows; lo rows} x 128 columns {* W_hi | * W_lo}
+constexpr int XLD = 68;                         // padded row (floats) of the lo*hi hand-over buffer [64 rows][64 columns], aliased on stage 0
 
 __device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_smem_addr, uint32_t cta) {
   uint32_t r;
@@ -51,6 +52,12 @@ __device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_smem_addr, uint32_
 __device__ __forceinline__ void dsmem_st_f4(uint32_t addr, float4 v) {
   asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+#define LRCN_TMEM_LD_16(taddr, v)                                                                                           \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"      \
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), \
+                 "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                                \
+               : "r"(taddr)                                                                                                  \
+               : "memory")
 #define LRCN_TMEM_LD_8(taddr, v)                                                                         \
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                  \
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) \
@@ -83,11 +90,13 @@ struct StepSmem {
   uint32_t base, full_bar0, empty_bar0, tfull_bar;
   uint32_t* tmem_slot;
   float* red;
+  float* x;   // hand-over buffer [LM][XLD]: stage 0, free once the accumulator is committed (every load into it has been consumed)
 };
 __device__ __forceinline__ StepSmem step_smem(uint8_t* smem_raw) {
   StepSmem s;
   s.base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // same offset in every CTA of the cluster
   uint8_t* al = smem_raw + (s.base - smem_u32(smem_raw));
+  s.x = reinterpret_cast<float*>(al);
   s.red = reinterpret_cast<float*>(al + STAGES * STAGE);
   uint64_t* bars = reinterpret_cast<uint64_t*>(al + STAGES * STAGE + RED_BYTES);
   s.full_bar0 = smem_u32(bars);
@@ -99,23 +108,22 @@ __device__ __forceinline__ StepSmem step_smem(uint8_t* smem_raw) {
 // MMA issue loop shared by both directions.  Called by the WHOLE (converged) warp: the loop runs on warp-uniform values and one
 // elected lane issues, so the descriptors stay in uniform registers (see elect_one(); inside `if (lane == 0)` every
 // tcgen05.mma was wrapped in an ELECT / R2UR / branch waterfall: ~125 clk per MMA instead of ~80).
+// STACKED SPLIT MMA (as in the sequence kernels): the stage holds {A_hi 64 rows; A_lo 64 rows} and {B_hi 64; B_lo 64} back to
+// back, each a valid 128-row K-major SWIZZLE_128B tile, so ONE 128x128x16 tcgen05.mma per k-step yields all split products:
+//   lanes 0-63 x cols 0-63: A_hi*B_hi | lanes 0-63 x cols 64-127: A_hi*B_lo | lanes 64-127 x cols 0-63: A_lo*B_hi | (lo*lo ignored)
+// -- a third of the instructions of three M=64 MMAs (the step is bound by MMA instructions and operand delivery, not flops).
 __device__ __forceinline__ void step_mma_loop(const StepSmem& sm, uint32_t tmem_base_any, int num_kb, bool mcast_release) {
-  const uint32_t idesc = idesc_bf16(LM, NT, false, false);
+  const uint32_t idesc = idesc_bf16(128, 128, false, false);
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_any, 0);
   for (int i = 0; i < num_kb; i++) {
     const int s = i % STAGES;
     mbar_wait(sm.full_bar0 + 8 * s, (i / STAGES) & 1);
     tc_fence_after();
     const uint32_t st = sm.base + s * STAGE;
-    const uint32_t a_hi = desc_lo_kmajor(st), a_lo = desc_lo_kmajor(st + A_HALF);
-    const uint32_t b_hi = desc_lo_kmajor(st + 2 * A_HALF), b_lo = desc_lo_kmajor(st + 2 * A_HALF + B_HALF);
+    const uint32_t a = desc_lo_kmajor(st), b = desc_lo_kmajor(st + 2 * A_HALF);
     if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < LBK / 16; k++) {
-        umma_bf16_lo(tmem_base, a_lo + 2u * k, b_hi + 2u * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
-        umma_bf16_lo(tmem_base, a_hi + 2u * k, b_lo + 2u * k, idesc, 1u);
-        umma_bf16_lo(tmem_base, a_hi + 2u * k, b_hi + 2u * k, idesc, 1u);
-      }
+      for (int k = 0; k < LBK / 16; k++) umma_bf16_lo(tmem_base, a + 2u * k, b + 2u * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
       if (mcast_release) umma_commit_mcast(sm.empty_bar0 + 8 * s, (uint16_t)((1u << CL) - 1));  // free in MY smem: tell all CL producers
       else umma_commit(sm.empty_bar0 + 8 * s);
     }
@@ -124,13 +132,15 @@ __device__ __forceinline__ void step_mma_loop(const StepSmem& sm, uint32_t tmem_
   if (elect_one()) umma_commit(sm.tfull_bar);
   __syncwarp();
 }
+// pair barrier of the hi-row warp and the lo-row warp that hold the same 32 batch rows and column half (64 threads)
+__device__ __forceinline__ void pair_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
 // ---------------------------------------------------------------------------------------------- forward step
 // A = h_{t-1} tile [64 rows][K=H] (each CTA loads 16 rows and multicasts them to the 4 CTAs of its cluster),
 // B = gate-interleaved W_h rows [64][K].  UMMA M=64 accumulator: tile row r lives in TMEM lane (r%16) + 32*(r/16).
 // Epilogue: 8 warps; warp (quad, half) reads units [8*half, +8) of its 16 rows, lanes 16-31 take units 4-7 by shuffle,
 // so all 256 threads finish 4 units each.
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(L_THREADS, 1)
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(L_THREADS, 2)
 lstm_fwd_step_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                      const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const StepParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -174,30 +184,56 @@ lstm_fwd_step_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   } else if (warp == 1) {
     if (num_kb > 0) step_mma_loop(sm, tmem_base, num_kb, true);
   } else {
-    const int ew = warp - 2, quad = warp & 3, half = ew >> 2;  // warp%4 fixes the TMEM lane quadrant
-    constexpr int NH = NT / 4;                                 // 16 units per CTA; columns are unit-major: col = u*4 + gate
-    uint32_t v[32];
+    // warp%4 fixes the TMEM lane quadrant: quadrants 0,1 hold the h_hi rows 0-63, quadrants 2,3 the h_lo rows 0-63 of the tile.
+    // The (quad, half) warp and the (quad+2, half) warp own the same 32 rows x 8 units (32 columns, unit-major: col = u*4 + gate):
+    // the hi warp finishes units 0-3, the lo warp units 4-7; each hands the other its part of the sum through shared memory.
+    const int ew = warp - 2, quad = warp & 3, half = ew >> 2, upper = quad >> 1;
+    constexpr int NH = NT / 4;                                 // 16 units per CTA
+    const int row = (quad & 1) * 32 + lane;
+    float acc[4][4];  // [gate][unit]
     if (num_kb > 0) {
       mbar_wait(sm.tfull_bar, 0);
       tc_fence_after();
-      LRCN_TMEM_LD_32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(32 * half), v);  // units [8*half, +8) x 4 gates
-      tmem_ld_wait();
+      const uint32_t tl = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(32 * half);
+      float* xr = sm.x + (size_t)row * XLD + 32 * half;
+      uint32_t keep[16], give[16];
+      if (!upper) {
+        uint32_t w[16];
+        LRCN_TMEM_LD_16(tl + 16u, give);       // h_hi*W_hi, units 4-7
+        LRCN_TMEM_LD_16(tl + 64u + 16u, w);    // h_hi*W_lo, units 4-7
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          *reinterpret_cast<float4*>(xr + 16 + 4 * q) = make_float4(__uint_as_float(give[4 * q]) + __uint_as_float(w[4 * q]), __uint_as_float(give[4 * q + 1]) + __uint_as_float(w[4 * q + 1]),
+                                                                     __uint_as_float(give[4 * q + 2]) + __uint_as_float(w[4 * q + 2]), __uint_as_float(give[4 * q + 3]) + __uint_as_float(w[4 * q + 3]));
+        LRCN_TMEM_LD_16(tl, keep);             // units 0-3
+        LRCN_TMEM_LD_16(tl + 64u, w);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 16; c++) keep[c] = __float_as_uint(__uint_as_float(keep[c]) + __uint_as_float(w[c]));
+      } else {
+        LRCN_TMEM_LD_16(tl, give);             // h_lo*W_hi, units 0-3
+        LRCN_TMEM_LD_16(tl + 16u, keep);       // units 4-7
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          *reinterpret_cast<float4*>(xr + 4 * q) = make_float4(__uint_as_float(give[4 * q]), __uint_as_float(give[4 * q + 1]), __uint_as_float(give[4 * q + 2]), __uint_as_float(give[4 * q + 3]));
+      }
+      pair_bar_sync(1 + (quad & 1) * 2 + half);
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const float4 o4 = *reinterpret_cast<const float4*>(xr + 16 * upper + 4 * e);
+        acc[0][e] = __uint_as_float(keep[4 * e]) + o4.x; acc[1][e] = __uint_as_float(keep[4 * e + 1]) + o4.y;
+        acc[2][e] = __uint_as_float(keep[4 * e + 2]) + o4.z; acc[3][e] = __uint_as_float(keep[4 * e + 3]) + o4.w;
+      }
     } else {
 #pragma unroll
-      for (int c = 0; c < 32; c++) v[c] = 0u;
+      for (int e = 0; e < 4; e++)
+#pragma unroll
+        for (int g = 0; g < 4; g++) acc[g][e] = 0.f;
     }
-    // lanes 0-15 own a row; lanes 16-31 take over units 4..7 of the row owned by lane-16
-    float acc[4][4];  // [gate][unit]
-    const int upper = lane >> 4;
-#pragma unroll
-    for (int e = 0; e < 4; e++)
-#pragma unroll
-      for (int g = 0; g < 4; g++) {
-        const uint32_t hi4 = __shfl_sync(0xffffffffu, v[16 + 4 * e + g], lane & 15);
-        acc[g][e] = __uint_as_float(upper ? hi4 : v[4 * e + g]);
-      }
     const int H = p.H;
-    const int m = m0 + quad * 16 + (lane & 15);
+    const int m = m0 + row;
     const int j = nt * NH + 8 * half + 4 * upper;  // first of this thread's 4 units (H % 4 == 0: a float4 never straddles H)
     if (m < p.B && j < H) {
       float* grow = p.gates + (size_t)m * 4 * H + j;
@@ -248,7 +284,7 @@ lstm_fwd_step_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
 // (each streams a quarter of dG_{t+1} and of the transposed weights: 4x fewer bytes per SM than sharing the tile), then
 // exchange their fp32 partials through distributed shared memory: CTA r receives columns [16r,16r+16) from all four,
 // sums them and runs the cell adjoint for those 16 units.
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(L_THREADS, 1)
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(L_THREADS, 2)
 lstm_bwd_step_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                      const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const StepParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -292,30 +328,49 @@ lstm_bwd_step_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   } else if (warp == 1) {
     if (num_kb > 0) step_mma_loop(sm, tmem_base, num_kb, false);
   } else if (p.has_rec) {
-    // phase 1: scatter this CTA's partial (64 rows x 64 units) to the four owners through DSMEM.
+    // phase 1: the lo-row warps hand their dG_lo*W_hi part to the hi-row warps of the same rows through shared memory; those
+    // scatter the CTA's partial (64 rows x 64 units, over this K-quarter) to the four owners through DSMEM.
     // receive buffer layout in every CTA: red[src][row][16] fp32
-    const int ew = warp - 2, quad = warp & 3, half = ew >> 2;
-    uint32_t v[32];
+    const int ew = warp - 2, quad = warp & 3, half = ew >> 2, upper = quad >> 1;
+    const int row = (quad & 1) * 32 + lane;
+    float* xr = sm.x + (size_t)row * XLD + 32 * half;
     if (num_kb > 0) {
       mbar_wait(sm.tfull_bar, 0);
       tc_fence_after();
-      LRCN_TMEM_LD_32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(32 * half), v);
-      tmem_ld_wait();
-    } else {
+      const uint32_t tl = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(32 * half);
+      if (upper) {
+        uint32_t v[32];
+        LRCN_TMEM_LD_32(tl, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 32; c++) v[c] = 0u;
-    }
-    if (lane < 16) {
-      const int row = quad * 16 + lane;
+        for (int q = 0; q < 8; q++)
+          *reinterpret_cast<float4*>(xr + 4 * q) = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+        pair_bar_sync(1 + (quad & 1) * 2 + half);
+      } else {
+        const uint32_t local = smem_u32(sm.red) + (uint32_t)(((int)rank * LM + row) * (NT / CL)) * 4u;
+        pair_bar_sync(1 + (quad & 1) * 2 + half);
+#pragma unroll
+        for (int d2 = 0; d2 < 2; d2++) {  // columns [32*half + 16*d2, +16) belong to CTA dst
+          uint32_t v[16], w[16];
+          LRCN_TMEM_LD_16(tl + 16u * d2, v);
+          LRCN_TMEM_LD_16(tl + 64u + 16u * d2, w);
+          tmem_ld_wait();
+          const uint32_t ra = dsmem_addr(local, (uint32_t)(2 * half + d2));
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const float4 x4 = *reinterpret_cast<const float4*>(xr + 16 * d2 + 4 * q);
+            dsmem_st_f4(ra + 16u * q, make_float4(__uint_as_float(v[4 * q]) + __uint_as_float(w[4 * q]) + x4.x, __uint_as_float(v[4 * q + 1]) + __uint_as_float(w[4 * q + 1]) + x4.y,
+                                                   __uint_as_float(v[4 * q + 2]) + __uint_as_float(w[4 * q + 2]) + x4.z, __uint_as_float(v[4 * q + 3]) + __uint_as_float(w[4 * q + 3]) + x4.w));
+          }
+        }
+      }
+    } else if (!upper) {  // this K-quarter is empty (short K): contribute zeros
       const uint32_t local = smem_u32(sm.red) + (uint32_t)(((int)rank * LM + row) * (NT / CL)) * 4u;
 #pragma unroll
-      for (int d2 = 0; d2 < 2; d2++) {  // columns [32*half + 16*d2, +16) belong to CTA dst
-        const uint32_t dst = (uint32_t)(2 * half + d2);
-        const uint32_t ra = dsmem_addr(local, dst);
+      for (int d2 = 0; d2 < 2; d2++) {
+        const uint32_t ra = dsmem_addr(local, (uint32_t)(2 * half + d2));
 #pragma unroll
-        for (int q = 0; q < 4; q++)
-          dsmem_st_f4(ra + 16u * q, make_float4(__uint_as_float(v[16 * d2 + 4 * q]), __uint_as_float(v[16 * d2 + 4 * q + 1]),
-                                                 __uint_as_float(v[16 * d2 + 4 * q + 2]), __uint_as_float(v[16 * d2 + 4 * q + 3])));
+        for (int q = 0; q < 4; q++) dsmem_st_f4(ra + 16u * q, make_float4(0.f, 0.f, 0.f, 0.f));
       }
     }
   }
@@ -323,8 +378,8 @@ lstm_bwd_step_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
 
   if (warp >= 2) {
     // phase 2: this CTA owns units [nt*64 + 16*rank, +16) of its 64 rows; 256 threads x 4 units
-    const int ew = warp - 2, quad = warp & 3, half = ew >> 2, upper = lane >> 4;
-    const int row = quad * 16 + (lane & 15);
+    const int ew = warp - 2, quad = warp & 3, half = ew >> 2, upper = quad >> 1;
+    const int row = (quad & 1) * 32 + lane;
     const int ug = 2 * half + upper;  // group of 4 units within the 16
     const int H = p.H;
     const int m = m0 + row;

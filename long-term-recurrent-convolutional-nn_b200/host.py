@@ -141,10 +141,16 @@ class LRCN:
                 progress(len(losses), losses[-1])
         return losses
 
-    def average_loss(self, seq, split=0):
-        """average_loss(param,seq,feats): token-weighted mean NLL, pdrop=0 (lrcn.jl:407-486)."""
+    def average_loss(self, seq, split=0, per_step=False):
+        """average_loss(param,seq,feats): token-weighted mean NLL, pdrop=0 (lrcn.jl:407-486).  Default: one library call for
+        the split (lrcn_loss_epoch, batches staged on the device); per_step=True: one lrcn_loss call per batch."""
         sequence, input_ids, lengths = seq
         batch_size = len(sequence[0])
+        if not per_step:
+            blens = np.asarray(lengths, dtype=np.int64)[::batch_size]
+            s, n = self.h.loss_epoch(split, np.stack([np.asarray(r, dtype=np.int64) for r in sequence]),
+                                     np.stack([np.asarray(r, dtype=np.int64) for r in input_ids]), blens)
+            return -s / n
         starts = self._start_indices(lengths, batch_size)
         total, count = 0.0, 0
         for b, t in enumerate(range(0, len(lengths), batch_size)):

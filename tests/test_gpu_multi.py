@@ -114,6 +114,9 @@ def test_single_process_group_matches_oracle_and_single_gpu(prec):
             per = [h.train_step(0, img_e[b], seq_e[st[b]:st[b] + blens[b]], 0.4, 5 + i) for i, b in enumerate([2, 0, 1])]
             np.testing.assert_allclose(ep, per, rtol=1e-6)
             assert max(relerr(a - model[k], h.get_param(k + 1) - model[k]) for k, a in enumerate(w_ep)) < 1e-3
+            s_e, n_e = h.loss_epoch(0, seq_e, img_e, blens)
+            per_l = [h.loss(0, img_e[b], seq_e[st[b]:st[b] + blens[b]]) for b in range(3)]
+            assert n_e == sum(p_[1] for p_ in per_l) and abs(s_e - sum(p_[0] for p_ in per_l)) < 1e-5 * abs(s_e)
             # generation: images sharded over the GPUs, no collective; same captions as one GPU
             h.set_model(model)
             toks, lens, prob, _ = h.beam_search(1, ids[:4 * N + 1], 3, 6)

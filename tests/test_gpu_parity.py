@@ -374,6 +374,11 @@ def test_train_epoch_on_device_equals_per_step_calls_and_oracle(prec, pdrop):
             assert relerr(h.get_adam_state(k, 0), h2.get_adam_state(k, 0)) < 1e-3, f"adam m {k}"
             if pdrop == 0.0:
                 assert relerr(h.get_param(k) - model[k - 1], ref[k - 1] - model[k - 1]) < 2e-2, f"epoch vs oracle, param {k}"
+        # forward-only epoch (average_loss, lrcn.jl:407-486) == the per-batch lrcn_loss calls
+        s_e, n_e = h.loss_epoch(0, seq, img, blens)
+        per = [h2.loss(0, img[b], seq[starts[b]:starts[b] + blens[b]]) for b in range(len(blens)) if blens[b] <= 8]
+        assert n_e == sum(p_[1] for p_ in per) == B * sum(l + 1 for l in blens if l <= 8)
+        assert abs(s_e - sum(p_[0] for p_ in per)) < 1e-5 * abs(s_e)
         # natural order (order = None) and a second epoch on the same handle (buffers are reused)
         l2 = h.train_epoch(0, seq, img, blens, None, pdrop, seed=30)
         w2 = [h2.train_step(0, img[b], seq[starts[b]:starts[b] + blens[b]], pdrop, 30 + i)

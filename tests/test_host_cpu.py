@@ -38,6 +38,15 @@ class FakeHandle:
             out.append(self.train_step(split, input_ids[b], sequence[starts[b]:starts[b] + l], pdrop, seed + len(out)))
         return out
 
+    def loss_epoch(self, split, sequence, input_ids, lengths):
+        starts = np.concatenate([[0], np.cumsum(lengths)])
+        tot, cnt = 0.0, 0
+        for b, l in enumerate(lengths):
+            if l <= 28:
+                s_, n_ = self.loss(split, input_ids[b], sequence[starts[b]:starts[b] + int(l)])
+                tot, cnt = tot + s_, cnt + n_
+        return tot, cnt
+
     def loss(self, split, ids, tok):
         self.calls.append(("loss", split, np.array(ids), np.array(tok)))
         l, B = tok.shape
@@ -99,9 +108,10 @@ def test_train1_visits_every_batch_once_in_shuffled_order_and_skips_long_caption
     assert [c[3].shape[0] for c in again.h.calls if c[0] == "train"] == [c[3].shape[0] for c in calls]  # the shuffled order is a function of the seed
 
 
-def test_average_loss_is_token_weighted_and_skips_long_captions(net):
+@pytest.mark.parametrize("per_step", [False, True])
+def test_average_loss_is_token_weighted_and_skips_long_captions(net, per_step):
     seq = make_seq([3, 29, 6])
-    val = net.average_loss(seq)
+    val = net.average_loss(seq, per_step=per_step)
     calls = [c for c in net.h.calls if c[0] == "loss"]
     assert [c[3].shape[0] for c in calls] == [3, 6]
     assert abs(val - 2.0) < 1e-12  # -(sum of log-probs) / (number of tokens), pooled over batches (lrcn.jl:476-486)
