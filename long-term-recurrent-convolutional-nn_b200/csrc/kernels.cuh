@@ -21,6 +21,8 @@ struct StepScalars {
   float lr, beta1, beta2, eps;
   float one_m_beta1;    // (float)(1 - beta1), computed in double like Knet's axpy!(1-p.beta1, ...)
   float one_m_beta2;
+  uint32_t xchg_epoch;  // data-parallel train steps run so far + 1 (same on every rank): the value of the fused exchange's chunk flags
+  uint32_t pad_;
 };
 
 // ---- programmatic dependent launch (PDL).  A kernel launched through launch_pdl may be scheduled while its predecessor in
@@ -208,10 +210,24 @@ void dp_p2p_shard(size_t n_floats, int nranks, int r, size_t* begin, size_t* end
 // copy-engine exchange (dp_p2p.cu): flag barrier on one of 4 independent flag sets; owner-side sum of the staged
 // contributions + Adam over the arena range [b, e) (floats, multiples of 4); stage rows have `stride` floats, the range's
 // contributions start at stage_off inside a row
-void dp_xgpu_barrier(cudaStream_t s, const P2PPeers& peers, unsigned int* epoch_ctr, int flagset);
+void dp_xgpu_barrier(cudaStream_t s, const P2PPeers& peers, unsigned int* epoch_ctr, int flagset, unsigned long long* trace = nullptr);
+void dp_stamp(cudaStream_t s, unsigned long long* out);
+// FUSED exchange of one gradient bucket (dp_p2p.cu): push of gradient chunks -> per-chunk flags -> owner-side sum + Adam ->
+// push of the new weights -> completion counters, all in ONE kernel.  The control words live behind the staging rows.
+constexpr int DP_XMAXCH = 512;                  // chunk flags per (bucket, source rank)
+constexpr size_t DP_XCTL_FLOATS = 20480;        // control area at the end of every rank's staging allocation (u32 words): 64 + 4 * 8 * 512
+struct FusedXArgs {
+  float* stage[LRCN_P2P_MAX_RANKS];             // every rank's staging allocation (own included)
+  size_t b4[LRCN_P2P_MAX_RANKS], e4[LRCN_P2P_MAX_RANKS];  // rank r's slice of the bucket, arena index in float4 units
+  size_t stride4, pre4, ctl4;                   // staging row stride, the bucket's offset inside a row, start of the control area (float4 units)
+  int bucket, sub;
+};
+void dp_fused_exchange(cudaStream_t s, const P2PPeers& peers, const FusedXArgs& a, float* m, float* v, const StepScalars* sc, double* loss_total, int grid_ctas);
 void dp_p2p_adam_range(cudaStream_t s, const P2PPeers& peers, size_t b, size_t e, float* m, float* v, const StepScalars* sc, double* loss_total, int grid_ctas);
-void dp_adam_staged(cudaStream_t s, float* w, float* g, float* m, float* v, const float* stage, size_t stride, size_t stage_off, size_t b, size_t e,
-                    const P2PPeers& peers, const StepScalars* sc, double* loss_total);
+void dp_adam_staged(cudaStream_t s, float* w, float* g, float* m, float* v, const float* stage, size_t stride, size_t stage_off, size_t b, size_t e, const P2PPeers& peers,
+                    const StepScalars* sc, double* loss_total, bool push_w = false, int grid_ctas = 0);
+// n slices: dst[q] (peer memory) <- src[q] (local), n_floats[q] floats each (multiples of 4, 16-byte aligned)
+void dp_push_slices(cudaStream_t s, int n, float* const* dst, const float* const* src, const size_t* n_floats, int grid_ctas);
 // diagnostics (probe_mma.cu): clocks to issue / to complete a chain of n_mma tcgen05.mma M x N x 16 from resident smem operands
 bool probe_mma(cudaStream_t s, int M, int N, int n_mma, int commit_every, int issuers, long long* issue_clk, long long* total_clk);
 

@@ -173,7 +173,7 @@ static int s_destroy(lrcn_handle* h) {
   if (h->h_sc) cudaFreeHost(h->h_sc);
   if (h->h_loss) cudaFreeHost(h->h_loss);
   if (h->h_ndone) cudaFreeHost(h->h_ndone);
-  for (cudaEvent_t e : {h->ev0, h->ev1, h->ev_seg[0], h->ev_seg[1], h->ev_seg[2], h->ev_comm}) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : {h->ev0, h->ev1, h->ev_seg[0], h->ev_seg[1], h->ev_seg[2], h->ev_seg[3], h->ev_comm}) if (e) cudaEventDestroy(e);
   if (h->ev_xfork) cudaEventDestroy(h->ev_xfork);
   for (int i = 0; i < lrcn_handle::NXFER; i++) { if (h->ev_xjoin[i]) cudaEventDestroy(h->ev_xjoin[i]); if (h->xfer[i]) cudaStreamDestroy(h->xfer[i]); }
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
@@ -219,7 +219,7 @@ static int create_impl(const lrcn_config* cfg, lrcn_handle* h) {
   CK(cudaEventCreateWithFlags(&h->ev_zero, cudaEventDisableTiming));
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
-  for (int i = 0; i < 3; i++) CK(cudaEventCreateWithFlags(&h->ev_seg[i], cudaEventDisableTiming));
+  for (int i = 0; i < 4; i++) CK(cudaEventCreateWithFlags(&h->ev_seg[i], cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->ev_xfork, cudaEventDisableTiming));
   for (int i = 0; i < lrcn_handle::NXFER; i++) {
@@ -235,12 +235,13 @@ static int create_impl(const lrcn_config* cfg, lrcn_handle* h) {
     if (i == 0) h->bucket_off[0] = pos;
     if (i == 2) h->bucket_off[1] = pos;
     if (i == 6) h->bucket_off[2] = pos;
+    if (i == 8) h->bucket_off[3] = pos;
     param_dims(h, k, &h->rows[k - 1], &h->cols[k - 1]);
     h->nel[k - 1] = (size_t)(h->rows[k - 1] * h->cols[k - 1]);
     h->off[k - 1] = pos;
     pos += (h->nel[k - 1] + 63) / 64 * 64;
   }
-  h->bucket_off[3] = pos;
+  h->bucket_off[lrcn_handle::NBUCKET] = pos;
   h->P = pos;
   CK(cudaMalloc(&h->w, h->P * 4)); CK(cudaMalloc(&h->g, h->P * 4)); CK(cudaMalloc(&h->m, h->P * 4)); CK(cudaMalloc(&h->v, h->P * 4));
   CK(cudaMemset(h->w, 0, h->P * 4)); CK(cudaMemset(h->g, 0, h->P * 4)); CK(cudaMemset(h->m, 0, h->P * 4)); CK(cudaMemset(h->v, 0, h->P * 4));
@@ -294,11 +295,12 @@ static int create_impl(const lrcn_config* cfg, lrcn_handle* h) {
   h->d_loss = &h->p2p_ctl->loss_partial;
   CK(cudaMalloc(&h->d_loss_total, 8)); CK(cudaMalloc(&h->d_epoch, 4)); CK(cudaMemset(h->d_epoch, 0, 4));
   CK(cudaMalloc(&h->d_epoch_side, 4)); CK(cudaMemset(h->d_epoch_side, 0, 4));
-  CK(cudaMalloc(&h->stage, (h->P + 1024) * 4));  // N staging rows of ~P/N floats each for the copy-engine gradient exchange
+  CK(cudaMalloc(&h->stage, (h->P + 1024 + DP_XCTL_FLOATS) * 4));  // + the control words of the fused exchange (dp_p2p.cu)
+  CK(cudaMemset(h->stage, 0, (h->P + 1024 + DP_XCTL_FLOATS) * 4));  // N staging rows of ~P/N floats each for the copy-engine gradient exchange
   CK(cudaMallocHost(&h->h_loss, 8));
   CK(cudaMalloc(&h->d_counters, 320 * sizeof(unsigned int)));  // [0,256): 4 LSTM launches x 64 (half-)tile barriers; [256,..): softmax
   CK(cudaMemset(h->d_counters, 0, 320 * sizeof(unsigned int)));
-  if (getenv("LRCN_SEQ_TRACE")) { CK(cudaMalloc(&h->d_trace, 64 * 32 * 8)); CK(cudaMemset(h->d_trace, 0, 64 * 32 * 8)); }
+  if (getenv("LRCN_SEQ_TRACE") || getenv("LRCN_DP_STAMPS")) { CK(cudaMalloc(&h->d_trace, 64 * 32 * 8)); CK(cudaMemset(h->d_trace, 0, 64 * 32 * 8)); }
   CK(cudaMalloc(&h->g_last, G * 4)); CK(cudaMalloc(&h->g_ctok, G * 16 * 4)); CK(cudaMalloc(&h->g_stok, G * 4)); CK(cudaMalloc(&h->g_spar, G * 4));
   CK(cudaMalloc(&h->g_hista, G * ML * 4)); CK(cudaMalloc(&h->g_histb, G * ML * 4)); CK(cudaMalloc(&h->g_done, G * 4));
   CK(cudaMalloc(&h->g_ndone, 4)); CK(cudaMalloc(&h->g_olen, G * 4)); CK(cudaMalloc(&h->g_rows, G * 4)); CK(cudaMalloc(&h->g_otok, G * ML * 8));
@@ -473,14 +475,17 @@ static BucketShard bucket_shard(const lrcn_handle* h, int k, int r) {
   }
   return s;
 }
-static size_t stage_stride(const lrcn_handle* h) { return bucket_shard(h, 2, 0).pre + bucket_shard(h, 2, 0).per; }
+static size_t stage_stride(const lrcn_handle* h) {
+  const BucketShard s = bucket_shard(h, lrcn_handle::NBUCKET - 1, 0);
+  return s.pre + s.per;
+}
 
 static int gather_shards(lrcn_handle* h, bool adam, bool grad) {
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaStreamSynchronize(h->stream));
   for (int r = 0; r < h->nranks; r++) {
     if (r == h->rank) continue;
-    for (int k = 0; k < (h->shard_by_bucket ? 3 : 1); k++) {
+    for (int k = 0; k < (h->shard_by_bucket ? lrcn_handle::NBUCKET : 1); k++) {
     size_t b, e;
     if (h->shard_by_bucket) { const BucketShard bs = bucket_shard(h, k, r); b = bs.b; e = bs.e; }
     else dp_p2p_shard(h->P, h->nranks, r, &b, &e);
@@ -626,7 +631,7 @@ static void lstm_layer_fwd(lrcn_handle* h, int layer, int T, int B, float* acts,
     shadow(h, hs, &hs_hi, &hs_lo);
     bool launched = false;
     if (!lstm_fwd_seq(h->stream, B, H, T, layer == 1 ? h->wp1_hi : h->wp2_hi, layer == 1 ? h->wp1_lo : h->wp2_lo, acts, hs, cs, hs_hi, hs_lo,
-                      h->d_counters + (layer == 1 ? 0 : 64), &launched, (layer == 2 && !getenv("LRCN_TRACE_BWD")) ? h->d_trace : nullptr))
+                      h->d_counters + (layer == 1 ? 0 : 64), &launched, (layer == 2 && !getenv("LRCN_TRACE_BWD") && !getenv("LRCN_DP_STAMPS")) ? h->d_trace : nullptr))
       throw GemmFail{gemm_bf16x3_last_error()};
     if (launched) return;
   }
@@ -640,7 +645,7 @@ static bool lstm_layer_bwd(lrcn_handle* h, int layer, int T, int B, float* acts,
     shadow(h, acts, &a_hi, &a_lo);
     bool launched = false;
     if (!lstm_bwd_seq(h->stream, B, H, T, layer == 1 ? h->wt1_hi : h->wt2_hi, layer == 1 ? h->wt1_lo : h->wt2_lo, acts, a_hi, a_lo, cs, dh_all, dc,
-                      h->d_counters + (layer == 2 ? 128 : 192), &launched, dbias, (layer == 2 && getenv("LRCN_TRACE_BWD")) ? h->d_trace : nullptr))
+                      h->d_counters + (layer == 2 ? 128 : 192), &launched, dbias, (layer == 2 && getenv("LRCN_TRACE_BWD") && !getenv("LRCN_DP_STAMPS")) ? h->d_trace : nullptr))
       throw GemmFail{gemm_bf16x3_last_error()};
     if (launched) return true;
   }
@@ -740,12 +745,17 @@ static void enqueue_backward_seg(lrcn_handle* h, int B, int l, bool train, int s
     gemm(h, true, false, R, H1, C, dZ, 2 * C, Wp(h, 5), H1, dh1, H1, false, nullptr);                             // dh1 = dq * Wf'
     gemm(h, false, false, C, LRCN_F_CNN, B, dv, ldv, X, LRCN_F_CNN, Gp(h, 6), LRCN_F_CNN, false, nullptr, false, true);        // dWcnn = X' * dv
   } else {
+    // seg 3 = the whole layer-1 segment; the data-parallel step runs it as 31 (BPTT, then the embedding gradient: the largest
+    // bucket of the segment is complete first and travels under 32) and 32 (the weight gradient of layer 1)
     float *dhrec = WS(h, o.dhrec1), *dc = WS(h, o.dc1);
-    const bool db_done = lstm_layer_bwd(h, 1, T, B, acts1, c1, dh1, dhrec, dc, Gp(h, 2));
-    gemm_dw_dual(h, 4 * H1, E, H1, R, acts1, 4 * H1, Eall, E, h1, H1, Gp(h, 1), E + H1);       // dW1 = dG1' * [E | h1_{t-1}]
-    if (!db_done) colsum(s, acts1, 4 * H1, R, 4 * H1, Gp(h, 2), true);
-    gemm(h, true, false, R, E, 4 * H1, acts1, 4 * H1, Wp(h, 1), E + H1, dE, E, false, nullptr, false, true);
-    scatter_add_embed(s, Gp(h, 7), h->d_tok_in, dE, R, E, h->d_sc, train);                                         // adjoint of Wemb[idx,:]
+    if (seg == 3 || seg == 31) {
+      const bool db_done = lstm_layer_bwd(h, 1, T, B, acts1, c1, dh1, dhrec, dc, Gp(h, 2));
+      if (!db_done) colsum(s, acts1, 4 * H1, R, 4 * H1, Gp(h, 2), true);
+      gemm(h, true, false, R, E, 4 * H1, acts1, 4 * H1, Wp(h, 1), E + H1, dE, E, false, nullptr, false, true);
+      scatter_add_embed(s, Gp(h, 7), h->d_tok_in, dE, R, E, h->d_sc, train);                                       // adjoint of Wemb[idx,:]
+    }
+    if (seg == 3 || seg == 32)
+      gemm_dw_dual(h, 4 * H1, E, H1, R, acts1, 4 * H1, Eall, E, h1, H1, Gp(h, 1), E + H1);     // dW1 = dG1' * [E | h1_{t-1}]
   }
 }
 
@@ -803,7 +813,8 @@ static int push_scalars(lrcn_handle* h, int B, int l, float pdrop, uint64_t seed
   sc->keep_scale = pdrop > 0.f ? 1.0f / (1.0f - pdrop) : 1.0f;
   sc->drop_thresh = pdrop > 0.f ? (uint32_t)((double)pdrop * 16777216.0) : 0u;
   sc->seed = seed + 0x9E3779B97F4A7C15ull * (uint64_t)h->rank;  // shards of one global batch draw different masks
-  if (bump_adam) h->adam_t += 1;
+  if (bump_adam) { h->adam_t += 1; h->dp_epoch += 1; }
+  sc->xchg_epoch = h->dp_epoch; sc->pad_ = 0;
   const int64_t t = h->adam_t > 0 ? h->adam_t : 1;
   sc->adam_d1 = (float)(1.0 - pow(h->cfg.beta1, (double)t));
   sc->adam_d2 = (float)(1.0 - pow(h->cfg.beta2, (double)t));
@@ -856,31 +867,104 @@ static int run_step(lrcn_handle* h, int split, int B, int l, float pdrop, uint64
       // under the layer-1 BPTT kernel: the persistent LSTM kernels hold 128 of the 148 SMs with one (register-file-filling) CTA
       // each, so the exchange CTAs land on the 20 SMs they leave free -- and because every exchange starts with a cross-GPU flag
       // barrier (a 1-warp kernel that co-resides anywhere), the LSTM grid is resident before the exchange kernel is launched.
-      // Only bucket 3 (W1, b1, Wemb), which is complete at the very end of the backward pass, is exposed.
+      // The layer-1 segment ends with two buckets: the embedding gradient (Wemb, two thirds of the segment's bytes) is produced
+      // FIRST (dE GEMM + scatter) and travels on the side stream under the layer-1 weight-gradient GEMM (whose CTAs leave room
+      // for co-resident exchange CTAs on every SM); only bucket 3 (W1, b1) is exposed.
+      static const int wemb_ctas = getenv("LRCN_DP_WEMB_CTAS") ? atoi(getenv("LRCN_DP_WEMB_CTAS")) : 148 * 4;
+      static const bool stamps = getenv("LRCN_DP_STAMPS") != nullptr;
       return run_cached(h, std::make_tuple(24, B, l, fl), [&] {
+        // stamps (tools/dp_timeline.py): main stream 0..7 = start, fwd done, seg1, seg2, seg31, seg32, last exchange done, joined;
+        // bucket k: 8+4k .. = enter, first barrier passed, exchange kernel done, second barrier + split done
+        auto stamp = [&](int id, cudaStream_t st) { if (stamps && h->d_trace) dp_stamp(st, h->d_trace + id); };
+        static const bool pull = getenv("LRCN_DP_PULL") != nullptr;  // round-2a exchange: the owner LOADS its shard from every peer
+        static const bool fused = !pull && getenv("LRCN_DP_PUSH") == nullptr;  // default; LRCN_DP_PUSH=1: push / barrier / Adam / barrier as four kernels
+        const size_t stride = stage_stride(h);
         auto exchange_bucket = [&](int k, cudaStream_t st, unsigned int* epoch, int flagset, bool last) {
-          dp_xgpu_barrier(st, h->peers, epoch, flagset);  // every rank's gradients of this bucket are complete, and every rank is past its last use of the bucket's weights
+          const int ctas = last ? 148 * 4 : (k == 3 ? wemb_ctas : 20 * 8);
+          if (fused) {
+            // ONE kernel per bucket: chunk-pipelined push -> flags -> owner sum + Adam -> weight push -> completion counters
+            stamp(8 + 4 * k, st);
+            FusedXArgs a{};
+            for (int r = 0; r < h->nranks; r++) {
+              const BucketShard bs = bucket_shard(h, k, r);
+              a.stage[r] = h->peer_stage[r]; a.b4[r] = bs.b / 4; a.e4[r] = bs.e / 4;
+              a.pre4 = bs.pre / 4;
+            }
+            a.stride4 = stride / 4; a.ctl4 = (h->P + 1024) / 4; a.bucket = k;
+            dp_fused_exchange(st, h->peers, a, h->m, h->v, h->d_sc, last ? h->d_loss_total : nullptr, last ? 148 * 4 : (k == 3 ? wemb_ctas : 20 * 4));
+            stamp(10 + 4 * k, st);
+            if (h->bf16mode) {
+              const size_t b0 = h->bucket_off[k], nn = h->bucket_off[k + 1] - b0;
+              split_bf16(st, h->w + b0, nn, h->w_hi + b0, h->w_lo + b0);
+            }
+            stamp(11 + 4 * k, st);
+            return;
+          }
+          if (!pull) {
+            // PUSH exchange: (1) every rank stores its slices of the bucket's gradient into the owners' staging rows; (2) flag
+            // barrier: all pushes have landed, and every rank is past its last use of the bucket's weights; (3) the owner sums the
+            // N contributions in rank order, runs Adam on its slice and stores the new weights into every peer's arena;
+            // (4) flag barrier: the new weights have landed everywhere; (5) local bf16 shadows.
+            stamp(8 + 4 * k, st);
+            float* dst[8]; const float* src[8]; size_t nf[8]; int n = 0;
+            for (int d = 1; d < h->nranks; d++) {
+              const int r = (h->rank + d) % h->nranks;  // staggered targets: no two ranks start on the same peer
+              const BucketShard bs = bucket_shard(h, k, r);
+              dst[n] = h->peer_stage[r] + (size_t)h->rank * stride + bs.pre; src[n] = h->g + bs.b; nf[n] = bs.e - bs.b; n++;
+            }
+            dp_push_slices(st, n, dst, src, nf, ctas);
+            dp_xgpu_barrier(st, h->peers, epoch, flagset, stamps && h->d_trace ? h->d_trace + 32 + k : nullptr);
+            stamp(9 + 4 * k, st);
+            const BucketShard me = bucket_shard(h, k, h->rank);
+            if (me.e > me.b || last)
+              dp_adam_staged(st, h->w, h->g, h->m, h->v, h->stage, stride, me.pre, me.b, me.e, h->peers, h->d_sc, last ? h->d_loss_total : nullptr, true, ctas);
+            stamp(10 + 4 * k, st);
+            dp_xgpu_barrier(st, h->peers, epoch, flagset);
+            if (h->bf16mode) {
+              const size_t b0 = h->bucket_off[k], nn = h->bucket_off[k + 1] - b0;
+              split_bf16(st, h->w + b0, nn, h->w_hi + b0, h->w_lo + b0);
+            }
+            stamp(11 + 4 * k, st);
+            return;
+          }
+          stamp(8 + 4 * k, st);
+          dp_xgpu_barrier(st, h->peers, epoch, flagset, stamps && h->d_trace ? h->d_trace + 32 + k : nullptr);  // every rank's gradients of this bucket are complete, and every rank is past its last use of the bucket's weights
+          stamp(9 + 4 * k, st);
           const BucketShard me = bucket_shard(h, k, h->rank);
-          if (me.e > me.b || last) dp_p2p_adam_range(st, h->peers, me.b, me.e, h->m, h->v, h->d_sc, last ? h->d_loss_total : nullptr, last ? 148 * 4 : 20 * 8);
+          if (me.e > me.b || last) dp_p2p_adam_range(st, h->peers, me.b, me.e, h->m, h->v, h->d_sc, last ? h->d_loss_total : nullptr, ctas);
+          stamp(10 + 4 * k, st);
           dp_xgpu_barrier(st, h->peers, epoch, flagset);  // every owner's new weights of this bucket have landed everywhere
           if (h->bf16mode) {
             const size_t b0 = h->bucket_off[k], n = h->bucket_off[k + 1] - b0;
             split_bf16(st, h->w + b0, n, h->w_hi + b0, h->w_lo + b0);
           }
+          stamp(11 + 4 * k, st);
         };
+        stamp(0, h->stream);
         enqueue_forward(h, split, B, l, true);
+        stamp(1, h->stream);
         enqueue_backward_seg(h, B, l, true, 1);
+        stamp(2, h->stream);
         cudaEventRecord(h->ev_seg[0], h->stream);
         cudaStreamWaitEvent(h->comm_stream, h->ev_seg[0], 0);
         exchange_bucket(0, h->comm_stream, h->d_epoch_side, 1, false);
         enqueue_backward_seg(h, B, l, true, 2);
+        stamp(3, h->stream);
         cudaEventRecord(h->ev_seg[1], h->stream);
         cudaStreamWaitEvent(h->comm_stream, h->ev_seg[1], 0);
         exchange_bucket(1, h->comm_stream, h->d_epoch_side, 1, false);
+        enqueue_backward_seg(h, B, l, true, 31);
+        stamp(4, h->stream);
+        cudaEventRecord(h->ev_seg[2], h->stream);
+        cudaStreamWaitEvent(h->comm_stream, h->ev_seg[2], 0);
+        exchange_bucket(3, h->comm_stream, h->d_epoch_side, 1, false);
         cudaEventRecord(h->ev_comm, h->comm_stream);
-        enqueue_backward_seg(h, B, l, true, 3);
+        enqueue_backward_seg(h, B, l, true, 32);
+        stamp(5, h->stream);
         exchange_bucket(2, h->stream, h->d_epoch, 0, true);
+        stamp(6, h->stream);
         cudaStreamWaitEvent(h->stream, h->ev_comm, 0);  // join the side branch
+        stamp(7, h->stream);
       });
     }
     if (mode == 2 && !replicated && !kernel_exchange) {
@@ -927,7 +1011,8 @@ static int run_step(lrcn_handle* h, int split, int B, int l, float pdrop, uint64
         exchange_bucket(1, h->comm_stream, h->d_epoch_side, 1, false);
         cudaEventRecord(h->ev_comm, h->comm_stream);
         enqueue_backward_seg(h, B, l, true, 3);
-        exchange_bucket(2, h->stream, h->d_epoch, 0, true);
+        exchange_bucket(2, h->stream, h->d_epoch, 0, false);
+        exchange_bucket(3, h->stream, h->d_epoch, 0, true);
         cudaStreamWaitEvent(h->stream, h->ev_comm, 0);  // join the side branch
       });
     }
@@ -974,7 +1059,7 @@ static int run_step(lrcn_handle* h, int split, int B, int l, float pdrop, uint64
     CK(cudaEventRecord(h->ev_seg[seg - 1], h->stream));
     CK(cudaStreamWaitEvent(h->comm_stream, h->ev_seg[seg - 1], 0));
     float* gb = h->g + h->bucket_off[seg - 1];
-    size_t cnt = h->bucket_off[seg] - h->bucket_off[seg - 1];
+    size_t cnt = h->bucket_off[seg == 3 ? lrcn_handle::NBUCKET : seg] - h->bucket_off[seg - 1];  // the last allreduce takes (W1, b1) and Wemb
     if (seg == 3) { rc = nccl_check(n->GroupStart(), "ncclGroupStart"); if (rc) return rc; }
     rc = nccl_check(n->AllReduce(gb, gb, cnt, NCCL_FLOAT32, NCCL_SUM, h->comm, h->comm_stream), "ncclAllReduce(grad bucket)");
     if (rc) return rc;
@@ -1386,6 +1471,8 @@ static int s_p2p_import(lrcn_handle* h, const char* blobs, int rank, int nranks)
   }
   h->peers = pe;
   h->rank = rank; h->nranks = nranks;
+  h->dp_epoch = 0;  // the fused exchange's flags / counters count the group's data-parallel steps: start them together
+  CK(cudaMemset(h->stage + h->P + 1024, 0, DP_XCTL_FLOATS * 4));
   h->p2p_ready = true;
   return LRCN_OK;
 }

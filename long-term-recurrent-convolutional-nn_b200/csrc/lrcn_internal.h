@@ -50,9 +50,10 @@ struct lrcn_handle {
   bool bf16mode;
   cudaStream_t stream = nullptr, comm_stream = nullptr, side_stream = nullptr;  // side: weight prep, concurrent with the step's first kernels
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_zero = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_seg[3] = {nullptr, nullptr, nullptr}, ev_comm = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_seg[4] = {nullptr, nullptr, nullptr, nullptr}, ev_comm = nullptr;
   // params
-  size_t P = 0, off[9], nel[9], bucket_off[4];
+  static constexpr int NBUCKET = 4;   // gradient buckets in backward-readiness order: [Wout,bout | W2,b2,Wf,Wcnn | W1,b1 | Wemb]
+  size_t P = 0, off[9], nel[9], bucket_off[NBUCKET + 1];
   int64_t rows[9], cols[9];
   float *w = nullptr, *g = nullptr, *m = nullptr, *v = nullptr;
   bf16 *w_hi = nullptr, *w_lo = nullptr;
@@ -98,6 +99,7 @@ struct lrcn_handle {
   // copy-engine exchange (dp_p2p.cu): staging rows for the gradient slices the peers push to this rank, and the peers' rows
   float* stage = nullptr;
   float* peer_stage[LRCN_P2P_MAX_RANKS] = {};
+  unsigned int dp_epoch = 0;          // data-parallel train steps run since the peer group was formed (the fused exchange's flag value)
   bool shard_by_bucket = false;       // how the last sharded step split the arena: per gradient bucket (copy engines) or as a whole
   unsigned int* d_epoch_side = nullptr;  // epoch counter of the side-stream barriers
   static constexpr int NXFER = 4;        // parallel copy branches (so that several DMA engines work on the N-1 slices of a phase)
