@@ -120,6 +120,8 @@ void scatter_add_embed(cudaStream_t s, float* dWembT, const int* tok, const floa
 // fused dense Adam over one flat range (Knet defaults, lrcn.jl:394,402); optionally refreshes bf16 hi/lo shadows
 void adam_flat(cudaStream_t s, float* w, const float* g, float* m, float* v, size_t n, const StepScalars* sc,
                __nv_bfloat16* w_hi, __nv_bfloat16* w_lo);
+void adam_range(cudaStream_t s, float* w, const float* g, float* m, float* v, size_t n, const StepScalars* sc, __nv_bfloat16* w_hi,
+                __nv_bfloat16* w_lo, int grid);
 void split_bf16(cudaStream_t s, const float* x, size_t n, __nv_bfloat16* hi, __nv_bfloat16* lo);
 // ---- batch staging on the device (lrcn.jl:351-376): the epoch's token matrix and image ids are resident
 // image id -> feature-table row for a whole epoch: ids [n] (1-based wire ids), sorted_ids/rowof [n_tab]; unknown ids raise *err

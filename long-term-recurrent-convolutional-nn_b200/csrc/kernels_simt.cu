@@ -801,6 +801,17 @@ void adam_flat(cudaStream_t s, float* w, const float* g, float* m, float* v, siz
   count_launch();
 }
 
+// Adam on an arena range with a bounded grid and no PDL attribute: a bucket of the step's update, launched on a side stream under
+// the rest of the backward pass (lrcn_api.cu)
+void adam_range(cudaStream_t s, float* w, const float* g, float* m, float* v, size_t n, const StepScalars* sc, __nv_bfloat16* w_hi,
+                __nv_bfloat16* w_lo, int grid) {
+  const size_t n4 = n / 4;
+  if (n4 == 0) return;
+  if (w_hi) adam_kernel<true><<<grid, 256, 0, s>>>((float4*)w, (const float4*)g, (float4*)m, (float4*)v, n4, sc, w_hi, w_lo);
+  else adam_kernel<false><<<grid, 256, 0, s>>>((float4*)w, (const float4*)g, (float4*)m, (float4*)v, n4, sc, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr);
+  count_launch();
+}
+
 __global__ void split_bf16_kernel(const float4* __restrict__ x, size_t n4, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 X = __ldg(x + i);

@@ -846,6 +846,40 @@ static int run_step(lrcn_handle* h, int split, int B, int l, float pdrop, uint64
   if (mode == 0) {
     return run_cached(h, std::make_tuple(0, B, l, fl), [&] { enqueue_forward(h, split, B, l, false); });
   }
+  static const bool adam_overlap = getenv("LRCN_ADAM_NO_OVERLAP") == nullptr;
+  if (h->nranks == 1 && mode == 2 && adam_overlap && h->bf16mode) {
+    // One GPU: the Adam update (HBM-bound, 7.8 % of the step when it ran after the backward pass) is cut into the gradient
+    // buckets of the data-parallel exchange and runs on a side stream -- a parallel branch of the step's graph -- UNDER the rest
+    // of the backward pass, as soon as a bucket's gradient is complete and its weights have had their last use: [Wout, bout]
+    // under the layer-2 BPTT kernel, [W2, b2, Wf, Wcnn] under the layer-1 BPTT kernel (on the 20 SMs the persistent LSTM
+    // kernels leave free; those kernels are latency-bound and leave the HBM idle), Wemb under the dW1 GEMM.  Only [W1, b1]
+    // (8.4 MB of 53) is updated after the last gradient kernel.  Same kernel, same per-element arithmetic as the flat update.
+    static const int c_lstm = getenv("LRCN_ADAM_CTAS_LSTM") ? atoi(getenv("LRCN_ADAM_CTAS_LSTM")) : 20 * 8;
+    static const int c_wemb = getenv("LRCN_ADAM_CTAS_WEMB") ? atoi(getenv("LRCN_ADAM_CTAS_WEMB")) : 148 * 8;
+    return run_cached(h, std::make_tuple(25, B, l, fl), [&] {
+      auto adam_bucket = [&](int k, cudaStream_t st, int grid) {
+        const size_t b0 = h->bucket_off[k], n = h->bucket_off[k + 1] - b0;
+        adam_range(st, h->w + b0, h->g + b0, h->m + b0, h->v + b0, n, h->d_sc, h->w_hi + b0, h->w_lo + b0, grid);
+      };
+      enqueue_forward(h, split, B, l, true);
+      enqueue_backward_seg(h, B, l, true, 1);
+      cudaEventRecord(h->ev_seg[0], h->stream);
+      cudaStreamWaitEvent(h->comm_stream, h->ev_seg[0], 0);
+      adam_bucket(0, h->comm_stream, c_lstm);
+      enqueue_backward_seg(h, B, l, true, 2);
+      cudaEventRecord(h->ev_seg[1], h->stream);
+      cudaStreamWaitEvent(h->comm_stream, h->ev_seg[1], 0);
+      adam_bucket(1, h->comm_stream, c_lstm);
+      enqueue_backward_seg(h, B, l, true, 31);
+      cudaEventRecord(h->ev_seg[2], h->stream);
+      cudaStreamWaitEvent(h->comm_stream, h->ev_seg[2], 0);
+      adam_bucket(3, h->comm_stream, c_wemb);
+      cudaEventRecord(h->ev_comm, h->comm_stream);
+      enqueue_backward_seg(h, B, l, true, 32);
+      adam_bucket(2, h->stream, 148 * 8);
+      cudaStreamWaitEvent(h->stream, h->ev_comm, 0);  // join the side branch
+    });
+  }
   if (h->nranks == 1) {
     return run_cached(h, std::make_tuple(mode == 2 ? 2 : 1, B, l, fl), [&] {
       enqueue_forward(h, split, B, l, true);
