@@ -163,6 +163,28 @@ class LRCN:
             count += n
         return -total / count
 
+    def train(self, sequence, vocab=None, epochs=1, batch_size=None, savefile=None, pdrop=0.4, out=sys.stdout, datasheet=None, shuffle_seed=0):
+        """train!(model, optim, sequence, vocab, o), lrcn.jl:222-239: per epoch one train1 pass at pdrop 0.4 over
+        sequence[0], the checkpoint (`save(o[:savefile], "model", model, "vocab", vocab)`), then average_loss at pdrop 0 on the
+        training split (feats, split 0) and the validation split (featsvl, split 1), printed -- and appended to the data sheet
+        the reference hard-codes -- as `(:epoch,e,:loss,l_trn,l_val)`.  Three library calls per epoch (lrcn_train_epoch, 2x
+        lrcn_loss_epoch): no per-batch host work.  Returns the list of (l_trn, l_val)."""
+        history = []
+        for epoch in range(1, epochs + 1):
+            self.train1(sequence[0], batch_size=batch_size, pdrop=pdrop, shuffle_seed=shuffle_seed + epoch)
+            if savefile is not None:
+                print(f"INFO: Saving last model to {savefile}", file=sys.stderr)   # info(...) lrcn.jl:227
+                self.save(savefile, vocab)
+            losses = (np.float32(self.average_loss(sequence[0], split=0)), np.float32(self.average_loss(sequence[1], split=1)))
+            line = f"(:epoch,{epoch},:loss,{losses[0]}f0,{losses[1]}f0)"
+            print(line, file=out)
+            if datasheet is not None:
+                with open(datasheet, "a+") as f:
+                    print(line, file=f)
+            history.append((float(losses[0]), float(losses[1])))
+        self.h.sync()  # gpu()>=0 && Knet.cudaDeviceSynchronize()  lrcn.jl:240
+        return history
+
     # ---- generation (lrcn.jl:585-642)
     def beam_search(self, image_ids, nword, beam_width, split=1):
         """Numeric part of generate()+beam_search() for many images; returns

@@ -508,9 +508,12 @@ def test_host_mirror_train_and_generate_text():
     net.load_features(feats, 1)
     before = net.average_loss(seq)
     assert abs(before - np.log(len(vocab))) < 0.2
-    for _ in range(3):
-        net.train1(seq, pdrop=0.0)
-    after = net.average_loss(seq)
+    log = io.StringIO()
+    hist = net.train((seq, seq), vocab, epochs=3, pdrop=0.0, out=log)     # train! (lrcn.jl:222-239): train1 + average_loss on both splits
+    assert len(hist) == 3 and log.getvalue().count("(:epoch,") == 3
+    assert abs(hist[-1][0] - hist[-1][1]) < 1e-5 * hist[-1][0]             # both splits hold the same data here
+    after = net.average_loss(seq, per_step=True)                           # the per-batch path agrees with the one-call path
+    assert abs(after - hist[-1][0]) < 1e-5 * after
     assert after < before - 0.05
     out, in_out = io.StringIO(), io.StringIO()
     hyp = net.generate(5, vocab, 30, 3, out=out, in_out=in_out)

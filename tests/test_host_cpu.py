@@ -22,6 +22,12 @@ class FakeHandle:
     def close(self):
         pass
 
+    def sync(self):
+        self.calls.append(("sync",))
+
+    def checkpoint_save(self, path, with_adam, aux):
+        self.calls.append(("save", path, with_adam, bytes(aux)))
+
     def train_step(self, split, ids, tok, pdrop, seed):
         self.calls.append(("train", split, np.array(ids), np.array(tok), pdrop, seed))
         return float(tok.shape[0])
@@ -170,3 +176,21 @@ def test_delete_unbatchable_captions_equals_the_restated_reference_whenever_it_t
         assert got == keep
         compared += 1
     assert compared > 1000
+
+
+def test_train_loop_mirrors_the_reference_epoch_loop(net, tmp_path):
+    """train! (lrcn.jl:222-239): per epoch train1 at pdrop 0.4, checkpoint, average_loss on both splits, one printed line."""
+    trn, val = make_seq([3, 5, 4]), make_seq([2, 6])
+    out = io.StringIO()
+    sheet = tmp_path / "sheet.out"
+    hist = net.train((trn, val), vocab={"a": 4}, epochs=2, savefile="ck.bin", out=out, datasheet=str(sheet))
+    kinds = [c[0] for c in net.h.calls if c[0] in ("epoch", "save", "sync")]
+    assert kinds == ["epoch", "save", "epoch", "save", "sync"]
+    assert all(c[4] == 0.4 for c in net.h.calls if c[0] == "train")            # lrcn.jl:227 hard-codes pdrop = 0.4
+    losses = [c for c in net.h.calls if c[0] == "loss"]
+    assert [c[1] for c in losses] == [0, 0, 0, 1, 1] * 2                       # training split then validation split, every epoch
+    lines = out.getvalue().splitlines()
+    assert lines == ["(:epoch,1,:loss,2.0f0,2.0f0)", "(:epoch,2,:loss,2.0f0,2.0f0)"] and sheet.read_text().splitlines() == lines
+    assert hist == [(2.0, 2.0), (2.0, 2.0)]
+    orders = [[c[3].shape[0] for c in net.h.calls if c[0] == "train"][:3], [c[3].shape[0] for c in net.h.calls if c[0] == "train"][3:]]
+    assert sorted(orders[0]) == sorted(orders[1]) == [3, 4, 5]                 # every batch once per epoch

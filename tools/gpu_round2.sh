@@ -9,6 +9,12 @@ fi
 if [ -z "$SKIP_BENCH" ]; then
   echo "== bench"; timeout 900 python bench.py --steps ${STEPS:-100} --warmup 5 > gpurun_out/r02_bench.log 2>&1; tail -c 6000 gpurun_out/r02_bench.log
 fi
+if [ -n "$EXTRA_BENCH" ]; then
+  for wl in flickr8k_train_b64 coco_2f_train_b256; do
+    timeout 600 python bench.py --workload $wl --steps 50 --warmup 5 --no-beam > gpurun_out/r02_bench_$wl.log 2>&1; grep '^{' gpurun_out/r02_bench_$wl.log | tail -1 | cut -c1-300
+  done
+  echo "== beam sweep (C5)"; timeout 600 python tools/beam_sweep.py > gpurun_out/r02_beam_sweep.md 2>gpurun_out/r02_beam_sweep.err; cat gpurun_out/r02_beam_sweep.md
+fi
 if [ -z "$SKIP_NCU" ]; then
   echo "== ncu launch list"
   PROFILE_STEP=1 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_step_launches.csv \
@@ -19,5 +25,21 @@ if [ -z "$SKIP_NCU" ]; then
       -o gpurun_out/r02_prof_lstm -f python tools/prof_kernels.py lstm_fwd lstm_bwd > gpurun_out/r02_ncu_lstm.log 2>&1
   tail -5 gpurun_out/r02_ncu_lstm.log
   ncu -i gpurun_out/r02_prof_lstm.ncu-rep --page raw --csv > gpurun_out/r02_prof_lstm_raw.csv 2>/dev/null
+  echo "== ncu full: the other hot kernels (one launch each)"
+  timeout 900 ncu --profile-from-start off --set full --clock-control none -k regex:"gemm2_bf16x3|adam_kernel|softmax_ce|gather_embed" -c 8 \
+      -o gpurun_out/r02_prof_other -f python tools/prof_kernels.py vocab_gemm adam softmax_ce gather > gpurun_out/r02_ncu_other.log 2>&1
+  ncu -i gpurun_out/r02_prof_other.ncu-rep --page raw --csv > gpurun_out/r02_prof_other_raw.csv 2>/dev/null
+  python - <<'PY'
+import csv
+a = list(csv.reader(open("gpurun_out/r02_prof_lstm_raw.csv")))
+b = list(csv.reader(open("gpurun_out/r02_prof_other_raw.csv")))
+if a[0] == b[0]:
+    csv.writer(open("gpurun_out/r02_prof_all_raw.csv", "w")).writerows(a + b[2:])
+else:  # different metric sets: align by header
+    idx = [b[0].index(h) if h in b[0] else None for h in a[0]]
+    csv.writer(open("gpurun_out/r02_prof_all_raw.csv", "w")).writerows(a + [[r[i] if i is not None else "0" for i in idx] for r in b[2:]])
+PY
+  python tools/ncu_to_traffic.py gpurun_out/r02_prof_all_raw.csv gpurun_out/r02_step_launches.csv flickr30k_train_b256 12 > gpurun_out/ncu_traffic.json; head -c 600 gpurun_out/ncu_traffic.json
+  rm -f gpurun_out/r02_prof_other.ncu-rep
   ls -la gpurun_out/r02_* | head
 fi
