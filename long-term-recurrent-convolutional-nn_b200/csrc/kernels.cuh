@@ -168,7 +168,7 @@ struct BeamCompactArgs {
   float *h1_s, *c1_s, *h2_s, *c2_s;                  // scratch, contiguous rows
   __nv_bfloat16 *h1_hi, *h1_lo, *h2_hi, *h2_lo;      // bf16 split of h (row pitch ld1 / ld2), rebuilt on copy-back; may be null
   const int* hist_src; int* hist_dst; const float* lp_src; float* lp_dst;   // ping-pong history buffers: gathered into the other one
-  float *prob, *prob_s; int *last, *last_s; float *v, *v_s; int *out_map, *out_map_s; int* done;
+  float *prob, *prob_s; int *last, *last_s; float *v, *v_s; int *out_map, *out_map_s; int *done, *done_s;
 };
 void beam_compact(cudaStream_t s, const BeamCompactArgs& a);
 

@@ -1562,7 +1562,7 @@ __global__ void __launch_bounds__(128) beam_compact_gather_kernel(BeamCompactArg
   if (k == 0) {
     const int io = a.keep[img];
     for (int j = threadIdx.x; j < a.ldv; j += blockDim.x) a.v_s[(size_t)img * a.ldv + j] = a.v[(size_t)io * a.ldv + j];
-    if (threadIdx.x == 0) a.out_map_s[img] = a.out_map[io];
+    if (threadIdx.x == 0) { a.out_map_s[img] = a.out_map[io]; a.done_s[img] = a.done[io]; }
   }
 }
 __global__ void __launch_bounds__(128) beam_compact_scatter_kernel(BeamCompactArgs a) {
@@ -1582,7 +1582,8 @@ __global__ void __launch_bounds__(128) beam_compact_scatter_kernel(BeamCompactAr
   if (threadIdx.x == 0) { a.prob[rn] = a.prob_s[rn]; a.last[rn] = a.last_s[rn]; }
   if (k == 0) {
     for (int j = threadIdx.x; j < a.ldv; j += blockDim.x) a.v[(size_t)img * a.ldv + j] = a.v_s[(size_t)img * a.ldv + j];
-    if (threadIdx.x == 0) { a.out_map[img] = a.out_map_s[img]; a.done[img] = 0; }
+    // the survivor list may be one step old (the host decides from an asynchronous snapshot): a survivor can have ended since
+    if (threadIdx.x == 0) { a.out_map[img] = a.out_map_s[img]; a.done[img] = a.done_s[img]; }
   }
 }
 void beam_compact(cudaStream_t s, const BeamCompactArgs& a) {

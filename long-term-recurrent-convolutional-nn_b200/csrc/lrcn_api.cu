@@ -173,6 +173,8 @@ static int s_destroy(lrcn_handle* h) {
   if (h->h_sc) cudaFreeHost(h->h_sc);
   if (h->h_loss) cudaFreeHost(h->h_loss);
   if (h->h_ndone) cudaFreeHost(h->h_ndone);
+  if (h->h_keep) cudaFreeHost(h->h_keep);
+  for (int i = 0; i < lrcn_handle::NSNAP; i++) { if (h->ev_snap[i]) cudaEventDestroy(h->ev_snap[i]); if (h->ev_keep[i]) cudaEventDestroy(h->ev_keep[i]); }
   for (cudaEvent_t e : {h->ev0, h->ev1, h->ev_seg[0], h->ev_seg[1], h->ev_seg[2], h->ev_seg[3], h->ev_comm}) if (e) cudaEventDestroy(e);
   if (h->ev_xfork) cudaEventDestroy(h->ev_xfork);
   for (int i = 0; i < lrcn_handle::NXFER; i++) { if (h->ev_xjoin[i]) cudaEventDestroy(h->ev_xjoin[i]); if (h->xfer[i]) cudaStreamDestroy(h->xfer[i]); }
@@ -304,8 +306,12 @@ static int create_impl(const lrcn_config* cfg, lrcn_handle* h) {
   CK(cudaMalloc(&h->g_last, G * 4)); CK(cudaMalloc(&h->g_ctok, G * 16 * 4)); CK(cudaMalloc(&h->g_stok, G * 4)); CK(cudaMalloc(&h->g_spar, G * 4));
   CK(cudaMalloc(&h->g_hista, G * ML * 4)); CK(cudaMalloc(&h->g_histb, G * ML * 4)); CK(cudaMalloc(&h->g_done, G * 4));
   CK(cudaMalloc(&h->g_ndone, 4)); CK(cudaMalloc(&h->g_olen, G * 4)); CK(cudaMalloc(&h->g_rows, G * 4)); CK(cudaMalloc(&h->g_otok, G * ML * 8));
-  CK(cudaMallocHost(&h->h_ndone, (G + 1) * 4));
-  CK(cudaMalloc(&h->g_keep, G * 4)); CK(cudaMalloc(&h->g_omap, G * 4)); CK(cudaMalloc(&h->g_omap_s, G * 4));
+  CK(cudaMallocHost(&h->h_ndone, (size_t)lrcn_handle::NSNAP * (G + 1) * 4));
+  CK(cudaMallocHost(&h->h_keep, (size_t)lrcn_handle::NSNAP * G * 4));
+  for (int i = 0; i < lrcn_handle::NSNAP; i++) {
+    CK(cudaEventCreateWithFlags(&h->ev_snap[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_keep[i], cudaEventDisableTiming));
+  }
+  CK(cudaMalloc(&h->g_keep, G * 4)); CK(cudaMalloc(&h->g_omap, G * 4)); CK(cudaMalloc(&h->g_omap_s, 2 * G * 4));  // g_omap_s: [G] map scratch + [G] done scratch
   h->l2_n = (size_t)64 << 20;  // 256 MiB of floats > 126 MB L2
   CK(cudaMalloc(&h->l2_scratch, h->l2_n * 4));
   CK(cudaDeviceSynchronize());
@@ -1309,10 +1315,10 @@ static void enqueue_beam_step(lrcn_handle* h, int n_img, int K, int step, int nw
   beam_advance(s, a);  // reorder/gather parent states (+ their bf16 split for the next recurrent GEMMs)                 lrcn.jl:670-677
 }
 
-__global__ void beam_init_kernel(int R, int maxlen, float* prob, int* last, int* hist, float* lp, int* done, int* n_done, int n_img) {
+__global__ void beam_init_kernel(int R, int maxlen, float* prob, int* last, int* hist, float* lp, int* done, int* n_done, int n_img, int* out_map) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r == 0) *n_done = 0;
-  if (r < n_img) done[r] = 0;
+  if (r < n_img) { done[r] = 0; out_map[r] = r; }  // compacted -> caller index: identity until the first compaction
   if (r >= R) return;
   prob[r] = 1.0f;  // (bos, 1.0)  lrcn.jl:627
   last[r] = 1;     // bos, 0-based
@@ -1354,7 +1360,7 @@ static int s_beam_search(lrcn_handle* h, int split, const int64_t* image_ids, in
       }
       gather_features(h->stream, tb.d, h->g_rows, ni, WS(h, o.gX), SH(h, WS(h, o.gX)).hi, SH(h, WS(h, o.gX)).lo);
       gemm(h, true, true, ni, h->C, LRCN_F_CNN, WS(h, o.gX), LRCN_F_CNN, Wp(h, 6), LRCN_F_CNN, WS(h, o.gv), h->ldv, false, nullptr);  // lrcn.jl:611
-      beam_init_kernel<<<(R + 255) / 256, 256, 0, h->stream>>>(R, maxlen, WS(h, o.gprob), h->g_last, h->g_hista, WS(h, o.glpa), h->g_done, h->g_ndone, ni);
+      beam_init_kernel<<<(R + 255) / 256, 256, 0, h->stream>>>(R, maxlen, WS(h, o.gprob), h->g_last, h->g_hista, WS(h, o.glpa), h->g_done, h->g_ndone, ni, h->g_omap);
       h->counter.n++;
       if (beam_wide(h, R)) {  // h_0 = 0 in the h columns of the [x|h] operands (fp32 and bf16 shadows)
         const size_t n1 = (size_t)R * (h->E + h->H1), n2 = (size_t)R * (2 * h->C + h->H2);
@@ -1367,53 +1373,69 @@ static int s_beam_search(lrcn_handle* h, int split, const int64_t* image_ids, in
       bool flip = false;
       const bool wide = beam_wide(h, R);  // fixed for the chunk: the two paths keep the states in different buffers
       int n_act = ni;                     // images still in flight (compacted to the front)
-      bool mapped = false;                // g_omap is in use (after the first compaction)
       static const bool no_compact = getenv("LRCN_BEAM_NO_COMPACT") != nullptr;
-      for (int step = 1; step <= nword + 1; step++) {
-        enqueue_beam_step(h, n_act, K, step, nword, maxlen, flip, logp_out ? WS(h, o.golp) : nullptr, wide, mapped ? h->g_omap : nullptr);
+      static const int den = getenv("LRCN_BEAM_COMPACT_DEN") ? atoi(getenv("LRCN_BEAM_COMPACT_DEN")) : 8;
+      static const int lag = getenv("LRCN_BEAM_LAG") ? atoi(getenv("LRCN_BEAM_LAG")) : 1;  // 1..NSNAP-1 (measured: 1 = 162k, 2 = 157k, 3 = 152k captions/s: later decisions cost more than the queued step gains)
+      // Asynchronous polling.  After EVERY step the done flags are copied into a ring of pinned snapshots (+ an event); the host
+      // reads the snapshot of step s-1 right after it has enqueued step s, so the GPU always has a whole step queued while the
+      // host waits, decides and enqueues -- the pipeline never drains (round 2a polled every 4 steps with a full
+      // synchronisation and two more per compaction).  A decision taken from a one-step-old snapshot is safe: done flags only
+      // ever rise, the compaction kernel carries the CURRENT flag of every survivor along, and an image that ended in between
+      // simply rides until the next compaction.
+      // Compaction: the reference decodes image by image and simply stops when an image ends (lrcn.jl:670); in a batch the
+      // finished images would ride along until the slowest one ends (COCO captions end after ~10 of the 31 possible steps).
+      // When at least 1/den of the images in flight have ended, the survivors move to the front and every later step (three
+      // GEMMs, top-K, state gather) runs on the smaller batch.
+      const int G1 = h->cfg.max_gen_rows + 1;
+      int snap_gen[lrcn_handle::NSNAP], snap_n[lrcn_handle::NSNAP], gen = 0, n_compactions = 0;
+      for (int q = 0; q < lrcn_handle::NSNAP; q++) snap_gen[q] = -1;
+      bool all_done = false;
+      for (int step = 1; step <= nword + 1 && !all_done; step++) {
+        enqueue_beam_step(h, n_act, K, step, nword, maxlen, flip, logp_out ? WS(h, o.golp) : nullptr, wide, h->g_omap);
         flip = !flip;
-        if ((step & 3) == 0 || step == nword + 1) {  // finished images are frozen on the device; poll the host only every 4 steps
-          CK(cudaMemcpyAsync(h->h_ndone, h->g_ndone, 4, cudaMemcpyDeviceToHost, h->stream));
-          CK(cudaMemcpyAsync(h->h_ndone + 1, h->g_done, (size_t)n_act * 4, cudaMemcpyDeviceToHost, h->stream));
-          CK(cudaStreamSynchronize(h->stream));
-          if (*h->h_ndone >= ni) break;
-          // Compaction: the reference decodes image by image and simply stops when an image ends (lrcn.jl:670); in a batch the
-          // finished images would ride along until the slowest one ends (COCO captions end after ~10 of the 31 possible steps).
-          // When at least a quarter of the images in flight have ended, the survivors move to the front and every later step
-          // (three GEMMs, top-K, state gather) runs on the smaller batch.
-          int n_keep = 0;
-          for (int i = 0; i < n_act; i++) n_keep += h->h_ndone[1 + i] ? 0 : 1;
-          if (!no_compact && step < nword + 1 && n_keep > 0 && n_keep * 4 <= n_act * 3) {
-            std::vector<int> keep;
-            keep.reserve(n_keep);
-            for (int i = 0; i < n_act; i++) if (!h->h_ndone[1 + i]) keep.push_back(i);
-            CK(cudaMemcpyAsync(h->g_keep, keep.data(), (size_t)n_keep * 4, cudaMemcpyHostToDevice, h->stream));
-            if (!mapped) {  // identity map before the first compaction
-              std::vector<int> ident(n_act);
-              for (int i = 0; i < n_act; i++) ident[i] = i;
-              CK(cudaMemcpyAsync(h->g_omap, ident.data(), (size_t)n_act * 4, cudaMemcpyHostToDevice, h->stream));
-              CK(cudaStreamSynchronize(h->stream));  // `ident` is a stack-lifetime host buffer
-              mapped = true;
-            }
-            BeamCompactArgs ca{};
-            ca.n_keep = n_keep; ca.K = K; ca.H1 = h->H1; ca.H2 = h->H2; ca.ldv = h->ldv; ca.maxlen = maxlen; ca.hist_len = step + 1;
-            ca.ld1 = wide ? h->E + h->H1 : h->H1; ca.ld2 = wide ? 2 * h->C + h->H2 : h->H2;
-            ca.keep = h->g_keep;
-            ca.h1 = wide ? WS(h, o.gxh1) + h->E : WS(h, o.gh1a); ca.h2 = wide ? WS(h, o.gxh2) + 2 * h->C : WS(h, o.gh2a);
-            ca.c1 = WS(h, o.gc1a); ca.c2 = WS(h, o.gc2a);
-            ca.h1_s = WS(h, o.gh1b); ca.c1_s = WS(h, o.gc1b); ca.h2_s = WS(h, o.gh2b); ca.c2_s = WS(h, o.gc2b);  // the "advanced state" buffers are free between steps
-            ca.h1_hi = SH(h, ca.h1).hi; ca.h1_lo = SH(h, ca.h1).lo; ca.h2_hi = SH(h, ca.h2).hi; ca.h2_lo = SH(h, ca.h2).lo;
-            ca.hist_src = flip ? h->g_histb : h->g_hista; ca.hist_dst = flip ? h->g_hista : h->g_histb;
-            ca.lp_src = flip ? WS(h, o.glpb) : WS(h, o.glpa); ca.lp_dst = flip ? WS(h, o.glpa) : WS(h, o.glpb);
-            ca.prob = WS(h, o.gprob); ca.prob_s = WS(h, o.gss); ca.last = h->g_last; ca.last_s = h->g_stok;
-            ca.v = WS(h, o.gv); ca.v_s = WS(h, o.gX);  // the gathered features are dead once v = X * Wcnn exists
-            ca.out_map = h->g_omap; ca.out_map_s = h->g_omap_s; ca.done = h->g_done;
-            beam_compact(h->stream, ca);
-            CK(cudaStreamSynchronize(h->stream));  // `keep` is a stack-lifetime host buffer
-            flip = !flip;  // the compacted histories live in the other ping-pong buffer
-            n_act = n_keep;
-          }
-        }
+        const int q = step % lrcn_handle::NSNAP;
+        int* snap = h->h_ndone + (size_t)q * G1;
+        // the copies run on the side stream (an in-stream D2H copy stalls the kernel stream for ~5 us); the flags only ever rise,
+        // so a copy that overlaps the next step is still a valid (older or newer) snapshot, and one that overlaps a compaction
+        // belongs to the old numbering and is ignored (its done-count stays valid)
+        CK(cudaEventRecord(h->ev_fork, h->stream));
+        CK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+        CK(cudaMemcpyAsync(snap, h->g_ndone, 4, cudaMemcpyDeviceToHost, h->side_stream));
+        CK(cudaMemcpyAsync(snap + 1, h->g_done, (size_t)n_act * 4, cudaMemcpyDeviceToHost, h->side_stream));
+        CK(cudaEventRecord(h->ev_snap[q], h->side_stream));
+        snap_gen[q] = gen; snap_n[q] = n_act;
+        if (step <= lag) continue;
+        const int p = (step - lag) % lrcn_handle::NSNAP;  // an earlier step's snapshot: the GPU keeps `lag` steps queued while the host waits
+        CK(cudaEventSynchronize(h->ev_snap[p]));
+        const int* ps = h->h_ndone + (size_t)p * G1;
+        if (ps[0] >= ni) { all_done = true; break; }      // (the step already enqueued runs on frozen images: a no-op)
+        if (snap_gen[p] != gen || no_compact || step >= nword + 1) continue;  // indices of an older numbering
+        int n_keep = 0;
+        for (int i = 0; i < n_act; i++) n_keep += ps[1 + i] ? 0 : 1;
+        if (n_keep == 0 || (n_act - n_keep) * den < n_act) continue;
+        const int kq = n_compactions % lrcn_handle::NSNAP;
+        if (n_compactions >= lrcn_handle::NSNAP) CK(cudaEventSynchronize(h->ev_keep[kq]));  // the list's previous upload has executed
+        int* keep = h->h_keep + (size_t)kq * h->cfg.max_gen_rows;
+        for (int i = 0, n = 0; i < n_act; i++) if (!ps[1 + i]) keep[n++] = i;
+        CK(cudaMemcpyAsync(h->g_keep, keep, (size_t)n_keep * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaEventRecord(h->ev_keep[kq], h->stream));
+        BeamCompactArgs ca{};
+        ca.n_keep = n_keep; ca.K = K; ca.H1 = h->H1; ca.H2 = h->H2; ca.ldv = h->ldv; ca.maxlen = maxlen; ca.hist_len = step + 1;
+        ca.ld1 = wide ? h->E + h->H1 : h->H1; ca.ld2 = wide ? 2 * h->C + h->H2 : h->H2;
+        ca.keep = h->g_keep;
+        ca.h1 = wide ? WS(h, o.gxh1) + h->E : WS(h, o.gh1a); ca.h2 = wide ? WS(h, o.gxh2) + 2 * h->C : WS(h, o.gh2a);
+        ca.c1 = WS(h, o.gc1a); ca.c2 = WS(h, o.gc2a);
+        ca.h1_s = WS(h, o.gh1b); ca.c1_s = WS(h, o.gc1b); ca.h2_s = WS(h, o.gh2b); ca.c2_s = WS(h, o.gc2b);  // the "advanced state" buffers are free between steps
+        ca.h1_hi = SH(h, ca.h1).hi; ca.h1_lo = SH(h, ca.h1).lo; ca.h2_hi = SH(h, ca.h2).hi; ca.h2_lo = SH(h, ca.h2).lo;
+        ca.hist_src = flip ? h->g_histb : h->g_hista; ca.hist_dst = flip ? h->g_hista : h->g_histb;
+        ca.lp_src = flip ? WS(h, o.glpb) : WS(h, o.glpa); ca.lp_dst = flip ? WS(h, o.glpa) : WS(h, o.glpb);
+        ca.prob = WS(h, o.gprob); ca.prob_s = WS(h, o.gss); ca.last = h->g_last; ca.last_s = h->g_stok;
+        ca.v = WS(h, o.gv); ca.v_s = WS(h, o.gX);  // the gathered features are dead once v = X * Wcnn exists
+        ca.out_map = h->g_omap; ca.out_map_s = h->g_omap_s; ca.done = h->g_done; ca.done_s = h->g_omap_s + h->cfg.max_gen_rows;
+        beam_compact(h->stream, ca);
+        flip = !flip;  // the compacted histories live in the other ping-pong buffer
+        n_act = n_keep;
+        gen++; n_compactions++;
       }
     } catch (GemmFail& f) {
       return fail(LRCN_ERR_CUDA, "%s", f.msg.c_str());

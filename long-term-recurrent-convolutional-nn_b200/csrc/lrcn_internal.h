@@ -121,6 +121,9 @@ struct lrcn_handle {
   int *g_last = nullptr, *g_ctok = nullptr, *g_stok = nullptr, *g_spar = nullptr, *g_hista = nullptr, *g_histb = nullptr, *g_done = nullptr,
       *g_ndone = nullptr, *g_olen = nullptr, *g_rows = nullptr;
   long long* g_otok = nullptr;
+  static constexpr int NSNAP = 4;   // ring of pinned snapshots of the done flags / survivor lists (asynchronous beam-search polling)
+  cudaEvent_t ev_snap[NSNAP] = {nullptr, nullptr, nullptr, nullptr}, ev_keep[NSNAP] = {nullptr, nullptr, nullptr, nullptr};
+  int* h_keep = nullptr;     // pinned: NSNAP survivor lists
   int* h_ndone = nullptr;    // pinned: [0] = images done so far, [1..] = done flags of the images in flight
   int *g_keep = nullptr, *g_omap = nullptr, *g_omap_s = nullptr;  // compaction: survivors, compacted -> caller index (+ scratch)
   float* l2_scratch = nullptr; size_t l2_n = 0;
