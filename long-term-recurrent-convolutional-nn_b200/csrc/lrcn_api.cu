@@ -18,6 +18,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <chrono>
 
 static thread_local std::string g_err;
 static thread_local int g_last_code = 0;  // code of the last fail() on this thread (read by ApiGuard)
@@ -1390,7 +1391,12 @@ static int s_beam_search(lrcn_handle* h, int split, const int64_t* image_ids, in
       int snap_gen[lrcn_handle::NSNAP], snap_n[lrcn_handle::NSNAP], gen = 0, n_compactions = 0;
       for (int q = 0; q < lrcn_handle::NSNAP; q++) snap_gen[q] = -1;
       bool all_done = false;
+      static const bool beam_debug = getenv("LRCN_BEAM_DEBUG") != nullptr;
+      double wait_us = 0.0;
+      const auto tl0 = std::chrono::steady_clock::now();
+      int steps_run = 0;
       for (int step = 1; step <= nword + 1 && !all_done; step++) {
+        steps_run = step;
         enqueue_beam_step(h, n_act, K, step, nword, maxlen, flip, logp_out ? WS(h, o.golp) : nullptr, wide, h->g_omap);
         flip = !flip;
         const int q = step % lrcn_handle::NSNAP;
@@ -1406,7 +1412,9 @@ static int s_beam_search(lrcn_handle* h, int split, const int64_t* image_ids, in
         snap_gen[q] = gen; snap_n[q] = n_act;
         if (step <= lag) continue;
         const int p = (step - lag) % lrcn_handle::NSNAP;  // an earlier step's snapshot: the GPU keeps `lag` steps queued while the host waits
+        const auto tw0 = std::chrono::steady_clock::now();
         CK(cudaEventSynchronize(h->ev_snap[p]));
+        if (beam_debug) wait_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tw0).count();
         const int* ps = h->h_ndone + (size_t)p * G1;
         if (ps[0] >= ni) { all_done = true; break; }      // (the step already enqueued runs on frozen images: a no-op)
         if (snap_gen[p] != gen || no_compact || step >= nword + 1) continue;  // indices of an older numbering
@@ -1437,6 +1445,9 @@ static int s_beam_search(lrcn_handle* h, int split, const int64_t* image_ids, in
         n_act = n_keep;
         gen++; n_compactions++;
       }
+      if (beam_debug)
+        fprintf(stderr, "[lrcn beam] %d images, %d steps enqueued, %d compactions: host loop %.0f us, of which %.0f us waiting for the GPU\n", ni, steps_run,
+                n_compactions, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tl0).count(), wait_us);
     } catch (GemmFail& f) {
       return fail(LRCN_ERR_CUDA, "%s", f.msg.c_str());
     }

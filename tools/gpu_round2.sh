@@ -13,7 +13,14 @@ if [ -n "$EXTRA_BENCH" ]; then
   for wl in flickr8k_train_b64 coco_2f_train_b256; do
     timeout 600 python bench.py --workload $wl --steps 50 --warmup 5 --no-beam > gpurun_out/r02_bench_$wl.log 2>&1; grep '^{' gpurun_out/r02_bench_$wl.log | tail -1 | cut -c1-300
   done
+fi
+if [ -n "$BEAM_SWEEP" ]; then
   echo "== beam sweep (C5)"; timeout 600 python tools/beam_sweep.py > gpurun_out/r02_beam_sweep.md 2>gpurun_out/r02_beam_sweep.err; cat gpurun_out/r02_beam_sweep.md
+fi
+if [ -n "$SANITIZER" ]; then
+  echo "== compute-sanitizer memcheck (subset: epoch staging, per-step LSTM kernels, beam search incl. compaction, top-K)"
+  timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -x -q -p no:cacheprovider \
+      -k "epoch or (loss_and_gradients and 0-case0) or beam_search_matches or many_rows" > gpurun_out/r02_sanitizer_memcheck2.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/r02_sanitizer_memcheck2.log
 fi
 if [ -z "$SKIP_NCU" ]; then
   echo "== ncu launch list"
