@@ -157,3 +157,9 @@ def test_caption_text_format_matches_shipped_outputs():
     assert host.caption_text([2, 1], idx2w) == "."
     assert host.caption_text([2, 4, 3], idx2w) == "a ## ."  # unk can be emitted; no eos -> runs to the end
     assert O.caption_text([2, 4, 5, 6, 1, 4], idx2w) == "a man riding ."
+
+
+def test_graft_entry_build_runs_on_cpu():
+    """The driver's "does it build" check: make for sm_100a, load both libraries, ABI version of header == binding == library."""
+    import __graft_entry__
+    __graft_entry__.build()
