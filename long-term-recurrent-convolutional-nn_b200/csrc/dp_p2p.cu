@@ -256,77 +256,10 @@ void dp_adam_staged(cudaStream_t s, float* w, float* g, float* m, float* v, cons
 }
 // SM-driven exchange of ONE arena range [b, e) owned by this rank (reduce-scatter + Adam + all-gather in one kernel, no
 // barriers: the caller brackets it with dp_xgpu_barrier).  grid_ctas bounds the SMs it may take.
-// The same exchange with U independent float4 elements per thread and iteration and a compile-time rank count: all N*U peer
-// loads and the 3*U local loads are issued before the first use.  The kernel is bound by NVLink LATENCY (a peer load returns
-// after ~3 us; dp_timeline: 7.9 MB per peer direction took 91 us with one 16-byte peer load in flight per thread), so bytes in
-// flight per thread are what counts -- above all for the buckets that travel under the LSTM kernels on a few SMs.
-// Same per-element operation order as adam_p2p_kernel (sum over ranks 0..N-1, then the Knet Adam form).
-template <int N, int U>
-__global__ void __launch_bounds__(256) adam_p2p_kernel_t(P2PPeers peers, size_t begin4, size_t end4, float4* __restrict__ m, float4* __restrict__ v,
-                                                         const StepScalars* __restrict__ sc, double* loss_total) {
-  const float b1 = sc->beta1, b2 = sc->beta2, lr = sc->lr, eps = sc->eps, d1 = sc->adam_d1, d2 = sc->adam_d2;
-  const float ob1 = sc->one_m_beta1, ob2 = sc->one_m_beta2;
-  const float4* wl = reinterpret_cast<const float4*>(peers.w[peers.rank]);
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i0 = begin4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < end4; i0 += stride * U) {
-    float4 x[U][N], W[U], Mv[U], Vv[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      const size_t i = i0 + (size_t)u * stride;
-      if (i < end4) {
-#pragma unroll
-        for (int p = 0; p < N; p++) x[u][p] = ld_peer_f4(reinterpret_cast<const float4*>(peers.g[p]) + i);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      const size_t i = i0 + (size_t)u * stride;
-      if (i < end4) { W[u] = wl[i]; Mv[u] = m[i]; Vv[u] = v[i]; }
-    }
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      const size_t i = i0 + (size_t)u * stride;
-      if (i >= end4) continue;
-      float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int p = 0; p < N; p++) { G.x += x[u][p].x; G.y += x[u][p].y; G.z += x[u][p].z; G.w += x[u][p].w; }
-      float* wp = reinterpret_cast<float*>(&W[u]);
-      const float* gp = reinterpret_cast<const float*>(&G);
-      float* mp = reinterpret_cast<float*>(&Mv[u]);
-      float* vp = reinterpret_cast<float*>(&Vv[u]);
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const float mm = __fadd_rn(__fmul_rn(b1, mp[k]), __fmul_rn(ob1, gp[k]));
-        const float vv = __fadd_rn(__fmul_rn(b2, vp[k]), __fmul_rn(ob2, __fmul_rn(gp[k], gp[k])));
-        const float upd = __fdiv_rn(__fdiv_rn(mm, d1), __fadd_rn(__fsqrt_rn(__fdiv_rn(vv, d2)), eps));
-        wp[k] = __fsub_rn(wp[k], __fmul_rn(lr, upd));
-        mp[k] = mm; vp[k] = vv;
-      }
-#pragma unroll
-      for (int p = 0; p < N; p++) reinterpret_cast<float4*>(peers.w[p])[i] = W[u];   // all-gather: the new weights into every rank's arena
-      m[i] = Mv[u]; v[i] = Vv[u];
-      reinterpret_cast<float4*>(peers.g[peers.rank])[i] = G;  // the summed gradient of the owned shard stays readable (lrcn_get_grad)
-    }
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && loss_total) {
-    double t = 0.0;
-    for (int p = 0; p < N; p++) {
-      double x;
-      asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(x) : "l"(&peers.ctl[p]->loss_partial) : "memory");
-      t += x;
-    }
-    *loss_total = t;
-  }
-  __threadfence_system();
-}
-
+// (An unrolled variant with U float4 per thread and all N*U peer loads issued up front was measured SLOWER -- 111 vs 91 us on a
+// 7.9 MB slice: the loads in flight per SM are bounded by the register file either way, and the larger CTAs only add waves.)
 void dp_p2p_adam_range(cudaStream_t s, const P2PPeers& peers, size_t b, size_t e, float* m, float* v, const StepScalars* sc, double* loss_total, int grid_ctas) {
-  float4 *m4 = reinterpret_cast<float4*>(m), *v4 = reinterpret_cast<float4*>(v);
-  static const bool old = getenv("LRCN_DP_OLD_EXCHANGE") != nullptr;
-  if (!old && peers.nranks == 2) adam_p2p_kernel_t<2, 4><<<grid_ctas, 256, 0, s>>>(peers, b / 4, e / 4, m4, v4, sc, loss_total);
-  else if (!old && peers.nranks == 4) adam_p2p_kernel_t<4, 2><<<grid_ctas, 256, 0, s>>>(peers, b / 4, e / 4, m4, v4, sc, loss_total);
-  else if (!old && peers.nranks == 8) adam_p2p_kernel_t<8, 1><<<grid_ctas, 256, 0, s>>>(peers, b / 4, e / 4, m4, v4, sc, loss_total);
-  else adam_p2p_kernel<<<grid_ctas, 256, 0, s>>>(peers, b / 4, e / 4, m4, v4, sc, loss_total);
+  adam_p2p_kernel<<<grid_ctas, 256, 0, s>>>(peers, b / 4, e / 4, reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), sc, loss_total);
   if (g_counter) g_counter->n++;
 }
 // ---------------------------------------------------------------------------------------------------------------------
@@ -472,6 +405,127 @@ void dp_fused_exchange(cudaStream_t s, const P2PPeers& peers, const FusedXArgs& 
   a.sub = (int)((longest + (size_t)XSUB * XMAXCH - 1) / ((size_t)XSUB * XMAXCH));  // at most XMAXCH chunks per slice
   if (a.sub < 1) a.sub = 1;
   fused_exchange_kernel<<<grid_ctas, 256, 0, s>>>(peers, a, reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), sc, loss_total);
+  if (g_counter) g_counter->n++;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// LL exchange of the exposed bucket.  What is left of the fused exchange when nothing hides it is latency: a system-scope fence
+// after the gradient pushes (~10 us: it waits for the NVLink write acknowledgements), the flag hop, a system-scope release
+// after the weight pushes (~10 us) and the counter hop.  Here every 16-byte line {f0, epoch, f1, epoch} is its own flag (the
+// protocol NCCL calls LL: 8-byte halves of a vector store are written atomically), so
+//   A  every rank stores its gradient slices as LL lines into the owners' LL areas              (posted stores, no fence)
+//   B  the owner polls the N-1 lines of each of its elements, sums in rank order, runs Adam, writes its own arena and stores
+//      the new weights as LL lines into every peer's LL weight area                             (no fence)
+//   C  every rank polls the LL weight lines of the other owners' slices and writes them into its own weight arena.
+// Twice the bytes on the wire for this one bucket (8.4 of 53 MB).  MEASURED SLOWER than the fused kernel (N = 2: 70 vs 50 us for the
+// bucket, 0.932 vs 0.915 ms per step -- every thread polls its own lines and the pollers compete with the incoming stores), so
+// it is opt-in (LRCN_DP_LL=1) and kept as the record of the experiment.  All CTAs are resident
+// (grid <= SMs) and run A before B before C; B polls only what peers' A phases push, C only what their B phases push.
+__device__ __forceinline__ void st_ll(uint4* p, float a, float b, unsigned int ep) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(__float_as_uint(a)), "r"(ep), "r"(__float_as_uint(b)), "r"(ep) : "memory");
+}
+__device__ __forceinline__ bool ld_ll(const uint4* p, unsigned int ep, float& a, float& b, unsigned int& spins) {
+  while (true) {
+    uint4 x;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "l"(p) : "memory");
+    if (x.y == ep && x.w == ep) { a = __uint_as_float(x.x); b = __uint_as_float(x.z); return true; }
+    if ((++spins & 1023u) == 0u) {
+      if (dev_aborted()) return false;
+      if (spins > (1u << 27)) {  // ~ tens of seconds of polling
+        printf("lrcn dp_p2p: LL exchange timeout (rank %d, epoch %u, have %u/%u)\n", 0, ep, x.y, x.w);
+        dev_abort_set();
+        return false;
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(256) ll_exchange_kernel(const P2PPeers peers, const LLXArgs a, float4* __restrict__ m, float4* __restrict__ v,
+                                                          const StepScalars* __restrict__ sc, double* loss_total) {
+  const int N = peers.nranks, me = peers.rank;
+  const unsigned int ep = sc->xchg_epoch;
+  const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const float4* gl = reinterpret_cast<const float4*>(peers.g[me]);
+  unsigned int spins = 0;
+  // ---- A: my gradient slices, as LL lines, into the owners' areas (region `me`)
+  for (int d = 1; d < N; d++) {
+    const int r = (me + d) % N;
+    const size_t n4 = a.e4[r] - a.b4[r];
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<float4*>(a.stage[r]) + a.llg4) + (size_t)me * 2 * a.per4;
+    for (size_t i = t0; i < n4; i += stride) {
+      const float4 x = gl[a.b4[r] + i];
+      st_ll(dst + 2 * i, x.x, x.y, ep);
+      st_ll(dst + 2 * i + 1, x.z, x.w, ep);
+    }
+  }
+  // ---- B: my slice
+  {
+    const float b1 = sc->beta1, b2 = sc->beta2, lr = sc->lr, eps = sc->eps, d1 = sc->adam_d1, d2 = sc->adam_d2;
+    const float ob1 = sc->one_m_beta1, ob2 = sc->one_m_beta2;
+    const size_t b4 = a.b4[me], n4 = a.e4[me] - a.b4[me];
+    const uint4* mine = reinterpret_cast<const uint4*>(reinterpret_cast<const float4*>(a.stage[me]) + a.llg4);
+    float4* wl = reinterpret_cast<float4*>(peers.w[me]);
+    float4* gw = reinterpret_cast<float4*>(peers.g[me]);
+    for (size_t i = t0; i < n4; i += stride) {
+      float4 W = wl[b4 + i], Mv = m[b4 + i], Vv = v[b4 + i];
+      const float4 own = gl[b4 + i];
+      float4 Gs = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = 0; q < N; q++) {  // fixed rank order: deterministic, identical on every rank
+        float4 x = own;
+        if (q != me) {
+          const uint4* src = mine + (size_t)q * 2 * a.per4 + 2 * i;
+          if (!ld_ll(src, ep, x.x, x.y, spins) || !ld_ll(src + 1, ep, x.z, x.w, spins)) return;
+        }
+        Gs.x += x.x; Gs.y += x.y; Gs.z += x.z; Gs.w += x.w;
+      }
+      float* wp = reinterpret_cast<float*>(&W);
+      const float* gp = reinterpret_cast<const float*>(&Gs);
+      float* mp = reinterpret_cast<float*>(&Mv);
+      float* vp = reinterpret_cast<float*>(&Vv);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const float mm = __fadd_rn(__fmul_rn(b1, mp[k]), __fmul_rn(ob1, gp[k]));
+        const float vv = __fadd_rn(__fmul_rn(b2, vp[k]), __fmul_rn(ob2, __fmul_rn(gp[k], gp[k])));
+        const float upd = __fdiv_rn(__fdiv_rn(mm, d1), __fadd_rn(__fsqrt_rn(__fdiv_rn(vv, d2)), eps));
+        wp[k] = __fsub_rn(wp[k], __fmul_rn(lr, upd));
+        mp[k] = mm; vp[k] = vv;
+      }
+      for (int d = 1; d < N; d++) {  // the new weights, as LL lines, into every peer's area (region `me`)
+        const int p = (me + d) % N;
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<float4*>(a.stage[p]) + a.llw4) + (size_t)me * 2 * a.per4;
+        st_ll(dst + 2 * i, W.x, W.y, ep);
+        st_ll(dst + 2 * i + 1, W.z, W.w, ep);
+      }
+      wl[b4 + i] = W; m[b4 + i] = Mv; v[b4 + i] = Vv;
+      gw[b4 + i] = Gs;  // the summed gradient of the owned slice stays readable (lrcn_get_grad gathers the slices)
+    }
+  }
+  // ---- C: the other owners' new weights
+  {
+    const uint4* mine = reinterpret_cast<const uint4*>(reinterpret_cast<const float4*>(a.stage[me]) + a.llw4);
+    float4* wl = reinterpret_cast<float4*>(peers.w[me]);
+    for (int d = 1; d < N; d++) {
+      const int q = (me + d) % N;
+      const size_t n4 = a.e4[q] - a.b4[q];
+      const uint4* src = mine + (size_t)q * 2 * a.per4;
+      for (size_t i = t0; i < n4; i += stride) {
+        float4 W;
+        if (!ld_ll(src + 2 * i, ep, W.x, W.y, spins) || !ld_ll(src + 2 * i + 1, ep, W.z, W.w, spins)) return;
+        wl[a.b4[q] + i] = W;
+      }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && loss_total) {
+    double t = 0.0;
+    for (int p = 0; p < N; p++) {
+      double x;
+      asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(x) : "l"(&peers.ctl[p]->loss_partial) : "memory");
+      t += x;
+    }
+    *loss_total = t;
+  }
+}
+void dp_ll_exchange(cudaStream_t s, const P2PPeers& peers, const LLXArgs& a, float* m, float* v, const StepScalars* sc, double* loss_total, int grid_ctas) {
+  ll_exchange_kernel<<<grid_ctas, 256, 0, s>>>(peers, a, reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), sc, loss_total);
   if (g_counter) g_counter->n++;
 }
 

@@ -225,6 +225,15 @@ struct FusedXArgs {
   int bucket, sub;
 };
 void dp_fused_exchange(cudaStream_t s, const P2PPeers& peers, const FusedXArgs& a, float* m, float* v, const StepScalars* sc, double* loss_total, int grid_ctas);
+// Flag-in-data ("LL") exchange of the EXPOSED bucket (dp_p2p.cu): every 16-byte line carries two floats and two copies of the
+// step's epoch, so a receiver knows a line has arrived from the line itself -- no system-scope fence, no flag round trip.
+struct LLXArgs {
+  float* stage[LRCN_P2P_MAX_RANKS];             // every rank's staging allocation
+  size_t b4[LRCN_P2P_MAX_RANKS], e4[LRCN_P2P_MAX_RANKS];  // rank r's slice of the bucket, arena index in float4 units
+  size_t per4;                                   // slice capacity (float4): a source's region of the LL areas holds 2 lines per float4
+  size_t llg4, llw4;                             // start of the LL gradient / LL weight areas inside a staging allocation (float4 units)
+};
+void dp_ll_exchange(cudaStream_t s, const P2PPeers& peers, const LLXArgs& a, float* m, float* v, const StepScalars* sc, double* loss_total, int grid_ctas);
 void dp_p2p_adam_range(cudaStream_t s, const P2PPeers& peers, size_t b, size_t e, float* m, float* v, const StepScalars* sc, double* loss_total, int grid_ctas);
 void dp_adam_staged(cudaStream_t s, float* w, float* g, float* m, float* v, const float* stage, size_t stride, size_t stage_off, size_t b, size_t e, const P2PPeers& peers,
                     const StepScalars* sc, double* loss_total, bool push_w = false, int grid_ctas = 0);

@@ -298,8 +298,11 @@ static int create_impl(const lrcn_config* cfg, lrcn_handle* h) {
   h->d_loss = &h->p2p_ctl->loss_partial;
   CK(cudaMalloc(&h->d_loss_total, 8)); CK(cudaMalloc(&h->d_epoch, 4)); CK(cudaMemset(h->d_epoch, 0, 4));
   CK(cudaMalloc(&h->d_epoch_side, 4)); CK(cudaMemset(h->d_epoch_side, 0, 4));
-  CK(cudaMalloc(&h->stage, (h->P + 1024 + DP_XCTL_FLOATS) * 4));  // + the control words of the fused exchange (dp_p2p.cu)
-  CK(cudaMemset(h->stage, 0, (h->P + 1024 + DP_XCTL_FLOATS) * 4));  // N staging rows of ~P/N floats each for the copy-engine gradient exchange
+  // + the control words of the fused exchange + the two LL areas of the exposed bucket [W1, b1] (dp_p2p.cu): 2 lines of 16 bytes
+  // per float4 and source rank, slices padded by up to 4 floats per rank
+  h->ll_floats = 2 * (h->bucket_off[3] - h->bucket_off[2] + 4 * LRCN_P2P_MAX_RANKS + 64);
+  CK(cudaMalloc(&h->stage, (h->P + 1024 + DP_XCTL_FLOATS + 2 * h->ll_floats) * 4));
+  CK(cudaMemset(h->stage, 0, (h->P + 1024 + DP_XCTL_FLOATS + 2 * h->ll_floats) * 4));  // N staging rows of ~P/N floats each for the copy-engine gradient exchange
   CK(cudaMallocHost(&h->h_loss, 8));
   CK(cudaMalloc(&h->d_counters, 320 * sizeof(unsigned int)));  // [0,256): 4 LSTM launches x 64 (half-)tile barriers; [256,..): softmax
   CK(cudaMemset(h->d_counters, 0, 320 * sizeof(unsigned int)));
@@ -918,10 +921,31 @@ static int run_step(lrcn_handle* h, int split, int B, int l, float pdrop, uint64
         // bucket k: 8+4k .. = enter, first barrier passed, exchange kernel done, second barrier + split done
         auto stamp = [&](int id, cudaStream_t st) { if (stamps && h->d_trace) dp_stamp(st, h->d_trace + id); };
         static const bool pull = getenv("LRCN_DP_PULL") != nullptr;  // round-2a exchange: the owner LOADS its shard from every peer
+        // measured at N = 2: 0.932 ms per step with the LL kernel on the exposed bucket vs 0.915 with the fused kernel (70 vs 50 us for
+        // the bucket: 38 k threads polling their lines compete with the incoming stores), so it is opt-in
+        static const bool ll = getenv("LRCN_DP_LL") != nullptr;
         static const bool fused = !pull && getenv("LRCN_DP_PUSH") == nullptr;  // default; LRCN_DP_PUSH=1: push / barrier / Adam / barrier as four kernels
         const size_t stride = stage_stride(h);
         auto exchange_bucket = [&](int k, cudaStream_t st, unsigned int* epoch, int flagset, bool last) {
           const int ctas = last ? 148 * 4 : (k == 3 ? wemb_ctas : 20 * 8);
+          if (fused && last && ll) {
+            // the exposed bucket: flag-in-data lines, no fences, no flag hops (dp_p2p.cu)
+            stamp(8 + 4 * k, st);
+            LLXArgs a{};
+            for (int r = 0; r < h->nranks; r++) {
+              const BucketShard bs = bucket_shard(h, k, r);
+              a.stage[r] = h->peer_stage[r]; a.b4[r] = bs.b / 4; a.e4[r] = bs.e / 4; a.per4 = bs.per / 4;
+            }
+            a.llg4 = (h->P + 1024 + DP_XCTL_FLOATS) / 4; a.llw4 = a.llg4 + h->ll_floats / 4;
+            dp_ll_exchange(st, h->peers, a, h->m, h->v, h->d_sc, h->d_loss_total, 148);
+            stamp(10 + 4 * k, st);
+            if (h->bf16mode) {
+              const size_t b0 = h->bucket_off[k], nn = h->bucket_off[k + 1] - b0;
+              split_bf16(st, h->w + b0, nn, h->w_hi + b0, h->w_lo + b0);
+            }
+            stamp(11 + 4 * k, st);
+            return;
+          }
           if (fused) {
             // ONE kernel per bucket: chunk-pipelined push -> flags -> owner sum + Adam -> weight push -> completion counters
             stamp(8 + 4 * k, st);
@@ -1539,7 +1563,7 @@ static int s_p2p_import(lrcn_handle* h, const char* blobs, int rank, int nranks)
   h->peers = pe;
   h->rank = rank; h->nranks = nranks;
   h->dp_epoch = 0;  // the fused exchange's flags / counters count the group's data-parallel steps: start them together
-  CK(cudaMemset(h->stage + h->P + 1024, 0, DP_XCTL_FLOATS * 4));
+  CK(cudaMemset(h->stage + h->P + 1024, 0, (DP_XCTL_FLOATS + 2 * h->ll_floats) * 4));
   h->p2p_ready = true;
   return LRCN_OK;
 }

@@ -99,6 +99,7 @@ struct lrcn_handle {
   // copy-engine exchange (dp_p2p.cu): staging rows for the gradient slices the peers push to this rank, and the peers' rows
   float* stage = nullptr;
   float* peer_stage[LRCN_P2P_MAX_RANKS] = {};
+  size_t ll_floats = 0;               // floats of each of the two LL areas (gradient lines, weight lines) behind the control words of `stage`
   unsigned int dp_epoch = 0;          // data-parallel train steps run since the peer group was formed (the fused exchange's flag value)
   bool shard_by_bucket = false;       // how the last sharded step split the arena: per gradient bucket (copy engines) or as a whole
   unsigned int* d_epoch_side = nullptr;  // epoch counter of the side-stream barriers
