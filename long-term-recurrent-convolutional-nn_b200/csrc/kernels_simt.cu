@@ -1410,11 +1410,126 @@ __global__ void __launch_bounds__(256, 3) beam_row_topk3_kernel(const float* __r
     }
   }
 }
+// Fourth generation: ONE WARP PER ROW, one streaming pass, no shared memory and no block barrier.  topk2 / topk3 process a row per
+// CTA in phases separated by four block barriers with a serial last phase in warp 0: ~8 us of latency per row and 3 rows in
+// flight per SM = 0.33 of the HBM peak (ncu launch list: 56 us for 3072 x 10000 logits).  Here every lane streams its float4
+// columns (16 loads in flight per lane, 32 independent rows per SM), keeps an online (max, sum exp) pair and its own top-KM list
+// in registers (sorted, strict '>' insertion in increasing column order: equal values keep the lower index first), and the warp
+// then pops the K global winners from the 32 list heads by (value desc, index asc).  A member of the global top-K is always in its
+// lane's top-K, so the selection is the exact top-K by (logit, index); probabilities are formed for the K winners only and winners
+// whose probabilities round to the same float are re-ordered by index, which is the order the reference's stable sort of the
+// probabilities gives (lrcn.jl:652-661).  Needs V % 4 == 0 and 16-byte aligned rows.
+template <bool FROM_LOGITS, int KM, int U>
+__global__ void __launch_bounds__(256) beam_row_topk4_kernel(const float* __restrict__ in, int ld, int R, int V, int K,
+                                                             const float* __restrict__ parent_prob, int* __restrict__ cand_tok,
+                                                             float* __restrict__ cand_score, float* __restrict__ cand_lp) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int V4 = V >> 2;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < R; r += gridDim.x * wpb) {
+    const float4* a4 = reinterpret_cast<const float4*>(in + (size_t)r * ld);
+    float tv[KM]; int ti[KM];
+#pragma unroll
+    for (int k = 0; k < KM; k++) { tv[k] = -INFINITY; ti[k] = 0x7fffffff; }
+    float m = -INFINITY, ssum = 0.f;
+    auto consider = [&](float val, int idx) {
+      if (val > tv[KM - 1]) {  // rare after the first few columns
+        tv[KM - 1] = val; ti[KM - 1] = idx;
+#pragma unroll
+        for (int k = KM - 1; k > 0; k--) {
+          if (tv[k] > tv[k - 1]) {  // strict: an equal earlier (lower-index) value stays in front
+            const float fv = tv[k]; tv[k] = tv[k - 1]; tv[k - 1] = fv;
+            const int iv = ti[k]; ti[k] = ti[k - 1]; ti[k - 1] = iv;
+          }
+        }
+      }
+    };
+    for (int q0 = lane; q0 < V4; q0 += 32 * U) {
+      float4 x[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int q = q0 + 32 * u;
+        x[u] = q < V4 ? __ldg(a4 + q) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int q = q0 + 32 * u;
+        if (q >= V4) break;
+        if (FROM_LOGITS) {
+          const float cm = fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w));
+          if (cm > m) { ssum = (m == -INFINITY) ? 0.f : ssum * __expf(m - cm); m = cm; }
+          if (m != -INFINITY) ssum += (__expf(x[u].x - m) + __expf(x[u].y - m)) + (__expf(x[u].z - m) + __expf(x[u].w - m));
+        }
+        consider(x[u].x, 4 * q); consider(x[u].y, 4 * q + 1); consider(x[u].z, 4 * q + 2); consider(x[u].w, 4 * q + 3);
+      }
+    }
+    float mx = 0.f, lse = 0.f;
+    if (FROM_LOGITS) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, ssum, o);
+        const float mn = fmaxf(m, m2);
+        ssum = (m == -INFINITY ? 0.f : ssum * __expf(m - mn)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mn));
+        m = mn;
+      }
+      mx = m; lse = logf(ssum);
+    }
+    // K rounds: the best list head of the warp by (value desc, index asc); the winning lane pops its list
+    float wv = -INFINITY; int wi = 0x7fffffff;  // lane k keeps winner k
+    for (int k = 0; k < K; k++) {
+      TopPair best; best.v = tv[0]; best.i = ti[0];
+      best = warp_top(best);
+      if (ti[0] == best.i) {  // indices are unique: exactly one lane owns the winner
+#pragma unroll
+        for (int j = 0; j < KM - 1; j++) { tv[j] = tv[j + 1]; ti[j] = ti[j + 1]; }
+        tv[KM - 1] = -INFINITY; ti[KM - 1] = 0x7fffffff;
+      }
+      if (lane == k) { wv = best.v; wi = best.i; }
+    }
+    const float lp = FROM_LOGITS ? ((wv - mx) - lse) : 0.f;
+    const float pr = FROM_LOGITS ? expf(lp) : wv;
+    // winners are ordered by (logit desc, index asc); probabilities are monotone in the logit, so only winners whose probabilities
+    // round to the same float can be out of (probability desc, index asc) order: rank them explicitly
+    int rank = 0;
+    for (int j = 0; j < K; j++) {
+      const float pj = __shfl_sync(0xffffffffu, pr, j);
+      const int ij = __shfl_sync(0xffffffffu, wi, j);
+      if (lane < K && j != lane && (pj > pr || (pj == pr && ij < wi))) rank++;
+    }
+    if (lane < K) {
+      const float pp = parent_prob[r];
+      cand_tok[(size_t)r * K + rank] = wi;
+      cand_score[(size_t)r * K + rank] = __fmul_rn(pr, pp);  // pmaxes = ynorm[xmaxes]*current_probability (lrcn.jl:657)
+      cand_lp[(size_t)r * K + rank] = FROM_LOGITS ? lp : logf(pr);
+    }
+  }
+}
+template <bool FROM_LOGITS>
+static void beam_topk4_launch(cudaStream_t s, const float* in, int ld, int R, int V, int K, const float* parent_prob, int* cand_tok, float* cand_score,
+                              float* cand_lp) {
+  const int want = (R + 7) / 8;
+  const int cap = 148 * 4;  // 48-64 registers per thread: four 256-thread CTAs per SM
+  const int grid = want < cap ? want : cap;
+  if (K <= 1) beam_row_topk4_kernel<FROM_LOGITS, 1, 8><<<grid, 256, 0, s>>>(in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+  else if (K <= 3) beam_row_topk4_kernel<FROM_LOGITS, 3, 8><<<grid, 256, 0, s>>>(in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+  else if (K <= 5) beam_row_topk4_kernel<FROM_LOGITS, 5, 8><<<grid, 256, 0, s>>>(in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+  else beam_row_topk4_kernel<FROM_LOGITS, TOPK_MAXK, 4><<<grid, 256, 0, s>>>(in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+  count_launch();
+}
 static void beam_topk_launch(cudaStream_t s, bool from_logits, const float* in, int ld, int R, int V, int K,
                              const float* parent_prob, int* cand_tok, float* cand_score, float* cand_lp) {
   const size_t smem = ((size_t)V + 4) * sizeof(float);
   const int grid = R < 148 * 4 ? R : 148 * 4;
   static const bool v1 = getenv("LRCN_TOPK_V1") != nullptr;
+  static const bool no_v4 = getenv("LRCN_TOPK_V3") != nullptr || getenv("LRCN_TOPK_V2") != nullptr;
+  // one warp per row needs many rows to fill the machine (a lone warp streams a 40 KB row in ~20 us); below that the CTA-per-row
+  // kernels are faster (measured: COCO-shaped decode, i.e. compacted batches, 157 k captions/s with topk4 everywhere vs 163 k)
+  static const int v4_rows = getenv("LRCN_TOPK_V4_ROWS") ? atoi(getenv("LRCN_TOPK_V4_ROWS")) : 2048;
+  if (!v1 && !no_v4 && R >= v4_rows && K <= TOPK_MAXK && V % 4 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && V >= 128) {
+    if (from_logits) beam_topk4_launch<true>(s, in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+    else beam_topk4_launch<false>(s, in, ld, R, V, K, parent_prob, cand_tok, cand_score, cand_lp);
+    return;
+  }
   static const bool no_v3 = getenv("LRCN_TOPK_V2") != nullptr;
   constexpr int NV4 = 11;  // V <= 11264 (COCO: 10000 / 10636)
   if (!v1 && !no_v3 && K <= TOPK_MAXK && V % 4 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && V > 4096 && V <= 4 * 256 * NV4) {

@@ -163,14 +163,16 @@ def test_c3_coco_shaped_beam_search_v10k(K):
     assert same >= int(np.ceil(0.99 * n_img)), f"only {same}/{n_img} captions identical at V=10000, K={K}"
 
 
+@pytest.mark.parametrize("R", [48, 2304])
 @pytest.mark.parametrize("K", [1, 3, 5, 10])
-def test_production_topk_kernel_from_logits_v10k(K):
-    """beam_row_topk2_kernel -- the kernel generation runs -- from LOGITS at V = 10 000 (lrcn.jl:652-661): near-uniform rows
+def test_production_topk_kernel_from_logits_v10k(K, R):
+    """The kernels generation runs -- beam_row_topk3_kernel (a CTA per row, R = 48) and beam_row_topk4_kernel (a warp per row,
+    chosen from 2048 rows up: R = 2304) -- from LOGITS at V = 10 000 (lrcn.jl:652-661): near-uniform rows
     (threshold select with many near-ties), rows with exact ties (lower index wins, lrcn.jl:655), an all-equal row (more
     candidates than the list holds: exact fallback), peaked rows.  Tokens bit-exact wherever the top-(K+1) probabilities are
     distinct in fp32; scores = prob * parent in fp32 within 1e-6 relative."""
     rs = np.random.RandomState(K)
-    V, R = 10000, 48
+    V = 10000
     logits = (rs.standard_normal((R, V)) * 0.02).astype(np.float32)        # untrained-model-like: near uniform
     logits[8:16] = (rs.standard_normal((8, V)) * 3).astype(np.float32)      # peaked
     logits[16, 123] = logits[16, 4567] = logits[16, 9999] = 5.0              # exact three-way tie at the top
