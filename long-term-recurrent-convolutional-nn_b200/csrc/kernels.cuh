@@ -156,6 +156,12 @@ struct BeamAdvanceArgs {
   float* prob; int* last_tok; int* done; int* n_done;
   long long* out_tokens; int* out_len; float* out_prob; float* out_lp;
   const int* out_map;  // compacted image index -> image index of the caller's chunk (outputs are written there); null = identity
+  // fused = 1: the row's CTA also does the image's stable selection over the K*K candidates (beam_select_kernel's job) and the
+  // k = 0 row marks the image done (beam_mark_done_kernel's job): one launch per step instead of three
+  int fused;
+  const int* cand_tok; const float* cand_score; const float* cand_lp;
+  // fused: the row also gathers the embedding of its new token -- the next step's x operand (gather_embed_kernel's job, lrcn.jl:650)
+  const float* wemb; float* e_out; __nv_bfloat16 *e_hi, *e_lo; int E, lde;
 };
 void beam_advance(cudaStream_t s, const BeamAdvanceArgs& a);
 // Compaction of the generation batch: images whose best hypothesis has ended (lrcn.jl:670) leave the batch, the survivors'

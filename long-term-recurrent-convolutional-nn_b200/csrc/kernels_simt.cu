@@ -1603,8 +1603,38 @@ void beam_select(cudaStream_t s, const int* cand_tok, const float* cand_score, c
 __global__ void __launch_bounds__(128) beam_advance_kernel(BeamAdvanceArgs a) {
   int r = blockIdx.x;
   int img = r / a.K, k = r - img * a.K;
-  if (a.done[img]) return;
-  int parent = img * a.K + a.sel_parent[r];
+  if (a.done[img]) return;  // (fused: the k = 0 row of this launch may set the flag meanwhile -- either outcome is fine, the image is frozen from here on)
+  __shared__ int s_tok, s_par;
+  __shared__ float s_score, s_lp;
+  if (a.fused) {
+    // the image's selection, as beam_select_kernel does it: k+1 rounds of "best unused candidate", strict '>' keeps the earlier
+    // list position (beam-major, rank-minor) on ties; this row takes the (k+1)-th
+    if (threadIdx.x == 0) {
+      const int ncand = a.step == 1 ? a.K : a.K * a.K;
+      const float* sc = a.cand_score + (size_t)img * a.K * a.K;
+      unsigned long long used_lo = 0, used_hi = 0;  // K*K <= 128 candidates
+      int best = -1;
+      float bv = 0.f;
+      for (int kk = 0; kk <= k; kk++) {
+        best = -1; bv = 0.f;
+        for (int c = 0; c < ncand; c++) {
+          const bool used = c < 64 ? ((used_lo >> c) & 1ull) : ((used_hi >> (c - 64)) & 1ull);
+          if (used) continue;
+          const float v = sc[c];
+          if (best < 0 || v > bv) { best = c; bv = v; }
+        }
+        if (best < 64) used_lo |= 1ull << best; else used_hi |= 1ull << (best - 64);
+      }
+      s_tok = a.cand_tok[(size_t)img * a.K * a.K + best];
+      s_par = best / a.K;  // ceil((best+1)/K) - 1  (lrcn.jl:675)
+      s_score = bv;
+      s_lp = a.cand_lp[(size_t)img * a.K * a.K + best];
+    }
+  } else if (threadIdx.x == 0) {
+    s_tok = a.sel_tok[r]; s_par = a.sel_parent[r]; s_score = a.sel_score[r]; s_lp = a.sel_lp[r];
+  }
+  __syncthreads();
+  int parent = img * a.K + s_par;
   for (int j = threadIdx.x; j < a.H1; j += blockDim.x) {
     const float hv = a.h1_in[(size_t)parent * a.H1 + j];
     a.h1_out[(size_t)r * a.ld1 + j] = hv;
@@ -1623,11 +1653,19 @@ __global__ void __launch_bounds__(128) beam_advance_kernel(BeamAdvanceArgs a) {
     a.hist_out[(size_t)r * a.maxlen + j] = a.hist_in[(size_t)parent * a.maxlen + j];
     a.lp_out[(size_t)r * a.maxlen + j] = a.lp_in[(size_t)parent * a.maxlen + j];
   }
-  int tok = a.sel_tok[r];
+  int tok = s_tok;
+  if (a.fused && a.wemb) {  // the next step's input embedding Wemb[tok,:] (+ its bf16 split)
+    const float* src = a.wemb + (size_t)tok * a.E;
+    for (int j = threadIdx.x; j < a.E; j += blockDim.x) {
+      const float x = __ldg(src + j);
+      a.e_out[(size_t)r * a.lde + j] = x;
+      if (a.e_hi) { __nv_bfloat16 hh, ll; split_one(x, hh, ll); a.e_hi[(size_t)r * a.lde + j] = hh; a.e_lo[(size_t)r * a.lde + j] = ll; }
+    }
+  }
   if (threadIdx.x == 0) {
     a.hist_out[(size_t)r * a.maxlen + len] = tok;
-    a.lp_out[(size_t)r * a.maxlen + len] = a.sel_lp[r];
-    a.prob[r] = a.sel_score[r];
+    a.lp_out[(size_t)r * a.maxlen + len] = s_lp;
+    a.prob[r] = s_score;
     a.last_tok[r] = tok;
   }
   if (k == 0) {
@@ -1642,7 +1680,8 @@ __global__ void __launch_bounds__(128) beam_advance_kernel(BeamAdvanceArgs a) {
       }
       if (threadIdx.x == 0) {
         a.out_len[oimg] = total;
-        a.out_prob[oimg] = a.sel_score[r];
+        a.out_prob[oimg] = s_score;
+        if (a.fused) { a.done[img] = 1; atomicAdd(a.n_done, 1); }
       }
     }
   }
@@ -1711,6 +1750,7 @@ void beam_compact(cudaStream_t s, const BeamCompactArgs& a) {
 void beam_advance(cudaStream_t s, const BeamAdvanceArgs& a) {
   beam_advance_kernel<<<a.n_img * a.K, 128, 0, s>>>(a);
   count_launch();
+  if (a.fused) return;
   beam_mark_done_kernel<<<(a.n_img + 127) / 128, 128, 0, s>>>(a.sel_tok, a.n_img, a.K, a.step, a.nword, a.done, a.n_done);
   count_launch();
 }

@@ -1292,7 +1292,10 @@ static void beam_lstm_step(lrcn_handle* h, int layer, int step, int R, float* g,
 // reference's hcat(input,hidden)*weight, lrcn.jl:529) so there is no accumulate pass over the gates.
 static bool beam_wide(const lrcn_handle* h, int R) { return h->bf16mode && R > 512; }
 
-static void enqueue_beam_step(lrcn_handle* h, int n_img, int K, int step, int nword, int maxlen, bool flip, float* out_lp, bool wide, const int* out_map) {
+// need_embed: gather the step's input embeddings here (first step, after a compaction, unfused mode); otherwise the previous
+// step's advance kernel has already written them
+static void enqueue_beam_step(lrcn_handle* h, int n_img, int K, int step, int nword, int maxlen, bool flip, float* out_lp, bool wide, const int* out_map,
+                              bool need_embed) {
   const int R = n_img * K, E = h->E, H1 = h->H1, H2 = h->H2, C = h->C, V = h->V, ldV = h->ldV, ldv = h->ldv;
   const Workspace& o = h->o;
   cudaStream_t s = h->stream;
@@ -1304,7 +1307,7 @@ static void enqueue_beam_step(lrcn_handle* h, int n_img, int K, int step, int nw
   if (wide) {
     float *xh1 = WS(h, o.gxh1), *xh2 = WS(h, o.gxh2);
     ld1 = E + H1; ld2 = 2 * C + H2;
-    gather_embed(s, Wp(h, 7), h->g_last, R, E, xh1, h->d_sc, false, SH(h, xh1).hi, SH(h, xh1).lo, ld1);     // Wemb[tok:tok,:]  lrcn.jl:650
+    if (need_embed) gather_embed(s, Wp(h, 7), h->g_last, R, E, xh1, h->d_sc, false, SH(h, xh1).hi, SH(h, xh1).lo, ld1);     // Wemb[tok:tok,:]  lrcn.jl:650
     gemm(h, true, true, R, 4 * H1, E + H1, xh1, ld1, Wp(h, 1), E + H1, g1, 4 * H1, false, Wp(h, 2));        // hcat(x,h)*W .+ b  lrcn.jl:529
     if (H1 % 4 == 0) lstm_cell_gen(s, g1, c1a, c1b, h1b, R, H1, SH(h, h1b).hi, SH(h, h1b).lo);
     else lstm_cell_fwd(s, g1, c1a, c1b, h1b, R, H1, SH(h, h1b).hi, SH(h, h1b).lo);
@@ -1316,7 +1319,7 @@ static void enqueue_beam_step(lrcn_handle* h, int n_img, int K, int step, int nw
     h1a = xh1 + E;       // the gathered parent states go straight into the h columns of the next step's operands
     h2a = xh2 + 2 * C;
   } else {
-    gather_embed(s, Wp(h, 7), h->g_last, R, E, e, h->d_sc, false, SH(h, e).hi, SH(h, e).lo);                // Wemb[tok:tok,:]  lrcn.jl:650
+    if (need_embed) gather_embed(s, Wp(h, 7), h->g_last, R, E, e, h->d_sc, false, SH(h, e).hi, SH(h, e).lo);                // Wemb[tok:tok,:]  lrcn.jl:650
     gemm(h, true, true, R, 4 * H1, E, e, E, Wp(h, 1), E + H1, g1, 4 * H1, false, Wp(h, 2));
     beam_lstm_step(h, 1, step, R, g1, h1a, c1a, h1b, c1b);
     gemm(h, true, true, R, C, H1, h1b, H1, Wp(h, 5), H1, z, 2 * C, false, nullptr);
@@ -1326,8 +1329,14 @@ static void enqueue_beam_step(lrcn_handle* h, int n_img, int K, int step, int nw
   }
   gemm(h, true, true, R, V, H2, h2b, H2, Wp(h, 8), H2, logits, ldV, false, Wp(h, 9));
   beam_row_topk(s, logits, ldV, R, V, K, WS(h, o.gprob), h->g_ctok, WS(h, o.gcs), WS(h, o.gclp));             // lrcn.jl:652-661
-  beam_select(s, h->g_ctok, WS(h, o.gcs), WS(h, o.gclp), n_img, K, step == 1, h->g_stok, h->g_spar, WS(h, o.gss), WS(h, o.gslp));  // :667-668
+  static const bool unfused = getenv("LRCN_BEAM_UNFUSED") != nullptr;  // selection, advance and done-marking as three launches
+  if (unfused) beam_select(s, h->g_ctok, WS(h, o.gcs), WS(h, o.gclp), n_img, K, step == 1, h->g_stok, h->g_spar, WS(h, o.gss), WS(h, o.gslp));  // :667-668
   BeamAdvanceArgs a;
+  a.fused = unfused ? 0 : 1; a.cand_tok = h->g_ctok; a.cand_score = WS(h, o.gcs); a.cand_lp = WS(h, o.gclp);
+  {
+    float* ebuf = wide ? WS(h, o.gxh1) : e;
+    a.wemb = unfused ? nullptr : Wp(h, 7); a.e_out = ebuf; a.e_hi = SH(h, ebuf).hi; a.e_lo = SH(h, ebuf).lo; a.E = E; a.lde = wide ? E + H1 : E;
+  }
   a.n_img = n_img; a.K = K; a.H1 = H1; a.H2 = H2; a.maxlen = maxlen; a.step = step; a.nword = nword;
   a.ld1 = ld1; a.ld2 = ld2;
   a.sel_tok = h->g_stok; a.sel_parent = h->g_spar; a.sel_score = WS(h, o.gss); a.sel_lp = WS(h, o.gslp);
@@ -1415,13 +1424,16 @@ static int s_beam_search(lrcn_handle* h, int split, const int64_t* image_ids, in
       int snap_gen[lrcn_handle::NSNAP], snap_n[lrcn_handle::NSNAP], gen = 0, n_compactions = 0;
       for (int q = 0; q < lrcn_handle::NSNAP; q++) snap_gen[q] = -1;
       bool all_done = false;
+      static const bool beam_unfused = getenv("LRCN_BEAM_UNFUSED") != nullptr;
+      bool need_embed = true;
       static const bool beam_debug = getenv("LRCN_BEAM_DEBUG") != nullptr;
       double wait_us = 0.0;
       const auto tl0 = std::chrono::steady_clock::now();
       int steps_run = 0;
       for (int step = 1; step <= nword + 1 && !all_done; step++) {
         steps_run = step;
-        enqueue_beam_step(h, n_act, K, step, nword, maxlen, flip, logp_out ? WS(h, o.golp) : nullptr, wide, h->g_omap);
+        enqueue_beam_step(h, n_act, K, step, nword, maxlen, flip, logp_out ? WS(h, o.golp) : nullptr, wide, h->g_omap, need_embed);
+        need_embed = beam_unfused;
         flip = !flip;
         const int q = step % lrcn_handle::NSNAP;
         int* snap = h->h_ndone + (size_t)q * G1;
@@ -1467,6 +1479,7 @@ static int s_beam_search(lrcn_handle* h, int split, const int64_t* image_ids, in
         beam_compact(h->stream, ca);
         flip = !flip;  // the compacted histories live in the other ping-pong buffer
         n_act = n_keep;
+        need_embed = true;  // rows moved: the next step gathers its embeddings from the compacted token list
         gen++; n_compactions++;
       }
       if (beam_debug)
