@@ -1635,6 +1635,22 @@ __global__ void __launch_bounds__(128) beam_advance_kernel(BeamAdvanceArgs a) {
   }
   __syncthreads();
   int parent = img * a.K + s_par;
+  // 128-bit copies when every row is 16-byte aligned (H, pitches and E multiples of 4: always in the bf16x3 mode)
+  const bool vec = ((a.H1 | a.H2 | a.ld1 | a.ld2 | a.E | a.lde) & 3) == 0;
+  if (vec) {
+    for (int q = threadIdx.x; q < (a.H1 >> 2); q += blockDim.x) {
+      const float4 hv = reinterpret_cast<const float4*>(a.h1_in + (size_t)parent * a.H1)[q];
+      reinterpret_cast<float4*>(a.h1_out + (size_t)r * a.ld1)[q] = hv;
+      reinterpret_cast<float4*>(a.c1_out + (size_t)r * a.H1)[q] = reinterpret_cast<const float4*>(a.c1_in + (size_t)parent * a.H1)[q];
+      if (a.h1_hi) store_split4(a.h1_hi, a.h1_lo, (size_t)r * a.ld1 + 4 * q, hv);
+    }
+    for (int q = threadIdx.x; q < (a.H2 >> 2); q += blockDim.x) {
+      const float4 hv = reinterpret_cast<const float4*>(a.h2_in + (size_t)parent * a.H2)[q];
+      reinterpret_cast<float4*>(a.h2_out + (size_t)r * a.ld2)[q] = hv;
+      reinterpret_cast<float4*>(a.c2_out + (size_t)r * a.H2)[q] = reinterpret_cast<const float4*>(a.c2_in + (size_t)parent * a.H2)[q];
+      if (a.h2_hi) store_split4(a.h2_hi, a.h2_lo, (size_t)r * a.ld2 + 4 * q, hv);
+    }
+  } else {
   for (int j = threadIdx.x; j < a.H1; j += blockDim.x) {
     const float hv = a.h1_in[(size_t)parent * a.H1 + j];
     a.h1_out[(size_t)r * a.ld1 + j] = hv;
@@ -1647,6 +1663,7 @@ __global__ void __launch_bounds__(128) beam_advance_kernel(BeamAdvanceArgs a) {
     a.c2_out[(size_t)r * a.H2 + j] = a.c2_in[(size_t)parent * a.H2 + j];
     if (a.h2_hi) { __nv_bfloat16 hh, ll; split_one(hv, hh, ll); a.h2_hi[(size_t)r * a.ld2 + j] = hh; a.h2_lo[(size_t)r * a.ld2 + j] = ll; }
   }
+  }
   // history so far has a.step tokens (bos + step-1 generated); append one
   int len = a.step;
   for (int j = threadIdx.x; j < len; j += blockDim.x) {
@@ -1656,6 +1673,13 @@ __global__ void __launch_bounds__(128) beam_advance_kernel(BeamAdvanceArgs a) {
   int tok = s_tok;
   if (a.fused && a.wemb) {  // the next step's input embedding Wemb[tok,:] (+ its bf16 split)
     const float* src = a.wemb + (size_t)tok * a.E;
+    if (vec) {
+      for (int q = threadIdx.x; q < (a.E >> 2); q += blockDim.x) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(src) + q);
+        reinterpret_cast<float4*>(a.e_out + (size_t)r * a.lde)[q] = x;
+        if (a.e_hi) store_split4(a.e_hi, a.e_lo, (size_t)r * a.lde + 4 * q, x);
+      }
+    } else
     for (int j = threadIdx.x; j < a.E; j += blockDim.x) {
       const float x = __ldg(src + j);
       a.e_out[(size_t)r * a.lde + j] = x;
@@ -1700,6 +1724,17 @@ __global__ void beam_mark_done_kernel(const int* __restrict__ sel_tok, int n_img
 __global__ void __launch_bounds__(128) beam_compact_gather_kernel(BeamCompactArgs a) {
   const int rn = blockIdx.x, img = rn / a.K, k = rn - img * a.K;
   const int ro = a.keep[img] * a.K + k;
+  const bool vec = ((a.H1 | a.H2 | a.ld1 | a.ld2) & 3) == 0;  // 128-bit copies when every row is 16-byte aligned
+  if (vec) {
+    for (int q = threadIdx.x; q < (a.H1 >> 2); q += blockDim.x) {
+      reinterpret_cast<float4*>(a.h1_s + (size_t)rn * a.H1)[q] = reinterpret_cast<const float4*>(a.h1 + (size_t)ro * a.ld1)[q];
+      reinterpret_cast<float4*>(a.c1_s + (size_t)rn * a.H1)[q] = reinterpret_cast<const float4*>(a.c1 + (size_t)ro * a.H1)[q];
+    }
+    for (int q = threadIdx.x; q < (a.H2 >> 2); q += blockDim.x) {
+      reinterpret_cast<float4*>(a.h2_s + (size_t)rn * a.H2)[q] = reinterpret_cast<const float4*>(a.h2 + (size_t)ro * a.ld2)[q];
+      reinterpret_cast<float4*>(a.c2_s + (size_t)rn * a.H2)[q] = reinterpret_cast<const float4*>(a.c2 + (size_t)ro * a.H2)[q];
+    }
+  } else {
   for (int j = threadIdx.x; j < a.H1; j += blockDim.x) {
     a.h1_s[(size_t)rn * a.H1 + j] = a.h1[(size_t)ro * a.ld1 + j];
     a.c1_s[(size_t)rn * a.H1 + j] = a.c1[(size_t)ro * a.H1 + j];
@@ -1707,6 +1742,7 @@ __global__ void __launch_bounds__(128) beam_compact_gather_kernel(BeamCompactArg
   for (int j = threadIdx.x; j < a.H2; j += blockDim.x) {
     a.h2_s[(size_t)rn * a.H2 + j] = a.h2[(size_t)ro * a.ld2 + j];
     a.c2_s[(size_t)rn * a.H2 + j] = a.c2[(size_t)ro * a.H2 + j];
+  }
   }
   for (int j = threadIdx.x; j < a.hist_len; j += blockDim.x) {
     a.hist_dst[(size_t)rn * a.maxlen + j] = a.hist_src[(size_t)ro * a.maxlen + j];
@@ -1721,6 +1757,21 @@ __global__ void __launch_bounds__(128) beam_compact_gather_kernel(BeamCompactArg
 }
 __global__ void __launch_bounds__(128) beam_compact_scatter_kernel(BeamCompactArgs a) {
   const int rn = blockIdx.x, img = rn / a.K, k = rn - img * a.K;
+  const bool vec = ((a.H1 | a.H2 | a.ld1 | a.ld2) & 3) == 0;
+  if (vec) {
+    for (int q = threadIdx.x; q < (a.H1 >> 2); q += blockDim.x) {
+      const float4 hv = reinterpret_cast<const float4*>(a.h1_s + (size_t)rn * a.H1)[q];
+      reinterpret_cast<float4*>(a.h1 + (size_t)rn * a.ld1)[q] = hv;
+      reinterpret_cast<float4*>(a.c1 + (size_t)rn * a.H1)[q] = reinterpret_cast<const float4*>(a.c1_s + (size_t)rn * a.H1)[q];
+      if (a.h1_hi) store_split4(a.h1_hi, a.h1_lo, (size_t)rn * a.ld1 + 4 * q, hv);
+    }
+    for (int q = threadIdx.x; q < (a.H2 >> 2); q += blockDim.x) {
+      const float4 hv = reinterpret_cast<const float4*>(a.h2_s + (size_t)rn * a.H2)[q];
+      reinterpret_cast<float4*>(a.h2 + (size_t)rn * a.ld2)[q] = hv;
+      reinterpret_cast<float4*>(a.c2 + (size_t)rn * a.H2)[q] = reinterpret_cast<const float4*>(a.c2_s + (size_t)rn * a.H2)[q];
+      if (a.h2_hi) store_split4(a.h2_hi, a.h2_lo, (size_t)rn * a.ld2 + 4 * q, hv);
+    }
+  } else {
   for (int j = threadIdx.x; j < a.H1; j += blockDim.x) {
     const float hv = a.h1_s[(size_t)rn * a.H1 + j];
     a.h1[(size_t)rn * a.ld1 + j] = hv;
@@ -1732,6 +1783,7 @@ __global__ void __launch_bounds__(128) beam_compact_scatter_kernel(BeamCompactAr
     a.h2[(size_t)rn * a.ld2 + j] = hv;
     a.c2[(size_t)rn * a.H2 + j] = a.c2_s[(size_t)rn * a.H2 + j];
     if (a.h2_hi) { __nv_bfloat16 hh, ll; split_one(hv, hh, ll); a.h2_hi[(size_t)rn * a.ld2 + j] = hh; a.h2_lo[(size_t)rn * a.ld2 + j] = ll; }
+  }
   }
   if (threadIdx.x == 0) { a.prob[rn] = a.prob_s[rn]; a.last[rn] = a.last_s[rn]; }
   if (k == 0) {
