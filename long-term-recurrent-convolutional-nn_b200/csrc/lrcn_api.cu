@@ -1693,17 +1693,27 @@ static int s_time_kernel(lrcn_handle* h, const char* name, int reps, float* avg_
 // and -- through ApiGuard -- promotion of a CUDA / NCCL failure to the handle's sticky state.
 #include <thread>
 
+#include <nvtx3/nvToolsExt.h>
+
+// LRCN_NVTX=1: every ABI call is an NVTX range named after the entry point (header-only NVTX3: a no-op unless a tool is attached;
+// `ncu --nvtx --nvtx-include "lrcn_train_step/"` then profiles exactly one call's kernels)
+static const bool g_nvtx = getenv("LRCN_NVTX") != nullptr;
 struct ApiGuard {
   lrcn_handle* h;
-  explicit ApiGuard(lrcn_handle* h_) : h(h_) { g_last_code = 0; }
+  bool pushed = false;
+  explicit ApiGuard(lrcn_handle* h_, const char* name) : h(h_) {
+    g_last_code = 0;
+    if (g_nvtx) { nvtxRangePushA(name); pushed = true; }
+  }
   ~ApiGuard() {
+    if (pushed) nvtxRangePop();
     if (h && !h->sticky_code && (g_last_code == LRCN_ERR_CUDA || g_last_code == LRCN_ERR_NCCL)) { h->sticky_code = g_last_code; h->sticky_msg = g_err; }
   }
 };
 #define ENTER(h)                                                                                               \
   if (!(h)) return fail(LRCN_ERR_ARG, "null handle");                                                          \
   if ((h)->sticky_code) return fail((h)->sticky_code, "handle failed earlier and is unusable: %s", (h)->sticky_msg.c_str()); \
-  ApiGuard guard_(const_cast<lrcn_handle*>(h))
+  ApiGuard guard_(const_cast<lrcn_handle*>(h), __func__)
 static inline bool is_group(const lrcn_handle* h) { return !h->members.empty(); }
 #define FOR_ALL(h, call)                                       \
   do {                                                         \
