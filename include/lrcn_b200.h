@@ -40,6 +40,8 @@ extern "C" {
 #define LRCN_API
 #endif
 
+/* 2: lrcn_config gained n_gpus / device_ids (single-process multi-GPU group); sticky errors; lrcn_checkpoint_save / _load;
+ *    lrcn_train_epoch / lrcn_loss_epoch (epoch-level calls, batches staged on the device: additive, same version) */
 #define LRCN_ABI_VERSION 2
 #define LRCN_F_CNN 4096 /* lrcn.jl:28  const cnnout = 4096 */
 #define LRCN_NUM_PARAMS 9
